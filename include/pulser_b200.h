@@ -1,0 +1,186 @@
+/*
+ * pulser_b200 -- C ABI of the B200-native time-evolution hot path.
+ *
+ * The reference (pasqal-io/Pulser) is pure Python and has no FFI: its "plugin
+ * boundary" for this path is the pair
+ *     Hamiltonian(samples, noise_trajectory, basis_data, lindblad_data, rate)
+ *         pulser-simulation/pulser_simulation/hamiltonian.py:45-81
+ *     QutipEmulator._run_solver(hamiltonian, ...) -> qutip.sesolve/mesolve/mcsolve
+ *         pulser-simulation/pulser_simulation/simulation.py:689-766
+ * Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; complex numbers are interleaved (re, im) doubles;
+ *   - all pointers are HOST pointers owned by the caller unless the name says
+ *     "device"; the library owns every device buffer inside the opaque plan;
+ *   - every function returns PB200_OK (0) or a negative error code and never
+ *     throws across the boundary; pb200_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - a plan is bound to one CUDA device and one stream; a plan is not
+ *     thread-safe, distinct plans are independent;
+ *   - state index: qudit 0 is the most significant digit (big-endian), digit
+ *     value = position in `eigenbasis` order (u,d,r,g,h,x subset), exactly as
+ *     qutip.tensor builds it at hamiltonian.py:169-200.
+ */
+#ifndef PULSER_B200_H
+#define PULSER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_OK 0
+#define PB200_ERR_INVALID -1   /* bad argument */
+#define PB200_ERR_CUDA -2      /* CUDA runtime failure (no device, OOM, ...) */
+#define PB200_ERR_UNSUPPORTED -3
+#define PB200_ERR_STATE -4     /* call order */
+
+#define PB200_MAX_QUDITS 40
+#define PB200_MAX_DRIVES 3
+
+typedef struct pb200_plan pb200_plan; /* opaque */
+
+/* One addressed basis: drive operator c(t)|to><from| + h.c. and detuning
+ * -det(t)|from><from| on every qudit (hamiltonian.py:340-352, 370-375):
+ * ground-rydberg: to=g, from=r; digital: to=h, from=g; XY: to=u, from=d. */
+typedef struct pb200_drive_desc {
+    int32_t state_to;    /* digit value of the |to> eigenstate   */
+    int32_t state_from;  /* digit value of the |from> eigenstate */
+    int32_t uniform;     /* 1: one table row shared by all qudits (Global) */
+    int32_t reserved;
+} pb200_drive_desc;
+
+/* Static description: replaces the arguments of Hamiltonian.__init__
+ * (hamiltonian.py:45-81) that do not change between noise trajectories. */
+typedef struct pb200_plan_desc {
+    int32_t n_qudits;       /* N */
+    int32_t dim;            /* d = len(eigenbasis): 2, 3 or 4 */
+    int32_t n_times;        /* len(sampling_times) */
+    int32_t interp_order;   /* QobjEvo array-coefficient interpolation: 0 step,
+                               1 linear, 3 cubic not-a-knot spline (QuTiP 5
+                               default; hamiltonian.py:436) */
+    int32_t n_drives;       /* addressed bases, <= PB200_MAX_DRIVES */
+    int32_t rydberg_state;  /* digit of |r> for the U_ij n_i n_j term
+                               (hamiltonian.py:260-274); -1: no interaction */
+    int32_t n_traj;         /* trajectories evolved together (batch B >= 1) */
+    int32_t device;         /* CUDA device ordinal */
+    const double* sampling_times; /* [n_times] microseconds, increasing */
+    pb200_drive_desc drives[PB200_MAX_DRIVES];
+} pb200_plan_desc;
+
+/* Integrator options (replace the `**options` handed to QuTiP at
+ * simulation.py:800-845: max_step / nsteps / atol / rtol have no meaning for
+ * the fixed-order propagator and are accepted-and-ignored on the Python side). */
+typedef struct pb200_run_opts {
+    int32_t max_step_samples; /* K: longest Magnus step, in sampling intervals
+                                 (>=1). 0 = library default. */
+    int32_t refine_window;    /* steps are 1 interval long within this many
+                                 intervals of a non-smooth sample; <0 = default */
+    double cheb_tol;          /* Chebyshev truncation tolerance per exponential;
+                                 0 = default (1e-12) */
+    double rough_tol;         /* relative 3rd-difference threshold that marks a
+                                 sample as non-smooth; 0 = default */
+    int32_t magnus_order;     /* 2 or 4 (default 4) */
+    int32_t reserved;
+} pb200_run_opts;
+
+typedef struct pb200_run_stats {
+    int64_t n_steps;        /* Magnus steps taken */
+    int64_t n_exponentials; /* matrix exponentials applied */
+    int64_t n_applies;      /* H-applies (Chebyshev terms), per trajectory */
+    int64_t n_launches;     /* CUDA kernel launches */
+    double gpu_ms;          /* device time of the propagation (CUDA events) */
+    double max_rho;         /* largest Chebyshev half-width encountered */
+} pb200_run_stats;
+
+int pb200_version(void);
+const char* pb200_last_error(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int pb200_device_count(void);
+
+/* ---- plan life cycle ---------------------------------------------------- */
+int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* desc);
+int pb200_plan_destroy(pb200_plan* plan);
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = the
+ * plan's own stream. */
+int pb200_plan_set_stream(pb200_plan* plan, void* cuda_stream);
+
+/* Interaction matrix of trajectories [traj0, traj0+count): U[count][N][N]
+ * (rad/us; only the strict upper triangle is read) and bad-atom mask
+ * bad[count][N] (may be NULL = all good).  Replaces
+ * noise_trajectory.interaction_matrix / bad_atoms as consumed by
+ * make_vdw_term / make_interaction_term (hamiltonian.py:260-331).
+ * shared != 0: the same matrix for every trajectory (count must be 1). */
+int pb200_plan_set_interaction(pb200_plan* plan, int32_t traj0, int32_t count,
+                               const double* U, const uint8_t* bad,
+                               int32_t shared);
+
+/* Sample tables of drive `drive` for trajectories [traj0, traj0+count):
+ *   coef[count][rows][n_times][2]  = 0.5*amp*exp(-i*phase)   (re, im)
+ *   det [count][rows][n_times]     = detuning (enters H as -det |from><from|)
+ * rows = 1 if the drive is uniform else N.  Replaces build_coeffs_ops
+ * (hamiltonian.py:333-389). */
+int pb200_plan_set_drive(pb200_plan* plan, int32_t drive, int32_t traj0,
+                         int32_t count, const double* coef, const double* det);
+
+/* ---- state --------------------------------------------------------------- */
+/* Upload initial states psi[count][D] (interleaved complex); psi == NULL sets
+ * basis state `basis_index` (e.g. all-ground, simulation.py:498-505) for the
+ * given trajectories.  `broadcast` != 0: psi holds ONE state copied to all. */
+int pb200_state_set(pb200_plan* plan, int32_t traj0, int32_t count,
+                    const double* psi, int64_t basis_index, int32_t broadcast);
+/* Download current states into psi[count][D]. */
+int pb200_state_get(pb200_plan* plan, int32_t traj0, int32_t count, double* psi);
+/* |psi|^2 summed into probs[count][D] (one array per trajectory). */
+int pb200_state_probabilities(pb200_plan* plan, int32_t traj0, int32_t count,
+                              double* probs);
+/* squared norms, norms2[count] */
+int pb200_state_norm2(pb200_plan* plan, int32_t traj0, int32_t count,
+                      double* norms2);
+/* Device pointer of the current state buffer (complex128 [n_traj][D]). */
+int pb200_state_device_ptr(pb200_plan* plan, void** dptr);
+
+/* ---- hot path ------------------------------------------------------------ */
+/* Advance every trajectory from t_start to t_stop (microseconds, inside the
+ * sampling-time range).  Replaces the qutip.sesolve call at
+ * simulation.py:729-735 for one [t_k, t_k+1] stretch of `tlist`. */
+int pb200_propagate(pb200_plan* plan, double t_start, double t_stop,
+                    const pb200_run_opts* opts, pb200_run_stats* stats);
+
+/* out = H(t) * in for trajectory `traj`, host buffers of D complex numbers.
+ * Replaces QobjEvo.__call__(t) @ psi, i.e. get_hamiltonian(t)
+ * (simulation.py:625-661) applied to a vector. */
+int pb200_apply_h(pb200_plan* plan, int32_t traj, double t_us,
+                  const double* in, double* out);
+
+/* Interpolated coefficient of (drive, row) at time t: out[0..1] = coef (re,im),
+ * out[2] = det.  The QobjEvo coefficient interpolant itself. */
+int pb200_coefficients_at(pb200_plan* plan, int32_t traj, int32_t drive,
+                          int32_t row, double t_us, double* out3);
+
+/* Time the bare H-apply kernel: `reps` applies of H(t) on the resident state,
+ * device time in ms through CUDA events (roofline measurement). */
+int pb200_bench_apply(pb200_plan* plan, double t_us, int32_t reps,
+                      double* ms_out, int64_t* launches_out);
+
+/* ---- host-side math, usable without a device (exercised by the CPU tests) -- */
+/* Interpolant of complex samples y[n] (re,im) over x[n] at nq query points:
+ * out[nq][2].  The QobjEvo array-coefficient rule (order 0 / 1 / 3). */
+int pb200_host_interpolate(const double* x, const double* y, int32_t n,
+                           int32_t order, const double* tq, int32_t nq,
+                           double* out);
+/* Exact Magnus moments over [a, b] of the same interpolant:
+ * out[0..1] = B0 = int S dt, out[2..3] = B1 = (1/(b-a)) int (t - (a+b)/2) S dt */
+int pb200_host_moments(const double* x, const double* y, int32_t n,
+                       int32_t order, double a, double b, double* out4);
+/* Chebyshev coefficients a_j of exp(-i*rho*x) on [-1,1], truncated at tol:
+ * writes up to cap (re,im) pairs, returns the count through *count. */
+int pb200_host_chebyshev(double rho, double tol, double* out, int32_t cap,
+                         int32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PULSER_B200_H */

@@ -1,0 +1,72 @@
+"""ORACLE (test infrastructure, never on the product path).
+
+Matrix-free numpy restatement of ``H(t) @ psi`` for sizes where the
+Kronecker-product assembly of ``oracle/ref_hamiltonian.py`` (the literal
+restatement of ``pulser_simulation/hamiltonian.py:145-200, 246-439``) is too
+slow.  ``tests/test_oracle_cpu.py`` checks it against that literal
+restatement on small systems; it follows SURVEY.md Appendix A.3:
+
+    (H psi)[s] = diag(s) psi[s] + sum_k c_k^(+/-) psi[s with digit_k swapped]
+    diag(s) = - sum_k det_k [s_k = from] + sum_{i<j} U_ij [s_i = r][s_j = r]
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+from scipy.interpolate import make_interp_spline
+
+from pulser_b200.spec import BASIS_ROLES
+
+
+class MatFreeHamiltonian:
+    def __init__(self, spec: Any, order: int = 3) -> None:
+        self.spec = spec
+        n, d = spec.n_qudits, spec.dim
+        self.n, self.d = n, d
+        D = d**n
+        idx = np.arange(D)
+        # digits[k] = digit of qudit k (qudit 0 most significant)
+        self.digits = np.array(
+            [(idx // d ** (n - 1 - k)) % d for k in range(n)], dtype=np.int8
+        )
+        self.dint = np.zeros(D)
+        if spec.has_interaction():
+            r = spec.eigenbasis.index("r")
+            U = spec.pair_matrix()
+            nr = (self.digits == r).astype(float)
+            for i in range(n):
+                for j in range(i + 1, n):
+                    if U[i, j] != 0.0:
+                        self.dint += U[i, j] * nr[i] * nr[j]
+        t = spec.sampling_times
+        self.fns = []
+        for drv in spec.drives:
+            to, frm = BASIS_ROLES[drv.basis]
+            if order == 0:
+                raise NotImplementedError
+            cf = make_interp_spline(t, drv.coef.T, k=order)
+            df = make_interp_spline(t, drv.det.T, k=order)
+            self.fns.append(
+                (spec.eigenbasis.index(to), spec.eigenbasis.index(frm), cf, df)
+            )
+
+    def apply(self, t_us: float, psi: np.ndarray) -> np.ndarray:
+        n, d = self.n, self.d
+        psi = np.asarray(psi, dtype=complex)
+        out = self.dint * psi
+        pt = psi.reshape([d] * n)
+        ot = out.reshape([d] * n)
+        for to, frm, cf, df in self.fns:
+            c = cf(t_us)
+            dt = df(t_us)
+            for k in range(n):
+                s_to = [slice(None)] * n
+                s_fr = [slice(None)] * n
+                s_to[k] = to
+                s_fr[k] = frm
+                s_to, s_fr = tuple(s_to), tuple(s_fr)
+                # c |to><from| + conj(c) |from><to| - det |from><from|
+                ot[s_to] += c[k] * pt[s_fr]
+                ot[s_fr] += np.conj(c[k]) * pt[s_to] - dt[k] * pt[s_fr]
+        return out

@@ -1,0 +1,390 @@
+// sm_100a kernels of the matrix-free propagator.
+//
+// Hot op (one Clenshaw stage of the Chebyshev expansion of exp(-iG)):
+//     out[s] = c_psi*psi[s] + c_b2*b2[s] + c_g * (Gt v)[s]
+//     (Gt v)[s] = (w*Dint[s] - sum_k th_k [digit_k(s)==from] - gamma) v[s]
+//               + sum_k ( digit_k(s)==to ? g_k : conj(g_k) ) v[s with digit_k swapped]
+// which restates, matrix-free, the CSR products QuTiP performs for the QobjEvo
+// built at pulser-simulation/pulser_simulation/hamiltonian.py:246-439
+// (SURVEY.md Appendix A.3).  HBM/L2-bound: algorithmic traffic is
+// 16 (v) + 8 (Dint) + 16 (out) = 40 B per amplitude per apply.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb200 {
+
+struct c2 { double x, y; };
+
+__host__ __device__ inline c2 cmul(c2 a, c2 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__host__ __device__ inline c2 cadd(c2 a, c2 b) { return {a.x + b.x, a.y + b.y}; }
+
+// ---- tile geometry of one pass -------------------------------------------
+// A tile gathers the amplitudes whose index differs only in the bits
+// [0, lo_bits) and [hi_shift, hi_shift + hi_bits); it is closed under flips of
+// those bits, so their partners are served from shared memory.  Bits in
+// `extra_mask` are flipped through coalesced global loads.
+struct PassGeom {
+    int n_bits;      // N (d = 2)
+    int lo_bits;     // contiguous low bits in the tile (row = 2^lo_bits amps)
+    int hi_shift;    // first bit of the high group
+    int hi_bits;     // bits in the high group (rows = 2^hi_bits)
+    uint32_t tile_flip_mask;   // tile-local bit positions whose flips belong to this pass
+    unsigned long long extra_mask;  // global bit positions flipped via global loads
+    int first_pass;  // 1: psi, b2 and the diagonal are added in this pass
+};
+
+struct StageCoef {  // complex scalars of the Clenshaw stage
+    c2 c_psi, c_b2, c_g;
+};
+
+struct UniformDrive {  // same coefficients on every qubit and trajectory
+    c2 g;          // scaled drive  g/rho
+    double theta;  // scaled detuning moment
+    double w;      // scaled weight of Dint
+    double gamma;  // scaled centre
+    int to_bit;    // digit value of |to> (1 for ground-rydberg / digital)
+    int from_count_is_popc;  // 1: [digit==from] counted by popc(idx) (from digit = 1)
+};
+
+// per-(exponential, trajectory) table for non-uniform drives, d = 2:
+//   tab[0 .. 2N)      g (re, im) per BIT position p
+//   tab[2N .. 3N)     theta per bit position p
+//   tab[3N], tab[3N+1] w, gamma
+__host__ __device__ inline int d2_table_stride(int n) { return 3 * n + 2; }
+
+// ---- PTX helpers: mbarrier + TMA 1-D bulk copy ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// streaming (read-once) 16-byte load / store
+__device__ __forceinline__ c2 ld_stream(const c2* p) {
+    double2 r = __ldcs(reinterpret_cast<const double2*>(p));
+    return {r.x, r.y};
+}
+__device__ __forceinline__ void st_c2(c2* p, c2 v) {
+    *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+}
+
+// ---- d = 2 tiled stage kernel ---------------------------------------------
+struct StageArgs {
+    const c2* v;      // gather source      [B][D]
+    const c2* psi;    // own element        [B][D]
+    const c2* b2;     // own element        [B][D] (may alias out)
+    c2* out;          // [B][D]
+    const double* dint;        // [Bd][D]
+    long long dint_stride;     // 0 when shared by all trajectories
+    long long D;               // 2^N
+    PassGeom geo;
+    StageCoef coef;
+    UniformDrive u;            // used when UNIFORM
+    const double* table;       // [B][stride] for this exponential (non-uniform)
+    int to_bit;
+    int from_is_one;
+};
+
+template <bool UNIFORM, bool REAL_G>
+__global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+
+    const PassGeom g = a.geo;
+    const int tbits = g.lo_bits + g.hi_bits;
+    const int tsize = 1 << tbits;
+    const long long traj = blockIdx.y;
+    const long long tile_id = blockIdx.x;
+    // bits of tile_id fill positions [lo, hi_shift) and [hi_shift + hi_bits, N)
+    const int mid_bits = g.hi_shift - g.lo_bits;
+    const long long mid = tile_id & ((1LL << mid_bits) - 1);
+    const long long top = tile_id >> mid_bits;
+    const long long base = (mid << g.lo_bits) | (top << (g.hi_shift + g.hi_bits));
+    const long long voff = traj * a.D;
+    const c2* vsrc = a.v + voff;
+
+    // per-bit tables for non-uniform drives live after the tile
+    double* tab = reinterpret_cast<double*>(tile + tsize);
+    if (!UNIFORM) {
+        const int stride = d2_table_stride(g.n_bits);
+        const double* src = a.table + traj * stride;
+        for (int i = threadIdx.x; i < stride; i += blockDim.x) tab[i] = src[i];
+    }
+
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)tsize * 16u);
+    {
+        const int rows = 1 << g.hi_bits;
+        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+        for (int r = threadIdx.x; r < rows; r += blockDim.x)
+            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+
+    const long long lomask = (1LL << g.lo_bits) - 1;
+    double w, gamma, theta_u;
+    c2 gu;
+    if (UNIFORM) {
+        w = a.u.w; gamma = a.u.gamma; theta_u = a.u.theta; gu = a.u.g;
+    } else {
+        w = tab[3 * g.n_bits]; gamma = tab[3 * g.n_bits + 1]; theta_u = 0.0; gu = {0.0, 0.0};
+    }
+    const int to_bit = a.to_bit;
+
+    for (int t = threadIdx.x; t < tsize; t += blockDim.x) {
+        const long long idx = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
+        const c2 vo = tile[t];
+        double pr = 0.0, pi = 0.0, qr = 0.0, qi = 0.0;  // uniform: P, Q sums; non-uniform: pr,pi = drive result
+        // flips served from shared memory
+#pragma unroll 1
+        for (uint32_t m = g.tile_flip_mask; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const c2 pv = tile[t ^ (1 << j)];
+            const int bit = (t >> j) & 1;
+            if (UNIFORM) {
+                pr += pv.x; pi += pv.y;
+                if (!REAL_G) {
+                    const double s = (bit == to_bit) ? 1.0 : -1.0;
+                    qr = fma(s, pv.x, qr); qi = fma(s, pv.y, qi);
+                }
+            } else {
+                const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+                const double gx = tab[2 * p];
+                const double gy = (bit == to_bit) ? tab[2 * p + 1] : -tab[2 * p + 1];
+                pr = fma(gx, pv.x, pr); pr = fma(-gy, pv.y, pr);
+                pi = fma(gx, pv.y, pi); pi = fma(gy, pv.x, pi);
+            }
+        }
+        // flips served by coalesced global loads
+#pragma unroll 1
+        for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
+            const int p = __ffsll((long long)m) - 1;
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(vsrc + (idx ^ (1LL << p))));
+            const c2 pv = {raw.x, raw.y};
+            const int bit = (int)((idx >> p) & 1);
+            if (UNIFORM) {
+                pr += pv.x; pi += pv.y;
+                if (!REAL_G) {
+                    const double s = (bit == to_bit) ? 1.0 : -1.0;
+                    qr = fma(s, pv.x, qr); qi = fma(s, pv.y, qi);
+                }
+            } else {
+                const double gx = tab[2 * p];
+                const double gy = (bit == to_bit) ? tab[2 * p + 1] : -tab[2 * p + 1];
+                pr = fma(gx, pv.x, pr); pr = fma(-gy, pv.y, pr);
+                pi = fma(gx, pv.y, pi); pi = fma(gy, pv.x, pi);
+            }
+        }
+        c2 drive;
+        if (UNIFORM) {
+            // g*S_to + conj(g)*S_from = x*P + i*y*Q
+            drive.x = gu.x * pr; drive.y = gu.x * pi;
+            if (!REAL_G) { drive.x = fma(-gu.y, qi, drive.x); drive.y = fma(gu.y, qr, drive.y); }
+        } else {
+            drive = {pr, pi};
+        }
+        c2 res;
+        if (g.first_pass) {
+            double diag = -gamma;
+            if (a.dint) diag = fma(w, __ldcs(a.dint + traj * a.dint_stride + idx), diag);
+            if (UNIFORM) {
+                const int ones = __popcll((unsigned long long)idx);
+                const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
+                diag = fma(-theta_u, (double)cnt, diag);
+            } else {
+                double acc = 0.0;
+                for (int p = 0; p < g.n_bits; ++p) {
+                    const int bit = (int)((idx >> p) & 1);
+                    acc += (bit == a.from_is_one) ? tab[2 * g.n_bits + p] : 0.0;
+                }
+                diag -= acc;
+            }
+            c2 gv = {fma(diag, vo.x, drive.x), fma(diag, vo.y, drive.y)};
+            res = cmul(a.coef.c_g, gv);
+            if (a.psi) res = cadd(res, cmul(a.coef.c_psi, ld_stream(a.psi + voff + idx)));
+            if (a.b2) res = cadd(res, cmul(a.coef.c_b2, ld_stream(a.b2 + voff + idx)));
+        } else {
+            res = cadd(ld_stream(a.out + voff + idx), cmul(a.coef.c_g, drive));
+        }
+        st_c2(a.out + voff + idx, res);
+    }
+}
+
+// ---- generic-d stage kernel (any dim, several drives; global gathers) -------
+// table per (exponential, trajectory):
+//   for each drive q: g[q][k] (re,im) per QUDIT k, theta[q][k]; then w, gamma
+__host__ __device__ inline int gen_table_stride(int n, int n_drives) { return n_drives * 3 * n + 2; }
+
+struct GenArgs {
+    const c2* v; const c2* psi; const c2* b2; c2* out;
+    const double* dint; long long dint_stride; long long D;
+    int n, dim, n_drives;
+    int to[3], from[3];
+    StageCoef coef;
+    const double* table;  // [B][stride]
+};
+
+__global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    const int stride = gen_table_stride(a.n, a.n_drives);
+    const long long traj = blockIdx.y;
+    for (int i = threadIdx.x; i < stride; i += blockDim.x) tab[i] = a.table[traj * stride + i];
+    __syncthreads();
+    const double w = tab[stride - 2], gamma = tab[stride - 1];
+    const long long voff = traj * a.D;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < a.D;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const c2 vo = a.v[voff + idx];
+        double diag = -gamma;
+        if (a.dint) diag = fma(w, a.dint[traj * a.dint_stride + idx], diag);
+        double rr = 0.0, ri = 0.0;
+        long long rem = idx, st = 1;
+        for (int k = a.n - 1; k >= 0; --k) {  // qudit k has stride dim^(n-1-k)
+            const int digit = (int)(rem % a.dim);
+            rem /= a.dim;
+            for (int q = 0; q < a.n_drives; ++q) {
+                const double* gq = tab + q * 3 * a.n;
+                if (digit == a.to[q]) {
+                    const c2 pv = a.v[voff + idx + (long long)(a.from[q] - a.to[q]) * st];
+                    const double gx = gq[2 * k], gy = gq[2 * k + 1];
+                    rr = fma(gx, pv.x, rr); rr = fma(-gy, pv.y, rr);
+                    ri = fma(gx, pv.y, ri); ri = fma(gy, pv.x, ri);
+                } else if (digit == a.from[q]) {
+                    const c2 pv = a.v[voff + idx + (long long)(a.to[q] - a.from[q]) * st];
+                    const double gx = gq[2 * k], gy = -gq[2 * k + 1];
+                    rr = fma(gx, pv.x, rr); rr = fma(-gy, pv.y, rr);
+                    ri = fma(gx, pv.y, ri); ri = fma(gy, pv.x, ri);
+                    diag -= gq[2 * a.n + k];
+                }
+            }
+            st *= a.dim;
+        }
+        c2 gv = {fma(diag, vo.x, rr), fma(diag, vo.y, ri)};
+        c2 res = cmul(a.coef.c_g, gv);
+        if (a.psi) res = cadd(res, cmul(a.coef.c_psi, a.psi[voff + idx]));
+        if (a.b2) res = cadd(res, cmul(a.coef.c_b2, a.b2[voff + idx]));
+        st_c2(a.out + voff + idx, res);
+    }
+}
+
+// ---- interaction diagonal ---------------------------------------------------
+// Dint[s] = sum_{i<j} U_ij [digit_i == r][digit_j == r]
+// (make_vdw_term, hamiltonian.py:260-274, after the + dag doubling of 0.5*U)
+__global__ void dint_kernel(double* dint, const double* U, int n, int dim, int rstate, long long D) {
+    extern __shared__ double Us[];
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) Us[i] = U[i];
+    __syncthreads();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < D;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int pos[64];
+        int cnt = 0;
+        long long rem = idx;
+        for (int k = n - 1; k >= 0; --k) {
+            if ((int)(rem % dim) == rstate) pos[cnt++] = k;
+            rem /= dim;
+        }
+        double acc = 0.0;
+        // pos is descending in k; accumulate pairs in (i<j) order of the reference loop
+        for (int a = cnt - 1; a >= 0; --a)
+            for (int b = a - 1; b >= 0; --b) acc += Us[pos[a] * n + pos[b]];
+        dint[idx] = acc;
+    }
+}
+
+// min / max of Dint grouped by the number of |r> digits (spectral bounds)
+__global__ void dint_bounds_kernel(const double* dint, int n, int dim, int rstate, long long D, double* mins,
+                                   double* maxs) {
+    // one thread per amplitude, atomics on (n+1) bins via ordered-int trick
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < D;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int cnt = 0;
+        long long rem = idx;
+        for (int k = 0; k < n; ++k) { cnt += ((int)(rem % dim) == rstate); rem /= dim; }
+        const double v = dint[idx];
+        // Dint >= 0 is not guaranteed (negative C6 never occurs, but be safe): use CAS loops
+        unsigned long long* pmin = reinterpret_cast<unsigned long long*>(mins + cnt);
+        unsigned long long old = *pmin;
+        while (__longlong_as_double((long long)old) > v) {
+            unsigned long long assumed = old;
+            old = atomicCAS(pmin, assumed, (unsigned long long)__double_as_longlong(v));
+            if (old == assumed) break;
+        }
+        unsigned long long* pmax = reinterpret_cast<unsigned long long*>(maxs + cnt);
+        old = *pmax;
+        while (__longlong_as_double((long long)old) < v) {
+            unsigned long long assumed = old;
+            old = atomicCAS(pmax, assumed, (unsigned long long)__double_as_longlong(v));
+            if (old == assumed) break;
+        }
+    }
+}
+
+// ---- small utilities --------------------------------------------------------
+__global__ void set_basis_kernel(c2* psi, long long D, long long index) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x)
+        psi[i] = {i == index ? 1.0 : 0.0, 0.0};
+}
+
+__global__ void prob_kernel(const c2* psi, double* probs, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 v = psi[i];
+        probs[i] = v.x * v.x + v.y * v.y;
+    }
+}
+
+// squared norm per trajectory: grid.y = trajectory, warp-shuffle + one atomic per block
+__global__ void norm2_kernel(const c2* psi, long long D, double* out) {
+    const long long traj = blockIdx.y;
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 v = psi[traj * D + i];
+        acc = fma(v.x, v.x, acc);
+        acc = fma(v.y, v.y, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += ws[i];
+        atomicAdd(out + traj, s);
+    }
+}
+
+}  // namespace pb200

@@ -1,0 +1,970 @@
+// Host side of the C ABI (include/pulser_b200.h): plan, interpolation tables,
+// Magnus/Chebyshev schedule, kernel launches.
+//
+// Algorithm: the sampling grid is cut into Magnus steps
+// [a, b]; on each step the exact moments B0 = int H dt and
+// B1 = (1/h) int (t - t_mid) H dt of the *interpolated* coefficient functions
+// define the 4th-order commutator-free propagator
+//     psi <- exp(-i(B0/2 + 2 B1)) exp(-i(B0/2 - 2 B1)) psi ,
+// and each exponential is a Chebyshev expansion evaluated with the Clenshaw
+// recurrence, one fused H-apply kernel per term.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pulser_b200.h"
+#include "kernels.cuh"
+#include "spline.hpp"
+
+namespace pb200 {
+
+static thread_local std::string g_last_error;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] static void fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(code, buf);
+}
+
+#define CUDA_CHECK(expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            fail(PB200_ERR_CUDA, "CUDA error %s at %s:%d: %s", #expr, __FILE__, __LINE__,       \
+                 cudaGetErrorString(e__));                                                      \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+struct DriveTables {  // one (trajectory, drive): rows x interpolants
+    std::vector<PiecewiseCubic<cplx>> coef;
+    std::vector<PiecewiseCubic<double>> det;
+    std::vector<double> coef_scale, det_scale;  // max |sample| per row
+};
+
+struct Plan {
+    pb200_plan_desc desc;
+    std::vector<double> times;
+    int n = 0, dim = 0, B = 1;
+    long long D = 0;
+    int n_drives = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // device buffers
+    c2* buf[3] = {nullptr, nullptr, nullptr};
+    int cur = 0;  // index of the current state buffer
+    double* dint = nullptr;
+    bool dint_shared = true;
+    bool has_interaction = false;
+    double* d_table = nullptr;  // per-exponential coefficient tables
+    size_t d_table_cap = 0;
+    double* d_scratch = nullptr;  // bins for reductions
+    // host-side interpolants: [traj][drive]
+    std::vector<std::vector<DriveTables>> tabs;
+    std::vector<std::vector<bool>> tabs_set;
+    // Dint bounds per |r>-count (shared-Dint case) and global bounds per trajectory
+    std::vector<double> dmin_cnt, dmax_cnt;
+    std::vector<double> dmin_traj, dmax_traj;
+    bool state_set = false;
+    int tile_bits = 12;
+    int max_extra = 3;
+    int sm_count = 148;
+    bool all_uniform() const {
+        for (int q = 0; q < n_drives; ++q)
+            if (!desc.drives[q].uniform) return false;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------
+static std::vector<PassGeom> plan_passes(int N, int TB, int EX) {
+    std::vector<PassGeom> passes;
+    PassGeom g{};
+    g.n_bits = N;
+    if (N <= TB) {
+        g.lo_bits = N; g.hi_shift = N; g.hi_bits = 0;
+        g.tile_flip_mask = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+        g.extra_mask = 0; g.first_pass = 1;
+        passes.push_back(g);
+        return passes;
+    }
+    if (N - TB <= EX) {
+        g.lo_bits = TB; g.hi_shift = TB; g.hi_bits = 0;
+        g.tile_flip_mask = (1u << TB) - 1u;
+        g.extra_mask = ((1ULL << N) - 1ULL) & ~((1ULL << TB) - 1ULL);
+        g.first_pass = 1;
+        passes.push_back(g);
+        return passes;
+    }
+    // pass A: the TB low bits
+    g.lo_bits = TB; g.hi_shift = TB; g.hi_bits = 0;
+    g.tile_flip_mask = (1u << TB) - 1u; g.extra_mask = 0; g.first_pass = 1;
+    passes.push_back(g);
+    int next = TB;  // first bit not yet covered
+    const int min_row_bits = 2;  // rows of >= 64 B
+    while (next < N) {
+        int rem = N - next;
+        PassGeom p{};
+        p.n_bits = N; p.first_pass = 0;
+        int hb = std::min(rem, TB - min_row_bits);
+        // leftover bits small enough -> take them as global-load extras
+        int left = rem - hb;
+        p.hi_bits = hb; p.hi_shift = next; p.lo_bits = TB - hb;
+        p.tile_flip_mask = ((1u << hb) - 1u) << p.lo_bits;
+        p.extra_mask = 0;
+        if (left > 0 && left <= EX) {
+            p.extra_mask = ((1ULL << N) - 1ULL) & ~((1ULL << (next + hb)) - 1ULL);
+            left = 0;
+            next = N;
+        } else {
+            next += hb;
+        }
+        passes.push_back(p);
+    }
+    return passes;
+}
+
+// ---------------------------------------------------------------------------
+struct ExpParams {  // one exponential exp(-i G), G from Magnus moments
+    // [traj][drive][row] unscaled g (complex) and theta; w common
+    std::vector<cplx> g;
+    std::vector<double> th;
+    double w = 0.0;
+};
+
+static inline size_t pidx(const Plan& P, int traj, int q, int row) {
+    return ((size_t)traj * P.n_drives + q) * P.n + row;
+}
+
+static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
+                         c2* out, StageCoef coef, bool uniform, bool real_g, const UniformDrive& ud,
+                         const double* table, long long& launches) {
+    const int N = P.n;
+    if (P.dim == 2 && P.n_drives == 1) {
+        for (const PassGeom& geo : passes) {
+            StageArgs a{};
+            a.v = v; a.psi = psi; a.b2 = b2; a.out = out;
+            a.dint = P.has_interaction ? P.dint : nullptr;
+            a.dint_stride = P.dint_shared ? 0 : P.D;
+            a.D = P.D; a.geo = geo; a.coef = coef; a.u = ud; a.table = table;
+            a.to_bit = P.desc.drives[0].state_to;
+            a.from_is_one = P.desc.drives[0].state_from;
+            const int tbits = geo.lo_bits + geo.hi_bits;
+            const long long tiles = P.D >> tbits;
+            const int tsize = 1 << tbits;
+            int threads = std::min(256, std::max(32, tsize));
+            size_t smem = (size_t)tsize * 16 + (uniform ? 0 : (size_t)d2_table_stride(N) * 8);
+            dim3 grid((unsigned)tiles, (unsigned)P.B);
+            if (uniform) {
+                if (real_g) stage_d2_kernel<true, true><<<grid, threads, smem, P.stream>>>(a);
+                else stage_d2_kernel<true, false><<<grid, threads, smem, P.stream>>>(a);
+            } else {
+                stage_d2_kernel<false, false><<<grid, threads, smem, P.stream>>>(a);
+            }
+            ++launches;
+        }
+    } else {
+        GenArgs a{};
+        a.v = v; a.psi = psi; a.b2 = b2; a.out = out;
+        a.dint = P.has_interaction ? P.dint : nullptr;
+        a.dint_stride = P.dint_shared ? 0 : P.D;
+        a.D = P.D; a.n = N; a.dim = P.dim; a.n_drives = P.n_drives;
+        for (int q = 0; q < P.n_drives; ++q) { a.to[q] = P.desc.drives[q].state_to; a.from[q] = P.desc.drives[q].state_from; }
+        a.coef = coef; a.table = table;
+        int threads = 256;
+        long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
+        dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
+        size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8;
+        stage_generic_kernel<<<grid, threads, smem, P.stream>>>(a);
+        ++launches;
+    }
+}
+
+// Fill the device-table entry (host staging) of one exponential for all
+// trajectories; returns gamma0, rho (common to the batch).
+static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, double& rho, std::vector<double>& host,
+                         bool d2path) {
+    const int N = P.n, B = P.B, nd = P.n_drives;
+    double lo = 1e300, hi = -1e300;
+    for (int b = 0; b < B; ++b) {
+        // drive norm bound
+        double dr = 0.0;
+        for (int q = 0; q < nd; ++q)
+            for (int k = 0; k < N; ++k) dr += std::abs(E.g[pidx(P, b, q, k)]);
+        double dlo, dhi;
+        const bool caseA = P.has_interaction && P.dint_shared && nd == 1 && P.desc.drives[0].uniform &&
+                           P.desc.drives[0].state_from == P.desc.rydberg_state && !P.dmin_cnt.empty();
+        if (caseA) {
+            const double th = E.th[pidx(P, b, 0, 0)];
+            dlo = 1e300; dhi = -1e300;
+            for (int c = 0; c <= N; ++c) {
+                if (P.dmin_cnt[c] > P.dmax_cnt[c]) continue;  // empty bin
+                dlo = std::min(dlo, E.w * P.dmin_cnt[c] - th * c);
+                dhi = std::max(dhi, E.w * P.dmax_cnt[c] - th * c);
+            }
+        } else {
+            double dmn = 0.0, dmx = 0.0;
+            if (P.has_interaction) {
+                dmn = P.dint_shared ? P.dmin_traj[0] : P.dmin_traj[b];
+                dmx = P.dint_shared ? P.dmax_traj[0] : P.dmax_traj[b];
+            }
+            dlo = E.w * dmn; dhi = E.w * dmx;
+            for (int k = 0; k < N; ++k) {
+                double mn = 0.0, mx = 0.0;  // a digit that is nobody's `from`
+                for (int dgt = 0; dgt < P.dim; ++dgt) {
+                    double val = 0.0;
+                    for (int q = 0; q < nd; ++q)
+                        if (P.desc.drives[q].state_from == dgt) val -= E.th[pidx(P, b, q, k)];
+                    mn = std::min(mn, val); mx = std::max(mx, val);
+                }
+                // if every digit is some drive's `from`, 0 is not attainable; keeping it only widens the bound
+                dlo += mn; dhi += mx;
+            }
+        }
+        lo = std::min(lo, dlo - dr);
+        hi = std::max(hi, dhi + dr);
+    }
+    gamma0 = 0.5 * (lo + hi);
+    rho = std::max(0.5 * (hi - lo) * (1.0 + 1e-9), 1e-9);
+    const double inv = 1.0 / rho;
+    if (d2path) {
+        const int stride = d2_table_stride(N);
+        host.assign((size_t)B * stride, 0.0);
+        for (int b = 0; b < B; ++b) {
+            double* t = host.data() + (size_t)b * stride;
+            for (int k = 0; k < N; ++k) {
+                const int p = N - 1 - k;  // bit position of qubit k
+                const cplx g = E.g[pidx(P, b, 0, k)] * inv;
+                t[2 * p] = g.real(); t[2 * p + 1] = g.imag();
+                t[2 * N + p] = E.th[pidx(P, b, 0, k)] * inv;
+            }
+            t[3 * N] = E.w * inv; t[3 * N + 1] = gamma0 * inv;
+        }
+    } else {
+        const int stride = gen_table_stride(N, nd);
+        host.assign((size_t)B * stride, 0.0);
+        for (int b = 0; b < B; ++b) {
+            double* t = host.data() + (size_t)b * stride;
+            for (int q = 0; q < nd; ++q) {
+                double* tq = t + (size_t)q * 3 * N;
+                for (int k = 0; k < N; ++k) {
+                    const cplx g = E.g[pidx(P, b, q, k)] * inv;
+                    tq[2 * k] = g.real(); tq[2 * k + 1] = g.imag();
+                    tq[2 * N + k] = E.th[pidx(P, b, q, k)] * inv;
+                }
+            }
+            t[stride - 2] = E.w * inv; t[stride - 1] = gamma0 * inv;
+        }
+    }
+}
+
+struct Program {  // a batch of exponentials prepared on the host
+    std::vector<double> tables;        // concatenated per-exponential tables
+    std::vector<size_t> offset;        // start of each exponential's table
+    std::vector<double> gamma0, rho;
+    std::vector<std::vector<cplx>> cheb;
+    std::vector<UniformDrive> ud;
+    std::vector<char> real_g;
+};
+
+static void ensure_table_capacity(Plan& P, size_t doubles) {
+    if (doubles <= P.d_table_cap) return;
+    if (P.d_table) CUDA_CHECK(cudaFree(P.d_table));
+    P.d_table = nullptr;
+    size_t cap = std::max(doubles, (size_t)1 << 16);
+    CUDA_CHECK(cudaMalloc(&P.d_table, cap * sizeof(double)));
+    P.d_table_cap = cap;
+}
+
+// apply exp(-iG) for every exponential in the program, in order
+static void run_program(Plan& P, const Program& prog, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
+    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool uniform = d2path && P.all_uniform() && P.B == 1;
+    if (!uniform) {
+        ensure_table_capacity(P, prog.tables.size());
+        CUDA_CHECK(cudaMemcpyAsync(P.d_table, prog.tables.data(), prog.tables.size() * sizeof(double),
+                                   cudaMemcpyHostToDevice, P.stream));
+    }
+    long long launches = 0;
+    for (size_t e = 0; e < prog.cheb.size(); ++e) {
+        const std::vector<cplx>& a = prog.cheb[e];
+        const int m = (int)a.size() - 1;
+        const cplx ph = std::exp(cplx(0.0, -prog.gamma0[e]));
+        const double* table = uniform ? nullptr : P.d_table + prog.offset[e];
+        c2* psi = P.buf[P.cur];
+        c2* scratch[2] = {P.buf[(P.cur + 1) % 3], P.buf[(P.cur + 2) % 3]};
+        // Clenshaw state
+        const c2* b1_buf = psi; cplx b1_scale = a[m];
+        int b2_kind = 0;  // 0 zero, 1 buffer, 2 virtual kappa*psi
+        c2* b2_buf = nullptr; cplx kappa = 0.0;
+        c2* out = nullptr;
+        for (int j = m - 1; j >= 0; --j) {
+            const double factor = (j == 0) ? 1.0 : 2.0;
+            const cplx phase = (j == 0) ? ph : cplx(1.0, 0.0);
+            const cplx cg = phase * factor * b1_scale;
+            const cplx cpsi = phase * (a[j] - (b2_kind == 2 ? kappa : cplx(0.0)));
+            const cplx cb2 = (b2_kind == 1) ? -phase : cplx(0.0);
+            if (b2_kind == 1) out = b2_buf;
+            else out = (scratch[0] != b1_buf) ? scratch[0] : scratch[1];
+            StageCoef sc{{cpsi.real(), cpsi.imag()}, {cb2.real(), cb2.imag()}, {cg.real(), cg.imag()}};
+            launch_stage(P, passes, b1_buf, psi, (b2_kind == 1) ? b2_buf : nullptr, out, sc, uniform,
+                         prog.real_g[e] != 0, prog.ud[e], table, launches);
+            // shift
+            if (b1_buf == psi) { b2_kind = 2; kappa = b1_scale; b2_buf = nullptr; }
+            else { b2_kind = 1; b2_buf = const_cast<c2*>(b1_buf); }
+            b1_buf = out; b1_scale = 1.0;
+        }
+        // result is in `out`
+        for (int i = 0; i < 3; ++i)
+            if (P.buf[i] == out) P.cur = i;
+        st.n_applies += m;
+        st.max_rho = std::max(st.max_rho, prog.rho[e]);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    st.n_launches += launches;
+    st.n_exponentials += (long long)prog.cheb.size();
+}
+
+// ---------------------------------------------------------------------------
+static void moments_for_step(const Plan& P, double a, double b, std::vector<cplx>& g0, std::vector<cplx>& g1,
+                             std::vector<double>& t0, std::vector<double>& t1) {
+    const int N = P.n, B = P.B, nd = P.n_drives;
+    g0.assign((size_t)B * nd * N, cplx(0)); g1 = g0;
+    t0.assign((size_t)B * nd * N, 0.0); t1 = t0;
+    for (int tr = 0; tr < B; ++tr)
+        for (int q = 0; q < nd; ++q) {
+            const DriveTables& T = P.tabs[tr][q];
+            const int rows = (int)T.coef.size();
+            for (int r = 0; r < rows; ++r) {
+                cplx c0, c1; double d0, d1;
+                magnus_moments(T.coef[r], P.times, a, b, c0, c1);
+                magnus_moments(T.det[r], P.times, a, b, d0, d1);
+                if (rows == 1) {
+                    for (int k = 0; k < N; ++k) {
+                        g0[pidx(P, tr, q, k)] = c0; g1[pidx(P, tr, q, k)] = c1;
+                        t0[pidx(P, tr, q, k)] = d0; t1[pidx(P, tr, q, k)] = d1;
+                    }
+                } else {
+                    g0[pidx(P, tr, q, r)] = c0; g1[pidx(P, tr, q, r)] = c1;
+                    t0[pidx(P, tr, q, r)] = d0; t1[pidx(P, tr, q, r)] = d1;
+                }
+            }
+        }
+}
+
+static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, double tol) {
+    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    double gamma0, rho;
+    std::vector<double> host;
+    build_tables(P, E, gamma0, rho, host, d2path);
+    prog.offset.push_back(prog.tables.size());
+    prog.tables.insert(prog.tables.end(), host.begin(), host.end());
+    prog.gamma0.push_back(gamma0);
+    prog.rho.push_back(rho);
+    prog.cheb.push_back(chebyshev_exp_coeffs(rho, tol));
+    UniformDrive ud{};
+    const cplx g = E.g[0] / rho;
+    ud.g = {g.real(), g.imag()};
+    ud.theta = E.th[0] / rho; ud.w = E.w / rho; ud.gamma = gamma0 / rho;
+    ud.to_bit = P.desc.drives[0].state_to;
+    prog.ud.push_back(ud);
+    prog.real_g.push_back(g.imag() == 0.0 ? 1 : 0);
+}
+
+// mark sampling intervals that must be stepped one by one
+static std::vector<char> fine_intervals(const Plan& P, int window, double rough_tol) {
+    const int nt = (int)P.times.size();
+    std::vector<char> rough(nt, 0);
+    auto scan = [&](auto const& pcs, const std::vector<double>& scales, auto absf) {
+        for (size_t r = 0; r < pcs.size(); ++r) {
+            const auto& pc = pcs[r];
+            const double sc = scales[r];
+            if (sc <= 0.0) continue;
+            // third differences of the samples (c0 holds y_i; last sample is implied by the last piece)
+            const int np = pc.pieces();
+            auto y = [&](int i) { return i < np ? pc.c0[i] : pc.eval_piece(np - 1, P.times[np] - P.times[np - 1]); };
+            for (int i = 1; i + 2 < nt; ++i) {
+                auto d3 = y(i + 2) - 3.0 * y(i + 1) + 3.0 * y(i) - y(i - 1);
+                if (absf(d3) > rough_tol * sc) { rough[i] = 1; rough[i + 1] = 1; }
+            }
+        }
+    };
+    for (int tr = 0; tr < P.B; ++tr)
+        for (int q = 0; q < P.n_drives; ++q) {
+            const DriveTables& T = P.tabs[tr][q];
+            scan(T.coef, T.coef_scale, [](cplx z) { return std::abs(z); });
+            scan(T.det, T.det_scale, [](double z) { return std::fabs(z); });
+        }
+    std::vector<char> fine(std::max(nt - 1, 1), 0);
+    for (int r = 0; r < nt; ++r)
+        if (rough[r])
+            for (int i = std::max(0, r - window); i <= std::min(nt - 2, r + window - 1); ++i) fine[i] = 1;
+    return fine;
+}
+
+static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats) {
+    if (!P.state_set) fail(PB200_ERR_STATE, "pb200_propagate: no state set (call pb200_state_set first)");
+    for (int tr = 0; tr < P.B; ++tr)
+        for (int q = 0; q < P.n_drives; ++q)
+            if (!P.tabs_set[tr][q]) fail(PB200_ERR_STATE, "pb200_propagate: drive %d of trajectory %d not set", q, tr);
+    const double tlo = P.times.front(), thi = P.times.back();
+    const double eps = 1e-12;
+    if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
+        fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
+    t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
+    int K = (o && o->max_step_samples > 0) ? o->max_step_samples : env_int("PB200_MAX_STEP", 4);
+    int W = (o && o->refine_window >= 0) ? o->refine_window : env_int("PB200_REFINE_WINDOW", 8);
+    double tol = (o && o->cheb_tol > 0) ? o->cheb_tol : 1e-12;
+    double rtol = (o && o->rough_tol > 0) ? o->rough_tol : 1e-4;
+    int order = (o && o->magnus_order) ? o->magnus_order : 4;
+    if (order != 2 && order != 4) fail(PB200_ERR_INVALID, "magnus_order must be 2 or 4");
+
+    pb200_run_stats st{};
+    const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
+    const std::vector<char> fine = fine_intervals(P, W, rtol);
+    const int nt = (int)P.times.size();
+
+    cudaEvent_t ev0, ev1;
+    CUDA_CHECK(cudaEventCreate(&ev0));
+    CUDA_CHECK(cudaEventCreate(&ev1));
+    CUDA_CHECK(cudaEventRecord(ev0, P.stream));
+
+    Program prog;
+    auto flush = [&]() {
+        if (prog.cheb.empty()) return;
+        run_program(P, prog, passes, st);
+        // tables were copied asynchronously from prog.tables: wait before reuse
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        prog = Program();
+    };
+    const size_t flush_doubles = (size_t)8 << 20;  // 64 MiB of tables per chunk
+    std::vector<cplx> g0, g1; std::vector<double> th0, th1;
+    double t = t_start;
+    while (t < t_stop - eps) {
+        int i = find_piece(P.times, t + eps);
+        double b;
+        if (fine[i]) {
+            b = P.times[i + 1];
+        } else {
+            int j = i, cnt = 0;
+            while (j < nt - 1 && !fine[j] && cnt < K) { ++j; ++cnt; }
+            b = P.times[j];
+        }
+        b = std::min(b, t_stop);
+        if (b <= t + eps) b = std::min(P.times[std::min(i + 1, nt - 1)], t_stop);
+        const double h = b - t;
+        moments_for_step(P, t, b, g0, g1, th0, th1);
+        const size_t cnt = g0.size();
+        if (order == 4) {
+            ExpParams E1, E2;
+            E1.g.resize(cnt); E1.th.resize(cnt); E2.g.resize(cnt); E2.th.resize(cnt);
+            for (size_t x = 0; x < cnt; ++x) {
+                E1.g[x] = 0.5 * g0[x] - 2.0 * g1[x]; E1.th[x] = 0.5 * th0[x] - 2.0 * th1[x];
+                E2.g[x] = 0.5 * g0[x] + 2.0 * g1[x]; E2.th[x] = 0.5 * th0[x] + 2.0 * th1[x];
+            }
+            E1.w = 0.5 * h; E2.w = 0.5 * h;
+            add_exponential(P, prog, E1, tol);
+            add_exponential(P, prog, E2, tol);
+        } else {
+            ExpParams E; E.g = g0; E.th = th0; E.w = h;
+            add_exponential(P, prog, E, tol);
+        }
+        ++st.n_steps;
+        t = b;
+        if (prog.tables.size() > flush_doubles) flush();
+    }
+    flush();
+    CUDA_CHECK(cudaEventRecord(ev1, P.stream));
+    CUDA_CHECK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    st.gpu_ms = ms;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (stats) *stats = st;
+}
+
+// H(t) parameters as an "exponential" description with w = 1 (for apply_h)
+static ExpParams params_at(const Plan& P, double t) {
+    ExpParams E;
+    const int N = P.n, B = P.B, nd = P.n_drives;
+    E.g.assign((size_t)B * nd * N, cplx(0)); E.th.assign((size_t)B * nd * N, 0.0); E.w = 1.0;
+    for (int tr = 0; tr < B; ++tr)
+        for (int q = 0; q < nd; ++q) {
+            const DriveTables& T = P.tabs[tr][q];
+            const int rows = (int)T.coef.size();
+            for (int k = 0; k < N; ++k) {
+                const int r = rows == 1 ? 0 : k;
+                E.g[pidx(P, tr, q, k)] = eval_at(T.coef[r], P.times, t, P.desc.interp_order);
+                E.th[pidx(P, tr, q, k)] = eval_at(T.det[r], P.times, t, P.desc.interp_order);
+            }
+        }
+    return E;
+}
+
+// one plain H-apply: out_buf = H(t) in_buf (device buffers [B][D])
+static void apply_h_device(Plan& P, double t, const c2* in, c2* out, long long& launches) {
+    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool uniform = d2path && P.all_uniform() && P.B == 1;
+    ExpParams E = params_at(P, t);
+    std::vector<double> host;
+    const int N = P.n;
+    // unscaled tables: rho = 1, gamma0 = 0
+    if (d2path) {
+        const int stride = d2_table_stride(N);
+        host.assign((size_t)P.B * stride, 0.0);
+        for (int b = 0; b < P.B; ++b) {
+            double* tb = host.data() + (size_t)b * stride;
+            for (int k = 0; k < N; ++k) {
+                const int p = N - 1 - k;
+                tb[2 * p] = E.g[pidx(P, b, 0, k)].real(); tb[2 * p + 1] = E.g[pidx(P, b, 0, k)].imag();
+                tb[2 * N + p] = E.th[pidx(P, b, 0, k)];
+            }
+            tb[3 * N] = 1.0; tb[3 * N + 1] = 0.0;
+        }
+    } else {
+        const int stride = gen_table_stride(N, P.n_drives);
+        host.assign((size_t)P.B * stride, 0.0);
+        for (int b = 0; b < P.B; ++b) {
+            double* tb = host.data() + (size_t)b * stride;
+            for (int q = 0; q < P.n_drives; ++q)
+                for (int k = 0; k < N; ++k) {
+                    tb[q * 3 * N + 2 * k] = E.g[pidx(P, b, q, k)].real();
+                    tb[q * 3 * N + 2 * k + 1] = E.g[pidx(P, b, q, k)].imag();
+                    tb[q * 3 * N + 2 * N + k] = E.th[pidx(P, b, q, k)];
+                }
+            tb[stride - 2] = 1.0; tb[stride - 1] = 0.0;
+        }
+    }
+    ensure_table_capacity(P, host.size());
+    CUDA_CHECK(cudaMemcpyAsync(P.d_table, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, P.stream));
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    UniformDrive ud{};
+    ud.g = {E.g[0].real(), E.g[0].imag()}; ud.theta = E.th[0]; ud.w = 1.0; ud.gamma = 0.0;
+    StageCoef sc{{0, 0}, {0, 0}, {1, 0}};
+    const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
+    launch_stage(P, passes, in, nullptr, nullptr, out, sc, uniform, E.g[0].imag() == 0.0, ud, P.d_table, launches);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace pb200
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace pb200;
+
+struct pb200_plan {
+    Plan p;
+};
+
+#define PB200_TRY try {
+#define PB200_CATCH                                         \
+    }                                                       \
+    catch (const Error& e) {                                \
+        g_last_error = e.what();                            \
+        return e.code;                                      \
+    }                                                       \
+    catch (const std::exception& e) {                       \
+        g_last_error = e.what();                            \
+        return PB200_ERR_INVALID;                           \
+    }                                                       \
+    return PB200_OK;
+
+extern "C" {
+
+int pb200_version(void) { return 100; }
+
+const char* pb200_last_error(void) { return g_last_error.c_str(); }
+
+int pb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
+    PB200_TRY
+    if (!out || !d) fail(PB200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->n_qudits < 1 || d->n_qudits > PB200_MAX_QUDITS) fail(PB200_ERR_INVALID, "n_qudits out of range");
+    if (d->dim < 2 || d->dim > 4) fail(PB200_ERR_INVALID, "dim must be 2, 3 or 4");
+    if (d->n_times < 2 || !d->sampling_times) fail(PB200_ERR_INVALID, "need >= 2 sampling times");
+    if (d->n_drives < 0 || d->n_drives > PB200_MAX_DRIVES) fail(PB200_ERR_INVALID, "n_drives out of range");
+    if (d->n_traj < 1) fail(PB200_ERR_INVALID, "n_traj must be >= 1");
+    if (d->interp_order != 0 && d->interp_order != 1 && d->interp_order != 3)
+        fail(PB200_ERR_INVALID, "interp_order must be 0, 1 or 3");
+    for (int i = 1; i < d->n_times; ++i)
+        if (!(d->sampling_times[i] > d->sampling_times[i - 1])) fail(PB200_ERR_INVALID, "sampling_times must increase");
+    for (int q = 0; q < d->n_drives; ++q) {
+        const pb200_drive_desc& dd = d->drives[q];
+        if (dd.state_to < 0 || dd.state_to >= d->dim || dd.state_from < 0 || dd.state_from >= d->dim ||
+            dd.state_to == dd.state_from)
+            fail(PB200_ERR_INVALID, "drive %d: bad eigenstate indices", q);
+    }
+    double Dd = std::pow((double)d->dim, d->n_qudits);
+    if (Dd * d->n_traj > 4.0e9) fail(PB200_ERR_UNSUPPORTED, "state too large: %g amplitudes", Dd * d->n_traj);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(PB200_ERR_CUDA, "no CUDA device available: the pulser_b200 hot path has no CPU fallback");
+    }
+    if (d->device < 0 || d->device >= ndev) fail(PB200_ERR_INVALID, "device ordinal %d out of range", d->device);
+    CUDA_CHECK(cudaSetDevice(d->device));
+    pb200_plan* h = new pb200_plan();
+    Plan& P = h->p;
+    P.desc = *d;
+    P.times.assign(d->sampling_times, d->sampling_times + d->n_times);
+    P.desc.sampling_times = nullptr;
+    P.n = d->n_qudits; P.dim = d->dim; P.B = d->n_traj; P.n_drives = d->n_drives;
+    long long D = 1;
+    for (int i = 0; i < P.n; ++i) D *= P.dim;
+    P.D = D;
+    P.tile_bits = std::min(13, std::max(2, env_int("PB200_TILE_BITS", 12)));
+    P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 3));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
+    P.sm_count = prop.multiProcessorCount;
+    try {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+        P.own_stream = true;
+        for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaMalloc(&P.buf[i], sizeof(c2) * (size_t)D * P.B));
+        CUDA_CHECK(cudaMalloc(&P.d_scratch, sizeof(double) * 4096));
+        // > 48 KB of dynamic shared memory for the tile kernels
+        const int max_smem = (1 << 13) * 16 + 1024;
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    } catch (...) {
+        pb200_plan_destroy(h);
+        throw;
+    }
+    P.tabs.assign(P.B, std::vector<DriveTables>(P.n_drives));
+    P.tabs_set.assign(P.B, std::vector<bool>(P.n_drives, false));
+    P.has_interaction = false;
+    *out = h;
+    PB200_CATCH
+}
+
+int pb200_plan_destroy(pb200_plan* h) {
+    if (!h) return PB200_OK;
+    Plan& P = h->p;
+    for (int i = 0; i < 3; ++i)
+        if (P.buf[i]) cudaFree(P.buf[i]);
+    if (P.dint) cudaFree(P.dint);
+    if (P.d_table) cudaFree(P.d_table);
+    if (P.d_scratch) cudaFree(P.d_scratch);
+    if (P.own_stream && P.stream) cudaStreamDestroy(P.stream);
+    delete h;
+    return PB200_OK;
+}
+
+int pb200_plan_set_stream(pb200_plan* h, void* s) {
+    PB200_TRY
+    if (!h) fail(PB200_ERR_INVALID, "null plan");
+    Plan& P = h->p;
+    if (s) {
+        if (P.own_stream && P.stream) { cudaStreamSynchronize(P.stream); cudaStreamDestroy(P.stream); }
+        P.stream = (cudaStream_t)s; P.own_stream = false;
+    }
+    PB200_CATCH
+}
+
+int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, const double* U, const uint8_t* bad,
+                               int32_t shared) {
+    PB200_TRY
+    if (!h || !U) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (P.desc.rydberg_state < 0) fail(PB200_ERR_INVALID, "plan has no interaction term (rydberg_state < 0)");
+    if (shared && (count != 1 || traj0 != 0)) fail(PB200_ERR_INVALID, "shared interaction: traj0 = 0, count = 1");
+    if (!shared && (traj0 < 0 || count < 1 || traj0 + count > P.B)) fail(PB200_ERR_INVALID, "trajectory range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    const int N = P.n;
+    const bool want_shared = shared != 0;
+    if (P.dint && P.dint_shared != want_shared) { CUDA_CHECK(cudaFree(P.dint)); P.dint = nullptr; }
+    if (!P.dint) {
+        CUDA_CHECK(cudaMalloc(&P.dint, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B)));
+        if (!want_shared) CUDA_CHECK(cudaMemsetAsync(P.dint, 0, sizeof(double) * (size_t)P.D * P.B, P.stream));
+    }
+    P.dint_shared = want_shared;
+    P.dmin_traj.resize(want_shared ? 1 : P.B, 0.0);
+    P.dmax_traj.resize(want_shared ? 1 : P.B, 0.0);
+    double* dU = nullptr;
+    CUDA_CHECK(cudaMalloc(&dU, sizeof(double) * N * N));
+    std::vector<double> Uc((size_t)N * N);
+    for (int c = 0; c < count; ++c) {
+        const double* Ui = U + (size_t)c * N * N;
+        const uint8_t* bi = bad ? bad + (size_t)c * N : nullptr;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                double u = (i < j) ? Ui[i * N + j] : (i > j ? Ui[j * N + i] : 0.0);
+                if (bi && (bi[i] || bi[j])) u = 0.0;
+                Uc[(size_t)i * N + j] = u;
+            }
+        CUDA_CHECK(cudaMemcpyAsync(dU, Uc.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, P.stream));
+        double* dst = P.dint + (want_shared ? 0 : (size_t)(traj0 + c) * P.D);
+        const int threads = 256;
+        const long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 16);
+        dint_kernel<<<(unsigned)std::max<long long>(blocks, 1), threads, sizeof(double) * N * N, P.stream>>>(
+            dst, dU, N, P.dim, P.desc.rydberg_state, P.D);
+        CUDA_CHECK(cudaGetLastError());
+        // bounds per |r>-count
+        std::vector<double> mins(N + 1, 1e300), maxs(N + 1, -1e300);
+        CUDA_CHECK(cudaMemcpyAsync(P.d_scratch, mins.data(), sizeof(double) * (N + 1), cudaMemcpyHostToDevice, P.stream));
+        CUDA_CHECK(cudaMemcpyAsync(P.d_scratch + 64, maxs.data(), sizeof(double) * (N + 1), cudaMemcpyHostToDevice, P.stream));
+        dint_bounds_kernel<<<(unsigned)std::max<long long>(blocks, 1), threads, 0, P.stream>>>(
+            dst, N, P.dim, P.desc.rydberg_state, P.D, P.d_scratch, P.d_scratch + 64);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(mins.data(), P.d_scratch, sizeof(double) * (N + 1), cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaMemcpyAsync(maxs.data(), P.d_scratch + 64, sizeof(double) * (N + 1), cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        double mn = 1e300, mx = -1e300;
+        for (int k = 0; k <= N; ++k)
+            if (mins[k] <= maxs[k]) { mn = std::min(mn, mins[k]); mx = std::max(mx, maxs[k]); }
+        const int slot = want_shared ? 0 : traj0 + c;
+        P.dmin_traj[slot] = mn; P.dmax_traj[slot] = mx;
+        if (want_shared) { P.dmin_cnt = mins; P.dmax_cnt = maxs; }
+    }
+    CUDA_CHECK(cudaFree(dU));
+    P.has_interaction = true;
+    PB200_CATCH
+}
+
+int pb200_plan_set_drive(pb200_plan* h, int32_t drive, int32_t traj0, int32_t count, const double* coef,
+                         const double* det) {
+    PB200_TRY
+    if (!h || !coef || !det) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (drive < 0 || drive >= P.n_drives) fail(PB200_ERR_INVALID, "drive index out of range");
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    const int rows = P.desc.drives[drive].uniform ? 1 : P.n;
+    const int nt = (int)P.times.size();
+    for (int c = 0; c < count; ++c) {
+        DriveTables& T = P.tabs[traj0 + c][drive];
+        T.coef.resize(rows); T.det.resize(rows);
+        T.coef_scale.assign(rows, 0.0); T.det_scale.assign(rows, 0.0);
+        for (int r = 0; r < rows; ++r) {
+            const cplx* y = reinterpret_cast<const cplx*>(coef) + ((size_t)c * rows + r) * nt;
+            const double* dd = det + ((size_t)c * rows + r) * nt;
+            T.coef[r] = make_interpolant<cplx>(P.times.data(), y, nt, P.desc.interp_order);
+            T.det[r] = make_interpolant<double>(P.times.data(), dd, nt, P.desc.interp_order);
+            for (int i = 0; i < nt; ++i) {
+                if (!std::isfinite(y[i].real()) || !std::isfinite(y[i].imag()) || !std::isfinite(dd[i]))
+                    fail(PB200_ERR_INVALID, "non-finite sample in drive table");
+                T.coef_scale[r] = std::max(T.coef_scale[r], std::abs(y[i]));
+                T.det_scale[r] = std::max(T.det_scale[r], std::fabs(dd[i]));
+            }
+        }
+        P.tabs_set[traj0 + c][drive] = true;
+    }
+    PB200_CATCH
+}
+
+int pb200_state_set(pb200_plan* h, int32_t traj0, int32_t count, const double* psi, int64_t basis_index,
+                    int32_t broadcast) {
+    PB200_TRY
+    if (!h) fail(PB200_ERR_INVALID, "null plan");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    c2* cur = P.buf[P.cur];
+    for (int c = 0; c < count; ++c) {
+        c2* dst = cur + (size_t)(traj0 + c) * P.D;
+        if (psi) {
+            const double* src = broadcast ? psi : psi + (size_t)c * P.D * 2;
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(c2) * (size_t)P.D, cudaMemcpyHostToDevice, P.stream));
+        } else {
+            if (basis_index < 0 || basis_index >= P.D) fail(PB200_ERR_INVALID, "basis_index out of range");
+            const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 16);
+            set_basis_kernel<<<(unsigned)blocks, 256, 0, P.stream>>>(dst, P.D, basis_index);
+            CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    P.state_set = true;
+    PB200_CATCH
+}
+
+int pb200_state_get(pb200_plan* h, int32_t traj0, int32_t count, double* psi) {
+    PB200_TRY
+    if (!h || !psi) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    CUDA_CHECK(cudaMemcpyAsync(psi, P.buf[P.cur] + (size_t)traj0 * P.D, sizeof(c2) * (size_t)P.D * count,
+                               cudaMemcpyDeviceToHost, P.stream));
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    PB200_CATCH
+}
+
+int pb200_state_probabilities(pb200_plan* h, int32_t traj0, int32_t count, double* probs) {
+    PB200_TRY
+    if (!h || !probs) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    // reuse a scratch state buffer for the doubles
+    double* tmp = reinterpret_cast<double*>(P.buf[(P.cur + 1) % 3]);
+    const long long total = P.D * count;
+    const long long blocks = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
+    prob_kernel<<<(unsigned)blocks, 256, 0, P.stream>>>(P.buf[P.cur] + (size_t)traj0 * P.D, tmp, total);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(probs, tmp, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, P.stream));
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    PB200_CATCH
+}
+
+int pb200_state_norm2(pb200_plan* h, int32_t traj0, int32_t count, double* norms2) {
+    PB200_TRY
+    if (!h || !norms2) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B || count > 4096) fail(PB200_ERR_INVALID, "trajectory range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * count, P.stream));
+    const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
+    dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
+    norm2_kernel<<<grid, 256, 0, P.stream>>>(P.buf[P.cur] + (size_t)traj0 * P.D, P.D, P.d_scratch);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(norms2, P.d_scratch, sizeof(double) * count, cudaMemcpyDeviceToHost, P.stream));
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    PB200_CATCH
+}
+
+int pb200_state_device_ptr(pb200_plan* h, void** dptr) {
+    PB200_TRY
+    if (!h || !dptr) fail(PB200_ERR_INVALID, "null argument");
+    *dptr = h->p.buf[h->p.cur];
+    PB200_CATCH
+}
+
+int pb200_propagate(pb200_plan* h, double t_start, double t_stop, const pb200_run_opts* opts, pb200_run_stats* stats) {
+    PB200_TRY
+    if (!h) fail(PB200_ERR_INVALID, "null plan");
+    CUDA_CHECK(cudaSetDevice(h->p.desc.device));
+    propagate(h->p, t_start, t_stop, opts, stats);
+    PB200_CATCH
+}
+
+int pb200_apply_h(pb200_plan* h, int32_t traj, double t_us, const double* in, double* out) {
+    PB200_TRY
+    if (!h || !in || !out) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj < 0 || traj >= P.B) fail(PB200_ERR_INVALID, "trajectory out of range");
+    for (int tr = 0; tr < P.B; ++tr)
+        for (int q = 0; q < P.n_drives; ++q)
+            if (!P.tabs_set[tr][q]) fail(PB200_ERR_STATE, "drive %d of trajectory %d not set", q, tr);
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    c2* bin = P.buf[(P.cur + 1) % 3];
+    c2* bout = P.buf[(P.cur + 2) % 3];
+    // the kernels run over the whole batch: zero the other trajectories' input
+    CUDA_CHECK(cudaMemsetAsync(bin, 0, sizeof(c2) * (size_t)P.D * P.B, P.stream));
+    CUDA_CHECK(cudaMemcpyAsync(bin + (size_t)traj * P.D, in, sizeof(c2) * (size_t)P.D, cudaMemcpyHostToDevice, P.stream));
+    long long launches = 0;
+    apply_h_device(P, t_us, bin, bout, launches);
+    CUDA_CHECK(cudaMemcpyAsync(out, bout + (size_t)traj * P.D, sizeof(c2) * (size_t)P.D, cudaMemcpyDeviceToHost, P.stream));
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    PB200_CATCH
+}
+
+int pb200_coefficients_at(pb200_plan* h, int32_t traj, int32_t drive, int32_t row, double t_us, double* out3) {
+    PB200_TRY
+    if (!h || !out3) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj < 0 || traj >= P.B || drive < 0 || drive >= P.n_drives) fail(PB200_ERR_INVALID, "index out of range");
+    if (!P.tabs_set[traj][drive]) fail(PB200_ERR_STATE, "drive not set");
+    const DriveTables& T = P.tabs[traj][drive];
+    if (row < 0 || row >= (int)T.coef.size()) fail(PB200_ERR_INVALID, "row out of range");
+    const cplx c = eval_at(T.coef[row], P.times, t_us, P.desc.interp_order);
+    out3[0] = c.real(); out3[1] = c.imag();
+    out3[2] = eval_at(T.det[row], P.times, t_us, P.desc.interp_order);
+    PB200_CATCH
+}
+
+int pb200_bench_apply(pb200_plan* h, double t_us, int32_t reps, double* ms_out, int64_t* launches_out) {
+    PB200_TRY
+    if (!h || !ms_out || reps < 1) fail(PB200_ERR_INVALID, "bad argument");
+    Plan& P = h->p;
+    if (!P.state_set) fail(PB200_ERR_STATE, "no state set");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    c2* in = P.buf[P.cur];
+    c2* outb = P.buf[(P.cur + 1) % 3];
+    long long launches = 0;
+    apply_h_device(P, t_us, in, outb, launches);  // warm-up + table upload
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool uniform = d2path && P.all_uniform() && P.B == 1;
+    ExpParams E = params_at(P, t_us);
+    UniformDrive ud{};
+    ud.g = {E.g[0].real(), E.g[0].imag()}; ud.theta = E.th[0]; ud.w = 1.0; ud.gamma = 0.0;
+    StageCoef sc{{0, 0}, {0, 0}, {1, 0}};
+    const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    launches = 0;
+    CUDA_CHECK(cudaEventRecord(e0, P.stream));
+    for (int r = 0; r < reps; ++r)
+        launch_stage(P, passes, in, nullptr, nullptr, outb, sc, uniform, E.g[0].imag() == 0.0, ud, P.d_table, launches);
+    CUDA_CHECK(cudaEventRecord(e1, P.stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    CUDA_CHECK(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out = ms;
+    if (launches_out) *launches_out = launches;
+    PB200_CATCH
+}
+
+int pb200_host_interpolate(const double* x, const double* y, int32_t n, int32_t order, const double* tq, int32_t nq,
+                           double* out) {
+    PB200_TRY
+    if (!x || !y || !tq || !out || n < 2) fail(PB200_ERR_INVALID, "bad argument");
+    std::vector<double> xs(x, x + n);
+    auto pc = make_interpolant<cplx>(x, reinterpret_cast<const cplx*>(y), n, order);
+    for (int i = 0; i < nq; ++i) {
+        const cplx v = eval_at(pc, xs, tq[i], order);
+        out[2 * i] = v.real(); out[2 * i + 1] = v.imag();
+    }
+    PB200_CATCH
+}
+
+int pb200_host_moments(const double* x, const double* y, int32_t n, int32_t order, double a, double b, double* out4) {
+    PB200_TRY
+    if (!x || !y || !out4 || n < 2) fail(PB200_ERR_INVALID, "bad argument");
+    std::vector<double> xs(x, x + n);
+    auto pc = make_interpolant<cplx>(x, reinterpret_cast<const cplx*>(y), n, order);
+    cplx b0, b1;
+    magnus_moments(pc, xs, a, b, b0, b1);
+    out4[0] = b0.real(); out4[1] = b0.imag(); out4[2] = b1.real(); out4[3] = b1.imag();
+    PB200_CATCH
+}
+
+int pb200_host_chebyshev(double rho, double tol, double* out, int32_t cap, int32_t* count) {
+    PB200_TRY
+    if (!out || !count) fail(PB200_ERR_INVALID, "bad argument");
+    std::vector<cplx> a = chebyshev_exp_coeffs(rho, tol);
+    *count = (int32_t)a.size();
+    for (int i = 0; i < (int)a.size() && i < cap; ++i) { out[2 * i] = a[i].real(); out[2 * i + 1] = a[i].imag(); }
+    PB200_CATCH
+}
+
+}  // extern "C"

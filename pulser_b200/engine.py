@@ -1,0 +1,255 @@
+"""Python face of the C-ABI plan: one ``HamiltonianSpec`` (or a batch of
+trajectories sharing its structure) -> device plan -> propagate.
+
+This is the host-side replacement of ``Hamiltonian(...)`` construction
+(reference ``pulser-simulation/pulser_simulation/simulation.py:299-311``) and
+of the ``qutip.sesolve`` call (``simulation.py:729-735``).  All arithmetic
+happens in ``libpulser_b200.so`` on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import PlanDesc, RunOpts, RunStats, check, lib
+from .spec import BASIS_ROLES, HamiltonianSpec
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+def all_ground_index(spec: HamiltonianSpec) -> int:
+    """Index of the all-ground product state (``simulation.py:498-505``)."""
+    eig = spec.eigenbasis
+    g = eig.index("u") if spec.interaction_type == "XY" else eig.index("g")
+    idx = 0
+    for _ in range(spec.n_qudits):
+        idx = idx * spec.dim + g
+    return idx
+
+
+class DevicePlan:
+    """A batch of trajectories of one sequence resident on one GPU."""
+
+    def __init__(
+        self,
+        specs: HamiltonianSpec | Sequence[HamiltonianSpec],
+        interp_order: int = 3,
+        device: int = 0,
+    ) -> None:
+        if isinstance(specs, HamiltonianSpec):
+            specs = [specs]
+        specs = list(specs)
+        s0 = specs[0]
+        if s0.interaction_type == "XY":
+            raise NotImplementedError(
+                "XY (flip-flop) interaction is not on the CUDA path yet"
+            )
+        for s in specs[1:]:
+            if (
+                s.n_qudits != s0.n_qudits
+                or s.eigenbasis != s0.eigenbasis
+                or len(s.drives) != len(s0.drives)
+                or [d.basis for d in s.drives] != [d.basis for d in s0.drives]
+                or not np.array_equal(s.sampling_times, s0.sampling_times)
+            ):
+                raise ValueError("trajectories must share basis, drives, times")
+        self.specs = specs
+        self.spec = s0
+        self.n_traj = len(specs)
+        self.n = s0.n_qudits
+        self.dim = s0.dim
+        self.D = s0.hilbert_dim
+        self.interp_order = interp_order
+        self._handle = C.c_void_p()
+        times = np.ascontiguousarray(s0.sampling_times, dtype=np.float64)
+        desc = PlanDesc()
+        desc.n_qudits = self.n
+        desc.dim = self.dim
+        desc.n_times = len(times)
+        desc.interp_order = interp_order
+        desc.n_drives = len(s0.drives)
+        any_inter = any(s.has_interaction() for s in specs)
+        desc.rydberg_state = s0.eigenbasis.index("r") if any_inter else -1
+        desc.n_traj = self.n_traj
+        desc.device = device
+        desc.sampling_times = _p(times)
+        self._uniform = []
+        for q, d in enumerate(s0.drives):
+            to, frm = BASIS_ROLES[d.basis]
+            desc.drives[q].state_to = s0.eigenbasis.index(to)
+            desc.drives[q].state_from = s0.eigenbasis.index(frm)
+            uni = all(s.drives[q].uniform for s in specs)
+            desc.drives[q].uniform = int(uni)
+            self._uniform.append(uni)
+        check(lib.pb200_plan_create(C.byref(self._handle), C.byref(desc)))
+        try:
+            self._upload(any_inter)
+        except Exception:
+            self.close()
+            raise
+
+    # ------------------------------------------------------------------
+    def _upload(self, any_inter: bool) -> None:
+        specs = self.specs
+        n, nt = self.n, len(self.spec.sampling_times)
+        if any_inter:
+            mats = [s.pair_matrix() for s in specs]
+            shared = all(np.array_equal(m, mats[0]) for m in mats[1:])
+            if shared:
+                U = np.ascontiguousarray(mats[0], dtype=np.float64)
+                check(lib.pb200_plan_set_interaction(self._handle, 0, 1, _p(U), None, 1))
+            else:
+                U = np.ascontiguousarray(np.stack(mats), dtype=np.float64)
+                check(
+                    lib.pb200_plan_set_interaction(
+                        self._handle, 0, self.n_traj, _p(U), None, 0
+                    )
+                )
+        for q, uni in enumerate(self._uniform):
+            rows = 1 if uni else n
+            # chunk the upload to bound host memory
+            chunk = max(1, (64 << 20) // (rows * nt * 24))
+            for b0 in range(0, self.n_traj, chunk):
+                part = specs[b0 : b0 + chunk]
+                coef = np.ascontiguousarray(
+                    np.stack([s.drives[q].coef[:rows] for s in part]),
+                    dtype=np.complex128,
+                )
+                det = np.ascontiguousarray(
+                    np.stack([s.drives[q].det[:rows] for s in part]),
+                    dtype=np.float64,
+                )
+                check(
+                    lib.pb200_plan_set_drive(
+                        self._handle, q, b0, len(part),
+                        _p(coef.view(np.float64)), _p(det),
+                    )
+                )
+
+    # ------------------------------------------------------------------
+    def close(self) -> None:
+        if self._handle:
+            lib.pb200_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self) -> "DevicePlan":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    def set_stream(self, cuda_stream: int) -> None:
+        check(lib.pb200_plan_set_stream(self._handle, C.c_void_p(cuda_stream)))
+
+    # ------------------------------------------------------------------
+    def set_state(self, psi: np.ndarray | str = "all-ground") -> None:
+        """Same state for every trajectory, or ``psi[n_traj, D]``."""
+        if isinstance(psi, str):
+            if psi != "all-ground":
+                raise ValueError(psi)
+            check(
+                lib.pb200_state_set(
+                    self._handle, 0, self.n_traj, None, all_ground_index(self.spec), 0
+                )
+            )
+            return
+        psi = np.ascontiguousarray(psi, dtype=np.complex128)
+        if psi.size == self.D:
+            check(
+                lib.pb200_state_set(
+                    self._handle, 0, self.n_traj, _p(psi.reshape(-1).view(np.float64)), -1, 1
+                )
+            )
+        elif psi.size == self.D * self.n_traj:
+            check(
+                lib.pb200_state_set(
+                    self._handle, 0, self.n_traj, _p(psi.reshape(-1).view(np.float64)), -1, 0
+                )
+            )
+        else:
+            raise ValueError(
+                "Incompatible shape of initial state."
+                + f"Expected {self.D}, got {psi.shape[0]}."
+            )
+
+    def get_state(self, traj0: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_traj - traj0 if count is None else count
+        out = np.empty((count, self.D), dtype=np.complex128)
+        check(lib.pb200_state_get(self._handle, traj0, count, _p(out.view(np.float64))))
+        return out
+
+    def probabilities(self, traj0: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.n_traj - traj0 if count is None else count
+        out = np.empty((count, self.D), dtype=np.float64)
+        check(lib.pb200_state_probabilities(self._handle, traj0, count, _p(out)))
+        return out
+
+    def norm2(self) -> np.ndarray:
+        out = np.empty(self.n_traj, dtype=np.float64)
+        check(lib.pb200_state_norm2(self._handle, 0, self.n_traj, _p(out)))
+        return out
+
+    def device_ptr(self) -> int:
+        ptr = C.c_void_p()
+        check(lib.pb200_state_device_ptr(self._handle, C.byref(ptr)))
+        return int(ptr.value)
+
+    # ------------------------------------------------------------------
+    def propagate(
+        self,
+        t_start: float,
+        t_stop: float,
+        max_step: int = 0,
+        refine_window: int = -1,
+        cheb_tol: float = 0.0,
+        rough_tol: float = 0.0,
+        magnus_order: int = 4,
+    ) -> dict:
+        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, 0)
+        st = RunStats()
+        check(
+            lib.pb200_propagate(
+                self._handle, float(t_start), float(t_stop), C.byref(opts), C.byref(st)
+            )
+        )
+        return {f: getattr(st, f) for f, _ in RunStats._fields_}
+
+    def apply_h(self, t_us: float, vec: np.ndarray, traj: int = 0) -> np.ndarray:
+        vec = np.ascontiguousarray(vec, dtype=np.complex128).reshape(-1)
+        if vec.size != self.D:
+            raise ValueError("vector has the wrong dimension")
+        out = np.empty(self.D, dtype=np.complex128)
+        check(
+            lib.pb200_apply_h(
+                self._handle, traj, float(t_us), _p(vec.view(np.float64)), _p(out.view(np.float64))
+            )
+        )
+        return out
+
+    def coefficients_at(self, t_us: float, drive: int = 0, row: int = 0, traj: int = 0):
+        out = np.empty(3)
+        check(lib.pb200_coefficients_at(self._handle, traj, drive, row, float(t_us), _p(out)))
+        return complex(out[0], out[1]), float(out[2])
+
+    def bench_apply(self, t_us: float, reps: int) -> tuple[float, int]:
+        ms = C.c_double()
+        n = C.c_int64()
+        check(lib.pb200_bench_apply(self._handle, float(t_us), reps, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def device_count() -> int:
+    return int(_lib.lib.pb200_device_count())

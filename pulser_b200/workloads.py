@@ -1,0 +1,179 @@
+"""Synthetic workloads of BASELINE.json ``configs`` as plain-array specs.
+
+The GPU box has neither ``/root/reference`` nor pulser, so the benchmark and
+the GPU parity tests build their inputs here with numpy only, restating what
+``pulser.sampler.sample`` + ``HamiltonianData`` produce for these sequences
+(waveform formulas: reference ``pulser-core/pulser/waveforms.py:584`` constant,
+``:661-674`` ramp, ``:740-743`` Blackman; C6 coefficients:
+``pulser-core/pulser/devices/interaction_coefficients/``; interaction matrix
+``pulser-core/pulser/_hamiltonian_data/hamiltonian_data.py:607-611``; the
+zero-padded extra sample ``pulser-simulation/pulser_simulation/simulation.py:172-173``).
+``tests/test_workloads_vs_pulser.py`` checks every builder against the real
+pulser objects whenever pulser is importable.
+
+Definitions follow SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .spec import DriveTable, HamiltonianSpec
+
+# device.interaction_coeff (rad/us * um^6)
+C6_LEVEL_70 = 5420158.53  # MockDevice, DigitalAnalogDevice
+C6_LEVEL_60 = 865723.02  # AnalogDevice
+
+
+# ---------------------------------------------------------------- waveforms
+def ramp(duration: int, start: float, stop: float) -> np.ndarray:
+    slope = (stop - start) / (duration - 1)
+    lo, hi = sorted([float(start), float(stop)])
+    return np.clip(slope * np.arange(duration, dtype=float) + start, lo, hi)
+
+
+def constant(duration: int, value: float) -> np.ndarray:
+    return value * np.ones(duration)
+
+
+def blackman(duration: int, area: float) -> np.ndarray:
+    norm = np.clip(np.blackman(duration), 0, np.inf)
+    return norm * (area / np.sum(norm) * 1e3)
+
+
+# ---------------------------------------------------------------- registers
+def disc_register(
+    n: int, radius: float, min_dist: float, seed: int
+) -> np.ndarray:
+    """n points uniform in a disc with rejection on the minimum distance."""
+    rng = np.random.default_rng(seed)
+    pts: list[np.ndarray] = []
+    while len(pts) < n:
+        p = rng.uniform(-radius, radius, size=2)
+        if np.hypot(*p) > radius:
+            continue
+        if all(np.hypot(*(p - q)) >= min_dist for q in pts):
+            pts.append(np.round(p, 6))
+    return np.array(pts)
+
+
+def square_register(side: int, spacing: float) -> np.ndarray:
+    """``Register.square(side, spacing)`` coordinates (centred, row-major).
+
+    Reference ``pulser-core/pulser/register/register.py`` (rectangle:
+    ``coords = [(x, y) for y in rows for x in columns] * spacing``, centred).
+    """
+    coords = (
+        np.array(
+            [(x, y) for y in range(side) for x in range(side)], dtype=float
+        )
+        * spacing
+    )
+    return coords - np.mean(coords, axis=0)
+
+
+def interaction_matrix(coords: np.ndarray, c6: float) -> np.ndarray:
+    """(1, N, N) C6/r^6 as ``HamiltonianData._interaction_matrix``."""
+    from scipy.spatial.distance import cdist
+
+    pts = np.round(np.asarray(coords, dtype=float), 6)
+    d = np.round(cdist(pts, pts), 6)  # COORD_PRECISION = 6
+    n = len(pts)
+    out = np.zeros((1, n, n))
+    iu = np.triu_indices(n, 1)
+    out[0][iu] = c6 / d[iu] ** 6
+    out[0] = out[0] + out[0].T
+    return out
+
+
+# ---------------------------------------------------------------- spec
+def ising_global_spec(
+    coords: np.ndarray,
+    c6: float,
+    amp: np.ndarray,
+    det: np.ndarray,
+    phase: np.ndarray | float = 0.0,
+    basis_name: str = "ground-rydberg",
+) -> HamiltonianSpec:
+    """Global ground-rydberg drive over ``len(amp)`` ns, sampling_rate 1.
+
+    Adds the zero-padded extra sample of ``extend_duration(T+1)``
+    (amp, det -> 0; phase -> edge value; reference ``samples.py:152-200``).
+    """
+    n = len(coords)
+    T = len(amp)
+    phase = np.broadcast_to(np.asarray(phase, dtype=float), (T,))
+    amp_e = np.append(amp, 0.0)
+    det_e = np.append(det, 0.0)
+    phase_e = np.append(phase, phase[-1])
+    coef = 0.5 * amp_e * np.exp(-1j * phase_e)
+    return HamiltonianSpec(
+        n_qudits=n,
+        dim=2,
+        eigenbasis=["r", "g"],
+        basis_name=basis_name,
+        interaction_type="ising",
+        sampling_times=np.arange(T + 1, dtype=np.double) / 1000,
+        total_duration_ns=T,
+        interaction_matrix=interaction_matrix(coords, c6),
+        bad_atoms=np.zeros(n, dtype=bool),
+        drives=[
+            DriveTable(
+                "ground-rydberg",
+                np.repeat(coef[None, :], n, axis=0),
+                np.repeat(det_e[None, :], n, axis=0),
+                True,
+            )
+        ],
+        collapse_ops=np.zeros((0, 2, 2), dtype=np.complex128),
+        qubit_ids=[f"q{i}" for i in range(n)],
+    )
+
+
+def blockade_sweep_waveforms(
+    omega: float = 2 * np.pi * 1.5,
+    t_rise: int = 500,
+    t_sweep: int = 2500,
+    t_fall: int = 1000,
+) -> tuple[np.ndarray, np.ndarray]:
+    """Rise / detuning sweep / fall of SURVEY 8(d) C2 (ends at Omega = 0)."""
+    U = omega / 2
+    d0, df = -6 * U, 2 * U
+    amp = np.concatenate(
+        [ramp(t_rise, 0.0, omega), constant(t_sweep, omega), ramp(t_fall, omega, 0.0)]
+    )
+    det = np.concatenate(
+        [constant(t_rise, d0), ramp(t_sweep, d0, df), constant(t_fall, df)]
+    )
+    return amp, det
+
+
+def config_c1() -> HamiltonianSpec:
+    """C1: 4-atom square, constant Omega/delta pulse, 1000 ns (MockDevice)."""
+    coords = square_register(2, 6.0)
+    return ising_global_spec(
+        coords, C6_LEVEL_70, constant(1000, 2 * np.pi), constant(1000, np.pi)
+    )
+
+
+def config_c2(n: int = 20, seed: int | None = None, **kw) -> HamiltonianSpec:
+    """C2: n-atom random 2D register (AnalogDevice limits), blockade sweep."""
+    coords = disc_register(n, 38.0, 5.0, n if seed is None else seed)
+    amp, det = blockade_sweep_waveforms(**kw)
+    return ising_global_spec(coords, C6_LEVEL_60, amp, det)
+
+
+def config_c5(n: int = 24, t_total: int = 4000) -> HamiltonianSpec:
+    """C5: n-atom adiabatic anneal 0 -> Omega -> 0 with a detuning ramp."""
+    coords = disc_register(n, 38.0, 5.0, n)
+    omega = 2 * np.pi * 1.5
+    U = omega / 2
+    t_edge = t_total // 4
+    amp = np.concatenate(
+        [
+            ramp(t_edge, 0.0, omega),
+            constant(t_total - 2 * t_edge, omega),
+            ramp(t_edge, omega, 0.0),
+        ]
+    )
+    det = ramp(t_total, -6 * U, 2 * U)
+    return ising_global_spec(coords, C6_LEVEL_60, amp, det)

@@ -1,0 +1,157 @@
+"""GPU parity tests: CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): rtol 1e-8 on Schroedinger state
+amplitudes, measured as max |psi_gpu - psi_oracle| (states have unit norm).
+"""
+import numpy as np
+import pytest
+
+from helpers import random_local_spec, random_state
+from pulser_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def engine(lib):
+    from pulser_b200 import engine
+
+    assert engine.device_count() > 0, "GPU tests need a CUDA device"
+    return engine
+
+
+def _oracle_final(spec, psi0, t_end=None, order=3):
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    H = OracleHamiltonian.from_spec(spec)
+    t_end = spec.sampling_times[-1] if t_end is None else t_end
+    return evolve.sesolve(H, psi0, [0.0, t_end], order=order, rtol=1e-13, atol=1e-15)[-1]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 7, 10, 12, 13, 15, 16])
+def test_apply_h_uniform(engine, n):
+    """H(t) psi on the device == matrix-free oracle (global drive)."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    spec = W.config_c2(n=n, seed=5) if n > 1 else W.ising_global_spec(
+        np.zeros((1, 2)), W.C6_LEVEL_60, *W.blockade_sweep_waveforms())
+    mf = MatFreeHamiltonian(spec)
+    v = random_state(spec.hilbert_dim, n)
+    with engine.DevicePlan(spec) as plan:
+        for t in (0.1234, 1.7, 3.9995):
+            got = plan.apply_h(t, v)
+            ref = mf.apply(t, v)
+            assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("n", [3, 6, 11, 14, 16])
+def test_apply_h_local_complex(engine, n):
+    """Per-qubit complex drives (noisy-trajectory shape)."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    spec = random_local_spec(n, T=64, seed=n)
+    mf = MatFreeHamiltonian(spec)
+    v = random_state(spec.hilbert_dim, n)
+    with engine.DevicePlan(spec) as plan:
+        for t in (0.0031, 0.0405):
+            got = plan.apply_h(t, v)
+            ref = mf.apply(t, v)
+            assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_c1_four_atom_square(engine):
+    """BASELINE config C1 end to end against the tight-tolerance oracle."""
+    from oracle import evolve
+
+    spec = W.config_c1()
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        st = plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    assert st["n_applies"] > 0 and st["n_launches"] > 0
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("n,max_step", [(6, 1), (8, 4), (10, 4)])
+def test_blockade_sweep_vs_oracle(engine, n, max_step):
+    """C2-shaped sequence (4000 ns) at oracle-sized registers."""
+    from oracle import evolve
+
+    spec = W.config_c2(n=n, seed=20)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1], max_step=max_step)
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+
+
+def test_local_noisy_trajectory_vs_oracle(engine):
+    from oracle import evolve
+
+    spec = random_local_spec(6, T=300, seed=3)
+    psi0 = random_state(spec.hilbert_dim, 9)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state(psi0)
+        plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+
+
+def test_batch_of_trajectories(engine):
+    """Three different trajectories evolved in one batch == one by one."""
+    specs = [random_local_spec(5, T=120, seed=s) for s in (11, 12, 13)]
+    psi0 = random_state(specs[0].hilbert_dim, 2)
+    singles = []
+    for s in specs:
+        with engine.DevicePlan(s) as plan:
+            plan.set_state(psi0)
+            plan.propagate(0.0, s.sampling_times[-1])
+            singles.append(plan.get_state()[0])
+    with engine.DevicePlan(specs) as plan:
+        plan.set_state(psi0)
+        plan.propagate(0.0, specs[0].sampling_times[-1])
+        got = plan.get_state()
+    for a, b in zip(got, singles):
+        assert np.max(np.abs(a - b)) < 1e-11
+    ref = _oracle_final(specs[1], psi0)
+    assert np.max(np.abs(got[1] - ref)) < STATE_TOL
+
+
+def test_intermediate_times_and_restart(engine):
+    """Propagating in pieces equals propagating at once (evaluation times)."""
+    spec = W.config_c2(n=7, seed=3)
+    tf = spec.sampling_times[-1]
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, tf)
+        whole = plan.get_state()[0]
+        plan.set_state("all-ground")
+        for a, b in [(0.0, 0.4567), (0.4567, 1.2), (1.2, 3.0005), (3.0005, tf)]:
+            plan.propagate(a, b)
+        pieces = plan.get_state()[0]
+    assert np.max(np.abs(whole - pieces)) < 2e-9
+
+
+@pytest.mark.parametrize("n", [18, 20])
+def test_full_size_properties(engine, n):
+    """BASELINE-size properties: unitarity and step-size self-convergence."""
+    spec = W.config_c2(n=n, t_rise=100, t_sweep=200, t_fall=100)
+    tf = spec.sampling_times[-1]
+    outs = {}
+    with engine.DevicePlan(spec) as plan:
+        for K in (2, 4):
+            plan.set_state("all-ground")
+            plan.propagate(0.0, tf, max_step=K)
+            n2 = plan.norm2()[0]
+            assert abs(n2 - 1.0) < 1e-9
+            outs[K] = plan.get_state()[0]
+    assert np.max(np.abs(outs[2] - outs[4])) < STATE_TOL
