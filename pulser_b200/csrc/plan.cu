@@ -392,9 +392,11 @@ static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, do
 }
 
 // mark sampling intervals that must be stepped one by one
-static std::vector<char> fine_intervals(const Plan& P, int window, double rough_tol) {
+static std::vector<char> fine_intervals(const Plan& P, int window, double rough_tol, double jump_tol,
+                                        std::vector<char>& jump) {
     const int nt = (int)P.times.size();
     std::vector<char> rough(nt, 0);
+    jump.assign(std::max(nt - 1, 1), 0);
     auto scan = [&](auto const& pcs, const std::vector<double>& scales, auto absf) {
         for (size_t r = 0; r < pcs.size(); ++r) {
             const auto& pc = pcs[r];
@@ -407,6 +409,11 @@ static std::vector<char> fine_intervals(const Plan& P, int window, double rough_
                 auto d3 = y(i + 2) - 3.0 * y(i + 1) + 3.0 * y(i) - y(i - 1);
                 if (absf(d3) > rough_tol * sc) { rough[i] = 1; rough[i + 1] = 1; }
             }
+            // sample-to-sample jumps (pulse edges, the zero-padded last sample): the interval and its
+            // neighbours (spline overshoot) are sub-stepped
+            for (int i = 0; i + 1 < nt; ++i)
+                if (absf(y(i + 1) - y(i)) > jump_tol * sc)
+                    for (int j = std::max(0, i - 2); j <= std::min(nt - 2, i + 2); ++j) jump[j] = 1;
         }
     };
     for (int tr = 0; tr < P.B; ++tr)
@@ -441,7 +448,12 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
 
     pb200_run_stats st{};
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
-    const std::vector<char> fine = fine_intervals(P, W, rtol);
+    std::vector<char> jump;
+    const std::vector<char> fine0 = fine_intervals(P, W, rtol, 0.05, jump);
+    const double magnus_tol = 1e-11;
+    std::vector<char> fine_m = fine0;
+    for (size_t i = 0; i < fine_m.size(); ++i) if (jump[i]) fine_m[i] = 1;
+    const std::vector<char>& fine = fine_m;
     const int nt = (int)P.times.size();
 
     cudaEvent_t ev0, ev1;
@@ -472,6 +484,25 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         }
         b = std::min(b, t_stop);
         if (b <= t + eps) b = std::min(P.times[std::min(i + 1, nt - 1)], t_stop);
+        if (jump[i] && order == 4) {
+            // a-priori bound of the 4th-order Magnus remainder, (2 rho)^3 |B1| / 60, sets the number of
+            // sub-steps of this interval (error per sub-step scales as h^5)
+            moments_for_step(P, t, b, g0, g1, th0, th1);
+            ExpParams E; E.g = g0; E.th = th0; E.w = b - t;
+            double gm, rh; std::vector<double> scratch_tab;
+            build_tables(P, E, gm, rh, scratch_tab, P.dim == 2 && P.n_drives == 1);
+            double b1 = 0.0;
+            for (int tr = 0; tr < P.B; ++tr) {
+                double acc = 0.0;
+                for (int q = 0; q < P.n_drives; ++q)
+                    for (int k = 0; k < P.n; ++k) acc += std::abs(g1[pidx(P, tr, q, k)]) + std::fabs(th1[pidx(P, tr, q, k)]);
+                b1 = std::max(b1, acc);
+            }
+            const double est = 8.0 * rh * rh * rh * b1 / 60.0;
+            int nsub = (int)std::ceil(std::pow(std::max(est / magnus_tol, 1.0), 0.25));
+            nsub = std::min(std::max(nsub, 1), 32);
+            if (nsub > 1) b = std::min(b, t + (P.times[i + 1] - P.times[i]) / nsub);
+        }
         const double h = b - t;
         moments_for_step(P, t, b, g0, g1, th0, th1);
         const size_t cnt = g0.size();
