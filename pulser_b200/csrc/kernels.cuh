@@ -241,6 +241,200 @@ __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
     }
 }
 
+// ---- d = 2 tiled stage kernel, register-blocked (the production kernel) ------
+// Each thread owns R = 2^RB amplitudes of the tile (tile index t = tid + r*NT,
+// i.e. the top RB tile bits live in registers): flips of those bits are
+// register-to-register, flips of the other tile bits cost one LDS.128 per owned
+// amplitude, all independent (fully unrolled) so that the shared-memory pipe
+// stays full.  Shared-memory operand traffic per amplitude and pass is
+// (flipped tile bits - RB + 1) x 16 B.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+__global__ void __launch_bounds__(1 << (TBITS - RB), (TBITS >= 12 ? 1 : 2)) stage_d2_rb_kernel(StageArgs a) {
+    constexpr int R = 1 << RB;
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+
+    const PassGeom g = a.geo;
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y;
+    const long long tile_id = blockIdx.x;
+    const int mid_bits = g.hi_shift - g.lo_bits;
+    const long long mid = tile_id & ((1LL << mid_bits) - 1);
+    const long long top = tile_id >> mid_bits;
+    const long long base = (mid << g.lo_bits) | (top << (g.hi_shift + g.hi_bits));
+    const long long voff = traj * a.D;
+    const c2* vsrc = a.v + voff;
+
+    double* tab = reinterpret_cast<double*>(tile + TSIZE);
+    if (!UNIFORM) {
+        const int stride = d2_table_stride(g.n_bits);
+        const double* src = a.table + traj * stride;
+        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
+    }
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
+    {
+        const int rows = 1 << g.hi_bits;
+        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+        for (int r = tid; r < rows; r += NT)
+            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+    }
+    const long long lomask = (1LL << g.lo_bits) - 1;
+    const int to_bit = a.to_bit;
+    // first tile bit whose flip belongs to this pass (pass A: 0, later passes: lo_bits)
+    const int jstart = __ffs(g.tile_flip_mask) - 1;
+
+    mbar_wait(&mbar, 0);
+
+    c2 v[R];
+    double pr[R], pi[R], qr[R], qi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        v[r] = tile[tid + r * NT];
+        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
+    }
+    // --- flips inside the register block (tile bits TBITS-RB .. TBITS-1) ---
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+        const int j = TBITS - RB + q;
+        double gx = 0.0, gyt = 0.0;
+        if (!UNIFORM) {
+            const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+            gx = tab[2 * p]; gyt = tab[2 * p + 1];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const c2 pv = v[r ^ (1 << q)];
+            const int bit = (r >> q) & 1;
+            if (UNIFORM) {
+                pr[r] += pv.x; pi[r] += pv.y;
+                if (!REAL_G) {
+                    if (bit == to_bit) { qr[r] += pv.x; qi[r] += pv.y; } else { qr[r] -= pv.x; qi[r] -= pv.y; }
+                }
+            } else {
+                const double gy = (bit == to_bit) ? gyt : -gyt;
+                pr[r] = fma(gx, pv.x, pr[r]); pr[r] = fma(-gy, pv.y, pr[r]);
+                pi[r] = fma(gx, pv.y, pi[r]); pi[r] = fma(gy, pv.x, pi[r]);
+            }
+        }
+    }
+    // --- flips served from shared memory ---
+#pragma unroll
+    for (int j = 0; j < TBITS - RB; ++j) {
+        if (j >= jstart) {
+            const int bit = (tid >> j) & 1;
+            const int ptid = tid ^ (1 << j);
+            double gx = 0.0, gy = 0.0;
+            if (!UNIFORM) {
+                const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+                gx = tab[2 * p];
+                gy = (bit == to_bit) ? tab[2 * p + 1] : -tab[2 * p + 1];
+            }
+            const double sg = (bit == to_bit) ? 1.0 : -1.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const c2 pv = tile[ptid + r * NT];
+                if (UNIFORM) {
+                    pr[r] += pv.x; pi[r] += pv.y;
+                    if (!REAL_G) { qr[r] = fma(sg, pv.x, qr[r]); qi[r] = fma(sg, pv.y, qi[r]); }
+                } else {
+                    pr[r] = fma(gx, pv.x, pr[r]); pr[r] = fma(-gy, pv.y, pr[r]);
+                    pi[r] = fma(gx, pv.y, pi[r]); pi[r] = fma(gy, pv.x, pi[r]);
+                }
+            }
+        }
+    }
+    // global index of each owned amplitude
+    long long idx[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int t = tid + r * NT;
+        idx[r] = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
+    }
+    // --- flips served by coalesced global loads (bits outside the tile) ---
+    for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
+        const int p = __ffsll((long long)m) - 1;
+        double gx = 0.0, gyt = 0.0;
+        if (!UNIFORM) { gx = tab[2 * p]; gyt = tab[2 * p + 1]; }
+        const int bit = (int)((base >> p) & 1);  // extra bits are never tile bits
+        const double sg = (bit == to_bit) ? 1.0 : -1.0;
+        const double gy = (bit == to_bit) ? gyt : -gyt;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
+            if (UNIFORM) {
+                pr[r] += raw.x; pi[r] += raw.y;
+                if (!REAL_G) { qr[r] = fma(sg, raw.x, qr[r]); qi[r] = fma(sg, raw.y, qi[r]); }
+            } else {
+                pr[r] = fma(gx, raw.x, pr[r]); pr[r] = fma(-gy, raw.y, pr[r]);
+                pi[r] = fma(gx, raw.y, pi[r]); pi[r] = fma(gy, raw.x, pi[r]);
+            }
+        }
+    }
+    // --- epilogue ---
+    double w = 0.0, gamma = 0.0, th_common = 0.0;
+    double th_r[R];
+    if (g.first_pass) {
+        if (UNIFORM) { w = a.u.w; gamma = a.u.gamma; }
+        else {
+            w = tab[3 * g.n_bits]; gamma = tab[3 * g.n_bits + 1];
+            // theta sum split into (bits of base) + (bits of tid) + (register bits)
+            const long long fixed = base | (tid & lomask) | ((long long)(tid >> g.lo_bits) << g.hi_shift);
+            for (int p = 0; p < g.n_bits; ++p) {
+                const int bit = (int)((fixed >> p) & 1);
+                th_common += (bit == a.from_is_one) ? tab[2 * g.n_bits + p] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int j = TBITS - RB + q;
+                    const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+                    // `fixed` has these bits at 0: replace the bit-0 contribution by the bit-(r>>q) one
+                    const double th = tab[2 * g.n_bits + p];
+                    const int bit = (r >> q) & 1;
+                    acc += ((bit == a.from_is_one) ? th : 0.0) - ((0 == a.from_is_one) ? th : 0.0);
+                }
+                th_r[r] = acc;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        c2 drive;
+        if (UNIFORM) {
+            drive.x = a.u.g.x * pr[r]; drive.y = a.u.g.x * pi[r];
+            if (!REAL_G) { drive.x = fma(-a.u.g.y, qi[r], drive.x); drive.y = fma(a.u.g.y, qr[r], drive.y); }
+        } else {
+            drive = {pr[r], pi[r]};
+        }
+        c2 res;
+        if (g.first_pass) {
+            double diag = -gamma;
+            if (a.dint) diag = fma(w, __ldcs(a.dint + traj * a.dint_stride + idx[r]), diag);
+            if (UNIFORM) {
+                const int ones = __popcll((unsigned long long)idx[r]);
+                const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
+                diag = fma(-a.u.theta, (double)cnt, diag);
+            } else {
+                diag -= th_common + th_r[r];
+            }
+            c2 gv = {fma(diag, v[r].x, drive.x), fma(diag, v[r].y, drive.y)};
+            res = cmul(a.coef.c_g, gv);
+            if (a.psi) res = cadd(res, cmul(a.coef.c_psi, ld_stream(a.psi + voff + idx[r])));
+            if (a.b2) res = cadd(res, cmul(a.coef.c_b2, ld_stream(a.b2 + voff + idx[r])));
+        } else {
+            res = cadd(ld_stream(a.out + voff + idx[r]), cmul(a.coef.c_g, drive));
+        }
+        st_c2(a.out + voff + idx[r], res);
+    }
+}
+
 // ---- generic-d stage kernel (any dim, several drives; global gathers) -------
 // table per (exponential, trajectory):
 //   for each drive q: g[q][k] (re,im) per QUDIT k, theta[q][k]; then w, gamma

@@ -89,6 +89,7 @@ struct Plan {
     int tile_bits = 12;
     int max_extra = 3;
     int sm_count = 148;
+    bool force_v1 = false;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -172,14 +173,33 @@ static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2*
             const int tbits = geo.lo_bits + geo.hi_bits;
             const long long tiles = P.D >> tbits;
             const int tsize = 1 << tbits;
-            int threads = std::min(256, std::max(32, tsize));
-            size_t smem = (size_t)tsize * 16 + (uniform ? 0 : (size_t)d2_table_stride(N) * 8);
+            const size_t tab_bytes = uniform ? 0 : (size_t)d2_table_stride(N) * 8;
             dim3 grid((unsigned)tiles, (unsigned)P.B);
-            if (uniform) {
-                if (real_g) stage_d2_kernel<true, true><<<grid, threads, smem, P.stream>>>(a);
-                else stage_d2_kernel<true, false><<<grid, threads, smem, P.stream>>>(a);
+            constexpr int RB = 3;
+            const bool rb_ok = (tbits == 11 || tbits == 12) && (geo.first_pass || geo.hi_bits >= RB) && !P.force_v1;
+            if (rb_ok) {
+                const size_t smem = (size_t)tsize * 16 + tab_bytes;
+                const int threads = tsize >> RB;
+#define PB200_LAUNCH_RB(TB)                                                                              \
+    do {                                                                                                 \
+        if (uniform) {                                                                                   \
+            if (real_g) stage_d2_rb_kernel<true, true, TB, RB><<<grid, threads, smem, P.stream>>>(a);    \
+            else stage_d2_rb_kernel<true, false, TB, RB><<<grid, threads, smem, P.stream>>>(a);          \
+        } else {                                                                                         \
+            stage_d2_rb_kernel<false, false, TB, RB><<<grid, threads, smem, P.stream>>>(a);              \
+        }                                                                                                \
+    } while (0)
+                if (tbits == 11) PB200_LAUNCH_RB(11); else PB200_LAUNCH_RB(12);
+#undef PB200_LAUNCH_RB
             } else {
-                stage_d2_kernel<false, false><<<grid, threads, smem, P.stream>>>(a);
+                int threads = std::min(256, std::max(32, tsize));
+                size_t smem = (size_t)tsize * 16 + tab_bytes;
+                if (uniform) {
+                    if (real_g) stage_d2_kernel<true, true><<<grid, threads, smem, P.stream>>>(a);
+                    else stage_d2_kernel<true, false><<<grid, threads, smem, P.stream>>>(a);
+                } else {
+                    stage_d2_kernel<false, false><<<grid, threads, smem, P.stream>>>(a);
+                }
             }
             ++launches;
         }
@@ -670,8 +690,9 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     long long D = 1;
     for (int i = 0; i < P.n; ++i) D *= P.dim;
     P.D = D;
-    P.tile_bits = std::min(13, std::max(2, env_int("PB200_TILE_BITS", 12)));
+    P.tile_bits = std::min(13, std::max(2, env_int("PB200_TILE_BITS", 11)));
     P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 3));
+    P.force_v1 = env_int("PB200_FORCE_V1", 0) != 0;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;
@@ -685,6 +706,12 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     } catch (...) {
         pb200_plan_destroy(h);
         throw;

@@ -75,7 +75,7 @@ def test_c1_four_atom_square(engine):
         got = plan.get_state()[0]
     assert st["n_applies"] > 0 and st["n_launches"] > 0
     assert np.max(np.abs(got - ref)) < STATE_TOL
-    assert abs(np.linalg.norm(got) - 1.0) < 1e-10
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-9
 
 
 @pytest.mark.parametrize("n,max_step", [(6, 1), (8, 4), (10, 4)])
