@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
 // stays full.  Shared-memory operand traffic per amplitude and pass is
 // (flipped tile bits - RB + 1) x 16 B.
 template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
-__global__ void __launch_bounds__(1 << (TBITS - RB), (TBITS >= 12 ? 1 : 2)) stage_d2_rb_kernel(StageArgs a) {
+__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
+stage_d2_rb_kernel(StageArgs a) {
     constexpr int R = 1 << RB;
     constexpr int NT = 1 << (TBITS - RB);
     constexpr int TSIZE = 1 << TBITS;
@@ -404,34 +405,60 @@ __global__ void __launch_bounds__(1 << (TBITS - RB), (TBITS >= 12 ? 1 : 2)) stag
             }
         }
     }
+    // drive term of every owned amplitude (frees the P/Q accumulators)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        c2 drive;
         if (UNIFORM) {
-            drive.x = a.u.g.x * pr[r]; drive.y = a.u.g.x * pi[r];
-            if (!REAL_G) { drive.x = fma(-a.u.g.y, qi[r], drive.x); drive.y = fma(a.u.g.y, qr[r], drive.y); }
-        } else {
-            drive = {pr[r], pi[r]};
+            const double dx = a.u.g.x * pr[r], dy = a.u.g.x * pi[r];
+            if (!REAL_G) { pr[r] = fma(-a.u.g.y, qi[r], dx); pi[r] = fma(a.u.g.y, qr[r], dy); }
+            else { pr[r] = dx; pi[r] = dy; }
         }
-        c2 res;
-        if (g.first_pass) {
-            double diag = -gamma;
-            if (a.dint) diag = fma(w, __ldcs(a.dint + traj * a.dint_stride + idx[r]), diag);
-            if (UNIFORM) {
-                const int ones = __popcll((unsigned long long)idx[r]);
-                const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
-                diag = fma(-a.u.theta, (double)cnt, diag);
-            } else {
-                diag -= th_common + th_r[r];
+    }
+    // own-element global operands are staged in registers half a block at a time so that the loads
+    // of one half are all in flight together (the stores to `out` may alias them for the compiler)
+    constexpr int H = (R >= 4) ? R / 2 : R;
+    if (g.first_pass) {
+        const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
+#pragma unroll
+        for (int h0 = 0; h0 < R; h0 += H) {
+            double dv[H];
+            c2 pv[H], bv[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                dv[r] = dsrc ? __ldcs(dsrc + idx[h0 + r]) : 0.0;
+                pv[r] = a.psi ? ld_stream(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                bv[r] = a.b2 ? ld_stream(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
             }
-            c2 gv = {fma(diag, v[r].x, drive.x), fma(diag, v[r].y, drive.y)};
-            res = cmul(a.coef.c_g, gv);
-            if (a.psi) res = cadd(res, cmul(a.coef.c_psi, ld_stream(a.psi + voff + idx[r])));
-            if (a.b2) res = cadd(res, cmul(a.coef.c_b2, ld_stream(a.b2 + voff + idx[r])));
-        } else {
-            res = cadd(ld_stream(a.out + voff + idx[r]), cmul(a.coef.c_g, drive));
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                const int rr = h0 + r;
+                double diag = fma(w, dv[r], -gamma);
+                if (UNIFORM) {
+                    const int ones = __popcll((unsigned long long)idx[rr]);
+                    const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
+                    diag = fma(-a.u.theta, (double)cnt, diag);
+                } else {
+                    diag -= th_common + th_r[rr];
+                }
+                const c2 gv = {fma(diag, v[rr].x, pr[rr]), fma(diag, v[rr].y, pi[rr])};
+                c2 res = cmul(a.coef.c_g, gv);
+                res = cadd(res, cmul(a.coef.c_psi, pv[r]));
+                res = cadd(res, cmul(a.coef.c_b2, bv[r]));
+                st_c2(a.out + voff + idx[rr], res);
+            }
         }
-        st_c2(a.out + voff + idx[r], res);
+    } else {
+#pragma unroll
+        for (int h0 = 0; h0 < R; h0 += H) {
+            c2 ov[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) ov[r] = ld_stream(a.out + voff + idx[h0 + r]);
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                const int rr = h0 + r;
+                st_c2(a.out + voff + idx[rr], cadd(ov[r], cmul(a.coef.c_g, c2{pr[rr], pi[rr]})));
+            }
+        }
     }
 }
 

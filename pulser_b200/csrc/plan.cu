@@ -90,6 +90,7 @@ struct Plan {
     int max_extra = 3;
     int sm_count = 148;
     bool force_v1 = false;
+    int reg_bits = 3;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -175,12 +176,12 @@ static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2*
             const int tsize = 1 << tbits;
             const size_t tab_bytes = uniform ? 0 : (size_t)d2_table_stride(N) * 8;
             dim3 grid((unsigned)tiles, (unsigned)P.B);
-            constexpr int RB = 3;
-            const bool rb_ok = (tbits == 11 || tbits == 12) && (geo.first_pass || geo.hi_bits >= RB) && !P.force_v1;
+            const int RBv = P.reg_bits;
+            const bool rb_ok = (tbits == 11 || tbits == 12) && (geo.first_pass || geo.hi_bits >= RBv) && !P.force_v1;
             if (rb_ok) {
                 const size_t smem = (size_t)tsize * 16 + tab_bytes;
-                const int threads = tsize >> RB;
-#define PB200_LAUNCH_RB(TB)                                                                              \
+                const int threads = tsize >> RBv;
+#define PB200_LAUNCH_RB(TB, RB)                                                                            \
     do {                                                                                                 \
         if (uniform) {                                                                                   \
             if (real_g) stage_d2_rb_kernel<true, true, TB, RB><<<grid, threads, smem, P.stream>>>(a);    \
@@ -189,7 +190,8 @@ static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2*
             stage_d2_rb_kernel<false, false, TB, RB><<<grid, threads, smem, P.stream>>>(a);              \
         }                                                                                                \
     } while (0)
-                if (tbits == 11) PB200_LAUNCH_RB(11); else PB200_LAUNCH_RB(12);
+                if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_RB(11, 3); else PB200_LAUNCH_RB(11, 2); }
+                else { if (RBv == 3) PB200_LAUNCH_RB(12, 3); else PB200_LAUNCH_RB(12, 2); }
 #undef PB200_LAUNCH_RB
             } else {
                 int threads = std::min(256, std::max(32, tsize));
@@ -693,6 +695,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.tile_bits = std::min(13, std::max(2, env_int("PB200_TILE_BITS", 11)));
     P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 3));
     P.force_v1 = env_int("PB200_FORCE_V1", 0) != 0;
+    P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;
@@ -706,12 +709,18 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     } catch (...) {
         pb200_plan_destroy(h);
         throw;
