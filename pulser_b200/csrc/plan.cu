@@ -693,7 +693,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     for (int i = 0; i < P.n; ++i) D *= P.dim;
     P.D = D;
     P.tile_bits = std::min(13, std::max(2, env_int("PB200_TILE_BITS", 11)));
-    P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 3));
+    P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 16));
     P.force_v1 = env_int("PB200_FORCE_V1", 0) != 0;
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
     cudaDeviceProp prop;

@@ -31,7 +31,7 @@ def _oracle_final(spec, psi0, t_end=None, order=3):
     return evolve.sesolve(H, psi0, [0.0, t_end], order=order, rtol=1e-13, atol=1e-15)[-1]
 
 
-@pytest.mark.parametrize("n", [1, 2, 4, 7, 10, 12, 13, 15, 16])
+@pytest.mark.parametrize("n", [1, 2, 4, 7, 10, 11, 12, 13, 15, 16])
 def test_apply_h_uniform(engine, n):
     """H(t) psi on the device == matrix-free oracle (global drive)."""
     from oracle.matfree import MatFreeHamiltonian
@@ -47,7 +47,7 @@ def test_apply_h_uniform(engine, n):
             assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
 
 
-@pytest.mark.parametrize("n", [3, 6, 11, 14, 16])
+@pytest.mark.parametrize("n", [3, 6, 11, 12, 14, 16])
 def test_apply_h_local_complex(engine, n):
     """Per-qubit complex drives (noisy-trajectory shape)."""
     from oracle.matfree import MatFreeHamiltonian
@@ -114,11 +114,11 @@ def test_batch_of_trajectories(engine):
     for s in specs:
         with engine.DevicePlan(s) as plan:
             plan.set_state(psi0)
-            plan.propagate(0.0, s.sampling_times[-1])
+            plan.propagate(0.0, s.sampling_times[-1], max_step=2)
             singles.append(plan.get_state()[0])
     with engine.DevicePlan(specs) as plan:
         plan.set_state(psi0)
-        plan.propagate(0.0, specs[0].sampling_times[-1])
+        plan.propagate(0.0, specs[0].sampling_times[-1], max_step=2)
         got = plan.get_state()
     for a, b in zip(got, singles):
         assert np.max(np.abs(a - b)) < 1e-11
@@ -155,3 +155,20 @@ def test_full_size_properties(engine, n):
             assert abs(n2 - 1.0) < 1e-9
             outs[K] = plan.get_state()[0]
     assert np.max(np.abs(outs[2] - outs[4])) < STATE_TOL
+
+
+@pytest.mark.parametrize("tile_bits,max_extra,reg_bits", [(11, 0, 3), (11, 2, 2), (12, 0, 3), (12, 3, 2), (11, 16, 3)])
+def test_pass_geometries(engine, monkeypatch, tile_bits, max_extra, reg_bits):
+    """Every tile / pass decomposition gives the same H psi (uniform and local drives)."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    monkeypatch.setenv("PB200_TILE_BITS", str(tile_bits))
+    monkeypatch.setenv("PB200_MAX_EXTRA", str(max_extra))
+    monkeypatch.setenv("PB200_REG_BITS", str(reg_bits))
+    for spec in (W.config_c2(n=17, seed=2), random_local_spec(16, T=32, seed=5)):
+        mf = MatFreeHamiltonian(spec)
+        v = random_state(spec.hilbert_dim, 4)
+        with engine.DevicePlan(spec) as plan:
+            got = plan.apply_h(0.0123, v)
+        ref = mf.apply(0.0123, v)
+        assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
