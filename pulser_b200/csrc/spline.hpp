@@ -22,6 +22,7 @@ template <typename T>
 struct PiecewiseCubic {
     // piece i on [x[i], x[i+1]]: c0 + c1*tau + c2*tau^2 + c3*tau^3
     std::vector<T> c0, c1, c2, c3;
+    T y_last = T(0);  // last sample (needed by the order-0 rule at the end point)
 
     int pieces() const { return (int)c0.size(); }
 
@@ -53,6 +54,7 @@ PiecewiseCubic<T> make_interpolant(const double* x, const T* y, int n, int order
     int np = n - 1;
     pc.c0.resize(np); pc.c1.assign(np, T(0)); pc.c2.assign(np, T(0)); pc.c3.assign(np, T(0));
     for (int i = 0; i < np; ++i) pc.c0[i] = y[i];
+    pc.y_last = y[n - 1];
     if (order == 0 || n < 2) return pc;
     if (order == 1 || n < 4) {
         for (int i = 0; i < np; ++i) pc.c1[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
@@ -120,7 +122,7 @@ template <typename T>
 T eval_at(const PiecewiseCubic<T>& pc, const std::vector<double>& x, double t, int order) {
     t = std::min(std::max(t, x.front()), x.back());
     int i = find_piece(x, t);
-    if (order == 0 && t >= x.back()) return pc.c0.back();  // last sample holds only at the end point
+    if (order == 0 && t >= x.back()) return pc.y_last;  // the last sample holds only at the end point
     return pc.eval_piece(i, t - x[i]);
 }
 

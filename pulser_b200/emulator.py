@@ -1,0 +1,547 @@
+"""``B200Emulator``: the ``QutipEmulator`` surface on top of the CUDA path.
+
+Drop-in for ``pulser_simulation.QutipEmulator``
+(reference ``pulser-simulation/pulser_simulation/simulation.py:84-1051``):
+same constructor / ``from_sequence`` / ``run`` / ``set_initial_state`` /
+``set_evaluation_times`` / ``get_hamiltonian`` / properties, same validation
+messages, same evaluation-time and trajectory semantics.  Everything upstream
+of the Hamiltonian (sampling, noise trajectories, interaction matrix) is the
+reference's own pulser-core code; ``Hamiltonian(...)`` construction
+(``simulation.py:299-311``) and ``_run_solver`` (``:689-766``) are replaced by
+``HamiltonianSpec`` -> ``DevicePlan`` -> ``pb200_propagate``.
+
+Not yet on the CUDA path (raise ``NotImplementedError``): collapse operators
+(mesolve / mcsolve, ``simulation.py:705-735``) and the XY interaction.
+"""
+from __future__ import annotations
+
+import warnings
+from collections import Counter
+from enum import Enum
+from typing import Any, Iterator, Optional, Union
+
+import numpy as np
+
+from ._compat import ensure_pulser
+from .results import B200Result, CoherentResults, NoisyResults, SampledCounts, StateVector
+from .spec import HamiltonianSpec, spec_from_pulser
+
+if not ensure_pulser():  # pragma: no cover
+    raise ImportError(
+        "pulser_b200.emulator needs pulser-core (set PULSER_B200_PULSER_PATH or "
+        "install pulser-core); the plain-array path is pulser_b200.engine."
+    )
+
+import pulser.sampler as sampler  # noqa: E402
+from pulser import Sequence  # noqa: E402
+from pulser._hamiltonian_data import (  # noqa: E402
+    HamiltonianData,
+    has_shot_to_shot_except_spam,
+)
+from pulser.devices._device_datacls import BaseDevice  # noqa: E402
+from pulser.noise_model import NoiseModel  # noqa: E402
+from pulser.register.base_register import BaseRegister  # noqa: E402
+from pulser.sampler.samples import ChannelSamples, SequenceSamples  # noqa: E402
+
+
+def _has_stochastic_noise(noise_model: NoiseModel) -> bool:
+    """simulation.py:61-64."""
+    return has_shot_to_shot_except_spam(noise_model) or (
+        "SPAM" in noise_model.noise_types and noise_model.state_prep_error != 0
+    )
+
+
+class Solver(str, Enum):
+    """simulation.py:67-81 (kept for signature compatibility)."""
+
+    DEFAULT = "default"
+    MESOLVER = "MasterEquation"
+    MCSOLVER = "MonteCarlo"
+
+
+# QuTiP solver options the reference forwards (simulation.py:800-845); they
+# have no meaning for the fixed-order propagator and are accepted and ignored.
+_QUTIP_OPTIONS = {
+    "max_step", "nsteps", "atol", "rtol", "method", "order", "min_step",
+    "first_step", "store_states", "store_final_state", "normalize_output",
+    "progress_kwargs", "keep_runs_results", "map", "num_cpus", "timeout",
+    "norm_steps", "norm_t_tol", "norm_tol", "mc_corr_eps", "improved_sampling",
+}
+# options of this backend
+_B200_OPTIONS = {"b200_max_step", "b200_cheb_tol", "b200_refine_window", "b200_batch"}
+
+
+class B200Emulator:
+    r"""Emulator of a pulse sequence on a B200 GPU.
+
+    Args: identical to ``QutipEmulator`` (simulation.py:84-141), plus
+        ``interp_order`` (QobjEvo coefficient interpolation order, 3 = QuTiP 5
+        default) and ``gpu`` (CUDA device ordinal).
+    """
+
+    def __init__(
+        self,
+        sampled_seq: SequenceSamples,
+        register: BaseRegister,
+        device: BaseDevice,
+        sampling_rate: float = 1.0,
+        config: Any = None,
+        evaluation_times: Union[float, str, Any] = "Full",
+        noise_model: NoiseModel | None = None,
+        solver: Solver = Solver.DEFAULT,
+        n_trajectories: int | None = None,
+        *,
+        interp_order: int = 3,
+        gpu: int = 0,
+    ) -> None:
+        if not isinstance(sampled_seq, SequenceSamples):
+            raise TypeError(
+                "The provided sequence has to be a valid "
+                "SequenceSamples instance."
+            )
+        if sampled_seq.max_duration == 0:
+            raise ValueError("SequenceSamples is empty.")
+        self._sampling_rate = sampling_rate
+        device.validate_register(register)
+        self._register = register
+        self.solver = Solver(solver)
+        if sampled_seq._slm_mask.end > 0 and not device.supports_slm_mask:
+            raise ValueError("Samples use SLM mask but device does not have one.")
+        if not sampled_seq.used_bases <= device.supported_bases:
+            raise ValueError("Bases used in samples should be supported by device.")
+        if not sampled_seq._slm_mask.targets <= set(register.qubit_ids):
+            raise ValueError(
+                "The ids of qubits targeted in SLM mask"
+                " should be defined in register."
+            )
+        self._tot_duration = sampled_seq.max_duration
+        self.samples_obj = sampled_seq.extend_duration(self._tot_duration + 1)
+        self._n_trajectories = n_trajectories
+        if not (0 < sampling_rate <= 1.0):
+            raise ValueError(
+                "The sampling rate (`sampling_rate` = "
+                f"{sampling_rate}) must be greater than 0 and "
+                "less than or equal to 1."
+            )
+        if int(self._tot_duration * sampling_rate) < 4:
+            raise ValueError("`sampling_rate` is too small, less than 4 data points.")
+        if noise_model is not None and config is not None:
+            raise ValueError(
+                "'noise_model' and 'config' cannot both be provided to "
+                "'QutipEmulator'. Please provide just a 'noise_model'."
+            )
+        if config is not None:
+            warnings.warn(
+                "Supplying a 'SimConfig' to QutipEmulator has been "
+                "deprecated. Please instantiate with a 'NoiseModel' "
+                "instead.",
+                DeprecationWarning,
+                stacklevel=2,
+            )
+            noise_model = config.to_noise_model()
+        if not noise_model:
+            noise_model = NoiseModel()
+        self._interp_order = interp_order
+        self._gpu = gpu
+        self._noise_trajectories_used = False
+        self._hamiltonian_data = HamiltonianData(
+            self.samples_obj,
+            register,
+            device,
+            noise_model,
+            self._get_n_trajectories(noise_model, check_value=True),
+        )
+        self._current_spec = next(self._specs)[0]
+        self._noiseless_cache: dict[bool, HamiltonianSpec] = {}
+        self._eval_times_array: np.ndarray
+        self.set_evaluation_times(evaluation_times)
+        if self.samples_obj._measurement:
+            self._meas_basis = self.samples_obj._measurement
+        else:
+            if "all" in self.basis_name:
+                self._meas_basis = "digital"
+            else:
+                self._meas_basis = self.basis_name.replace("_with_error", "")
+        self.set_initial_state("all-ground")
+        self.last_run_stats: dict = {}
+
+    # ------------------------------------------------------------------
+    def _get_n_trajectories(self, noise_model: NoiseModel, check_value: bool) -> int | None:
+        n_trajectories = (
+            self._n_trajectories if self._n_trajectories is not None else noise_model.runs
+        )
+        if check_value and _has_stochastic_noise(noise_model) and n_trajectories is None:
+            raise ValueError(
+                "'n_trajectories' must be defined when the NoiseModel contains"
+                " stochastic noise, which is the case for the given noise "
+                f"model: {noise_model!r}"
+            )
+        return n_trajectories
+
+    @property
+    def n_trajectories(self) -> int | None:
+        return self._get_n_trajectories(self.noise_model, check_value=False)
+
+    @property
+    def device(self) -> BaseDevice:
+        return self._hamiltonian_data.device
+
+    def _spec_of(self, hd: HamiltonianData, traj: Any, noisy_samples: Any) -> HamiltonianSpec:
+        return spec_from_pulser(
+            noisy_samples, traj, hd.basis_data, hd.lindblad_data,
+            self._sampling_rate, self._tot_duration,
+        )
+
+    @property
+    def _specs(self) -> Iterator[tuple[HamiltonianSpec, int]]:
+        """One spec per noise trajectory (replaces ``_hamiltonians``, :299-311)."""
+        hd = self._hamiltonian_data
+        for traj, noisy_samples, reps in hd.noisy_samples:
+            yield self._spec_of(hd, traj, noisy_samples), reps
+
+    def _noiseless_spec(self) -> HamiltonianSpec:
+        if False not in self._noiseless_cache:
+            hd = HamiltonianData(
+                self.samples_obj, self._register, self.device, NoiseModel(), n_trajectories=1
+            )
+            self._noiseless_cache[False] = self._spec_of(
+                hd, hd.noise_trajectories[0].trajectory, hd.samples
+            )
+        return self._noiseless_cache[False]
+
+    @property
+    def sampling_times(self) -> np.ndarray:
+        return self._noiseless_spec().sampling_times
+
+    @property
+    def dim(self) -> int:
+        return self._hamiltonian_data.basis_data.dim
+
+    @property
+    def basis_name(self) -> str:
+        return self._hamiltonian_data.basis_data.basis_name
+
+    @property
+    def basis(self) -> dict[str, StateVector]:
+        eig = self._hamiltonian_data.basis_data.eigenbasis
+        return {s: StateVector(np.eye(len(eig))[i]) for i, s in enumerate(eig)}
+
+    @property
+    def noise_model(self) -> NoiseModel:
+        return self._hamiltonian_data.noise_model
+
+    @property
+    def total_duration_ns(self) -> int:
+        return self._tot_duration
+
+    # ------------------------------------------------------------------
+    @property
+    def initial_state(self) -> StateVector:
+        return self._initial_state
+
+    def _all_ground(self) -> StateVector:
+        hd = self._hamiltonian_data
+        eig = hd.basis_data.eigenbasis
+        g = eig.index("u" if hd.basis_data.interaction_type == "XY" else "g")
+        d, n = hd.basis_data.dim, hd.n_qudits
+        idx = 0
+        for _ in range(n):
+            idx = idx * d + g
+        psi = np.zeros(d**n, dtype=complex)
+        psi[idx] = 1.0
+        return StateVector(psi, [[d] * n, [1] * n])
+
+    def set_initial_state(self, state: Union[str, np.ndarray, Any]) -> None:
+        """simulation.py:484-525."""
+        hd = self._hamiltonian_data
+        if isinstance(state, str) and state == "all-ground":
+            self._initial_state = self._all_ground()
+            self._initial_is_ground = True
+            return
+        arr = state.full() if hasattr(state, "full") else np.asarray(state)
+        shape = arr.shape[0]
+        legal_shape = hd.basis_data.dim**hd.n_qudits
+        if shape != legal_shape:
+            raise ValueError(
+                "Incompatible shape of initial state."
+                + f"Expected {legal_shape}, got {shape}."
+            )
+        d, n = hd.basis_data.dim, hd.n_qudits
+        self._initial_state = StateVector(arr.reshape(-1), [[d] * n, [1] * n]).unit()
+        self._initial_is_ground = self._initial_state == self._all_ground()
+
+    @property
+    def evaluation_times(self) -> np.ndarray:
+        return np.array(self._eval_times_array)
+
+    def set_evaluation_times(self, value: Union[str, Any, float]) -> None:
+        """simulation.py:532-599."""
+        times = self.sampling_times
+        if isinstance(value, str):
+            if value == "Full":
+                eval_times = np.copy(times)
+            elif value == "Minimal":
+                eval_times = np.array([])
+            else:
+                raise ValueError(
+                    "Wrong evaluation time label. It should "
+                    "be `Full`, `Minimal`, an array of times or"
+                    + " a float between 0 and 1."
+                )
+        elif isinstance(value, float):
+            if value > 1 or value <= 0:
+                raise ValueError("evaluation_times float must be between 0 and 1.")
+            indices = np.linspace(0, len(times) - 1, int(value * len(times)), dtype=int)
+            eval_times = times[indices]
+        elif isinstance(value, (list, tuple, np.ndarray)):
+            if np.max(value, initial=0) > self._tot_duration * 1e-3:
+                raise ValueError(
+                    "Provided evaluation-time list extends "
+                    "further than sequence duration."
+                )
+            if np.min(value, initial=0) < 0:
+                raise ValueError(
+                    "Provided evaluation-time list contains negative values."
+                )
+            eval_times = np.array(value)
+        else:
+            raise ValueError(
+                "Wrong evaluation time label. It should "
+                "be `Full`, `Minimal`, an array of times or a "
+                + "float between 0 and 1."
+            )
+        self._eval_times_array = np.union1d(eval_times, [0.0, self._tot_duration * 1e-3])
+        self._eval_times_instruction = value
+
+    # ------------------------------------------------------------------
+    def get_hamiltonian(self, time: float, noiseless: bool = False) -> np.ndarray:
+        """Dense H(t) in rad/us (simulation.py:625-661); small systems only.
+
+        Built on the device by applying H(t) to the basis vectors (``pb200_apply_h``).
+        """
+        if time > self._tot_duration:
+            raise ValueError(
+                f"Provided time (`time` = {time}) must be "
+                "less than or equal to the sequence duration "
+                f"({self._tot_duration})."
+            )
+        if time < 0:
+            raise ValueError(
+                f"Provided time (`time` = {time}) must be "
+                "greater than or equal to 0."
+            )
+        from .engine import DevicePlan
+
+        spec = self._noiseless_spec() if noiseless else self._current_spec
+        D = spec.hilbert_dim
+        if D > 4096:
+            raise ValueError("get_hamiltonian: dense matrix limited to 4096 states")
+        H = np.zeros((D, D), dtype=complex)
+        with DevicePlan(spec, self._interp_order, self._gpu) as plan:
+            eye = np.eye(D, dtype=complex)
+            for j in range(D):
+                H[:, j] = plan.apply_h(time / 1000, eye[j])
+        return H
+
+    @staticmethod
+    def _get_min_variation(ch_sample: ChannelSamples) -> int:
+        """simulation.py:663-687 (only used to report ``max_step``)."""
+        end_point = ch_sample.duration - 1
+        mv = []
+        for sample in (ch_sample.amp.as_array(detach=True), ch_sample.det.as_array(detach=True)):
+            mv.append(
+                int(np.min(np.diff(np.nonzero(np.diff(sample)), prepend=-1, append=end_point)))
+            )
+        return min(mv)
+
+    # ------------------------------------------------------------------
+    def _check_supported(self) -> None:
+        if len(self._hamiltonian_data.lindblad_data.local_collapse_ops) > 0:
+            raise NotImplementedError(
+                "Collapse operators (dephasing / relaxation / depolarizing / "
+                "eff_noise -> mesolve / mcsolve) are not on the CUDA path yet."
+            )
+
+    def _validate_options(self, options: dict) -> dict:
+        unknown = set(options) - _QUTIP_OPTIONS - _B200_OPTIONS
+        if unknown:
+            raise TypeError(f"Unknown solver options: {sorted(unknown)}")
+        if "SPAM" in self.noise_model.noise_types:
+            if self.noise_model.state_prep_error > 0 and not self._initial_is_ground:
+                raise NotImplementedError(
+                    "Can't combine state preparation errors with an initial "
+                    "state different from the ground."
+                )
+        return {
+            "max_step": int(options.get("b200_max_step", 0)),
+            "cheb_tol": float(options.get("b200_cheb_tol", 0.0)),
+            "refine_window": int(options.get("b200_refine_window", -1)),
+        }
+
+    def _run_batch(self, specs: list[HamiltonianSpec], opts: dict) -> list[list[np.ndarray]]:
+        """States [n_eval][n_traj, D] of a batch of trajectories (replaces
+        ``_run_solver``'s ``qutip.sesolve`` call, simulation.py:729-735)."""
+        from .engine import DevicePlan
+
+        times = self._eval_times_array
+        out = []
+        stats: dict = {}
+        with DevicePlan(specs, self._interp_order, self._gpu) as plan:
+            plan.set_state(self._initial_state.full().reshape(-1))
+            out.append(plan.get_state())
+            for t0, t1 in zip(times[:-1], times[1:]):
+                st = plan.propagate(t0, t1, **opts)
+                for k, v in st.items():
+                    stats[k] = max(stats.get(k, 0), v) if k == "max_rho" else stats.get(k, 0) + v
+                out.append(plan.get_state())
+        self.last_run_stats = stats
+        return out
+
+    def _wrap(self, states: list[np.ndarray]) -> CoherentResults:
+        hd = self._hamiltonian_data
+        d, n = hd.basis_data.dim, hd.n_qudits
+        results = [
+            B200Result(
+                tuple(hd.register.qubits),
+                self._meas_basis,
+                StateVector(s, [[d] * n, [1] * n]),
+                self._meas_basis in self.basis_name,
+                evaluation_time=t / (self._tot_duration * 1e-3),
+            )
+            for s, t in zip(states, self._eval_times_array)
+        ]
+        meas_errors = (
+            {
+                "epsilon": self.noise_model.p_false_pos,
+                "epsilon_prime": self.noise_model.p_false_neg,
+            }
+            if "SPAM" in self.noise_model.noise_types
+            else None
+        )
+        return CoherentResults(
+            results, n, self.basis_name, self._eval_times_array, self._meas_basis, meas_errors
+        )
+
+    def run(self, progress_bar: bool = False, print_progress: bool = False, **options: Any):
+        """Simulate the sequence (simulation.py:800-883).
+
+        Returns ``CoherentResults``, or ``NoisyResults`` when the noise model
+        has stochastic noise.
+        """
+        if progress_bar not in (True, False, None):
+            raise ValueError("`progress_bar` must be a bool.")
+        opts = self._validate_options(options)
+        self._check_supported()
+        if not _has_stochastic_noise(self.noise_model):
+            if print_progress:
+                print("Emulating Trajectory 1/1")
+            states = self._run_batch([self._current_spec], opts)
+            return self._wrap([s[0] for s in states])
+
+        total_count = np.array([Counter() for _ in self._eval_times_array])
+        for cleanres, reps in self._noisy_runs(
+            print_progress=print_progress, batch=int(options.get("b200_batch", 0)), opts=opts
+        ):
+            total_count += np.array(
+                [
+                    cleanres.sample_state(t, n_samples=self.noise_model.samples_per_run * reps)
+                    for t in self._eval_times_array
+                ]
+            )
+        n_measures = int(self.n_trajectories) * self.noise_model.samples_per_run
+        hd = self._hamiltonian_data
+        results = [
+            SampledCounts(
+                tuple(hd.register.qubits), self._meas_basis, total_count[ind],
+                evaluation_time=t / (self._tot_duration * 1e-3),
+            )
+            for ind, t in enumerate(self._eval_times_array)
+        ]
+        return NoisyResults(
+            results, hd.n_qudits, self.basis_name, self._eval_times_array, n_measures
+        )
+
+    def _noisy_runs(self, print_progress: bool, batch: int, opts: dict):
+        """simulation.py:885-915, trajectories evolved in device batches."""
+        n_trajectories = self.n_trajectories
+        if self._noise_trajectories_used:
+            nm = self._hamiltonian_data.noise_model
+            self._hamiltonian_data = HamiltonianData(
+                self.samples_obj, self._register, self.device, nm,
+                self._get_n_trajectories(nm, check_value=True),
+            )
+        self._noise_trajectories_used = True
+        pending = list(self._specs)
+        if not pending:
+            return
+        D = pending[0][0].hilbert_dim
+        if batch <= 0:
+            # bound device memory: 3 state buffers + (maybe) per-trajectory Dint
+            batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
+        traj_nb = 0
+        for b0 in range(0, len(pending), batch):
+            chunk = pending[b0 : b0 + batch]
+            states = self._run_batch([s for s, _ in chunk], opts)
+            for i, (spec, reps) in enumerate(chunk):
+                if print_progress:
+                    if reps == 1:
+                        print(f"Emulating Trajectory {traj_nb+1}/{n_trajectories}")
+                    else:
+                        print(
+                            "Emulating Trajectories "
+                            f"[{traj_nb+1} - {traj_nb+reps}]/{n_trajectories}"
+                        )
+                self._current_spec = spec
+                traj_nb += reps
+                yield self._wrap([s[i] for s in states]), reps
+
+    # ------------------------------------------------------------------
+    @classmethod
+    def from_sequence(
+        cls,
+        sequence: Sequence,
+        sampling_rate: float = 1.0,
+        config: Any = None,
+        evaluation_times: Union[float, str, Any] = "Full",
+        with_modulation: bool = False,
+        noise_model: NoiseModel | None = None,
+        solver: Solver = Solver.DEFAULT,
+        n_trajectories: int | None = None,
+        **kwargs: Any,
+    ) -> "B200Emulator":
+        """simulation.py:955-1051."""
+        if not isinstance(sequence, Sequence):
+            raise TypeError(
+                "The provided sequence has to be a valid "
+                "pulser.Sequence instance."
+            )
+        if sequence.is_parametrized() or sequence.is_register_mappable():
+            raise ValueError(
+                "The provided sequence needs to be built to be simulated. Call"
+                " `Sequence.build()` with the necessary parameters."
+            )
+        if not sequence._schedule:
+            raise ValueError("The provided sequence has no declared channels.")
+        if all(sequence._schedule[x][-1].tf == 0 for x in sequence.declared_channels):
+            raise ValueError("No instructions given for the channels in the sequence.")
+        if with_modulation and sequence._slm_mask_targets:
+            raise NotImplementedError(
+                "Simulation of sequences combining an SLM mask and output "
+                "modulation is not supported."
+            )
+        return cls(
+            sampler.sample(
+                sequence,
+                modulation=with_modulation,
+                extended_duration=sequence.get_duration(include_fall_time=with_modulation),
+            ),
+            sequence.register,
+            sequence.device,
+            sampling_rate,
+            config,
+            evaluation_times,
+            noise_model=noise_model,
+            solver=solver,
+            n_trajectories=n_trajectories,
+            **kwargs,
+        )

@@ -1,0 +1,168 @@
+"""Generate the committed golden fixtures from the REAL reference (pulser-core
+imported from /root/reference) plus the tight-tolerance oracle.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+
+Each ``*.npz`` holds a HamiltonianSpec (what the reference's Hamiltonian
+constructor receives, extracted from real pulser objects), an initial state and
+the expected output.  Sources of the expected values:
+  * ``ref_*``  : numbers hard-coded in the reference's own tests
+                 (tests/pulser_simulation/test_simulation.py etc., cited below);
+  * ``orc_*``  : oracle (oracle/evolve.py, DOP853 rtol 1e-13) on the same spec.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import pulser_b200  # noqa: F401,E402  (import hooks)
+from pulser import NoiseModel, Pulse, Register, Sequence  # noqa: E402
+from pulser._hamiltonian_data import HamiltonianData  # noqa: E402
+from pulser.devices import AnalogDevice, DigitalAnalogDevice, MockDevice  # noqa: E402
+from pulser.sampler import sampler  # noqa: E402
+from pulser.waveforms import BlackmanWaveform, RampWaveform  # noqa: E402
+
+from oracle import evolve  # noqa: E402
+from oracle.ref_hamiltonian import OracleHamiltonian  # noqa: E402
+from pulser_b200.spec import spec_from_pulser  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def hdata(seq, noise_model=None, n_traj=None, rate=1.0):
+    samples = sampler.sample(seq, extended_duration=seq.get_duration())
+    T = samples.max_duration
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hd = HamiltonianData(
+            samples.extend_duration(T + 1), seq.register, seq.device,
+            noise_model or NoiseModel(), n_traj,
+        )
+    return hd, T
+
+
+def specs_of(seq, noise_model=None, n_traj=None, rate=1.0):
+    hd, T = hdata(seq, noise_model, n_traj, rate)
+    out = []
+    for traj, ns, reps in hd.noisy_samples:
+        out.append((spec_from_pulser(ns, traj, hd.basis_data, hd.lindblad_data, rate, T), reps))
+    return out
+
+
+def oracle_final(spec, psi0):
+    H = OracleHamiltonian.from_spec(spec)
+    return evolve.sesolve(H, psi0, [0.0, spec.sampling_times[-1]], rtol=1e-13, atol=1e-15)[-1]
+
+
+def save(name, spec, **extra):
+    spec.save(os.path.join(OUT, name + ".npz"), **extra)
+    print("wrote", name)
+
+
+def main():
+    # --- reference golden: test_get_hamiltonian (test_simulation.py:476-588) ---
+    reg = Register.from_coordinates([[10, 0], [0, 0]], prefix="atom")
+    seq = Sequence(reg, DigitalAnalogDevice)
+    seq.declare_channel("ising", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(RampWaveform(1500, 0.0, 2.0), 1.0, 0.0), "ising")
+    spec = specs_of(seq, rate=0.01)[0][0]
+    save("ref_get_hamiltonian_rate001", spec, t_ns=143.0,
+         h00=DigitalAnalogDevice.interaction_coeff / 10**6 - 2 * 1.0)
+    np.random.seed(123)
+    spec = specs_of(seq, NoiseModel(samples_per_run=1, temperature=20000), 15)[0][0]
+    save("ref_get_hamiltonian_doppler", spec, t_ns=144.0, h=np.array(
+        [[4.47984523, 0.09606404, 0.09606404, 0.0],
+         [0.09606404, 12.03082372, 0.0, 0.09606404],
+         [0.09606404, 0.0, -12.97113702, 0.09606404],
+         [0.0, 0.09606404, 0.09606404, 0.0]]))
+    np.random.seed(456)
+    spec = specs_of(seq, NoiseModel(samples_per_run=1, temperature=50.0, trap_depth=150.0,
+                                    trap_waist=1.0), 1)[0][0]
+    save("ref_get_hamiltonian_register", spec, t_ns=144.0, h=np.array(
+        [[4.92294305, 0.09606404, 0.09606404, 0.0],
+         [0.09606404, -0.59902269, 0.0, 0.09606404],
+         [0.09606404, 0.0, -0.70099956, 0.09606404],
+         [0.0, 0.09606404, 0.09606404, 0.0]]))
+
+    # --- reference golden: test_initial_state_sim (test_simulation.py:2156-2190), rtol 1e-2 ---
+    seq = Sequence(Register({"q0": (-6, 0), "q1": (0, 0), "q2": (6, 0)}), AnalogDevice)
+    seq.declare_channel("ising", "rydberg_global")
+    seq.add(Pulse.ConstantPulse(4000, 9.28, 18.7, 0), "ising")
+    spec = specs_of(seq)[0][0]
+    psi0 = np.ones(8, dtype=complex) / np.sqrt(8)
+    gold = np.array([0.28985369 + 0.13530479j, 0.40220557 + 0.0j, 0.27445983 + 0.15541026j,
+                     0.29608403 + 0.06155379j, 0.40220557 + 0.0j, 0.36173532 - 0.01617572j,
+                     0.29608403 + 0.06155379j, 0.36931122 - 0.15570528j])
+    save("ref_initial_state_sim", spec, psi0=psi0, ref_final=gold, orc_final=oracle_final(spec, psi0))
+
+    # --- reference golden: test_qutip_backend (test_qutip_backend.py:43-59), atol 1e-5 ---
+    seq = Sequence(Register({"q0": (0, 0)}), MockDevice)
+    seq.declare_channel("raman_local", "raman_local", initial_target="q0")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0, 0), "raman_local")
+    spec = specs_of(seq)[0][0]
+    psi0 = evolve.all_ground_state(spec)
+    save("ref_qutip_backend_pi_pulse", spec, psi0=psi0, ref_final_abs=np.array([0.0, 1.0]),
+         orc_final=oracle_final(spec, psi0))
+
+    # --- reference golden: test_add_max_step_and_delays (test_simulation.py:612-633) ---
+    seq = Sequence(Register.from_coordinates([(0, 0)], prefix="q"), DigitalAnalogDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    seq.delay(1500, "ch")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(600, np.pi), 0, 0), "ch")
+    seq.delay(2000, "ch")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(600, np.pi / 2), 0, 0), "ch")
+    spec = specs_of(seq)[0][0]
+    psi0 = evolve.all_ground_state(spec)
+    save("ref_delays_occupation", spec, psi0=psi0, ref_r_occupation=0.5,
+         orc_final=oracle_final(spec, psi0))
+
+    # --- oracle goldens on real pulser sequences -------------------------------
+    # C1 (BASELINE configs[0])
+    seq = Sequence(Register.square(2, spacing=6.0, prefix="q"), MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    seq.add(Pulse.ConstantPulse(1000, 2 * np.pi, np.pi, 0), "ch")
+    spec = specs_of(seq)[0][0]
+    psi0 = evolve.all_ground_state(spec)
+    save("orc_c1_square", spec, psi0=psi0, orc_final=oracle_final(spec, psi0))
+
+    # 3-level 'all' basis: raman (digital) + rydberg channels, CCZ-like (test_simulation.py:43-95)
+    reg = Register({"control1": np.array([-4.0, 0.0]), "target": np.array([0.0, 4.0]),
+                    "control2": np.array([4.0, 0.0])})
+    seq = Sequence(reg, DigitalAnalogDevice)
+    seq.declare_channel("raman", "raman_local", "control1")
+    pi_Y = Pulse.ConstantDetuning(BlackmanWaveform(400, np.pi), 0.0, -np.pi / 2)
+    pi_p = Pulse.ConstantDetuning(BlackmanWaveform(400, np.pi), 0.0, 0)
+    twopi = Pulse.ConstantDetuning(BlackmanWaveform(400, 2 * np.pi), 0.0, 0)
+    seq.add(pi_Y, "raman"); seq.target("target", "raman"); seq.add(pi_Y, "raman")
+    seq.declare_channel("ryd", "rydberg_local", "control1")
+    seq.add(pi_p, "ryd", protocol="wait-for-all")
+    seq.target("control2", "ryd"); seq.add(pi_p, "ryd")
+    seq.target("target", "ryd"); seq.add(twopi, "ryd")
+    seq.declare_channel("glob", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(600, 0.7 * np.pi), 1.5, 0.3), "glob",
+            protocol="wait-for-all")
+    spec = specs_of(seq)[0][0]
+    psi0 = evolve.all_ground_state(spec)
+    save("orc_all_basis_3atoms", spec, psi0=psi0, orc_final=oracle_final(spec, psi0))
+
+    # noisy trajectories (doppler + amplitude, SURVEY 8(d) C4 shape, small)
+    np.random.seed(7)
+    reg = Register.square(2, spacing=6.5, prefix="q")
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    om = 2 * np.pi * 1.5
+    seq.add(Pulse.ConstantDetuning(RampWaveform(152, 0, om), -6.0, 0), "ch")
+    seq.add(Pulse.ConstantAmplitude(om, RampWaveform(400, -6.0, 8.0), 0), "ch")
+    seq.add(Pulse.ConstantDetuning(RampWaveform(200, om, 0), 8.0, 0), "ch")
+    nm = NoiseModel(temperature=50.0, amp_sigma=0.05, laser_waist=175.0)
+    for i, (spec, reps) in enumerate(specs_of(seq, nm, 3)):
+        psi0 = evolve.all_ground_state(spec)
+        save(f"orc_noisy_traj{i}", spec, psi0=psi0, orc_final=oracle_final(spec, psi0), reps=reps)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+"""CPU tests: the oracle against the reference's own golden numbers, the
+matrix-free oracle against the literal restatement, workloads against pulser."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import random_local_spec, random_state
+from oracle import evolve
+from oracle.matfree import MatFreeHamiltonian
+from oracle.ref_hamiltonian import OracleHamiltonian
+from pulser_b200 import HAVE_PULSER, workloads as W
+from pulser_b200.spec import HamiltonianSpec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    path = os.path.join(GOLD, name + ".npz")
+    with np.load(path, allow_pickle=False) as data:
+        return HamiltonianSpec.from_npz(data), {k: data[k] for k in data.files}
+
+
+def test_golden_get_hamiltonian_h00():
+    """reference tests/pulser_simulation/test_simulation.py:489-494"""
+    spec, extra = load("ref_get_hamiltonian_rate001")
+    H = OracleHamiltonian.from_spec(spec)
+    h = H.matrix_at(float(extra["t_ns"]) / 1000).toarray()
+    assert np.isclose(h[0, 0], float(extra["h00"]))
+    assert np.allclose(h, h.conj().T)
+
+
+@pytest.mark.parametrize("name", ["ref_get_hamiltonian_doppler", "ref_get_hamiltonian_register"])
+def test_golden_get_hamiltonian_noisy(name):
+    """reference test_simulation.py:496-588 (assert_allclose default rtol 1e-7)"""
+    spec, extra = load(name)
+    H = OracleHamiltonian.from_spec(spec)
+    h = H.matrix_at(float(extra["t_ns"]) / 1000).toarray()
+    np.testing.assert_allclose(h, extra["h"], rtol=1e-7, atol=1e-8)
+
+
+def test_golden_initial_state_sim():
+    """reference test_simulation.py:2156-2190 pins the 3-atom final state to
+    rtol 1e-2 (generated with an older pulser/QuTiP).  The restatement agrees
+    to 5.8e-3 max-abs; the residual is the zero-padded last nanosecond
+    (SURVEY.md Appendix C.3), so the check here is max-abs < 1e-2."""
+    spec, extra = load("ref_initial_state_sim")
+    H = OracleHamiltonian.from_spec(spec)
+    out = evolve.sesolve(H, extra["psi0"], [0, spec.sampling_times[-1]], rtol=1e-10, atol=1e-12)[-1]
+    out = out * np.exp(-1j * np.angle(out[np.argmax(np.abs(out))]))
+    assert np.max(np.abs(out - extra["ref_final"])) < 1e-2
+    f = extra["orc_final"]
+    f = f * np.exp(-1j * np.angle(f[np.argmax(np.abs(f))]))
+    assert np.max(np.abs(out - f)) < 1e-8
+
+
+def test_golden_pi_pulse_digital():
+    """reference tests/pulser_simulation/test_qutip_backend.py:43-59 (atol 1e-5)"""
+    spec, extra = load("ref_qutip_backend_pi_pulse")
+    assert spec.eigenbasis == ["g", "h"] and not spec.has_interaction()
+    H = OracleHamiltonian.from_spec(spec)
+    out = evolve.sesolve(H, extra["psi0"], [0, spec.sampling_times[-1]], rtol=1e-10, atol=1e-12)[-1]
+    np.testing.assert_allclose(np.abs(out), extra["ref_final_abs"], atol=1e-5)
+    assert np.max(np.abs(out - extra["orc_final"])) < 1e-8
+
+
+def test_golden_delays_occupation():
+    """reference test_simulation.py:612-633: final |r> occupation 0.5 (1e-4)"""
+    spec, extra = load("ref_delays_occupation")
+    f = extra["orc_final"]
+    assert np.all(np.isfinite(f))
+    assert abs(abs(f[0]) ** 2 - float(extra["ref_r_occupation"])) < 1e-4
+
+
+def test_zvode_adams_default_options_match_tight_oracle():
+    """QuTiP-default stand-in (adams, atol 1e-8, rtol 1e-6, max_step 1 ns)
+    agrees with the tight oracle at the reference's own accuracy (~1e-5)."""
+    spec = W.config_c1()
+    H = OracleHamiltonian.from_spec(spec)
+    psi0 = evolve.all_ground_state(spec)
+    tf = spec.sampling_times[-1]
+    tight = evolve.sesolve(H, psi0, [0, tf])[-1]
+    loose, stats = evolve.sesolve(H, psi0, [0, tf], method="zvode-adams", rtol=1e-6, atol=1e-8,
+                                  max_step=1e-3, nsteps=100000, return_stats=True)
+    assert np.max(np.abs(loose[-1] - tight)) < 1e-4
+    assert stats["rhs_calls"] >= spec.total_duration_ns  # >= 1 RHS per ns
+
+
+@pytest.mark.parametrize("builder", [
+    lambda: W.config_c1(),
+    lambda: W.config_c2(n=6, seed=3),
+    lambda: random_local_spec(5, T=64, seed=2),
+])
+def test_matfree_equals_literal_restatement(builder):
+    spec = builder()
+    mf = MatFreeHamiltonian(spec)
+    H = OracleHamiltonian.from_spec(spec)
+    v = random_state(spec.hilbert_dim, 1)
+    for t in (0.0, 0.0123, spec.sampling_times[-1] * 0.77):
+        ref = H.matrix_at(t) @ v
+        assert np.max(np.abs(mf.apply(t, v) - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_matfree_all_basis():
+    spec, _ = load("orc_all_basis_3atoms")
+    assert spec.dim == 3 and spec.basis_name == "all" and len(spec.drives) == 2
+    mf = MatFreeHamiltonian(spec)
+    H = OracleHamiltonian.from_spec(spec)
+    v = random_state(27, 5)
+    for t in (0.2, 1.0, 1.9):
+        assert np.max(np.abs(mf.apply(t, v) - H.matrix_at(t) @ v)) < 1e-12
+
+
+def test_spec_roundtrip(tmp_path):
+    spec = random_local_spec(4, T=32, seed=8)
+    p = str(tmp_path / "s.npz")
+    spec.save(p)
+    back = HamiltonianSpec.load(p)
+    assert back.eigenbasis == spec.eigenbasis
+    np.testing.assert_array_equal(back.drives[0].coef, spec.drives[0].coef)
+    np.testing.assert_array_equal(back.interaction_matrix, spec.interaction_matrix)
+
+
+def test_fixtures_present():
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 11
+
+
+@pytest.mark.skipif(not HAVE_PULSER, reason="pulser-core not importable here")
+class TestAgainstPulser:
+    def _spec(self, seq, rate=1.0):
+        from pulser import NoiseModel
+        from pulser._hamiltonian_data import HamiltonianData
+        from pulser.sampler import sampler
+        from pulser_b200.spec import spec_from_pulser
+
+        samples = sampler.sample(seq, extended_duration=seq.get_duration())
+        T = samples.max_duration
+        hd = HamiltonianData(samples.extend_duration(T + 1), seq.register, seq.device, NoiseModel(), None)
+        traj, ns, _ = next(iter(hd.noisy_samples))
+        return spec_from_pulser(ns, traj, hd.basis_data, hd.lindblad_data, rate, T), (ns, traj, hd)
+
+    def test_workload_c1_c2_equal_pulser(self):
+        from pulser import Pulse, Register, Sequence
+        from pulser.devices import AnalogDevice, MockDevice
+        from pulser.waveforms import RampWaveform
+
+        seq = Sequence(Register.square(2, spacing=6.0, prefix="q"), MockDevice)
+        seq.declare_channel("ch", "rydberg_global")
+        seq.add(Pulse.ConstantPulse(1000, 2 * np.pi, np.pi, 0), "ch")
+        a, _ = self._spec(seq)
+        b = W.config_c1()
+        np.testing.assert_array_equal(a.drives[0].coef, b.drives[0].coef)
+        np.testing.assert_array_equal(a.drives[0].det, b.drives[0].det)
+        np.testing.assert_allclose(a.interaction_matrix, b.interaction_matrix, rtol=1e-15)
+
+        n = 9
+        coords = W.disc_register(n, 38.0, 5.0, n)
+        seq = Sequence(Register.from_coordinates(coords, center=False, prefix="q"), AnalogDevice)
+        seq.declare_channel("ch", "rydberg_global")
+        om = 2 * np.pi * 1.5
+        U = om / 2
+        seq.add(Pulse.ConstantDetuning(RampWaveform(500, 0, om), -6 * U, 0), "ch")
+        seq.add(Pulse.ConstantAmplitude(om, RampWaveform(2500, -6 * U, 2 * U), 0), "ch")
+        seq.add(Pulse.ConstantDetuning(RampWaveform(1000, om, 0), 2 * U, 0), "ch")
+        a, _ = self._spec(seq)
+        b = W.config_c2(n=n)
+        np.testing.assert_array_equal(a.drives[0].coef, b.drives[0].coef)
+        np.testing.assert_array_equal(a.drives[0].det, b.drives[0].det)
+        np.testing.assert_allclose(a.interaction_matrix, b.interaction_matrix, rtol=1e-14)
+        np.testing.assert_array_equal(a.sampling_times, b.sampling_times)
+
+    def test_spec_extraction_equals_direct_restatement(self):
+        """OracleHamiltonian.from_pulser walks the nested dict itself
+        (hamiltonian.py:426-431); from_spec goes through the product's spec."""
+        from pulser import Pulse, Register, Sequence
+        from pulser.devices import DigitalAnalogDevice
+        from pulser.waveforms import BlackmanWaveform
+
+        reg = Register({"a": (-4.0, 0.0), "b": (0.0, 4.0), "c": (4.0, 0.0)})
+        seq = Sequence(reg, DigitalAnalogDevice)
+        seq.declare_channel("raman", "raman_local", "a")
+        seq.add(Pulse.ConstantDetuning(BlackmanWaveform(200, np.pi), 0.0, -np.pi / 2), "raman")
+        seq.declare_channel("ryd", "rydberg_local", "b")
+        seq.add(Pulse.ConstantDetuning(BlackmanWaveform(200, np.pi), 1.0, 0.4), "ryd")
+        seq.declare_channel("glob", "rydberg_global")
+        seq.add(Pulse.ConstantDetuning(BlackmanWaveform(300, 1.0), -2.0, 0.0), "glob")
+        for rate in (1.0, 0.3):
+            spec, (ns, traj, hd) = self._spec(seq, rate)
+            A = OracleHamiltonian.from_spec(spec)
+            B = OracleHamiltonian.from_pulser(ns, traj, hd.basis_data, hd.lindblad_data, rate)
+            np.testing.assert_array_equal(A.sampling_times, B.sampling_times)
+            for t in (0.01, 0.25, 0.41):
+                assert abs(A.matrix_at(t) - B.matrix_at(t)).max() < 1e-12
