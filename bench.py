@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's metric.
+
+metric : time-steps/s  (one time-step = one 1-ns sampling interval, the
+         granularity the reference forces QuTiP to)
+workload (N=1 and per GPU for N>1): BASELINE configs[1] = C2, 20-atom random 2D
+         register (AnalogDevice limits), Rydberg-blockade sweep, 4000 ns,
+         Schroedinger fp64, Hilbert dim 2^20.
+step   : one pass of the hot path over the whole 4000-step sequence.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo
+    python bench.py --impl reference ...                   # CPU arm (oracle port)
+
+N > 1: one process per GPU (torchrun), replicas of the sequence with different
+register seeds (the single-state path does not shard: "replicas only",
+DESIGN.md), one NCCL all-reduce for the final observables; weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ATOMS = int(os.environ.get("PB200_BENCH_ATOMS", "20"))
+METRIC = "time-steps/s (1 ns sampling intervals of the Sequence evolved per second)"
+UNIT = "steps/s"
+
+
+def workload(seed: int):
+    from pulser_b200 import workloads as W
+
+    return W.config_c2(n=N_ATOMS, seed=seed)
+
+
+def config_dict(n_gpus: int) -> dict:
+    return {
+        "workload": f"C2: {N_ATOMS}-atom random 2D register (disc R=38um, min dist 5um, AnalogDevice C6), "
+                    "Rydberg-blockade sweep 500+2500+1000 ns, ground-rydberg basis, Schroedinger fp64",
+        "hilbert_dim": 2**N_ATOMS,
+        "time_steps_per_sequence": 4000,
+        "accuracy": "CF4 Magnus (exact spline moments) + Chebyshev 1e-12, max_step 4 samples; "
+                    "state error <= 1e-8 (tests/test_gpu_parity.py)",
+        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (one Sequence per GPU), 1 all-reduce",
+        "l2": "L2 flushed between timed iterations (256 MiB write); the 16 MiB state is L2-resident within a step",
+    }
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples: list[list[str]] = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch() -> float | None:
+    """dram bytes per launch of the dominant kernel from the committed ncu summary."""
+    p = os.path.join(ROOT, "profiles", "r01_stage_kernel_summary.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------
+def cpu_reference_run(spec, n_sample_steps: int, t_begin_us: float = 1.0) -> dict:
+    """The reference's CPU path (oracle port of QobjEvo + qutip.sesolve at
+    QuTiP-default options, zvode Adams, max_step 1 ns) on a bounded sample of
+    the workload: `n_sample_steps` consecutive 1-ns steps starting mid-sweep."""
+    from oracle import evolve
+    from oracle.fast_terms import global_ising_hamiltonian
+
+    H = global_ising_hamiltonian(spec)
+    psi0 = evolve.all_ground_state(spec)
+    # warm the integrator / caches with 2 steps, then time the sample
+    evolve.sesolve(H, psi0, [t_begin_us, t_begin_us + 2e-3], method="zvode-adams", rtol=1e-6, atol=1e-8,
+                   max_step=1e-3, nsteps=10**6)
+    t0 = time.perf_counter()
+    _, stats = evolve.sesolve(H, psi0, [t_begin_us, t_begin_us + n_sample_steps * 1e-3], method="zvode-adams",
+                              rtol=1e-6, atol=1e-8, max_step=1e-3, nsteps=10**6, return_stats=True)
+    dt = time.perf_counter() - t0
+    return {"value": n_sample_steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_sample_steps} consecutive 1-ns steps of the same {N_ATOMS}-atom sequence from t={t_begin_us} us, "
+                      f"scipy CSR (5 QobjEvo terms) + zvode Adams atol 1e-8 rtol 1e-6 max_step 1 ns "
+                      f"(QuTiP defaults as pulser sets them), {stats['rhs_calls']} RHS calls, {dt:.1f} s; "
+                      "QuTiP's CSR matvec is single-threaded, host has %d cores" % (os.cpu_count() or 1)}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = workload(N_ATOMS)
+    n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "25" if N_ATOMS >= 20 else "400"))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(spec, n_sample)
+        if i >= args.warmup:
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals]))
+    cb = dict(vals[-1]); cb["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+        "data": "synthetic", "config": config_dict(args.gpus), "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+def run_gpu(args) -> None:
+    import torch
+
+    from pulser_b200 import build
+    build.build()
+    from pulser_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if engine.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # type: ignore
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spec = workload(N_ATOMS + rank)  # replica r evolves its own register
+    T = spec.total_duration_ns
+    tf = spec.sampling_times[-1]
+    D = spec.hilbert_dim
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident: plan + tables + psi0 already in HBM ----
+    plan = engine.DevicePlan(spec, device=local)
+    plan.set_stream(stream.cuda_stream)
+    launches = applies = 0
+    kernel_ms = 0.0
+    for _ in range(args.warmup):
+        plan.set_state("all-ground")
+        plan.propagate(0.0, tf)
+    times_ms = []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            plan.set_state("all-ground")
+            flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            st = plan.propagate(0.0, tf)
+            e1.record(stream)
+            barrier()
+            times_ms.append(e0.elapsed_time(e1))
+            launches += st["n_launches"]; applies += st["n_applies"]; kernel_ms += st["gpu_ms"]
+    norm2 = float(plan.norm2()[0])
+    # final observable of this replica: Rydberg density per atom (host side, from |psi|^2)
+    probs = plan.probabilities()[0]
+    idx = np.arange(D)
+    dens = np.array([probs[((idx >> (N_ATOMS - 1 - k)) & 1) == 0].sum() for k in range(N_ATOMS)])
+    total_ms = float(np.sum(times_ms))
+    t_all = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    obs = torch.tensor(dens, dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)  # max over ranks
+        dist.all_reduce(obs, op=dist.ReduceOp.SUM)    # THE collective of the path: final expectation values
+    total_ms = float(t_all.item())
+    value = world * T * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ----
+    psi0_host = np.zeros(D, dtype=np.complex128)
+    psi0_host[D - 1] = 1.0
+    psi0_pinned = torch.from_numpy(psi0_host).pin_memory().numpy()
+    h2d = psi0_host.nbytes + sum(d.coef[:1].nbytes + d.det[:1].nbytes for d in spec.drives) \
+        + spec.interaction_matrix.nbytes + spec.sampling_times.nbytes
+    d2h = psi0_host.nbytes
+    plan.close()
+    e2e_times = []
+    for i in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        with engine.DevicePlan(spec, device=local) as p2:   # uploads tables + U, builds Dint on device
+            p2.set_state(psi0_pinned)                        # H2D of the initial state
+            p2.propagate(0.0, tf)
+            final = p2.get_state()[0]                        # D2H of the result
+        barrier()
+        if i >= args.warmup:
+            e2e_times.append(time.perf_counter() - t0)
+    assert abs(np.vdot(final, final).real - 1.0) < 1e-8
+    e2e_t = torch.tensor([float(np.sum(e2e_times))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * T * args.steps / float(e2e_t.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_launch_s = (kernel_ms * 1e-3) / max(launches, 1)
+        alg_bytes = 40.0 * D  # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply
+        achieved = alg_bytes / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": config_dict(world),
+            "steps_x_dim": value * D,
+            "h_applies_per_time_step": applies / (T * args.steps),
+            "norm2_final": norm2,
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "pulser_b200.engine.DevicePlan(spec).set_state/propagate/get_state (C-ABI, host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                         "kernel": "stage_d2_rb_kernel (one fused H-apply + Clenshaw update per launch)",
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "avg_launch_us": per_launch_s * 1e6,
+                         "note": "CUDA-event time of the propagation / launches (includes launch gaps); "
+                                 "the 16 MiB state is L2-resident, DRAM traffic per launch is far below the algorithmic bytes"},
+        }
+        if os.environ.get("PB200_BENCH_SKIP_CPU", "0") != "1":
+            n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "25" if N_ATOMS >= 20 else "400"))
+            line["cpu_baseline"] = cpu_reference_run(workload(N_ATOMS), n_sample) if world == 1 else None
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

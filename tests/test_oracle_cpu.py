@@ -192,3 +192,14 @@ class TestAgainstPulser:
             np.testing.assert_array_equal(A.sampling_times, B.sampling_times)
             for t in (0.01, 0.25, 0.41):
                 assert abs(A.matrix_at(t) - B.matrix_at(t)).max() < 1e-12
+
+
+def test_fast_terms_equal_kron_terms():
+    from oracle.fast_terms import global_ising_hamiltonian
+
+    spec = W.config_c2(n=7, seed=4)
+    A = global_ising_hamiltonian(spec)
+    B = OracleHamiltonian.from_spec(spec)
+    assert len(A.terms) == len(B.terms) == 6  # interaction(+dag), amp(+dag), det(+dag)
+    for t in (0.3, 2.2, 3.7):
+        assert abs(A.matrix_at(t) - B.matrix_at(t)).max() < 1e-13
