@@ -75,7 +75,7 @@ typedef struct pb200_plan_desc {
  * the fixed-order propagator and are accepted-and-ignored on the Python side). */
 typedef struct pb200_run_opts {
     int32_t max_step_samples; /* K: longest Magnus step, in sampling intervals
-                                 (>=1). 0 = library default. */
+                                 (>=1). 0 = library default (16 adaptive, 4 fixed). */
     int32_t refine_window;    /* steps are 1 interval long within this many
                                  intervals of a non-smooth sample; <0 = default */
     double cheb_tol;          /* Chebyshev truncation tolerance per exponential;
@@ -83,7 +83,12 @@ typedef struct pb200_run_opts {
     double rough_tol;         /* relative 3rd-difference threshold that marks a
                                  sample as non-smooth; 0 = default */
     int32_t magnus_order;     /* 2 or 4 (default 4) */
-    int32_t reserved;
+    int32_t check_every;      /* adaptive mode: smooth steps between two
+                                 step-doubling checks; 0 = default (12) */
+    double tol;               /* > 0: adaptive Magnus step, target 2-norm error of
+                                 the state accumulated over the whole sampling-
+                                 time range; 0 = default (1e-9); < 0: fixed steps
+                                 of max_step_samples intervals */
 } pb200_run_opts;
 
 typedef struct pb200_run_stats {
@@ -93,6 +98,9 @@ typedef struct pb200_run_stats {
     int64_t n_launches;     /* CUDA kernel launches */
     double gpu_ms;          /* device time of the propagation (CUDA events) */
     double max_rho;         /* largest Chebyshev half-width encountered */
+    int64_t n_checks;       /* step-doubling checks performed (adaptive mode) */
+    double err_estimate;    /* accumulated local-error estimate (adaptive mode) */
+    double mean_step_samples; /* average smooth-step length, in sampling intervals */
 } pb200_run_stats;
 
 int pb200_version(void);

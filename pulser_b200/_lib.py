@@ -46,7 +46,8 @@ class RunOpts(C.Structure):
         ("cheb_tol", C.c_double),
         ("rough_tol", C.c_double),
         ("magnus_order", C.c_int32),
-        ("reserved", C.c_int32),
+        ("check_every", C.c_int32),
+        ("tol", C.c_double),
     ]
 
 
@@ -58,6 +59,9 @@ class RunStats(C.Structure):
         ("n_launches", C.c_int64),
         ("gpu_ms", C.c_double),
         ("max_rho", C.c_double),
+        ("n_checks", C.c_int64),
+        ("err_estimate", C.c_double),
+        ("mean_step_samples", C.c_double),
     ]
 
 

@@ -608,4 +608,26 @@ __global__ void norm2_kernel(const c2* psi, long long D, double* out) {
     }
 }
 
+// squared distance per trajectory (step-doubling error estimate)
+__global__ void diffnorm2_kernel(const c2* a, const c2* b, long long D, double* out) {
+    const long long traj = blockIdx.y;
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 x = a[traj * D + i], y = b[traj * D + i];
+        const double dr = x.x - y.x, di = x.y - y.y;
+        acc = fma(dr, dr, acc);
+        acc = fma(di, di, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += ws[i];
+        atomicAdd(out + traj, s);
+    }
+}
+
 }  // namespace pb200

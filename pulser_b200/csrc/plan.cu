@@ -72,6 +72,7 @@ struct Plan {
     bool own_stream = false;
     // device buffers
     c2* buf[3] = {nullptr, nullptr, nullptr};
+    c2* aux[2] = {nullptr, nullptr};  // step-doubling check: saved state / full-step result
     int cur = 0;  // index of the current state buffer
     double* dint = nullptr;
     bool dint_shared = true;
@@ -451,6 +452,52 @@ static std::vector<char> fine_intervals(const Plan& P, int window, double rough_
     return fine;
 }
 
+// Magnus step [a, b] appended to the program (2 exponentials for order 4)
+static void add_step(const Plan& P, Program& prog, double a, double b, int order, double tol) {
+    std::vector<cplx> g0, g1; std::vector<double> th0, th1;
+    moments_for_step(P, a, b, g0, g1, th0, th1);
+    const double h = b - a;
+    const size_t cnt = g0.size();
+    if (order == 4) {
+        ExpParams E1, E2;
+        E1.g.resize(cnt); E1.th.resize(cnt); E2.g.resize(cnt); E2.th.resize(cnt);
+        for (size_t x = 0; x < cnt; ++x) {
+            E1.g[x] = 0.5 * g0[x] - 2.0 * g1[x]; E1.th[x] = 0.5 * th0[x] - 2.0 * th1[x];
+            E2.g[x] = 0.5 * g0[x] + 2.0 * g1[x]; E2.th[x] = 0.5 * th0[x] + 2.0 * th1[x];
+        }
+        E1.w = 0.5 * h; E2.w = 0.5 * h;
+        add_exponential(P, prog, E1, tol);
+        add_exponential(P, prog, E2, tol);
+    } else {
+        ExpParams E; E.g = g0; E.th = th0; E.w = h;
+        add_exponential(P, prog, E, tol);
+    }
+}
+
+// number of sub-steps of a jump interval from the a-priori Magnus remainder bound
+static int jump_substeps(const Plan& P, double a, double b, double magnus_tol) {
+    std::vector<cplx> g0, g1; std::vector<double> th0, th1;
+    moments_for_step(P, a, b, g0, g1, th0, th1);
+    ExpParams E; E.g = g0; E.th = th0; E.w = b - a;
+    double gm, rh; std::vector<double> scratch_tab;
+    build_tables(P, E, gm, rh, scratch_tab, P.dim == 2 && P.n_drives == 1);
+    double b1 = 0.0;
+    for (int tr = 0; tr < P.B; ++tr) {
+        double acc = 0.0;
+        for (int q = 0; q < P.n_drives; ++q)
+            for (int k = 0; k < P.n; ++k) acc += std::abs(g1[pidx(P, tr, q, k)]) + std::fabs(th1[pidx(P, tr, q, k)]);
+        b1 = std::max(b1, acc);
+    }
+    const double est = 8.0 * rh * rh * rh * b1 / 60.0;  // (2 rho)^3 |B1| / 60
+    int nsub = (int)std::ceil(std::pow(std::max(est / magnus_tol, 1.0), 0.25));
+    return std::min(std::max(nsub, 1), 32);
+}
+
+static void ensure_aux_buffers(Plan& P) {
+    for (int i = 0; i < 2; ++i)
+        if (!P.aux[i]) CUDA_CHECK(cudaMalloc(&P.aux[i], sizeof(c2) * (size_t)P.D * P.B));
+}
+
 static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats) {
     if (!P.state_set) fail(PB200_ERR_STATE, "pb200_propagate: no state set (call pb200_state_set first)");
     for (int tr = 0; tr < P.B; ++tr)
@@ -461,22 +508,26 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
-    int K = (o && o->max_step_samples > 0) ? o->max_step_samples : env_int("PB200_MAX_STEP", 4);
+    const double gtol = (o && o->tol != 0.0) ? o->tol : 1e-9;
+    const bool adaptive = gtol > 0.0;
+    int Kmax = (o && o->max_step_samples > 0) ? o->max_step_samples
+                                               : env_int("PB200_MAX_STEP", adaptive ? 16 : 4);
     int W = (o && o->refine_window >= 0) ? o->refine_window : env_int("PB200_REFINE_WINDOW", 8);
     double tol = (o && o->cheb_tol > 0) ? o->cheb_tol : 1e-12;
     double rtol = (o && o->rough_tol > 0) ? o->rough_tol : 1e-4;
     int order = (o && o->magnus_order) ? o->magnus_order : 4;
+    int check_every = (o && o->check_every > 0) ? o->check_every : 12;
     if (order != 2 && order != 4) fail(PB200_ERR_INVALID, "magnus_order must be 2 or 4");
 
     pb200_run_stats st{};
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
     std::vector<char> jump;
-    const std::vector<char> fine0 = fine_intervals(P, W, rtol, 0.05, jump);
+    std::vector<char> fine = fine_intervals(P, W, rtol, 0.05, jump);
+    for (size_t i = 0; i < fine.size(); ++i) if (jump[i]) fine[i] = 1;
     const double magnus_tol = 1e-11;
-    std::vector<char> fine_m = fine0;
-    for (size_t i = 0; i < fine_m.size(); ++i) if (jump[i]) fine_m[i] = 1;
-    const std::vector<char>& fine = fine_m;
     const int nt = (int)P.times.size();
+    // error budget per unit of time: gtol over the whole sampling-time range
+    const double rate_allowed = adaptive ? gtol / std::max(thi - tlo, 1e-30) : 0.0;
 
     cudaEvent_t ev0, ev1;
     CUDA_CHECK(cudaEventCreate(&ev0));
@@ -487,64 +538,85 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     auto flush = [&]() {
         if (prog.cheb.empty()) return;
         run_program(P, prog, passes, st);
-        // tables were copied asynchronously from prog.tables: wait before reuse
-        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));  // tables are copied asynchronously from prog
         prog = Program();
     };
     const size_t flush_doubles = (size_t)8 << 20;  // 64 MiB of tables per chunk
-    std::vector<cplx> g0, g1; std::vector<double> th0, th1;
+    // current smooth-step length in sampling intervals (real: < 1 means sub-steps)
+    double Kc = adaptive ? std::min(4.0, (double)Kmax) : (double)Kmax;
+    int since_check = 1 << 30;  // force a check at the first smooth step
+    double smooth_len = 0.0; long long smooth_steps = 0;
     double t = t_start;
     while (t < t_stop - eps) {
-        int i = find_piece(P.times, t + eps);
+        const int i = find_piece(P.times, t + eps);
+        const double hi_i = P.times[i + 1] - P.times[i];
         double b;
-        if (fine[i]) {
+        bool smooth = !fine[i];
+        if (!smooth) {
             b = P.times[i + 1];
-        } else {
+            if (jump[i] && order == 4) {
+                const int nsub = jump_substeps(P, t, std::min(b, t_stop), magnus_tol);
+                if (nsub > 1) b = std::min(b, t + hi_i / nsub);
+            }
+        } else if (Kc >= 1.0) {
+            const int K = std::max(1, std::min((int)std::floor(Kc + 1e-9), Kmax));
             int j = i, cnt = 0;
             while (j < nt - 1 && !fine[j] && cnt < K) { ++j; ++cnt; }
             b = P.times[j];
+        } else {
+            const int nsub = std::min(64, (int)std::ceil(1.0 / Kc - 1e-9));
+            b = std::min(P.times[i + 1], t + hi_i / nsub);
         }
         b = std::min(b, t_stop);
         if (b <= t + eps) b = std::min(P.times[std::min(i + 1, nt - 1)], t_stop);
-        if (jump[i] && order == 4) {
-            // a-priori bound of the 4th-order Magnus remainder, (2 rho)^3 |B1| / 60, sets the number of
-            // sub-steps of this interval (error per sub-step scales as h^5)
-            moments_for_step(P, t, b, g0, g1, th0, th1);
-            ExpParams E; E.g = g0; E.th = th0; E.w = b - t;
-            double gm, rh; std::vector<double> scratch_tab;
-            build_tables(P, E, gm, rh, scratch_tab, P.dim == 2 && P.n_drives == 1);
-            double b1 = 0.0;
-            for (int tr = 0; tr < P.B; ++tr) {
-                double acc = 0.0;
-                for (int q = 0; q < P.n_drives; ++q)
-                    for (int k = 0; k < P.n; ++k) acc += std::abs(g1[pidx(P, tr, q, k)]) + std::fabs(th1[pidx(P, tr, q, k)]);
-                b1 = std::max(b1, acc);
-            }
-            const double est = 8.0 * rh * rh * rh * b1 / 60.0;
-            int nsub = (int)std::ceil(std::pow(std::max(est / magnus_tol, 1.0), 0.25));
-            nsub = std::min(std::max(nsub, 1), 32);
-            if (nsub > 1) b = std::min(b, t + (P.times[i + 1] - P.times[i]) / nsub);
-        }
-        const double h = b - t;
-        moments_for_step(P, t, b, g0, g1, th0, th1);
-        const size_t cnt = g0.size();
-        if (order == 4) {
-            ExpParams E1, E2;
-            E1.g.resize(cnt); E1.th.resize(cnt); E2.g.resize(cnt); E2.th.resize(cnt);
-            for (size_t x = 0; x < cnt; ++x) {
-                E1.g[x] = 0.5 * g0[x] - 2.0 * g1[x]; E1.th[x] = 0.5 * th0[x] - 2.0 * th1[x];
-                E2.g[x] = 0.5 * g0[x] + 2.0 * g1[x]; E2.th[x] = 0.5 * th0[x] + 2.0 * th1[x];
-            }
-            E1.w = 0.5 * h; E2.w = 0.5 * h;
-            add_exponential(P, prog, E1, tol);
-            add_exponential(P, prog, E2, tol);
+
+        if (smooth && adaptive && since_check >= check_every && (P.D * (long long)P.B) <= (1LL << 31)) {
+            // ---- step-doubling check: one step of h against two of h/2 ----
+            flush();
+            ensure_aux_buffers(P);
+            const size_t bytes = sizeof(c2) * (size_t)P.D * P.B;
+            CUDA_CHECK(cudaMemcpyAsync(P.aux[0], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
+            add_step(P, prog, t, b, order, tol);
+            flush();
+            CUDA_CHECK(cudaMemcpyAsync(P.aux[1], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
+            CUDA_CHECK(cudaMemcpyAsync(P.buf[P.cur], P.aux[0], bytes, cudaMemcpyDeviceToDevice, P.stream));
+            const double mid = 0.5 * (t + b);
+            add_step(P, prog, t, mid, order, tol);
+            add_step(P, prog, mid, b, order, tol);
+            flush();
+            CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * std::min(P.B, 4096), P.stream));
+            const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
+            dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)std::min(P.B, 4096));
+            diffnorm2_kernel<<<grid, 256, 0, P.stream>>>(P.buf[P.cur], P.aux[1], P.D, P.d_scratch);
+            CUDA_CHECK(cudaGetLastError());
+            std::vector<double> d2(std::min(P.B, 4096));
+            CUDA_CHECK(cudaMemcpyAsync(d2.data(), P.d_scratch, sizeof(double) * d2.size(), cudaMemcpyDeviceToHost, P.stream));
+            CUDA_CHECK(cudaStreamSynchronize(P.stream));
+            double e = 0.0;
+            for (double v : d2) e = std::max(e, v);
+            // two half steps carry 1/15 of the difference (4th order); the full step 16/15
+            const int pw = (order == 4) ? 4 : 2;
+            const double scale = std::pow(2.0, pw) - 1.0;
+            const double err_big = std::sqrt(e) * std::pow(2.0, pw) / scale;
+            st.err_estimate += std::sqrt(e) / scale;
+            ++st.n_checks;
+            st.n_launches += 1;
+            // choose the step whose error rate meets the budget: err ~ h^(pw+1) per step
+            const double h_samples = (b - t) / hi_i;
+            const double rate = err_big / std::max(b - t, 1e-30);
+            double factor = 2.0;
+            if (rate > 0.0) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
+            factor = std::min(2.0, std::max(0.2, factor));
+            Kc = std::min((double)Kmax, std::max(1.0 / 64.0, h_samples * factor));
+            since_check = (factor < 0.7) ? check_every - 2 : 0;  // re-check soon after a big cut
+            ++st.n_steps; smooth_len += h_samples; ++smooth_steps;
         } else {
-            ExpParams E; E.g = g0; E.th = th0; E.w = h;
-            add_exponential(P, prog, E, tol);
+            add_step(P, prog, t, b, order, tol);
+            ++st.n_steps;
+            if (smooth) { ++since_check; smooth_len += (b - t) / hi_i; ++smooth_steps; }
+            if (prog.tables.size() > flush_doubles) flush();
         }
-        ++st.n_steps;
         t = b;
-        if (prog.tables.size() > flush_doubles) flush();
     }
     flush();
     CUDA_CHECK(cudaEventRecord(ev1, P.stream));
@@ -552,6 +624,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     st.gpu_ms = ms;
+    st.mean_step_samples = smooth_steps ? smooth_len / smooth_steps : 0.0;
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) *stats = st;
 }
@@ -737,6 +810,8 @@ int pb200_plan_destroy(pb200_plan* h) {
     Plan& P = h->p;
     for (int i = 0; i < 3; ++i)
         if (P.buf[i]) cudaFree(P.buf[i]);
+    for (int i = 0; i < 2; ++i)
+        if (P.aux[i]) cudaFree(P.aux[i]);
     if (P.dint) cudaFree(P.dint);
     if (P.d_table) cudaFree(P.d_table);
     if (P.d_scratch) cudaFree(P.d_scratch);

@@ -68,7 +68,7 @@ _QUTIP_OPTIONS = {
     "norm_steps", "norm_t_tol", "norm_tol", "mc_corr_eps", "improved_sampling",
 }
 # options of this backend
-_B200_OPTIONS = {"b200_max_step", "b200_cheb_tol", "b200_refine_window", "b200_batch"}
+_B200_OPTIONS = {"b200_max_step", "b200_cheb_tol", "b200_refine_window", "b200_batch", "b200_tol"}
 
 
 class B200Emulator:
@@ -376,6 +376,7 @@ class B200Emulator:
             "max_step": int(options.get("b200_max_step", 0)),
             "cheb_tol": float(options.get("b200_cheb_tol", 0.0)),
             "refine_window": int(options.get("b200_refine_window", -1)),
+            "tol": float(options.get("b200_tol", 0.0)),
         }
 
     def _run_batch(self, specs: list[HamiltonianSpec], opts: dict) -> list[list[np.ndarray]]:

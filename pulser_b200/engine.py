@@ -217,8 +217,15 @@ class DevicePlan:
         cheb_tol: float = 0.0,
         rough_tol: float = 0.0,
         magnus_order: int = 4,
+        tol: float = 0.0,
+        check_every: int = 0,
     ) -> dict:
-        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, 0)
+        """Advance all trajectories from ``t_start`` to ``t_stop`` (us).
+
+        ``tol > 0`` (default 1e-9): adaptive Magnus steps with step-doubling
+        error control; ``tol < 0``: fixed steps of ``max_step`` samples.
+        """
+        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, check_every, tol)
         st = RunStats()
         check(
             lib.pb200_propagate(

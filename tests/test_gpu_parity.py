@@ -78,9 +78,10 @@ def test_c1_four_atom_square(engine):
     assert abs(np.linalg.norm(got) - 1.0) < 1e-9
 
 
-@pytest.mark.parametrize("n,max_step", [(6, 1), (8, 4), (10, 4)])
-def test_blockade_sweep_vs_oracle(engine, n, max_step):
-    """C2-shaped sequence (4000 ns) at oracle-sized registers."""
+@pytest.mark.parametrize("n,max_step,tol", [(6, 1, -1.0), (8, 2, -1.0), (8, 0, 0.0), (10, 0, 0.0), (12, 0, 0.0)])
+def test_blockade_sweep_vs_oracle(engine, n, max_step, tol):
+    """C2-shaped sequence (4000 ns) at oracle-sized registers; fixed steps
+    (tol < 0) and the default adaptive step-doubling controller (tol = 0)."""
     from oracle import evolve
 
     spec = W.config_c2(n=n, seed=20)
@@ -88,9 +89,26 @@ def test_blockade_sweep_vs_oracle(engine, n, max_step):
     ref = _oracle_final(spec, psi0)
     with engine.DevicePlan(spec) as plan:
         plan.set_state("all-ground")
-        plan.propagate(0.0, spec.sampling_times[-1], max_step=max_step)
+        st = plan.propagate(0.0, spec.sampling_times[-1], max_step=max_step, tol=tol)
         got = plan.get_state()[0]
     assert np.max(np.abs(got - ref)) < STATE_TOL
+    assert (st["n_checks"] > 0) == (tol >= 0)
+
+
+def test_dense_strongly_interacting_register(engine):
+    """Closely packed atoms (U ~ 100 rad/us): the controller must shorten the steps."""
+    from oracle import evolve
+
+    amp, det = W.blockade_sweep_waveforms(t_rise=100, t_sweep=400, t_fall=100)
+    spec = W.ising_global_spec(W.square_register(3, 6.0)[:8], W.C6_LEVEL_70, amp, det)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        st = plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+    assert st["mean_step_samples"] < 4.0
 
 
 def test_local_noisy_trajectory_vs_oracle(engine):
@@ -114,11 +132,11 @@ def test_batch_of_trajectories(engine):
     for s in specs:
         with engine.DevicePlan(s) as plan:
             plan.set_state(psi0)
-            plan.propagate(0.0, s.sampling_times[-1], max_step=2)
+            plan.propagate(0.0, s.sampling_times[-1], max_step=2, tol=-1.0)
             singles.append(plan.get_state()[0])
     with engine.DevicePlan(specs) as plan:
         plan.set_state(psi0)
-        plan.propagate(0.0, specs[0].sampling_times[-1], max_step=2)
+        plan.propagate(0.0, specs[0].sampling_times[-1], max_step=2, tol=-1.0)
         got = plan.get_state()
     for a, b in zip(got, singles):
         assert np.max(np.abs(a - b)) < 1e-11
@@ -138,7 +156,7 @@ def test_intermediate_times_and_restart(engine):
         for a, b in [(0.0, 0.4567), (0.4567, 1.2), (1.2, 3.0005), (3.0005, tf)]:
             plan.propagate(a, b)
         pieces = plan.get_state()[0]
-    assert np.max(np.abs(whole - pieces)) < 2e-9
+    assert np.max(np.abs(whole - pieces)) < STATE_TOL
 
 
 @pytest.mark.parametrize("n", [18, 20])
@@ -148,13 +166,13 @@ def test_full_size_properties(engine, n):
     tf = spec.sampling_times[-1]
     outs = {}
     with engine.DevicePlan(spec) as plan:
-        for K in (2, 4):
+        for tol in (0.0, 1e-11):  # default controller against a 100x tighter one
             plan.set_state("all-ground")
-            plan.propagate(0.0, tf, max_step=K)
+            plan.propagate(0.0, tf, tol=tol)
             n2 = plan.norm2()[0]
             assert abs(n2 - 1.0) < 1e-9
-            outs[K] = plan.get_state()[0]
-    assert np.max(np.abs(outs[2] - outs[4])) < STATE_TOL
+            outs[tol] = plan.get_state()[0]
+    assert np.max(np.abs(outs[0.0] - outs[1e-11])) < STATE_TOL
 
 
 @pytest.mark.parametrize("tile_bits,max_extra,reg_bits", [(11, 0, 3), (11, 2, 2), (12, 0, 3), (12, 3, 2), (11, 16, 3)])

@@ -19,13 +19,13 @@ def main():
                               "launches_per_apply": launches // 50,
                               "alg_GBs": round(40 * D / (per * 1e-3) / 1e9, 1)}))
             if n <= 22:
-                for K in (4,):
+                for K, tol in ((4, -1.0), (0, 0.0)):
                     plan.set_state("all-ground")
                     t2 = time.time()
-                    st = plan.propagate(0.0, spec.sampling_times[-1], max_step=K)
+                    st = plan.propagate(0.0, spec.sampling_times[-1], max_step=K, tol=tol)
                     wall = time.time() - t2
                     T = spec.total_duration_ns
-                    st.update({"K": K, "wall_s": round(wall, 3), "steps_per_s": round(T / wall, 1),
+                    st.update({"K": K, "tol": tol, "wall_s": round(wall, 3), "steps_per_s": round(T / wall, 1),
                                "applies_per_ns": round(st["n_applies"] / T, 2),
                                "us_per_apply": round(st["gpu_ms"] * 1e3 / st["n_applies"], 2),
                                "norm2": float(plan.norm2()[0])})
