@@ -508,12 +508,12 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
-    const double gtol = (o && o->tol != 0.0) ? o->tol : 1e-9;
+    const double gtol = (o && o->tol != 0.0) ? o->tol : 3e-9;
     const bool adaptive = gtol > 0.0;
     int Kmax = (o && o->max_step_samples > 0) ? o->max_step_samples
                                                : env_int("PB200_MAX_STEP", adaptive ? 16 : 4);
     int W = (o && o->refine_window >= 0) ? o->refine_window : env_int("PB200_REFINE_WINDOW", 8);
-    double tol = (o && o->cheb_tol > 0) ? o->cheb_tol : 1e-12;
+    const double tol_user = (o && o->cheb_tol > 0) ? o->cheb_tol : 0.0;
     double rtol = (o && o->rough_tol > 0) ? o->rough_tol : 1e-4;
     int order = (o && o->magnus_order) ? o->magnus_order : 4;
     int check_every = (o && o->check_every > 0) ? o->check_every : 12;
@@ -528,6 +528,14 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     const int nt = (int)P.times.size();
     // error budget per unit of time: gtol over the whole sampling-time range
     const double rate_allowed = adaptive ? gtol / std::max(thi - tlo, 1e-30) : 0.0;
+    // Chebyshev truncation per exponential: a fifth of the step's share of the error budget
+    // (a hundredth inside a step-doubling check so that the estimate is not truncation noise)
+    auto cheb_tol_for = [&](double h, bool check) {
+        if (tol_user > 0.0) return tol_user;
+        if (!adaptive) return 1e-12;
+        const double share = rate_allowed * h;
+        return std::min(1e-12, std::max(2e-15, (check ? 0.01 : 0.2) * share));
+    };
 
     cudaEvent_t ev0, ev1;
     CUDA_CHECK(cudaEventCreate(&ev0));
@@ -576,13 +584,14 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             ensure_aux_buffers(P);
             const size_t bytes = sizeof(c2) * (size_t)P.D * P.B;
             CUDA_CHECK(cudaMemcpyAsync(P.aux[0], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
-            add_step(P, prog, t, b, order, tol);
+            const double ctol = cheb_tol_for(b - t, true);
+            add_step(P, prog, t, b, order, ctol);
             flush();
             CUDA_CHECK(cudaMemcpyAsync(P.aux[1], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
             CUDA_CHECK(cudaMemcpyAsync(P.buf[P.cur], P.aux[0], bytes, cudaMemcpyDeviceToDevice, P.stream));
             const double mid = 0.5 * (t + b);
-            add_step(P, prog, t, mid, order, tol);
-            add_step(P, prog, mid, b, order, tol);
+            add_step(P, prog, t, mid, order, ctol);
+            add_step(P, prog, mid, b, order, ctol);
             flush();
             CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * std::min(P.B, 4096), P.stream));
             const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
@@ -605,13 +614,15 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             const double h_samples = (b - t) / hi_i;
             const double rate = err_big / std::max(b - t, 1e-30);
             double factor = 2.0;
-            if (rate > 0.0) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
+            // differences at the level of truncation / rounding noise carry no information
+            const double noise = 50.0 * ctol + 1e-14;
+            if (err_big > noise) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
             factor = std::min(2.0, std::max(0.2, factor));
-            Kc = std::min((double)Kmax, std::max(1.0 / 64.0, h_samples * factor));
+            Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
             since_check = (factor < 0.7) ? check_every - 2 : 0;  // re-check soon after a big cut
             ++st.n_steps; smooth_len += h_samples; ++smooth_steps;
         } else {
-            add_step(P, prog, t, b, order, tol);
+            add_step(P, prog, t, b, order, cheb_tol_for(b - t, false));
             ++st.n_steps;
             if (smooth) { ++since_check; smooth_len += (b - t) / hi_i; ++smooth_steps; }
             if (prog.tables.size() > flush_doubles) flush();
