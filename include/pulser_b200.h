@@ -89,6 +89,9 @@ typedef struct pb200_run_opts {
                                  the state accumulated over the whole sampling-
                                  time range; 0 = default (1e-9); < 0: fixed steps
                                  of max_step_samples intervals */
+    int32_t extrapolate;      /* 1: every smooth step is a step-doubling pair combined
+                                 by Richardson extrapolation (6th order); 0: off */
+    int32_t reserved;
 } pb200_run_opts;
 
 typedef struct pb200_run_stats {

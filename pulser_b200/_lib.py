@@ -48,6 +48,8 @@ class RunOpts(C.Structure):
         ("magnus_order", C.c_int32),
         ("check_every", C.c_int32),
         ("tol", C.c_double),
+        ("extrapolate", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

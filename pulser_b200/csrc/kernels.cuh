@@ -608,6 +608,15 @@ __global__ void norm2_kernel(const c2* psi, long long D, double* out) {
     }
 }
 
+// y = alpha*y + beta*x (Richardson combination of the step-doubling pair)
+__global__ void axpby_kernel(c2* y, const c2* x, double alpha, double beta, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 a = y[i], b = x[i];
+        y[i] = {alpha * a.x + beta * b.x, alpha * a.y + beta * b.y};
+    }
+}
+
 // squared distance per trajectory (step-doubling error estimate)
 __global__ void diffnorm2_kernel(const c2* a, const c2* b, long long D, double* out) {
     const long long traj = blockIdx.y;

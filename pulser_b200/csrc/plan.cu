@@ -508,7 +508,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
-    const double gtol = (o && o->tol != 0.0) ? o->tol : 3e-9;
+    const double gtol = (o && o->tol != 0.0) ? o->tol : 1e-8;
+    const bool extrap = o && o->extrapolate != 0;
     const bool adaptive = gtol > 0.0;
     int Kmax = (o && o->max_step_samples > 0) ? o->max_step_samples
                                                : env_int("PB200_MAX_STEP", adaptive ? 16 : 4);
@@ -578,13 +579,13 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         b = std::min(b, t_stop);
         if (b <= t + eps) b = std::min(P.times[std::min(i + 1, nt - 1)], t_stop);
 
-        if (smooth && adaptive && since_check >= check_every && (P.D * (long long)P.B) <= (1LL << 31)) {
+        if (smooth && ((adaptive && since_check >= check_every) || extrap) && (P.D * (long long)P.B) <= (1LL << 31)) {
             // ---- step-doubling check: one step of h against two of h/2 ----
             flush();
             ensure_aux_buffers(P);
             const size_t bytes = sizeof(c2) * (size_t)P.D * P.B;
             CUDA_CHECK(cudaMemcpyAsync(P.aux[0], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
-            const double ctol = cheb_tol_for(b - t, true);
+            const double ctol = adaptive ? cheb_tol_for(b - t, true) : 1e-13;
             add_step(P, prog, t, b, order, ctol);
             flush();
             CUDA_CHECK(cudaMemcpyAsync(P.aux[1], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
@@ -603,8 +604,16 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             CUDA_CHECK(cudaStreamSynchronize(P.stream));
             double e = 0.0;
             for (double v : d2) e = std::max(e, v);
-            // two half steps carry 1/15 of the difference (4th order); the full step 16/15
             const int pw = (order == 4) ? 4 : 2;
+            if (extrap) {  // psi = R2 + (R2 - R1) / (2^pw - 1)
+                const double sc = std::pow(2.0, pw) - 1.0;
+                const long long total = P.D * (long long)P.B;
+                const long long nb = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
+                axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(P.buf[P.cur], P.aux[1], 1.0 + 1.0 / sc, -1.0 / sc, total);
+                CUDA_CHECK(cudaGetLastError());
+                st.n_launches += 1;
+            }
+            // two half steps carry 1/15 of the difference (4th order); the full step 16/15
             const double scale = std::pow(2.0, pw) - 1.0;
             const double err_big = std::sqrt(e) * std::pow(2.0, pw) / scale;
             st.err_estimate += std::sqrt(e) / scale;
@@ -618,7 +627,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             const double noise = 50.0 * ctol + 1e-14;
             if (err_big > noise) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
             factor = std::min(2.0, std::max(0.2, factor));
-            Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
+            if (adaptive) Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
             since_check = (factor < 0.7) ? check_every - 2 : 0;  // re-check soon after a big cut
             ++st.n_steps; smooth_len += h_samples; ++smooth_steps;
         } else {

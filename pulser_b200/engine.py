@@ -219,13 +219,14 @@ class DevicePlan:
         magnus_order: int = 4,
         tol: float = 0.0,
         check_every: int = 0,
+        extrapolate: int = 0,
     ) -> dict:
         """Advance all trajectories from ``t_start`` to ``t_stop`` (us).
 
         ``tol > 0`` (default 1e-9): adaptive Magnus steps with step-doubling
         error control; ``tol < 0``: fixed steps of ``max_step`` samples.
         """
-        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, check_every, tol)
+        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, check_every, tol, extrapolate, 0)
         st = RunStats()
         check(
             lib.pb200_propagate(
