@@ -75,7 +75,8 @@ typedef struct pb200_plan_desc {
  * the fixed-order propagator and are accepted-and-ignored on the Python side). */
 typedef struct pb200_run_opts {
     int32_t max_step_samples; /* K: longest Magnus step, in sampling intervals
-                                 (>=1). 0 = library default (16 adaptive, 4 fixed). */
+                                 (>=1). 0 = library default (64 adaptive+extrapolated,
+                                 16 adaptive, 4 fixed). */
     int32_t refine_window;    /* steps are 1 interval long within this many
                                  intervals of a non-smooth sample; <0 = default */
     double cheb_tol;          /* Chebyshev truncation tolerance per exponential;
@@ -87,10 +88,11 @@ typedef struct pb200_run_opts {
                                  step-doubling checks; 0 = default (12) */
     double tol;               /* > 0: adaptive Magnus step, target 2-norm error of
                                  the state accumulated over the whole sampling-
-                                 time range; 0 = default (1e-9); < 0: fixed steps
+                                 time range; 0 = default (1e-8); < 0: fixed steps
                                  of max_step_samples intervals */
-    int32_t extrapolate;      /* 1: every smooth step is a step-doubling pair combined
-                                 by Richardson extrapolation (6th order); 0: off */
+    int32_t extrapolate;      /* 0 / 1 (default): every smooth step is a step-doubling
+                                 pair combined by Richardson extrapolation (6th
+                                 order); -1: plain 4th-order steps */
     int32_t reserved;
 } pb200_run_opts;
 

@@ -72,7 +72,7 @@ struct Plan {
     bool own_stream = false;
     // device buffers
     c2* buf[3] = {nullptr, nullptr, nullptr};
-    c2* aux[2] = {nullptr, nullptr};  // step-doubling check: saved state / full-step result
+    c2* aux[4] = {nullptr, nullptr, nullptr, nullptr};  // step-doubling: saved states / full-step results
     int cur = 0;  // index of the current state buffer
     double* dint = nullptr;
     bool dint_shared = true;
@@ -494,7 +494,7 @@ static int jump_substeps(const Plan& P, double a, double b, double magnus_tol) {
 }
 
 static void ensure_aux_buffers(Plan& P) {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
         if (!P.aux[i]) CUDA_CHECK(cudaMalloc(&P.aux[i], sizeof(c2) * (size_t)P.D * P.B));
 }
 
@@ -509,10 +509,11 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
     const double gtol = (o && o->tol != 0.0) ? o->tol : 1e-8;
-    const bool extrap = o && o->extrapolate != 0;
+    // Richardson extrapolation: on by default (extrapolate = 0 or 1), -1 switches it off
+    const bool extrap = !(o && o->extrapolate < 0);
     const bool adaptive = gtol > 0.0;
     int Kmax = (o && o->max_step_samples > 0) ? o->max_step_samples
-                                               : env_int("PB200_MAX_STEP", adaptive ? 16 : 4);
+                                               : env_int("PB200_MAX_STEP", adaptive ? (extrap ? 64 : 16) : 4);
     int W = (o && o->refine_window >= 0) ? o->refine_window : env_int("PB200_REFINE_WINDOW", 8);
     const double tol_user = (o && o->cheb_tol > 0) ? o->cheb_tol : 0.0;
     double rtol = (o && o->rough_tol > 0) ? o->rough_tol : 1e-4;
@@ -551,8 +552,48 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         prog = Program();
     };
     const size_t flush_doubles = (size_t)8 << 20;  // 64 MiB of tables per chunk
+    const size_t state_bytes = sizeof(c2) * (size_t)P.D * P.B;
+    auto copy_state = [&](c2* dst, const c2* src) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, src, state_bytes, cudaMemcpyDeviceToDevice, P.stream));
+    };
+    auto max_diff2 = [&](const c2* x, const c2* y) {
+        const int nb = std::min(P.B, 4096);
+        CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * nb, P.stream));
+        const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
+        dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)nb);
+        diffnorm2_kernel<<<grid, 256, 0, P.stream>>>(x, y, P.D, P.d_scratch);
+        CUDA_CHECK(cudaGetLastError());
+        std::vector<double> d2(nb);
+        CUDA_CHECK(cudaMemcpyAsync(d2.data(), P.d_scratch, sizeof(double) * nb, cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        st.n_launches += 1;
+        double e = 0.0;
+        for (double v : d2) e = std::max(e, v);
+        return e;
+    };
+    // Richardson-extrapolated step: one CF4 step of h and two of h/2 from the same state,
+    // psi <- R2 + (R2 - R1) / (2^p - 1); the symmetric scheme gains two orders (6th for CF4)
+    auto extrap_step = [&](double a, double b2, double ctol) {
+        flush();
+        ensure_aux_buffers(P);
+        copy_state(P.aux[0], P.buf[P.cur]);
+        add_step(P, prog, a, b2, order, ctol);
+        flush();
+        copy_state(P.aux[1], P.buf[P.cur]);
+        copy_state(P.buf[P.cur], P.aux[0]);
+        const double mid = 0.5 * (a + b2);
+        add_step(P, prog, a, mid, order, ctol);
+        add_step(P, prog, mid, b2, order, ctol);
+        flush();
+        const double sc = std::pow(2.0, (order == 4) ? 4 : 2) - 1.0;
+        const long long total = P.D * (long long)P.B;
+        const long long nb = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
+        axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(P.buf[P.cur], P.aux[1], 1.0 + 1.0 / sc, -1.0 / sc, total);
+        CUDA_CHECK(cudaGetLastError());
+        st.n_launches += 1;
+    };
     // current smooth-step length in sampling intervals (real: < 1 means sub-steps)
-    double Kc = adaptive ? std::min(4.0, (double)Kmax) : (double)Kmax;
+    double Kc = adaptive ? std::min(extrap ? 8.0 : 4.0, (double)Kmax) : (double)Kmax;
     int since_check = 1 << 30;  // force a check at the first smooth step
     double smooth_len = 0.0; long long smooth_steps = 0;
     double t = t_start;
@@ -579,56 +620,59 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         b = std::min(b, t_stop);
         if (b <= t + eps) b = std::min(P.times[std::min(i + 1, nt - 1)], t_stop);
 
-        if (smooth && ((adaptive && since_check >= check_every) || extrap) && (P.D * (long long)P.B) <= (1LL << 31)) {
-            // ---- step-doubling check: one step of h against two of h/2 ----
-            flush();
-            ensure_aux_buffers(P);
-            const size_t bytes = sizeof(c2) * (size_t)P.D * P.B;
-            CUDA_CHECK(cudaMemcpyAsync(P.aux[0], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
-            const double ctol = adaptive ? cheb_tol_for(b - t, true) : 1e-13;
-            add_step(P, prog, t, b, order, ctol);
-            flush();
-            CUDA_CHECK(cudaMemcpyAsync(P.aux[1], P.buf[P.cur], bytes, cudaMemcpyDeviceToDevice, P.stream));
-            CUDA_CHECK(cudaMemcpyAsync(P.buf[P.cur], P.aux[0], bytes, cudaMemcpyDeviceToDevice, P.stream));
-            const double mid = 0.5 * (t + b);
-            add_step(P, prog, t, mid, order, ctol);
-            add_step(P, prog, mid, b, order, ctol);
-            flush();
-            CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * std::min(P.B, 4096), P.stream));
-            const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
-            dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)std::min(P.B, 4096));
-            diffnorm2_kernel<<<grid, 256, 0, P.stream>>>(P.buf[P.cur], P.aux[1], P.D, P.d_scratch);
-            CUDA_CHECK(cudaGetLastError());
-            std::vector<double> d2(std::min(P.B, 4096));
-            CUDA_CHECK(cudaMemcpyAsync(d2.data(), P.d_scratch, sizeof(double) * d2.size(), cudaMemcpyDeviceToHost, P.stream));
-            CUDA_CHECK(cudaStreamSynchronize(P.stream));
-            double e = 0.0;
-            for (double v : d2) e = std::max(e, v);
-            const int pw = (order == 4) ? 4 : 2;
-            if (extrap) {  // psi = R2 + (R2 - R1) / (2^pw - 1)
-                const double sc = std::pow(2.0, pw) - 1.0;
-                const long long total = P.D * (long long)P.B;
-                const long long nb = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
-                axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(P.buf[P.cur], P.aux[1], 1.0 + 1.0 / sc, -1.0 / sc, total);
-                CUDA_CHECK(cudaGetLastError());
-                st.n_launches += 1;
-            }
-            // two half steps carry 1/15 of the difference (4th order); the full step 16/15
-            const double scale = std::pow(2.0, pw) - 1.0;
-            const double err_big = std::sqrt(e) * std::pow(2.0, pw) / scale;
-            st.err_estimate += std::sqrt(e) / scale;
-            ++st.n_checks;
-            st.n_launches += 1;
-            // choose the step whose error rate meets the budget: err ~ h^(pw+1) per step
+        const bool can_aux = (P.D * (long long)P.B) <= (1LL << 31);
+        const bool do_check = smooth && adaptive && since_check >= check_every && can_aux;
+        if (smooth && (do_check || (extrap && can_aux))) {
             const double h_samples = (b - t) / hi_i;
-            const double rate = err_big / std::max(b - t, 1e-30);
-            double factor = 2.0;
-            // differences at the level of truncation / rounding noise carry no information
-            const double noise = 50.0 * ctol + 1e-14;
-            if (err_big > noise) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
-            factor = std::min(2.0, std::max(0.2, factor));
-            if (adaptive) Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
-            since_check = (factor < 0.7) ? check_every - 2 : 0;  // re-check soon after a big cut
+            const int pw_base = (order == 4) ? 4 : 2;
+            const double ctol = adaptive ? cheb_tol_for(b - t, do_check) : 1e-13;
+            double e = 0.0;  // squared distance of the two solutions compared by a check
+            if (!extrap) {
+                // plain step-doubling check: one step of h against two of h/2 (keep the latter)
+                flush();
+                ensure_aux_buffers(P);
+                copy_state(P.aux[0], P.buf[P.cur]);
+                add_step(P, prog, t, b, order, ctol);
+                flush();
+                copy_state(P.aux[1], P.buf[P.cur]);
+                copy_state(P.buf[P.cur], P.aux[0]);
+                const double mid = 0.5 * (t + b);
+                add_step(P, prog, t, mid, order, ctol);
+                add_step(P, prog, mid, b, order, ctol);
+                flush();
+                e = max_diff2(P.buf[P.cur], P.aux[1]);
+            } else if (!do_check) {
+                extrap_step(t, b, ctol);
+            } else {
+                // check of the extrapolated scheme: E(h) against E(h/2) o E(h/2)
+                flush();
+                ensure_aux_buffers(P);
+                copy_state(P.aux[2], P.buf[P.cur]);
+                extrap_step(t, b, ctol);
+                copy_state(P.aux[3], P.buf[P.cur]);
+                copy_state(P.buf[P.cur], P.aux[2]);
+                const double mid = 0.5 * (t + b);
+                extrap_step(t, mid, ctol);
+                extrap_step(mid, b, ctol);
+                e = max_diff2(P.buf[P.cur], P.aux[3]);
+            }
+            if (do_check) {
+                const int pw = extrap ? pw_base + 2 : pw_base;
+                const double scale = std::pow(2.0, pw) - 1.0;
+                const double err_big = std::sqrt(e) * std::pow(2.0, pw) / scale;
+                st.err_estimate += std::sqrt(e) / scale;
+                ++st.n_checks;
+                const double rate = err_big / std::max(b - t, 1e-30);
+                double factor = 2.0;
+                // differences at the level of truncation / rounding noise carry no information
+                const double noise = 50.0 * ctol + 1e-14;
+                if (err_big > noise) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
+                factor = std::min(2.0, std::max(0.2, factor));
+                Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
+                since_check = (factor < 0.7) ? check_every - 2 : 0;  // re-check soon after a big cut
+            } else {
+                ++since_check;
+            }
             ++st.n_steps; smooth_len += h_samples; ++smooth_steps;
         } else {
             add_step(P, prog, t, b, order, cheb_tol_for(b - t, false));
@@ -830,7 +874,7 @@ int pb200_plan_destroy(pb200_plan* h) {
     Plan& P = h->p;
     for (int i = 0; i < 3; ++i)
         if (P.buf[i]) cudaFree(P.buf[i]);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
         if (P.aux[i]) cudaFree(P.aux[i]);
     if (P.dint) cudaFree(P.dint);
     if (P.d_table) cudaFree(P.d_table);

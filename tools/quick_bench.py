@@ -19,7 +19,7 @@ def main():
                               "launches_per_apply": launches // 50,
                               "alg_GBs": round(40 * D / (per * 1e-3) / 1e9, 1)}))
             if n <= 22:
-                for K, tol in ((4, -1.0), (0, 0.0)):
+                for K, tol in ((0, 0.0),):
                     plan.set_state("all-ground")
                     t2 = time.time()
                     st = plan.propagate(0.0, spec.sampling_times[-1], max_step=K, tol=tol)
