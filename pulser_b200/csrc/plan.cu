@@ -416,7 +416,7 @@ static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, do
 
 // mark sampling intervals that must be stepped one by one
 static std::vector<char> fine_intervals(const Plan& P, int window, double rough_tol, double jump_tol,
-                                        std::vector<char>& jump) {
+                                        std::vector<char>& jump, std::vector<int>& dist) {
     const int nt = (int)P.times.size();
     std::vector<char> rough(nt, 0);
     jump.assign(std::max(nt - 1, 1), 0);
@@ -449,6 +449,13 @@ static std::vector<char> fine_intervals(const Plan& P, int window, double rough_
     for (int r = 0; r < nt; ++r)
         if (rough[r])
             for (int i = std::max(0, r - window); i <= std::min(nt - 2, r + window - 1); ++i) fine[i] = 1;
+    // distance (in intervals) from interval i to the nearest non-smooth sample
+    const int BIG = 1 << 28;
+    dist.assign(std::max(nt - 1, 1), BIG);
+    int last = -BIG;
+    for (int i = 0; i < nt - 1; ++i) { if (rough[i]) last = i; dist[i] = std::min(dist[i], i - last); }
+    last = BIG;
+    for (int i = nt - 2; i >= 0; --i) { if (rough[i + 1]) last = i + 1; dist[i] = std::min(dist[i], last - i); }
     return fine;
 }
 
@@ -524,7 +531,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     pb200_run_stats st{};
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
     std::vector<char> jump;
-    std::vector<char> fine = fine_intervals(P, W, rtol, 0.05, jump);
+    std::vector<int> dist;
+    std::vector<char> fine = fine_intervals(P, W, rtol, 0.05, jump, dist);
     for (size_t i = 0; i < fine.size(); ++i) if (jump[i]) fine[i] = 1;
     const double magnus_tol = 1e-11;
     const int nt = (int)P.times.size();
@@ -603,15 +611,18 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         double b;
         bool smooth = !fine[i];
         if (!smooth) {
+            since_check = 1 << 30;  // re-validate the step length when the smooth region resumes
             b = P.times[i + 1];
             if (jump[i] && order == 4) {
                 const int nsub = jump_substeps(P, t, std::min(b, t_stop), magnus_tol);
                 if (nsub > 1) b = std::min(b, t + hi_i / nsub);
             }
         } else if (Kc >= 1.0) {
-            const int K = std::max(1, std::min((int)std::floor(Kc + 1e-9), Kmax));
+            // graded steps: no longer than half the distance to the nearest non-smooth sample on either side
+            int K = std::max(1, std::min((int)std::floor(Kc + 1e-9), Kmax));
+            K = std::max(1, std::min(K, dist[i] / 2));
             int j = i, cnt = 0;
-            while (j < nt - 1 && !fine[j] && cnt < K) { ++j; ++cnt; }
+            while (j < nt - 1 && !fine[j] && cnt < K && (cnt == 0 || 2 * (cnt + 1) <= std::max(dist[j], 2))) { ++j; ++cnt; }
             b = P.times[j];
         } else {
             const int nsub = std::min(64, (int)std::ceil(1.0 / Kc - 1e-9));
