@@ -75,7 +75,7 @@ typedef struct pb200_plan_desc {
  * the fixed-order propagator and are accepted-and-ignored on the Python side). */
 typedef struct pb200_run_opts {
     int32_t max_step_samples; /* K: longest Magnus step, in sampling intervals
-                                 (>=1). 0 = library default (64 adaptive+extrapolated,
+                                 (>=1). 0 = library default (32 adaptive+extrapolated,
                                  16 adaptive, 4 fixed). */
     int32_t refine_window;    /* steps are 1 interval long within this many
                                  intervals of a non-smooth sample; <0 = default */

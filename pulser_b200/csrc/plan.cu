@@ -520,7 +520,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     const bool extrap = !(o && o->extrapolate < 0);
     const bool adaptive = gtol > 0.0;
     int Kmax = (o && o->max_step_samples > 0) ? o->max_step_samples
-                                               : env_int("PB200_MAX_STEP", adaptive ? (extrap ? 64 : 16) : 4);
+                                               : env_int("PB200_MAX_STEP", adaptive ? (extrap ? 32 : 16) : 4);
     int W = (o && o->refine_window >= 0) ? o->refine_window : env_int("PB200_REFINE_WINDOW", 8);
     const double tol_user = (o && o->cheb_tol > 0) ? o->cheb_tol : 0.0;
     double rtol = (o && o->rough_tol > 0) ? o->rough_tol : 1e-4;
@@ -535,6 +535,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     std::vector<char> fine = fine_intervals(P, W, rtol, 0.05, jump, dist);
     for (size_t i = 0; i < fine.size(); ++i) if (jump[i]) fine[i] = 1;
     const double magnus_tol = 1e-11;
+    const double rho_cap = 3.0;
     const int nt = (int)P.times.size();
     // error budget per unit of time: gtol over the whole sampling-time range
     const double rate_allowed = adaptive ? gtol / std::max(thi - tlo, 1e-30) : 0.0;
@@ -620,6 +621,17 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         } else if (Kc >= 1.0) {
             // graded steps: no longer than half the distance to the nearest non-smooth sample on either side
             int K = std::max(1, std::min((int)std::floor(Kc + 1e-9), Kmax));
+            {   // keep the step inside the convergence radius of the Magnus expansion: the spectral
+                // half-width of int H dt over the step stays below rho_cap (~pi)
+                std::vector<cplx> q0, q1; std::vector<double> r0, r1;
+                moments_for_step(P, t, std::min(P.times[i + 1], t_stop), q0, q1, r0, r1);
+                ExpParams E; E.g = q0; E.th = r0; E.w = std::min(P.times[i + 1], t_stop) - t;
+                double gm, rh1; std::vector<double> scratch_tab;
+                build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
+                const double frac = E.w / hi_i;  // fraction of a sampling interval covered by this probe
+                const double rho_per_sample = rh1 / std::max(frac, 1e-9);
+                K = std::max(1, std::min(K, (int)std::floor(rho_cap / std::max(rho_per_sample, 1e-12))));
+            }
             K = std::max(1, std::min(K, dist[i] / 2));
             int j = i, cnt = 0;
             while (j < nt - 1 && !fine[j] && cnt < K && (cnt == 0 || 2 * (cnt + 1) <= std::max(dist[j], 2))) { ++j; ++cnt; }

@@ -108,7 +108,7 @@ def test_dense_strongly_interacting_register(engine):
         st = plan.propagate(0.0, spec.sampling_times[-1])
         got = plan.get_state()[0]
     assert np.max(np.abs(got - ref)) < STATE_TOL
-    assert st["mean_step_samples"] < 4.0
+    assert st["mean_step_samples"] < 8.0  # dense register: the spectral-radius cap shortens the steps
 
 
 def test_local_noisy_trajectory_vs_oracle(engine):
