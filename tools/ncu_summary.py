@@ -1,0 +1,83 @@
+"""Turn ncu CSV exports into the small JSON/markdown summaries kept under profiles/.
+
+    python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r01_launches_summary.json
+    python tools/ncu_summary.py full gpurun_out/prof_stage.ncu-rep profiles/r01_stage_kernel_summary.json
+"""
+import csv
+import json
+import subprocess
+import sys
+from collections import defaultdict
+
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    h = rows[0]
+    k, m, v = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value")
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        if r[m] == "gpu__time_duration.sum":
+            name = r[k].split("(")[0]
+            agg[name][0] += 1
+            agg[name][1] += float(r[v].replace(",", ""))
+    total = sum(x[1] for x in agg.values())
+    res = {"unit": "ns", "total_ns": total, "kernels": [
+        {"kernel": n, "launches": c, "sum_ns": s, "avg_ns": s / c, "share": s / total}
+        for n, (c, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])]}
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum",
+    "lts__t_bytes.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "sm__cycles_elapsed.max",
+]
+
+
+def full(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    launches_ = []
+    for r in data:
+        d = {"kernel": r[idx["Kernel Name"]]}
+        for w in WANT:
+            if w in idx:
+                try:
+                    d[w] = float(r[idx[w]].replace(",", ""))
+                except ValueError:
+                    d[w] = r[idx[w]]
+                d[w + "|unit"] = units[idx[w]]
+        launches_.append(d)
+
+    def to_bytes(d, key):
+        u = d.get(key + "|unit", "byte")
+        f = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        return d.get(key, 0.0) * f
+
+    dram = [to_bytes(d, "dram__bytes_read.sum") + to_bytes(d, "dram__bytes_write.sum") for d in launches_]
+    res = {"source": rep, "n_launches_captured": len(launches_),
+           "dram_bytes_per_launch": sum(dram) / max(len(dram), 1), "launches": launches_}
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k != "launches"}, indent=1))
+    for d in launches_:
+        print({k: v for k, v in d.items() if not k.endswith("|unit")})
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
