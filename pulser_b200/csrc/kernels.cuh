@@ -248,48 +248,20 @@ __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
 // amplitude, all independent (fully unrolled) so that the shared-memory pipe
 // stays full.  Shared-memory operand traffic per amplitude and pass is
 // (flipped tile bits - RB + 1) x 16 B.
+// Compute phase of one tile, shared by the one-shot and the persistent kernels: gathers from the tile in
+// shared memory (register-blocked), optional global-load partners, fused epilogue and store.
 template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
-__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
-stage_d2_rb_kernel(StageArgs a) {
+__device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* __restrict__ tile,
+                                                const double* __restrict__ tab, long long base, long long traj,
+                                                int tid) {
     constexpr int R = 1 << RB;
     constexpr int NT = 1 << (TBITS - RB);
-    constexpr int TSIZE = 1 << TBITS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    c2* tile = reinterpret_cast<c2*>(smem_raw);
-    __shared__ __align__(8) uint64_t mbar;
-
-    const PassGeom g = a.geo;
-    const int tid = threadIdx.x;
-    const long long traj = blockIdx.y;
-    const long long tile_id = blockIdx.x;
-    const int mid_bits = g.hi_shift - g.lo_bits;
-    const long long mid = tile_id & ((1LL << mid_bits) - 1);
-    const long long top = tile_id >> mid_bits;
-    const long long base = (mid << g.lo_bits) | (top << (g.hi_shift + g.hi_bits));
     const long long voff = traj * a.D;
     const c2* vsrc = a.v + voff;
-
-    double* tab = reinterpret_cast<double*>(tile + TSIZE);
-    if (!UNIFORM) {
-        const int stride = d2_table_stride(g.n_bits);
-        const double* src = a.table + traj * stride;
-        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
-    }
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
-    {
-        const int rows = 1 << g.hi_bits;
-        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
-        for (int r = tid; r < rows; r += NT)
-            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
-    }
     const long long lomask = (1LL << g.lo_bits) - 1;
     const int to_bit = a.to_bit;
     // first tile bit whose flip belongs to this pass (pass A: 0, later passes: lo_bits)
     const int jstart = __ffs(g.tile_flip_mask) - 1;
-
-    mbar_wait(&mbar, 0);
 
     c2 v[R];
     double pr[R], pi[R], qr[R], qi[R];
@@ -459,6 +431,118 @@ stage_d2_rb_kernel(StageArgs a) {
                 st_c2(a.out + voff + idx[rr], cadd(ov[r], cmul(a.coef.c_g, c2{pr[rr], pi[rr]})));
             }
         }
+    }
+}
+
+__device__ __forceinline__ long long tile_base_of(const PassGeom& g, long long tile_id) {
+    // bits of tile_id fill positions [lo, hi_shift) and [hi_shift + hi_bits, N)
+    const int mid_bits = g.hi_shift - g.lo_bits;
+    const long long mid = tile_id & ((1LL << mid_bits) - 1);
+    const long long top = tile_id >> mid_bits;
+    return (mid << g.lo_bits) | (top << (g.hi_shift + g.hi_bits));
+}
+
+// programmatic dependent launch: wait for the producer grid's memory before the first global read
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- d = 2 tiled stage kernel, one tile per CTA --------------------------------
+// Each thread owns R = 2^RB amplitudes of the tile (tile index t = tid + r*NT,
+// i.e. the top RB tile bits live in registers): flips of those bits are
+// register-to-register, flips of the other tile bits cost one LDS.128 per owned
+// amplitude, all independent (fully unrolled) so that the shared-memory pipe
+// stays full.  Shared-memory operand traffic per amplitude and pass is
+// (flipped tile bits - RB + 1) x 16 B.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
+stage_d2_rb_kernel(StageArgs a) {
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+
+    const PassGeom g = a.geo;
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y;
+    const long long base = tile_base_of(g, blockIdx.x);
+    const c2* vsrc = a.v + traj * a.D;
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    pdl_wait();
+    pdl_launch_dependents();
+    double* tab = reinterpret_cast<double*>(tile + TSIZE);
+    if (!UNIFORM) {
+        const int stride = d2_table_stride(g.n_bits);
+        const double* src = a.table + traj * stride;
+        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
+    }
+    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
+    {
+        const int rows = 1 << g.hi_bits;
+        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+        for (int r = tid; r < rows; r += NT)
+            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
+}
+
+// ---- d = 2 tiled stage kernel, persistent with a TMA prefetch pipeline -----------
+// One CTA loops over work items (tile, trajectory) w = blockIdx.x + i*gridDim.x and keeps STAGES tiles in
+// flight: the bulk copies of item i+STAGES-1 are issued before item i is computed, so the L2/HBM latency
+// of a tile load overlaps the shared-memory phase of the previous one.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB, int STAGES>
+__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
+stage_d2_pipe_kernel(StageArgs a, long long tiles_per_traj, long long n_items) {
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tiles = reinterpret_cast<c2*>(smem_raw);
+    double* tab = reinterpret_cast<double*>(tiles + (size_t)STAGES * TSIZE);
+    __shared__ __align__(8) uint64_t mbar[STAGES];
+
+    const PassGeom g = a.geo;
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s) mbar_init(&mbar[s], 1);
+    pdl_wait();
+    pdl_launch_dependents();
+    __syncthreads();
+    const int rows = 1 << g.hi_bits;
+    const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+    auto issue = [&](long long w, int s) {
+        const long long traj = w / tiles_per_traj;
+        const long long base = tile_base_of(g, w - traj * tiles_per_traj);
+        const c2* vsrc = a.v + traj * a.D;
+        c2* dst = tiles + (size_t)s * TSIZE;
+        if (tid == 0) mbar_arrive_expect_tx(&mbar[s], (uint32_t)TSIZE * 16u);
+        for (int r = tid; r < rows; r += NT)
+            tma_load_1d(dst + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar[s]);
+    };
+    const long long w0 = blockIdx.x, dw = gridDim.x;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s)
+        if (w0 + s * dw < n_items) issue(w0 + s * dw, s);
+    long long tab_traj = -1;
+    int it = 0;
+    for (long long w = w0; w < n_items; w += dw, ++it) {
+        const int s = it % STAGES;
+        const long long wn = w + (long long)(STAGES - 1) * dw;
+        if (wn < n_items) issue(wn, (it + STAGES - 1) % STAGES);  // that stage was released by the barrier below
+        const long long traj = w / tiles_per_traj;
+        const long long base = tile_base_of(g, w - traj * tiles_per_traj);
+        if (!UNIFORM && traj != tab_traj) {
+            const int stride = d2_table_stride(g.n_bits);
+            const double* src = a.table + traj * stride;
+            for (int i = tid; i < stride; i += NT) tab[i] = src[i];
+            tab_traj = traj;
+            __syncthreads();
+        }
+        mbar_wait(&mbar[s], (uint32_t)((it / STAGES) & 1));
+        rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tiles + (size_t)s * TSIZE, tab, base, traj, tid);
+        __syncthreads();  // everyone is done with stage s (and with tab) before it is refilled
     }
 }
 

@@ -92,12 +92,28 @@ struct Plan {
     int sm_count = 148;
     bool force_v1 = false;
     int reg_bits = 3;
+    bool use_pipe = true;
+    bool use_pdl = true;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
         return true;
     }
 };
+
+// launch with (optional) programmatic dependent launch: the kernel's prologue overlaps the tail of the
+// previous stage kernel; the kernel itself executes griddepcontrol.wait before its first global read
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
 
 // ---------------------------------------------------------------------------
 static std::vector<PassGeom> plan_passes(int N, int TB, int EX) {
@@ -180,20 +196,42 @@ static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2*
             const int RBv = P.reg_bits;
             const bool rb_ok = (tbits == 11 || tbits == 12) && (geo.first_pass || geo.hi_bits >= RBv) && !P.force_v1;
             if (rb_ok) {
-                const size_t smem = (size_t)tsize * 16 + tab_bytes;
                 const int threads = tsize >> RBv;
-#define PB200_LAUNCH_RB(TB, RB)                                                                            \
-    do {                                                                                                 \
-        if (uniform) {                                                                                   \
-            if (real_g) stage_d2_rb_kernel<true, true, TB, RB><<<grid, threads, smem, P.stream>>>(a);    \
-            else stage_d2_rb_kernel<true, false, TB, RB><<<grid, threads, smem, P.stream>>>(a);          \
-        } else {                                                                                         \
-            stage_d2_rb_kernel<false, false, TB, RB><<<grid, threads, smem, P.stream>>>(a);              \
-        }                                                                                                \
+                const long long n_items = tiles * (long long)P.B;
+                const int ctas_per_sm = (tbits == 11 && RBv == 3) ? 2 : ((tbits == 11) ? 2 : 1);
+                const long long slots = (long long)P.sm_count * ctas_per_sm;
+                const bool pipe = P.use_pipe && n_items >= 2 * slots;
+                if (pipe) {
+                    const int stages = (tbits == 11) ? 3 : 2;
+                    const size_t smem = (size_t)stages * tsize * 16 + tab_bytes;
+                    dim3 pgrid((unsigned)slots);
+#define PB200_LAUNCH_PIPE(TB, RB, ST)                                                                          \
+    do {                                                                                                       \
+        if (uniform) {                                                                                         \
+            if (real_g) launch_k(stage_d2_pipe_kernel<true, true, TB, RB, ST>, pgrid, dim3(threads), smem, P.stream, P.use_pdl, a, tiles, n_items);  \
+            else launch_k(stage_d2_pipe_kernel<true, false, TB, RB, ST>, pgrid, dim3(threads), smem, P.stream, P.use_pdl, a, tiles, n_items);        \
+        } else {                                                                                               \
+            launch_k(stage_d2_pipe_kernel<false, false, TB, RB, ST>, pgrid, dim3(threads), smem, P.stream, P.use_pdl, a, tiles, n_items);            \
+        }                                                                                                      \
     } while (0)
-                if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_RB(11, 3); else PB200_LAUNCH_RB(11, 2); }
-                else { if (RBv == 3) PB200_LAUNCH_RB(12, 3); else PB200_LAUNCH_RB(12, 2); }
+                    if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_PIPE(11, 3, 3); else PB200_LAUNCH_PIPE(11, 2, 3); }
+                    else { if (RBv == 3) PB200_LAUNCH_PIPE(12, 3, 2); else PB200_LAUNCH_PIPE(12, 2, 2); }
+#undef PB200_LAUNCH_PIPE
+                } else {
+                    const size_t smem = (size_t)tsize * 16 + tab_bytes;
+#define PB200_LAUNCH_RB(TB, RB)                                                                                \
+    do {                                                                                                       \
+        if (uniform) {                                                                                         \
+            if (real_g) launch_k(stage_d2_rb_kernel<true, true, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, a);   \
+            else launch_k(stage_d2_rb_kernel<true, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, a);         \
+        } else {                                                                                               \
+            launch_k(stage_d2_rb_kernel<false, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, a);             \
+        }                                                                                                      \
+    } while (0)
+                    if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_RB(11, 3); else PB200_LAUNCH_RB(11, 2); }
+                    else { if (RBv == 3) PB200_LAUNCH_RB(12, 3); else PB200_LAUNCH_RB(12, 2); }
 #undef PB200_LAUNCH_RB
+                }
             } else {
                 int threads = std::min(256, std::max(32, tsize));
                 size_t smem = (size_t)tsize * 16 + tab_bytes;
@@ -856,6 +894,8 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 16));
     P.force_v1 = env_int("PB200_FORCE_V1", 0) != 0;
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
+    P.use_pipe = env_int("PB200_PIPE", 1) != 0;
+    P.use_pdl = env_int("PB200_PDL", 1) != 0;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;
@@ -881,6 +921,18 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 11, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 11, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 11, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 11, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 11, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 11, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
     } catch (...) {
         pb200_plan_destroy(h);
         throw;
