@@ -114,6 +114,13 @@ struct StageArgs {
     int from_is_one;
 };
 
+// up to two independent Clenshaw chains per launch (the h and the h/2 branches of a Richardson step):
+// blockIdx.y = chain * n_traj + trajectory
+struct StageArgs2 {
+    StageArgs a[2];
+    int n_traj;
+};
+
 template <bool UNIFORM, bool REAL_G>
 __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -455,16 +462,18 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // (flipped tile bits - RB + 1) x 16 B.
 template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
 __global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
-stage_d2_rb_kernel(StageArgs a) {
+stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
     constexpr int NT = 1 << (TBITS - RB);
     constexpr int TSIZE = 1 << TBITS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     c2* tile = reinterpret_cast<c2*>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;
 
+    const int chain = blockIdx.y / m.n_traj;
+    const StageArgs& a = m.a[chain];
     const PassGeom g = a.geo;
     const int tid = threadIdx.x;
-    const long long traj = blockIdx.y;
+    const long long traj = blockIdx.y - chain * m.n_traj;
     const long long base = tile_base_of(g, blockIdx.x);
     const c2* vsrc = a.v + traj * a.D;
 

@@ -72,7 +72,7 @@ struct Plan {
     bool own_stream = false;
     // device buffers
     c2* buf[3] = {nullptr, nullptr, nullptr};
-    c2* aux[4] = {nullptr, nullptr, nullptr, nullptr};  // step-doubling: saved states / full-step results
+    c2* aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..3] chain pools, [4..5] check copies
     int cur = 0;  // index of the current state buffer
     double* dint = nullptr;
     bool dint_shared = true;
@@ -92,7 +92,8 @@ struct Plan {
     int sm_count = 148;
     bool force_v1 = false;
     int reg_bits = 3;
-    bool use_pipe = true;
+    bool use_pipe = false;
+    bool use_dual = true;
     bool use_pdl = true;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
@@ -175,33 +176,55 @@ static inline size_t pidx(const Plan& P, int traj, int q, int row) {
     return ((size_t)traj * P.n_drives + q) * P.n + row;
 }
 
-static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
-                         c2* out, StageCoef coef, bool uniform, bool real_g, const UniformDrive& ud,
-                         const double* table, long long& launches) {
+struct StageIO {  // one Clenshaw stage of one chain
+    const c2* v; const c2* psi; const c2* b2; c2* out;
+    StageCoef coef; UniformDrive ud; const double* table; bool real_g;
+};
+
+static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io) {
+    StageArgs a{};
+    a.v = io.v; a.psi = io.psi; a.b2 = io.b2; a.out = io.out;
+    a.dint = P.has_interaction ? P.dint : nullptr;
+    a.dint_stride = P.dint_shared ? 0 : P.D;
+    a.D = P.D; a.geo = geo; a.coef = io.coef; a.u = io.ud; a.table = io.table;
+    a.to_bit = P.desc.drives[0].state_to;
+    a.from_is_one = P.desc.drives[0].state_from;
+    return a;
+}
+
+static bool rb_eligible(const Plan& P, const PassGeom& geo) {
+    const int tbits = geo.lo_bits + geo.hi_bits;
+    return (tbits == 11 || tbits == 12) && (geo.first_pass || geo.hi_bits >= P.reg_bits) && !P.force_v1;
+}
+
+// every pass of the geometry can carry two chains in one launch
+static bool dual_chain_ok(const Plan& P, const std::vector<PassGeom>& passes) {
+    if (!(P.dim == 2 && P.n_drives == 1) || !P.use_dual) return false;
+    for (const PassGeom& g : passes)
+        if (!rb_eligible(P, g)) return false;
+    return (long long)P.B * 2 <= 65535;
+}
+
+// launch one stage for `n` (1 or 2) chains
+static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, const StageIO* io, int n, bool uniform,
+                               long long& launches) {
     const int N = P.n;
     if (P.dim == 2 && P.n_drives == 1) {
+        bool real_g = true;
+        for (int c = 0; c < n; ++c) real_g = real_g && io[c].real_g;
         for (const PassGeom& geo : passes) {
-            StageArgs a{};
-            a.v = v; a.psi = psi; a.b2 = b2; a.out = out;
-            a.dint = P.has_interaction ? P.dint : nullptr;
-            a.dint_stride = P.dint_shared ? 0 : P.D;
-            a.D = P.D; a.geo = geo; a.coef = coef; a.u = ud; a.table = table;
-            a.to_bit = P.desc.drives[0].state_to;
-            a.from_is_one = P.desc.drives[0].state_from;
             const int tbits = geo.lo_bits + geo.hi_bits;
             const long long tiles = P.D >> tbits;
             const int tsize = 1 << tbits;
             const size_t tab_bytes = uniform ? 0 : (size_t)d2_table_stride(N) * 8;
-            dim3 grid((unsigned)tiles, (unsigned)P.B);
             const int RBv = P.reg_bits;
-            const bool rb_ok = (tbits == 11 || tbits == 12) && (geo.first_pass || geo.hi_bits >= RBv) && !P.force_v1;
-            if (rb_ok) {
+            if (rb_eligible(P, geo)) {
                 const int threads = tsize >> RBv;
                 const long long n_items = tiles * (long long)P.B;
-                const int ctas_per_sm = (tbits == 11 && RBv == 3) ? 2 : ((tbits == 11) ? 2 : 1);
-                const long long slots = (long long)P.sm_count * ctas_per_sm;
-                const bool pipe = P.use_pipe && n_items >= 2 * slots;
+                const long long slots = (long long)P.sm_count * ((tbits == 11) ? 2 : 1);
+                const bool pipe = P.use_pipe && n == 1 && n_items > slots;
                 if (pipe) {
+                    StageArgs a = make_stage_args(P, geo, io[0]);
                     const int stages = (tbits == 11) ? 3 : 2;
                     const size_t smem = (size_t)stages * tsize * 16 + tab_bytes;
                     dim3 pgrid((unsigned)slots);
@@ -217,48 +240,67 @@ static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2*
                     if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_PIPE(11, 3, 3); else PB200_LAUNCH_PIPE(11, 2, 3); }
                     else { if (RBv == 3) PB200_LAUNCH_PIPE(12, 3, 2); else PB200_LAUNCH_PIPE(12, 2, 2); }
 #undef PB200_LAUNCH_PIPE
+                    ++launches;
                 } else {
+                    StageArgs2 m{};
+                    for (int c = 0; c < n; ++c) m.a[c] = make_stage_args(P, geo, io[c]);
+                    m.n_traj = P.B;
+                    dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
                     const size_t smem = (size_t)tsize * 16 + tab_bytes;
 #define PB200_LAUNCH_RB(TB, RB)                                                                                \
     do {                                                                                                       \
         if (uniform) {                                                                                         \
-            if (real_g) launch_k(stage_d2_rb_kernel<true, true, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, a);   \
-            else launch_k(stage_d2_rb_kernel<true, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, a);         \
+            if (real_g) launch_k(stage_d2_rb_kernel<true, true, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);   \
+            else launch_k(stage_d2_rb_kernel<true, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);         \
         } else {                                                                                               \
-            launch_k(stage_d2_rb_kernel<false, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, a);             \
+            launch_k(stage_d2_rb_kernel<false, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);             \
         }                                                                                                      \
     } while (0)
                     if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_RB(11, 3); else PB200_LAUNCH_RB(11, 2); }
                     else { if (RBv == 3) PB200_LAUNCH_RB(12, 3); else PB200_LAUNCH_RB(12, 2); }
 #undef PB200_LAUNCH_RB
+                    ++launches;
                 }
             } else {
-                int threads = std::min(256, std::max(32, tsize));
-                size_t smem = (size_t)tsize * 16 + tab_bytes;
-                if (uniform) {
-                    if (real_g) stage_d2_kernel<true, true><<<grid, threads, smem, P.stream>>>(a);
-                    else stage_d2_kernel<true, false><<<grid, threads, smem, P.stream>>>(a);
-                } else {
-                    stage_d2_kernel<false, false><<<grid, threads, smem, P.stream>>>(a);
+                for (int c = 0; c < n; ++c) {
+                    StageArgs a = make_stage_args(P, geo, io[c]);
+                    dim3 grid((unsigned)tiles, (unsigned)P.B);
+                    int threads = std::min(256, std::max(32, tsize));
+                    size_t smem = (size_t)tsize * 16 + tab_bytes;
+                    if (uniform) {
+                        if (real_g) stage_d2_kernel<true, true><<<grid, threads, smem, P.stream>>>(a);
+                        else stage_d2_kernel<true, false><<<grid, threads, smem, P.stream>>>(a);
+                    } else {
+                        stage_d2_kernel<false, false><<<grid, threads, smem, P.stream>>>(a);
+                    }
+                    ++launches;
                 }
             }
-            ++launches;
         }
     } else {
-        GenArgs a{};
-        a.v = v; a.psi = psi; a.b2 = b2; a.out = out;
-        a.dint = P.has_interaction ? P.dint : nullptr;
-        a.dint_stride = P.dint_shared ? 0 : P.D;
-        a.D = P.D; a.n = N; a.dim = P.dim; a.n_drives = P.n_drives;
-        for (int q = 0; q < P.n_drives; ++q) { a.to[q] = P.desc.drives[q].state_to; a.from[q] = P.desc.drives[q].state_from; }
-        a.coef = coef; a.table = table;
-        int threads = 256;
-        long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
-        dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
-        size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8;
-        stage_generic_kernel<<<grid, threads, smem, P.stream>>>(a);
-        ++launches;
+        for (int c = 0; c < n; ++c) {
+            GenArgs a{};
+            a.v = io[c].v; a.psi = io[c].psi; a.b2 = io[c].b2; a.out = io[c].out;
+            a.dint = P.has_interaction ? P.dint : nullptr;
+            a.dint_stride = P.dint_shared ? 0 : P.D;
+            a.D = P.D; a.n = N; a.dim = P.dim; a.n_drives = P.n_drives;
+            for (int q = 0; q < P.n_drives; ++q) { a.to[q] = P.desc.drives[q].state_to; a.from[q] = P.desc.drives[q].state_from; }
+            a.coef = io[c].coef; a.table = io[c].table;
+            int threads = 256;
+            long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
+            dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
+            size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8;
+            stage_generic_kernel<<<grid, threads, smem, P.stream>>>(a);
+            ++launches;
+        }
     }
+}
+
+static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
+                         c2* out, StageCoef coef, bool uniform, bool real_g, const UniformDrive& ud,
+                         const double* table, long long& launches) {
+    StageIO io{v, psi, b2, out, coef, ud, table, real_g};
+    launch_stage_multi(P, passes, &io, 1, uniform, launches);
 }
 
 // Fill the device-table entry (host staging) of one exponential for all
@@ -357,53 +399,112 @@ static void ensure_table_capacity(Plan& P, size_t doubles) {
     P.d_table_cap = cap;
 }
 
-// apply exp(-iG) for every exponential in the program, in order
-static void run_program(Plan& P, const Program& prog, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
+// One chain = a program (sequence of exponentials) applied to a state with its own buffers.  `next` emits
+// the next Clenshaw stage; chains are independent, so two of them can share every kernel launch.
+struct Chain {
+    const Program* prog = nullptr;
+    size_t table_base = 0;   // offset of this program's tables in P.d_table
+    c2* psi = nullptr;       // input of the current exponential (never written by it)
+    c2* pool[3] = {nullptr, nullptr, nullptr};  // private buffers
+    bool psi_is_private = false;
+    // exponential / Clenshaw state
+    size_t e = 0; int j = -1;
+    const c2* b1_buf = nullptr; cplx b1_scale = 0.0;
+    int b2_kind = 0; c2* b2_buf = nullptr; cplx kappa = 0.0;
+    c2* out = nullptr;
+    c2* scratch[2] = {nullptr, nullptr};
+    long long applies = 0; double max_rho = 0.0;
+
+    bool done() const { return e >= prog->cheb.size(); }
+    c2* result() const { return psi; }
+
+    void begin_exponential() {
+        const std::vector<cplx>& a = prog->cheb[e];
+        const int m = (int)a.size() - 1;
+        j = m - 1;
+        b1_buf = psi; b1_scale = a[m];
+        b2_kind = 0; b2_buf = nullptr; kappa = 0.0; out = nullptr;
+        // scratch: the two private buffers that are not the input
+        int k = 0;
+        for (int i = 0; i < 3 && k < 2; ++i)
+            if (pool[i] != psi) scratch[k++] = pool[i];
+    }
+    // fill io for the next stage and advance; requires !done()
+    void next(const Plan& P, bool uniform, StageIO& io) {
+        if (j < 0) begin_exponential();
+        const std::vector<cplx>& a = prog->cheb[e];
+        const cplx ph = std::exp(cplx(0.0, -prog->gamma0[e]));
+        const double factor = (j == 0) ? 1.0 : 2.0;
+        const cplx phase = (j == 0) ? ph : cplx(1.0, 0.0);
+        const cplx cg = phase * factor * b1_scale;
+        const cplx cpsi = phase * (a[j] - (b2_kind == 2 ? kappa : cplx(0.0)));
+        const cplx cb2 = (b2_kind == 1) ? -phase : cplx(0.0);
+        if (b2_kind == 1) out = b2_buf;
+        else out = (scratch[0] != b1_buf) ? scratch[0] : scratch[1];
+        io.v = b1_buf; io.psi = psi; io.b2 = (b2_kind == 1) ? b2_buf : nullptr; io.out = out;
+        io.coef = StageCoef{{cpsi.real(), cpsi.imag()}, {cb2.real(), cb2.imag()}, {cg.real(), cg.imag()}};
+        io.ud = prog->ud[e];
+        io.table = uniform ? nullptr : P.d_table + table_base + prog->offset[e];
+        io.real_g = prog->real_g[e] != 0;
+        // shift the recurrence
+        if (b1_buf == psi) { b2_kind = 2; kappa = b1_scale; b2_buf = nullptr; }
+        else { b2_kind = 1; b2_buf = const_cast<c2*>(b1_buf); }
+        b1_buf = out; b1_scale = 1.0;
+        if (--j < 0) {  // exponential finished: its result becomes the next input
+            applies += (long long)a.size() - 1;
+            max_rho = std::max(max_rho, prog->rho[e]);
+            if (!psi_is_private) {
+                // the shared input stays untouched; the third private buffer joins the rotation
+                psi_is_private = true;
+            }
+            psi = out;
+            ++e;
+        }
+    }
+};
+
+static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
     const bool d2path = (P.dim == 2 && P.n_drives == 1);
     const bool uniform = d2path && P.all_uniform() && P.B == 1;
     if (!uniform) {
-        ensure_table_capacity(P, prog.tables.size());
-        CUDA_CHECK(cudaMemcpyAsync(P.d_table, prog.tables.data(), prog.tables.size() * sizeof(double),
-                                   cudaMemcpyHostToDevice, P.stream));
+        size_t total = 0;
+        for (int c = 0; c < n; ++c) { chains[c].table_base = total; total += chains[c].prog->tables.size(); }
+        ensure_table_capacity(P, total);
+        for (int c = 0; c < n; ++c)
+            if (!chains[c].prog->tables.empty())
+                CUDA_CHECK(cudaMemcpyAsync(P.d_table + chains[c].table_base, chains[c].prog->tables.data(),
+                                           chains[c].prog->tables.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                           P.stream));
     }
     long long launches = 0;
-    for (size_t e = 0; e < prog.cheb.size(); ++e) {
-        const std::vector<cplx>& a = prog.cheb[e];
-        const int m = (int)a.size() - 1;
-        const cplx ph = std::exp(cplx(0.0, -prog.gamma0[e]));
-        const double* table = uniform ? nullptr : P.d_table + prog.offset[e];
-        c2* psi = P.buf[P.cur];
-        c2* scratch[2] = {P.buf[(P.cur + 1) % 3], P.buf[(P.cur + 2) % 3]};
-        // Clenshaw state
-        const c2* b1_buf = psi; cplx b1_scale = a[m];
-        int b2_kind = 0;  // 0 zero, 1 buffer, 2 virtual kappa*psi
-        c2* b2_buf = nullptr; cplx kappa = 0.0;
-        c2* out = nullptr;
-        for (int j = m - 1; j >= 0; --j) {
-            const double factor = (j == 0) ? 1.0 : 2.0;
-            const cplx phase = (j == 0) ? ph : cplx(1.0, 0.0);
-            const cplx cg = phase * factor * b1_scale;
-            const cplx cpsi = phase * (a[j] - (b2_kind == 2 ? kappa : cplx(0.0)));
-            const cplx cb2 = (b2_kind == 1) ? -phase : cplx(0.0);
-            if (b2_kind == 1) out = b2_buf;
-            else out = (scratch[0] != b1_buf) ? scratch[0] : scratch[1];
-            StageCoef sc{{cpsi.real(), cpsi.imag()}, {cb2.real(), cb2.imag()}, {cg.real(), cg.imag()}};
-            launch_stage(P, passes, b1_buf, psi, (b2_kind == 1) ? b2_buf : nullptr, out, sc, uniform,
-                         prog.real_g[e] != 0, prog.ud[e], table, launches);
-            // shift
-            if (b1_buf == psi) { b2_kind = 2; kappa = b1_scale; b2_buf = nullptr; }
-            else { b2_kind = 1; b2_buf = const_cast<c2*>(b1_buf); }
-            b1_buf = out; b1_scale = 1.0;
-        }
-        // result is in `out`
-        for (int i = 0; i < 3; ++i)
-            if (P.buf[i] == out) P.cur = i;
-        st.n_applies += m;
-        st.max_rho = std::max(st.max_rho, prog.rho[e]);
+    StageIO io[2];
+    while (true) {
+        int k = 0;
+        for (int c = 0; c < n; ++c)
+            if (!chains[c].done()) chains[c].next(P, uniform, io[k++]);
+        if (k == 0) break;
+        launch_stage_multi(P, passes, io, k, uniform, launches);
     }
     CUDA_CHECK(cudaGetLastError());
     st.n_launches += launches;
-    st.n_exponentials += (long long)prog.cheb.size();
+    for (int c = 0; c < n; ++c) {
+        st.n_applies += chains[c].applies;
+        st.max_rho = std::max(st.max_rho, chains[c].max_rho);
+        st.n_exponentials += (long long)chains[c].prog->cheb.size();
+    }
+}
+
+// apply exp(-iG) for every exponential in the program, in order, to the current state
+static void run_program(Plan& P, const Program& prog, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
+    if (prog.cheb.empty()) return;
+    Chain ch;
+    ch.prog = &prog;
+    ch.psi = P.buf[P.cur];
+    ch.psi_is_private = true;
+    for (int i = 0; i < 3; ++i) ch.pool[i] = P.buf[i];
+    run_chains(P, &ch, 1, passes, st);
+    for (int i = 0; i < 3; ++i)
+        if (P.buf[i] == ch.result()) P.cur = i;
 }
 
 // ---------------------------------------------------------------------------
@@ -539,7 +640,7 @@ static int jump_substeps(const Plan& P, double a, double b, double magnus_tol) {
 }
 
 static void ensure_aux_buffers(Plan& P) {
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
         if (!P.aux[i]) CUDA_CHECK(cudaMalloc(&P.aux[i], sizeof(c2) * (size_t)P.D * P.B));
 }
 
@@ -620,21 +721,50 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     };
     // Richardson-extrapolated step: one CF4 step of h and two of h/2 from the same state,
     // psi <- R2 + (R2 - R1) / (2^p - 1); the symmetric scheme gains two orders (6th for CF4)
+    const bool dual_ok = dual_chain_ok(P, passes);
     auto extrap_step = [&](double a, double b2, double ctol) {
         flush();
         ensure_aux_buffers(P);
+        const double mid = 0.5 * (a + b2);
+        const double sc = std::pow(2.0, (order == 4) ? 4 : 2) - 1.0;
+        const long long total = P.D * (long long)P.B;
+        const long long nb = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
+        if (dual_ok) {
+            // the h branch and the h/2 branch start from the same state and are independent: they run as two
+            // chains sharing every kernel launch, each in its own buffers (no state copies at all)
+            Program big, half;
+            add_step(P, big, a, b2, order, ctol);
+            add_step(P, half, a, mid, order, ctol);
+            add_step(P, half, mid, b2, order, ctol);
+            c2* X = P.buf[P.cur];
+            c2* others[6]; int k = 0;
+            for (int i = 0; i < 3; ++i) if (i != P.cur) others[k++] = P.buf[i];
+            for (int i = 0; i < 4; ++i) others[k++] = P.aux[i];
+            Chain ch[2];
+            ch[0].prog = &half; ch[0].psi = X; for (int i = 0; i < 3; ++i) ch[0].pool[i] = others[i];
+            ch[1].prog = &big;  ch[1].psi = X; for (int i = 0; i < 3; ++i) ch[1].pool[i] = others[3 + i];
+            run_chains(P, ch, 2, passes, st);
+            c2* res = ch[0].result();
+            axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(res, ch[1].result(), 1.0 + 1.0 / sc, -1.0 / sc, total);
+            CUDA_CHECK(cudaGetLastError());
+            st.n_launches += 1;
+            // make `res` the current state buffer (swap pointer slots if it lives in the aux set)
+            bool found = false;
+            for (int i = 0; i < 3; ++i) if (P.buf[i] == res) { P.cur = i; found = true; }
+            if (!found)
+                for (int i = 0; i < 4; ++i) if (P.aux[i] == res) { std::swap(P.aux[i], P.buf[P.cur]); break; }
+            if (!(P.dim == 2 && P.n_drives == 1 && P.all_uniform() && P.B == 1))
+                CUDA_CHECK(cudaStreamSynchronize(P.stream));  // tables of big/half were uploaded from this scope
+            return;
+        }
         copy_state(P.aux[0], P.buf[P.cur]);
         add_step(P, prog, a, b2, order, ctol);
         flush();
         copy_state(P.aux[1], P.buf[P.cur]);
         copy_state(P.buf[P.cur], P.aux[0]);
-        const double mid = 0.5 * (a + b2);
         add_step(P, prog, a, mid, order, ctol);
         add_step(P, prog, mid, b2, order, ctol);
         flush();
-        const double sc = std::pow(2.0, (order == 4) ? 4 : 2) - 1.0;
-        const long long total = P.D * (long long)P.B;
-        const long long nb = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
         axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(P.buf[P.cur], P.aux[1], 1.0 + 1.0 / sc, -1.0 / sc, total);
         CUDA_CHECK(cudaGetLastError());
         st.n_launches += 1;
@@ -708,14 +838,14 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
                 // check of the extrapolated scheme: E(h) against E(h/2) o E(h/2)
                 flush();
                 ensure_aux_buffers(P);
-                copy_state(P.aux[2], P.buf[P.cur]);
+                copy_state(P.aux[4], P.buf[P.cur]);
                 extrap_step(t, b, ctol);
-                copy_state(P.aux[3], P.buf[P.cur]);
-                copy_state(P.buf[P.cur], P.aux[2]);
+                copy_state(P.aux[5], P.buf[P.cur]);
+                copy_state(P.buf[P.cur], P.aux[4]);
                 const double mid = 0.5 * (t + b);
                 extrap_step(t, mid, ctol);
                 extrap_step(mid, b, ctol);
-                e = max_diff2(P.buf[P.cur], P.aux[3]);
+                e = max_diff2(P.buf[P.cur], P.aux[5]);
             }
             if (do_check) {
                 const int pw = extrap ? pw_base + 2 : pw_base;
@@ -894,7 +1024,8 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 16));
     P.force_v1 = env_int("PB200_FORCE_V1", 0) != 0;
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
-    P.use_pipe = env_int("PB200_PIPE", 1) != 0;
+    P.use_pipe = env_int("PB200_PIPE", 0) != 0;
+    P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
@@ -949,7 +1080,7 @@ int pb200_plan_destroy(pb200_plan* h) {
     Plan& P = h->p;
     for (int i = 0; i < 3; ++i)
         if (P.buf[i]) cudaFree(P.buf[i]);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
         if (P.aux[i]) cudaFree(P.aux[i]);
     if (P.dint) cudaFree(P.dint);
     if (P.d_table) cudaFree(P.d_table);
