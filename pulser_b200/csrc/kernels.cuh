@@ -112,6 +112,7 @@ struct StageArgs {
     const double* table;       // [B][stride] for this exponential (non-uniform)
     int to_bit;
     int from_is_one;
+    int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
 };
 
 // up to two independent Clenshaw chains per launch (the h and the h/2 branches of a Richardson step):
@@ -305,7 +306,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
     // --- flips served from shared memory ---
 #pragma unroll
     for (int j = 0; j < TBITS - RB; ++j) {
-        if (j >= jstart) {
+        if (j >= jstart && !(a.dbg & 1)) {
             const int bit = (tid >> j) & 1;
             const int ptid = tid ^ (1 << j);
             double gx = 0.0, gy = 0.0;
@@ -336,7 +337,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         idx[r] = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
     }
     // --- flips served by coalesced global loads (bits outside the tile) ---
-    for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
+    for (unsigned long long m = (a.dbg & 2) ? 0ULL : g.extra_mask; m; m &= m - 1) {
         const int p = __ffsll((long long)m) - 1;
         double gx = 0.0, gyt = 0.0;
         if (!UNIFORM) { gx = tab[2 * p]; gyt = tab[2 * p + 1]; }
@@ -397,7 +398,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
     // of one half are all in flight together (the stores to `out` may alias them for the compiler)
     constexpr int H = (R >= 4) ? R / 2 : R;
     if (g.first_pass) {
-        const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
+        const double* dsrc = (a.dint && !(a.dbg & 4)) ? a.dint + traj * a.dint_stride : nullptr;
 #pragma unroll
         for (int h0 = 0; h0 < R; h0 += H) {
             double dv[H];
@@ -423,7 +424,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 c2 res = cmul(a.coef.c_g, gv);
                 res = cadd(res, cmul(a.coef.c_psi, pv[r]));
                 res = cadd(res, cmul(a.coef.c_b2, bv[r]));
-                st_c2(a.out + voff + idx[rr], res);
+                if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
             }
         }
     } else {

@@ -94,6 +94,7 @@ struct Plan {
     int reg_bits = 3;
     bool use_pipe = false;
     bool use_dual = true;
+    int dbg = 0;
     bool use_pdl = true;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
@@ -189,6 +190,7 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.D = P.D; a.geo = geo; a.coef = io.coef; a.u = io.ud; a.table = io.table;
     a.to_bit = P.desc.drives[0].state_to;
     a.from_is_one = P.desc.drives[0].state_from;
+    a.dbg = P.dbg;
     return a;
 }
 
@@ -1026,6 +1028,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
     P.use_pipe = env_int("PB200_PIPE", 0) != 0;
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
+    P.dbg = env_int("PB200_DBG", 0);
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
