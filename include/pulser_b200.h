@@ -138,6 +138,21 @@ int pb200_plan_set_interaction(pb200_plan* plan, int32_t traj0, int32_t count,
 int pb200_plan_set_drive(pb200_plan* plan, int32_t drive, int32_t traj0,
                          int32_t count, const double* coef, const double* det);
 
+/* Lindblad master equation (replaces qutip.mesolve(H, rho0, tlist, c_ops),
+ * simulation.py:724-735).  The plan must describe the VECTORISED density matrix
+ * as a system of 2N qudits: qudits 0..N-1 = row digits evolving under H,
+ * qudits N..2N-1 = column digits evolving under -H^T (drive -conj(c), detuning
+ * -det, interaction -U); the Python layer builds that description
+ * (pulser_b200/lindblad.py).  `generators` holds, for each of the n_pairs = N
+ * qudits, the d^2 x d^2 superoperator  sum_L ( L (x) conj(L) - 1/2 L^+L (x) 1
+ * - 1/2 1 (x) (L^+L)^T )  of its collapse operators (hamiltonian.py:97-124),
+ * row-major, interleaved complex, acting on the (row digit, column digit) pair
+ * (k, k + N).  Afterwards pb200_propagate integrates  rho' = -i[H,rho] + D(rho)
+ * by symmetric splitting  exp(h/2 D) U(h) exp(h/2 D)  with Richardson
+ * extrapolation and the same step controller (order 2 -> 4).  d <= 3. */
+int pb200_plan_set_dissipator(pb200_plan* plan, int32_t n_pairs,
+                              const double* generators);
+
 /* ---- state --------------------------------------------------------------- */
 /* Upload initial states psi[count][D] (interleaved complex); psi == NULL sets
  * basis state `basis_index` (e.g. all-ground, simulation.py:498-505) for the

@@ -95,6 +95,9 @@ struct Plan {
     bool use_pipe = false;
     bool use_dual = true;
     int dbg = 0;
+    // Lindblad: per-qudit generators of the dissipator on the (row, column) digit pair
+    std::vector<std::vector<cplx>> diss_gen;
+    bool has_diss = false;
     bool use_pdl = true;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
@@ -390,6 +393,8 @@ struct Program {  // a batch of exponentials prepared on the host
     std::vector<std::vector<cplx>> cheb;
     std::vector<UniformDrive> ud;
     std::vector<char> real_g;
+    // Lindblad splitting: dissipator exp(h D) applied before / after exponential e (0 = none)
+    std::vector<double> pre_diss, post_diss;
 };
 
 static void ensure_table_capacity(Plan& P, size_t doubles) {
@@ -465,6 +470,8 @@ struct Chain {
     }
 };
 
+static void apply_dissipator(Plan& P, c2* buf, double h, long long& launches);
+
 static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
     const bool d2path = (P.dim == 2 && P.n_drives == 1);
     const bool uniform = d2path && P.all_uniform() && P.B == 1;
@@ -480,12 +487,23 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
     }
     long long launches = 0;
     StageIO io[2];
+    if (P.has_diss && n != 1) fail(PB200_ERR_STATE, "internal: Lindblad splitting runs one chain at a time");
     while (true) {
         int k = 0;
+        size_t e_before = 0;
         for (int c = 0; c < n; ++c)
-            if (!chains[c].done()) chains[c].next(P, uniform, io[k++]);
+            if (!chains[c].done()) {
+                if (P.has_diss) {
+                    e_before = chains[c].e;
+                    if (chains[c].j < 0 && chains[c].prog->pre_diss[e_before] > 0.0)
+                        apply_dissipator(P, chains[c].psi, chains[c].prog->pre_diss[e_before], launches);
+                }
+                chains[c].next(P, uniform, io[k++]);
+            }
         if (k == 0) break;
         launch_stage_multi(P, passes, io, k, uniform, launches);
+        if (P.has_diss && chains[0].e != e_before && chains[0].prog->post_diss[e_before] > 0.0)
+            apply_dissipator(P, chains[0].psi, chains[0].prog->post_diss[e_before], launches);
     }
     CUDA_CHECK(cudaGetLastError());
     st.n_launches += launches;
@@ -553,6 +571,61 @@ static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, do
     ud.to_bit = P.desc.drives[0].state_to;
     prog.ud.push_back(ud);
     prog.real_g.push_back(g.imag() == 0.0 ? 1 : 0);
+    prog.pre_diss.push_back(0.0);
+    prog.post_diss.push_back(0.0);
+}
+
+// exp(h*A) of a small dense matrix (scaling and squaring, Taylor order 20)
+static std::vector<cplx> small_expm(const std::vector<cplx>& A, int n, double h) {
+    double nrm = 0.0;
+    for (const cplx& z : A) nrm = std::max(nrm, std::abs(z) * std::fabs(h));
+    nrm *= n;
+    int sq = 0;
+    while (nrm > 0.25 && sq < 60) { nrm *= 0.5; ++sq; }
+    const double sc = h / std::pow(2.0, sq);
+    std::vector<cplx> X(A.size()), T(n * n, cplx(0)), R(n * n, cplx(0)), Tn(n * n);
+    for (size_t i = 0; i < A.size(); ++i) X[i] = A[i] * sc;
+    for (int i = 0; i < n; ++i) { T[i * n + i] = 1.0; R[i * n + i] = 1.0; }
+    for (int k = 1; k <= 20; ++k) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                cplx acc = 0.0;
+                for (int l = 0; l < n; ++l) acc += T[i * n + l] * X[l * n + j];
+                Tn[i * n + j] = acc / (double)k;
+            }
+        T = Tn;
+        for (int i = 0; i < n * n; ++i) R[i] += T[i];
+    }
+    for (int q = 0; q < sq; ++q) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                cplx acc = 0.0;
+                for (int l = 0; l < n; ++l) acc += R[i * n + l] * R[l * n + j];
+                Tn[i * n + j] = acc;
+            }
+        R = Tn;
+    }
+    return R;
+}
+
+// rho <- exp(h D) rho on the vectorised density matrix in `buf` (all trajectories)
+static void apply_dissipator(Plan& P, c2* buf, double h, long long& launches) {
+    const int npairs = (int)P.diss_gen.size();
+    const int dd = P.dim * P.dim;
+    for (int k = 0; k < npairs; ++k) {
+        const std::vector<cplx> E = small_expm(P.diss_gen[k], dd, h);
+        PairOp op{};
+        for (int i = 0; i < dd * dd; ++i) op.m[i] = {E[i].real(), E[i].imag()};
+        long long s_hi = 1, s_lo = 1;
+        for (int i = 0; i < P.n - 1 - k; ++i) s_hi *= P.dim;            // row qudit k
+        for (int i = 0; i < P.n - 1 - (k + npairs); ++i) s_lo *= P.dim;  // column qudit k + N
+        const long long groups = P.D / dd;
+        const long long blocks = std::min<long long>((groups + 255) / 256, (long long)P.sm_count * 16);
+        dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
+        pair_op_kernel<<<grid, 256, 0, P.stream>>>(buf, P.D, P.dim, s_hi, s_lo, op);
+        ++launches;
+    }
+    CUDA_CHECK(cudaGetLastError());
 }
 
 // mark sampling intervals that must be stepped one by one
@@ -606,6 +679,16 @@ static void add_step(const Plan& P, Program& prog, double a, double b, int order
     moments_for_step(P, a, b, g0, g1, th0, th1);
     const double h = b - a;
     const size_t cnt = g0.size();
+    const size_t first = prog.cheb.size();
+    struct DissMark {  // symmetric splitting exp(h/2 D) U(h) exp(h/2 D) around the unitary part of the step
+        const Plan& P; Program& prog; size_t first; double h;
+        ~DissMark() {
+            if (P.has_diss && prog.cheb.size() > first) {
+                prog.pre_diss[first] = 0.5 * h;
+                prog.post_diss[prog.cheb.size() - 1] = 0.5 * h;
+            }
+        }
+    } mark{P, prog, first, h};
     if (order == 4) {
         ExpParams E1, E2;
         E1.g.resize(cnt); E1.th.resize(cnt); E2.g.resize(cnt); E2.th.resize(cnt);
@@ -656,7 +739,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
-    const double gtol = (o && o->tol != 0.0) ? o->tol : 1e-8;
+    const double gtol = (o && o->tol != 0.0) ? o->tol : (P.has_diss ? 1e-6 : 1e-8);
     // Richardson extrapolation: on by default (extrapolate = 0 or 1), -1 switches it off
     const bool extrap = !(o && o->extrapolate < 0);
     const bool adaptive = gtol > 0.0;
@@ -723,12 +806,15 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     };
     // Richardson-extrapolated step: one CF4 step of h and two of h/2 from the same state,
     // psi <- R2 + (R2 - R1) / (2^p - 1); the symmetric scheme gains two orders (6th for CF4)
-    const bool dual_ok = dual_chain_ok(P, passes);
+    const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss;
+    // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
+    // a symmetric 2nd-order scheme whatever the order of its unitary part
+    const int pw_base = P.has_diss ? 2 : ((order == 4) ? 4 : 2);
     auto extrap_step = [&](double a, double b2, double ctol) {
         flush();
         ensure_aux_buffers(P);
         const double mid = 0.5 * (a + b2);
-        const double sc = std::pow(2.0, (order == 4) ? 4 : 2) - 1.0;
+        const double sc = std::pow(2.0, pw_base) - 1.0;
         const long long total = P.D * (long long)P.B;
         const long long nb = std::min<long long>((total + 255) / 256, (long long)P.sm_count * 16);
         if (dual_ok) {
@@ -817,7 +903,6 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         const bool do_check = smooth && adaptive && since_check >= check_every && can_aux;
         if (smooth && (do_check || (extrap && can_aux))) {
             const double h_samples = (b - t) / hi_i;
-            const int pw_base = (order == 4) ? 4 : 2;
             const double ctol = adaptive ? cheb_tol_for(b - t, do_check) : 1e-13;
             double e = 0.0;  // squared distance of the two solutions compared by a check
             if (!extrap) {
@@ -1191,6 +1276,25 @@ int pb200_plan_set_drive(pb200_plan* h, int32_t drive, int32_t traj0, int32_t co
         }
         P.tabs_set[traj0 + c][drive] = true;
     }
+    PB200_CATCH
+}
+
+int pb200_plan_set_dissipator(pb200_plan* h, int32_t n_pairs, const double* generators) {
+    PB200_TRY
+    if (!h || !generators) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (P.dim > 3) fail(PB200_ERR_UNSUPPORTED, "dissipator: d <= 3 only");
+    if (n_pairs < 1 || 2 * n_pairs != P.n) fail(PB200_ERR_INVALID, "dissipator: the plan must hold 2*n_pairs qudits");
+    const int dd = P.dim * P.dim;
+    P.diss_gen.assign(n_pairs, std::vector<cplx>((size_t)dd * dd));
+    const cplx* src = reinterpret_cast<const cplx*>(generators);
+    for (int k = 0; k < n_pairs; ++k)
+        for (int i = 0; i < dd * dd; ++i) {
+            const cplx z = src[(size_t)k * dd * dd + i];
+            if (!std::isfinite(z.real()) || !std::isfinite(z.imag())) fail(PB200_ERR_INVALID, "non-finite generator");
+            P.diss_gen[k][i] = z;
+        }
+    P.has_diss = true;
     PB200_CATCH
 }
 

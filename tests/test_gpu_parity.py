@@ -190,3 +190,47 @@ def test_pass_geometries(engine, monkeypatch, tile_bits, max_extra, reg_bits):
             got = plan.apply_h(0.0123, v)
         ref = mf.apply(0.0123, v)
         assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+# ---------------------------------------------------------------------------
+# Lindblad master equation (mesolve replacement); north_star tolerance 1e-4
+LINDBLAD_TOL = 1e-4
+
+
+def _lindblad_spec(n, T, ops, seed=0):
+    from pulser_b200.spec import HamiltonianSpec
+
+    amp, det = W.blockade_sweep_waveforms(t_rise=T // 4, t_sweep=T // 2, t_fall=T // 4)
+    coords = W.disc_register(n, 12.0, 5.0, seed + 3)
+    spec = W.ising_global_spec(coords, W.C6_LEVEL_60, amp, det)
+    spec.collapse_ops = np.asarray(ops, dtype=complex)
+    return spec
+
+
+@pytest.mark.parametrize("n,kind", [(2, "dephasing+relaxation"), (4, "dephasing+relaxation"), (3, "depolarizing")])
+def test_lindblad_vs_oracle_mesolve(engine, n, kind):
+    """Density-matrix evolution against the dense-Lindblad oracle (qutip.mesolve restatement)."""
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+    from pulser_b200.lindblad import LindbladPlan
+
+    if kind == "depolarizing":  # sqrt(G/4) X, Y, Z (hamiltonian_data.py:699-716)
+        g = np.sqrt(0.4 / 4)
+        ops = [g * np.array([[0, 1], [1, 0]]), g * np.array([[0, -1j], [1j, 0]]), g * np.array([[1, 0], [0, -1]])]
+    else:  # sqrt(2 G_d)|r><r| and sqrt(G_rel)|g><r| in the [r, g] eigenbasis
+        ops = [np.sqrt(2 * 0.3) * np.array([[1, 0], [0, 0]]), np.sqrt(0.2) * np.array([[0, 0], [1, 0]])]
+    spec = _lindblad_spec(n, 400, ops)
+    tf = spec.sampling_times[-1]
+    H = OracleHamiltonian.from_spec(spec)
+    psi0 = evolve.all_ground_state(spec)
+    ref = evolve.mesolve(H, psi0, [0.0, tf])[-1]
+    with LindbladPlan(spec) as lp:
+        lp.set_state(psi0)
+        st = lp.propagate(0.0, tf)
+        rho = lp.get_rho()[0]
+    assert st["n_launches"] > 0
+    assert abs(np.trace(rho).real - 1.0) < 1e-6
+    assert np.max(np.abs(rho - rho.conj().T)) < 1e-8
+    assert np.max(np.abs(rho - ref)) < LINDBLAD_TOL
+    # populations decohered: purity below one
+    assert np.trace(rho @ rho).real < 0.999
