@@ -10,8 +10,10 @@ reference's own pulser-core code; ``Hamiltonian(...)`` construction
 (``simulation.py:299-311``) and ``_run_solver`` (``:689-766``) are replaced by
 ``HamiltonianSpec`` -> ``DevicePlan`` -> ``pb200_propagate``.
 
-Not yet on the CUDA path (raise ``NotImplementedError``): collapse operators
-(mesolve / mcsolve, ``simulation.py:705-735``) and the XY interaction.
+Collapse operators (``simulation.py:705-735``) run as a master equation on the
+vectorised density matrix (``lindblad.py``, registers with dim^(2N) <= 2^26).
+Not yet on the CUDA path (raise ``NotImplementedError``): wave-function Monte
+Carlo for larger registers and the XY interaction.
 """
 from __future__ import annotations
 
@@ -23,7 +25,14 @@ from typing import Any, Iterator, Optional, Union
 import numpy as np
 
 from ._compat import ensure_pulser
-from .results import B200Result, CoherentResults, NoisyResults, SampledCounts, StateVector
+from .results import (
+    B200Result,
+    CoherentResults,
+    DensityMatrix,
+    NoisyResults,
+    SampledCounts,
+    StateVector,
+)
 from .spec import HamiltonianSpec, spec_from_pulser
 
 if not ensure_pulser():  # pragma: no cover
@@ -355,12 +364,23 @@ class B200Emulator:
         return min(mv)
 
     # ------------------------------------------------------------------
+    def _has_collapse_ops(self) -> bool:
+        return len(self._hamiltonian_data.lindblad_data.local_collapse_ops) > 0
+
     def _check_supported(self) -> None:
-        if len(self._hamiltonian_data.lindblad_data.local_collapse_ops) > 0:
-            raise NotImplementedError(
-                "Collapse operators (dephasing / relaxation / depolarizing / "
-                "eff_noise -> mesolve / mcsolve) are not on the CUDA path yet."
-            )
+        """Collapse operators run as a master equation on the vectorised density
+        matrix (``pulser_b200/lindblad.py``): deterministic where the reference uses
+        ``mesolve`` and, for ``mcsolve`` requests, the exact ensemble average that the
+        Monte-Carlo trajectories estimate (``simulation.py:705-718``)."""
+        if self._has_collapse_ops():
+            hd = self._hamiltonian_data
+            size = hd.basis_data.dim ** (2 * hd.n_qudits)
+            if hd.basis_data.dim > 3 or size > (1 << 26):
+                raise NotImplementedError(
+                    "Collapse operators: the density-matrix path holds dim^(2N) <= 2^26 "
+                    "amplitudes and d <= 3; wave-function Monte Carlo for larger registers "
+                    "is not on the CUDA path yet."
+                )
 
     def _validate_options(self, options: dict) -> dict:
         unknown = set(options) - _QUTIP_OPTIONS - _B200_OPTIONS
@@ -382,19 +402,26 @@ class B200Emulator:
     def _run_batch(self, specs: list[HamiltonianSpec], opts: dict) -> list[list[np.ndarray]]:
         """States [n_eval][n_traj, D] of a batch of trajectories (replaces
         ``_run_solver``'s ``qutip.sesolve`` call, simulation.py:729-735)."""
-        from .engine import DevicePlan
+        from . import engine, lindblad
 
         times = self._eval_times_array
         out = []
         stats: dict = {}
-        with DevicePlan(specs, self._interp_order, self._gpu) as plan:
+        lind = self._has_collapse_ops()
+        plan_cm = (
+            lindblad.LindbladPlan(specs, self._interp_order, self._gpu)
+            if lind
+            else engine.DevicePlan(specs, self._interp_order, self._gpu)
+        )
+        with plan_cm as plan:
             plan.set_state(self._initial_state.full().reshape(-1))
-            out.append(plan.get_state())
+            fetch = plan.get_rho if lind else plan.get_state
+            out.append(fetch())
             for t0, t1 in zip(times[:-1], times[1:]):
                 st = plan.propagate(t0, t1, **opts)
                 for k, v in st.items():
                     stats[k] = max(stats.get(k, 0), v) if k == "max_rho" else stats.get(k, 0) + v
-                out.append(plan.get_state())
+                out.append(fetch())
         self.last_run_stats = stats
         return out
 
@@ -405,7 +432,11 @@ class B200Emulator:
             B200Result(
                 tuple(hd.register.qubits),
                 self._meas_basis,
-                StateVector(s, [[d] * n, [1] * n]),
+                (
+                    DensityMatrix(s, [[d] * n, [d] * n])
+                    if np.ndim(s) == 2
+                    else StateVector(s, [[d] * n, [1] * n])
+                ),
                 self._meas_basis in self.basis_name,
                 evaluation_time=t / (self._tot_duration * 1e-3),
             )

@@ -88,6 +88,44 @@ class StateVector:
         return f"StateVector(dims={self.dims}, data={self._data!r})"
 
 
+class DensityMatrix:
+    """A density operator with the slice of the Qobj API the result classes use."""
+
+    isket = False
+    isoper = True
+
+    def __init__(self, data: np.ndarray, dims: Optional[list] = None) -> None:
+        data = np.asarray(data, dtype=np.complex128)
+        n = int(np.rint(np.sqrt(data.size)))
+        self._data = data.reshape(n, n)
+        self.dims = dims if dims is not None else [[n], [n]]
+
+    def full(self) -> np.ndarray:
+        return self._data.copy()
+
+    def diag(self) -> np.ndarray:
+        return np.diagonal(self._data).copy()
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return self._data.shape
+
+    def copy(self) -> "DensityMatrix":
+        return DensityMatrix(self._data.copy(), self.dims)
+
+    def tr(self) -> complex:
+        return complex(np.trace(self._data))
+
+    def tidyup(self, atol: float = 1e-12) -> "DensityMatrix":
+        d = self._data.copy()
+        d.real[np.abs(d.real) < atol] = 0.0
+        d.imag[np.abs(d.imag) < atol] = 0.0
+        return DensityMatrix(d, self.dims)
+
+    def __repr__(self) -> str:
+        return f"DensityMatrix(dims={self.dims}, shape={self.shape})"
+
+
 def multinomial(n_samples: int, probabilities: np.ndarray) -> np.ndarray:
     """``pulser.math.multinomial`` (same RNG consumption)."""
     rnd = np.random.rand(n_samples)
@@ -117,7 +155,7 @@ class B200Result:
         return len(self.atom_order)
 
     @property
-    def _dim(self) -> int:
+    def _dim(self) -> int:  # qutip_result.py:57-65
         return int(np.rint(self.state.shape[0] ** (1 / self._size)))
 
     @property
@@ -145,7 +183,10 @@ class B200Result:
 
     def _weights(self) -> np.ndarray:  # qutip_result.py:101-158
         size = self._size
-        probs = (np.abs(self.state.full()) ** 2).flatten()
+        if not self.state.isket:
+            probs = np.abs(self.state.diag())
+        else:
+            probs = (np.abs(self.state.full()) ** 2).flatten()
         if self._dim == 2:
             if self.matching_meas_basis:
                 weights = probs[::-1] if self.meas_basis == "ground-rydberg" else probs
@@ -195,7 +236,13 @@ class B200Result:
         normalize: bool = True,
     ) -> StateVector:  # qutip_result.py:160-242
         state = self.state.copy()
-        if ignore_global_phase:
+        is_density_matrix = not state.isket
+        if is_density_matrix and self._dim != 2 and reduce_to_basis is not None:
+            raise NotImplementedError(
+                "Reduce to basis not implemented for density matrix"
+                " states."
+            )
+        if ignore_global_phase and not is_density_matrix:
             full = state.full()
             global_ph = float(np.angle(full[np.argmax(np.abs(full))])[0])
             state = state * np.exp(-1j * global_ph)
@@ -369,8 +416,11 @@ class SimulationResults:
                 mat = obs if sparse else _as_dense(obs)
                 vals = []
                 for res in self:
-                    v = res.state.full().reshape(-1)
-                    vals.append(np.vdot(v, mat @ v))
+                    if res.state.isket:
+                        v = res.state.full().reshape(-1)
+                        vals.append(np.vdot(v, mat @ v))
+                    else:
+                        vals.append(np.trace(mat @ res.state.full()))
             arr = np.array(vals)
             if np.allclose(arr.imag, 0.0, atol=1e-12):
                 arr = arr.real

@@ -1,0 +1,59 @@
+"""TEST-ONLY stand-ins for the device plans, backed by the CPU oracle, so that
+the host logic of ``B200Emulator`` (evaluation times, trajectories, sampling,
+result wrapping) can be exercised where there is no GPU.  Never imported by the
+product."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import evolve
+from oracle.ref_hamiltonian import OracleHamiltonian
+
+
+class FakeDevicePlan:
+    calls = 0
+
+    def __init__(self, specs, interp_order=3, device=0):
+        from pulser_b200.spec import HamiltonianSpec
+
+        self.specs = [specs] if isinstance(specs, HamiltonianSpec) else list(specs)
+        self.hams = [OracleHamiltonian.from_spec(s) for s in self.specs]
+        self.order = interp_order
+        self.states = None
+        FakeDevicePlan.calls += 1
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def set_state(self, psi):
+        psi = np.asarray(psi, dtype=complex).reshape(-1)
+        self.states = [psi.copy() for _ in self.hams]
+
+    def propagate(self, t0, t1, **opts):
+        self.states = [
+            evolve.sesolve(h, s, [t0, t1], order=self.order, rtol=1e-10, atol=1e-12)[-1]
+            for h, s in zip(self.hams, self.states)
+        ]
+        return {"n_steps": 1, "n_applies": 1, "n_launches": 0, "max_rho": 0.0}
+
+    def get_state(self):
+        return np.stack(self.states)
+
+
+class FakeLindbladPlan(FakeDevicePlan):
+    def set_state(self, psi):
+        psi = np.asarray(psi, dtype=complex).reshape(-1)
+        self.states = [np.outer(psi, psi.conj()) for _ in self.hams]
+
+    def propagate(self, t0, t1, **opts):
+        self.states = [
+            evolve.mesolve(h, s, [t0, t1], order=self.order, rtol=1e-9, atol=1e-11)[-1]
+            for h, s in zip(self.hams, self.states)
+        ]
+        return {"n_steps": 1, "n_applies": 1, "n_launches": 0, "max_rho": 0.0}
+
+    def get_rho(self):
+        return np.stack(self.states)

@@ -1,0 +1,147 @@
+"""CPU tests of the ``B200Emulator`` facade (needs pulser-core; the device plan
+is replaced by the oracle-backed fake of tests/fake_device.py, so only the host
+logic is under test here)."""
+import warnings
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from pulser_b200 import HAVE_PULSER
+
+pytestmark = pytest.mark.skipif(not HAVE_PULSER, reason="pulser-core not importable here")
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    from fake_device import FakeDevicePlan, FakeLindbladPlan
+    from pulser_b200 import emulator, engine, lindblad
+
+    monkeypatch.setattr(engine, "DevicePlan", FakeDevicePlan)
+    monkeypatch.setattr(lindblad, "LindbladPlan", FakeLindbladPlan)
+    return emulator
+
+
+def _seq(n_side=2, duration=400, device=None):
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    seq = Sequence(Register.square(n_side, spacing=6.0, prefix="q"), device or MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    seq.add(Pulse.ConstantPulse(duration, 2 * np.pi, np.pi, 0), "ch")
+    return seq
+
+
+def test_constructor_messages(emu):
+    """same checks and messages as simulation.py:130-230, 955-1034"""
+    from pulser import Register, Sequence
+    from pulser.devices import MockDevice
+
+    with pytest.raises(TypeError, match="sequence has to be a valid"):
+        emu.B200Emulator.from_sequence({"pulse": "fake"})
+    empty = Sequence(Register.square(2, prefix="q"), MockDevice)
+    with pytest.raises(ValueError, match="no declared channels"):
+        emu.B200Emulator.from_sequence(empty)
+    empty.declare_channel("ch", "rydberg_global")
+    with pytest.raises(ValueError, match="No instructions given"):
+        emu.B200Emulator.from_sequence(empty)
+    with pytest.raises(ValueError, match="must be greater than 0"):
+        emu.B200Emulator.from_sequence(_seq(), sampling_rate=0.0)
+    with pytest.raises(ValueError, match="too small, less than 4 data points"):
+        emu.B200Emulator.from_sequence(_seq(duration=16), sampling_rate=0.1)
+    sim = emu.B200Emulator.from_sequence(_seq())
+    with pytest.raises(ValueError, match="Incompatible shape of initial state"):
+        sim.set_initial_state(np.ones(3))
+    with pytest.raises(ValueError, match="Wrong evaluation time label"):
+        sim.set_evaluation_times("Sometimes")
+    with pytest.raises(ValueError, match="extends further than sequence duration"):
+        sim.set_evaluation_times([0.1, 9.0])
+    with pytest.raises(TypeError, match="Unknown solver options"):
+        sim.run(not_an_option=1)
+
+
+def test_evaluation_times_and_properties(emu):
+    sim = emu.B200Emulator.from_sequence(_seq(), evaluation_times="Minimal")
+    np.testing.assert_allclose(sim.evaluation_times, [0.0, 0.4])
+    assert sim.basis_name == "ground-rydberg" and sim.dim == 2 and sim.total_duration_ns == 400
+    assert len(sim.sampling_times) == 401
+    sim.set_evaluation_times(0.5)
+    assert len(sim.evaluation_times) == 200 and sim.evaluation_times[-1] == 0.4
+    sim.set_evaluation_times([0.1, 0.25])
+    np.testing.assert_allclose(sim.evaluation_times, [0.0, 0.1, 0.25, 0.4])
+    assert sim.initial_state.full()[-1, 0] == 1.0  # all-ground = last basis vector (r, g ordering)
+
+
+def test_coherent_run_wraps_states(emu, capsys):
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    sim = emu.B200Emulator.from_sequence(_seq(), evaluation_times=[0.2])
+    res = sim.run(print_progress=True, max_step=1e-3, nsteps=5000)  # QuTiP option names are accepted
+    assert "Emulating Trajectory 1/1" in capsys.readouterr().out
+    assert len(res) == 3 and res._basis_name == "ground-rydberg"
+    ref = evolve.sesolve(OracleHamiltonian.from_spec(sim._current_spec), evolve.all_ground_state(sim._current_spec),
+                         [0, 0.4], rtol=1e-10, atol=1e-12)[-1]
+    np.testing.assert_allclose(res.states[-1].full().ravel(), ref, atol=1e-7)
+    fs = res.get_final_state()
+    assert abs(fs.full()[np.argmax(np.abs(fs.full()))].imag) < 1e-12  # ignore_global_phase
+    np.random.seed(3)
+    c = res.sample_final_state(500)
+    assert sum(c.values()) == 500 and all(len(k) == 4 for k in c)
+    n0 = np.diag(1.0 - ((np.arange(16) >> 3) & 1))  # |r><r| on qubit 0
+    occ = res.expect([n0])[0]
+    assert occ.shape == (3,) and abs(occ[0]) < 1e-12 and 0 < occ[-1] < 1
+
+
+def test_noisy_run_trajectories(emu, capsys):
+    from fake_device import FakeDevicePlan
+    from pulser import NoiseModel
+
+    np.random.seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nm = NoiseModel(temperature=50.0, amp_sigma=0.05, laser_waist=175.0, samples_per_run=7)
+        sim = emu.B200Emulator.from_sequence(_seq(duration=200), noise_model=nm, n_trajectories=5,
+                                             evaluation_times="Minimal")
+        FakeDevicePlan.calls = 0
+        res = sim.run(print_progress=True)
+    out = capsys.readouterr().out
+    assert "Emulating Trajectory 1/5" in out and "Emulating Trajectory 5/5" in out
+    assert FakeDevicePlan.calls == 1  # all trajectories evolved as ONE device batch
+    assert type(res).__name__ == "NoisyResults" and res.n_measures == 35
+    assert all(sum(r.bitstring_counts.values()) == 35 for r in res)
+    assert res[0].bitstring_counts == {"0000": 35}  # t = 0: everything in the ground state
+    with pytest.raises(ValueError, match="'n_trajectories' must be defined"):
+        emu.B200Emulator.from_sequence(_seq(), noise_model=nm)
+
+
+def test_spam_bad_atoms_are_merged_with_reps(emu):
+    from pulser import NoiseModel
+
+    np.random.seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nm = NoiseModel(state_prep_error=0.3, p_false_pos=0.0, p_false_neg=0.0, samples_per_run=1)
+        sim = emu.B200Emulator.from_sequence(_seq(n_side=1, duration=100), noise_model=nm, n_trajectories=40,
+                                             evaluation_times="Minimal")
+        reps = [r for _, r in sim._specs]
+        res = sim.run()
+    assert sum(reps) == 40 and len(reps) <= 2  # hamiltonian_data.py:795-835 merges identical patterns
+    assert sum(res[-1].bitstring_counts.values()) == 40
+
+
+def test_collapse_operators_use_master_equation(emu):
+    from pulser import NoiseModel
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nm = NoiseModel(dephasing_rate=0.4, relaxation_rate=0.2)
+        sim = emu.B200Emulator.from_sequence(_seq(n_side=1, duration=200), noise_model=nm, evaluation_times="Minimal")
+        res = sim.run()
+    rho = res.states[-1]
+    assert not rho.isket and rho.shape == (2, 2)
+    assert abs(rho.tr() - 1) < 1e-7 and np.trace(rho.full() @ rho.full()).real < 1.0
+    w = res[-1]._weights()
+    np.testing.assert_allclose(w, np.abs(rho.diag())[::-1] / np.sum(np.abs(rho.diag())))
+    r_proj = np.diag([1.0, 0.0])
+    assert 0 < res.expect([r_proj])[0][-1] < 1
