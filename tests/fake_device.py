@@ -42,6 +42,9 @@ class FakeDevicePlan:
     def get_state(self):
         return np.stack(self.states)
 
+    def apply_h(self, t_us, vec, traj=0):
+        return self.hams[traj].matrix_at(t_us, self.order) @ np.asarray(vec, dtype=complex)
+
 
 class FakeLindbladPlan(FakeDevicePlan):
     def set_state(self, psi):
