@@ -480,6 +480,14 @@ class B200Emulator:
                     for t in self._eval_times_array
                 ]
             )
+        # one process per GPU: every rank evolved its stripe of the trajectories; the Counters are additive
+        # (simulation.py:848-861), so ONE all-reduce of the histograms merges them (parallel.py)
+        from . import parallel
+
+        if parallel.world_size() > 1:
+            total_count = np.array(
+                parallel.merge_trajectory_counts(list(total_count), self._hamiltonian_data.n_qudits)
+            )
         n_measures = int(self.n_trajectories) * self.noise_model.samples_per_run
         hd = self._hamiltonian_data
         results = [
@@ -504,6 +512,10 @@ class B200Emulator:
             )
         self._noise_trajectories_used = True
         pending = list(self._specs)
+        from . import parallel
+
+        if parallel.world_size() > 1:  # trajectory j -> rank j mod world (same seed on every rank)
+            pending = [pending[j] for j in parallel.stripe(len(pending), parallel.rank(), parallel.world_size())]
         if not pending:
             return
         D = pending[0][0].hilbert_dim

@@ -16,6 +16,24 @@ from typing import Sequence
 import numpy as np
 
 
+def world_size() -> int:
+    try:
+        import torch.distributed as dist
+
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    except Exception:  # pragma: no cover
+        return 1
+
+
+def rank() -> int:
+    try:
+        import torch.distributed as dist
+
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    except Exception:  # pragma: no cover
+        return 0
+
+
 def stripe(n_items: int, rank: int, world: int) -> list[int]:
     """Trajectory j -> rank j mod world."""
     return list(range(rank, n_items, world))

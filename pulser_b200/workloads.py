@@ -177,3 +177,64 @@ def config_c5(n: int = 24, t_total: int = 4000) -> HamiltonianSpec:
     )
     det = ramp(t_total, -6 * U, 2 * U)
     return ising_global_spec(coords, C6_LEVEL_60, amp, det)
+
+
+# ---------------------------------------------------------------- noisy trajectories (C4)
+KEFF = 8.7  # rad/us per (um/us), pulser-core/pulser/constants.py (conversion in noise_model._doppler_sigma)
+
+
+def doppler_sigma(temperature_uK: float) -> float:
+    """``pulser.noise_model._doppler_sigma`` (CORE/noise_model.py:127-133):
+    KEFF * sqrt(KB * T / MASS) with T in K."""
+    KB = 1.38e-23
+    MASS = 1.45e-25
+    return KEFF * float(np.sqrt(KB * temperature_uK * 1e-6 / MASS))
+
+
+def waist_amp_fraction(coords: np.ndarray, waist: float, prop_dir=(0.0, 1.0, 0.0)) -> np.ndarray:
+    """Gaussian-beam amplitude loss per atom for a global channel
+    (``HamiltonianData._finite_waist_amp_fraction``, hamiltonian_data.py:758-780):
+    exp(-(distance to the optical axis / waist)^2), axis along ``prop_dir``."""
+    pts = np.zeros((len(coords), 3))
+    pts[:, : coords.shape[1]] = coords
+    u = np.asarray(prop_dir, dtype=float)
+    u = u / np.linalg.norm(u)
+    perp = pts - np.outer(pts @ u, u)
+    return np.exp(-(np.linalg.norm(perp, axis=1) / waist) ** 2)
+
+
+def noisy_trajectory_spec(base: HamiltonianSpec, coords: np.ndarray, doppler: np.ndarray, amp_fluct: float,
+                          waist: float | None, slot_mask: np.ndarray | None = None) -> HamiltonianSpec:
+    """One noise trajectory of a global ground-rydberg sequence (doppler + amplitude noise),
+    restating ``HamiltonianData._sample_with_trajectory`` (hamiltonian_data.py:408-534): inside the pulse
+    slots det_k += doppler_k and amp_k *= amp_fluct * waist_fraction_k; all samples become Local."""
+    import copy
+
+    n = base.n_qudits
+    d0 = base.drives[0]
+    nt = d0.coef.shape[1]
+    mask = np.ones(nt) if slot_mask is None else slot_mask
+    if slot_mask is None:
+        mask[-1] = 0.0  # the zero-padded extra sample lies outside every slot
+    frac = amp_fluct * (waist_amp_fraction(coords, waist) if waist is not None else np.ones(n))
+    coef = d0.coef * np.where(mask[None, :] > 0, frac[:, None], 1.0)
+    det = d0.det + np.asarray(doppler)[:, None] * mask[None, :]
+    spec = copy.copy(base)
+    spec.drives = [DriveTable(d0.basis, coef, det, False)]
+    return spec
+
+
+def config_c4(n_traj: int = 1024, seed: int = 4, side: int = 4, temperature: float = 50.0,
+              amp_sigma: float = 0.05, laser_waist: float = 175.0) -> list[HamiltonianSpec]:
+    """C4: 16-atom 4x4 square (6 um), blockade sweep, doppler + amplitude noise trajectories."""
+    coords = square_register(side, 6.0)
+    amp, det = blockade_sweep_waveforms()
+    base = ising_global_spec(coords, C6_LEVEL_70, amp, det)
+    rng = np.random.default_rng(seed)
+    sig = doppler_sigma(temperature)
+    out = []
+    for _ in range(n_traj):
+        dop = rng.normal(0.0, sig, size=len(coords))
+        fl = max(0.0, rng.normal(1.0, amp_sigma))
+        out.append(noisy_trajectory_spec(base, coords, dop, fl, laser_waist))
+    return out
