@@ -47,7 +47,7 @@ def config_dict(n_gpus: int) -> dict:
                     "Rydberg-blockade sweep 500+2500+1000 ns, ground-rydberg basis, Schroedinger fp64",
         "hilbert_dim": 2**N_ATOMS,
         "time_steps_per_sequence": 4000,
-        "accuracy": "CF4 Magnus (exact spline moments), step-doubling controller tol 1e-9, Chebyshev 1e-12; "
+        "accuracy": "Richardson-extrapolated CF4 Magnus (exact spline moments), adaptive, 2-norm error budget 1e-8, Chebyshev-Clenshaw exponentials; "
                     "state error <= 1e-8 (tests/test_gpu_parity.py)",
         "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (one Sequence per GPU), 1 all-reduce",
         "l2": "L2 flushed between timed iterations (256 MiB write); the 16 MiB state is L2-resident within a step",

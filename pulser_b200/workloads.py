@@ -238,3 +238,28 @@ def config_c4(n_traj: int = 1024, seed: int = 4, side: int = 4, temperature: flo
         fl = max(0.0, rng.normal(1.0, amp_sigma))
         out.append(noisy_trajectory_spec(base, coords, dop, fl, laser_waist))
     return out
+
+
+# ---------------------------------------------------------------- 3-level "all" basis (C3)
+def config_c3(n: int = 14, seed: int | None = None, t_raman: int = 500, t_ryd: int = 1000) -> HamiltonianSpec:
+    """C3: n atoms, basis "all" (eigenbasis r, g, h): raman_global Blackman pi/2, then
+    rydberg_global Blackman pi, then raman_global Blackman pi/2 again (MockDevice)."""
+    coords = disc_register(n, 22.0, 6.0, (100 + n) if seed is None else seed)
+    T = 2 * t_raman + t_ryd
+    amp_dig = np.zeros(T)
+    amp_dig[:t_raman] = blackman(t_raman, np.pi / 2)
+    amp_dig[t_raman + t_ryd:] = blackman(t_raman, np.pi / 2)
+    amp_ryd = np.zeros(T)
+    amp_ryd[t_raman:t_raman + t_ryd] = blackman(t_ryd, np.pi)
+
+    def table(basis: str, amp: np.ndarray) -> DriveTable:
+        coef = 0.5 * np.append(amp, 0.0).astype(np.complex128)
+        return DriveTable(basis, np.repeat(coef[None, :], n, axis=0), np.zeros((n, T + 1)), True)
+
+    return HamiltonianSpec(
+        n_qudits=n, dim=3, eigenbasis=["r", "g", "h"], basis_name="all", interaction_type="ising",
+        sampling_times=np.arange(T + 1, dtype=np.double) / 1000, total_duration_ns=T,
+        interaction_matrix=interaction_matrix(coords, C6_LEVEL_70), bad_atoms=np.zeros(n, dtype=bool),
+        drives=[table("ground-rydberg", amp_ryd), table("digital", amp_dig)],
+        collapse_ops=np.zeros((0, 3, 3), dtype=np.complex128), qubit_ids=[f"q{i}" for i in range(n)],
+    )

@@ -234,3 +234,51 @@ def test_lindblad_vs_oracle_mesolve(engine, n, kind):
     assert np.max(np.abs(rho - ref)) < LINDBLAD_TOL
     # populations decohered: purity below one
     assert np.trace(rho @ rho).real < 0.999
+
+
+# ---------------------------------------------------------------------------
+# 3-level "all" basis (BASELINE config C3) and noisy trajectories (C4)
+def test_c3_all_basis_vs_oracle(engine):
+    from oracle import evolve
+
+    spec = W.config_c3(n=5, t_raman=200, t_ryd=400)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+
+
+def test_c3_larger_register_properties(engine):
+    """3^11 = 177147 amplitudes: unitarity and agreement with a 100x tighter controller."""
+    spec = W.config_c3(n=11, t_raman=100, t_ryd=200)
+    tf = spec.sampling_times[-1]
+    outs = []
+    with engine.DevicePlan(spec) as plan:
+        for tol in (0.0, 1e-10):
+            plan.set_state("all-ground")
+            plan.propagate(0.0, tf, tol=tol)
+            assert abs(plan.norm2()[0] - 1.0) < 1e-9
+            outs.append(plan.get_state()[0])
+    assert np.max(np.abs(outs[0] - outs[1])) < STATE_TOL
+
+
+def test_c4_noisy_trajectories_batch_vs_oracle(engine):
+    """Doppler + amplitude noise trajectories (C4 shape, 2x2 register so that the oracle can follow)."""
+    from oracle import evolve
+
+    coords = W.square_register(2, 6.0)
+    amp, det = W.blockade_sweep_waveforms(t_rise=100, t_sweep=300, t_fall=100)
+    base = W.ising_global_spec(coords, W.C6_LEVEL_70, amp, det)
+    rng = np.random.default_rng(0)
+    specs = [W.noisy_trajectory_spec(base, coords, rng.normal(0, 0.6, 4), max(0.0, rng.normal(1, 0.05)), 175.0)
+             for _ in range(5)]
+    psi0 = evolve.all_ground_state(base)
+    with engine.DevicePlan(specs) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, base.sampling_times[-1])
+        got = plan.get_state()
+    for g, s in zip(got, specs):
+        assert np.max(np.abs(g - _oracle_final(s, psi0))) < STATE_TOL

@@ -203,3 +203,59 @@ def test_fast_terms_equal_kron_terms():
     assert len(A.terms) == len(B.terms) == 6  # interaction(+dag), amp(+dag), det(+dag)
     for t in (0.3, 2.2, 3.7):
         assert abs(A.matrix_at(t) - B.matrix_at(t)).max() < 1e-13
+
+
+@pytest.mark.skipif(not HAVE_PULSER, reason="pulser-core not importable here")
+def test_workloads_c3_c4_equal_pulser():
+    """The numpy restatements of BASELINE configs C3 / C4 equal what pulser-core produces."""
+    import warnings
+
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser._hamiltonian_data import HamiltonianData
+    from pulser.devices import MockDevice
+    from pulser.sampler import sampler
+    from pulser.waveforms import BlackmanWaveform, RampWaveform
+    from pulser_b200.spec import spec_from_pulser
+
+    def first_specs(seq, nm=None, ntraj=None):
+        samples = sampler.sample(seq, extended_duration=seq.get_duration())
+        T = samples.max_duration
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hd = HamiltonianData(samples.extend_duration(T + 1), seq.register, seq.device, nm or NoiseModel(), ntraj)
+        return [(spec_from_pulser(ns, tr, hd.basis_data, hd.lindblad_data, 1.0, T), tr) for tr, ns, _ in hd.noisy_samples]
+
+    n = 5
+    coords = W.disc_register(n, 22.0, 6.0, 100 + n)
+    seq = Sequence(Register.from_coordinates(coords, center=False, prefix="q"), MockDevice)
+    seq.declare_channel("ram", "raman_global")
+    seq.declare_channel("ryd", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(500, np.pi / 2), 0, 0), "ram")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0, 0), "ryd", protocol="wait-for-all")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(500, np.pi / 2), 0, 0), "ram", protocol="wait-for-all")
+    ref = first_specs(seq)[0][0]
+    mine = W.config_c3(n)
+    assert ref.eigenbasis == mine.eigenbasis == ["r", "g", "h"] and ref.basis_name == "all"
+    for a in mine.drives:
+        b = [d for d in ref.drives if d.basis == a.basis][0]
+        np.testing.assert_array_equal(a.coef, b.coef)
+        np.testing.assert_array_equal(a.det, b.det)
+    np.testing.assert_allclose(mine.interaction_matrix, ref.interaction_matrix, rtol=1e-14)
+
+    seq = Sequence(Register.square(4, spacing=6.0, prefix="q"), MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    om = 2 * np.pi * 1.5
+    U = om / 2
+    seq.add(Pulse.ConstantDetuning(RampWaveform(500, 0, om), -6 * U, 0), "ch")
+    seq.add(Pulse.ConstantAmplitude(om, RampWaveform(2500, -6 * U, 2 * U), 0), "ch")
+    seq.add(Pulse.ConstantDetuning(RampWaveform(1000, om, 0), 2 * U, 0), "ch")
+    np.random.seed(3)
+    nm = NoiseModel(temperature=50.0, amp_sigma=0.05, laser_waist=175.0)
+    coords = W.square_register(4, 6.0)
+    base = W.ising_global_spec(coords, W.C6_LEVEL_70, *W.blockade_sweep_waveforms())
+    for ref, tr in first_specs(seq, nm, 2):
+        dop = np.array([tr.doppler_detune[q] for q in seq.register.qubit_ids])
+        mine = W.noisy_trajectory_spec(base, coords, dop, tr.amp_fluctuations["ch"], 175.0)
+        np.testing.assert_array_equal(mine.drives[0].coef, ref.drives[0].coef)
+        np.testing.assert_array_equal(mine.drives[0].det, ref.drives[0].det)
+    assert abs(W.doppler_sigma(50.0) - 0.600149981254686) < 1e-15
