@@ -93,7 +93,9 @@ typedef struct pb200_run_opts {
     int32_t extrapolate;      /* 0 / 1 (default): every smooth step is a step-doubling
                                  pair combined by Richardson extrapolation (6th
                                  order); -1: plain 4th-order steps */
-    int32_t reserved;
+    int32_t integrator;       /* exponential of each Magnus step: 1 Chebyshev-Clenshaw,
+                                 2 Lanczos (Krylov), 0 auto (Lanczos for strongly
+                                 blockaded registers whose spectrum is wide) */
 } pb200_run_opts;
 
 typedef struct pb200_run_stats {
@@ -106,6 +108,7 @@ typedef struct pb200_run_stats {
     int64_t n_checks;       /* step-doubling checks performed (adaptive mode) */
     double err_estimate;    /* accumulated local-error estimate (adaptive mode) */
     double mean_step_samples; /* average smooth-step length, in sampling intervals */
+    int64_t integrator;     /* 1 Chebyshev, 2 Lanczos: what the run used */
 } pb200_run_stats;
 
 int pb200_version(void);

@@ -49,7 +49,7 @@ class RunOpts(C.Structure):
         ("check_every", C.c_int32),
         ("tol", C.c_double),
         ("extrapolate", C.c_int32),
-        ("reserved", C.c_int32),
+        ("integrator", C.c_int32),
     ]
 
 
@@ -64,6 +64,7 @@ class RunStats(C.Structure):
         ("n_checks", C.c_int64),
         ("err_estimate", C.c_double),
         ("mean_step_samples", C.c_double),
+        ("integrator", C.c_int64),
     ]
 
 

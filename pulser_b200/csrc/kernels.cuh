@@ -112,6 +112,7 @@ struct StageArgs {
     const double* table;       // [B][stride] for this exponential (non-uniform)
     int to_bit;
     int from_is_one;
+    const double* beta_dev;  // Lanczos: c_b2 = -beta_dev[traj] read on the device (nullptr: use coef.c_b2)
     int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
 };
 
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
             c2 gv = {fma(diag, vo.x, drive.x), fma(diag, vo.y, drive.y)};
             res = cmul(a.coef.c_g, gv);
             if (a.psi) res = cadd(res, cmul(a.coef.c_psi, ld_stream(a.psi + voff + idx)));
-            if (a.b2) res = cadd(res, cmul(a.coef.c_b2, ld_stream(a.b2 + voff + idx)));
+            if (a.b2) res = cadd(res, cmul(a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2, ld_stream(a.b2 + voff + idx)));
         } else {
             res = cadd(ld_stream(a.out + voff + idx), cmul(a.coef.c_g, drive));
         }
@@ -397,6 +398,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
     // own-element global operands are staged in registers half a block at a time so that the loads
     // of one half are all in flight together (the stores to `out` may alias them for the compiler)
     constexpr int H = (R >= 4) ? R / 2 : R;
+    const c2 cb2 = a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2;
     if (g.first_pass) {
         const double* dsrc = (a.dint && !(a.dbg & 4)) ? a.dint + traj * a.dint_stride : nullptr;
 #pragma unroll
@@ -423,7 +425,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 const c2 gv = {fma(diag, v[rr].x, pr[rr]), fma(diag, v[rr].y, pi[rr])};
                 c2 res = cmul(a.coef.c_g, gv);
                 res = cadd(res, cmul(a.coef.c_psi, pv[r]));
-                res = cadd(res, cmul(a.coef.c_b2, bv[r]));
+                res = cadd(res, cmul(cb2, bv[r]));
                 if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
             }
         }
@@ -568,6 +570,7 @@ struct GenArgs {
     int to[3], from[3];
     StageCoef coef;
     const double* table;  // [B][stride]
+    const double* beta_dev;
 };
 
 __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
@@ -609,7 +612,7 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
         c2 gv = {fma(diag, vo.x, rr), fma(diag, vo.y, ri)};
         c2 res = cmul(a.coef.c_g, gv);
         if (a.psi) res = cadd(res, cmul(a.coef.c_psi, a.psi[voff + idx]));
-        if (a.b2) res = cadd(res, cmul(a.coef.c_b2, a.b2[voff + idx]));
+        if (a.b2) res = cadd(res, cmul(a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2, a.b2[voff + idx]));
         st_c2(a.out + voff + idx, res);
     }
 }
@@ -737,6 +740,93 @@ __global__ void pair_op_kernel(c2* psi, long long D, int dim, long long s_hi, lo
         }
         for (int a = 0; a < dim; ++a)
             for (int b = 0; b < dim; ++b) base[idx0 + a * s_hi + b * s_lo] = w[a * dim + b];
+    }
+}
+
+// ---- Lanczos (Krylov) propagator helpers ------------------------------------------------------------------
+// acc[traj][0] += Re<v, w>, acc[traj][1] += <w, w>   (warp __shfl reduction, one atomic pair per block)
+__global__ void dot2_kernel(const c2* v, const c2* w, long long D, double* acc) {
+    const long long traj = blockIdx.y;
+    double a0 = 0.0, a1 = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 x = v[traj * D + i], y = w[traj * D + i];
+        a0 = fma(x.x, y.x, a0); a0 = fma(x.y, y.y, a0);
+        a1 = fma(y.x, y.x, a1); a1 = fma(y.y, y.y, a1);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    __shared__ double ws[2][8];
+    if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = a0; ws[1][threadIdx.x >> 5] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += ws[0][i]; s1 += ws[1][i]; }
+        atomicAdd(acc + 2 * traj, s0);
+        atomicAdd(acc + 2 * traj + 1, s1);
+    }
+}
+
+// w <- (w - alpha v) / beta with alpha = acc[0], beta = sqrt(acc[1] - alpha^2); records alpha, beta
+// (beta = 0 and w = 0 on breakdown) and clears the accumulator of the other parity for the next iteration.
+__global__ void lanczos_update_kernel(c2* w, const c2* v, long long D, const double* acc, double* alpha_out,
+                                      double* beta_out, double* acc_clear) {
+    const long long traj = blockIdx.y;
+    const double alpha = acc[2 * traj];
+    const double ww = acc[2 * traj + 1];
+    const double b2 = ww - alpha * alpha;
+    const double beta = (b2 > 1e-28 * fmax(ww, 1e-300)) ? sqrt(b2) : 0.0;
+    const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 x = v[traj * D + i];
+        c2 y = w[traj * D + i];
+        y.x = (y.x - alpha * x.x) * inv;
+        y.y = (y.y - alpha * x.y) * inv;
+        w[traj * D + i] = y;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        alpha_out[traj] = alpha;
+        beta_out[traj] = beta;
+        acc_clear[2 * traj] = 0.0;
+        acc_clear[2 * traj + 1] = 0.0;
+    }
+}
+
+// v0 <- psi / ||psi|| with ||psi||^2 = acc[1]; records the norm
+__global__ void normalize_copy_kernel(c2* v0, const c2* psi, long long D, const double* acc, double* norm_out,
+                                      double* acc_clear) {
+    const long long traj = blockIdx.y;
+    const double nrm = sqrt(acc[2 * traj + 1]);
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 x = psi[traj * D + i];
+        v0[traj * D + i] = {x.x * inv, x.y * inv};
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        norm_out[traj] = nrm;
+        acc_clear[2 * traj] = 0.0;
+        acc_clear[2 * traj + 1] = 0.0;
+    }
+}
+
+// out = sum_j y[traj][j] V_j   (V_j = V + j * vstride; y interleaved complex [traj][m])
+__global__ void krylov_combine_kernel(c2* out, const c2* V, long long vstride, long long D, const double* y, int m) {
+    const long long traj = blockIdx.y;
+    const double* yt = y + 2 * (long long)m * traj;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        double xr = 0.0, xi = 0.0;
+        for (int j = 0; j < m; ++j) {
+            const c2 v = V[j * vstride + traj * D + i];
+            const double yr = yt[2 * j], yi = yt[2 * j + 1];
+            xr = fma(yr, v.x, xr); xr = fma(-yi, v.y, xr);
+            xi = fma(yr, v.y, xi); xi = fma(yi, v.x, xi);
+        }
+        out[traj * D + i] = {xr, xi};
     }
 }
 

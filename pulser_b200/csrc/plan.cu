@@ -97,6 +97,12 @@ struct Plan {
     int dbg = 0;
     // Lindblad: per-qudit generators of the dissipator on the (row, column) digit pair
     std::vector<std::vector<cplx>> diss_gen;
+    // Krylov (Lanczos) propagator workspace
+    c2* kry = nullptr; int kry_cap = 0;     // (kry_cap + 1) vectors of B*D
+    double* d_kry = nullptr;                // alpha[m][B], beta[m][B], acc[2][B][2], norm[B], y[B][m][2]
+    int m_last = 8;
+    bool use_krylov = false;
+    long long kry_iters = 0;
     bool has_diss = false;
     bool use_pdl = true;
     bool all_uniform() const {
@@ -183,6 +189,7 @@ static inline size_t pidx(const Plan& P, int traj, int q, int row) {
 struct StageIO {  // one Clenshaw stage of one chain
     const c2* v; const c2* psi; const c2* b2; c2* out;
     StageCoef coef; UniformDrive ud; const double* table; bool real_g;
+    const double* beta_dev = nullptr;
 };
 
 static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io) {
@@ -194,6 +201,7 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.to_bit = P.desc.drives[0].state_to;
     a.from_is_one = P.desc.drives[0].state_from;
     a.dbg = P.dbg;
+    a.beta_dev = io.beta_dev;
     return a;
 }
 
@@ -290,7 +298,7 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             a.dint_stride = P.dint_shared ? 0 : P.D;
             a.D = P.D; a.n = N; a.dim = P.dim; a.n_drives = P.n_drives;
             for (int q = 0; q < P.n_drives; ++q) { a.to[q] = P.desc.drives[q].state_to; a.from[q] = P.desc.drives[q].state_from; }
-            a.coef = io[c].coef; a.table = io[c].table;
+            a.coef = io[c].coef; a.table = io[c].table; a.beta_dev = io[c].beta_dev;
             int threads = 256;
             long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
             dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
@@ -304,14 +312,14 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
 static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
                          c2* out, StageCoef coef, bool uniform, bool real_g, const UniformDrive& ud,
                          const double* table, long long& launches) {
-    StageIO io{v, psi, b2, out, coef, ud, table, real_g};
+    StageIO io{v, psi, b2, out, coef, ud, table, real_g, nullptr};
     launch_stage_multi(P, passes, &io, 1, uniform, launches);
 }
 
 // Fill the device-table entry (host staging) of one exponential for all
 // trajectories; returns gamma0, rho (common to the batch).
 static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, double& rho, std::vector<double>& host,
-                         bool d2path) {
+                         bool d2path, bool scaled = true) {
     const int N = P.n, B = P.B, nd = P.n_drives;
     double lo = 1e300, hi = -1e300;
     for (int b = 0; b < B; ++b) {
@@ -354,6 +362,8 @@ static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, doub
     }
     gamma0 = 0.5 * (lo + hi);
     rho = std::max(0.5 * (hi - lo) * (1.0 + 1e-9), 1e-9);
+    const double rho_bound = rho;
+    if (!scaled) { gamma0 = 0.0; rho = 1.0; }  // raw operator (Krylov path); the bound is still reported
     const double inv = 1.0 / rho;
     if (d2path) {
         const int stride = d2_table_stride(N);
@@ -384,6 +394,7 @@ static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, doub
             t[stride - 2] = E.w * inv; t[stride - 1] = gamma0 * inv;
         }
     }
+    if (!scaled) rho = rho_bound;
 }
 
 struct Program {  // a batch of exponentials prepared on the host
@@ -395,6 +406,8 @@ struct Program {  // a batch of exponentials prepared on the host
     std::vector<char> real_g;
     // Lindblad splitting: dissipator exp(h D) applied before / after exponential e (0 = none)
     std::vector<double> pre_diss, post_diss;
+    std::vector<ExpParams> raw;  // unscaled generators (Krylov path)
+    std::vector<double> ktol;    // convergence tolerance of each Krylov exponential
 };
 
 static void ensure_table_capacity(Plan& P, size_t doubles) {
@@ -514,9 +527,183 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
     }
 }
 
+// eigen-decomposition of a real symmetric tridiagonal matrix (implicit QL, eigenvectors accumulated);
+// d: diagonal (in) / eigenvalues (out), e: sub-diagonal e[0..n-2], z: n x n row-major, identity on entry
+static void tridiag_ql(std::vector<double>& d, std::vector<double> e, std::vector<double>& z, int n) {
+    e.resize(n, 0.0);
+    for (int l = 0; l < n; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; ++m) {
+                const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= 1e-300 + 2.3e-16 * dd) break;
+            }
+            if (m != l) {
+                if (++iter > 200) break;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0 ? std::fabs(r) : -std::fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i], b = c * e[i];
+                    r = std::hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                    s = f / r; c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = c * r - b;
+                    for (int k = 0; k < n; ++k) {
+                        f = z[k * n + i + 1];
+                        z[k * n + i + 1] = s * z[k * n + i] + c * f;
+                        z[k * n + i] = c * z[k * n + i] - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p; e[l] = g; e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+}
+
+// y = exp(-i T_m) e_1 for the Lanczos tridiagonal T_m
+static std::vector<cplx> tridiag_exp_e1(const double* alpha, const double* beta, int m) {
+    std::vector<double> d(alpha, alpha + m), e(m > 1 ? m - 1 : 0), z((size_t)m * m, 0.0);
+    for (int i = 0; i + 1 < m; ++i) e[i] = beta[i];
+    for (int i = 0; i < m; ++i) z[(size_t)i * m + i] = 1.0;
+    tridiag_ql(d, e, z, m);
+    std::vector<cplx> y(m, cplx(0));
+    for (int k = 0; k < m; ++k) {
+        const cplx ph = std::exp(cplx(0.0, -d[k])) * z[k];  // z[0*m + k]: first component of eigenvector k
+        for (int i = 0; i < m; ++i) y[i] += ph * z[(size_t)i * m + k];
+    }
+    return y;
+}
+
+static void ensure_krylov(Plan& P, int m_cap) {
+    if (P.kry && P.kry_cap >= m_cap) return;
+    if (P.kry) { CUDA_CHECK(cudaFree(P.kry)); P.kry = nullptr; }
+    if (P.d_kry) { CUDA_CHECK(cudaFree(P.d_kry)); P.d_kry = nullptr; }
+    CUDA_CHECK(cudaMalloc(&P.kry, sizeof(c2) * (size_t)P.D * P.B * (m_cap + 1)));
+    const size_t nd = (size_t)m_cap * P.B * 2 + (size_t)4 * P.B + P.B + (size_t)P.B * m_cap * 2;
+    CUDA_CHECK(cudaMalloc(&P.d_kry, sizeof(double) * nd));
+    P.kry_cap = m_cap;
+}
+
+// psi <- exp(-iG) psi by the Lanczos process: orthonormal basis V_0..V_{m-1} of the Krylov space of (G, psi),
+// exponential of the m x m tridiagonal on the host, a-posteriori error estimate beta_{m-1} |y_{m-1}|.
+static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const std::vector<PassGeom>& passes,
+                               pb200_run_stats& st) {
+    const int M = 64;
+    ensure_krylov(P, M);
+    const int B = P.B;
+    const long long D = P.D;
+    const long long vstride = D * (long long)B;
+    double* d_alpha = P.d_kry;
+    double* d_beta = d_alpha + (size_t)M * B;
+    double* d_acc = d_beta + (size_t)M * B;   // [2][B][2]
+    double* d_norm = d_acc + (size_t)4 * B;
+    double* d_y = d_norm + B;
+    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool uniform = d2path && P.all_uniform() && B == 1;
+    double gm, rh; std::vector<double> host;
+    build_tables(P, E, gm, rh, host, d2path, /*scaled=*/false);
+    st.max_rho = std::max(st.max_rho, rh);
+    if (!uniform) {
+        ensure_table_capacity(P, host.size());
+        CUDA_CHECK(cudaMemcpyAsync(P.d_table, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, P.stream));
+    }
+    UniformDrive ud{};
+    ud.g = {E.g[0].real(), E.g[0].imag()}; ud.theta = E.th[0]; ud.w = E.w; ud.gamma = 0.0;
+    const bool real_g = E.g[0].imag() == 0.0;
+    c2* psi = P.buf[P.cur];
+    c2* outb = P.buf[(P.cur + 1) % 3];
+    const long long rblocks = std::min<long long>((D + 255) / 256, (long long)P.sm_count * 4);
+    dim3 rgrid((unsigned)std::max<long long>(rblocks, 1), (unsigned)B);
+    long long launches = 0;
+    CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 4 * B, P.stream));
+    dot2_kernel<<<rgrid, 256, 0, P.stream>>>(psi, psi, D, d_acc);
+    normalize_copy_kernel<<<rgrid, 256, 0, P.stream>>>(P.kry, psi, D, d_acc, d_norm, d_acc + 2 * B);
+    launches += 2;
+    int m_check = std::min(M, std::max(3, P.m_last));
+    std::vector<double> ha((size_t)M * B), hb((size_t)M * B), hn(B);
+    std::vector<std::vector<cplx>> ys(B);
+    int m_used = 0;
+    int j = 0;
+    while (true) {
+        for (; j < m_check; ++j) {
+            StageIO io{};
+            io.v = P.kry + (size_t)j * vstride;
+            io.psi = nullptr;
+            io.b2 = (j > 0) ? P.kry + (size_t)(j - 1) * vstride : nullptr;
+            io.out = P.kry + (size_t)(j + 1) * vstride;
+            io.coef = StageCoef{{0, 0}, {0, 0}, {1, 0}};
+            io.ud = ud; io.table = uniform ? nullptr : P.d_table; io.real_g = real_g;
+            io.beta_dev = (j > 0) ? d_beta + (size_t)(j - 1) * B : nullptr;
+            launch_stage_multi(P, passes, &io, 1, uniform, launches);
+            const int p = (j + 1) & 1;
+            dot2_kernel<<<rgrid, 256, 0, P.stream>>>(io.v, io.out, D, d_acc + (size_t)p * 2 * B);
+            lanczos_update_kernel<<<rgrid, 256, 0, P.stream>>>(io.out, io.v, D, d_acc + (size_t)p * 2 * B,
+                                                               d_alpha + (size_t)j * B, d_beta + (size_t)j * B,
+                                                               d_acc + (size_t)(p ^ 1) * 2 * B);
+            launches += 2;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(ha.data(), d_alpha, sizeof(double) * (size_t)m_check * B, cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaMemcpyAsync(hb.data(), d_beta, sizeof(double) * (size_t)m_check * B, cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaMemcpyAsync(hn.data(), d_norm, sizeof(double) * B, cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        double worst = 0.0;
+        for (int b = 0; b < B; ++b) {
+            // per-trajectory effective dimension: stop at a breakdown (beta = 0: invariant subspace reached)
+            int m = m_check;
+            std::vector<double> al(m), be(m);
+            for (int i = 0; i < m; ++i) { al[i] = ha[(size_t)i * B + b]; be[i] = hb[(size_t)i * B + b]; }
+            for (int i = 0; i < m; ++i)
+                if (be[i] == 0.0) { m = i + 1; break; }
+            ys[b] = tridiag_exp_e1(al.data(), be.data(), m);
+            const double err = (m < m_check || be[m - 1] == 0.0) ? 0.0 : hn[b] * be[m - 1] * std::abs(ys[b][m - 1]);
+            worst = std::max(worst, err);
+            ys[b].resize(m_check, cplx(0));
+            for (cplx& z : ys[b]) z *= hn[b];
+        }
+        m_used = m_check;
+        if (worst <= tol || m_check >= M) break;
+        m_check = std::min(M, m_check + 4);
+    }
+    P.m_last = std::max(3, m_used - 1);
+    std::vector<double> hy((size_t)B * m_used * 2);
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < m_used; ++i) { hy[((size_t)b * m_used + i) * 2] = ys[b][i].real(); hy[((size_t)b * m_used + i) * 2 + 1] = ys[b][i].imag(); }
+    CUDA_CHECK(cudaMemcpyAsync(d_y, hy.data(), sizeof(double) * hy.size(), cudaMemcpyHostToDevice, P.stream));
+    krylov_combine_kernel<<<rgrid, 256, 0, P.stream>>>(outb, P.kry, vstride, D, d_y, m_used);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));  // hy / host tables go out of scope
+    launches += 1;
+    P.cur = (P.cur + 1) % 3;
+    st.n_launches += launches;
+    st.n_applies += m_used;
+    st.n_exponentials += 1;
+    P.kry_iters += m_used;
+}
+
+static void run_program_krylov(Plan& P, const Program& prog, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
+    long long launches = 0;
+    for (size_t e = 0; e < prog.raw.size(); ++e) {
+        if (P.has_diss && prog.pre_diss[e] > 0.0) apply_dissipator(P, P.buf[P.cur], prog.pre_diss[e], launches);
+        krylov_exponential(P, prog.raw[e], prog.ktol.empty() ? 1e-12 : prog.ktol[e], passes, st);
+        if (P.has_diss && prog.post_diss[e] > 0.0) apply_dissipator(P, P.buf[P.cur], prog.post_diss[e], launches);
+    }
+    st.n_launches += launches;
+}
+
 // apply exp(-iG) for every exponential in the program, in order, to the current state
 static void run_program(Plan& P, const Program& prog, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
     if (prog.cheb.empty()) return;
+    if (P.use_krylov) { run_program_krylov(P, prog, passes, st); return; }
     Chain ch;
     ch.prog = &prog;
     ch.psi = P.buf[P.cur];
@@ -573,6 +760,7 @@ static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, do
     prog.real_g.push_back(g.imag() == 0.0 ? 1 : 0);
     prog.pre_diss.push_back(0.0);
     prog.post_diss.push_back(0.0);
+    if (P.use_krylov) { prog.raw.push_back(E); prog.ktol.push_back(tol); }
 }
 
 // exp(h*A) of a small dense matrix (scaling and squaring, Taylor order 20)
@@ -759,7 +947,6 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     std::vector<char> fine = fine_intervals(P, W, rtol, 0.05, jump, dist);
     for (size_t i = 0; i < fine.size(); ++i) if (jump[i]) fine[i] = 1;
     const double magnus_tol = 1e-11;
-    const double rho_cap = 3.0;
     const int nt = (int)P.times.size();
     // error budget per unit of time: gtol over the whole sampling-time range
     const double rate_allowed = adaptive ? gtol / std::max(thi - tlo, 1e-30) : 0.0;
@@ -806,7 +993,26 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     };
     // Richardson-extrapolated step: one CF4 step of h and two of h/2 from the same state,
     // psi <- R2 + (R2 - R1) / (2^p - 1); the symmetric scheme gains two orders (6th for CF4)
-    const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss;
+    // exponential: Chebyshev-Clenshaw (cost ~ full spectral width) or Lanczos (cost ~ populated spectral width);
+    // auto picks Lanczos when one sampling interval already spans a Chebyshev half-width near 1, i.e. for
+    // strongly blockaded registers whose high-energy states are not populated
+    {
+        const int req = o ? o->integrator : 0;
+        bool kry = (req == 2);
+        if (req == 0) {
+            std::vector<cplx> q0, q1; std::vector<double> r0, r1;
+            const double tb = std::min(P.times[std::min(1, nt - 1)], t_stop);
+            moments_for_step(P, P.times[0], P.times[std::min(1, nt - 1)], q0, q1, r0, r1);
+            ExpParams E; E.g = q0; E.th = r0; E.w = P.times[std::min(1, nt - 1)] - P.times[0];
+            double gm, rh1; std::vector<double> scratch_tab;
+            build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
+            kry = rh1 > env_int("PB200_KRYLOV_RHO_MILLI", 900) * 1e-3;
+            (void)tb;
+        }
+        P.use_krylov = kry;
+    }
+    const double rho_cap = P.use_krylov ? 12.0 : 3.0;
+    const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss && !P.use_krylov;
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
     // a symmetric 2nd-order scheme whatever the order of its unitary part
     const int pw_base = P.has_diss ? 2 : ((order == 4) ? 4 : 2);
@@ -967,6 +1173,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     st.gpu_ms = ms;
     st.mean_step_samples = smooth_steps ? smooth_len / smooth_steps : 0.0;
+    st.integrator = P.use_krylov ? 2 : 1;
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) *stats = st;
 }
@@ -1170,6 +1377,8 @@ int pb200_plan_destroy(pb200_plan* h) {
         if (P.buf[i]) cudaFree(P.buf[i]);
     for (int i = 0; i < 6; ++i)
         if (P.aux[i]) cudaFree(P.aux[i]);
+    if (P.kry) cudaFree(P.kry);
+    if (P.d_kry) cudaFree(P.d_kry);
     if (P.dint) cudaFree(P.dint);
     if (P.d_table) cudaFree(P.d_table);
     if (P.d_scratch) cudaFree(P.d_scratch);

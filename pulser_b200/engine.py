@@ -220,13 +220,14 @@ class DevicePlan:
         tol: float = 0.0,
         check_every: int = 0,
         extrapolate: int = 0,
+        integrator: int = 0,
     ) -> dict:
         """Advance all trajectories from ``t_start`` to ``t_stop`` (us).
 
         ``tol > 0`` (default 1e-9): adaptive Magnus steps with step-doubling
         error control; ``tol < 0``: fixed steps of ``max_step`` samples.
         """
-        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, check_every, tol, extrapolate, 0)
+        opts = RunOpts(max_step, refine_window, cheb_tol, rough_tol, magnus_order, check_every, tol, extrapolate, integrator)
         st = RunStats()
         check(
             lib.pb200_propagate(

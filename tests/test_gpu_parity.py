@@ -282,3 +282,46 @@ def test_c4_noisy_trajectories_batch_vs_oracle(engine):
         got = plan.get_state()
     for g, s in zip(got, specs):
         assert np.max(np.abs(g - _oracle_final(s, psi0))) < STATE_TOL
+
+
+# ---------------------------------------------------------------------------
+# Lanczos (Krylov) exponentials
+@pytest.mark.parametrize("builder", [
+    lambda: W.config_c1(),
+    lambda: W.config_c2(n=9, seed=20, t_rise=100, t_sweep=400, t_fall=100),
+    lambda: random_local_spec(6, T=200, seed=4),
+    lambda: W.config_c3(n=4, t_raman=100, t_ryd=200),
+])
+def test_krylov_integrator_vs_oracle(engine, builder):
+    from oracle import evolve
+
+    spec = builder()
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        st = plan.propagate(0.0, spec.sampling_times[-1], integrator=2)
+        got = plan.get_state()[0]
+    assert st["integrator"] == 2 and st["n_applies"] > 0
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-9
+
+
+def test_auto_integrator_picks_lanczos_for_blockaded_register(engine):
+    """Dense 3x3 array at 6 um (U = 116 rad/us): Chebyshev would need sub-sample steps."""
+    from oracle import evolve
+
+    amp, det = W.blockade_sweep_waveforms(t_rise=100, t_sweep=300, t_fall=100)
+    spec = W.ising_global_spec(W.square_register(3, 6.0), W.C6_LEVEL_70, amp, det)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    out = {}
+    with engine.DevicePlan(spec) as plan:
+        for integ in (0, 1):
+            plan.set_state("all-ground")
+            st = plan.propagate(0.0, spec.sampling_times[-1], integrator=integ)
+            out[integ] = (st, plan.get_state()[0])
+    assert out[0][0]["integrator"] == 2 and out[1][0]["integrator"] == 1
+    for st, got in out.values():
+        assert np.max(np.abs(got - ref)) < STATE_TOL
+    assert out[0][0]["n_applies"] < out[1][0]["n_applies"]
