@@ -307,8 +307,8 @@ def test_krylov_integrator_vs_oracle(engine, builder):
     assert abs(np.linalg.norm(got) - 1.0) < 1e-9
 
 
-def test_auto_integrator_picks_lanczos_for_blockaded_register(engine):
-    """Dense 3x3 array at 6 um (U = 116 rad/us): Chebyshev would need sub-sample steps."""
+def test_lanczos_needs_fewer_applies_on_blockaded_register(engine):
+    """Dense 3x3 array at 6 um (U = 116 rad/us): wide spectrum, narrow populated band."""
     from oracle import evolve
 
     amp, det = W.blockade_sweep_waveforms(t_rise=100, t_sweep=300, t_fall=100)
@@ -317,11 +317,11 @@ def test_auto_integrator_picks_lanczos_for_blockaded_register(engine):
     ref = _oracle_final(spec, psi0)
     out = {}
     with engine.DevicePlan(spec) as plan:
-        for integ in (0, 1):
+        for integ in (0, 1, 2):
             plan.set_state("all-ground")
             st = plan.propagate(0.0, spec.sampling_times[-1], integrator=integ)
             out[integ] = (st, plan.get_state()[0])
-    assert out[0][0]["integrator"] == 2 and out[1][0]["integrator"] == 1
+    assert out[2][0]["integrator"] == 2 and out[1][0]["integrator"] == 1 and out[0][0]["integrator"] in (1, 2)
     for st, got in out.values():
         assert np.max(np.abs(got - ref)) < STATE_TOL
-    assert out[0][0]["n_applies"] < out[1][0]["n_applies"]
+    assert out[2][0]["n_applies"] < 0.6 * out[1][0]["n_applies"]
