@@ -113,6 +113,7 @@ struct StageArgs {
     int to_bit;
     int from_is_one;
     const double* beta_dev;  // Lanczos: c_b2 = -beta_dev[traj] read on the device (nullptr: use coef.c_b2)
+    double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<v, out>, acc[traj][1] += <out, out> (fused reductions)
     int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
 };
 
@@ -399,6 +400,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
     // of one half are all in flight together (the stores to `out` may alias them for the compiler)
     constexpr int H = (R >= 4) ? R / 2 : R;
     const c2 cb2 = a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2;
+    double dot0 = 0.0, dot1 = 0.0;
     if (g.first_pass) {
         const double* dsrc = (a.dint && !(a.dbg & 4)) ? a.dint + traj * a.dint_stride : nullptr;
 #pragma unroll
@@ -426,6 +428,8 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 c2 res = cmul(a.coef.c_g, gv);
                 res = cadd(res, cmul(a.coef.c_psi, pv[r]));
                 res = cadd(res, cmul(cb2, bv[r]));
+                dot0 = fma(v[rr].x, res.x, dot0); dot0 = fma(v[rr].y, res.y, dot0);
+                dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
                 if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
             }
         }
@@ -438,8 +442,27 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 const int rr = h0 + r;
-                st_c2(a.out + voff + idx[rr], cadd(ov[r], cmul(a.coef.c_g, c2{pr[rr], pi[rr]})));
+                const c2 res = cadd(ov[r], cmul(a.coef.c_g, c2{pr[rr], pi[rr]}));
+                dot0 = fma(v[rr].x, res.x, dot0); dot0 = fma(v[rr].y, res.y, dot0);
+                dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
+                st_c2(a.out + voff + idx[rr], res);
             }
+        }
+    }
+    if (a.dot_acc) {  // block reduction of the fused Lanczos inner products, one atomic pair per CTA
+        for (int o = 16; o > 0; o >>= 1) {
+            dot0 += __shfl_xor_sync(0xffffffffu, dot0, o);
+            dot1 += __shfl_xor_sync(0xffffffffu, dot1, o);
+        }
+        __shared__ double dred[2][NT / 32 > 0 ? NT / 32 : 1];
+        if ((tid & 31) == 0) { dred[0][tid >> 5] = dot0; dred[1][tid >> 5] = dot1; }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NT / 32; ++i) { s0 += dred[0][i]; s1 += dred[1][i]; }
+            atomicAdd(a.dot_acc + 2 * traj, s0);
+            atomicAdd(a.dot_acc + 2 * traj + 1, s1);
         }
     }
 }

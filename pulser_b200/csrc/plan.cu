@@ -190,9 +190,10 @@ struct StageIO {  // one Clenshaw stage of one chain
     const c2* v; const c2* psi; const c2* b2; c2* out;
     StageCoef coef; UniformDrive ud; const double* table; bool real_g;
     const double* beta_dev = nullptr;
+    double* dot_acc = nullptr;  // fused <v,out>, <out,out> (only honoured by the register-blocked d=2 kernels)
 };
 
-static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io) {
+static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io, bool geo_is_last = true) {
     StageArgs a{};
     a.v = io.v; a.psi = io.psi; a.b2 = io.b2; a.out = io.out;
     a.dint = P.has_interaction ? P.dint : nullptr;
@@ -202,6 +203,7 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.from_is_one = P.desc.drives[0].state_from;
     a.dbg = P.dbg;
     a.beta_dev = io.beta_dev;
+    a.dot_acc = (geo_is_last ? io.dot_acc : nullptr);
     return a;
 }
 
@@ -225,7 +227,9 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
     if (P.dim == 2 && P.n_drives == 1) {
         bool real_g = true;
         for (int c = 0; c < n; ++c) real_g = real_g && io[c].real_g;
-        for (const PassGeom& geo : passes) {
+        for (size_t gi = 0; gi < passes.size(); ++gi) {
+            const PassGeom& geo = passes[gi];
+            const bool last_pass = (gi + 1 == passes.size());
             const int tbits = geo.lo_bits + geo.hi_bits;
             const long long tiles = P.D >> tbits;
             const int tsize = 1 << tbits;
@@ -256,7 +260,7 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
                     ++launches;
                 } else {
                     StageArgs2 m{};
-                    for (int c = 0; c < n; ++c) m.a[c] = make_stage_args(P, geo, io[c]);
+                    for (int c = 0; c < n; ++c) m.a[c] = make_stage_args(P, geo, io[c], last_pass);
                     m.n_traj = P.B;
                     dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
                     const size_t smem = (size_t)tsize * 16 + tab_bytes;
@@ -619,6 +623,8 @@ static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const st
     UniformDrive ud{};
     ud.g = {E.g[0].real(), E.g[0].imag()}; ud.theta = E.th[0]; ud.w = E.w; ud.gamma = 0.0;
     const bool real_g = E.g[0].imag() == 0.0;
+    bool fused_dot = d2path && !P.use_pipe;
+    for (const PassGeom& g : passes) fused_dot = fused_dot && rb_eligible(P, g);
     c2* psi = P.buf[P.cur];
     c2* outb = P.buf[(P.cur + 1) % 3];
     const long long rblocks = std::min<long long>((D + 255) / 256, (long long)P.sm_count * 4);
@@ -643,13 +649,14 @@ static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const st
             io.coef = StageCoef{{0, 0}, {0, 0}, {1, 0}};
             io.ud = ud; io.table = uniform ? nullptr : P.d_table; io.real_g = real_g;
             io.beta_dev = (j > 0) ? d_beta + (size_t)(j - 1) * B : nullptr;
-            launch_stage_multi(P, passes, &io, 1, uniform, launches);
             const int p = (j + 1) & 1;
-            dot2_kernel<<<rgrid, 256, 0, P.stream>>>(io.v, io.out, D, d_acc + (size_t)p * 2 * B);
+            io.dot_acc = fused_dot ? d_acc + (size_t)p * 2 * B : nullptr;
+            launch_stage_multi(P, passes, &io, 1, uniform, launches);
+            if (!fused_dot) { dot2_kernel<<<rgrid, 256, 0, P.stream>>>(io.v, io.out, D, d_acc + (size_t)p * 2 * B); ++launches; }
             lanczos_update_kernel<<<rgrid, 256, 0, P.stream>>>(io.out, io.v, D, d_acc + (size_t)p * 2 * B,
                                                                d_alpha + (size_t)j * B, d_beta + (size_t)j * B,
                                                                d_acc + (size_t)(p ^ 1) * 2 * B);
-            launches += 2;
+            launches += 1;
         }
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaMemcpyAsync(ha.data(), d_alpha, sizeof(double) * (size_t)m_check * B, cudaMemcpyDeviceToHost, P.stream));

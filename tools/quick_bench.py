@@ -18,11 +18,11 @@ def main():
             print(json.dumps({"n": n, "plan_s": round(t1 - t0, 3), "apply_us": round(per * 1e3, 2),
                               "launches_per_apply": launches // 50,
                               "alg_GBs": round(40 * D / (per * 1e-3) / 1e9, 1)}))
-            if n <= 22:
-                for K, tol in ((0, 0.0),):
+            if True:
+                for K, tol, integ in ((0, 0.0, 1), (0, 0.0, 2)):
                     plan.set_state("all-ground")
                     t2 = time.time()
-                    st = plan.propagate(0.0, spec.sampling_times[-1], max_step=K, tol=tol)
+                    st = plan.propagate(0.0, spec.sampling_times[-1], max_step=K, tol=tol, integrator=integ)
                     wall = time.time() - t2
                     T = spec.total_duration_ns
                     st.update({"K": K, "tol": tol, "wall_s": round(wall, 3), "steps_per_s": round(T / wall, 1),
