@@ -1013,7 +1013,9 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             ExpParams E; E.g = q0; E.th = r0; E.w = P.times[std::min(1, nt - 1)] - P.times[0];
             double gm, rh1; std::vector<double> scratch_tab;
             build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
-            kry = rh1 > env_int("PB200_KRYLOV_RHO_MILLI", 900) * 1e-3;
+            // ... or when the state no longer fits L2 (fewer, fatter iterations win once HBM-bound)
+            kry = rh1 > env_int("PB200_KRYLOV_RHO_MILLI", 900) * 1e-3 ||
+                  (double)P.D * P.B * 16.0 > (double)env_int("PB200_KRYLOV_MIB", 96) * 1048576.0;
             (void)tb;
         }
         P.use_krylov = kry;
