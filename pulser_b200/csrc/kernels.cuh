@@ -114,6 +114,7 @@ struct StageArgs {
     int from_is_one;
     const double* beta_dev;  // Lanczos: c_b2 = -beta_dev[traj] read on the device (nullptr: use coef.c_b2)
     double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<v, out>, acc[traj][1] += <out, out> (fused reductions)
+    int swz;  // > 0: number of tile-id bits, tile order bit-reversed (L2 locality of high-bit partners)
     int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
 };
 
@@ -500,7 +501,11 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
     const PassGeom g = a.geo;
     const int tid = threadIdx.x;
     const long long traj = blockIdx.y - chain * m.n_traj;
-    const long long base = tile_base_of(g, blockIdx.x);
+    // tile order: with `swz` set, consecutive CTAs differ in the HIGHEST tile-id bits, so that the CTAs
+    // resident together form a sub-cube closed under the high-bit flips (their partners hit in L2)
+    long long tile_id = blockIdx.x;
+    if (a.swz > 0) tile_id = (long long)(__brev((unsigned)blockIdx.x) >> (32 - a.swz));
+    const long long base = tile_base_of(g, tile_id);
     const c2* vsrc = a.v + traj * a.D;
 
     if (tid == 0) mbar_init(&mbar, 1);

@@ -95,6 +95,8 @@ struct Plan {
     bool use_pipe = false;
     bool use_dual = true;
     int dbg = 0;
+    bool swizzle = false;
+    int swizzle_min_bits = 12;
     // Lindblad: per-qudit generators of the dissipator on the (row, column) digit pair
     std::vector<std::vector<cplx>> diss_gen;
     // Krylov (Lanczos) propagator workspace
@@ -202,6 +204,11 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.to_bit = P.desc.drives[0].state_to;
     a.from_is_one = P.desc.drives[0].state_from;
     a.dbg = P.dbg;
+    {
+        const int tb = geo.lo_bits + geo.hi_bits;
+        const int idbits = P.n - tb;
+        a.swz = (P.swizzle && idbits >= P.swizzle_min_bits && idbits <= 31) ? idbits : 0;
+    }
     a.beta_dev = io.beta_dev;
     a.dot_acc = (geo_is_last ? io.dot_acc : nullptr);
     return a;
@@ -1020,7 +1027,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         }
         P.use_krylov = kry;
     }
-    const double rho_cap = P.use_krylov ? 12.0 : 3.0;
+    const double rho_cap = P.use_krylov ? env_int("PB200_RHO_CAP_KRYLOV_MILLI", 12000) * 1e-3
+                                        : env_int("PB200_RHO_CAP_MILLI", 3600) * 1e-3;
     const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss && !P.use_krylov;
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
     // a symmetric 2nd-order scheme whatever the order of its unitary part
@@ -1330,6 +1338,8 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_pipe = env_int("PB200_PIPE", 0) != 0;
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.dbg = env_int("PB200_DBG", 0);
+    P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
+    P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
