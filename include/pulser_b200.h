@@ -170,6 +170,17 @@ int pb200_state_probabilities(pb200_plan* plan, int32_t traj0, int32_t count,
 /* squared norms, norms2[count] */
 int pb200_state_norm2(pb200_plan* plan, int32_t traj0, int32_t count,
                       double* norms2);
+/* Populations: occ[count][N], occ[t][k] = sum_s |psi_s|^2 [digit_k(s) == digit]
+ * (the Occupation observable; default_observables.py:377-436). */
+int pb200_state_occupation(pb200_plan* plan, int32_t traj0, int32_t count,
+                           int32_t digit, double* occ);
+/* Bitstring sampling on the device (QutipResult._weights + multinomial,
+ * qutip_result.py:101-158, pulser/math/multinomial.py:17-36): weights over the
+ * 2^N bitstrings (bit k = [digit_k == one_digit]), normalised, cumulated, and
+ * searched with the caller's uniforms u[n_shots] (np.random.rand): out[i] =
+ * bitstring index of shot i.  Only 8*n_shots bytes travel each way. */
+int pb200_state_sample(pb200_plan* plan, int32_t traj, int32_t one_digit,
+                       const double* uniforms, int32_t n_shots, int64_t* out);
 /* Device pointer of the current state buffer (complex128 [n_traj][D]). */
 int pb200_state_device_ptr(pb200_plan* plan, void** dptr);
 

@@ -697,6 +697,59 @@ __global__ void dint_bounds_kernel(const double* dint, int n, int dim, int rstat
     }
 }
 
+// ---- measurement: bitstring weights, occupations, sampling ---------------------------------------------------
+// weights[b(s)] += |psi_s|^2 with bit k of b = [digit_k(s) == one_digit], qudit 0 = most significant bit
+// (QutipResult._weights, qutip_result.py:101-158: reversal for ground-rydberg and the 3/4-level
+// marginalisation are both this rule)
+__global__ void bitstring_weights_kernel(const c2* psi, double* weights, long long D, int n, int dim, int one_digit) {
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < D;
+         s += (long long)gridDim.x * blockDim.x) {
+        const c2 v = psi[s];
+        const double p = v.x * v.x + v.y * v.y;
+        long long rem = s, b = 0;
+        for (int k = n - 1; k >= 0; --k) {  // qudit k <-> bit n-1-k
+            if ((int)(rem % dim) == one_digit) b |= 1LL << (n - 1 - k);
+            rem /= dim;
+        }
+        if (dim == 2) weights[b] = p;  // a permutation: no atomics needed
+        else atomicAdd(weights + b, p);
+    }
+}
+
+// occ[k] += sum_s |psi_s|^2 [digit_k(s) == digit]   (Occupation observable / <n_k>)
+__global__ void occupation_kernel(const c2* psi, double* occ, long long D, int n, int dim, int digit) {
+    extern __shared__ double socc[];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) socc[i] = 0.0;
+    __syncthreads();
+    const long long traj = blockIdx.y;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < D;
+         s += (long long)gridDim.x * blockDim.x) {
+        const c2 v = psi[traj * D + s];
+        const double p = v.x * v.x + v.y * v.y;
+        if (p == 0.0) continue;
+        long long rem = s;
+        for (int k = n - 1; k >= 0; --k) {
+            if ((int)(rem % dim) == digit) atomicAdd(&socc[k], p);
+            rem /= dim;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(occ + traj * n + i, socc[i]);
+}
+
+// indices[i] = first j with cum[j] >= u[i] * total  (np.searchsorted(cumsum(w / sum w), rnd), side="left")
+__global__ void search_sorted_kernel(const double* cum, long long M, const double* u, long long* idx, int n_shots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_shots) return;
+    const double target = u[i] * cum[M - 1];
+    long long lo = 0, hi = M;  // first index with cum >= target
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (cum[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    idx[i] = lo < M ? lo : M - 1;
+}
+
 // ---- small utilities --------------------------------------------------------
 __global__ void set_basis_kernel(c2* psi, long long D, long long index) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;

@@ -24,6 +24,7 @@
 #include "../../include/pulser_b200.h"
 #include "kernels.cuh"
 #include "spline.hpp"
+#include <cub/device/device_scan.cuh>
 
 namespace pb200 {
 
@@ -1593,6 +1594,68 @@ int pb200_state_norm2(pb200_plan* h, int32_t traj0, int32_t count, double* norms
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(norms2, P.d_scratch, sizeof(double) * count, cudaMemcpyDeviceToHost, P.stream));
     CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    PB200_CATCH
+}
+
+int pb200_state_occupation(pb200_plan* h, int32_t traj0, int32_t count, int32_t digit, double* occ) {
+    PB200_TRY
+    if (!h || !occ) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    if (digit < 0 || digit >= P.dim) fail(PB200_ERR_INVALID, "digit out of range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    double* d_occ = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_occ, sizeof(double) * (size_t)count * P.n));
+    CUDA_CHECK(cudaMemsetAsync(d_occ, 0, sizeof(double) * (size_t)count * P.n, P.stream));
+    const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
+    dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
+    occupation_kernel<<<grid, 256, sizeof(double) * P.n, P.stream>>>(P.buf[P.cur] + (size_t)traj0 * P.D, d_occ, P.D, P.n,
+                                                                       P.dim, digit);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(occ, d_occ, sizeof(double) * (size_t)count * P.n, cudaMemcpyDeviceToHost, P.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
+    cudaFree(d_occ);
+    if (e != cudaSuccess) fail(PB200_ERR_CUDA, "occupation: %s", cudaGetErrorString(e));
+    PB200_CATCH
+}
+
+int pb200_state_sample(pb200_plan* h, int32_t traj, int32_t one_digit, const double* uniforms, int32_t n_shots,
+                       int64_t* out) {
+    PB200_TRY
+    if (!h || !uniforms || !out || n_shots < 1) fail(PB200_ERR_INVALID, "bad argument");
+    Plan& P = h->p;
+    if (traj < 0 || traj >= P.B) fail(PB200_ERR_INVALID, "trajectory out of range");
+    if (one_digit < 0 || one_digit >= P.dim) fail(PB200_ERR_INVALID, "one_digit out of range");
+    if (P.n > 40) fail(PB200_ERR_UNSUPPORTED, "too many qudits for bitstring sampling");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    const long long M = 1LL << P.n;
+    double *d_w = nullptr, *d_u = nullptr; long long* d_idx = nullptr; void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() { cudaFree(d_w); cudaFree(d_u); cudaFree(d_idx); cudaFree(d_tmp); };
+    try {
+        CUDA_CHECK(cudaMalloc(&d_w, sizeof(double) * (size_t)M));
+        CUDA_CHECK(cudaMalloc(&d_u, sizeof(double) * (size_t)n_shots));
+        CUDA_CHECK(cudaMalloc(&d_idx, sizeof(long long) * (size_t)n_shots));
+        CUDA_CHECK(cudaMemsetAsync(d_w, 0, sizeof(double) * (size_t)M, P.stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_u, uniforms, sizeof(double) * (size_t)n_shots, cudaMemcpyHostToDevice, P.stream));
+        const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
+        bitstring_weights_kernel<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, P.stream>>>(
+            P.buf[P.cur] + (size_t)traj * P.D, d_w, P.D, P.n, P.dim, one_digit);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_w, d_w, (int)M, P.stream));
+        CUDA_CHECK(cudaMalloc(&d_tmp, tmp_bytes));
+        CUDA_CHECK(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_w, d_w, (int)M, P.stream));
+        search_sorted_kernel<<<(n_shots + 255) / 256, 256, 0, P.stream>>>(d_w, M, d_u, d_idx, n_shots);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(out, d_idx, sizeof(long long) * (size_t)n_shots, cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    (void)e;
+    cleanup();
     PB200_CATCH
 }
 

@@ -202,6 +202,29 @@ class DevicePlan:
         check(lib.pb200_state_norm2(self._handle, 0, self.n_traj, _p(out)))
         return out
 
+    def occupation(self, digit: int, traj0: int = 0, count: int | None = None) -> np.ndarray:
+        """Per-qudit population of eigenstate ``digit``, ``[count, N]`` (device reduction)."""
+        count = self.n_traj - traj0 if count is None else count
+        out = np.empty((count, self.n), dtype=np.float64)
+        check(lib.pb200_state_occupation(self._handle, traj0, count, int(digit), _p(out)))
+        return out
+
+    def sample(self, n_samples: int, one_state: str, traj: int = 0) -> "Counter[str]":
+        """Bitstring samples of trajectory ``traj`` drawn on the device with the
+        reference's recipe and the global ``np.random`` stream
+        (``qutip_result.py:101-158`` + ``pulser/math/multinomial.py:17-36``)."""
+        from collections import Counter
+
+        u = np.ascontiguousarray(np.random.rand(n_samples), dtype=np.float64)
+        idx = np.empty(n_samples, dtype=np.int64)
+        check(
+            lib.pb200_state_sample(
+                self._handle, traj, self.spec.eigenbasis.index(one_state), _p(u), n_samples,
+                idx.ctypes.data_as(C.POINTER(C.c_int64)),
+            )
+        )
+        return Counter(np.binary_repr(int(i), self.n) for i in idx)
+
     def device_ptr(self) -> int:
         ptr = C.c_void_p()
         check(lib.pb200_state_device_ptr(self._handle, C.byref(ptr)))

@@ -325,3 +325,31 @@ def test_lanczos_needs_fewer_applies_on_blockaded_register(engine):
     for st, got in out.values():
         assert np.max(np.abs(got - ref)) < STATE_TOL
     assert out[2][0]["n_applies"] < 0.6 * out[1][0]["n_applies"]
+
+
+# ---------------------------------------------------------------------------
+# measurement on the device
+def test_device_sampling_equals_reference_recipe(engine):
+    """Same state + same np.random seed -> the Counter the reference's host recipe gives
+    (QutipResult._weights + multinomial), for d = 2 (reversed order) and the 3-level marginalisation."""
+    from pulser_b200.results import B200Result, StateVector
+
+    for spec, meas, one, matching in (
+        (W.config_c2(n=9, seed=2, t_rise=50, t_sweep=100, t_fall=50), "ground-rydberg", "r", True),
+        (W.config_c3(n=5, t_raman=100, t_ryd=150), "digital", "h", False),
+        (W.config_c3(n=5, t_raman=100, t_ryd=150), "ground-rydberg", "r", False),
+    ):
+        with engine.DevicePlan(spec) as plan:
+            plan.set_state("all-ground")
+            plan.propagate(0.0, spec.sampling_times[-1])
+            psi = plan.get_state()[0]
+            np.random.seed(77)
+            dev = plan.sample(2000, one)
+            occ = plan.occupation(spec.eigenbasis.index(one))[0]
+        np.random.seed(77)
+        host = B200Result(tuple(range(spec.n_qudits)), meas, StateVector(psi), matching).get_samples(2000)
+        assert dev == host
+        d, n = spec.dim, spec.n_qudits
+        probs = (np.abs(psi) ** 2).reshape([d] * n)
+        ref_occ = [np.take(probs, spec.eigenbasis.index(one), axis=k).sum() for k in range(n)]
+        np.testing.assert_allclose(occ, ref_occ, atol=1e-12)
