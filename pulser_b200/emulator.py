@@ -471,14 +471,19 @@ class B200Emulator:
             return self._wrap([s[0] for s in states])
 
         total_count = np.array([Counter() for _ in self._eval_times_array])
-        for cleanres, reps in self._noisy_runs(
-            print_progress=print_progress, batch=int(options.get("b200_batch", 0)), opts=opts
-        ):
-            total_count += np.array(
-                [
-                    cleanres.sample_state(t, n_samples=self.noise_model.samples_per_run * reps)
-                    for t in self._eval_times_array
-                ]
+        if self._has_collapse_ops():
+            for cleanres, reps in self._noisy_runs(
+                print_progress=print_progress, batch=int(options.get("b200_batch", 0)), opts=opts
+            ):
+                total_count += np.array(
+                    [
+                        cleanres.sample_state(t, n_samples=self.noise_model.samples_per_run * reps)
+                        for t in self._eval_times_array
+                    ]
+                )
+        else:
+            total_count += self._noisy_counts(
+                print_progress=print_progress, batch=int(options.get("b200_batch", 0)), opts=opts
             )
         # one process per GPU: every rank evolved its stripe of the trajectories; the Counters are additive
         # (simulation.py:848-861), so ONE all-reduce of the histograms merges them (parallel.py)
@@ -501,9 +506,8 @@ class B200Emulator:
             results, hd.n_qudits, self.basis_name, self._eval_times_array, n_measures
         )
 
-    def _noisy_runs(self, print_progress: bool, batch: int, opts: dict):
-        """simulation.py:885-915, trajectories evolved in device batches."""
-        n_trajectories = self.n_trajectories
+    def _pending_trajectories(self) -> list:
+        """(spec, reps) of this rank's stripe; redraws the trajectories on repeated runs (:892-902)."""
         if self._noise_trajectories_used:
             nm = self._hamiltonian_data.noise_model
             self._hamiltonian_data = HamiltonianData(
@@ -516,6 +520,71 @@ class B200Emulator:
 
         if parallel.world_size() > 1:  # trajectory j -> rank j mod world (same seed on every rank)
             pending = [pending[j] for j in parallel.stripe(len(pending), parallel.rank(), parallel.world_size())]
+        return pending
+
+    def _noisy_counts(self, print_progress: bool, batch: int, opts: dict) -> np.ndarray:
+        """Bitstring Counters per evaluation time of all noise trajectories, sampled ON THE DEVICE
+        (``pb200_state_sample``): only the shots travel to the host, never the states.
+        Replaces the per-trajectory ``sample_state`` loop of simulation.py:850-861."""
+        from . import engine
+        from .results import CoherentResults
+
+        times = self._eval_times_array
+        counts = np.array([Counter() for _ in times])
+        pending = self._pending_trajectories()
+        if not pending:
+            return counts
+        hd = self._hamiltonian_data
+        n = hd.n_qudits
+        D = pending[0][0].hilbert_dim
+        if batch <= 0:
+            batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
+        one_state = {"ground-rydberg": "r", "digital": "h", "XY": "d"}[self._meas_basis]
+        matching = self._meas_basis in self.basis_name
+        spr = self.noise_model.samples_per_run
+        flipper = None
+        if "SPAM" in self.noise_model.noise_types and (
+            self.noise_model.p_false_pos > 0 or self.noise_model.p_false_neg > 0
+        ):
+            flipper = CoherentResults(
+                [], n, self.basis_name, times, self._meas_basis,
+                {"epsilon": self.noise_model.p_false_pos, "epsilon_prime": self.noise_model.p_false_neg},
+            )
+        traj_nb = 0
+        n_trajectories = self.n_trajectories
+
+        def sample_all(plan, chunk, t_index):
+            for i, (_, reps) in enumerate(chunk):
+                if hd.basis_data.dim == 2 and not matching:
+                    c = Counter({"0" * n: spr * reps})  # only 000...0 is measured (qutip_result.py:120-123)
+                else:
+                    c = plan.sample(spr * reps, one_state, traj=i)
+                if flipper is not None:
+                    c = flipper._flip(c)
+                counts[t_index] += c
+
+        for b0 in range(0, len(pending), batch):
+            chunk = pending[b0 : b0 + batch]
+            if print_progress:
+                for _, reps in chunk:
+                    if reps == 1:
+                        print(f"Emulating Trajectory {traj_nb+1}/{n_trajectories}")
+                    else:
+                        print("Emulating Trajectories " f"[{traj_nb+1} - {traj_nb+reps}]/{n_trajectories}")
+                    traj_nb += reps
+            with engine.DevicePlan([s for s, _ in chunk], self._interp_order, self._gpu) as plan:
+                plan.set_state(self._initial_state.full().reshape(-1))
+                sample_all(plan, chunk, 0)
+                for k, (t0, t1) in enumerate(zip(times[:-1], times[1:])):
+                    plan.propagate(t0, t1, **opts)
+                    sample_all(plan, chunk, k + 1)
+            self._current_spec = chunk[-1][0]
+        return counts
+
+    def _noisy_runs(self, print_progress: bool, batch: int, opts: dict):
+        """simulation.py:885-915, trajectories evolved in device batches."""
+        n_trajectories = self.n_trajectories
+        pending = self._pending_trajectories()
         if not pending:
             return
         D = pending[0][0].hilbert_dim

@@ -485,7 +485,10 @@ class CoherentResults(SimulationResults):
         )
 
     def sample_state(self, t: float, n_samples: int = 1000, t_tol: float = 1.0e-3) -> Counter:
-        sampled = super().sample_state(t, n_samples, t_tol)
+        return self._flip(super().sample_state(t, n_samples, t_tol))
+
+    def _flip(self, sampled: Counter) -> Counter:
+        """Detection errors epsilon / epsilon' applied to sampled bitstrings (simresults.py:522-568)."""
         if self._meas_errors is None or (
             self._meas_errors["epsilon"] == 0.0 and self._meas_errors["epsilon_prime"] == 0
         ):

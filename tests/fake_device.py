@@ -42,6 +42,15 @@ class FakeDevicePlan:
     def get_state(self):
         return np.stack(self.states)
 
+    def sample(self, n_samples, one_state, traj=0):
+        from pulser_b200.results import B200Result, StateVector
+
+        spec = self.specs[traj]
+        meas = {"r": "ground-rydberg", "h": "digital", "d": "XY"}[one_state]
+        matching = meas in spec.basis_name
+        res = B200Result(tuple(range(spec.n_qudits)), meas, StateVector(self.states[traj]), matching)
+        return res.get_samples(n_samples)
+
     def apply_h(self, t_us, vec, traj=0):
         return self.hams[traj].matrix_at(t_us, self.order) @ np.asarray(vec, dtype=complex)
 
