@@ -260,7 +260,10 @@ def run_gpu(args) -> None:
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_s = (kernel_ms * 1e-3) / max(launches, 1)
-        alg_bytes = 40.0 * D  # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply
+        # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply; a launch of the stage kernel
+        # carries one H-apply, or two when the h and h/2 Richardson chains share it
+        applies_per_launch = applies / max(launches, 1)
+        alg_bytes = 40.0 * D * applies_per_launch
         achieved = alg_bytes / per_launch_s / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -269,6 +272,7 @@ def run_gpu(args) -> None:
             "config": config_dict(world),
             "steps_x_dim": value * D,
             "h_applies_per_time_step": applies / (T * args.steps),
+            "integrator": {1: "chebyshev-clenshaw", 2: "lanczos"}.get(int(st.get("integrator", 1)), "?"),
             "norm2_final": norm2,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -276,8 +280,9 @@ def run_gpu(args) -> None:
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
-                         "kernel": "stage_d2_rb_kernel (one fused H-apply + Clenshaw update per launch)",
+                         "kernel": "stage_d2_rb_kernel (fused H-apply + Clenshaw update; 1 or 2 chains per launch)",
                          "algorithmic_bytes_per_launch": alg_bytes,
+                         "h_applies_per_launch": applies_per_launch,
                          "avg_launch_us": per_launch_s * 1e6,
                          "note": "CUDA-event time of the propagation / launches (includes launch gaps); "
                                  "the 16 MiB state is L2-resident, DRAM traffic per launch is far below the algorithmic bytes"},
