@@ -261,7 +261,15 @@ __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
 // (flipped tile bits - RB + 1) x 16 B.
 // Compute phase of one tile, shared by the one-shot and the persistent kernels: gathers from the tile in
 // shared memory (register-blocked), optional global-load partners, fused epilogue and store.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+// own-element global load: streaming (one-shot kernels) or L1-bypassing (cooperative kernel, where the data
+// was written by other CTAs earlier in the same launch and L1 is not coherent)
+template <bool COH>
+__device__ __forceinline__ c2 ld_own(const c2* p) {
+    double2 r = COH ? __ldcg(reinterpret_cast<const double2*>(p)) : __ldcs(reinterpret_cast<const double2*>(p));
+    return {r.x, r.y};
+}
+
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false>
 __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* __restrict__ tile,
                                                 const double* __restrict__ tab, long long base, long long traj,
                                                 int tid) {
@@ -349,7 +357,8 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         const double gy = (bit == to_bit) ? gyt : -gyt;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const double2 raw = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
+            const double2 raw = COH ? __ldcg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))))
+                                    : __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
             if (UNIFORM) {
                 pr[r] += raw.x; pi[r] += raw.y;
                 if (!REAL_G) { qr[r] = fma(sg, raw.x, qr[r]); qi[r] = fma(sg, raw.y, qi[r]); }
@@ -411,8 +420,8 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 dv[r] = dsrc ? __ldcs(dsrc + idx[h0 + r]) : 0.0;
-                pv[r] = a.psi ? ld_stream(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
-                bv[r] = a.b2 ? ld_stream(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                pv[r] = a.psi ? ld_own<COH>(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                bv[r] = a.b2 ? ld_own<COH>(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
             }
 #pragma unroll
             for (int r = 0; r < H; ++r) {
@@ -439,7 +448,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         for (int h0 = 0; h0 < R; h0 += H) {
             c2 ov[H];
 #pragma unroll
-            for (int r = 0; r < H; ++r) ov[r] = ld_stream(a.out + voff + idx[h0 + r]);
+            for (int r = 0; r < H; ++r) ov[r] = ld_own<COH>(a.out + voff + idx[h0 + r]);
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 const int rr = h0 + r;
@@ -583,6 +592,133 @@ stage_d2_pipe_kernel(StageArgs a, long long tiles_per_traj, long long n_items) {
         mbar_wait(&mbar[s], (uint32_t)((it / STAGES) & 1));
         rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tiles + (size_t)s * TSIZE, tab, base, traj, tid);
         __syncthreads();  // everyone is done with stage s (and with tab) before it is refilled
+    }
+}
+
+// ---- d = 2 cooperative persistent kernel: a whole program of Clenshaw stages in ONE launch ----------------------
+// All CTAs are co-resident (cooperative launch).  Every stage runs its tile passes (pass A: the low TBITS bits,
+// later passes: the high bits gathered by strided TMA rows, 88-120 B/amplitude through L2 instead of ~200 with
+// out-of-tile partner loads) separated by grid-wide barriers; the stage list (buffers, Clenshaw scalars, drive
+// parameters of up to two chains) is a table in global memory, so a sequence of exponentials costs one launch.
+struct CoopChain {
+    const c2* v; const c2* psi; const c2* b2; c2* out;
+    StageCoef coef; UniformDrive u; const double* table;
+};
+struct CoopStage {
+    CoopChain c[2];
+    int n_chains;
+    int pad;
+};
+struct CoopArgs {
+    const CoopStage* stages;
+    int n_stages;
+    int n_passes;
+    PassGeom geo[4];
+    const double* dint; long long dint_stride; long long D;
+    int n_traj; int to_bit; int from_is_one;
+    unsigned int* barrier;  // [0] arrivals, [1] generation
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(&bar[0], 1u);
+        if (prev == nblocks - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(&bar[1], 1u);
+        } else {
+            unsigned int cur;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
+            } while (cur == gen);
+        }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    ++gen;
+    __syncthreads();
+}
+
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+__global__ void __launch_bounds__(1 << (TBITS - RB), 2) coop_program_kernel(const __grid_constant__ CoopArgs A) {
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tiles = reinterpret_cast<c2*>(smem_raw);                       // 2 tile buffers
+    double* tab = reinterpret_cast<double*>(tiles + 2 * (size_t)TSIZE);  // per-bit table (non-uniform drives)
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ StageArgs sargs[2];
+    __shared__ long long sbase[2];
+    __shared__ long long straj[2];
+
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    __syncthreads();
+    unsigned int gen = 0;  // only thread 0's copy is compared in the barrier
+    if (tid == 0) gen = *reinterpret_cast<volatile unsigned int*>(A.barrier + 1);
+    unsigned int it = 0;  // tile tasks processed by this CTA so far (mbarrier parity bookkeeping)
+
+    for (int s = 0; s < A.n_stages; ++s) {
+        const CoopStage* stg = A.stages + s;
+        const int n_chains = stg->n_chains;
+        for (int pass = 0; pass < A.n_passes; ++pass) {
+            const PassGeom g = A.geo[pass];
+            const int tbits = g.lo_bits + g.hi_bits;
+            const long long tiles_per_traj = A.D >> tbits;
+            const long long per_chain = tiles_per_traj * A.n_traj;
+            const long long n_tasks = per_chain * n_chains;
+            const int rows = 1 << g.hi_bits;
+            const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+            auto issue = [&](long long w, int slot) {
+                const int chain = (int)(w / per_chain);
+                const long long r1 = w - chain * per_chain;
+                const long long traj = r1 / tiles_per_traj;
+                const long long base = tile_base_of(g, r1 - traj * tiles_per_traj);
+                const CoopChain& cc = stg->c[chain];
+                if (tid == 0) {
+                    StageArgs& a = sargs[slot];
+                    a.v = cc.v; a.psi = cc.psi; a.b2 = cc.b2; a.out = cc.out;
+                    a.dint = A.dint; a.dint_stride = A.dint_stride; a.D = A.D;
+                    a.geo = g; a.coef = cc.coef; a.u = cc.u; a.table = cc.table;
+                    a.to_bit = A.to_bit; a.from_is_one = A.from_is_one;
+                    a.beta_dev = nullptr; a.dot_acc = nullptr; a.swz = 0; a.dbg = 0;
+                    sbase[slot] = base; straj[slot] = traj;
+                    mbar_arrive_expect_tx(&mbar[slot], (uint32_t)TSIZE * 16u);
+                }
+                const c2* vsrc = cc.v + traj * A.D;
+                c2* dst = tiles + (size_t)slot * TSIZE;
+                for (int r = tid; r < rows; r += NT)
+                    tma_load_1d(dst + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar[slot]);
+            };
+            long long w = blockIdx.x;
+            if (w < n_tasks) issue(w, it & 1);
+            long long tab_key = -1;
+            for (; w < n_tasks; w += gridDim.x, ++it) {
+                const int slot = it & 1;
+                const long long wn = w + gridDim.x;
+                if (wn < n_tasks) issue(wn, slot ^ 1);  // the other buffer was released by the barrier below
+                __syncthreads();                          // sargs / sbase of `slot` written by thread 0 are visible
+                const long long traj = straj[slot];
+                if (!UNIFORM) {
+                    const int chain = (int)(w / per_chain);
+                    const long long key = chain * (long long)A.n_traj + traj;
+                    if (key != tab_key) {
+                        const int stride = d2_table_stride(g.n_bits);
+                        const double* src = stg->c[chain].table + traj * stride;
+                        for (int i = tid; i < stride; i += NT) tab[i] = __ldcg(src + i);
+                        tab_key = key;
+                        __syncthreads();
+                    }
+                }
+                mbar_wait(&mbar[slot], (it >> 1) & 1u);
+                rb_tile_compute<UNIFORM, REAL_G, TBITS, RB, true>(sargs[slot], g, tiles + (size_t)slot * TSIZE, tab,
+                                                                   sbase[slot], traj, tid);
+                __syncthreads();
+            }
+            grid_barrier(A.barrier, gridDim.x, gen);
+        }
     }
 }
 

@@ -95,6 +95,12 @@ struct Plan {
     int reg_bits = 3;
     bool use_pipe = false;
     bool use_dual = true;
+    bool use_coop = true;
+    bool coop_now = false;                 // decided per propagate call
+    std::vector<PassGeom> coop_passes;
+    CoopStage* d_coop = nullptr; size_t d_coop_cap = 0;
+    unsigned int* d_bar = nullptr;
+    int coop_slots[3] = {0, 0, 0};  // co-resident CTAs of the 3 template variants (0 = not queried)
     int dbg = 0;
     bool swizzle = false;
     int swizzle_min_bits = 12;
@@ -539,6 +545,95 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
     }
 }
 
+// ---- cooperative persistent execution of whole programs ---------------------------------------------------------
+static bool coop_eligible(const Plan& P, const std::vector<PassGeom>& cpasses) {
+    if (!P.use_coop || !(P.dim == 2 && P.n_drives == 1) || P.has_diss || P.use_krylov || P.force_v1) return false;
+    if (P.reg_bits != 3 || cpasses.size() > 4) return false;
+    if ((double)P.D * P.B * 16.0 > (double)env_int("PB200_COOP_MIB", 72) * 1048576.0) return false;  // L2-resident only
+    if (P.n < 14) return false;
+    for (const PassGeom& g : cpasses) {
+        if (g.lo_bits + g.hi_bits != 11 || g.extra_mask != 0) return false;
+        if (!g.first_pass && g.hi_bits < 3) return false;
+    }
+    return true;
+}
+
+static void run_chains_coop(Plan& P, Chain* chains, int n, const std::vector<PassGeom>& cpasses, pb200_run_stats& st) {
+    const bool uniform = P.all_uniform() && P.B == 1;
+    if (!uniform) {
+        size_t total = 0;
+        for (int c = 0; c < n; ++c) { chains[c].table_base = total; total += chains[c].prog->tables.size(); }
+        ensure_table_capacity(P, total);
+        for (int c = 0; c < n; ++c)
+            if (!chains[c].prog->tables.empty())
+                CUDA_CHECK(cudaMemcpyAsync(P.d_table + chains[c].table_base, chains[c].prog->tables.data(),
+                                           chains[c].prog->tables.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                           P.stream));
+    }
+    // unroll the chains into the stage table
+    std::vector<CoopStage> table;
+    bool real_g = true;
+    while (true) {
+        CoopStage cs{};
+        int k = 0;
+        for (int c = 0; c < n; ++c)
+            if (!chains[c].done()) {
+                StageIO io{};
+                chains[c].next(P, uniform, io);
+                CoopChain& cc = cs.c[k++];
+                cc.v = io.v; cc.psi = io.psi; cc.b2 = io.b2; cc.out = io.out;
+                cc.coef = io.coef; cc.u = io.ud; cc.table = io.table;
+                real_g = real_g && io.real_g;
+            }
+        if (k == 0) break;
+        cs.n_chains = k;
+        table.push_back(cs);
+    }
+    if (table.empty()) return;
+    if (table.size() > P.d_coop_cap) {
+        if (P.d_coop) CUDA_CHECK(cudaFree(P.d_coop));
+        P.d_coop = nullptr;
+        P.d_coop_cap = std::max(table.size(), (size_t)4096);
+        CUDA_CHECK(cudaMalloc(&P.d_coop, sizeof(CoopStage) * P.d_coop_cap));
+    }
+    if (!P.d_bar) {
+        CUDA_CHECK(cudaMalloc(&P.d_bar, 2 * sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemsetAsync(P.d_bar, 0, 2 * sizeof(unsigned int), P.stream));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(P.d_coop, table.data(), sizeof(CoopStage) * table.size(), cudaMemcpyHostToDevice, P.stream));
+    CoopArgs A{};
+    A.stages = P.d_coop; A.n_stages = (int)table.size(); A.n_passes = (int)cpasses.size();
+    for (size_t i = 0; i < cpasses.size(); ++i) A.geo[i] = cpasses[i];
+    A.dint = P.has_interaction ? P.dint : nullptr;
+    A.dint_stride = P.dint_shared ? 0 : P.D;
+    A.D = P.D; A.n_traj = P.B;
+    A.to_bit = P.desc.drives[0].state_to; A.from_is_one = P.desc.drives[0].state_from;
+    A.barrier = P.d_bar;
+    const int threads = 256;
+    const size_t smem = (size_t)2 * 2048 * 16 + (uniform ? 0 : (size_t)d2_table_stride(P.n) * 8);
+    void* fn = uniform ? (real_g ? (void*)coop_program_kernel<true, true, 11, 3> : (void*)coop_program_kernel<true, false, 11, 3>)
+                       : (void*)coop_program_kernel<false, false, 11, 3>;
+    const int variant = uniform ? (real_g ? 0 : 1) : 2;
+    if (P.coop_slots[variant] == 0) {
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 2048 * 16 + 1024)));
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+        if (per_sm < 1) fail(PB200_ERR_CUDA, "cooperative kernel does not fit on an SM");
+        P.coop_slots[variant] = per_sm * P.sm_count;
+    }
+    const long long max_tasks = (P.D >> 11) * (long long)P.B * 2;
+    const int grid = (int)std::min<long long>(P.coop_slots[variant], std::max<long long>(max_tasks, 1));
+    void* kargs[] = {(void*)&A};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, P.stream));
+    CUDA_CHECK(cudaStreamSynchronize(P.stream));  // the host-side stage / coefficient tables are reused next
+    st.n_launches += 1;
+    for (int c = 0; c < n; ++c) {
+        st.n_applies += chains[c].applies;
+        st.max_rho = std::max(st.max_rho, chains[c].max_rho);
+        st.n_exponentials += (long long)chains[c].prog->cheb.size();
+    }
+}
+
 // eigen-decomposition of a real symmetric tridiagonal matrix (implicit QL, eigenvectors accumulated);
 // d: diagonal (in) / eigenvalues (out), e: sub-diagonal e[0..n-2], z: n x n row-major, identity on entry
 static void tridiag_ql(std::vector<double>& d, std::vector<double> e, std::vector<double>& z, int n) {
@@ -724,7 +819,8 @@ static void run_program(Plan& P, const Program& prog, const std::vector<PassGeom
     ch.psi = P.buf[P.cur];
     ch.psi_is_private = true;
     for (int i = 0; i < 3; ++i) ch.pool[i] = P.buf[i];
-    run_chains(P, &ch, 1, passes, st);
+    if (P.coop_now) run_chains_coop(P, &ch, 1, P.coop_passes, st);
+    else run_chains(P, &ch, 1, passes, st);
     for (int i = 0; i < 3; ++i)
         if (P.buf[i] == ch.result()) P.cur = i;
 }
@@ -1030,7 +1126,9 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     }
     const double rho_cap = P.use_krylov ? env_int("PB200_RHO_CAP_KRYLOV_MILLI", 12000) * 1e-3
                                         : env_int("PB200_RHO_CAP_MILLI", 3600) * 1e-3;
-    const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss && !P.use_krylov;
+    P.coop_passes = plan_passes(P.n, 11, 0);
+    P.coop_now = coop_eligible(P, P.coop_passes);
+    const bool dual_ok = (dual_chain_ok(P, passes) || P.coop_now) && !P.has_diss && !P.use_krylov;
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
     // a symmetric 2nd-order scheme whatever the order of its unitary part
     const int pw_base = P.has_diss ? 2 : ((order == 4) ? 4 : 2);
@@ -1055,7 +1153,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             Chain ch[2];
             ch[0].prog = &half; ch[0].psi = X; for (int i = 0; i < 3; ++i) ch[0].pool[i] = others[i];
             ch[1].prog = &big;  ch[1].psi = X; for (int i = 0; i < 3; ++i) ch[1].pool[i] = others[3 + i];
-            run_chains(P, ch, 2, passes, st);
+            if (P.coop_now) run_chains_coop(P, ch, 2, P.coop_passes, st);
+            else run_chains(P, ch, 2, passes, st);
             c2* res = ch[0].result();
             axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(res, ch[1].result(), 1.0 + 1.0 / sc, -1.0 / sc, total);
             CUDA_CHECK(cudaGetLastError());
@@ -1338,6 +1437,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
     P.use_pipe = env_int("PB200_PIPE", 0) != 0;
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
+    P.use_coop = env_int("PB200_COOP", 1) != 0;
     P.dbg = env_int("PB200_DBG", 0);
     P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
     P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);
@@ -1397,6 +1497,8 @@ int pb200_plan_destroy(pb200_plan* h) {
         if (P.buf[i]) cudaFree(P.buf[i]);
     for (int i = 0; i < 6; ++i)
         if (P.aux[i]) cudaFree(P.aux[i]);
+    if (P.d_coop) cudaFree(P.d_coop);
+    if (P.d_bar) cudaFree(P.d_bar);
     if (P.kry) cudaFree(P.kry);
     if (P.d_kry) cudaFree(P.d_kry);
     if (P.dint) cudaFree(P.dint);
