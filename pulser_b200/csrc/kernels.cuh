@@ -527,14 +527,25 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
         for (int i = tid; i < stride; i += NT) tab[i] = src[i];
     }
     __syncthreads();
-    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
-    {
+    if (a.dbg & 16) {
+        // experiment: plain LDG.128 -> STS.128 tile load instead of TMA bulk copies
+        const long long lomask = (1LL << g.lo_bits) - 1;
+#pragma unroll
+        for (int r = 0; r < (1 << RB); ++r) {
+            const int t = tid + r * NT;
+            const long long idx = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(vsrc + idx));
+            tile[t] = {raw.x, raw.y};
+        }
+        __syncthreads();
+    } else {
+        if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
         const int rows = 1 << g.hi_bits;
         const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
         for (int r = tid; r < rows; r += NT)
             tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+        mbar_wait(&mbar, 0);
     }
-    mbar_wait(&mbar, 0);
     rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
 }
 

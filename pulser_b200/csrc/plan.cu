@@ -552,7 +552,7 @@ static bool coop_eligible(const Plan& P, const std::vector<PassGeom>& cpasses) {
     if ((double)P.D * P.B * 16.0 > (double)env_int("PB200_COOP_MIB", 72) * 1048576.0) return false;  // L2-resident only
     if (P.n < 14) return false;
     for (const PassGeom& g : cpasses) {
-        if (g.lo_bits + g.hi_bits != 11 || g.extra_mask != 0) return false;
+        if (g.lo_bits + g.hi_bits != 11) return false;
         if (!g.first_pass && g.hi_bits < 3) return false;
     }
     return true;
@@ -1126,7 +1126,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     }
     const double rho_cap = P.use_krylov ? env_int("PB200_RHO_CAP_KRYLOV_MILLI", 12000) * 1e-3
                                         : env_int("PB200_RHO_CAP_MILLI", 3600) * 1e-3;
-    P.coop_passes = plan_passes(P.n, 11, 0);
+    P.coop_passes = plan_passes(P.n, 11, env_int("PB200_COOP_EXTRA", 0));
     P.coop_now = coop_eligible(P, P.coop_passes);
     const bool dual_ok = (dual_chain_ok(P, passes) || P.coop_now) && !P.has_diss && !P.use_krylov;
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
@@ -1437,7 +1437,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
     P.use_pipe = env_int("PB200_PIPE", 0) != 0;
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
-    P.use_coop = env_int("PB200_COOP", 1) != 0;
+    P.use_coop = env_int("PB200_COOP", 0) != 0;  // experiment: slower than per-stage launches
     P.dbg = env_int("PB200_DBG", 0);
     P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
     P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);

@@ -164,5 +164,37 @@ def main():
         save(f"orc_noisy_traj{i}", spec, psi0=psi0, orc_final=oracle_final(spec, psi0), reps=reps)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--extra" not in sys.argv:
     main()
+
+
+def extra():
+    """Second batch: non-uniform sampling grid (sampling_rate < 1) and leakage + effective noise (Lindblad, d = 3)."""
+    reg = Register({"a": (-4.0, 0.0), "b": (0.0, 4.0), "c": (4.0, 0.0)})
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(600, 1.3 * np.pi), -2.0, 0.4), "ch")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(400, 0.6 * np.pi), 3.0, 0.0), "ch")
+    spec = specs_of(seq, rate=0.3)[0][0]
+    assert len(np.unique(np.round(np.diff(spec.sampling_times), 9))) > 1  # non-uniform grid
+    psi0 = evolve.all_ground_state(spec)
+    save("orc_sampling_rate_03", spec, psi0=psi0, orc_final=oracle_final(spec, psi0))
+
+    # leakage: eigenbasis (r, g, x) with effective-noise jump operators (reference hamiltonian_data.py:718-738)
+    reg = Register({"a": (-3.5, 0.0), "b": (3.5, 0.0)})
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(500, np.pi), 1.0, 0.0), "ch")
+    leak = np.zeros((3, 3)); leak[2, 0] = 1.0   # |x><r|
+    deph = np.diag([1.0, 0.0, 0.0])
+    nm = NoiseModel(with_leakage=True, eff_noise_opers=(leak, deph), eff_noise_rates=(0.3, 0.5))
+    spec = specs_of(seq, nm)[0][0]
+    assert spec.eigenbasis == ["r", "g", "x"] and spec.collapse_ops.shape == (2, 3, 3)
+    from oracle.ref_hamiltonian import OracleHamiltonian as OH
+    psi0 = evolve.all_ground_state(spec)
+    rho = evolve.mesolve(OH.from_spec(spec), psi0, [0.0, spec.sampling_times[-1]])[-1]
+    save("orc_leakage_lindblad", spec, psi0=psi0, orc_rho=rho)
+
+
+if __name__ == "__main__" and "--extra" in sys.argv:
+    extra()

@@ -88,3 +88,47 @@ def test_all_basis_apply_h(engine):
     with engine.DevicePlan(spec) as plan:
         for t in (0.2, 1.0, 1.9):
             assert np.max(np.abs(plan.apply_h(t, v) - mf.apply(t, v))) < 1e-12
+
+
+def test_nonuniform_sampling_grid(engine):
+    """sampling_rate = 0.3: integer-truncated, non-uniform sampling times (hamiltonian.py:87-95)."""
+    spec, extra = load("orc_sampling_rate_03")
+    assert len(np.unique(np.round(np.diff(spec.sampling_times), 9))) > 1
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state(extra["psi0"])
+        plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - extra["orc_final"])) < STATE_TOL
+
+
+def test_leakage_effective_noise_lindblad(engine):
+    """3-level (r, g, x) register with effective-noise collapse operators: master equation, tol 1e-4."""
+    from pulser_b200.lindblad import LindbladPlan
+
+    spec, extra = load("orc_leakage_lindblad")
+    with LindbladPlan(spec) as lp:
+        lp.set_state(extra["psi0"])
+        lp.propagate(0.0, spec.sampling_times[-1])
+        rho = lp.get_rho()[0]
+    assert np.max(np.abs(rho - extra["orc_rho"])) < 1e-4
+    assert abs(np.trace(rho).real - 1.0) < 1e-6
+    x_pop = sum(rho[i, i].real for i in range(9) if 2 in divmod(i, 3))
+    assert x_pop > 1e-3  # the leakage state got populated
+
+
+@pytest.mark.parametrize("order", [0, 1, 3])
+def test_interpolation_orders(engine, order):
+    """QobjEvo coefficient interpolation is switchable (step / linear / cubic); each matches the oracle run
+    with the same rule."""
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    spec, extra = load("orc_noisy_traj1")
+    ref = evolve.sesolve(OracleHamiltonian.from_spec(spec), extra["psi0"], [0.0, spec.sampling_times[-1]],
+                         order=order, rtol=1e-12, atol=1e-14, max_step=2.5e-4)[-1]
+    with engine.DevicePlan(spec, interp_order=order) as plan:
+        plan.set_state(extra["psi0"])
+        plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    # piecewise-constant / piecewise-linear H(t) limits the accuracy of the adaptive ODE oracle, not ours
+    assert np.max(np.abs(got - ref)) < (STATE_TOL if order == 3 else 5e-7)
