@@ -1184,40 +1184,48 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     double Kc = adaptive ? std::min(extrap ? 8.0 : 4.0, (double)Kmax) : (double)Kmax;
     int since_check = 1 << 30;  // force a check at the first smooth step
     double smooth_len = 0.0; long long smooth_steps = 0;
+    bool last_fine = false;
     double t = t_start;
     while (t < t_stop - eps) {
         const int i = find_piece(P.times, t + eps);
         const double hi_i = P.times[i + 1] - P.times[i];
         double b;
-        bool smooth = !fine[i];
-        if (!smooth) {
-            since_check = 1 << 30;  // re-validate the step length when the smooth region resumes
-            b = P.times[i + 1];
-            if (jump[i] && order == 4) {
-                const int nsub = jump_substeps(P, t, std::min(b, t_stop), magnus_tol);
-                if (nsub > 1) b = std::min(b, t + hi_i / nsub);
+        // Every step is error-controlled.  "Fine" intervals (next to a non-smooth sample) are never merged with
+        // their neighbours; elsewhere up to Kc intervals form one step.  In both cases the step may be a
+        // fraction of an interval when the controller or the convergence-radius cap ask for it.
+        const bool is_fine = fine[i] != 0;
+        const bool smooth = true;
+        if (is_fine != last_fine) { since_check = 1 << 30; last_fine = is_fine; }  // re-validate on region change
+        double Kuse = is_fine ? std::min(Kc, 1.0) : Kc;
+        {   // keep the step inside the convergence radius of the Magnus expansion: the spectral
+            // half-width of int H dt over the step stays below rho_cap (~pi)
+            std::vector<cplx> q0, q1; std::vector<double> r0, r1;
+            moments_for_step(P, t, std::min(P.times[i + 1], t_stop), q0, q1, r0, r1);
+            ExpParams E; E.g = q0; E.th = r0; E.w = std::min(P.times[i + 1], t_stop) - t;
+            double gm, rh1; std::vector<double> scratch_tab;
+            build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
+            const double frac = E.w / hi_i;  // fraction of a sampling interval covered by this probe
+            const double rho_per_sample = rh1 / std::max(frac, 1e-9);
+            Kuse = std::min(Kuse, rho_cap / std::max(rho_per_sample, 1e-12));
+        }
+        if (Kuse >= 1.0) {
+            int K = std::max(1, std::min((int)std::floor(Kuse + 1e-9), Kmax));
+            if (is_fine) {
+                b = P.times[i + 1];
+            } else {
+                // graded steps: no longer than half the distance to the nearest non-smooth sample on either side
+                K = std::max(1, std::min(K, dist[i] / 2));
+                int j = i, cnt = 0;
+                while (j < nt - 1 && !fine[j] && cnt < K && (cnt == 0 || 2 * (cnt + 1) <= std::max(dist[j], 2))) { ++j; ++cnt; }
+                b = P.times[j];
             }
-        } else if (Kc >= 1.0) {
-            // graded steps: no longer than half the distance to the nearest non-smooth sample on either side
-            int K = std::max(1, std::min((int)std::floor(Kc + 1e-9), Kmax));
-            {   // keep the step inside the convergence radius of the Magnus expansion: the spectral
-                // half-width of int H dt over the step stays below rho_cap (~pi)
-                std::vector<cplx> q0, q1; std::vector<double> r0, r1;
-                moments_for_step(P, t, std::min(P.times[i + 1], t_stop), q0, q1, r0, r1);
-                ExpParams E; E.g = q0; E.th = r0; E.w = std::min(P.times[i + 1], t_stop) - t;
-                double gm, rh1; std::vector<double> scratch_tab;
-                build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
-                const double frac = E.w / hi_i;  // fraction of a sampling interval covered by this probe
-                const double rho_per_sample = rh1 / std::max(frac, 1e-9);
-                K = std::max(1, std::min(K, (int)std::floor(rho_cap / std::max(rho_per_sample, 1e-12))));
-            }
-            K = std::max(1, std::min(K, dist[i] / 2));
-            int j = i, cnt = 0;
-            while (j < nt - 1 && !fine[j] && cnt < K && (cnt == 0 || 2 * (cnt + 1) <= std::max(dist[j], 2))) { ++j; ++cnt; }
-            b = P.times[j];
         } else {
-            const int nsub = std::min(64, (int)std::ceil(1.0 / Kc - 1e-9));
+            const int nsub = std::min(64, (int)std::ceil(1.0 / std::max(Kuse, 1.0 / 64.0) - 1e-9));
             b = std::min(P.times[i + 1], t + hi_i / nsub);
+        }
+        if (jump[i] && order == 4) {  // a-priori sub-stepping of sample-to-sample jumps
+            const int nsub = jump_substeps(P, t, std::min(P.times[i + 1], t_stop), magnus_tol);
+            if (nsub > 1) b = std::min(b, t + hi_i / nsub);
         }
         b = std::min(b, t_stop);
         if (b <= t + eps) b = std::min(P.times[std::min(i + 1, nt - 1)], t_stop);
@@ -1270,7 +1278,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
                 if (err_big > noise) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
                 factor = std::min(2.0, std::max(0.2, factor));
                 Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
-                since_check = (factor < 0.7) ? check_every - 2 : 0;  // re-check soon after a big cut
+                // re-check soon after a big cut, and while the step is still growing at the maximum rate
+                since_check = (factor < 0.7) ? check_every - 2 : ((factor >= 1.9) ? check_every - 3 : 0);
             } else {
                 ++since_check;
             }
