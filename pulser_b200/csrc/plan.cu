@@ -1277,9 +1277,12 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
                 const double noise = 50.0 * ctol + 1e-14;
                 if (err_big > noise) factor = std::pow(0.5 * rate_allowed / rate, 1.0 / pw);
                 factor = std::min(2.0, std::max(0.2, factor));
+                const bool controller_limited = h_samples >= 0.9 * Kc;  // not shortened by a cap / grading
                 Kc = std::min((double)Kmax, std::max(1.0 / 16.0, h_samples * factor));
-                // re-check soon after a big cut, and while the step is still growing at the maximum rate
-                since_check = (factor < 0.7) ? check_every - 2 : ((factor >= 1.9) ? check_every - 3 : 0);
+                // re-check soon after a big cut, and while a controller-limited step is still growing at the
+                // maximum rate (so that the step recovers quickly after a non-smooth stretch)
+                since_check = (factor < 0.7) ? check_every - 2
+                                             : ((factor >= 1.9 && controller_limited) ? check_every - 3 : 0);
             } else {
                 ++since_check;
             }
