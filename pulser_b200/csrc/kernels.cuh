@@ -269,10 +269,13 @@ __device__ __forceinline__ c2 ld_own(const c2* p) {
     return {r.x, r.y};
 }
 
+// `ring` (optional): two tile-sized shared-memory slots through which the out-of-tile partner tiles are
+// streamed by TMA (slots 0 and 1 already hold / are receiving the partners of the first two extra bits when
+// this function is entered); `rbar` their mbarriers.
 template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false>
 __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* __restrict__ tile,
                                                 const double* __restrict__ tab, long long base, long long traj,
-                                                int tid) {
+                                                int tid, c2* ring = nullptr, uint64_t* rbar = nullptr) {
     constexpr int R = 1 << RB;
     constexpr int NT = 1 << (TBITS - RB);
     const long long voff = traj * a.D;
@@ -347,24 +350,43 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         const int t = tid + r * NT;
         idx[r] = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
     }
-    // --- flips served by coalesced global loads (bits outside the tile) ---
-    for (unsigned long long m = (a.dbg & 2) ? 0ULL : g.extra_mask; m; m &= m - 1) {
+    // --- flips of the bits outside the tile: partner tiles streamed through the TMA ring, or coalesced loads ---
+    int e_cnt = 0;
+    for (unsigned long long m = (a.dbg & 2) ? 0ULL : g.extra_mask; m; m &= m - 1, ++e_cnt) {
         const int p = __ffsll((long long)m) - 1;
         double gx = 0.0, gyt = 0.0;
         if (!UNIFORM) { gx = tab[2 * p]; gyt = tab[2 * p + 1]; }
         const int bit = (int)((base >> p) & 1);  // extra bits are never tile bits
         const double sg = (bit == to_bit) ? 1.0 : -1.0;
         const double gy = (bit == to_bit) ? gyt : -gyt;
+        const c2* slot = nullptr;
+        if (ring) {
+            slot = ring + (size_t)(e_cnt & 1) * (1 << TBITS);
+            mbar_wait(&rbar[e_cnt & 1], (uint32_t)((e_cnt >> 1) & 1));
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const double2 raw = COH ? __ldcg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))))
-                                    : __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
+            double2 raw;
+            if (ring) { const c2 sv = slot[tid + r * NT]; raw = make_double2(sv.x, sv.y); }
+            else raw = COH ? __ldcg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))))
+                           : __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
             if (UNIFORM) {
                 pr[r] += raw.x; pi[r] += raw.y;
                 if (!REAL_G) { qr[r] = fma(sg, raw.x, qr[r]); qi[r] = fma(sg, raw.y, qi[r]); }
             } else {
                 pr[r] = fma(gx, raw.x, pr[r]); pr[r] = fma(-gy, raw.y, pr[r]);
                 pi[r] = fma(gx, raw.y, pi[r]); pi[r] = fma(gy, raw.x, pi[r]);
+            }
+        }
+        if (ring) {
+            __syncthreads();  // every thread has consumed the slot: refill it with the partner tile after next
+            unsigned long long m2 = m & (m - 1);
+            m2 &= m2 - 1;      // second next extra bit
+            if (m2 && tid == 0) {
+                const int p2 = __ffsll((long long)m2) - 1;
+                mbar_arrive_expect_tx(&rbar[e_cnt & 1], (uint32_t)(1 << TBITS) * 16u);
+                tma_load_1d(ring + (size_t)(e_cnt & 1) * (1 << TBITS), vsrc + (base ^ (1LL << p2)),
+                            (uint32_t)(1 << TBITS) * 16u, &rbar[e_cnt & 1]);
             }
         }
     }
@@ -547,6 +569,52 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
         mbar_wait(&mbar, 0);
     }
     rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
+}
+
+// ---- d = 2 single-pass stage kernel with TMA-streamed partner tiles ----------------------------------------------
+// Same maths as stage_d2_rb_kernel, but the partner tiles of the bits above the tile (contiguous 2^TBITS
+// amplitudes each) are brought in by bulk copies into a two-slot shared-memory ring, two tiles ahead, instead
+// of latency-exposed LDG.128: the L2 traffic is identical, its latency is hidden behind the in-tile gathers.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
+stage_d2_stream_kernel(const __grid_constant__ StageArgs2 m) {
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    c2* ring = tile + TSIZE;                                          // 2 slots
+    double* tab = reinterpret_cast<double*>(ring + 2 * (size_t)TSIZE);
+    __shared__ __align__(8) uint64_t mbar[3];
+
+    const int chain = blockIdx.y / m.n_traj;
+    const StageArgs& a = m.a[chain];
+    const PassGeom g = a.geo;  // single pass: lo_bits = TBITS, hi_bits = 0, extra_mask = all higher bits
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y - chain * m.n_traj;
+    const long long base = tile_base_of(g, blockIdx.x);
+    const c2* vsrc = a.v + traj * a.D;
+
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); }
+    pdl_wait();
+    pdl_launch_dependents();
+    if (!UNIFORM) {
+        const int stride = d2_table_stride(g.n_bits);
+        const double* src = a.table + traj * stride;
+        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&mbar[0], (uint32_t)TSIZE * 16u);
+        tma_load_1d(tile, vsrc + base, (uint32_t)TSIZE * 16u, &mbar[0]);
+        unsigned long long em = (a.dbg & 2) ? 0ULL : g.extra_mask;
+        for (int e = 0; e < 2 && em; ++e, em &= em - 1) {
+            const int p = __ffsll((long long)em) - 1;
+            mbar_arrive_expect_tx(&mbar[1 + e], (uint32_t)TSIZE * 16u);
+            tma_load_1d(ring + (size_t)e * TSIZE, vsrc + (base ^ (1LL << p)), (uint32_t)TSIZE * 16u, &mbar[1 + e]);
+        }
+    }
+    mbar_wait(&mbar[0], 0);
+    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid, ring, &mbar[1]);
 }
 
 // ---- d = 2 tiled stage kernel, persistent with a TMA prefetch pipeline -----------

@@ -96,6 +96,7 @@ struct Plan {
     bool use_pipe = false;
     bool use_dual = true;
     bool use_coop = true;
+    bool use_stream = false;
     bool coop_now = false;                 // decided per propagate call
     std::vector<PassGeom> coop_passes;
     CoopStage* d_coop = nullptr; size_t d_coop_cap = 0;
@@ -271,6 +272,19 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
                     if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_PIPE(11, 3, 3); else PB200_LAUNCH_PIPE(11, 2, 3); }
                     else { if (RBv == 3) PB200_LAUNCH_PIPE(12, 3, 2); else PB200_LAUNCH_PIPE(12, 2, 2); }
 #undef PB200_LAUNCH_PIPE
+                    ++launches;
+                } else if (P.use_stream && tbits == 11 && RBv == 3 && geo.hi_bits == 0 && geo.extra_mask != 0) {
+                    StageArgs2 m{};
+                    for (int c = 0; c < n; ++c) m.a[c] = make_stage_args(P, geo, io[c], last_pass);
+                    m.n_traj = P.B;
+                    dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
+                    const size_t smem = (size_t)3 * tsize * 16 + tab_bytes;
+                    if (uniform) {
+                        if (real_g) launch_k(stage_d2_stream_kernel<true, true, 11, 3>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);
+                        else launch_k(stage_d2_stream_kernel<true, false, 11, 3>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);
+                    } else {
+                        launch_k(stage_d2_stream_kernel<false, false, 11, 3>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);
+                    }
                     ++launches;
                 } else {
                     StageArgs2 m{};
@@ -1451,6 +1465,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_coop = env_int("PB200_COOP", 0) != 0;  // experiment: slower than per-stage launches
     P.dbg = env_int("PB200_DBG", 0);
+    P.use_stream = env_int("PB200_STREAM", 0) != 0;
     P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
     P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
@@ -1491,6 +1506,9 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
     } catch (...) {
         pb200_plan_destroy(h);
         throw;
