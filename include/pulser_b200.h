@@ -156,6 +156,22 @@ int pb200_plan_set_drive(pb200_plan* plan, int32_t drive, int32_t traj0,
 int pb200_plan_set_dissipator(pb200_plan* plan, int32_t n_pairs,
                               const double* generators);
 
+/* Monte-Carlo wave function (replaces qutip.mcsolve(H, psi0, tlist, c_ops, ntraj),
+ * simulation.py:710-735) for registers whose density matrix does not fit:
+ * `ops` = n_ops single-qudit collapse matrices (d x d, row-major, interleaved
+ * complex, coefficient included), each acting on every qudit
+ * (hamiltonian.py:97-124).  Every L^+L must be diagonal (dephasing, relaxation,
+ * depolarizing and transition/projector-type effective noise).  Afterwards
+ * pb200_propagate evolves every trajectory under
+ * H_eff = H - i/2 sum L^+L (symmetric splitting around the unitary step), and
+ * applies a quantum jump whenever a trajectory's squared norm falls below its
+ * random threshold (jump channel drawn from the <L^+L> weights; time resolution
+ * = one step); states are renormalised at the end of the call. */
+int pb200_plan_set_collapse(pb200_plan* plan, int32_t n_ops, const double* ops,
+                            uint64_t seed);
+/* number of quantum jumps applied so far, jumps[n_traj] */
+int pb200_plan_jump_counts(pb200_plan* plan, int64_t* jumps);
+
 /* ---- state --------------------------------------------------------------- */
 /* Upload initial states psi[count][D] (interleaved complex); psi == NULL sets
  * basis state `basis_index` (e.g. all-ground, simulation.py:498-505) for the

@@ -1126,6 +1126,54 @@ __global__ void krylov_combine_kernel(c2* out, const c2* V, long long vstride, l
     }
 }
 
+// ---- Monte-Carlo wave function: non-Hermitian decay and quantum jumps ---------------------------------------------
+// psi[s] *= exp(-h/2 * sum_k gamma[digit_k(s)])  -- the diagonal part -i/2 sum L^+L of H_eff
+struct DecayTable { double gamma[4]; };
+__global__ void mcwf_decay_kernel(c2* psi, long long D, int n, int dim, double half_h, const __grid_constant__ DecayTable tb) {
+    const long long traj = blockIdx.y;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < D;
+         s += (long long)gridDim.x * blockDim.x) {
+        long long rem = s;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) { acc += tb.gamma[(int)(rem % dim)]; rem /= dim; }
+        const double f = exp(-half_h * acc);
+        c2 v = psi[traj * D + s];
+        v.x *= f; v.y *= f;
+        psi[traj * D + s] = v;
+    }
+}
+
+// psi <- scale * (L on qudit with stride `st`) psi for one trajectory; L row-major d x d
+struct QuditOp { c2 m[16]; };
+__global__ void qudit_op_kernel(c2* psi, long long D, int dim, long long st, double scale, const __grid_constant__ QuditOp op) {
+    const long long groups = D / dim;
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < groups;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        const long long low = gidx % st, high = gidx / st;
+        const long long idx0 = low + high * st * dim;
+        c2 v[4], w[4];
+        for (int a = 0; a < dim; ++a) v[a] = psi[idx0 + a * st];
+        for (int r = 0; r < dim; ++r) {
+            double xr = 0.0, xi = 0.0;
+            for (int c = 0; c < dim; ++c) {
+                const c2 mm = op.m[r * dim + c];
+                xr = fma(mm.x, v[c].x, xr); xr = fma(-mm.y, v[c].y, xr);
+                xi = fma(mm.x, v[c].y, xi); xi = fma(mm.y, v[c].x, xi);
+            }
+            w[r] = {xr * scale, xi * scale};
+        }
+        for (int a = 0; a < dim; ++a) psi[idx0 + a * st] = w[a];
+    }
+}
+
+__global__ void scale_kernel(c2* psi, long long D, double scale) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        c2 v = psi[i];
+        psi[i] = {v.x * scale, v.y * scale};
+    }
+}
+
 // y = alpha*y + beta*x (Richardson combination of the step-doubling pair)
 __global__ void axpby_kernel(c2* y, const c2* x, double alpha, double beta, long long total) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;

@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "spline.hpp"
 #include <cub/device/device_scan.cuh>
+#include <random>
 
 namespace pb200 {
 
@@ -114,6 +115,13 @@ struct Plan {
     bool use_krylov = false;
     long long kry_iters = 0;
     bool has_diss = false;
+    // Monte-Carlo wave function: single-qudit collapse operators (L^+L diagonal), thresholds, RNG
+    std::vector<std::vector<cplx>> jump_ops;      // [n_ops][d*d]
+    std::vector<std::vector<double>> jump_ldl;    // [n_ops][d]: diagonal of L^+L
+    bool has_collapse = false;
+    std::mt19937_64 rng;
+    std::vector<double> thresholds;               // per trajectory
+    std::vector<long long> jump_count;
     bool use_pdl = true;
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
@@ -1042,6 +1050,123 @@ static void ensure_aux_buffers(Plan& P) {
         if (!P.aux[i]) CUDA_CHECK(cudaMalloc(&P.aux[i], sizeof(c2) * (size_t)P.D * P.B));
 }
 
+// ---- Monte-Carlo wave-function propagation (collapse operators without a density matrix) ------------------------
+static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats) {
+    const double eps = 1e-12;
+    const int nt = (int)P.times.size();
+    pb200_run_stats st{};
+    P.use_krylov = false; P.coop_now = false;
+    const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
+    std::vector<char> jump; std::vector<int> dist;
+    const std::vector<char> fine = fine_intervals(P, 8, 1e-4, 0.05, jump, dist);
+    (void)fine;
+    const int K = (o && o->max_step_samples > 0) ? o->max_step_samples : 1;
+    DecayTable dt{};
+    for (int dgt = 0; dgt < P.dim; ++dgt) {
+        double g = 0.0;
+        for (const auto& l : P.jump_ldl) g += l[dgt];
+        dt.gamma[dgt] = g;
+    }
+    const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
+    dim3 bgrid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
+    cudaEvent_t ev0, ev1;
+    CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
+    CUDA_CHECK(cudaEventRecord(ev0, P.stream));
+    std::vector<double> norms(P.B), occ((size_t)P.dim * P.n);
+    double* d_occ = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_occ, sizeof(double) * P.n));
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    auto norms2 = [&]() {
+        CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * P.B, P.stream));
+        const long long nb = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
+        dim3 grid((unsigned)std::max<long long>(nb, 1), (unsigned)P.B);
+        norm2_kernel<<<grid, 256, 0, P.stream>>>(P.buf[P.cur], P.D, P.d_scratch);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(norms.data(), P.d_scratch, sizeof(double) * P.B, cudaMemcpyDeviceToHost, P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        st.n_launches += 1;
+    };
+    double t = t_start;
+    while (t < t_stop - eps) {
+        const int i = find_piece(P.times, t + eps);
+        const double hi_i = P.times[i + 1] - P.times[i];
+        double b = P.times[std::min(i + K, nt - 1)];
+        if (jump[i]) {
+            const int nsub = jump_substeps(P, t, std::min(P.times[i + 1], t_stop), 1e-9);
+            b = std::min(P.times[i + 1], t + hi_i / nsub);
+        }
+        b = std::min(b, t_stop);
+        const double h = b - t;
+        // exp(-i H_eff h) ~ decay(h/2) U(h) decay(h/2)
+        mcwf_decay_kernel<<<bgrid, 256, 0, P.stream>>>(P.buf[P.cur], P.D, P.n, P.dim, 0.25 * h, dt);
+        Program prog;
+        add_step(P, prog, t, b, 4, 1e-11);
+        run_program(P, prog, passes, st);
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        mcwf_decay_kernel<<<bgrid, 256, 0, P.stream>>>(P.buf[P.cur], P.D, P.n, P.dim, 0.25 * h, dt);
+        CUDA_CHECK(cudaGetLastError());
+        st.n_launches += 2; ++st.n_steps;
+        // quantum jumps
+        norms2();
+        for (int tr = 0; tr < P.B; ++tr) {
+            if (norms[tr] > P.thresholds[tr]) continue;
+            c2* psi = P.buf[P.cur] + (size_t)tr * P.D;
+            // populations of every digit on every qudit
+            for (int dgt = 0; dgt < P.dim; ++dgt) {
+                CUDA_CHECK(cudaMemsetAsync(d_occ, 0, sizeof(double) * P.n, P.stream));
+                const long long nb = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
+                occupation_kernel<<<(unsigned)std::max<long long>(nb, 1), 256, sizeof(double) * P.n, P.stream>>>(
+                    psi, d_occ, P.D, P.n, P.dim, dgt);
+                CUDA_CHECK(cudaMemcpyAsync(occ.data() + (size_t)dgt * P.n, d_occ, sizeof(double) * P.n, cudaMemcpyDeviceToHost, P.stream));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(P.stream));
+            // channel (op, qudit) with probability <L^+L>
+            std::vector<double> wts(P.jump_ops.size() * (size_t)P.n);
+            double tot = 0.0;
+            for (size_t op = 0; op < P.jump_ops.size(); ++op)
+                for (int k = 0; k < P.n; ++k) {
+                    double wv = 0.0;
+                    for (int dgt = 0; dgt < P.dim; ++dgt) wv += P.jump_ldl[op][dgt] * occ[(size_t)dgt * P.n + k];
+                    wts[op * P.n + k] = wv; tot += wv;
+                }
+            if (tot <= 0.0) { P.thresholds[tr] = uni(P.rng); continue; }
+            double x = uni(P.rng) * tot; size_t sel = 0;
+            for (; sel + 1 < wts.size(); ++sel) { x -= wts[sel]; if (x <= 0.0) break; }
+            const size_t op = sel / P.n; const int k = (int)(sel % P.n);
+            QuditOp qo{};
+            for (int q = 0; q < P.dim * P.dim; ++q) qo.m[q] = {P.jump_ops[op][q].real(), P.jump_ops[op][q].imag()};
+            long long stq = 1;
+            for (int q = 0; q < P.n - 1 - k; ++q) stq *= P.dim;
+            const double scale = 1.0 / std::sqrt(std::max(wts[sel], 1e-300));  // psi <- L psi / ||L psi||
+            const long long nb = std::min<long long>((P.D / P.dim + 255) / 256, (long long)P.sm_count * 8);
+            qudit_op_kernel<<<(unsigned)std::max<long long>(nb, 1), 256, 0, P.stream>>>(psi, P.D, P.dim, stq, scale, qo);
+            CUDA_CHECK(cudaGetLastError());
+            st.n_launches += 1 + P.dim;
+            P.thresholds[tr] = uni(P.rng);
+            P.jump_count[tr] += 1;
+        }
+        t = b;
+    }
+    // renormalise for the caller (mcsolve returns normalised states); thresholds are kept relative to norm 1
+    norms2();
+    for (int tr = 0; tr < P.B; ++tr) {
+        if (norms[tr] <= 0.0) continue;
+        const double sc = 1.0 / std::sqrt(norms[tr]);
+        scale_kernel<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, P.stream>>>(P.buf[P.cur] + (size_t)tr * P.D, P.D, sc);
+        P.thresholds[tr] /= norms[tr];  // the same decay continues from the rescaled state
+        P.thresholds[tr] = std::min(P.thresholds[tr], 1.0);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    cudaFree(d_occ);
+    CUDA_CHECK(cudaEventRecord(ev1, P.stream));
+    CUDA_CHECK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    st.gpu_ms = ms; st.integrator = 1; st.mean_step_samples = K;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (stats) *stats = st;
+}
+
 static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats) {
     if (!P.state_set) fail(PB200_ERR_STATE, "pb200_propagate: no state set (call pb200_state_set first)");
     for (int tr = 0; tr < P.B; ++tr)
@@ -1052,6 +1177,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
+    if (P.has_collapse) { propagate_mcwf(P, t_start, t_stop, o, stats); return; }
     const double gtol = (o && o->tol != 0.0) ? o->tol : (P.has_diss ? 1e-6 : 1e-8);
     // Richardson extrapolation: on by default (extrapolate = 0 or 1), -1 switches it off
     const bool extrap = !(o && o->extrapolate < 0);
@@ -1656,6 +1782,44 @@ int pb200_plan_set_dissipator(pb200_plan* h, int32_t n_pairs, const double* gene
             P.diss_gen[k][i] = z;
         }
     P.has_diss = true;
+    PB200_CATCH
+}
+
+int pb200_plan_set_collapse(pb200_plan* h, int32_t n_ops, const double* ops, uint64_t seed) {
+    PB200_TRY
+    if (!h || !ops || n_ops < 1) fail(PB200_ERR_INVALID, "bad argument");
+    Plan& P = h->p;
+    if (P.has_diss) fail(PB200_ERR_STATE, "plan already carries a dissipator (density-matrix mode)");
+    const int d = P.dim;
+    P.jump_ops.assign(n_ops, std::vector<cplx>((size_t)d * d));
+    P.jump_ldl.assign(n_ops, std::vector<double>(d, 0.0));
+    const cplx* src = reinterpret_cast<const cplx*>(ops);
+    for (int op = 0; op < n_ops; ++op) {
+        for (int q = 0; q < d * d; ++q) P.jump_ops[op][q] = src[(size_t)op * d * d + q];
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) {
+                cplx acc = 0.0;  // (L^+ L)[a][b] = sum_c conj(L[c][a]) L[c][b]
+                for (int c = 0; c < d; ++c) acc += std::conj(P.jump_ops[op][c * d + a]) * P.jump_ops[op][c * d + b];
+                if (a == b) P.jump_ldl[op][a] = acc.real();
+                else if (std::abs(acc) > 1e-12)
+                    fail(PB200_ERR_UNSUPPORTED, "collapse operator %d: L^+L is not diagonal (wave-function Monte Carlo "
+                         "supports dephasing, relaxation, depolarizing and projector/transition-type operators)", op);
+            }
+    }
+    P.rng.seed(seed);
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    P.thresholds.resize(P.B);
+    for (double& r : P.thresholds) r = uni(P.rng);
+    P.jump_count.assign(P.B, 0);
+    P.has_collapse = true;
+    PB200_CATCH
+}
+
+int pb200_plan_jump_counts(pb200_plan* h, int64_t* jumps) {
+    PB200_TRY
+    if (!h || !jumps) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    for (int i = 0; i < P.B; ++i) jumps[i] = P.has_collapse ? (int64_t)P.jump_count[i] : 0;
     PB200_CATCH
 }
 

@@ -367,19 +367,24 @@ class B200Emulator:
     def _has_collapse_ops(self) -> bool:
         return len(self._hamiltonian_data.lindblad_data.local_collapse_ops) > 0
 
+    def _density_matrix_fits(self) -> bool:
+        hd = self._hamiltonian_data
+        return hd.basis_data.dim <= 3 and hd.basis_data.dim ** (2 * hd.n_qudits) <= (1 << 26)
+
+    def _use_mcwf(self) -> bool:
+        return self._has_collapse_ops() and not self._density_matrix_fits()
+
     def _check_supported(self) -> None:
         """Collapse operators run as a master equation on the vectorised density
         matrix (``pulser_b200/lindblad.py``): deterministic where the reference uses
         ``mesolve`` and, for ``mcsolve`` requests, the exact ensemble average that the
         Monte-Carlo trajectories estimate (``simulation.py:705-718``)."""
-        if self._has_collapse_ops():
-            hd = self._hamiltonian_data
-            size = hd.basis_data.dim ** (2 * hd.n_qudits)
-            if hd.basis_data.dim > 3 or size > (1 << 26):
-                raise NotImplementedError(
-                    "Collapse operators: the density-matrix path holds dim^(2N) <= 2^26 "
-                    "amplitudes and d <= 3; wave-function Monte Carlo for larger registers "
-                    "is not on the CUDA path yet."
+        if self._has_collapse_ops() and not self._density_matrix_fits():
+            # wave-function Monte Carlo (pb200_plan_set_collapse): needs a trajectory count
+            if self.n_trajectories is None:
+                raise ValueError(
+                    "'n_trajectories' must be defined to emulate collapse operators on a register "
+                    "whose density matrix does not fit on the device (Monte-Carlo wave function)."
                 )
 
     def _validate_options(self, options: dict) -> dict:
@@ -464,14 +469,14 @@ class B200Emulator:
             raise ValueError("`progress_bar` must be a bool.")
         opts = self._validate_options(options)
         self._check_supported()
-        if not _has_stochastic_noise(self.noise_model):
+        if not _has_stochastic_noise(self.noise_model) and not self._use_mcwf():
             if print_progress:
                 print("Emulating Trajectory 1/1")
             states = self._run_batch([self._current_spec], opts)
             return self._wrap([s[0] for s in states])
 
         total_count = np.array([Counter() for _ in self._eval_times_array])
-        if self._has_collapse_ops():
+        if self._has_collapse_ops() and not self._use_mcwf():
             for cleanres, reps in self._noisy_runs(
                 print_progress=print_progress, batch=int(options.get("b200_batch", 0)), opts=opts
             ):
@@ -516,6 +521,12 @@ class B200Emulator:
             )
         self._noise_trajectories_used = True
         pending = list(self._specs)
+        if self._use_mcwf():
+            # every Monte-Carlo trajectory is its own random realisation: no merging by `reps`
+            if not _has_stochastic_noise(self.noise_model):
+                pending = [(pending[0][0], 1)] * int(self.n_trajectories)
+            else:
+                pending = [(s, 1) for s, reps in pending for _ in range(reps)]
         from . import parallel
 
         if parallel.world_size() > 1:  # trajectory j -> rank j mod world (same seed on every rank)
@@ -573,6 +584,8 @@ class B200Emulator:
                         print("Emulating Trajectories " f"[{traj_nb+1} - {traj_nb+reps}]/{n_trajectories}")
                     traj_nb += reps
             with engine.DevicePlan([s for s, _ in chunk], self._interp_order, self._gpu) as plan:
+                if self._use_mcwf():
+                    plan.set_collapse(chunk[0][0].collapse_ops, seed=int(np.random.randint(0, 2**31 - 1)))
                 plan.set_state(self._initial_state.full().reshape(-1))
                 sample_all(plan, chunk, 0)
                 for k, (t0, t1) in enumerate(zip(times[:-1], times[1:])):

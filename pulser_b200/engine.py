@@ -151,6 +151,17 @@ class DevicePlan:
     def __exit__(self, *exc) -> None:
         self.close()
 
+    def set_collapse(self, ops: np.ndarray, seed: int = 0) -> None:
+        """Switch the plan to wave-function Monte Carlo with single-qudit collapse
+        operators ``ops[n_ops, d, d]`` acting on every qudit (``pb200_plan_set_collapse``)."""
+        ops = np.ascontiguousarray(ops, dtype=np.complex128)
+        check(lib.pb200_plan_set_collapse(self._handle, ops.shape[0], _p(ops.view(np.float64)), C.c_uint64(seed)))
+
+    def jump_counts(self) -> np.ndarray:
+        out = np.zeros(self.n_traj, dtype=np.int64)
+        check(lib.pb200_plan_jump_counts(self._handle, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     def set_stream(self, cuda_stream: int) -> None:
         check(lib.pb200_plan_set_stream(self._handle, C.c_void_p(cuda_stream)))
 

@@ -353,3 +353,40 @@ def test_device_sampling_equals_reference_recipe(engine):
         probs = (np.abs(psi) ** 2).reshape([d] * n)
         ref_occ = [np.take(probs, spec.eigenbasis.index(one), axis=k).sum() for k in range(n)]
         np.testing.assert_allclose(occ, ref_occ, atol=1e-12)
+
+
+def test_mcwf_average_matches_master_equation(engine):
+    """Quantum-jump trajectories (mcsolve replacement): the ensemble average of the populations agrees with
+    the Lindblad oracle within the statistical error of 3000 trajectories."""
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    ops = [np.sqrt(2 * 1.5) * np.array([[1, 0], [0, 0]]), np.sqrt(2.0) * np.array([[0, 0], [1, 0]])]
+    spec = _lindblad_spec(2, 300, ops)
+    tf = spec.sampling_times[-1]
+    psi0 = evolve.all_ground_state(spec)
+    rho = evolve.mesolve(OracleHamiltonian.from_spec(spec), psi0, [0.0, tf])[-1]
+    ref = np.real(np.diag(rho))
+    B = 3000
+    with engine.DevicePlan([spec] * B) as plan:
+        plan.set_collapse(np.asarray(ops, dtype=complex), seed=12345)
+        plan.set_state("all-ground")
+        plan.propagate(0.0, 0.5 * tf)   # thresholds persist across calls
+        plan.propagate(0.5 * tf, tf)
+        probs = plan.probabilities()
+        jumps = plan.jump_counts()
+        n2 = plan.norm2()
+    np.testing.assert_allclose(n2, 1.0, atol=1e-9)
+    assert jumps.sum() > B // 20
+    mean = probs.mean(axis=0)
+    sigma = np.sqrt(np.maximum(ref * (1 - ref), 1e-4) / B)
+    assert np.all(np.abs(mean - ref) < 5 * sigma + 2e-3)
+
+
+def test_mcwf_rejects_non_diagonal_ldl(engine):
+    from pulser_b200._lib import PB200Error
+
+    spec = _lindblad_spec(2, 100, [np.eye(2)])
+    with engine.DevicePlan(spec) as plan:
+        with pytest.raises(PB200Error, match="not diagonal"):
+            plan.set_collapse(np.array([[[1, 1], [0, 1]]], dtype=complex))
