@@ -145,3 +145,20 @@ def test_collapse_operators_use_master_equation(emu):
     np.testing.assert_allclose(w, np.abs(rho.diag())[::-1] / np.sum(np.abs(rho.diag())))
     r_proj = np.diag([1.0, 0.0])
     assert 0 < res.expect([r_proj])[0][-1] < 1
+
+
+def test_large_register_collapse_needs_trajectories(emu):
+    """Density matrix of 14 qubits does not fit: wave-function Monte Carlo is used and asks for n_trajectories."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    reg = Register.from_coordinates([(8.0 * (i % 7), 8.0 * (i // 7)) for i in range(14)], prefix="q")
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch", "rydberg_global")
+    seq.add(Pulse.ConstantPulse(100, 1.0, 0.0, 0), "ch")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(dephasing_rate=0.1), evaluation_times="Minimal")
+    assert sim._use_mcwf() and not sim._density_matrix_fits()
+    with pytest.raises(ValueError, match="'n_trajectories' must be defined"):
+        sim.run()
