@@ -133,6 +133,16 @@ int pb200_plan_set_interaction(pb200_plan* plan, int32_t traj0, int32_t count,
                                const double* U, const uint8_t* bad,
                                int32_t shared);
 
+/* XY mode (microwave channel, eigenbasis u, d): exchange couplings
+ * Uxy[count][N][N] of  Uxy_ij (|u d><d u| + h.c.)  (make_xy_term,
+ * hamiltonian.py:276-294; interaction_matrix[0] in XY mode).  The |uu><uu| term
+ * of the same function goes through pb200_plan_set_interaction with
+ * rydberg_state = digit of |u>.  The SLM-mask time dependence (:399-424) is not
+ * supported.  shared != 0: one matrix for all trajectories. */
+int pb200_plan_set_xy(pb200_plan* plan, int32_t traj0, int32_t count,
+                      const double* Uxy, const uint8_t* bad, int32_t shared,
+                      int32_t digit_u, int32_t digit_d);
+
 /* Sample tables of drive `drive` for trajectories [traj0, traj0+count):
  *   coef[count][rows][n_times][2]  = 0.5*amp*exp(-i*phase)   (re, im)
  *   det [count][rows][n_times]     = detuning (enters H as -det |from><from|)

@@ -31,8 +31,11 @@ class MatFreeHamiltonian:
             [(idx // d ** (n - 1 - k)) % d for k in range(n)], dtype=np.int8
         )
         self.dint = np.zeros(D)
+        self.xy = None
+        if spec.has_interaction() and spec.interaction_type == "XY":
+            self.xy = (spec.xy_matrix(), spec.eigenbasis.index("u"), spec.eigenbasis.index("d"))
         if spec.has_interaction():
-            r = spec.eigenbasis.index("r")
+            r = spec.eigenbasis.index("u" if spec.interaction_type == "XY" else "r")
             U = spec.pair_matrix()
             nr = (self.digits == r).astype(float)
             for i in range(n):
@@ -69,4 +72,17 @@ class MatFreeHamiltonian:
                 # c |to><from| + conj(c) |from><to| - det |from><from|
                 ot[s_to] += c[k] * pt[s_fr]
                 ot[s_fr] += np.conj(c[k]) * pt[s_to] - dt[k] * pt[s_fr]
+        if self.xy is not None:  # U_xy (|u d><d u| + h.c.) on every pair
+            U, iu, idn = self.xy
+            for i in range(n):
+                for j in range(i + 1, n):
+                    if U[i, j] == 0.0:
+                        continue
+                    a = [slice(None)] * n
+                    b = [slice(None)] * n
+                    a[i], a[j] = iu, idn
+                    b[i], b[j] = idn, iu
+                    a, b = tuple(a), tuple(b)
+                    ot[a] += U[i, j] * pt[b]
+                    ot[b] += U[i, j] * pt[a]
         return out

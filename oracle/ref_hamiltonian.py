@@ -112,18 +112,25 @@ class OracleHamiltonian:
         bad = np.asarray(spec.bad_atoms, dtype=bool)
         effective_size = n - int(bad.sum())
         if "digital" not in spec.basis_name and effective_size > 1:
-            if spec.interaction_type == "XY":
-                raise NotImplementedError("XY interaction: oracle TODO")
+            if spec.interaction_type == "XY" and spec.slm_end > 0:
+                raise NotImplementedError("XY interaction with an SLM mask: oracle TODO")
             inter = sp.csr_matrix(
                 (spec.dim**n, spec.dim**n), dtype=complex
             )
             for q1, q2 in itertools.combinations(range(n), 2):
                 if bad[q1] or bad[q2]:
                     continue
-                u = 0.5 * spec.interaction_matrix[-1, q1, q2]
-                inter = inter + u * build_operator(
-                    n, ops, [("sigma_rr", [q1, q2])]
-                )
+                if spec.interaction_type == "XY":  # make_xy_term, hamiltonian.py:276-294
+                    u_xy = spec.interaction_matrix[0, q1, q2]
+                    u_ryd = spec.interaction_matrix[1, q1, q2]
+                    inter = inter + u_xy * build_operator(
+                        n, ops, [("sigma_ud", [q1]), ("sigma_du", [q2])]
+                    ) + 0.5 * u_ryd * build_operator(n, ops, [("sigma_uu", [q1, q2])])
+                else:  # make_vdw_term, hamiltonian.py:260-274
+                    u = 0.5 * spec.interaction_matrix[-1, q1, q2]
+                    inter = inter + u * build_operator(
+                        n, ops, [("sigma_rr", [q1, q2])]
+                    )
             qobj_list.append((sp.csr_matrix(inter), None))
         for drv in spec.drives:
             op_ids = _OP_IDS[drv.basis]
@@ -194,16 +201,21 @@ class OracleHamiltonian:
         effective_size = n - sum(bad.values())
         imat = noise_trajectory.interaction_matrix.as_array(detach=True)
         if "digital" not in basis_data.basis_name and effective_size > 1:
-            if basis_data.interaction_type == "XY":
-                raise NotImplementedError("XY interaction: oracle TODO")
+            if basis_data.interaction_type == "XY" and samples._slm_mask.end > 0:
+                raise NotImplementedError("XY interaction with an SLM mask: oracle TODO")
             inter = sp.csr_matrix((d**n, d**n), dtype=complex)
             for q1, q2 in itertools.combinations(qids, 2):
                 if bad[q1] or bad[q2]:
                     continue
-                u = 0.5 * imat[-1, qidx[q1], qidx[q2]]
-                inter = inter + u * build_operator(
-                    n, ops, [("sigma_rr", [qidx[q1], qidx[q2]])]
-                )
+                i1, i2 = qidx[q1], qidx[q2]
+                if basis_data.interaction_type == "XY":
+                    inter = inter + imat[0, i1, i2] * build_operator(
+                        n, ops, [("sigma_ud", [i1]), ("sigma_du", [i2])]
+                    ) + 0.5 * imat[1, i1, i2] * build_operator(n, ops, [("sigma_uu", [i1, i2])])
+                else:
+                    inter = inter + 0.5 * imat[-1, i1, i2] * build_operator(
+                        n, ops, [("sigma_rr", [i1, i2])]
+                    )
             qobj_list.append((sp.csr_matrix(inter), None))
         nested = samples.to_nested_dict()
         for addr in nested:

@@ -91,6 +91,8 @@ def _load() -> C.CDLL:
         "pb200_plan_set_stream": (C.c_int, [vp, vp]),
         "pb200_plan_set_interaction": (
             C.c_int, [vp, C.c_int32, C.c_int32, dp, C.POINTER(C.c_uint8), C.c_int32]),
+        "pb200_plan_set_xy": (
+            C.c_int, [vp, C.c_int32, C.c_int32, dp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32]),
         "pb200_plan_set_drive": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, dp, dp]),
         "pb200_plan_set_dissipator": (C.c_int, [vp, C.c_int32, dp]),
         "pb200_plan_set_collapse": (C.c_int, [vp, C.c_int32, dp, C.c_uint64]),
@@ -127,7 +129,7 @@ def _load() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "pb200_version", "pb200_last_error", "pb200_device_count",
     "pb200_plan_create", "pb200_plan_destroy", "pb200_plan_set_stream",
-    "pb200_plan_set_interaction", "pb200_plan_set_drive", "pb200_plan_set_dissipator", "pb200_plan_set_collapse",
+    "pb200_plan_set_interaction", "pb200_plan_set_xy", "pb200_plan_set_drive", "pb200_plan_set_dissipator", "pb200_plan_set_collapse",
     "pb200_plan_jump_counts", "pb200_state_set",
     "pb200_state_get", "pb200_state_probabilities", "pb200_state_norm2",
     "pb200_state_occupation", "pb200_state_sample", "pb200_state_device_ptr", "pb200_propagate", "pb200_apply_h",

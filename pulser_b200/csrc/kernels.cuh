@@ -814,6 +814,8 @@ struct GenArgs {
     StageCoef coef;
     const double* table;  // [B][stride]
     const double* beta_dev;
+    // XY mode: exchange couplings U^xy_ij (|u d><d u| + h.c.), [Bx][n*n], weighted by the table's w like Dint
+    const double* xy; long long xy_stride; int xy_u, xy_d;
 };
 
 __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
@@ -823,6 +825,12 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
     const long long traj = blockIdx.y;
     for (int i = threadIdx.x; i < stride; i += blockDim.x) tab[i] = a.table[traj * stride + i];
     __syncthreads();
+    double* xys = tab + stride;  // XY couplings of this trajectory, weighted like Dint
+    if (a.xy) {
+        const double wx = tab[stride - 2];
+        for (int i = threadIdx.x; i < a.n * a.n; i += blockDim.x) xys[i] = a.xy[traj * a.xy_stride + i] * wx;
+        __syncthreads();
+    }
     const double w = tab[stride - 2], gamma = tab[stride - 1];
     const long long voff = traj * a.D;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < a.D;
@@ -851,6 +859,24 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
                 }
             }
             st *= a.dim;
+        }
+        if (a.xy) {  // flip-flop partners: every pair (i, j) holding (u, d) or (d, u)  (make_xy_term, :276-294)
+            signed char dg[40];
+            long long sts[40];
+            long long r2 = idx, s2 = 1;
+            for (int k = a.n - 1; k >= 0; --k) { dg[k] = (signed char)(r2 % a.dim); r2 /= a.dim; sts[k] = s2; s2 *= a.dim; }
+            for (int i = 0; i < a.n; ++i) {
+                if (dg[i] != a.xy_u && dg[i] != a.xy_d) continue;
+                for (int j = i + 1; j < a.n; ++j) {
+                    if ((dg[i] == a.xy_u && dg[j] == a.xy_d) || (dg[i] == a.xy_d && dg[j] == a.xy_u)) {
+                        const double u = xys[i * a.n + j];
+                        if (u == 0.0) continue;
+                        const long long pidx2 = idx + (long long)(dg[j] - dg[i]) * sts[i] + (long long)(dg[i] - dg[j]) * sts[j];
+                        const c2 pv = a.v[voff + pidx2];
+                        rr = fma(u, pv.x, rr); ri = fma(u, pv.y, ri);
+                    }
+                }
+            }
         }
         c2 gv = {fma(diag, vo.x, rr), fma(diag, vo.y, ri)};
         c2 res = cmul(a.coef.c_g, gv);

@@ -119,6 +119,9 @@ struct Plan {
     std::vector<std::vector<cplx>> jump_ops;      // [n_ops][d*d]
     std::vector<std::vector<double>> jump_ldl;    // [n_ops][d]: diagonal of L^+L
     bool has_collapse = false;
+    // XY mode: exchange couplings on the device, their absolute row sums (spectral bound)
+    double* d_xy = nullptr; bool xy_shared = true; bool has_xy = false; int xy_u = 0, xy_d = 1;
+    std::vector<double> xy_norm;  // per trajectory: sum_{i<j} |Uxy_ij|
     std::mt19937_64 rng;
     std::vector<double> thresholds;               // per trajectory
     std::vector<long long> jump_count;
@@ -200,6 +203,8 @@ struct ExpParams {  // one exponential exp(-i G), G from Magnus moments
     double w = 0.0;
 };
 
+static inline bool is_d2path(const Plan& P) { return P.dim == 2 && P.n_drives == 1 && !P.has_xy; }
+
 static inline size_t pidx(const Plan& P, int traj, int q, int row) {
     return ((size_t)traj * P.n_drives + q) * P.n + row;
 }
@@ -237,7 +242,7 @@ static bool rb_eligible(const Plan& P, const PassGeom& geo) {
 
 // every pass of the geometry can carry two chains in one launch
 static bool dual_chain_ok(const Plan& P, const std::vector<PassGeom>& passes) {
-    if (!(P.dim == 2 && P.n_drives == 1) || !P.use_dual) return false;
+    if (!is_d2path(P) || !P.use_dual) return false;
     for (const PassGeom& g : passes)
         if (!rb_eligible(P, g)) return false;
     return (long long)P.B * 2 <= 65535;
@@ -247,7 +252,7 @@ static bool dual_chain_ok(const Plan& P, const std::vector<PassGeom>& passes) {
 static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, const StageIO* io, int n, bool uniform,
                                long long& launches) {
     const int N = P.n;
-    if (P.dim == 2 && P.n_drives == 1) {
+    if (is_d2path(P)) {
         bool real_g = true;
         for (int c = 0; c < n; ++c) real_g = real_g && io[c].real_g;
         for (size_t gi = 0; gi < passes.size(); ++gi) {
@@ -339,10 +344,12 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             a.D = P.D; a.n = N; a.dim = P.dim; a.n_drives = P.n_drives;
             for (int q = 0; q < P.n_drives; ++q) { a.to[q] = P.desc.drives[q].state_to; a.from[q] = P.desc.drives[q].state_from; }
             a.coef = io[c].coef; a.table = io[c].table; a.beta_dev = io[c].beta_dev;
+            a.xy = P.has_xy ? P.d_xy : nullptr; a.xy_stride = P.xy_shared ? 0 : (long long)N * N;
+            a.xy_u = P.xy_u; a.xy_d = P.xy_d;
             int threads = 256;
             long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
             dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
-            size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8;
+            size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8 + (P.has_xy ? (size_t)N * N * 8 : 0);
             stage_generic_kernel<<<grid, threads, smem, P.stream>>>(a);
             ++launches;
         }
@@ -367,6 +374,7 @@ static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, doub
         double dr = 0.0;
         for (int q = 0; q < nd; ++q)
             for (int k = 0; k < N; ++k) dr += std::abs(E.g[pidx(P, b, q, k)]);
+        if (P.has_xy) dr += std::fabs(E.w) * (P.xy_shared ? P.xy_norm[0] : P.xy_norm[b]);  // |flip-flop| <= 1
         double dlo, dhi;
         const bool caseA = P.has_interaction && P.dint_shared && nd == 1 && P.desc.drives[0].uniform &&
                            P.desc.drives[0].state_from == P.desc.rydberg_state && !P.dmin_cnt.empty();
@@ -526,7 +534,7 @@ struct Chain {
 static void apply_dissipator(Plan& P, c2* buf, double h, long long& launches);
 
 static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom>& passes, pb200_run_stats& st) {
-    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool d2path = is_d2path(P);
     const bool uniform = d2path && P.all_uniform() && P.B == 1;
     if (!uniform) {
         size_t total = 0;
@@ -569,7 +577,7 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
 
 // ---- cooperative persistent execution of whole programs ---------------------------------------------------------
 static bool coop_eligible(const Plan& P, const std::vector<PassGeom>& cpasses) {
-    if (!P.use_coop || !(P.dim == 2 && P.n_drives == 1) || P.has_diss || P.use_krylov || P.force_v1) return false;
+    if (!P.use_coop || !is_d2path(P) || P.has_diss || P.use_krylov || P.force_v1) return false;
     if (P.reg_bits != 3 || cpasses.size() > 4) return false;
     if ((double)P.D * P.B * 16.0 > (double)env_int("PB200_COOP_MIB", 72) * 1048576.0) return false;  // L2-resident only
     if (P.n < 14) return false;
@@ -736,7 +744,7 @@ static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const st
     double* d_acc = d_beta + (size_t)M * B;   // [2][B][2]
     double* d_norm = d_acc + (size_t)4 * B;
     double* d_y = d_norm + B;
-    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool d2path = is_d2path(P);
     const bool uniform = d2path && P.all_uniform() && B == 1;
     double gm, rh; std::vector<double> host;
     build_tables(P, E, gm, rh, host, d2path, /*scaled=*/false);
@@ -773,7 +781,7 @@ static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const st
             io.out = P.kry + (size_t)(j + 1) * vstride;
             io.coef = StageCoef{{0, 0}, {0, 0}, {1, 0}};
             io.ud = ud; io.table = uniform ? nullptr : P.d_table; io.real_g = real_g;
-            io.beta_dev = (j > 0) ? d_beta + (size_t)(j - 1) * B : nullptr;
+                    io.beta_dev = (j > 0) ? d_beta + (size_t)(j - 1) * B : nullptr;
             const int p = (j + 1) & 1;
             io.dot_acc = fused_dot ? d_acc + (size_t)p * 2 * B : nullptr;
             launch_stage_multi(P, passes, &io, 1, uniform, launches);
@@ -875,7 +883,7 @@ static void moments_for_step(const Plan& P, double a, double b, std::vector<cplx
 }
 
 static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, double tol) {
-    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool d2path = is_d2path(P);
     double gamma0, rho;
     std::vector<double> host;
     build_tables(P, E, gamma0, rho, host, d2path);
@@ -1032,7 +1040,7 @@ static int jump_substeps(const Plan& P, double a, double b, double magnus_tol) {
     moments_for_step(P, a, b, g0, g1, th0, th1);
     ExpParams E; E.g = g0; E.th = th0; E.w = b - a;
     double gm, rh; std::vector<double> scratch_tab;
-    build_tables(P, E, gm, rh, scratch_tab, P.dim == 2 && P.n_drives == 1);
+    build_tables(P, E, gm, rh, scratch_tab, is_d2path(P));
     double b1 = 0.0;
     for (int tr = 0; tr < P.B; ++tr) {
         double acc = 0.0;
@@ -1256,7 +1264,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             moments_for_step(P, P.times[0], P.times[std::min(1, nt - 1)], q0, q1, r0, r1);
             ExpParams E; E.g = q0; E.th = r0; E.w = P.times[std::min(1, nt - 1)] - P.times[0];
             double gm, rh1; std::vector<double> scratch_tab;
-            build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
+            build_tables(P, E, gm, rh1, scratch_tab, is_d2path(P));
             // ... or when the state no longer fits L2 (fewer, fatter iterations win once HBM-bound)
             kry = rh1 > env_int("PB200_KRYLOV_RHO_MILLI", 900) * 1e-3 ||
                   (double)P.D * P.B * 16.0 > (double)env_int("PB200_KRYLOV_MIB", 96) * 1048576.0;
@@ -1304,7 +1312,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             for (int i = 0; i < 3; ++i) if (P.buf[i] == res) { P.cur = i; found = true; }
             if (!found)
                 for (int i = 0; i < 4; ++i) if (P.aux[i] == res) { std::swap(P.aux[i], P.buf[P.cur]); break; }
-            if (!(P.dim == 2 && P.n_drives == 1 && P.all_uniform() && P.B == 1))
+            if (!(is_d2path(P) && P.all_uniform() && P.B == 1))
                 CUDA_CHECK(cudaStreamSynchronize(P.stream));  // tables of big/half were uploaded from this scope
             return;
         }
@@ -1343,7 +1351,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             moments_for_step(P, t, std::min(P.times[i + 1], t_stop), q0, q1, r0, r1);
             ExpParams E; E.g = q0; E.th = r0; E.w = std::min(P.times[i + 1], t_stop) - t;
             double gm, rh1; std::vector<double> scratch_tab;
-            build_tables(P, E, gm, rh1, scratch_tab, P.dim == 2 && P.n_drives == 1);
+            build_tables(P, E, gm, rh1, scratch_tab, is_d2path(P));
             const double frac = E.w / hi_i;  // fraction of a sampling interval covered by this probe
             const double rho_per_sample = rh1 / std::max(frac, 1e-9);
             Kuse = std::min(Kuse, rho_cap / std::max(rho_per_sample, 1e-12));
@@ -1467,7 +1475,7 @@ static ExpParams params_at(const Plan& P, double t) {
 
 // one plain H-apply: out_buf = H(t) in_buf (device buffers [B][D])
 static void apply_h_device(Plan& P, double t, const c2* in, c2* out, long long& launches) {
-    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool d2path = is_d2path(P);
     const bool uniform = d2path && P.all_uniform() && P.B == 1;
     ExpParams E = params_at(P, t);
     std::vector<double> host;
@@ -1655,6 +1663,7 @@ int pb200_plan_destroy(pb200_plan* h) {
         if (P.aux[i]) cudaFree(P.aux[i]);
     if (P.d_coop) cudaFree(P.d_coop);
     if (P.d_bar) cudaFree(P.d_bar);
+    if (P.d_xy) cudaFree(P.d_xy);
     if (P.kry) cudaFree(P.kry);
     if (P.d_kry) cudaFree(P.d_kry);
     if (P.dint) cudaFree(P.dint);
@@ -1733,6 +1742,48 @@ int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, cons
     }
     CUDA_CHECK(cudaFree(dU));
     P.has_interaction = true;
+    PB200_CATCH
+}
+
+int pb200_plan_set_xy(pb200_plan* h, int32_t traj0, int32_t count, const double* Uxy, const uint8_t* bad, int32_t shared,
+                      int32_t digit_u, int32_t digit_d) {
+    PB200_TRY
+    if (!h || !Uxy) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (shared && (count != 1 || traj0 != 0)) fail(PB200_ERR_INVALID, "shared couplings: traj0 = 0, count = 1");
+    if (!shared && (traj0 < 0 || count < 1 || traj0 + count > P.B)) fail(PB200_ERR_INVALID, "trajectory range");
+    if (digit_u < 0 || digit_u >= P.dim || digit_d < 0 || digit_d >= P.dim || digit_u == digit_d)
+        fail(PB200_ERR_INVALID, "bad eigenstate digits");
+    if (P.n > 40) fail(PB200_ERR_UNSUPPORTED, "XY mode: at most 40 qudits");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    const int N = P.n;
+    const bool want_shared = shared != 0;
+    if (P.d_xy && P.xy_shared != want_shared) { CUDA_CHECK(cudaFree(P.d_xy)); P.d_xy = nullptr; }
+    if (!P.d_xy) {
+        CUDA_CHECK(cudaMalloc(&P.d_xy, sizeof(double) * (size_t)N * N * (want_shared ? 1 : P.B)));
+        CUDA_CHECK(cudaMemsetAsync(P.d_xy, 0, sizeof(double) * (size_t)N * N * (want_shared ? 1 : P.B), P.stream));
+    }
+    P.xy_shared = want_shared;
+    P.xy_norm.resize(want_shared ? 1 : P.B, 0.0);
+    std::vector<double> Uc((size_t)N * N);
+    for (int c = 0; c < count; ++c) {
+        const double* Ui = Uxy + (size_t)c * N * N;
+        const uint8_t* bi = bad ? bad + (size_t)c * N : nullptr;
+        double nrm = 0.0;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                double u = (i < j) ? Ui[i * N + j] : (i > j ? Ui[j * N + i] : 0.0);
+                if (bi && (bi[i] || bi[j])) u = 0.0;
+                Uc[(size_t)i * N + j] = u;
+                if (i < j) nrm += std::fabs(u);
+            }
+        const int slot = want_shared ? 0 : traj0 + c;
+        CUDA_CHECK(cudaMemcpyAsync(P.d_xy + (size_t)slot * N * N, Uc.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, P.stream));
+        CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        P.xy_norm[slot] = nrm;
+    }
+    P.xy_u = digit_u; P.xy_d = digit_d;
+    P.has_xy = true;
     PB200_CATCH
 }
 
@@ -2016,7 +2067,7 @@ int pb200_bench_apply(pb200_plan* h, double t_us, int32_t reps, double* ms_out, 
     long long launches = 0;
     apply_h_device(P, t_us, in, outb, launches);  // warm-up + table upload
     CUDA_CHECK(cudaStreamSynchronize(P.stream));
-    const bool d2path = (P.dim == 2 && P.n_drives == 1);
+    const bool d2path = is_d2path(P);
     const bool uniform = d2path && P.all_uniform() && P.B == 1;
     ExpParams E = params_at(P, t_us);
     UniformDrive ud{};

@@ -11,9 +11,10 @@ reference's own pulser-core code; ``Hamiltonian(...)`` construction
 ``HamiltonianSpec`` -> ``DevicePlan`` -> ``pb200_propagate``.
 
 Collapse operators (``simulation.py:705-735``) run as a master equation on the
-vectorised density matrix (``lindblad.py``, registers with dim^(2N) <= 2^26).
-Not yet on the CUDA path (raise ``NotImplementedError``): wave-function Monte
-Carlo for larger registers and the XY interaction.
+vectorised density matrix (``lindblad.py``, registers with dim^(2N) <= 2^26) and
+as Monte-Carlo wave functions beyond that (``n_trajectories`` set).  XY mode runs
+the coherent and the Monte-Carlo path; not on the CUDA path (raise
+``NotImplementedError``): XY master equation, XY with an SLM mask.
 """
 from __future__ import annotations
 
@@ -369,6 +370,8 @@ class B200Emulator:
 
     def _density_matrix_fits(self) -> bool:
         hd = self._hamiltonian_data
+        if hd.basis_data.interaction_type == "XY":  # exchange term not vectorised: Monte-Carlo path
+            return False
         return hd.basis_data.dim <= 3 and hd.basis_data.dim ** (2 * hd.n_qudits) <= (1 << 26)
 
     def _use_mcwf(self) -> bool:

@@ -47,9 +47,10 @@ class DevicePlan:
             specs = [specs]
         specs = list(specs)
         s0 = specs[0]
-        if s0.interaction_type == "XY":
+        self._xy = s0.interaction_type == "XY"
+        if self._xy and any(s.slm_end > 0 and len(s.slm_targets) for s in specs):
             raise NotImplementedError(
-                "XY (flip-flop) interaction is not on the CUDA path yet"
+                "XY mode with an SLM mask (time-dependent interaction term) is not on the CUDA path"
             )
         for s in specs[1:]:
             if (
@@ -76,7 +77,9 @@ class DevicePlan:
         desc.interp_order = interp_order
         desc.n_drives = len(s0.drives)
         any_inter = any(s.has_interaction() for s in specs)
-        desc.rydberg_state = s0.eigenbasis.index("r") if any_inter else -1
+        # XY mode: the |uu><uu| van der Waals term sits on |u> (hamiltonian.py:276-294)
+        ryd = "u" if self._xy else "r"
+        desc.rydberg_state = s0.eigenbasis.index(ryd) if any_inter else -1
         desc.n_traj = self.n_traj
         desc.device = device
         desc.sampling_times = _p(times)
@@ -112,6 +115,16 @@ class DevicePlan:
                         self._handle, 0, self.n_traj, _p(U), None, 0
                     )
                 )
+        if any_inter and self._xy:
+            mats = [s.xy_matrix() for s in specs]
+            iu, idn = self.spec.eigenbasis.index("u"), self.spec.eigenbasis.index("d")
+            shared = all(np.array_equal(m, mats[0]) for m in mats[1:])
+            U = np.ascontiguousarray(mats[0] if shared else np.stack(mats), dtype=np.float64)
+            check(
+                lib.pb200_plan_set_xy(
+                    self._handle, 0, 1 if shared else self.n_traj, _p(U), None, int(shared), iu, idn
+                )
+            )
         for q, uni in enumerate(self._uniform):
             rows = 1 if uni else n
             # chunk the upload to bound host memory

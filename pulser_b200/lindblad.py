@@ -78,6 +78,8 @@ class LindbladPlan:
         s0 = self.specs[0]
         if s0.dim > 3:
             raise NotImplementedError("Lindblad path: d <= 3")
+        if s0.interaction_type == "XY":
+            raise NotImplementedError("Lindblad path: XY exchange term is not vectorised (use the Monte-Carlo path)")
         if len(s0.collapse_ops) == 0:
             raise ValueError("no collapse operators: use DevicePlan")
         # a non-interacting original must not acquire an interaction through has_interaction()

@@ -105,6 +105,20 @@ class HamiltonianSpec:
             u[:] = 0.0
         return u
 
+    def xy_matrix(self) -> np.ndarray:
+        """XY exchange couplings U^xy_ij (C3 (1 - 3 cos^2) / r^3) with bad atoms removed.
+
+        Reference ``hamiltonian.py:276-294`` (``interaction_matrix[0]`` in XY mode).
+        """
+        n = self.n_qudits
+        u = np.array(self.interaction_matrix[0], dtype=np.float64)
+        good = ~np.asarray(self.bad_atoms, dtype=bool)
+        u = u * good[:, None] * good[None, :]
+        u[np.arange(n), np.arange(n)] = 0.0
+        if not self.has_interaction() or self.interaction_type != "XY":
+            u[:] = 0.0
+        return u
+
     # ------------------------------------------------------------------
     def to_npz_dict(self) -> dict[str, Any]:
         out: dict[str, Any] = dict(

@@ -263,3 +263,46 @@ def config_c3(n: int = 14, seed: int | None = None, t_raman: int = 500, t_ryd: i
         drives=[table("ground-rydberg", amp_ryd), table("digital", amp_dig)],
         collapse_ops=np.zeros((0, 3, 3), dtype=np.complex128), qubit_ids=[f"q{i}" for i in range(n)],
     )
+
+
+# ---------------------------------------------------------------- XY mode (microwave channel)
+C3_XY = 36288.3559282823  # device.interaction_coeff_xy at Rydberg level 70 (MockDevice), rad/us * um^3
+
+
+def xy_interaction_matrix(coords: np.ndarray, c3: float, c6: float, magnetic_field=(0.0, 0.0, 30.0)) -> np.ndarray:
+    """(2, N, N): [0] = C3 (1 - 3 cos^2 theta) / r^3, [1] = C6 / r^6
+    (``HamiltonianData._interaction_matrix``, hamiltonian_data.py:585-611)."""
+    n = len(coords)
+    pts = np.zeros((n, 3))
+    pts[:, : coords.shape[1]] = np.round(np.asarray(coords, dtype=float), 6)
+    mag = np.asarray(magnetic_field, dtype=float)
+    out = np.zeros((2, n, n))
+    out[1] = interaction_matrix(coords, c6)[0]
+    for i in range(n):
+        for j in range(i + 1, n):
+            diff = pts[i] - pts[j]
+            r = np.round(np.linalg.norm(diff), 6)
+            cosine = diff @ mag / (np.linalg.norm(diff) * np.linalg.norm(mag))
+            out[0, i, j] = out[0, j, i] = c3 * (1 - 3 * cosine**2) / r**3
+    return out
+
+
+def config_xy(n: int = 8, seed: int = 7, t_total: int = 600, local_rows: bool = False,
+              magnetic_field=(0.0, 0.0, 30.0)) -> HamiltonianSpec:
+    """n-atom XY-mode register driven by a global microwave pulse (Blackman envelope, constant detuning)."""
+    coords = disc_register(n, 30.0, 8.0, seed)
+    amp = np.append(blackman(t_total, 1.5 * np.pi), 0.0)
+    det = np.append(constant(t_total, 0.8), 0.0)
+    coef = np.repeat((0.5 * amp.astype(np.complex128))[None, :], n, axis=0)
+    dets = np.repeat(det[None, :], n, axis=0)
+    if local_rows:  # per-atom amplitude / detuning spread, as a noise trajectory would have
+        rng = np.random.default_rng(seed + 1)
+        coef = coef * rng.normal(1.0, 0.05, size=(n, 1))
+        dets = dets + rng.normal(0.0, 0.3, size=(n, 1)) * (np.arange(t_total + 1) < t_total)
+    return HamiltonianSpec(
+        n_qudits=n, dim=2, eigenbasis=["u", "d"], basis_name="XY", interaction_type="XY",
+        sampling_times=np.arange(t_total + 1, dtype=np.double) / 1000, total_duration_ns=t_total,
+        interaction_matrix=xy_interaction_matrix(coords, C3_XY, C6_LEVEL_70, magnetic_field),
+        bad_atoms=np.zeros(n, dtype=bool), drives=[DriveTable("XY", coef, dets, not local_rows)],
+        collapse_ops=np.zeros((0, 2, 2), dtype=np.complex128), qubit_ids=[f"q{i}" for i in range(n)],
+    )

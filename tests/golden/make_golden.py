@@ -2,7 +2,7 @@
 imported from /root/reference) plus the tight-tolerance oracle.
 
 Run in the build container only (the GPU box has no /root/reference):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--extra | --xy]
 
 Each ``*.npz`` holds a HamiltonianSpec (what the reference's Hamiltonian
 constructor receives, extracted from real pulser objects), an initial state and
@@ -164,7 +164,7 @@ def main():
         save(f"orc_noisy_traj{i}", spec, psi0=psi0, orc_final=oracle_final(spec, psi0), reps=reps)
 
 
-if __name__ == "__main__" and "--extra" not in sys.argv:
+if __name__ == "__main__" and "--extra" not in sys.argv and "--xy" not in sys.argv:
     main()
 
 
@@ -198,3 +198,31 @@ def extra():
 
 if __name__ == "__main__" and "--extra" in sys.argv:
     extra()
+
+
+def xy():
+    """Third batch: XY mode (microwave channel, eigenbasis u, d)."""
+    # reference tests/pulser_simulation/test_simulation.py:1430-1491 (test_get_xy_hamiltonian)
+    reg = Register.from_coordinates([[0, 10], [10, 0], [0, 0]], prefix="atom")
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch0", "mw_global")
+    seq.set_magnetic_field(0, 1.0, 0.0)
+    seq.add(Pulse.ConstantPulse(1500, 3.0, 1.0, 0.0), "ch0")
+    spec = specs_of(seq, rate=0.03)[0][0]
+    assert spec.eigenbasis == ["u", "d"] and spec.interaction_type == "XY"
+    save("ref_get_xy_hamiltonian", spec, t_ns=143.0, c3=MockDevice.interaction_coeff_xy, c6=MockDevice.interaction_coeff)
+
+    # XY evolution of a 4-atom register under a tilted field, full sampling: oracle end state
+    reg = Register.from_coordinates([[0, 0], [9, 0], [1, 8], [10, 9]], prefix="a", center=False)
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch0", "mw_global")
+    seq.set_magnetic_field(0.4, 1.0, 0.7)
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(400, 1.2 * np.pi), 0.7, 0.3), "ch0")
+    seq.add(Pulse.ConstantPulse(200, 2.0, -1.0, 0.0), "ch0")
+    spec = specs_of(seq)[0][0]
+    psi0 = evolve.all_ground_state(spec)
+    save("orc_xy_evolution", spec, psi0=psi0, orc_final=oracle_final(spec, psi0))
+
+
+if __name__ == "__main__" and "--xy" in sys.argv:
+    xy()

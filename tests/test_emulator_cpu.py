@@ -162,3 +162,30 @@ def test_large_register_collapse_needs_trajectories(emu):
     assert sim._use_mcwf() and not sim._density_matrix_fits()
     with pytest.raises(ValueError, match="'n_trajectories' must be defined"):
         sim.run()
+
+
+def test_run_xy(emu):
+    """reference tests/pulser_simulation/test_simulation.py:1493-1530 (test_run_xy): XY mode through the facade."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    seq = Sequence(Register.from_coordinates([[10, 0], [0, 0]], prefix="atom"), MockDevice)
+    seq.declare_channel("ch0", "mw_global")
+    seq.add(Pulse.ConstantPulse(1500, 3.0, 1.0, 0.0), "ch0")
+    sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01)
+    assert sim.basis_name == "XY" and sim.dim == 2
+    good = np.r_[1, np.zeros(3)]
+    sim.set_initial_state(good)
+    np.testing.assert_array_equal(sim.initial_state.full().ravel(), good)  # all-|u> is the default
+    res = sim.run()
+    final = res.get_final_state().full().ravel()
+    assert abs(np.linalg.norm(final) - 1) < 1e-8 and abs(final[0]) < 1.0
+    # exchange symmetry of the two-atom register: |ud> and |du> amplitudes agree
+    assert abs(final[1] - final[2]) < 1e-8
+    assert not sim.samples_obj._measurement
+    seq.measure(basis="XY")
+    sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01)
+    res = sim.run()
+    assert sim.samples_obj._measurement == "XY"
+    counts = res.sample_final_state(500)
+    assert sum(counts.values()) == 500 and set(counts) <= {"00", "01", "10", "11"}

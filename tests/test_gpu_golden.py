@@ -46,6 +46,7 @@ def test_get_hamiltonian_reference_goldens(engine):
 @pytest.mark.parametrize("name", [
     "ref_initial_state_sim", "ref_qutip_backend_pi_pulse", "ref_delays_occupation",
     "orc_c1_square", "orc_all_basis_3atoms", "orc_noisy_traj0", "orc_noisy_traj1", "orc_noisy_traj2",
+    "orc_xy_evolution",
 ])
 def test_final_state_goldens(engine, name):
     spec, extra = load(name)
@@ -132,3 +133,18 @@ def test_interpolation_orders(engine, order):
         got = plan.get_state()[0]
     # piecewise-constant / piecewise-linear H(t) limits the accuracy of the adaptive ODE oracle, not ours
     assert np.max(np.abs(got - ref)) < (STATE_TOL if order == 3 else 5e-7)
+
+
+def test_get_xy_hamiltonian_reference_golden(engine):
+    """reference tests/pulser_simulation/test_simulation.py:1430-1491 on the device: H(143 ns) column by column."""
+    spec, extra = load("ref_get_xy_hamiltonian")
+    c3, c6 = float(extra["c3"]), float(extra["c6"])
+    with engine.DevicePlan(spec) as plan:
+        h = dense_h(plan, spec.hilbert_dim, float(extra["t_ns"]) / 1000)
+    assert h[1, 2] == c3 / 10**3
+    assert abs(h[1, 4] - (-2 * c3 / 10**3)) < 1e-10
+    assert h[0, 1] == 0.5 * 3.0
+    n_d = np.array([0, 1, 1, 2, 1, 2, 2, 3])
+    vdw = np.array([2 + 1 / 8, 1 / 8, 1, 0, 1, 0, 0, 0]) * c6 / 1e6
+    np.testing.assert_array_almost_equal(np.diag(h).real, -1.0 * n_d + vdw)
+    assert np.allclose(h, h.conj().T)

@@ -390,3 +390,63 @@ def test_mcwf_rejects_non_diagonal_ldl(engine):
     with engine.DevicePlan(spec) as plan:
         with pytest.raises(PB200Error, match="not diagonal"):
             plan.set_collapse(np.array([[[1, 1], [0, 1]]], dtype=complex))
+
+
+@pytest.mark.parametrize("n,local_rows", [(2, False), (5, False), (9, True), (12, False), (13, True)])
+def test_xy_apply_h(engine, n, local_rows):
+    """XY mode: exchange term U_ij (|ud><du| + h.c.) + |uu><uu| van der Waals + microwave drive vs the oracle."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    spec = W.config_xy(n=n, seed=n, t_total=80, local_rows=local_rows, magnetic_field=(0.3, 1.0, 0.5))
+    mf = MatFreeHamiltonian(spec)
+    v = random_state(spec.hilbert_dim, n)
+    with engine.DevicePlan(spec) as plan:
+        for t in (0.0123, 0.0551):
+            got = plan.apply_h(t, v)
+            ref = mf.apply(t, v)
+            assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("n,integrator", [(4, "chebyshev"), (7, "chebyshev"), (7, "lanczos"), (9, "auto")])
+def test_xy_evolution_vs_oracle(engine, n, integrator):
+    from oracle import evolve
+
+    spec = W.config_xy(n=n, seed=40 + n, t_total=300)
+    psi0 = evolve.all_ground_state(spec)
+    assert abs(psi0[0]) == 1.0  # all-|u>
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1], integrator=integrator)
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+
+
+def test_xy_batch_with_missing_atoms(engine):
+    """Trajectories with different bad atoms: per-trajectory exchange couplings."""
+    import copy
+    from oracle import evolve
+
+    base = W.config_xy(n=6, seed=3, t_total=200)
+    specs = []
+    for bad in ([], [2], [0, 5]):
+        s = copy.copy(base)
+        s.bad_atoms = np.zeros(6, dtype=bool)
+        s.bad_atoms[bad] = True
+        s.interaction_matrix = base.interaction_matrix.copy()
+        s.interaction_matrix[:, bad, :] = 0.0
+        s.interaction_matrix[:, :, bad] = 0.0
+        d0 = base.drives[0]
+        coef, det = d0.coef.copy(), d0.det.copy()
+        coef[bad] = 0.0
+        det[bad] = 0.0
+        from pulser_b200.spec import DriveTable
+        s.drives = [DriveTable(d0.basis, coef, det, False)]
+        specs.append(s)
+    psi0 = evolve.all_ground_state(base)
+    with engine.DevicePlan(specs) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, base.sampling_times[-1])
+        got = plan.get_state()
+    for b, s in enumerate(specs):
+        assert np.max(np.abs(got[b] - _oracle_final(s, psi0))) < STATE_TOL

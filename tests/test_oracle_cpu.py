@@ -40,6 +40,30 @@ def test_golden_get_hamiltonian_noisy(name):
     np.testing.assert_allclose(h, extra["h"], rtol=1e-7, atol=1e-8)
 
 
+def test_golden_get_xy_hamiltonian():
+    """reference tests/pulser_simulation/test_simulation.py:1430-1491 (test_get_xy_hamiltonian)"""
+    spec, extra = load("ref_get_xy_hamiltonian")
+    c3, c6 = float(extra["c3"]), float(extra["c6"])
+    h = OracleHamiltonian.from_spec(spec).matrix_at(float(extra["t_ns"]) / 1000).toarray()
+    assert h[1, 2] == c3 / 10**3
+    assert abs(h[1, 4] - (-2 * c3 / 10**3)) < 1e-10
+    assert h[0, 1] == 0.5 * 3.0
+    n_d = np.array([0, 1, 1, 2, 1, 2, 2, 3])
+    vdw = np.array([2 + 1 / 8, 1 / 8, 1, 0, 1, 0, 0, 0]) * c6 / 1e6
+    np.testing.assert_array_almost_equal(np.diag(h).real, -1.0 * n_d + vdw)
+    # matrix-free oracle == literal restatement in XY mode
+    v = random_state(8, 3)
+    assert np.max(np.abs(MatFreeHamiltonian(spec).apply(0.143, v) - h @ v)) < 1e-12
+
+
+def test_xy_workload_matrix_free_equals_literal():
+    spec = W.config_xy(n=5, seed=2, t_total=60, local_rows=True, magnetic_field=(0.3, 1.0, 0.5))
+    H = OracleHamiltonian.from_spec(spec)
+    v = random_state(32, 1)
+    for t in (0.004, 0.0313):
+        assert np.max(np.abs(MatFreeHamiltonian(spec).apply(t, v) - H.matrix_at(t) @ v)) < 1e-11
+
+
 def test_golden_initial_state_sim():
     """reference test_simulation.py:2156-2190 pins the 3-atom final state to
     rtol 1e-2 (generated with an older pulser/QuTiP).  The restatement agrees
@@ -259,3 +283,34 @@ def test_workloads_c3_c4_equal_pulser():
         np.testing.assert_array_equal(mine.drives[0].coef, ref.drives[0].coef)
         np.testing.assert_array_equal(mine.drives[0].det, ref.drives[0].det)
     assert abs(W.doppler_sigma(50.0) - 0.600149981254686) < 1e-15
+
+
+@pytest.mark.skipif(not HAVE_PULSER, reason="pulser-core not importable here")
+def test_xy_workload_equals_pulser():
+    """workloads.config_xy restates what pulser-core produces for a global microwave pulse under a tilted field."""
+    import warnings
+
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser._hamiltonian_data import HamiltonianData
+    from pulser.devices import MockDevice
+    from pulser.sampler import sampler
+    from pulser.waveforms import BlackmanWaveform
+    from pulser_b200.spec import spec_from_pulser
+
+    n, T, field = 5, 120, (0.3, 1.0, 0.5)
+    mine = W.config_xy(n=n, seed=9, t_total=T, magnetic_field=field)
+    coords = W.disc_register(n, 30.0, 8.0, 9)
+    seq = Sequence(Register.from_coordinates(coords, center=False, prefix="q"), MockDevice)
+    seq.declare_channel("mw", "mw_global")
+    seq.set_magnetic_field(*field)
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(T, 1.5 * np.pi), 0.8, 0), "mw")
+    samples = sampler.sample(seq, extended_duration=seq.get_duration())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hd = HamiltonianData(samples.extend_duration(T + 1), seq.register, seq.device, NoiseModel(), None)
+    tr, ns, _ = next(iter(hd.noisy_samples))
+    ref = spec_from_pulser(ns, tr, hd.basis_data, hd.lindblad_data, 1.0, T)
+    assert ref.eigenbasis == mine.eigenbasis and ref.interaction_type == "XY"
+    assert np.allclose(ref.interaction_matrix, mine.interaction_matrix, rtol=1e-12, atol=0)
+    assert np.allclose(ref.drives[0].coef, mine.drives[0].coef, rtol=1e-12, atol=1e-15)
+    assert np.allclose(ref.drives[0].det, mine.drives[0].det, rtol=1e-12, atol=1e-15)
