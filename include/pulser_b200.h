@@ -200,6 +200,23 @@ int pb200_state_norm2(pb200_plan* plan, int32_t traj0, int32_t count,
  * (the Occupation observable; default_observables.py:377-436). */
 int pb200_state_occupation(pb200_plan* plan, int32_t traj0, int32_t count,
                            int32_t digit, double* occ);
+/* <n_i n_j> of the current states, n_k = |digit><digit| on qudit k:
+ * corr[count][N][N] (symmetric; the diagonal is the occupation).  Replaces the
+ * CorrelationMatrix / Occupation observables' per-pair operator products
+ * (pulser-core/pulser/backend/default_observables.py:331-428). */
+int pb200_state_correlation(pb200_plan* plan, int32_t traj0, int32_t count,
+                            int32_t digit, double* corr);
+
+/* energy[b] = <psi_b|H_b(t)|psi_b>, h2[b] = <psi_b|H_b(t)^2|psi_b> for every
+ * trajectory of the plan (Energy, EnergyVariance, EnergySecondMoment:
+ * default_observables.py:431-561). */
+int pb200_state_energy(pb200_plan* plan, double t_us, double* energy, double* h2);
+
+/* out[c] = <phi|psi_{traj0+c}> as (re, im); phi: complex128[D] on the host
+ * (Fidelity observable / State.overlap, default_observables.py:184-243). */
+int pb200_state_overlap(pb200_plan* plan, int32_t traj0, int32_t count,
+                        const double* phi, double* out);
+
 /* Bitstring sampling on the device (QutipResult._weights + multinomial,
  * qutip_result.py:101-158, pulser/math/multinomial.py:17-36): weights over the
  * 2^N bitstrings (bit k = [digit_k == one_digit]), normalised, cumulated, and

@@ -102,6 +102,9 @@ def _load() -> C.CDLL:
         "pb200_state_probabilities": (C.c_int, [vp, C.c_int32, C.c_int32, dp]),
         "pb200_state_norm2": (C.c_int, [vp, C.c_int32, C.c_int32, dp]),
         "pb200_state_occupation": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, dp]),
+        "pb200_state_correlation": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, dp]),
+        "pb200_state_energy": (C.c_int, [vp, C.c_double, dp, dp]),
+        "pb200_state_overlap": (C.c_int, [vp, C.c_int32, C.c_int32, dp, dp]),
         "pb200_state_sample": (
             C.c_int, [vp, C.c_int32, C.c_int32, dp, C.c_int32, C.POINTER(C.c_int64)]),
         "pb200_state_device_ptr": (C.c_int, [vp, C.POINTER(vp)]),
@@ -132,7 +135,7 @@ EXPORTED_SYMBOLS = [
     "pb200_plan_set_interaction", "pb200_plan_set_xy", "pb200_plan_set_drive", "pb200_plan_set_dissipator", "pb200_plan_set_collapse",
     "pb200_plan_jump_counts", "pb200_state_set",
     "pb200_state_get", "pb200_state_probabilities", "pb200_state_norm2",
-    "pb200_state_occupation", "pb200_state_sample", "pb200_state_device_ptr", "pb200_propagate", "pb200_apply_h",
+    "pb200_state_occupation", "pb200_state_correlation", "pb200_state_energy", "pb200_state_overlap", "pb200_state_sample", "pb200_state_device_ptr", "pb200_propagate", "pb200_apply_h",
     "pb200_coefficients_at", "pb200_bench_apply", "pb200_host_interpolate",
     "pb200_host_moments", "pb200_host_chebyshev",
 ]

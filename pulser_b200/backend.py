@@ -155,17 +155,152 @@ class B200State(State[complex, float]):
         )
 
 
+class _DeviceResident:
+    """Marker + protocol of states whose data lives in a ``DevicePlan``."""
+
+    def _projector_expect(self, coeff: complex, letter: str | None, targets: frozenset) -> complex | None:
+        raise NotImplementedError
+
+
+class DeviceStateView(_DeviceResident, B200State):
+    """The current state of trajectory 0 of a ``DevicePlan``, left on the GPU.
+
+    Handed to the observables by ``B200Backend`` while it steps through the
+    evaluation times: ``Occupation`` / ``CorrelationMatrix`` (number-operator
+    expectations), ``Energy*`` (with ``DeviceHamiltonian``), ``Fidelity`` and
+    ``BitStrings`` reduce on the device (``pb200_state_occupation / _correlation /
+    _energy / _overlap / _sample``); anything else falls back to a host copy
+    (``to_array``), fetched once.  Replaces the replay of stored ``QutipState``s of
+    ``qutip_backend.py:254-280``, which cannot hold one state per step at N >= 20.
+    """
+
+    def __init__(self, plan: Any, *, eigenstates: Sequence[str]):
+        State.__init__(self, eigenstates=eigenstates)
+        self._plan = plan
+        self._host: np.ndarray | None = None
+        self._norm2 = float(plan.norm2()[0])
+        self._corr: dict[int, np.ndarray] = {}
+        self._energy: dict[float, tuple[float, float]] = {}
+
+    @property
+    def _state(self) -> np.ndarray:  # host copy, normalised like qutip_backend.py:268-272
+        if self._host is None:
+            self._host = self._plan.get_state()[0] / math.sqrt(self._norm2)
+        return self._host
+
+    @property
+    def is_ket(self) -> bool:
+        return True
+
+    @property
+    def n_qudits(self) -> int:
+        return int(self._plan.n)
+
+    def _correlations(self, letter: str) -> np.ndarray:
+        digit = self.eigenstates.index(letter)
+        if digit not in self._corr:
+            self._corr[digit] = self._plan.correlation(digit, 0, 1)[0] / self._norm2
+        return self._corr[digit]
+
+    def _projector_expect(self, coeff, letter, targets):
+        if len(targets) == 0:
+            return complex(coeff)
+        if len(targets) > 2:
+            return None
+        idx = sorted(targets)
+        return complex(coeff) * float(self._correlations(letter)[idx[0], idx[-1]])
+
+    def _energy_moments(self, plan: Any, t_us: float) -> tuple[float, float] | None:
+        if plan is not self._plan:
+            return None
+        if t_us not in self._energy:
+            e, e2 = plan.energy(t_us)
+            self._energy[t_us] = (float(e[0]) / self._norm2, float(e2[0]) / self._norm2)
+        return self._energy[t_us]
+
+    def overlap(self, other: "B200State") -> float:
+        if isinstance(other, B200State) and not isinstance(other, _DeviceResident) and other.is_ket \
+                and other.eigenstates == self.eigenstates and other.n_qudits == self.n_qudits:
+            return float(abs(self._plan.overlap(other._state, 0, 1)[0]) ** 2 / self._norm2)
+        return B200State.overlap(self, other)
+
+    def sample(self, *, num_shots: int, one_state: str | None = None, p_false_pos: float = 0.0,
+               p_false_neg: float = 0.0) -> Counter:
+        """Shots drawn on the device (``pb200_state_sample``: cumulative sum + searchsorted of the uniforms of
+        the global ``np.random`` stream, the recipe of ``qutip_result.py:101-158``); same distribution as
+        ``B200State.sample`` without the host-side probability dictionary."""
+        one_state = one_state or self.infer_one_state()
+        counts = self._plan.sample(int(num_shots), one_state, 0)
+        if p_false_pos == 0.0 and p_false_neg == 0.0:
+            return counts
+        keys = list(counts)
+        bitstr_arr = np.repeat(np.array([list(k) for k in keys], dtype=int), [counts[k] for k in keys], axis=0)
+        flip_probs = np.where(bitstr_arr == 1, p_false_neg, p_false_pos)
+        flips = np.random.uniform(size=flip_probs.shape) < flip_probs
+        new_counts: Counter = Counter(map(tuple, bitstr_arr ^ flips))
+        return Counter({"".join(map(str, k)): v for k, v in new_counts.items()})
+
+    def __repr__(self) -> str:
+        return f"DeviceStateView(eigenstates={self.eigenstates}, n_qudits={self.n_qudits})"
+
+
+class _HPsiView(_DeviceResident, B200State):
+    """``H(t)|psi>`` of a device-resident state: its squared norm is known from the fused device reduction,
+    the vector itself is only formed (one more H-apply, fetched to the host) if somebody asks for it."""
+
+    def __init__(self, source: DeviceStateView, ham: "DeviceHamiltonian", norm2: float):
+        State.__init__(self, eigenstates=source.eigenstates)
+        self._source, self._ham, self._weight = source, ham, norm2
+        self._host: np.ndarray | None = None
+
+    @property
+    def _state(self) -> np.ndarray:
+        if self._host is None:
+            self._host = self._ham._matvec(self._source._state)
+        return self._host
+
+    @property
+    def is_ket(self) -> bool:
+        return True
+
+    @property
+    def n_qudits(self) -> int:
+        return self._source.n_qudits
+
+    def _projector_expect(self, coeff, letter, targets):
+        return complex(coeff) * self._weight if len(targets) == 0 else None
+
+
 class B200Operator(Operator[complex, complex, B200State]):
     """An operator as a scipy sparse matrix (``QutipOperator`` mirror)."""
 
-    def __init__(self, operator: Any, eigenstates: Sequence[str]):
+    def __init__(self, operator: Any, eigenstates: Sequence[str], *, pattern: tuple | None = None):
+        """``operator``: a matrix, or a zero-argument callable building it on first use.
+
+        ``pattern = (coeff, state, frozenset(qudits))`` marks ``coeff * prod_k |state><state|_k`` (identity for an
+        empty set): its expectation on a device-resident state is a reduction on the GPU, the matrix is never built.
+        """
         super().__init__()
         B200State._validate_eigenstates(eigenstates)
         self._eigenstates = eigenstates
+        self._pattern = pattern
+        if callable(operator):
+            self._builder, self._matrix = operator, None
+        else:
+            self._builder, self._matrix = None, self._as_matrix(operator)
+
+    @staticmethod
+    def _as_matrix(operator: Any) -> sp.csr_matrix:
         mat = sp.csr_matrix(operator.full() if hasattr(operator, "full") else operator, dtype=np.complex128)
         if mat.shape[0] != mat.shape[1]:
             raise TypeError("'operator' must be a square matrix.")
-        self._operator = mat
+        return mat
+
+    @property
+    def _operator(self) -> sp.csr_matrix:
+        if self._matrix is None:
+            self._matrix = self._as_matrix(self._builder())
+        return self._matrix
 
     @property
     def eigenstates(self) -> tuple[str, ...]:
@@ -195,7 +330,8 @@ class B200Operator(Operator[complex, complex, B200State]):
         out = self._matvec(state._state)
         if not state.is_ket:
             out = self._matvec(out.conj().T).conj().T  # O rho O^+
-        return type(state)(out, eigenstates=state.eigenstates)
+        cls = B200State if isinstance(state, _DeviceResident) else type(state)
+        return cls(out, eigenstates=state.eigenstates)
 
     @property
     def _isherm(self) -> bool:
@@ -207,6 +343,10 @@ class B200Operator(Operator[complex, complex, B200State]):
     def expect(self, state: B200State, /) -> complex:
         """``qutip.expect`` semantics: a real number for a Hermitian operator."""
         self._validate_other(state, B200State, "B200Operator.expect()")
+        if self._pattern is not None and isinstance(state, _DeviceResident):
+            val = state._projector_expect(*self._pattern)
+            if val is not None:
+                return val.real if val.imag == 0.0 else val
         if state.is_ket:
             val = complex(np.vdot(state._state, self._matvec(state._state)))
         else:
@@ -218,11 +358,19 @@ class B200Operator(Operator[complex, complex, B200State]):
         return B200Operator(self._operator + other._operator, eigenstates=self.eigenstates)
 
     def __rmul__(self, scalar: complex) -> "B200Operator":
-        return B200Operator(complex(scalar) * self._operator, eigenstates=self.eigenstates)
+        pat = self._pattern
+        if pat is not None:
+            pat = (complex(scalar) * pat[0], pat[1], pat[2])
+        return B200Operator(lambda: complex(scalar) * self._operator, eigenstates=self.eigenstates, pattern=pat)
 
     def __matmul__(self, other: "B200Operator") -> "B200Operator":
         self._validate_other(other, B200Operator, "__matmul__")
-        return B200Operator(self._operator @ other._operator, eigenstates=self.eigenstates)
+        pat = None
+        a, b = self._pattern, getattr(other, "_pattern", None)
+        if a is not None and b is not None and (a[1] == b[1] or not a[2] or not b[2]):
+            # projectors on one eigenstate commute and are idempotent: the product is the projector on the union
+            pat = (a[0] * b[0], a[1] if a[2] else b[1], a[2] | b[2])
+        return B200Operator(lambda: self._operator @ other._operator, eigenstates=self.eigenstates, pattern=pat)
 
     @classmethod
     def _from_operator_repr(cls, *, eigenstates: Sequence[str], n_qudits: int, operations: Any):
@@ -235,21 +383,49 @@ class B200Operator(Operator[complex, complex, B200State]):
                 m[eigenstates.index(proj_str[0]), eigenstates.index(proj_str[1])] += complex(coeff)
             return m.tocsr()
 
-        full = sp.csr_matrix((d**n_qudits, d**n_qudits), dtype=np.complex128)
         reconstructed = []
         for coeff, tensor_op in operations:
-            factors = [sp.identity(d, format="csr", dtype=np.complex128) for _ in range(n_qudits)]
-            re_tensor = []
-            for qop, inds in tensor_op:
-                for ind in inds:
-                    factors[ind] = qudit_op(qop)
-                re_tensor.append(({k: complex(v) for k, v in qop.items()}, set(inds)))
-            term = factors[0]
-            for f in factors[1:]:
-                term = sp.kron(term, f, format="csr")
-            full = full + complex(coeff) * term
+            re_tensor = [({k: complex(v) for k, v in qop.items()}, set(inds)) for qop, inds in tensor_op]
+            for qop, inds in re_tensor:
+                for key in qop:
+                    if len(key) != 2 or key[0] not in eigenstates or key[1] not in eigenstates:
+                        raise ValueError(f"Invalid projector '{key}' for eigenstates {tuple(eigenstates)}.")
+                if any(ind < 0 or ind >= n_qudits for ind in inds):
+                    raise ValueError("Qudit index out of range in the operator representation.")
             reconstructed.append((complex(coeff), re_tensor))
-        return B200Operator(full, eigenstates=eigenstates), reconstructed
+
+        def build() -> sp.csr_matrix:
+            full = sp.csr_matrix((d**n_qudits, d**n_qudits), dtype=np.complex128)
+            for coeff, re_tensor in reconstructed:
+                factors = [sp.identity(d, format="csr", dtype=np.complex128) for _ in range(n_qudits)]
+                for qop, inds in re_tensor:
+                    for ind in inds:
+                        factors[ind] = qudit_op(qop)
+                term = factors[0]
+                for f in factors[1:]:
+                    term = sp.kron(term, f, format="csr")
+                full = full + coeff * term
+            return full
+
+        # one term made of |a><a| projectors of a single eigenstate (number operators, identity)?
+        pattern = None
+        if len(reconstructed) == 1:
+            coeff, re_tensor = reconstructed[0]
+            letters, targets, scale, ok = set(), set(), complex(1.0), True
+            for qop, inds in re_tensor:
+                if len(qop) != 1 or targets & inds:
+                    ok = False
+                    break
+                (key, val), = qop.items()
+                if key[0] != key[1]:
+                    ok = False
+                    break
+                letters.add(key[0])
+                targets |= inds
+                scale *= val ** len(inds)
+            if ok and len(letters) <= 1:
+                pattern = (coeff * scale, next(iter(letters)) if letters else None, frozenset(targets))
+        return B200Operator(build, eigenstates=eigenstates, pattern=pattern), reconstructed
 
     def __repr__(self) -> str:
         return f"B200Operator(eigenstates={self.eigenstates}, shape={self._operator.shape})"
@@ -273,8 +449,29 @@ class DeviceHamiltonian(B200Operator):
         self._eigenstates = eigenstates
         self._plan = plan
         self._t = t_us
-        self._operator = None  # never materialised
+        self._pattern = None
+        self._builder, self._matrix = None, None  # never materialised
         self._herm_cache = True
+
+    @property
+    def _operator(self):
+        raise NotImplementedError("DeviceHamiltonian is matrix-free")
+
+    def expect(self, state: B200State, /) -> complex:
+        if isinstance(state, DeviceStateView):
+            self._validate_other(state, B200State, "B200Operator.expect()")
+            mom = state._energy_moments(self._plan, self._t)
+            if mom is not None:
+                return mom[0]
+        return super().expect(state)
+
+    def apply_to(self, state: B200State, /) -> B200State:
+        if isinstance(state, DeviceStateView):
+            self._validate_other(state, B200State, "B200Operator.apply_to()")
+            mom = state._energy_moments(self._plan, self._t)
+            if mom is not None:
+                return _HPsiView(state, self, mom[1])
+        return super().apply_to(state)
 
     def _matvec(self, arr: np.ndarray) -> np.ndarray:
         if arr.ndim == 1:
@@ -384,6 +581,34 @@ class B200Backend(EmulatorBackend):
             for obs in config.observables:
                 obs(config=config, t=t, state=state, hamiltonian=ham, result=res)
 
+    def _stream(self, plan: Any, res: Results) -> None:
+        """Noiseless sequence: step the device plan through the evaluation times and hand the observables a
+        view of the state that stays on the GPU (no per-time state on the host)."""
+        sim, config = self._sim_obj, self._config
+        eig = sim._hamiltonian_data.basis_data.eigenbasis
+        opts = sim._validate_options({})
+        if config.print_progress:
+            print("Emulating Trajectory 1/1")
+        plan.set_state(sim._initial_state.full().reshape(-1))
+        times = sim._eval_times_array
+        stats: dict = {}
+        prev = float(times[0])
+        for t_us in times:
+            t_us = float(t_us)
+            if t_us > prev:
+                st = plan.propagate(prev, t_us, **opts)
+                for k, v in st.items():
+                    stats[k] = max(stats.get(k, 0), v) if k == "max_rho" else stats.get(k, 0) + v
+                prev = t_us
+            t = t_us / (sim._tot_duration * 1e-3)
+            state = DeviceStateView(plan, eigenstates=eig)
+            ham = DeviceHamiltonian(plan, t_us, eig)
+            for callback in config.callbacks:
+                callback(config=config, t=t, state=state, hamiltonian=ham, result=res)
+            for obs in config.observables:
+                obs(config=config, t=t, state=state, hamiltonian=ham, result=res)
+        sim.last_run_stats = stats
+
     def run(self) -> Results:
         from . import engine
 
@@ -391,6 +616,13 @@ class B200Backend(EmulatorBackend):
         opts = {"print_progress": self._config.print_progress, "progress_bar": self._config.progress_bar}
         atom_order = tuple(sim._register.qubit_ids)
         with engine.DevicePlan(sim._noiseless_spec(), sim._interp_order, sim._gpu) as hplan:
+            if not sim.noise_model.noise_types:
+                # no noise at all: the evolved Hamiltonian IS the noiseless one handed to the observables
+                sim._validate_options({})
+                sim._check_supported()
+                res = Results(atom_order=atom_order, total_duration=sim.total_duration_ns)
+                self._stream(hplan, res)
+                return res
             if not _has_stochastic_noise(sim.noise_model):
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore", DeprecationWarning)

@@ -978,6 +978,73 @@ __global__ void occupation_kernel(const c2* psi, double* occ, long long D, int n
     for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(occ + traj * n + i, socc[i]);
 }
 
+// corr[traj][i*n+j] (i <= j) += sum_s |psi_s|^2 [digit_i(s) == digit][digit_j(s) == digit]
+// (CorrelationMatrix observable <n_i n_j>; the diagonal is the occupation).  A block stages 2048 probabilities and
+// their per-qudit match masks in shared memory; each warp then reduces a subset of the n(n+1)/2 pairs over them.
+__global__ void __launch_bounds__(256) correlation_kernel(const c2* psi, double* corr, long long D, int n, int dim, int digit) {
+    constexpr int CH = 2048;
+    __shared__ double sp[CH];
+    __shared__ unsigned long long sm[CH];
+    const long long traj = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int npairs = n * (n + 1) / 2;
+    for (long long base = blockIdx.x * (long long)CH; base < D; base += (long long)gridDim.x * CH) {
+        for (int e = threadIdx.x; e < CH; e += blockDim.x) {
+            const long long s = base + e;
+            double p = 0.0;
+            unsigned long long m = 0ull;
+            if (s < D) {
+                const c2 v = psi[traj * D + s];
+                p = v.x * v.x + v.y * v.y;
+                long long rem = s;
+                for (int k = n - 1; k >= 0; --k) {
+                    if ((int)(rem % dim) == digit) m |= 1ull << k;
+                    rem /= dim;
+                }
+            }
+            sp[e] = p; sm[e] = m;
+        }
+        __syncthreads();
+        int i = 0, first = 0;  // pairs enumerated row by row: (0,0..n-1), (1,1..n-1), ...
+        for (int pr = warp; pr < npairs; pr += nw) {
+            while (pr - first >= n - i) { first += n - i; ++i; }
+            const int j = i + (pr - first);
+            const unsigned long long need = (1ull << i) | (1ull << j);
+            double acc = 0.0;
+            for (int e = lane; e < CH; e += 32)
+                if ((sm[e] & need) == need) acc += sp[e];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0 && acc != 0.0) atomicAdd(corr + traj * n * n + i * n + j, acc);
+        }
+        __syncthreads();
+    }
+}
+
+// acc[traj] += <phi, psi_traj> (complex; phi shared by all trajectories)   (Fidelity observable / State.overlap)
+__global__ void overlap_kernel(const c2* phi, const c2* psi, long long D, double* acc) {
+    const long long traj = blockIdx.y;
+    double re = 0.0, im = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < D;
+         i += (long long)gridDim.x * blockDim.x) {
+        const c2 a = phi[i], b = psi[traj * D + i];
+        re = fma(a.x, b.x, re); re = fma(a.y, b.y, re);
+        im = fma(a.x, b.y, im); im = fma(-a.y, b.x, im);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    __shared__ double ws[2][8];
+    if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = re; ws[1][threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s0 += ws[0][i]; s1 += ws[1][i]; }
+        atomicAdd(acc + 2 * traj, s0);
+        atomicAdd(acc + 2 * traj + 1, s1);
+    }
+}
+
 // indices[i] = first j with cum[j] >= u[i] * total  (np.searchsorted(cumsum(w / sum w), rnd), side="left")
 __global__ void search_sorted_kernel(const double* cum, long long M, const double* u, long long* idx, int n_shots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

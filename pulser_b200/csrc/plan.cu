@@ -1966,6 +1966,81 @@ int pb200_state_occupation(pb200_plan* h, int32_t traj0, int32_t count, int32_t 
     PB200_CATCH
 }
 
+int pb200_state_correlation(pb200_plan* h, int32_t traj0, int32_t count, int32_t digit, double* corr) {
+    PB200_TRY
+    if (!h || !corr) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    if (digit < 0 || digit >= P.dim) fail(PB200_ERR_INVALID, "digit out of range");
+    if (P.n > 40) fail(PB200_ERR_UNSUPPORTED, "too many qudits for the correlation matrix");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    const size_t nn = (size_t)P.n * P.n;
+    double* d_c = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_c, sizeof(double) * count * nn));
+    CUDA_CHECK(cudaMemsetAsync(d_c, 0, sizeof(double) * count * nn, P.stream));
+    const long long blocks = std::min<long long>((P.D + 2047) / 2048, (long long)P.sm_count * 4);
+    dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
+    correlation_kernel<<<grid, 256, 0, P.stream>>>(P.buf[P.cur] + (size_t)traj0 * P.D, d_c, P.D, P.n, P.dim, digit);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(corr, d_c, sizeof(double) * count * nn, cudaMemcpyDeviceToHost, P.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
+    cudaFree(d_c);
+    if (e != cudaSuccess) fail(PB200_ERR_CUDA, "correlation: %s", cudaGetErrorString(e));
+    for (int c = 0; c < count; ++c)  // the kernel fills i <= j
+        for (int i = 0; i < P.n; ++i)
+            for (int j = 0; j < i; ++j) corr[c * nn + (size_t)i * P.n + j] = corr[c * nn + (size_t)j * P.n + i];
+    PB200_CATCH
+}
+
+int pb200_state_energy(pb200_plan* h, double t_us, double* energy, double* h2) {
+    PB200_TRY
+    if (!h || !energy || !h2) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    for (int tr = 0; tr < P.B; ++tr)
+        for (int q = 0; q < P.n_drives; ++q)
+            if (!P.tabs_set[tr][q]) fail(PB200_ERR_STATE, "drive %d of trajectory %d not set", q, tr);
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    c2* hpsi = P.buf[(P.cur + 2) % 3];
+    long long launches = 0;
+    apply_h_device(P, t_us, P.buf[P.cur], hpsi, launches);
+    double* d_acc = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_acc, sizeof(double) * 2 * P.B));
+    CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * P.B, P.stream));
+    const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
+    dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
+    dot2_kernel<<<grid, 256, 0, P.stream>>>(P.buf[P.cur], hpsi, P.D, d_acc);  // Re<psi, H psi>, <H psi, H psi>
+    std::vector<double> acc(2 * (size_t)P.B);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), d_acc, sizeof(double) * 2 * P.B, cudaMemcpyDeviceToHost, P.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
+    cudaFree(d_acc);
+    if (e != cudaSuccess) fail(PB200_ERR_CUDA, "energy: %s", cudaGetErrorString(e));
+    for (int b = 0; b < P.B; ++b) { energy[b] = acc[2 * b]; h2[b] = acc[2 * b + 1]; }
+    PB200_CATCH
+}
+
+int pb200_state_overlap(pb200_plan* h, int32_t traj0, int32_t count, const double* phi, double* out) {
+    PB200_TRY
+    if (!h || !phi || !out) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
+    CUDA_CHECK(cudaSetDevice(P.desc.device));
+    c2* d_phi = P.buf[(P.cur + 1) % 3];
+    CUDA_CHECK(cudaMemcpyAsync(d_phi, phi, sizeof(c2) * (size_t)P.D, cudaMemcpyHostToDevice, P.stream));
+    double* d_acc = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_acc, sizeof(double) * 2 * count));
+    CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * count, P.stream));
+    const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
+    dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
+    overlap_kernel<<<grid, 256, 0, P.stream>>>(d_phi, P.buf[P.cur] + (size_t)traj0 * P.D, P.D, d_acc);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_acc, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost, P.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
+    cudaFree(d_acc);
+    if (e != cudaSuccess) fail(PB200_ERR_CUDA, "overlap: %s", cudaGetErrorString(e));
+    PB200_CATCH
+}
+
 int pb200_state_sample(pb200_plan* h, int32_t traj, int32_t one_digit, const double* uniforms, int32_t n_shots,
                        int64_t* out) {
     PB200_TRY

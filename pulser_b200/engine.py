@@ -233,6 +233,32 @@ class DevicePlan:
         check(lib.pb200_state_occupation(self._handle, traj0, count, int(digit), _p(out)))
         return out
 
+    def correlation(self, digit: int, traj0: int = 0, count: int | None = None) -> np.ndarray:
+        """``<n_i n_j>`` with ``n_k = |digit><digit|``, ``[count, N, N]`` (device reduction;
+        CorrelationMatrix observable, ``pulser/backend/default_observables.py:331-394``)."""
+        count = self.n_traj - traj0 if count is None else count
+        out = np.empty((count, self.n, self.n), dtype=np.float64)
+        check(lib.pb200_state_correlation(self._handle, traj0, count, int(digit), _p(out)))
+        return out
+
+    def energy(self, t_us: float) -> tuple[np.ndarray, np.ndarray]:
+        """``(<H(t)>, <H(t)^2>)`` of every trajectory, one H-apply + one fused dot on the
+        device (Energy / EnergyVariance / EnergySecondMoment, ``default_observables.py:431-561``)."""
+        e = np.empty(self.n_traj, dtype=np.float64)
+        e2 = np.empty(self.n_traj, dtype=np.float64)
+        check(lib.pb200_state_energy(self._handle, float(t_us), _p(e), _p(e2)))
+        return e, e2
+
+    def overlap(self, phi: np.ndarray, traj0: int = 0, count: int | None = None) -> np.ndarray:
+        """``<phi|psi_b>`` (complex) for the selected trajectories (Fidelity observable)."""
+        count = self.n_traj - traj0 if count is None else count
+        v = np.ascontiguousarray(np.asarray(phi, dtype=np.complex128).reshape(-1))
+        if v.shape[0] != self.D:
+            raise ValueError(f"state of length {v.shape[0]}, expected {self.D}")
+        out = np.empty((count, 2), dtype=np.float64)
+        check(lib.pb200_state_overlap(self._handle, traj0, count, _p(v.view(np.float64)), _p(out)))
+        return out[:, 0] + 1j * out[:, 1]
+
     def sample(self, n_samples: int, one_state: str, traj: int = 0) -> "Counter[str]":
         """Bitstring samples of trajectory ``traj`` drawn on the device with the
         reference's recipe and the global ``np.random`` stream

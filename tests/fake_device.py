@@ -51,6 +51,42 @@ class FakeDevicePlan:
         res = B200Result(tuple(range(spec.n_qudits)), meas, StateVector(self.states[traj]), matching)
         return res.get_samples(n_samples)
 
+    # --- device reductions used by DeviceStateView (numpy stand-ins) ---
+    @property
+    def n(self):
+        return self.specs[0].n_qudits
+
+    def norm2(self):
+        return np.array([np.vdot(s, s).real for s in self.states])
+
+    def _digits(self):
+        spec = self.specs[0]
+        idx = np.arange(spec.hilbert_dim)
+        return [(idx // spec.dim ** (spec.n_qudits - 1 - k)) % spec.dim for k in range(spec.n_qudits)]
+
+    def occupation(self, digit, traj0=0, count=None):
+        return np.stack([np.diagonal(c) for c in self.correlation(digit, traj0, count)])
+
+    def correlation(self, digit, traj0=0, count=None):
+        count = len(self.states) - traj0 if count is None else count
+        dg = self._digits()
+        out = np.zeros((count, self.n, self.n))
+        for c in range(count):
+            p = np.abs(self.states[traj0 + c]) ** 2
+            for i in range(self.n):
+                for j in range(self.n):
+                    out[c, i, j] = p[(dg[i] == digit) & (dg[j] == digit)].sum()
+        return out
+
+    def energy(self, t_us):
+        hs = [h.matrix_at(t_us, self.order) @ s for h, s in zip(self.hams, self.states)]
+        return (np.array([np.vdot(s, w).real for s, w in zip(self.states, hs)]),
+                np.array([np.vdot(w, w).real for w in hs]))
+
+    def overlap(self, phi, traj0=0, count=None):
+        count = len(self.states) - traj0 if count is None else count
+        return np.array([np.vdot(phi, self.states[traj0 + c]) for c in range(count)])
+
     def apply_h(self, t_us, vec, traj=0):
         return self.hams[traj].matrix_at(t_us, self.order) @ np.asarray(vec, dtype=complex)
 

@@ -105,3 +105,85 @@ def test_config_validation(backend):
         backend.B200Config(solver="rk4")
     with pytest.raises(TypeError, match="must be an instance of `B200State`"):
         backend.B200Config(initial_state=np.ones(4))
+
+
+def test_streaming_observables_match_host_formulas(backend, monkeypatch):
+    """Noiseless runs hand the observables a device-resident state (``DeviceStateView``): every default observable
+    of pulser/backend/default_observables.py must give what the plain matrix formulas give on the oracle states."""
+    from pulser.backend.default_observables import (
+        BitStrings, CorrelationMatrix, Energy, EnergySecondMoment, EnergyVariance, Expectation, Fidelity,
+        Occupation, StateResult)
+
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    seq = _seq(n=3, duration=240)
+    eig = ("r", "g")
+    S, O = backend.B200State, backend.B200Operator
+    target = S.from_state_amplitudes(eigenstates=eig, amplitudes={"rgg": 1.0, "grg": 1.0, "ggr": 1.0})
+    target = S(target.to_array() / np.sqrt(3), eigenstates=eig)
+    sx0 = O.from_operator_repr(eigenstates=eig, n_qudits=3, operations=[(1.0, [({"rg": 1.0, "gr": 1.0}, {0})])])
+    sx0.to_array()  # a general operator: its matrix is legitimately needed (host fallback); build it up front
+    times = [0.25, 1.0]
+    cfg = backend.B200Config(observables=[
+        Occupation(evaluation_times=times), CorrelationMatrix(evaluation_times=times),
+        Energy(evaluation_times=times), EnergyVariance(evaluation_times=times),
+        EnergySecondMoment(evaluation_times=times), Fidelity(target, evaluation_times=times),
+        Expectation(sx0, evaluation_times=times), BitStrings(evaluation_times=[1.0], num_shots=50),
+        StateResult(evaluation_times=[1.0])])
+    np.random.seed(5)
+    built = []
+    orig = backend.B200Operator._as_matrix
+    monkeypatch.setattr(backend.B200Operator, "_as_matrix", staticmethod(lambda op: (built.append(1), orig(op))[1]))
+    res = backend.B200Backend(seq, config=cfg).run()
+    monkeypatch.undo()
+    # number operators / identity were never turned into matrices during the run
+    assert len(built) == 0
+    sim = backend.B200Emulator.from_sequence(seq)
+    spec = sim._noiseless_spec()
+    H = OracleHamiltonian.from_spec(spec)
+    T = spec.sampling_times[-1]
+    states = evolve.sesolve(H, evolve.all_ground_state(spec), [0.0, 0.25 * T, T], rtol=1e-11, atol=1e-13)[1:]
+    idx = np.arange(8)
+    is_r = [((idx >> (2 - k)) & 1) == 0 for k in range(3)]
+    for t_rel, st in zip(times, states):
+        st = st / np.linalg.norm(st)
+        p = np.abs(st) ** 2
+        corr = np.array([[p[is_r[i] & is_r[j]].sum() for j in range(3)] for i in range(3)])
+        np.testing.assert_allclose(np.asarray(res.get_result("occupation", t_rel), dtype=float), np.diag(corr), atol=1e-7)
+        np.testing.assert_allclose(np.asarray(res.get_result("correlation_matrix", t_rel), dtype=float), corr, atol=1e-7)
+        hm = H.matrix_at(t_rel * T)
+        e, e2 = np.vdot(st, hm @ st).real, np.vdot(hm @ st, hm @ st).real
+        assert float(np.real(res.get_result("energy", t_rel))) == pytest.approx(e, abs=1e-6)
+        assert float(np.real(res.get_result("energy_second_moment", t_rel))) == pytest.approx(e2, abs=1e-5)
+        assert float(np.real(res.get_result("energy_variance", t_rel))) == pytest.approx(e2 - e * e, abs=1e-5)
+        assert float(res.get_result("fidelity", t_rel)) == pytest.approx(abs(np.vdot(target.to_array(), st)) ** 2, abs=1e-7)
+        sx = np.vdot(st, sx0.to_array() @ st).real
+        assert float(np.real(res.get_result("expectation", t_rel))) == pytest.approx(sx, abs=1e-7)
+    assert sum(res.final_bitstrings.values()) == 50
+    np.testing.assert_allclose(res.final_state.to_array(), states[-1] / np.linalg.norm(states[-1]), atol=1e-7)
+
+
+def test_projector_patterns(backend):
+    """Products / multiples of number operators keep their 'projector pattern' (what lets a device-resident state
+    answer them with one reduction); everything else drops it."""
+    O = backend.B200Operator
+    eig = ("r", "g", "h")
+
+    def num(i, letter="r", c=1.0):
+        return O.from_operator_repr(eigenstates=eig, n_qudits=3, operations=[(c, [({letter * 2: 1.0}, {i})])])
+
+    assert num(0)._pattern == (1.0, "r", frozenset({0}))
+    assert (num(0) @ num(2))._pattern == (1.0, "r", frozenset({0, 2}))
+    assert (2.0 * num(1, c=0.5))._pattern == (1.0, "r", frozenset({1}))
+    assert (num(0) @ num(1, "h"))._pattern is None          # different eigenstates: not one projector
+    assert (num(0) + num(1))._pattern is None
+    ident = O.from_operator_repr(eigenstates=eig, n_qudits=3, operations=[(1.0, [])])
+    assert ident._pattern == (1.0, None, frozenset())
+    assert (ident @ num(1))._pattern == (1.0, "r", frozenset({1}))
+    flip = O.from_operator_repr(eigenstates=eig, n_qudits=3, operations=[(1.0, [({"rg": 1.0}, {0})])])
+    assert flip._pattern is None
+    # lazily built matrices still agree with the eager formulas
+    v = np.zeros(27, dtype=complex); v[0 * 9 + 1 * 3 + 0] = 1.0  # |r g r>
+    st = backend.B200State(v, eigenstates=eig)
+    assert (num(0) @ num(2)).expect(st) == pytest.approx(1.0) and (num(0) @ num(1)).expect(st) == pytest.approx(0.0)

@@ -407,7 +407,7 @@ def test_xy_apply_h(engine, n, local_rows):
             assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
 
 
-@pytest.mark.parametrize("n,integrator", [(4, "chebyshev"), (7, "chebyshev"), (7, "lanczos"), (9, "auto")])
+@pytest.mark.parametrize("n,integrator", [(4, 1), (7, 1), (7, 2), (9, 0)])  # 0 auto, 1 Chebyshev, 2 Lanczos
 def test_xy_evolution_vs_oracle(engine, n, integrator):
     from oracle import evolve
 
@@ -450,3 +450,81 @@ def test_xy_batch_with_missing_atoms(engine):
         got = plan.get_state()
     for b, s in enumerate(specs):
         assert np.max(np.abs(got[b] - _oracle_final(s, psi0))) < STATE_TOL
+
+
+@pytest.mark.parametrize("builder", [
+    lambda: W.config_c2(n=10, seed=4),
+    lambda: W.config_c3(n=5),
+    lambda: random_local_spec(9, T=80, seed=3),
+    lambda: W.config_xy(n=7, seed=1, t_total=80),
+])
+def test_device_observable_reductions(engine, builder):
+    """pb200_state_correlation / _energy / _overlap against the plain formulas on the downloaded state
+    (CorrelationMatrix, Energy*, Fidelity of pulser/backend/default_observables.py)."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    spec = builder()
+    D, n, d = spec.hilbert_dim, spec.n_qudits, spec.dim
+    mf = MatFreeHamiltonian(spec)
+    psi = random_state(D, 11) * 1.3          # not normalised on purpose
+    phi = random_state(D, 12)
+    idx = np.arange(D)
+    digits = [(idx // d ** (n - 1 - k)) % d for k in range(n)]
+    t = float(spec.sampling_times[len(spec.sampling_times) // 3]) + 1e-4
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state(psi)
+        p = np.abs(psi) ** 2
+        for digit in range(d):
+            corr = plan.correlation(digit)[0]
+            ref = np.array([[p[(digits[i] == digit) & (digits[j] == digit)].sum() for j in range(n)] for i in range(n)])
+            assert np.max(np.abs(corr - ref)) < 1e-12 * p.sum()
+            assert np.max(np.abs(np.diag(corr) - plan.occupation(digit)[0])) < 1e-12 * p.sum()
+        e, e2 = plan.energy(t)
+        hpsi = mf.apply(t, psi)
+        assert abs(e[0] - np.vdot(psi, hpsi).real) < 1e-11 * max(1.0, abs(np.vdot(hpsi, hpsi).real) ** 0.5)
+        assert abs(e2[0] - np.vdot(hpsi, hpsi).real) < 1e-11 * max(1.0, np.vdot(hpsi, hpsi).real)
+        ov = plan.overlap(phi)[0]
+        assert abs(ov - np.vdot(phi, psi)) < 1e-12
+        assert np.max(np.abs(plan.get_state()[0] - psi)) == 0.0   # the reductions leave the state untouched
+
+
+def test_device_observables_full_size(engine):
+    """N = 20: no oracle matrix; consistency of the device reductions among themselves."""
+    spec = W.config_c2(n=20)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, 0.4)
+        corr = plan.correlation(0)[0]
+        occ = plan.occupation(0)[0]
+        nrm = plan.norm2()[0]
+        assert np.max(np.abs(np.diag(corr) - occ)) < 1e-12
+        assert np.all(corr <= np.minimum.outer(occ, occ) + 1e-12) and np.all(corr >= -1e-15)
+        assert np.allclose(corr, corr.T, atol=0)
+        e, e2 = plan.energy(0.4)
+        assert e2[0] >= e[0] ** 2 / nrm - 1e-9           # Cauchy-Schwarz: <H^2> >= <H>^2
+        psi = plan.get_state()[0]
+        assert abs(plan.overlap(psi)[0] - nrm) < 1e-11
+        hpsi = plan.apply_h(0.4, psi)
+        assert abs(e[0] - np.vdot(psi, hpsi).real) < 1e-9 and abs(e2[0] - np.vdot(hpsi, hpsi).real) < 1e-8
+
+
+def test_xy_with_leakage_level(engine):
+    """XY eigenbasis (u, d, x): d = 3 with the flip-flop term (leakage NoiseModel shape, hamiltonian_data.py:927-931)."""
+    from oracle import evolve
+    from oracle.matfree import MatFreeHamiltonian
+
+    spec = W.config_xy(n=5, seed=2, t_total=150, local_rows=True)
+    spec.dim = 3
+    spec.eigenbasis = ["u", "d", "x"]
+    spec.basis_name = "XY_with_error"
+    spec.collapse_ops = np.zeros((0, 3, 3), dtype=np.complex128)
+    mf = MatFreeHamiltonian(spec)
+    v = random_state(spec.hilbert_dim, 8)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        got = plan.apply_h(0.0313, v)
+        assert np.max(np.abs(got - mf.apply(0.0313, v))) < 1e-12 * np.max(np.abs(got))
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1])
+        assert np.max(np.abs(plan.get_state()[0] - ref)) < STATE_TOL
