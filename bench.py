@@ -284,8 +284,10 @@ def run_gpu(args) -> None:
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "h_applies_per_launch": applies_per_launch,
                          "avg_launch_us": per_launch_s * 1e6,
-                         "note": "CUDA-event time of the propagation / launches (includes launch gaps); "
-                                 "the 16 MiB state is L2-resident, DRAM traffic per launch is far below the algorithmic bytes"},
+                         "note": "achieved = algorithmic bytes / (CUDA-event time of the propagation / launches), launch "
+                                 "gaps included; traffic = dram read+write per launch from the committed ncu --set full "
+                                 "capture (profiles/r01_stage_kernel_summary.json): two-chain launches (2 H-applies, 83.9 MB "
+                                 "algorithmic), cold L2 at every ncu replay; in the timed run the 16 MiB state stays L2-resident"},
         }
         if os.environ.get("PB200_BENCH_SKIP_CPU", "0") != "1":
             n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "25" if N_ATOMS >= 20 else "400"))
