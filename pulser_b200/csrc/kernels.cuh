@@ -115,6 +115,11 @@ struct StageArgs {
     const double* beta_dev;  // Lanczos: c_b2 = -beta_dev[traj] read on the device (nullptr: use coef.c_b2)
     double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<v, out>, acc[traj][1] += <out, out> (fused reductions)
     int swz;  // > 0: number of tile-id bits, tile order bit-reversed (L2 locality of high-bit partners)
+    // partner-sum forwarding (FWD kernels): w_in[s] = drive-weighted sum of v over the flips this stage does not
+    // perform itself (computed by the producer of v, whose tile was closed under them); w_out: the same sum of
+    // `out` over THIS stage's tile flips, for the consumer.  Both may alias (own-element read, then write).
+    const c2* w_in;
+    c2* w_out;
     int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
 };
 
@@ -269,29 +274,16 @@ __device__ __forceinline__ c2 ld_own(const c2* p) {
     return {r.x, r.y};
 }
 
-// `ring` (optional): two tile-sized shared-memory slots through which the out-of-tile partner tiles are
-// streamed by TMA (slots 0 and 1 already hold / are receiving the partners of the first two extra bits when
-// this function is entered); `rbar` their mbarriers.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false>
-__device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* __restrict__ tile,
-                                                const double* __restrict__ tab, long long base, long long traj,
-                                                int tid, c2* ring = nullptr, uint64_t* rbar = nullptr) {
+// In-tile partner sums of the R = 2^RB amplitudes a thread owns (tile index t = tid + r*NT): flips of the
+// register-block bits (tile bits TBITS-RB .. TBITS-1) are register moves, flips of the tile bits
+// [jstart, TBITS-RB) are independent LDS.128 from `tile`.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+__device__ __forceinline__ void rb_tile_gather(const PassGeom& g, const c2* tile, const double* __restrict__ tab, int tid,
+                                               int to_bit, int jstart, bool skip_smem, const c2 (&v)[1 << RB],
+                                               double (&pr)[1 << RB], double (&pi)[1 << RB], double (&qr)[1 << RB],
+                                               double (&qi)[1 << RB]) {
     constexpr int R = 1 << RB;
     constexpr int NT = 1 << (TBITS - RB);
-    const long long voff = traj * a.D;
-    const c2* vsrc = a.v + voff;
-    const long long lomask = (1LL << g.lo_bits) - 1;
-    const int to_bit = a.to_bit;
-    // first tile bit whose flip belongs to this pass (pass A: 0, later passes: lo_bits)
-    const int jstart = __ffs(g.tile_flip_mask) - 1;
-
-    c2 v[R];
-    double pr[R], pi[R], qr[R], qi[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        v[r] = tile[tid + r * NT];
-        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
-    }
     // --- flips inside the register block (tile bits TBITS-RB .. TBITS-1) ---
 #pragma unroll
     for (int q = 0; q < RB; ++q) {
@@ -320,7 +312,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
     // --- flips served from shared memory ---
 #pragma unroll
     for (int j = 0; j < TBITS - RB; ++j) {
-        if (j >= jstart && !(a.dbg & 1)) {
+        if (j >= jstart && !skip_smem) {
             const int bit = (tid >> j) & 1;
             const int ptid = tid ^ (1 << j);
             double gx = 0.0, gy = 0.0;
@@ -343,6 +335,33 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
             }
         }
     }
+}
+
+// `ring` (optional): two tile-sized shared-memory slots through which the out-of-tile partner tiles are
+// streamed by TMA (slots 0 and 1 already hold / are receiving the partners of the first two extra bits when
+// this function is entered); `rbar` their mbarriers.
+// FWD: partner-sum forwarding (a.w_in / a.w_out, see StageArgs); the tile buffer is reused for the results.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false, bool FWD = false>
+__device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, c2* tile,
+                                                const double* __restrict__ tab, long long base, long long traj,
+                                                int tid, c2* ring = nullptr, uint64_t* rbar = nullptr) {
+    constexpr int R = 1 << RB;
+    constexpr int NT = 1 << (TBITS - RB);
+    const long long voff = traj * a.D;
+    const c2* vsrc = a.v + voff;
+    const long long lomask = (1LL << g.lo_bits) - 1;
+    const int to_bit = a.to_bit;
+    // first tile bit whose flip belongs to this pass (pass A: 0, later passes: lo_bits)
+    const int jstart = __ffs(g.tile_flip_mask) - 1;
+
+    c2 v[R];
+    double pr[R], pi[R], qr[R], qi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        v[r] = tile[tid + r * NT];
+        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
+    }
+    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, (a.dbg & 1) != 0, v, pr, pi, qr, qi);
     // global index of each owned amplitude
     long long idx[R];
 #pragma unroll
@@ -444,6 +463,10 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 dv[r] = dsrc ? __ldcs(dsrc + idx[h0 + r]) : 0.0;
                 pv[r] = a.psi ? ld_own<COH>(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
                 bv[r] = a.b2 ? ld_own<COH>(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                if (FWD && a.w_in) {  // forwarded partner sums of the flips this stage does not perform
+                    const c2 wv = ld_own<COH>(a.w_in + voff + idx[h0 + r]);
+                    pr[h0 + r] += wv.x; pi[h0 + r] += wv.y;
+                }
             }
 #pragma unroll
             for (int r = 0; r < H; ++r) {
@@ -463,6 +486,28 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 dot0 = fma(v[rr].x, res.x, dot0); dot0 = fma(v[rr].y, res.y, dot0);
                 dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
                 if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
+                if (FWD) v[rr] = res;  // kept for the forwarded partner sums below
+            }
+        }
+        if (FWD && a.w_out) {
+            // Partner sums of the RESULT over this tile's flips, for the next Clenshaw stage (whose tile is
+            // closed under the complementary bits): the tile buffer now receives the results.
+            __syncthreads();  // every thread has finished gathering the input tile
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                tile[tid + r * NT] = v[r];
+                pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
+            }
+            __syncthreads();
+            rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                c2 wsum = {pr[r], pi[r]};
+                if (UNIFORM) {
+                    wsum.x = a.u.g.x * pr[r]; wsum.y = a.u.g.x * pi[r];
+                    if (!REAL_G) { wsum.x = fma(-a.u.g.y, qi[r], wsum.x); wsum.y = fma(a.u.g.y, qr[r], wsum.y); }
+                }
+                st_c2(a.w_out + voff + idx[r], wsum);
             }
         }
     } else {
@@ -518,7 +563,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // amplitude, all independent (fully unrolled) so that the shared-memory pipe
 // stays full.  Shared-memory operand traffic per amplitude and pass is
 // (flipped tile bits - RB + 1) x 16 B.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool FWD = false>
 __global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
 stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
     constexpr int NT = 1 << (TBITS - RB);
@@ -568,7 +613,7 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
             tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
         mbar_wait(&mbar, 0);
     }
-    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
+    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB, false, FWD>(a, g, tile, tab, base, traj, tid);
 }
 
 // ---- d = 2 single-pass stage kernel with TMA-streamed partner tiles ----------------------------------------------

@@ -126,6 +126,12 @@ struct Plan {
     std::vector<double> thresholds;               // per trajectory
     std::vector<long long> jump_count;
     bool use_pdl = true;
+    // partner-sum forwarding between Clenshaw stages (kernels.cuh, FWD): geometry of the first stage of an
+    // exponential [0], of the odd stages [1] (high-bit tile) and of the later even stages [2]
+    int use_fwd = -1;               // PB200_FWD: 1 on, 0 off, -1 auto (state small enough to live in L2)
+    bool fwd_now = false;           // decided per propagate call
+    PassGeom fwd_geo[3];
+    c2* wbuf[2] = {nullptr, nullptr};  // forwarded sums, one vector per chain
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -214,6 +220,8 @@ struct StageIO {  // one Clenshaw stage of one chain
     StageCoef coef; UniformDrive ud; const double* table; bool real_g;
     const double* beta_dev = nullptr;
     double* dot_acc = nullptr;  // fused <v,out>, <out,out> (only honoured by the register-blocked d=2 kernels)
+    // partner-sum forwarding: stage index inside its exponential and whether another stage follows
+    int stage_idx = 0; bool has_next = false; c2* wbuf = nullptr;
 };
 
 static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io, bool geo_is_last = true) {
@@ -354,6 +362,76 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             ++launches;
         }
     }
+}
+
+// ---- partner-sum forwarding ------------------------------------------------------------------------------------
+// Inside one exponential the Clenshaw stages alternate between two tile geometries whose flip sets are
+// complementary: A = the low TB bits, B = the hb bits above them (plus TB - hb low bits that only fill the tile).
+// A stage gathers its own tile's flips from shared memory, receives the complementary sums from the stage that
+// produced its input (w_in) and emits the sums of its result over its own flips (w_out): no out-of-tile partner
+// loads at all (the 9 x 16 B per amplitude that bound the single-pass kernel at the L2 -> SM limit become
+// 2 x 16 B of streaming traffic).  Bits above TB + hb, if any, stay global partner loads; the first stage of an
+// exponential has no producer and is the ordinary single-pass stage (it only emits).
+static bool fwd_eligible(const Plan& P, const std::vector<PassGeom>& passes) {
+    if (!is_d2path(P) || P.force_v1 || P.reg_bits != 3 || P.use_pipe || P.use_stream) return false;
+    if (P.tile_bits != 11 && P.tile_bits != 12) return false;
+    if (passes.size() != 1 || passes[0].hi_bits != 0 || passes[0].lo_bits != P.tile_bits) return false;
+    if (P.n - P.tile_bits < 3) return false;  // the register block of the B tile must consist of flipped bits
+    if ((long long)P.B * 2 > 65535) return false;
+    if (P.use_fwd >= 0) return P.use_fwd != 0;
+    return (double)P.D * P.B * 16.0 <= (double)env_int("PB200_FWD_MIB", 64) * 1048576.0;
+}
+
+static void plan_fwd_geometry(Plan& P) {
+    const int N = P.n, TB = P.tile_bits;
+    const int hb = std::min(N - TB, TB - 2);
+    const unsigned long long all = (N >= 64) ? ~0ULL : ((1ULL << N) - 1ULL);
+    const unsigned long long rest = all & ~((1ULL << (TB + hb)) - 1ULL);
+    PassGeom a{};
+    a.n_bits = N; a.lo_bits = TB; a.hi_shift = TB; a.hi_bits = 0; a.first_pass = 1;
+    a.tile_flip_mask = (1u << TB) - 1u;
+    a.extra_mask = all & ~((1ULL << TB) - 1ULL);
+    P.fwd_geo[0] = a;
+    a.extra_mask = rest;
+    P.fwd_geo[2] = a;
+    PassGeom b{};
+    b.n_bits = N; b.lo_bits = TB - hb; b.hi_shift = TB; b.hi_bits = hb; b.first_pass = 1;
+    b.tile_flip_mask = ((1u << hb) - 1u) << b.lo_bits;
+    b.extra_mask = rest;
+    P.fwd_geo[1] = b;
+}
+
+static void launch_stage_fwd(Plan& P, const StageIO* io, int n, bool uniform, long long& launches) {
+    bool real_g = true;
+    for (int c = 0; c < n; ++c) real_g = real_g && io[c].real_g;
+    const int tbits = P.tile_bits;
+    const long long tiles = P.D >> tbits;
+    const int tsize = 1 << tbits;
+    const size_t tab_bytes = uniform ? 0 : (size_t)d2_table_stride(P.n) * 8;
+    StageArgs2 m{};
+    for (int c = 0; c < n; ++c) {
+        const int role = (io[c].stage_idx == 0) ? 0 : ((io[c].stage_idx & 1) ? 1 : 2);
+        m.a[c] = make_stage_args(P, P.fwd_geo[role], io[c], true);
+        m.a[c].swz = 0;
+        m.a[c].w_in = (io[c].stage_idx > 0) ? io[c].wbuf : nullptr;
+        m.a[c].w_out = io[c].has_next ? io[c].wbuf : nullptr;
+    }
+    m.n_traj = P.B;
+    dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
+    const int threads = tsize >> 3;
+    const size_t smem = (size_t)tsize * 16 + tab_bytes;
+#define PB200_LAUNCH_FWD(TB)                                                                                   \
+    do {                                                                                                       \
+        if (uniform) {                                                                                         \
+            if (real_g) launch_k(stage_d2_rb_kernel<true, true, TB, 3, true>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);   \
+            else launch_k(stage_d2_rb_kernel<true, false, TB, 3, true>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);         \
+        } else {                                                                                               \
+            launch_k(stage_d2_rb_kernel<false, false, TB, 3, true>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);             \
+        }                                                                                                      \
+    } while (0)
+    if (tbits == 11) PB200_LAUNCH_FWD(11); else PB200_LAUNCH_FWD(12);
+#undef PB200_LAUNCH_FWD
+    ++launches;
 }
 
 static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
@@ -514,6 +592,7 @@ struct Chain {
         io.ud = prog->ud[e];
         io.table = uniform ? nullptr : P.d_table + table_base + prog->offset[e];
         io.real_g = prog->real_g[e] != 0;
+        io.stage_idx = (int)a.size() - 2 - j; io.has_next = (j > 0);
         // shift the recurrence
         if (b1_buf == psi) { b2_kind = 2; kappa = b1_scale; b2_buf = nullptr; }
         else { b2_kind = 1; b2_buf = const_cast<c2*>(b1_buf); }
@@ -548,6 +627,9 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
     }
     long long launches = 0;
     StageIO io[2];
+    if (P.fwd_now)
+        for (int c = 0; c < n; ++c)
+            if (!P.wbuf[c]) CUDA_CHECK(cudaMalloc(&P.wbuf[c], sizeof(c2) * (size_t)P.D * P.B));
     if (P.has_diss && n != 1) fail(PB200_ERR_STATE, "internal: Lindblad splitting runs one chain at a time");
     while (true) {
         int k = 0;
@@ -559,10 +641,12 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
                     if (chains[c].j < 0 && chains[c].prog->pre_diss[e_before] > 0.0)
                         apply_dissipator(P, chains[c].psi, chains[c].prog->pre_diss[e_before], launches);
                 }
+                io[k].wbuf = P.wbuf[c];
                 chains[c].next(P, uniform, io[k++]);
             }
         if (k == 0) break;
-        launch_stage_multi(P, passes, io, k, uniform, launches);
+        if (P.fwd_now) launch_stage_fwd(P, io, k, uniform, launches);
+        else launch_stage_multi(P, passes, io, k, uniform, launches);
         if (P.has_diss && chains[0].e != e_before && chains[0].prog->post_diss[e_before] > 0.0)
             apply_dissipator(P, chains[0].psi, chains[0].prog->post_diss[e_before], launches);
     }
@@ -1185,6 +1269,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
+    P.fwd_now = false;
     if (P.has_collapse) { propagate_mcwf(P, t_start, t_stop, o, stats); return; }
     const double gtol = (o && o->tol != 0.0) ? o->tol : (P.has_diss ? 1e-6 : 1e-8);
     // Richardson extrapolation: on by default (extrapolate = 0 or 1), -1 switches it off
@@ -1276,6 +1361,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
                                         : env_int("PB200_RHO_CAP_MILLI", 3600) * 1e-3;
     P.coop_passes = plan_passes(P.n, 11, env_int("PB200_COOP_EXTRA", 0));
     P.coop_now = coop_eligible(P, P.coop_passes);
+    P.fwd_now = !P.coop_now && !P.use_krylov && fwd_eligible(P, passes);
+    if (P.fwd_now) plan_fwd_geometry(P);
     const bool dual_ok = (dual_chain_ok(P, passes) || P.coop_now) && !P.has_diss && !P.use_krylov;
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
     // a symmetric 2nd-order scheme whatever the order of its unitary part
@@ -1603,6 +1690,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
     P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
+    P.use_fwd = env_int("PB200_FWD", -1);
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;
@@ -1662,6 +1750,8 @@ int pb200_plan_destroy(pb200_plan* h) {
     for (int i = 0; i < 6; ++i)
         if (P.aux[i]) cudaFree(P.aux[i]);
     if (P.d_coop) cudaFree(P.d_coop);
+    for (int i = 0; i < 2; ++i)
+        if (P.wbuf[i]) cudaFree(P.wbuf[i]);
     if (P.d_bar) cudaFree(P.d_bar);
     if (P.d_xy) cudaFree(P.d_xy);
     if (P.kry) cudaFree(P.kry);

@@ -528,3 +528,58 @@ def test_xy_with_leakage_level(engine):
         plan.set_state("all-ground")
         plan.propagate(0.0, spec.sampling_times[-1])
         assert np.max(np.abs(plan.get_state()[0] - ref)) < STATE_TOL
+
+
+# ---------------------------------------------------------------------------
+# Partner-sum forwarding between Clenshaw stages (kernels.cuh FWD): the alternating-geometry
+# stages must reproduce the single-pass stages bit for bit up to rounding.
+def _fwd_specs(kind, n):
+    if kind == "uniform-real":
+        return W.config_c2(n=n, seed=3, t_rise=40, t_sweep=80, t_fall=40)
+    if kind == "uniform-complex":
+        amp, det = W.blockade_sweep_waveforms(t_rise=40, t_sweep=80, t_fall=40)
+        phase = 0.3 + 0.004 * np.arange(len(amp))
+        return W.ising_global_spec(W.disc_register(n, 38.0, 5.0, 3), W.C6_LEVEL_60, amp, det, phase=phase)
+    if kind == "local":
+        return random_local_spec(n, T=60, seed=n)
+    if kind == "batch":
+        return [random_local_spec(n, T=60, seed=s) for s in (21, 22)]
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,n,tile_bits", [
+    ("uniform-real", 14, 11), ("uniform-real", 17, 11), ("uniform-real", 20, 11), ("uniform-real", 21, 11),
+    ("uniform-real", 16, 12), ("uniform-complex", 15, 11), ("local", 14, 11), ("local", 16, 12), ("batch", 15, 11),
+])
+def test_partner_sum_forwarding_equals_single_pass(engine, monkeypatch, kind, n, tile_bits):
+    spec = _fwd_specs(kind, n)
+    first = spec[0] if isinstance(spec, list) else spec
+    tf = first.sampling_times[-1]
+    psi0 = random_state(first.hilbert_dim, 5)
+    monkeypatch.setenv("PB200_TILE_BITS", str(tile_bits))
+    out = {}
+    for fwd in (0, 1):
+        monkeypatch.setenv("PB200_FWD", str(fwd))
+        with engine.DevicePlan(spec) as plan:
+            plan.set_state(psi0)
+            st = plan.propagate(0.0, tf)
+            out[fwd] = (plan.get_state().copy(), st)
+    a, b = out[0][0], out[1][0]
+    assert np.max(np.abs(a - b)) < 2e-13
+    assert out[0][1]["n_applies"] == out[1][1]["n_applies"]
+    assert out[0][1]["n_launches"] == out[1][1]["n_launches"]  # one launch per stage either way
+
+
+def test_partner_sum_forwarding_vs_oracle(engine, monkeypatch):
+    """The forwarding path against the tight-tolerance oracle at the smallest eligible register (N = 14)."""
+    from oracle import evolve
+
+    monkeypatch.setenv("PB200_FWD", "1")
+    spec = W.config_c2(n=14, seed=20, t_rise=100, t_sweep=300, t_fall=100)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1])
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
