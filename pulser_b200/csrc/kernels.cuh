@@ -120,6 +120,7 @@ struct StageArgs {
     // `out` over THIS stage's tile flips, for the consumer.  Both may alias (own-element read, then write).
     const c2* w_in;
     c2* w_out;
+    int fwd_flags;  // stage_d2_fwd_kernel: 1/2/4 stage w_in / b2 / psi tiles through TMA, 8 separate result tile, 16 L1 prefetch
     int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
 };
 
@@ -340,9 +341,8 @@ __device__ __forceinline__ void rb_tile_gather(const PassGeom& g, const c2* tile
 // `ring` (optional): two tile-sized shared-memory slots through which the out-of-tile partner tiles are
 // streamed by TMA (slots 0 and 1 already hold / are receiving the partners of the first two extra bits when
 // this function is entered); `rbar` their mbarriers.
-// FWD: partner-sum forwarding (a.w_in / a.w_out, see StageArgs); the tile buffer is reused for the results.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false, bool FWD = false>
-__device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, c2* tile,
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false>
+__device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* tile,
                                                 const double* __restrict__ tab, long long base, long long traj,
                                                 int tid, c2* ring = nullptr, uint64_t* rbar = nullptr) {
     constexpr int R = 1 << RB;
@@ -463,10 +463,6 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 dv[r] = dsrc ? __ldcs(dsrc + idx[h0 + r]) : 0.0;
                 pv[r] = a.psi ? ld_own<COH>(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
                 bv[r] = a.b2 ? ld_own<COH>(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
-                if (FWD && a.w_in) {  // forwarded partner sums of the flips this stage does not perform
-                    const c2 wv = ld_own<COH>(a.w_in + voff + idx[h0 + r]);
-                    pr[h0 + r] += wv.x; pi[h0 + r] += wv.y;
-                }
             }
 #pragma unroll
             for (int r = 0; r < H; ++r) {
@@ -486,28 +482,6 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 dot0 = fma(v[rr].x, res.x, dot0); dot0 = fma(v[rr].y, res.y, dot0);
                 dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
                 if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
-                if (FWD) v[rr] = res;  // kept for the forwarded partner sums below
-            }
-        }
-        if (FWD && a.w_out) {
-            // Partner sums of the RESULT over this tile's flips, for the next Clenshaw stage (whose tile is
-            // closed under the complementary bits): the tile buffer now receives the results.
-            __syncthreads();  // every thread has finished gathering the input tile
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                tile[tid + r * NT] = v[r];
-                pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
-            }
-            __syncthreads();
-            rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                c2 wsum = {pr[r], pi[r]};
-                if (UNIFORM) {
-                    wsum.x = a.u.g.x * pr[r]; wsum.y = a.u.g.x * pi[r];
-                    if (!REAL_G) { wsum.x = fma(-a.u.g.y, qi[r], wsum.x); wsum.y = fma(a.u.g.y, qr[r], wsum.y); }
-                }
-                st_c2(a.w_out + voff + idx[r], wsum);
             }
         }
     } else {
@@ -563,7 +537,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // amplitude, all independent (fully unrolled) so that the shared-memory pipe
 // stays full.  Shared-memory operand traffic per amplitude and pass is
 // (flipped tile bits - RB + 1) x 16 B.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool FWD = false>
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
 __global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
 stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
     constexpr int NT = 1 << (TBITS - RB);
@@ -613,7 +587,209 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
             tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
         mbar_wait(&mbar, 0);
     }
-    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB, false, FWD>(a, g, tile, tab, base, traj, tid);
+    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
+}
+
+// ---- d = 2 stage kernel with partner-sum forwarding and TMA-staged operands ------------------------------------
+// One Clenshaw stage  out = c_psi psi + c_b2 b2 + c_g (Gt v)  on one tile, where the drive partners of the flips
+// outside the tile arrive as forwarded sums w_in (see StageArgs) and the sums of the result over the tile's own
+// flips leave as w_out.  The input tile and (fwd_flags) the own-element operand tiles w_in / b2 / psi are all
+// brought in by TMA bulk copies on ONE mbarrier, so a CTA has a single exposed memory latency; the remaining
+// own-element operands can be prefetched into L1 while the copies are in flight.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
+__global__ void __launch_bounds__(1 << (TBITS - RB), (TBITS == 11 ? 2 : 1))
+stage_d2_fwd_kernel(const __grid_constant__ StageArgs2 m) {
+    constexpr int R = 1 << RB;
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int chain = blockIdx.y / m.n_traj;
+    const StageArgs& a = m.a[chain];
+    const PassGeom g = a.geo;
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y - chain * m.n_traj;
+    const long long base = tile_base_of(g, blockIdx.x);
+    const long long voff = traj * a.D;
+    const int fl = a.fwd_flags;
+
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    c2* nxt = tile + TSIZE;
+    const c2* s_w = nullptr; const c2* s_b2 = nullptr; const c2* s_psi = nullptr;
+    int n_staged = 1;
+    if ((fl & 1) && a.w_in) { s_w = nxt; nxt += TSIZE; ++n_staged; }
+    if ((fl & 2) && a.b2) { s_b2 = nxt; nxt += TSIZE; ++n_staged; }
+    if ((fl & 4) && a.psi) { s_psi = nxt; nxt += TSIZE; ++n_staged; }
+    c2* rtile = tile;
+    if (fl & 8) { rtile = nxt; nxt += TSIZE; }
+    double* tab = reinterpret_cast<double*>(nxt);
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    pdl_wait();
+    pdl_launch_dependents();
+    if (!UNIFORM) {
+        const int stride = d2_table_stride(g.n_bits);
+        const double* src = a.table + traj * stride;
+        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
+    }
+    __syncthreads();
+    {
+        if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)n_staged * (uint32_t)TSIZE * 16u);
+        const int rows = 1 << g.hi_bits;
+        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+        for (int r = tid; r < rows; r += NT) {
+            const long long goff = voff + base + ((long long)r << g.hi_shift);
+            const size_t soff = (size_t)r << g.lo_bits;
+            tma_load_1d(tile + soff, a.v + goff, row_bytes, &mbar);
+            if (s_w) tma_load_1d(const_cast<c2*>(s_w) + soff, a.w_in + goff, row_bytes, &mbar);
+            if (s_b2) tma_load_1d(const_cast<c2*>(s_b2) + soff, a.b2 + goff, row_bytes, &mbar);
+            if (s_psi) tma_load_1d(const_cast<c2*>(s_psi) + soff, a.psi + goff, row_bytes, &mbar);
+        }
+    }
+    const long long lomask = (1LL << g.lo_bits) - 1;
+    // global index of owned amplitude r: the thread's fixed part plus the register-block bits (recomputed on use)
+    const long long fixed = base | (tid & lomask) | ((long long)(tid >> g.lo_bits) << g.hi_shift);
+    int pq[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+        const int j = TBITS - RB + q;
+        pq[q] = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+    }
+    auto idx_of = [&](int r) {
+        long long o = fixed;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) o |= (long long)((r >> q) & 1) << pq[q];
+        return o;
+    };
+    const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
+    if (fl & 16) {  // own-element operands that are not staged: pull their lines into L1 behind the bulk copies
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (dsrc) prefetch_l1(dsrc + idx_of(r));
+            if (a.psi && !s_psi) prefetch_l1(a.psi + voff + idx_of(r));
+            if (a.b2 && !s_b2) prefetch_l1(a.b2 + voff + idx_of(r));
+            if (a.w_in && !s_w) prefetch_l1(a.w_in + voff + idx_of(r));
+        }
+    }
+    mbar_wait(&mbar, 0);
+
+    const int to_bit = a.to_bit;
+    const int jstart = __ffs(g.tile_flip_mask) - 1;
+    c2 v[R];
+    double pr[R], pi[R], qr[R], qi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        v[r] = tile[tid + r * NT];
+        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
+    }
+    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
+    // flips of the bits above both tile geometries (large registers only): coalesced partner loads
+    for (unsigned long long em = g.extra_mask; em; em &= em - 1) {
+        const int p = __ffsll((long long)em) - 1;
+        double gx = 0.0, gyt = 0.0;
+        if (!UNIFORM) { gx = tab[2 * p]; gyt = tab[2 * p + 1]; }
+        const int bit = (int)((base >> p) & 1);
+        const double sg = (bit == to_bit) ? 1.0 : -1.0;
+        const double gy = (bit == to_bit) ? gyt : -gyt;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + voff + (idx_of(r) ^ (1LL << p))));
+            if (UNIFORM) {
+                pr[r] += raw.x; pi[r] += raw.y;
+                if (!REAL_G) { qr[r] = fma(sg, raw.x, qr[r]); qi[r] = fma(sg, raw.y, qi[r]); }
+            } else {
+                pr[r] = fma(gx, raw.x, pr[r]); pr[r] = fma(-gy, raw.y, pr[r]);
+                pi[r] = fma(gx, raw.y, pi[r]); pi[r] = fma(gy, raw.x, pi[r]);
+            }
+        }
+    }
+    // diagonal parameters
+    double w = 0.0, gamma = 0.0, th_common = 0.0;
+    double th_r[R];
+    if (UNIFORM) { w = a.u.w; gamma = a.u.gamma; }
+    else {
+        w = tab[3 * g.n_bits]; gamma = tab[3 * g.n_bits + 1];
+        for (int p = 0; p < g.n_bits; ++p) {
+            const int bit = (int)((fixed >> p) & 1);
+            th_common += (bit == a.from_is_one) ? tab[2 * g.n_bits + p] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int j = TBITS - RB + q;
+                const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+                const double th = tab[2 * g.n_bits + p];
+                const int bit = (r >> q) & 1;
+                acc += ((bit == a.from_is_one) ? th : 0.0) - ((0 == a.from_is_one) ? th : 0.0);
+            }
+            th_r[r] = acc;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (UNIFORM) {
+            const double dx = a.u.g.x * pr[r], dy = a.u.g.x * pi[r];
+            if (!REAL_G) { pr[r] = fma(-a.u.g.y, qi[r], dx); pi[r] = fma(a.u.g.y, qr[r], dy); }
+            else { pr[r] = dx; pi[r] = dy; }
+        }
+    }
+    constexpr int H = (R >= 4) ? R / 2 : R;
+#pragma unroll
+    for (int h0 = 0; h0 < R; h0 += H) {
+        double dv[H];
+        c2 pv[H], bv[H], wv[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const int rr = h0 + r;
+            const int t = tid + rr * NT;
+            dv[r] = dsrc ? __ldcs(dsrc + idx_of(rr)) : 0.0;
+            pv[r] = s_psi ? s_psi[t] : (a.psi ? ld_own<false>(a.psi + voff + idx_of(rr)) : c2{0.0, 0.0});
+            bv[r] = s_b2 ? s_b2[t] : (a.b2 ? ld_own<false>(a.b2 + voff + idx_of(rr)) : c2{0.0, 0.0});
+            wv[r] = s_w ? s_w[t] : (a.w_in ? ld_own<false>(a.w_in + voff + idx_of(rr)) : c2{0.0, 0.0});
+        }
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const int rr = h0 + r;
+            double diag = fma(w, dv[r], -gamma);
+            if (UNIFORM) {
+                const int ones = __popcll((unsigned long long)idx_of(rr));
+                const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
+                diag = fma(-a.u.theta, (double)cnt, diag);
+            } else {
+                diag -= th_common + th_r[rr];
+            }
+            const c2 gv = {fma(diag, v[rr].x, pr[rr] + wv[r].x), fma(diag, v[rr].y, pi[rr] + wv[r].y)};
+            c2 res = cmul(a.coef.c_g, gv);
+            res = cadd(res, cmul(a.coef.c_psi, pv[r]));
+            res = cadd(res, cmul(a.coef.c_b2, bv[r]));
+            st_c2(a.out + voff + idx_of(rr), res);
+            v[rr] = res;
+        }
+    }
+    if (a.w_out) {
+        if (rtile == tile) __syncthreads();  // every thread has finished gathering the input tile
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            rtile[tid + r * NT] = v[r];
+            pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
+        }
+        __syncthreads();
+        rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, rtile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            c2 wsum = {pr[r], pi[r]};
+            if (UNIFORM) {
+                wsum.x = a.u.g.x * pr[r]; wsum.y = a.u.g.x * pi[r];
+                if (!REAL_G) { wsum.x = fma(-a.u.g.y, qi[r], wsum.x); wsum.y = fma(a.u.g.y, qr[r], wsum.y); }
+            }
+            st_c2(a.w_out + voff + idx_of(r), wsum);
+        }
+    }
 }
 
 // ---- d = 2 single-pass stage kernel with TMA-streamed partner tiles ----------------------------------------------

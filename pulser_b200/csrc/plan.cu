@@ -128,10 +128,11 @@ struct Plan {
     bool use_pdl = true;
     // partner-sum forwarding between Clenshaw stages (kernels.cuh, FWD): geometry of the first stage of an
     // exponential [0], of the odd stages [1] (high-bit tile) and of the later even stages [2]
-    int use_fwd = -1;               // PB200_FWD: 1 on, 0 off, -1 auto (state small enough to live in L2)
+    int use_fwd = 0;                // PB200_FWD: 1 on (experiment, slower than the single-pass stages)
     bool fwd_now = false;           // decided per propagate call
     PassGeom fwd_geo[3];
     c2* wbuf[2] = {nullptr, nullptr};  // forwarded sums, one vector per chain
+    int fwd_flags = 0;              // PB200_FWD_FLAGS: operand staging switches of stage_d2_fwd_kernel
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -373,13 +374,17 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
 // 2 x 16 B of streaming traffic).  Bits above TB + hb, if any, stay global partner loads; the first stage of an
 // exponential has no producer and is the ordinary single-pass stage (it only emits).
 static bool fwd_eligible(const Plan& P, const std::vector<PassGeom>& passes) {
-    if (!is_d2path(P) || P.force_v1 || P.reg_bits != 3 || P.use_pipe || P.use_stream) return false;
+    if (!is_d2path(P) || P.force_v1 || P.use_pipe || P.use_stream) return false;
     if (P.tile_bits != 11 && P.tile_bits != 12) return false;
     if (passes.size() != 1 || passes[0].hi_bits != 0 || passes[0].lo_bits != P.tile_bits) return false;
-    if (P.n - P.tile_bits < 3) return false;  // the register block of the B tile must consist of flipped bits
+    if (P.n - P.tile_bits < P.reg_bits) return false;  // the register block of the B tile must consist of flipped bits
     if ((long long)P.B * 2 > 65535) return false;
-    if (P.use_fwd >= 0) return P.use_fwd != 0;
-    return (double)P.D * P.B * 16.0 <= (double)env_int("PB200_FWD_MIB", 64) * 1048576.0;
+    // operand staging must fit the 227 KB of an SM
+    const int extra = ((P.fwd_flags & 1) ? 1 : 0) + ((P.fwd_flags & 2) ? 1 : 0) + ((P.fwd_flags & 4) ? 1 : 0) +
+                      ((P.fwd_flags & 8) ? 1 : 0);
+    if ((size_t)(1 + extra) * ((size_t)16 << P.tile_bits) + (size_t)d2_table_stride(P.n) * 8 > (size_t)200 * 1024) return false;
+    // measured slower than the single-pass stages on B200: an experiment, off unless asked for
+    return P.use_fwd > 0;
 }
 
 static void plan_fwd_geometry(Plan& P) {
@@ -409,27 +414,35 @@ static void launch_stage_fwd(Plan& P, const StageIO* io, int n, bool uniform, lo
     const int tsize = 1 << tbits;
     const size_t tab_bytes = uniform ? 0 : (size_t)d2_table_stride(P.n) * 8;
     StageArgs2 m{};
+    int extra_tiles = 0;
     for (int c = 0; c < n; ++c) {
         const int role = (io[c].stage_idx == 0) ? 0 : ((io[c].stage_idx & 1) ? 1 : 2);
-        m.a[c] = make_stage_args(P, P.fwd_geo[role], io[c], true);
-        m.a[c].swz = 0;
-        m.a[c].w_in = (io[c].stage_idx > 0) ? io[c].wbuf : nullptr;
-        m.a[c].w_out = io[c].has_next ? io[c].wbuf : nullptr;
+        StageArgs& a = m.a[c];
+        a = make_stage_args(P, P.fwd_geo[role], io[c], true);
+        a.swz = 0;
+        a.w_in = (io[c].stage_idx > 0) ? io[c].wbuf : nullptr;
+        a.w_out = io[c].has_next ? io[c].wbuf : nullptr;
+        a.fwd_flags = P.fwd_flags;
+        if (!a.w_out) a.fwd_flags &= ~8;
+        const int t = (((a.fwd_flags & 1) && a.w_in) ? 1 : 0) + (((a.fwd_flags & 2) && a.b2) ? 1 : 0) +
+                      (((a.fwd_flags & 4) && a.psi) ? 1 : 0) + ((a.fwd_flags & 8) ? 1 : 0);
+        extra_tiles = std::max(extra_tiles, t);
     }
     m.n_traj = P.B;
     dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
-    const int threads = tsize >> 3;
-    const size_t smem = (size_t)tsize * 16 + tab_bytes;
-#define PB200_LAUNCH_FWD(TB)                                                                                   \
+    const int threads = tsize >> P.reg_bits;
+    const size_t smem = (size_t)(1 + extra_tiles) * tsize * 16 + tab_bytes;
+#define PB200_LAUNCH_FWD(TB, RB)                                                                               \
     do {                                                                                                       \
         if (uniform) {                                                                                         \
-            if (real_g) launch_k(stage_d2_rb_kernel<true, true, TB, 3, true>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);   \
-            else launch_k(stage_d2_rb_kernel<true, false, TB, 3, true>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);         \
+            if (real_g) launch_k(stage_d2_fwd_kernel<true, true, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);   \
+            else launch_k(stage_d2_fwd_kernel<true, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);         \
         } else {                                                                                               \
-            launch_k(stage_d2_rb_kernel<false, false, TB, 3, true>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);             \
+            launch_k(stage_d2_fwd_kernel<false, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);             \
         }                                                                                                      \
     } while (0)
-    if (tbits == 11) PB200_LAUNCH_FWD(11); else PB200_LAUNCH_FWD(12);
+    if (tbits == 11) { if (P.reg_bits == 3) PB200_LAUNCH_FWD(11, 3); else PB200_LAUNCH_FWD(11, 2); }
+    else { if (P.reg_bits == 3) PB200_LAUNCH_FWD(12, 3); else PB200_LAUNCH_FWD(12, 2); }
 #undef PB200_LAUNCH_FWD
     ++launches;
 }
@@ -1690,7 +1703,8 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
     P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
-    P.use_fwd = env_int("PB200_FWD", -1);
+    P.use_fwd = env_int("PB200_FWD", 0);
+    P.fwd_flags = env_int("PB200_FWD_FLAGS", 0);
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;
@@ -1728,6 +1742,12 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+#define PB200_FWD_ATTR(TB, RB)                                                                                                              \
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, true, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   \
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  \
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<false, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PB200_FWD_ATTR(11, 3) PB200_FWD_ATTR(11, 2) PB200_FWD_ATTR(12, 3) PB200_FWD_ATTR(12, 2)
+#undef PB200_FWD_ATTR
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));

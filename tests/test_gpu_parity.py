@@ -547,11 +547,16 @@ def _fwd_specs(kind, n):
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("kind,n,tile_bits", [
-    ("uniform-real", 14, 11), ("uniform-real", 17, 11), ("uniform-real", 20, 11), ("uniform-real", 21, 11),
-    ("uniform-real", 16, 12), ("uniform-complex", 15, 11), ("local", 14, 11), ("local", 16, 12), ("batch", 15, 11),
+@pytest.mark.parametrize("kind,n,tile_bits,flags,reg_bits", [
+    ("uniform-real", 14, 11, 0, 3), ("uniform-real", 17, 11, 27, 3), ("uniform-real", 20, 11, 11, 3),
+    ("uniform-real", 21, 11, 16, 3), ("uniform-real", 16, 12, 0, 3), ("uniform-real", 16, 12, 9, 2),
+    ("uniform-complex", 15, 11, 0, 3), ("uniform-complex", 15, 11, 31, 2), ("local", 14, 11, 0, 3),
+    ("local", 15, 11, 15, 3), ("local", 16, 12, 24, 3), ("batch", 15, 11, 3, 3), ("batch", 14, 11, 0, 2),
 ])
-def test_partner_sum_forwarding_equals_single_pass(engine, monkeypatch, kind, n, tile_bits):
+def test_partner_sum_forwarding_equals_single_pass(engine, monkeypatch, kind, n, tile_bits, flags, reg_bits):
+    """flags = PB200_FWD_FLAGS (TMA-staged w_in / b2 / psi tiles, separate result tile, L1 prefetch)."""
+    monkeypatch.setenv("PB200_FWD_FLAGS", str(flags))
+    monkeypatch.setenv("PB200_REG_BITS", str(reg_bits))
     spec = _fwd_specs(kind, n)
     first = spec[0] if isinstance(spec, list) else spec
     tf = first.sampling_times[-1]
