@@ -137,11 +137,19 @@ int pb200_plan_set_interaction(pb200_plan* plan, int32_t traj0, int32_t count,
  * Uxy[count][N][N] of  Uxy_ij (|u d><d u| + h.c.)  (make_xy_term,
  * hamiltonian.py:276-294; interaction_matrix[0] in XY mode).  The |uu><uu| term
  * of the same function goes through pb200_plan_set_interaction with
- * rydberg_state = digit of |u>.  The SLM-mask time dependence (:399-424) is not
- * supported.  shared != 0: one matrix for all trajectories. */
+ * rydberg_state = digit of |u>.  The SLM-mask time dependence (:399-424) is set with
+ * pb200_plan_set_slm_mask.  shared != 0: one matrix for all trajectories. */
 int pb200_plan_set_xy(pb200_plan* plan, int32_t traj0, int32_t count,
                       const double* Uxy, const uint8_t* bad, int32_t shared,
                       int32_t digit_u, int32_t digit_d);
+
+/* XY mode with an SLM mask (hamiltonian.py:399-424): the interaction of every pair that contains a masked
+ * qudit (masked[N] != 0) is multiplied by the interpolated coefficient coeff[n_times] -- the 0/1 array the
+ * reference builds at :405-407 (0 up to the end of the mask, 1 afterwards) after _adapt_to_sampling_rate --
+ * while the other pairs keep weight 1; i.e. H_int(t) = c(t) H_all + (1 - c(t)) H_unmasked, both terms spline-
+ * interpolated like every QobjEvo coefficient.  Must be called before pb200_plan_set_interaction /
+ * pb200_plan_set_xy (which split their matrices accordingly); one mask for all trajectories. */
+int pb200_plan_set_slm_mask(pb200_plan* plan, const uint8_t* masked, const double* coeff);
 
 /* Sample tables of drive `drive` for trajectories [traj0, traj0+count):
  *   coef[count][rows][n_times][2]  = 0.5*amp*exp(-i*phase)   (re, im)

@@ -34,6 +34,19 @@ class MatFreeHamiltonian:
         self.xy = None
         if spec.has_interaction() and spec.interaction_type == "XY":
             self.xy = (spec.xy_matrix(), spec.eigenbasis.index("u"), spec.eigenbasis.index("d"))
+        # XY + SLM mask (hamiltonian.py:399-424): pairs touching a masked qudit carry the interpolated 0/1
+        # coefficient of the unmasked term; the other pairs have weight c + (1 - c) = 1
+        self.slm_fn = None
+        self.touched = np.zeros((n, n), dtype=bool)
+        self.dint_c = np.zeros(D)
+        slm_c = spec.slm_coefficient() if hasattr(spec, "slm_coefficient") else None
+        if slm_c is not None:
+            if order == 0:
+                raise NotImplementedError
+            self.slm_fn = make_interp_spline(spec.sampling_times, slm_c, k=order)
+            m = np.zeros(n, dtype=bool)
+            m[list(spec.slm_targets)] = True
+            self.touched = m[:, None] | m[None, :]
         if spec.has_interaction():
             r = spec.eigenbasis.index("u" if spec.interaction_type == "XY" else "r")
             U = spec.pair_matrix()
@@ -41,7 +54,10 @@ class MatFreeHamiltonian:
             for i in range(n):
                 for j in range(i + 1, n):
                     if U[i, j] != 0.0:
-                        self.dint += U[i, j] * nr[i] * nr[j]
+                        if self.touched[i, j]:
+                            self.dint_c += U[i, j] * nr[i] * nr[j]
+                        else:
+                            self.dint += U[i, j] * nr[i] * nr[j]
         t = spec.sampling_times
         self.fns = []
         for drv in spec.drives:
@@ -57,7 +73,8 @@ class MatFreeHamiltonian:
     def apply(self, t_us: float, psi: np.ndarray) -> np.ndarray:
         n, d = self.n, self.d
         psi = np.asarray(psi, dtype=complex)
-        out = self.dint * psi
+        cm = float(self.slm_fn(t_us)) if self.slm_fn is not None else 1.0
+        out = (self.dint + cm * self.dint_c) * psi
         pt = psi.reshape([d] * n)
         ot = out.reshape([d] * n)
         for to, frm, cf, df in self.fns:
@@ -83,6 +100,7 @@ class MatFreeHamiltonian:
                     a[i], a[j] = iu, idn
                     b[i], b[j] = idn, iu
                     a, b = tuple(a), tuple(b)
-                    ot[a] += U[i, j] * pt[b]
-                    ot[b] += U[i, j] * pt[a]
+                    u = U[i, j] * (cm if self.touched[i, j] else 1.0)
+                    ot[a] += u * pt[b]
+                    ot[b] += u * pt[a]
         return out

@@ -112,26 +112,45 @@ class OracleHamiltonian:
         bad = np.asarray(spec.bad_atoms, dtype=bool)
         effective_size = n - int(bad.sum())
         if "digital" not in spec.basis_name and effective_size > 1:
+            slm = set(int(t) for t in spec.slm_targets)
+
+            def make_interaction_term(masked: bool = False) -> sp.csr_matrix:
+                # hamiltonian.py:296-331
+                inter = sp.csr_matrix((spec.dim**n, spec.dim**n), dtype=complex)
+                if masked:
+                    eff = n - int(bad.sum()) - sum(1 for q in slm if not bad[q])
+                    if eff < 2:
+                        return inter
+                for q1, q2 in itertools.combinations(range(n), 2):
+                    if bad[q1] or bad[q2]:
+                        continue
+                    if masked and spec.interaction_type == "XY" and (q1 in slm or q2 in slm):
+                        continue
+                    if spec.interaction_type == "XY":  # make_xy_term, hamiltonian.py:276-294
+                        u_xy = spec.interaction_matrix[0, q1, q2]
+                        u_ryd = spec.interaction_matrix[1, q1, q2]
+                        inter = inter + u_xy * build_operator(
+                            n, ops, [("sigma_ud", [q1]), ("sigma_du", [q2])]
+                        ) + 0.5 * u_ryd * build_operator(n, ops, [("sigma_uu", [q1, q2])])
+                    else:  # make_vdw_term, hamiltonian.py:260-274
+                        u = 0.5 * spec.interaction_matrix[-1, q1, q2]
+                        inter = inter + u * build_operator(
+                            n, ops, [("sigma_rr", [q1, q2])]
+                        )
+                return sp.csr_matrix(inter)
+
             if spec.interaction_type == "XY" and spec.slm_end > 0:
-                raise NotImplementedError("XY interaction with an SLM mask: oracle TODO")
-            inter = sp.csr_matrix(
-                (spec.dim**n, spec.dim**n), dtype=complex
-            )
-            for q1, q2 in itertools.combinations(range(n), 2):
-                if bad[q1] or bad[q2]:
-                    continue
-                if spec.interaction_type == "XY":  # make_xy_term, hamiltonian.py:276-294
-                    u_xy = spec.interaction_matrix[0, q1, q2]
-                    u_ryd = spec.interaction_matrix[1, q1, q2]
-                    inter = inter + u_xy * build_operator(
-                        n, ops, [("sigma_ud", [q1]), ("sigma_du", [q2])]
-                    ) + 0.5 * u_ryd * build_operator(n, ops, [("sigma_uu", [q1, q2])])
-                else:  # make_vdw_term, hamiltonian.py:260-274
-                    u = 0.5 * spec.interaction_matrix[-1, q1, q2]
-                    inter = inter + u * build_operator(
-                        n, ops, [("sigma_rr", [q1, q2])]
-                    )
-            qobj_list.append((sp.csr_matrix(inter), None))
+                # hamiltonian.py:399-424: binary coefficient arrays for the two interaction terms
+                duration = int(spec.total_duration_ns) + 1
+                coeff = np.ones(duration - 1)
+                coeff[0 : spec.slm_end] = 0
+                idx = np.linspace(0, len(coeff) - 1, len(spec.sampling_times), dtype=int)
+                qobj_list.append((make_interaction_term(), coeff[idx]))
+                qobj_list.append(
+                    (make_interaction_term(masked=True), np.logical_not(coeff).astype(int)[idx].astype(float))
+                )
+            else:
+                qobj_list.append((make_interaction_term(), None))
         for drv in spec.drives:
             op_ids = _OP_IDS[drv.basis]
             if drv.uniform:
@@ -201,22 +220,39 @@ class OracleHamiltonian:
         effective_size = n - sum(bad.values())
         imat = noise_trajectory.interaction_matrix.as_array(detach=True)
         if "digital" not in basis_data.basis_name and effective_size > 1:
+            slm = set(samples._slm_mask.targets)
+
+            def make_interaction_term(masked: bool = False) -> sp.csr_matrix:
+                inter = sp.csr_matrix((d**n, d**n), dtype=complex)
+                if masked:
+                    eff = n - sum(bad.values()) - sum(1 for q in slm if not bad[q])
+                    if eff < 2:
+                        return inter
+                for q1, q2 in itertools.combinations(qids, 2):
+                    if bad[q1] or bad[q2]:
+                        continue
+                    if masked and basis_data.interaction_type == "XY" and (q1 in slm or q2 in slm):
+                        continue
+                    i1, i2 = qidx[q1], qidx[q2]
+                    if basis_data.interaction_type == "XY":
+                        inter = inter + imat[0, i1, i2] * build_operator(
+                            n, ops, [("sigma_ud", [i1]), ("sigma_du", [i2])]
+                        ) + 0.5 * imat[1, i1, i2] * build_operator(n, ops, [("sigma_uu", [i1, i2])])
+                    else:
+                        inter = inter + 0.5 * imat[-1, i1, i2] * build_operator(
+                            n, ops, [("sigma_rr", [i1, i2])]
+                        )
+                return sp.csr_matrix(inter)
+
             if basis_data.interaction_type == "XY" and samples._slm_mask.end > 0:
-                raise NotImplementedError("XY interaction with an SLM mask: oracle TODO")
-            inter = sp.csr_matrix((d**n, d**n), dtype=complex)
-            for q1, q2 in itertools.combinations(qids, 2):
-                if bad[q1] or bad[q2]:
-                    continue
-                i1, i2 = qidx[q1], qidx[q2]
-                if basis_data.interaction_type == "XY":
-                    inter = inter + imat[0, i1, i2] * build_operator(
-                        n, ops, [("sigma_ud", [i1]), ("sigma_du", [i2])]
-                    ) + 0.5 * imat[1, i1, i2] * build_operator(n, ops, [("sigma_uu", [i1, i2])])
-                else:
-                    inter = inter + 0.5 * imat[-1, i1, i2] * build_operator(
-                        n, ops, [("sigma_rr", [i1, i2])]
-                    )
-            qobj_list.append((sp.csr_matrix(inter), None))
+                coeff = np.ones(duration - 1)  # hamiltonian.py:405-407
+                coeff[0 : samples._slm_mask.end] = 0
+                qobj_list.append((make_interaction_term(), adapt(coeff)))
+                qobj_list.append(
+                    (make_interaction_term(masked=True), adapt(np.logical_not(coeff).astype(int)).astype(float))
+                )
+            else:
+                qobj_list.append((make_interaction_term(), None))
         nested = samples.to_nested_dict()
         for addr in nested:
             for basis in nested[addr]:

@@ -93,6 +93,7 @@ def _load() -> C.CDLL:
             C.c_int, [vp, C.c_int32, C.c_int32, dp, C.POINTER(C.c_uint8), C.c_int32]),
         "pb200_plan_set_xy": (
             C.c_int, [vp, C.c_int32, C.c_int32, dp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32]),
+        "pb200_plan_set_slm_mask": (C.c_int, [vp, C.POINTER(C.c_uint8), dp]),
         "pb200_plan_set_drive": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, dp, dp]),
         "pb200_plan_set_dissipator": (C.c_int, [vp, C.c_int32, dp]),
         "pb200_plan_set_collapse": (C.c_int, [vp, C.c_int32, dp, C.c_uint64]),
@@ -132,7 +133,7 @@ def _load() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "pb200_version", "pb200_last_error", "pb200_device_count",
     "pb200_plan_create", "pb200_plan_destroy", "pb200_plan_set_stream",
-    "pb200_plan_set_interaction", "pb200_plan_set_xy", "pb200_plan_set_drive", "pb200_plan_set_dissipator", "pb200_plan_set_collapse",
+    "pb200_plan_set_interaction", "pb200_plan_set_xy", "pb200_plan_set_slm_mask", "pb200_plan_set_drive", "pb200_plan_set_dissipator", "pb200_plan_set_collapse",
     "pb200_plan_jump_counts", "pb200_state_set",
     "pb200_state_get", "pb200_state_probabilities", "pb200_state_norm2",
     "pb200_state_occupation", "pb200_state_correlation", "pb200_state_energy", "pb200_state_overlap", "pb200_state_sample", "pb200_state_device_ptr", "pb200_propagate", "pb200_apply_h",

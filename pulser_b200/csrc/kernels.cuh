@@ -1025,7 +1025,9 @@ __global__ void __launch_bounds__(1 << (TBITS - RB), 2) coop_program_kernel(cons
 // ---- generic-d stage kernel (any dim, several drives; global gathers) -------
 // table per (exponential, trajectory):
 //   for each drive q: g[q][k] (re,im) per QUDIT k, theta[q][k]; then w, gamma
-__host__ __device__ inline int gen_table_stride(int n, int n_drives) { return n_drives * 3 * n + 2; }
+// per-(exponential, trajectory) table of the generic kernel: per drive q [g (re,im) per qudit | theta per qudit],
+// then wc (weight of the SLM-masked part of the interaction, XY mode), w, gamma
+__host__ __device__ inline int gen_table_stride(int n, int n_drives) { return n_drives * 3 * n + 3; }
 
 struct GenArgs {
     const c2* v; const c2* psi; const c2* b2; c2* out;
@@ -1037,6 +1039,9 @@ struct GenArgs {
     const double* beta_dev;
     // XY mode: exchange couplings U^xy_ij (|u d><d u| + h.c.), [Bx][n*n], weighted by the table's w like Dint
     const double* xy; long long xy_stride; int xy_u, xy_d;
+    // XY mode with an SLM mask (hamiltonian.py:399-424): pairs touching a masked qudit (bit k of slm_mask) carry the
+    // weight wc = table[stride - 3] instead of w; dint2 = interaction diagonal of those pairs (dint: the others)
+    unsigned long long slm_mask; const double* dint2;
 };
 
 __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
@@ -1048,8 +1053,12 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
     __syncthreads();
     double* xys = tab + stride;  // XY couplings of this trajectory, weighted like Dint
     if (a.xy) {
-        const double wx = tab[stride - 2];
-        for (int i = threadIdx.x; i < a.n * a.n; i += blockDim.x) xys[i] = a.xy[traj * a.xy_stride + i] * wx;
+        const double wx = tab[stride - 2], wxc = tab[stride - 3];
+        for (int i = threadIdx.x; i < a.n * a.n; i += blockDim.x) {
+            const int qi = i / a.n, qj = i - qi * a.n;
+            const bool touched = ((a.slm_mask >> qi) | (a.slm_mask >> qj)) & 1ULL;
+            xys[i] = a.xy[traj * a.xy_stride + i] * (touched ? wxc : wx);
+        }
         __syncthreads();
     }
     const double w = tab[stride - 2], gamma = tab[stride - 1];
@@ -1059,6 +1068,7 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
         const c2 vo = a.v[voff + idx];
         double diag = -gamma;
         if (a.dint) diag = fma(w, a.dint[traj * a.dint_stride + idx], diag);
+        if (a.dint2) diag = fma(tab[stride - 3], a.dint2[traj * a.dint_stride + idx], diag);
         double rr = 0.0, ri = 0.0;
         long long rem = idx, st = 1;
         for (int k = a.n - 1; k >= 0; --k) {  // qudit k has stride dim^(n-1-k)

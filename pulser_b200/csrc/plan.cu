@@ -121,7 +121,12 @@ struct Plan {
     bool has_collapse = false;
     // XY mode: exchange couplings on the device, their absolute row sums (spectral bound)
     double* d_xy = nullptr; bool xy_shared = true; bool has_xy = false; int xy_u = 0, xy_d = 1;
-    std::vector<double> xy_norm;  // per trajectory: sum_{i<j} |Uxy_ij|
+    std::vector<double> xy_norm;  // per trajectory: sum_{i<j} |Uxy_ij| (pairs not touching the SLM mask)
+    // XY mode with an SLM mask: the interaction of the pairs touching a masked qudit is weighted by the
+    // interpolated 0/1 coefficient slm_coef(t) (hamiltonian.py:399-424)
+    bool has_slm = false; unsigned long long slm_bits = 0; PiecewiseCubic<double> slm_coef;
+    double* dint2 = nullptr;                 // interaction diagonal of the pairs touching the mask
+    std::vector<double> xy_norm2, dmin2_traj, dmax2_traj;
     std::mt19937_64 rng;
     std::vector<double> thresholds;               // per trajectory
     std::vector<long long> jump_count;
@@ -208,6 +213,7 @@ struct ExpParams {  // one exponential exp(-i G), G from Magnus moments
     std::vector<cplx> g;
     std::vector<double> th;
     double w = 0.0;
+    double wc = 0.0;  // weight of the SLM-masked pairs (XY mode with a mask); unused otherwise
 };
 
 static inline bool is_d2path(const Plan& P) { return P.dim == 2 && P.n_drives == 1 && !P.has_xy; }
@@ -355,6 +361,7 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             a.coef = io[c].coef; a.table = io[c].table; a.beta_dev = io[c].beta_dev;
             a.xy = P.has_xy ? P.d_xy : nullptr; a.xy_stride = P.xy_shared ? 0 : (long long)N * N;
             a.xy_u = P.xy_u; a.xy_d = P.xy_d;
+            a.slm_mask = P.has_slm ? P.slm_bits : 0ULL; a.dint2 = (P.has_slm && P.has_interaction) ? P.dint2 : nullptr;
             int threads = 256;
             long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
             dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
@@ -466,8 +473,9 @@ static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, doub
         for (int q = 0; q < nd; ++q)
             for (int k = 0; k < N; ++k) dr += std::abs(E.g[pidx(P, b, q, k)]);
         if (P.has_xy) dr += std::fabs(E.w) * (P.xy_shared ? P.xy_norm[0] : P.xy_norm[b]);  // |flip-flop| <= 1
+        if (P.has_xy && P.has_slm) dr += std::fabs(E.wc) * (P.xy_shared ? P.xy_norm2[0] : P.xy_norm2[b]);
         double dlo, dhi;
-        const bool caseA = P.has_interaction && P.dint_shared && nd == 1 && P.desc.drives[0].uniform &&
+        const bool caseA = !P.has_slm && P.has_interaction && P.dint_shared && nd == 1 && P.desc.drives[0].uniform &&
                            P.desc.drives[0].state_from == P.desc.rydberg_state && !P.dmin_cnt.empty();
         if (caseA) {
             const double th = E.th[pidx(P, b, 0, 0)];
@@ -484,6 +492,11 @@ static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, doub
                 dmx = P.dint_shared ? P.dmax_traj[0] : P.dmax_traj[b];
             }
             dlo = E.w * dmn; dhi = E.w * dmx;
+            if (P.has_slm && P.has_interaction) {  // second diagonal, weight wc (may be slightly outside [0, w])
+                const double m2 = P.dint_shared ? P.dmin2_traj[0] : P.dmin2_traj[b];
+                const double x2 = P.dint_shared ? P.dmax2_traj[0] : P.dmax2_traj[b];
+                dlo += std::min(E.wc * m2, E.wc * x2); dhi += std::max(E.wc * m2, E.wc * x2);
+            }
             for (int k = 0; k < N; ++k) {
                 double mn = 0.0, mx = 0.0;  // a digit that is nobody's `from`
                 for (int dgt = 0; dgt < P.dim; ++dgt) {
@@ -530,7 +543,7 @@ static void build_tables(const Plan& P, const ExpParams& E, double& gamma0, doub
                     tq[2 * N + k] = E.th[pidx(P, b, q, k)] * inv;
                 }
             }
-            t[stride - 2] = E.w * inv; t[stride - 1] = gamma0 * inv;
+            t[stride - 3] = E.wc * inv; t[stride - 2] = E.w * inv; t[stride - 1] = gamma0 * inv;
         }
     }
     if (!scaled) rho = rho_bound;
@@ -979,6 +992,12 @@ static void moments_for_step(const Plan& P, double a, double b, std::vector<cplx
         }
 }
 
+// Magnus moments of the SLM coefficient over [a, b]: c0 = int c dt, c1 = (1/(b-a)) int (t - mid) c dt
+static void slm_moments(const Plan& P, double a, double b, double& c0, double& c1) {
+    c0 = 0.0; c1 = 0.0;
+    if (P.has_slm) magnus_moments(P.slm_coef, P.times, a, b, c0, c1);
+}
+
 static void add_exponential(const Plan& P, Program& prog, const ExpParams& E, double tol) {
     const bool d2path = is_d2path(P);
     double gamma0, rho;
@@ -1085,6 +1104,10 @@ static std::vector<char> fine_intervals(const Plan& P, int window, double rough_
             scan(T.coef, T.coef_scale, [](cplx z) { return std::abs(z); });
             scan(T.det, T.det_scale, [](double z) { return std::fabs(z); });
         }
+    if (P.has_slm) {  // the 0 -> 1 switch of the masked interaction is a jump like a pulse edge
+        std::vector<PiecewiseCubic<double>> one{P.slm_coef};
+        scan(one, std::vector<double>{1.0}, [](double z) { return std::fabs(z); });
+    }
     std::vector<char> fine(std::max(nt - 1, 1), 0);
     for (int r = 0; r < nt; ++r)
         if (rough[r])
@@ -1123,10 +1146,12 @@ static void add_step(const Plan& P, Program& prog, double a, double b, int order
             E2.g[x] = 0.5 * g0[x] + 2.0 * g1[x]; E2.th[x] = 0.5 * th0[x] + 2.0 * th1[x];
         }
         E1.w = 0.5 * h; E2.w = 0.5 * h;
+        { double c0, c1; slm_moments(P, a, b, c0, c1); E1.wc = 0.5 * c0 - 2.0 * c1; E2.wc = 0.5 * c0 + 2.0 * c1; }
         add_exponential(P, prog, E1, tol);
         add_exponential(P, prog, E2, tol);
     } else {
         ExpParams E; E.g = g0; E.th = th0; E.w = h;
+        { double c0, c1; slm_moments(P, a, b, c0, c1); E.wc = c0; }
         add_exponential(P, prog, E, tol);
     }
 }
@@ -1136,6 +1161,7 @@ static int jump_substeps(const Plan& P, double a, double b, double magnus_tol) {
     std::vector<cplx> g0, g1; std::vector<double> th0, th1;
     moments_for_step(P, a, b, g0, g1, th0, th1);
     ExpParams E; E.g = g0; E.th = th0; E.w = b - a;
+    { double c0, c1; slm_moments(P, a, b, c0, c1); E.wc = c0; }
     double gm, rh; std::vector<double> scratch_tab;
     build_tables(P, E, gm, rh, scratch_tab, is_d2path(P));
     double b1 = 0.0;
@@ -1361,6 +1387,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             const double tb = std::min(P.times[std::min(1, nt - 1)], t_stop);
             moments_for_step(P, P.times[0], P.times[std::min(1, nt - 1)], q0, q1, r0, r1);
             ExpParams E; E.g = q0; E.th = r0; E.w = P.times[std::min(1, nt - 1)] - P.times[0];
+            { double c0, c1; slm_moments(P, P.times[0], P.times[std::min(1, nt - 1)], c0, c1); E.wc = c0; }
             double gm, rh1; std::vector<double> scratch_tab;
             build_tables(P, E, gm, rh1, scratch_tab, is_d2path(P));
             // ... or when the state no longer fits L2 (fewer, fatter iterations win once HBM-bound)
@@ -1450,6 +1477,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             std::vector<cplx> q0, q1; std::vector<double> r0, r1;
             moments_for_step(P, t, std::min(P.times[i + 1], t_stop), q0, q1, r0, r1);
             ExpParams E; E.g = q0; E.th = r0; E.w = std::min(P.times[i + 1], t_stop) - t;
+            { double c0, c1; slm_moments(P, t, std::min(P.times[i + 1], t_stop), c0, c1); E.wc = c0; }
             double gm, rh1; std::vector<double> scratch_tab;
             build_tables(P, E, gm, rh1, scratch_tab, is_d2path(P));
             const double frac = E.w / hi_i;  // fraction of a sampling interval covered by this probe
@@ -1560,6 +1588,7 @@ static ExpParams params_at(const Plan& P, double t) {
     ExpParams E;
     const int N = P.n, B = P.B, nd = P.n_drives;
     E.g.assign((size_t)B * nd * N, cplx(0)); E.th.assign((size_t)B * nd * N, 0.0); E.w = 1.0;
+    if (P.has_slm) E.wc = eval_at(P.slm_coef, P.times, t, P.desc.interp_order);
     for (int tr = 0; tr < B; ++tr)
         for (int q = 0; q < nd; ++q) {
             const DriveTables& T = P.tabs[tr][q];
@@ -1604,7 +1633,7 @@ static void apply_h_device(Plan& P, double t, const c2* in, c2* out, long long& 
                     tb[q * 3 * N + 2 * k + 1] = E.g[pidx(P, b, q, k)].imag();
                     tb[q * 3 * N + 2 * N + k] = E.th[pidx(P, b, q, k)];
                 }
-            tb[stride - 2] = 1.0; tb[stride - 1] = 0.0;
+            tb[stride - 3] = E.wc; tb[stride - 2] = 1.0; tb[stride - 1] = 0.0;
         }
     }
     ensure_table_capacity(P, host.size());
@@ -1774,6 +1803,7 @@ int pb200_plan_destroy(pb200_plan* h) {
         if (P.wbuf[i]) cudaFree(P.wbuf[i]);
     if (P.d_bar) cudaFree(P.d_bar);
     if (P.d_xy) cudaFree(P.d_xy);
+    if (P.dint2) cudaFree(P.dint2);
     if (P.kry) cudaFree(P.kry);
     if (P.d_kry) cudaFree(P.d_kry);
     if (P.dint) cudaFree(P.dint);
@@ -1814,20 +1844,33 @@ int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, cons
     P.dint_shared = want_shared;
     P.dmin_traj.resize(want_shared ? 1 : P.B, 0.0);
     P.dmax_traj.resize(want_shared ? 1 : P.B, 0.0);
+    if (P.has_slm) {
+        if (P.dint2) { CUDA_CHECK(cudaFree(P.dint2)); P.dint2 = nullptr; }
+        CUDA_CHECK(cudaMalloc(&P.dint2, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B)));
+        CUDA_CHECK(cudaMemsetAsync(P.dint2, 0, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B), P.stream));
+        P.dmin2_traj.assign(want_shared ? 1 : P.B, 0.0);
+        P.dmax2_traj.assign(want_shared ? 1 : P.B, 0.0);
+    }
     double* dU = nullptr;
     CUDA_CHECK(cudaMalloc(&dU, sizeof(double) * N * N));
     std::vector<double> Uc((size_t)N * N);
-    for (int c = 0; c < count; ++c) {
+    // part 0: pairs weighted by w (all pairs, or the pairs not touching the SLM mask); part 1: the pairs touching it
+    for (int c = 0; c < count; ++c)
+      for (int part = 0; part < (P.has_slm ? 2 : 1); ++part) {
         const double* Ui = U + (size_t)c * N * N;
         const uint8_t* bi = bad ? bad + (size_t)c * N : nullptr;
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) {
                 double u = (i < j) ? Ui[i * N + j] : (i > j ? Ui[j * N + i] : 0.0);
                 if (bi && (bi[i] || bi[j])) u = 0.0;
+                if (P.has_slm) {
+                    const bool touched = ((P.slm_bits >> i) | (P.slm_bits >> j)) & 1ULL;
+                    if (touched != (part == 1)) u = 0.0;
+                }
                 Uc[(size_t)i * N + j] = u;
             }
         CUDA_CHECK(cudaMemcpyAsync(dU, Uc.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, P.stream));
-        double* dst = P.dint + (want_shared ? 0 : (size_t)(traj0 + c) * P.D);
+        double* dst = (part == 0 ? P.dint : P.dint2) + (want_shared ? 0 : (size_t)(traj0 + c) * P.D);
         const int threads = 256;
         const long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 16);
         dint_kernel<<<(unsigned)std::max<long long>(blocks, 1), threads, sizeof(double) * N * N, P.stream>>>(
@@ -1847,9 +1890,13 @@ int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, cons
         for (int k = 0; k <= N; ++k)
             if (mins[k] <= maxs[k]) { mn = std::min(mn, mins[k]); mx = std::max(mx, maxs[k]); }
         const int slot = want_shared ? 0 : traj0 + c;
-        P.dmin_traj[slot] = mn; P.dmax_traj[slot] = mx;
-        if (want_shared) { P.dmin_cnt = mins; P.dmax_cnt = maxs; }
-    }
+        if (part == 0) {
+            P.dmin_traj[slot] = mn; P.dmax_traj[slot] = mx;
+            if (want_shared) { P.dmin_cnt = mins; P.dmax_cnt = maxs; }
+        } else {
+            P.dmin2_traj[slot] = mn; P.dmax2_traj[slot] = mx;
+        }
+      }
     CUDA_CHECK(cudaFree(dU));
     P.has_interaction = true;
     PB200_CATCH
@@ -1875,25 +1922,45 @@ int pb200_plan_set_xy(pb200_plan* h, int32_t traj0, int32_t count, const double*
     }
     P.xy_shared = want_shared;
     P.xy_norm.resize(want_shared ? 1 : P.B, 0.0);
+    P.xy_norm2.resize(want_shared ? 1 : P.B, 0.0);
     std::vector<double> Uc((size_t)N * N);
     for (int c = 0; c < count; ++c) {
         const double* Ui = Uxy + (size_t)c * N * N;
         const uint8_t* bi = bad ? bad + (size_t)c * N : nullptr;
-        double nrm = 0.0;
+        double nrm = 0.0, nrm2 = 0.0;
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) {
                 double u = (i < j) ? Ui[i * N + j] : (i > j ? Ui[j * N + i] : 0.0);
                 if (bi && (bi[i] || bi[j])) u = 0.0;
                 Uc[(size_t)i * N + j] = u;
-                if (i < j) nrm += std::fabs(u);
+                const bool touched = P.has_slm && (((P.slm_bits >> i) | (P.slm_bits >> j)) & 1ULL);
+                if (i < j) { if (touched) nrm2 += std::fabs(u); else nrm += std::fabs(u); }
             }
         const int slot = want_shared ? 0 : traj0 + c;
         CUDA_CHECK(cudaMemcpyAsync(P.d_xy + (size_t)slot * N * N, Uc.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, P.stream));
         CUDA_CHECK(cudaStreamSynchronize(P.stream));
-        P.xy_norm[slot] = nrm;
+        P.xy_norm[slot] = nrm; P.xy_norm2[slot] = nrm2;
     }
     P.xy_u = digit_u; P.xy_d = digit_d;
     P.has_xy = true;
+    PB200_CATCH
+}
+
+int pb200_plan_set_slm_mask(pb200_plan* h, const uint8_t* masked, const double* coeff) {
+    PB200_TRY
+    if (!h || !masked || !coeff) fail(PB200_ERR_INVALID, "null argument");
+    Plan& P = h->p;
+    if (P.has_interaction || P.has_xy)
+        fail(PB200_ERR_STATE, "pb200_plan_set_slm_mask must precede pb200_plan_set_interaction / pb200_plan_set_xy");
+    if (P.n > 63) fail(PB200_ERR_UNSUPPORTED, "SLM mask: at most 63 qudits");
+    const int nt = (int)P.times.size();
+    for (int i = 0; i < nt; ++i)
+        if (!std::isfinite(coeff[i])) fail(PB200_ERR_INVALID, "non-finite SLM coefficient sample");
+    P.slm_bits = 0;
+    for (int k = 0; k < P.n; ++k)
+        if (masked[k]) P.slm_bits |= 1ULL << k;
+    P.slm_coef = make_interpolant<double>(P.times.data(), coeff, nt, P.desc.interp_order);
+    P.has_slm = P.slm_bits != 0;
     PB200_CATCH
 }
 

@@ -13,8 +13,8 @@ reference's own pulser-core code; ``Hamiltonian(...)`` construction
 Collapse operators (``simulation.py:705-735``) run as a master equation on the
 vectorised density matrix (``lindblad.py``, registers with dim^(2N) <= 2^26) and
 as Monte-Carlo wave functions beyond that (``n_trajectories`` set).  XY mode runs
-the coherent and the Monte-Carlo path; not on the CUDA path (raise
-``NotImplementedError``): XY master equation, XY with an SLM mask.
+the coherent path (SLM mask included: ``pb200_plan_set_slm_mask``) and the Monte-Carlo
+path; not on the CUDA path (raise ``NotImplementedError``): XY master equation.
 """
 from __future__ import annotations
 

@@ -48,10 +48,13 @@ class DevicePlan:
         specs = list(specs)
         s0 = specs[0]
         self._xy = s0.interaction_type == "XY"
-        if self._xy and any(s.slm_end > 0 and len(s.slm_targets) for s in specs):
-            raise NotImplementedError(
-                "XY mode with an SLM mask (time-dependent interaction term) is not on the CUDA path"
-            )
+        self._slm = s0.slm_coefficient()
+        for s in specs[1:]:
+            c = s.slm_coefficient()
+            if (c is None) != (self._slm is None) or (
+                c is not None and (not np.array_equal(c, self._slm) or list(s.slm_targets) != list(s0.slm_targets))
+            ):
+                raise ValueError("trajectories must share the SLM mask")
         for s in specs[1:]:
             if (
                 s.n_qudits != s0.n_qudits
@@ -102,6 +105,12 @@ class DevicePlan:
     def _upload(self, any_inter: bool) -> None:
         specs = self.specs
         n, nt = self.n, len(self.spec.sampling_times)
+        if self._slm is not None and any_inter:
+            # XY + SLM mask (hamiltonian.py:399-424): must precede the interaction matrices, which it splits
+            masked = np.zeros(n, dtype=np.uint8)
+            masked[list(self.spec.slm_targets)] = 1
+            coeff = np.ascontiguousarray(self._slm, dtype=np.float64)
+            check(lib.pb200_plan_set_slm_mask(self._handle, masked.ctypes.data_as(C.POINTER(C.c_uint8)), _p(coeff)))
         if any_inter:
             mats = [s.pair_matrix() for s in specs]
             shared = all(np.array_equal(m, mats[0]) for m in mats[1:])

@@ -70,9 +70,28 @@ class HamiltonianSpec:
     collapse_ops: np.ndarray
     qubit_ids: list[str] = dataclasses.field(default_factory=list)
     # XY + SLM mask: interaction switched off until ``slm_end`` for masked
-    # qubits (reference hamiltonian.py:399-424). Not on the CUDA path yet.
+    # qubits (reference hamiltonian.py:399-424).
     slm_end: int = 0
     slm_targets: list[int] = dataclasses.field(default_factory=list)
+
+    def slm_coefficient(self) -> np.ndarray | None:
+        """Samples of the coefficient of the *unmasked* interaction term, or None.
+
+        Restates ``hamiltonian.py:399-411``: ``coeff = ones(duration - 1);
+        coeff[:slm_end] = 0`` pushed through ``_adapt_to_sampling_rate``
+        (``:87-95``; duration = T + 1 extended samples, so the index grid has
+        one more entry than the array it indexes -- kept as is).  Only XY mode
+        has a time-dependent interaction; elsewhere the mask acts through the
+        drive samples alone.
+        """
+        if self.interaction_type != "XY" or self.slm_end <= 0 or not len(self.slm_targets):
+            return None
+        duration = int(self.total_duration_ns) + 1
+        coeff = np.ones(duration - 1)
+        coeff[0 : self.slm_end] = 0
+        nt = len(self.sampling_times)
+        idx = np.linspace(0, len(coeff) - 1, nt, dtype=int)
+        return coeff[idx]
 
     # ------------------------------------------------------------------
     @property

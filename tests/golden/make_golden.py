@@ -2,7 +2,7 @@
 imported from /root/reference) plus the tight-tolerance oracle.
 
 Run in the build container only (the GPU box has no /root/reference):
-    python tests/golden/make_golden.py [--extra | --xy]
+    python tests/golden/make_golden.py [--extra | --xy | --slm]
 
 Each ``*.npz`` holds a HamiltonianSpec (what the reference's Hamiltonian
 constructor receives, extracted from real pulser objects), an initial state and
@@ -164,7 +164,7 @@ def main():
         save(f"orc_noisy_traj{i}", spec, psi0=psi0, orc_final=oracle_final(spec, psi0), reps=reps)
 
 
-if __name__ == "__main__" and "--extra" not in sys.argv and "--xy" not in sys.argv:
+if __name__ == "__main__" and "--extra" not in sys.argv and "--xy" not in sys.argv and "--slm" not in sys.argv:
     main()
 
 
@@ -226,3 +226,74 @@ def xy():
 
 if __name__ == "__main__" and "--xy" in sys.argv:
     xy()
+
+
+def slm():
+    """Fourth batch: XY mode with an SLM mask (time-dependent interaction, hamiltonian.py:399-424)."""
+    import scipy.sparse as sp
+
+    # reference tests/pulser_simulation/test_simulation.py:1792-1838 (test_mask_two_pulses_xy): the masked
+    # Hamiltonian equals (two-qubit H) x 1 while the mask is on and the three-qubit H afterwards.  Checked here
+    # on the ORACLE built from the real pulser objects (this pins the oracle's two-term interaction), then the
+    # spec and the sample times are stored for the GPU apply_h test.
+    reg_three = Register({"q0": (0, 0), "q1": (10, 10), "q2": (-10, -10)})
+    reg_two = Register({"q0": (0, 0), "q1": (10, 10)})
+    pulse = Pulse.ConstantPulse(100, 10, 0, 0)
+    no_pulse = Pulse.ConstantPulse(100, 0, 0, 0)
+
+    def build(reg, pulses, mask=None):
+        seq = Sequence(reg, MockDevice)
+        seq.declare_channel("ch", "mw_global")
+        if mask:
+            seq.config_slm_mask(mask)
+        for p in pulses:
+            seq.add(p, "ch")
+        return seq
+
+    seq_masked = build(reg_three, [pulse, pulse, pulse], ["q2"])
+    seq_three = build(reg_three, [no_pulse, pulse, pulse])
+    seq_two = build(reg_two, [pulse, no_pulse, no_pulse])
+
+    def oracle_of(seq):
+        hd, T = hdata(seq)
+        traj, ns, _ = next(iter(hd.noisy_samples))
+        return OracleHamiltonian.from_pulser(ns, traj, hd.basis_data, hd.lindblad_data, 1.0)
+
+    Hm, H3, H2 = oracle_of(seq_masked), oracle_of(seq_three), oracle_of(seq_two)
+    ti, tf = seq_masked._slm_mask_time
+    eye2 = sp.identity(2, format="csr")
+    for t in Hm.sampling_times:
+        hm = Hm.matrix_at(t).toarray()
+        if ti <= t * 1000 < tf:  # mask on (sample times strictly inside; the switching sample itself is 1)
+            np.testing.assert_allclose(hm, sp.kron(H2.matrix_at(t), eye2).toarray(), atol=1e-12)
+        elif t * 1000 > tf:
+            np.testing.assert_allclose(hm, H3.matrix_at(t).toarray(), atol=1e-12)
+    spec = specs_of(seq_masked)[0][0]
+    assert spec.slm_end == tf and spec.slm_targets == [2]
+    # spec-built oracle == pulser-built oracle, between samples too (spline of the 0/1 coefficient)
+    Hs = OracleHamiltonian.from_spec(spec)
+    for t in (0.0, 0.0503, 0.0991, 0.1004, 0.1507, 0.2999):
+        np.testing.assert_allclose(Hs.matrix_at(t).toarray(), Hm.matrix_at(t).toarray(), atol=1e-12)
+    rng = np.random.default_rng(7)
+    psi0 = rng.normal(size=8) + 1j * rng.normal(size=8)
+    psi0 /= np.linalg.norm(psi0)
+    save("ref_mask_two_pulses_xy", spec, psi0=psi0, orc_final=oracle_final(spec, psi0),
+         h_two_kron=np.stack([sp.kron(H2.matrix_at(t), eye2).toarray() for t in (0.01, 0.05, 0.09)]),
+         h_three=np.stack([H3.matrix_at(t).toarray() for t in (0.15, 0.2, 0.29)]))
+
+    # a 6-atom register, two masked atoms, tilted field, mask ending inside the first of two pulses' successor
+    reg = Register.from_coordinates([[0, 0], [9, 0], [1, 8], [10, 9], [-8, 3], [4, -9]], prefix="a", center=False)
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch0", "mw_global")
+    seq.set_magnetic_field(0.4, 1.0, 0.7)
+    seq.config_slm_mask(["a1", "a4"])
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(300, 1.1 * np.pi), 0.5, 0.2), "ch0")
+    seq.add(Pulse.ConstantPulse(300, 2.5, -0.8, 0.0), "ch0")
+    spec = specs_of(seq)[0][0]
+    assert spec.slm_end == 300 and sorted(spec.slm_targets) == [1, 4]
+    psi0 = evolve.all_ground_state(spec)
+    save("orc_xy_slm_evolution", spec, psi0=psi0, orc_final=oracle_final(spec, psi0))
+
+
+if __name__ == "__main__" and "--slm" in sys.argv:
+    slm()

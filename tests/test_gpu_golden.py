@@ -46,7 +46,7 @@ def test_get_hamiltonian_reference_goldens(engine):
 @pytest.mark.parametrize("name", [
     "ref_initial_state_sim", "ref_qutip_backend_pi_pulse", "ref_delays_occupation",
     "orc_c1_square", "orc_all_basis_3atoms", "orc_noisy_traj0", "orc_noisy_traj1", "orc_noisy_traj2",
-    "orc_xy_evolution",
+    "orc_xy_evolution", "ref_mask_two_pulses_xy", "orc_xy_slm_evolution",
 ])
 def test_final_state_goldens(engine, name):
     spec, extra = load(name)
@@ -148,3 +148,32 @@ def test_get_xy_hamiltonian_reference_golden(engine):
     vdw = np.array([2 + 1 / 8, 1 / 8, 1, 0, 1, 0, 0, 0]) * c6 / 1e6
     np.testing.assert_array_almost_equal(np.diag(h).real, -1.0 * n_d + vdw)
     assert np.allclose(h, h.conj().T)
+
+
+def test_xy_slm_mask_reference_property(engine):
+    """reference test_simulation.py:1792-1838 (test_mask_two_pulses_xy) through pb200_apply_h: while the SLM mask
+    is on the Hamiltonian is (two-qubit H) x 1, afterwards the unmasked three-qubit one (matrices produced from the
+    real pulser objects by tests/golden/make_golden.py --slm), and in between the spline-weighted mixture the oracle
+    builds from the two QobjEvo terms of hamiltonian.py:399-424."""
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    spec, extra = load("ref_mask_two_pulses_xy")
+    orc = OracleHamiltonian.from_spec(spec)
+    with engine.DevicePlan(spec) as plan:
+        for t, ref in zip((0.01, 0.05, 0.09), extra["h_two_kron"]):
+            np.testing.assert_allclose(dense_h(plan, 8, t), ref, atol=1e-11)
+        for t, ref in zip((0.15, 0.2, 0.29), extra["h_three"]):
+            np.testing.assert_allclose(dense_h(plan, 8, t), ref, atol=1e-11)
+        for t in (0.0985, 0.0995, 0.1003, 0.1012, 0.1049):  # around the switch: interpolated 0/1 coefficient
+            np.testing.assert_allclose(dense_h(plan, 8, t), orc.matrix_at(t).toarray(), atol=1e-11)
+
+
+@pytest.mark.parametrize("integrator", [1, 2])
+def test_xy_slm_mask_evolution_integrators(engine, integrator):
+    spec, extra = load("orc_xy_slm_evolution")
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state(extra["psi0"])
+        st = plan.propagate(0.0, spec.sampling_times[-1], integrator=integrator)
+        got = plan.get_state()[0]
+    assert st["integrator"] == integrator
+    assert np.max(np.abs(got - extra["orc_final"])) < STATE_TOL

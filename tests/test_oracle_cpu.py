@@ -314,3 +314,36 @@ def test_xy_workload_equals_pulser():
     assert np.allclose(ref.interaction_matrix, mine.interaction_matrix, rtol=1e-12, atol=0)
     assert np.allclose(ref.drives[0].coef, mine.drives[0].coef, rtol=1e-12, atol=1e-15)
     assert np.allclose(ref.drives[0].det, mine.drives[0].det, rtol=1e-12, atol=1e-15)
+
+
+def test_golden_xy_slm_mask_two_pulses():
+    """reference tests/pulser_simulation/test_simulation.py:1792-1838 (test_mask_two_pulses_xy): the oracle built
+    from the plain spec reproduces the (two-qubit H) x 1 / three-qubit H matrices that make_golden.py --slm derived
+    from the real pulser objects, and the reference's coefficient arrays (hamiltonian.py:405-421)."""
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    spec, extra = load("ref_mask_two_pulses_xy")
+    c = spec.slm_coefficient()
+    assert c is not None and len(c) == len(spec.sampling_times)
+    assert set(np.unique(c)) == {0.0, 1.0} and c[0] == 0.0 and c[-1] == 1.0
+    # _adapt_to_sampling_rate indexes a (T)-long array with T + 1 indices: the switch lands one sample late
+    assert c[spec.slm_end] == 0.0 and c[spec.slm_end + 1] == 1.0
+    orc = OracleHamiltonian.from_spec(spec)
+    for t, ref in zip((0.01, 0.05, 0.09), extra["h_two_kron"]):
+        np.testing.assert_allclose(orc.matrix_at(t).toarray(), ref, atol=1e-12)
+    for t, ref in zip((0.15, 0.2, 0.29), extra["h_three"]):
+        np.testing.assert_allclose(orc.matrix_at(t).toarray(), ref, atol=1e-12)
+
+
+def test_xy_slm_matrix_free_equals_literal():
+    """oracle/matfree.py (the GPU tests' apply_h reference) handles the masked interaction like the literal oracle."""
+    from oracle.matfree import MatFreeHamiltonian
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    spec, _ = load("orc_xy_slm_evolution")
+    mf = MatFreeHamiltonian(spec)
+    orc = OracleHamiltonian.from_spec(spec)
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=spec.hilbert_dim) + 1j * rng.normal(size=spec.hilbert_dim)
+    for t in (0.05, 0.2995, 0.3004, 0.45):
+        np.testing.assert_allclose(mf.apply(t, v), orc.matrix_at(t) @ v, atol=1e-11)
