@@ -1029,6 +1029,8 @@ __global__ void __launch_bounds__(1 << (TBITS - RB), 2) coop_program_kernel(cons
 // then wc (weight of the SLM-masked part of the interaction, XY mode), w, gamma
 __host__ __device__ inline int gen_table_stride(int n, int n_drives) { return n_drives * 3 * n + 3; }
 
+#define PB200_TILED_MAX_HIGH 40
+#define PB200_MAX_DRIVES_K 3
 struct GenArgs {
     const c2* v; const c2* psi; const c2* b2; c2* out;
     const double* dint; long long dint_stride; long long D;
@@ -1113,6 +1115,117 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
         c2 res = cmul(a.coef.c_g, gv);
         if (a.psi) res = cadd(res, cmul(a.coef.c_psi, a.psi[voff + idx]));
         if (a.b2) res = cadd(res, cmul(a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2, a.b2[voff + idx]));
+        st_c2(a.out + voff + idx, res);
+    }
+}
+
+// ---- tiled stage kernel for d = 3 / 4 (the "all" basis, leakage levels) ---------------------------------------
+// Same maths as stage_generic_kernel without the XY exchange term.  A CTA owns the DIM^K amplitudes that share
+// their n - K most significant digits (one contiguous run, brought in by ONE TMA bulk copy): partners across the
+// K low digits are shared-memory reads selected arithmetically (no divergence: a digit that is neither |to> nor
+// |from> of a drive reads itself with a zero coefficient); the high digits are the same for the whole tile, so
+// their partners are a short CTA-uniform list of (offset, coefficient) pairs served by coalesced loads.
+struct TileExtra { long long off; double gx, gy; };
+
+template <int DIM, int K>
+__global__ void __launch_bounds__(256) stage_tiled_kernel(GenArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ TileExtra extra[PB200_MAX_DRIVES_K * PB200_TILED_MAX_HIGH];
+    __shared__ int n_extra;
+    __shared__ double diag_high;
+
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y;
+    const int n = a.n;
+    const int kk = n < K ? n : K;           // digits inside the tile
+    int tsz = 1;
+    for (int j = 0; j < kk; ++j) tsz *= DIM;
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    double* tab = reinterpret_cast<double*>(smem_raw + (((size_t)tsz * 16 + 127) / 128) * 128);
+    const int stride = gen_table_stride(n, a.n_drives);
+    const long long base = (long long)blockIdx.x * tsz;
+    const long long voff = traj * a.D;
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    for (int i = tid; i < stride; i += blockDim.x) tab[i] = a.table[traj * stride + i];
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&mbar, (uint32_t)tsz * 16u);
+        tma_load_1d(tile, a.v + voff + base, (uint32_t)tsz * 16u, &mbar);
+        // partners across the high digits (identical for every amplitude of the tile)
+        int cnt = 0;
+        double dh = 0.0;
+        long long rem = blockIdx.x, st = tsz;
+        for (int j = kk; j < n; ++j) {       // digit j counted from the least significant one: qudit n - 1 - j
+            const int digit = (int)(rem % DIM);
+            rem /= DIM;
+            const int k = n - 1 - j;
+            for (int q = 0; q < a.n_drives; ++q) {
+                const double* gq = tab + q * 3 * n;
+                if (digit == a.to[q]) {
+                    extra[cnt++] = {(long long)(a.from[q] - a.to[q]) * st, gq[2 * k], gq[2 * k + 1]};
+                } else if (digit == a.from[q]) {
+                    extra[cnt++] = {(long long)(a.to[q] - a.from[q]) * st, gq[2 * k], -gq[2 * k + 1]};
+                    dh -= gq[2 * n + k];
+                }
+            }
+            st *= DIM;
+        }
+        n_extra = cnt;
+        diag_high = dh;
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+
+    const double w = tab[stride - 2], gamma = tab[stride - 1];
+    const c2 cb2 = a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2;
+    const int nex = n_extra;
+    const double dhigh = diag_high - gamma;
+    const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
+    for (int t = tid; t < tsz; t += blockDim.x) {
+        const long long idx = base + t;
+        // own-element operands first: their latency overlaps the shared-memory gathers
+        const double dv = dsrc ? __ldcs(dsrc + idx) : 0.0;
+        c2 pv0 = {0.0, 0.0}, bv0 = {0.0, 0.0};
+        if (a.psi) { const double2 r = __ldcs(reinterpret_cast<const double2*>(a.psi + voff + idx)); pv0 = {r.x, r.y}; }
+        if (a.b2) { const double2 r = __ldcs(reinterpret_cast<const double2*>(a.b2 + voff + idx)); bv0 = {r.x, r.y}; }
+        const c2 vo = tile[t];
+        double diag = dhigh, rr = 0.0, ri = 0.0;
+        int rem = t, st = 1;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < kk) {
+                const int digit = rem % DIM;
+                rem /= DIM;
+                const int k = n - 1 - j;
+                for (int q = 0; q < a.n_drives; ++q) {
+                    const double* gq = tab + q * 3 * n;
+                    const bool is_to = digit == a.to[q], is_from = digit == a.from[q];
+                    const int delta = is_to ? (a.from[q] - a.to[q]) : (is_from ? (a.to[q] - a.from[q]) : 0);
+                    const c2 pv = tile[t + delta * st];
+                    const double use = (is_to || is_from) ? 1.0 : 0.0;
+                    const double gx = gq[2 * k] * use;
+                    const double gy = is_to ? gq[2 * k + 1] : (is_from ? -gq[2 * k + 1] : 0.0);
+                    rr = fma(gx, pv.x, rr); rr = fma(-gy, pv.y, rr);
+                    ri = fma(gx, pv.y, ri); ri = fma(gy, pv.x, ri);
+                    diag -= is_from ? gq[2 * n + k] : 0.0;
+                }
+                st *= DIM;
+            }
+        }
+#pragma unroll 4
+        for (int e = 0; e < nex; ++e) {
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + voff + idx + extra[e].off));
+            const double gx = extra[e].gx, gy = extra[e].gy;
+            rr = fma(gx, raw.x, rr); rr = fma(-gy, raw.y, rr);
+            ri = fma(gx, raw.y, ri); ri = fma(gy, raw.x, ri);
+        }
+        diag = fma(w, dv, diag);
+        const c2 gv = {fma(diag, vo.x, rr), fma(diag, vo.y, ri)};
+        c2 res = cmul(a.coef.c_g, gv);
+        res = cadd(res, cmul(a.coef.c_psi, pv0));
+        res = cadd(res, cmul(cb2, bv0));
         st_c2(a.out + voff + idx, res);
     }
 }

@@ -138,6 +138,8 @@ struct Plan {
     PassGeom fwd_geo[3];
     c2* wbuf[2] = {nullptr, nullptr};  // forwarded sums, one vector per chain
     int fwd_flags = 0;              // PB200_FWD_FLAGS: operand staging switches of stage_d2_fwd_kernel
+    bool use_tiled = true;          // PB200_TILED: d = 3 / 4 registers use stage_tiled_kernel
+    bool tiled_big = false;         // PB200_TILED_BIG: one more digit per tile (3^8 / 4^6 amplitudes)
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -363,6 +365,23 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             a.xy_u = P.xy_u; a.xy_d = P.xy_d;
             a.slm_mask = P.has_slm ? P.slm_bits : 0ULL; a.dint2 = (P.has_slm && P.has_interaction) ? P.dint2 : nullptr;
             int threads = 256;
+            if (P.use_tiled && !P.has_xy && (P.dim == 3 || P.dim == 4) && N <= PB200_TILED_MAX_HIGH) {
+                // tiled kernel: one CTA per run of dim^K amplitudes (K low digits in shared memory)
+                const int K = (P.dim == 3) ? (P.tiled_big ? 8 : 7) : (P.tiled_big ? 6 : 5);
+                long long tsz = 1;
+                for (int j = 0; j < std::min(K, N); ++j) tsz *= P.dim;
+                dim3 tgrid((unsigned)(P.D / tsz), (unsigned)P.B);
+                const size_t tsmem = (((size_t)tsz * 16 + 127) / 128) * 128 + (size_t)gen_table_stride(N, P.n_drives) * 8;
+                if (P.dim == 3) {
+                    if (P.tiled_big) stage_tiled_kernel<3, 8><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    else stage_tiled_kernel<3, 7><<<tgrid, threads, tsmem, P.stream>>>(a);
+                } else {
+                    if (P.tiled_big) stage_tiled_kernel<4, 6><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    else stage_tiled_kernel<4, 5><<<tgrid, threads, tsmem, P.stream>>>(a);
+                }
+                ++launches;
+                continue;
+            }
             long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
             dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
             size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8 + (P.has_xy ? (size_t)N * N * 8 : 0);
@@ -1734,6 +1753,8 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_fwd = env_int("PB200_FWD", 0);
     P.fwd_flags = env_int("PB200_FWD_FLAGS", 0);
+    P.use_tiled = env_int("PB200_TILED", 1) != 0;
+    P.tiled_big = env_int("PB200_TILED_BIG", 0) != 0;
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;
@@ -1771,6 +1792,10 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
         CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
 #define PB200_FWD_ATTR(TB, RB)                                                                                                              \
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, true, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   \
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  \

@@ -13,8 +13,7 @@ reference's own pulser-core code; ``Hamiltonian(...)`` construction
 Collapse operators (``simulation.py:705-735``) run as a master equation on the
 vectorised density matrix (``lindblad.py``, registers with dim^(2N) <= 2^26) and
 as Monte-Carlo wave functions beyond that (``n_trajectories`` set).  XY mode runs
-the coherent path (SLM mask included: ``pb200_plan_set_slm_mask``) and the Monte-Carlo
-path; not on the CUDA path (raise ``NotImplementedError``): XY master equation.
+the same paths (SLM mask included: ``pb200_plan_set_slm_mask``).
 """
 from __future__ import annotations
 
@@ -370,8 +369,6 @@ class B200Emulator:
 
     def _density_matrix_fits(self) -> bool:
         hd = self._hamiltonian_data
-        if hd.basis_data.interaction_type == "XY":  # exchange term not vectorised: Monte-Carlo path
-            return False
         return hd.basis_data.dim <= 3 and hd.basis_data.dim ** (2 * hd.n_qudits) <= (1 << 26)
 
     def _use_mcwf(self) -> bool:

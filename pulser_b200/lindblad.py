@@ -9,7 +9,8 @@ Here the density matrix is vectorised row-major, ``vec(rho)[i*D + j] = rho[i,j]`
 i.e. it is the state of 2N qudits: row digits evolve under ``H``, column digits
 under ``-H^T``.  For the Pulser Hamiltonian that is again a Pulser-shaped
 Hamiltonian (drive ``-conj(c)``, detuning ``-det``, interaction ``-U`` on the
-column qudits), so the unitary part reuses the Schroedinger kernels unchanged;
+column qudits; in XY mode the real symmetric exchange couplings become ``-U^xy``
+there as well), so the unitary part reuses the Schroedinger kernels unchanged;
 the dissipator of single-qudit collapse operators factorises into one
 ``d^2 x d^2`` matrix per (row digit, column digit) pair (``pair_op_kernel``).
 The two are combined by symmetric splitting + Richardson extrapolation inside
@@ -64,6 +65,9 @@ def doubled_spec(spec: HamiltonianSpec) -> HamiltonianSpec:
         drives=drives,
         collapse_ops=np.zeros((0, spec.dim, spec.dim), dtype=np.complex128),
         qubit_ids=[f"row{i}" for i in range(n)] + [f"col{i}" for i in range(n)],
+        # XY + SLM mask: the masked pairs of the row block and of the column block switch on together
+        slm_end=spec.slm_end,
+        slm_targets=list(spec.slm_targets) + [t + n for t in spec.slm_targets],
     )
 
 
@@ -78,8 +82,6 @@ class LindbladPlan:
         s0 = self.specs[0]
         if s0.dim > 3:
             raise NotImplementedError("Lindblad path: d <= 3")
-        if s0.interaction_type == "XY":
-            raise NotImplementedError("Lindblad path: XY exchange term is not vectorised (use the Monte-Carlo path)")
         if len(s0.collapse_ops) == 0:
             raise ValueError("no collapse operators: use DevicePlan")
         # a non-interacting original must not acquire an interaction through has_interaction()

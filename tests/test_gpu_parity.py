@@ -236,6 +236,33 @@ def test_lindblad_vs_oracle_mesolve(engine, n, kind):
     assert np.trace(rho @ rho).real < 0.999
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_lindblad_xy_vs_oracle_mesolve(engine, masked):
+    """XY master equation (exchange couplings doubled onto the column qudits with the opposite sign), with and
+    without an SLM mask, against the dense-Lindblad oracle."""
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+    from pulser_b200.lindblad import LindbladPlan
+
+    spec = W.config_xy(n=3, seed=4, t_total=300, magnetic_field=(0.3, 1.0, 0.5))
+    # sqrt(2 G_d)|u><u| (dephasing) and sqrt(G)|d><u| (decay) in the [u, d] eigenbasis
+    spec.collapse_ops = np.asarray([np.sqrt(2 * 0.25) * np.array([[1, 0], [0, 0]]),
+                                    np.sqrt(0.3) * np.array([[0, 0], [1, 0]])], dtype=complex)
+    if masked:
+        spec.slm_end, spec.slm_targets = 120, [1]
+    tf = spec.sampling_times[-1]
+    H = OracleHamiltonian.from_spec(spec)
+    psi0 = random_state(spec.hilbert_dim, 6)
+    ref = evolve.mesolve(H, psi0, [0.0, tf])[-1]
+    with LindbladPlan(spec) as lp:
+        lp.set_state(psi0)
+        lp.propagate(0.0, tf)
+        rho = lp.get_rho()[0]
+    assert abs(np.trace(rho).real - 1.0) < 1e-6
+    assert np.max(np.abs(rho - ref)) < LINDBLAD_TOL
+    assert np.trace(rho @ rho).real < 0.999
+
+
 # ---------------------------------------------------------------------------
 # 3-level "all" basis (BASELINE config C3) and noisy trajectories (C4)
 def test_c3_all_basis_vs_oracle(engine):
@@ -263,6 +290,43 @@ def test_c3_larger_register_properties(engine):
             assert abs(plan.norm2()[0] - 1.0) < 1e-9
             outs.append(plan.get_state()[0])
     assert np.max(np.abs(outs[0] - outs[1])) < STATE_TOL
+
+
+def _multilevel_spec(n, dim, seed=0, T=48):
+    """'all'-basis register (digital + ground-rydberg drives) with per-atom complex tables; dim 4 adds a leakage
+    level |x> that no drive touches."""
+    base = W.config_c3(n=n, t_raman=T // 3, t_ryd=T - 2 * (T // 3))
+    rng = np.random.default_rng(seed)
+    nt = len(base.sampling_times)
+    for d in base.drives:  # make the rows differ (noisy-trajectory shape) and the drives complex
+        d.coef = d.coef * rng.normal(1.0, 0.1, size=(n, 1)) * np.exp(1j * rng.uniform(-1, 1, size=(n, 1)))
+        d.det = d.det + rng.normal(0.0, 0.5, size=(n, 1)) * (np.arange(nt) < nt - 1)
+        d.uniform = False
+    if dim == 4:
+        base.eigenbasis = list(base.eigenbasis) + ["x"]
+        base.dim = 4
+    return base
+
+
+@pytest.mark.parametrize("n,dim,big", [(3, 3, 0), (7, 3, 0), (8, 3, 0), (9, 3, 1), (10, 3, 0), (5, 4, 0), (7, 4, 0), (7, 4, 1)])
+def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, big):
+    """stage_tiled_kernel (d = 3 / 4) == matrix-free oracle == the one-thread-per-amplitude generic kernel."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    spec = _multilevel_spec(n, dim, seed=n)
+    mf = MatFreeHamiltonian(spec)
+    v = random_state(spec.hilbert_dim, n)
+    out = {}
+    for tiled in (1, 0):
+        monkeypatch.setenv("PB200_TILED", str(tiled))
+        monkeypatch.setenv("PB200_TILED_BIG", str(big))
+        with engine.DevicePlan(spec) as plan:
+            out[tiled] = [plan.apply_h(t, v) for t in (0.0071, 0.0302)]
+    for t, got, gen in zip((0.0071, 0.0302), out[1], out[0]):
+        ref = mf.apply(t, v)
+        scale = max(1.0, np.max(np.abs(ref)))
+        assert np.max(np.abs(got - ref)) < 1e-12 * scale
+        assert np.max(np.abs(got - gen)) < 1e-12 * scale
 
 
 def test_c4_noisy_trajectories_batch_vs_oracle(engine):

@@ -347,3 +347,20 @@ def test_xy_slm_matrix_free_equals_literal():
     v = rng.normal(size=spec.hilbert_dim) + 1j * rng.normal(size=spec.hilbert_dim)
     for t in (0.05, 0.2995, 0.3004, 0.45):
         np.testing.assert_allclose(mf.apply(t, v), orc.matrix_at(t) @ v, atol=1e-11)
+
+
+def test_doubled_xy_spec_is_the_commutator_generator():
+    """pulser_b200/lindblad.py::doubled_spec in XY mode with an SLM mask: the 2N-qudit Hamiltonian is
+    H (x) 1 - 1 (x) H^T, between samples too (host logic of the XY master equation)."""
+    from oracle.ref_hamiltonian import OracleHamiltonian
+    from pulser_b200.lindblad import doubled_spec
+
+    spec = W.config_xy(n=3, seed=4, t_total=300, magnetic_field=(0.3, 1.0, 0.5))
+    spec.slm_end, spec.slm_targets = 120, [1]
+    d = doubled_spec(spec)
+    assert d.slm_targets == [1, 4] and np.array_equal(d.slm_coefficient(), spec.slm_coefficient())
+    H, Hd = OracleHamiltonian.from_spec(spec), OracleHamiltonian.from_spec(d)
+    eye = np.eye(8)
+    for t in (0.05, 0.1207, 0.25):
+        h = H.matrix_at(t).toarray()
+        np.testing.assert_allclose(Hd.matrix_at(t).toarray(), np.kron(h, eye) - np.kron(eye, h.T), atol=1e-12)
