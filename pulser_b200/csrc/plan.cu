@@ -139,7 +139,7 @@ struct Plan {
     c2* wbuf[2] = {nullptr, nullptr};  // forwarded sums, one vector per chain
     int fwd_flags = 0;              // PB200_FWD_FLAGS: operand staging switches of stage_d2_fwd_kernel
     bool use_tiled = true;          // PB200_TILED: d = 3 / 4 registers use stage_tiled_kernel
-    bool tiled_big = false;         // PB200_TILED_BIG: one more digit per tile (3^8 / 4^6 amplitudes)
+    int tiled_k = 0;                // PB200_TILED_K: digits per tile (d = 3: 6..8, default 7; d = 4: 4..6, default 5)
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -367,17 +367,20 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             int threads = 256;
             if (P.use_tiled && !P.has_xy && (P.dim == 3 || P.dim == 4) && N <= PB200_TILED_MAX_HIGH) {
                 // tiled kernel: one CTA per run of dim^K amplitudes (K low digits in shared memory)
-                const int K = (P.dim == 3) ? (P.tiled_big ? 8 : 7) : (P.tiled_big ? 6 : 5);
+                const int Kdef = (P.dim == 3) ? 7 : 5;
+                const int K = std::min(Kdef + 1, std::max(Kdef - 1, P.tiled_k ? P.tiled_k : Kdef));
                 long long tsz = 1;
                 for (int j = 0; j < std::min(K, N); ++j) tsz *= P.dim;
                 dim3 tgrid((unsigned)(P.D / tsz), (unsigned)P.B);
                 const size_t tsmem = (((size_t)tsz * 16 + 127) / 128) * 128 + (size_t)gen_table_stride(N, P.n_drives) * 8;
                 if (P.dim == 3) {
-                    if (P.tiled_big) stage_tiled_kernel<3, 8><<<tgrid, threads, tsmem, P.stream>>>(a);
-                    else stage_tiled_kernel<3, 7><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    if (K == 8) stage_tiled_kernel<3, 8><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    else if (K == 7) stage_tiled_kernel<3, 7><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    else stage_tiled_kernel<3, 6><<<tgrid, threads, tsmem, P.stream>>>(a);
                 } else {
-                    if (P.tiled_big) stage_tiled_kernel<4, 6><<<tgrid, threads, tsmem, P.stream>>>(a);
-                    else stage_tiled_kernel<4, 5><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    if (K == 6) stage_tiled_kernel<4, 6><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    else if (K == 5) stage_tiled_kernel<4, 5><<<tgrid, threads, tsmem, P.stream>>>(a);
+                    else stage_tiled_kernel<4, 4><<<tgrid, threads, tsmem, P.stream>>>(a);
                 }
                 ++launches;
                 continue;
@@ -1754,7 +1757,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_fwd = env_int("PB200_FWD", 0);
     P.fwd_flags = env_int("PB200_FWD_FLAGS", 0);
     P.use_tiled = env_int("PB200_TILED", 1) != 0;
-    P.tiled_big = env_int("PB200_TILED_BIG", 0) != 0;
+    P.tiled_k = env_int("PB200_TILED_K", 0);
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
     P.sm_count = prop.multiProcessorCount;

@@ -294,6 +294,24 @@ def slm():
     psi0 = evolve.all_ground_state(spec)
     save("orc_xy_slm_evolution", spec, psi0=psi0, orc_final=oracle_final(spec, psi0))
 
+    # reference tests/pulser_simulation/test_simulation.py:1960-1998 (test_effective_size_disjoint, mw_global):
+    # SPAM leaves atom0 and atom2 unprepared (seed 15092021), the SLM mask covers atom1, so fewer than two good
+    # unmasked atoms remain: H(0) = 0.5 * amp * sigma_x on atom3 alone (no interaction, masked atom not driven).
+    np.random.seed(15092021)
+    seq = Sequence(Register.square(2, prefix="atom"), MockDevice)
+    seq.declare_channel("ch0", "mw_global")
+    seq.add(Pulse.ConstantPulse(1500, 1, 0, 0), "ch0")
+    seq.config_slm_mask(["atom1"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nm = NoiseModel(samples_per_run=5, state_prep_error=0.4, p_false_pos=0.01, p_false_neg=0.05)
+    spec = specs_of(seq, nm, n_traj=15, rate=0.01)[0][0]
+    assert list(spec.bad_atoms) == [True, False, True, False], spec.bad_atoms
+    assert spec.slm_targets == [1] and spec.slm_end == 1500
+    sx3 = np.kron(np.eye(8), np.array([[0.0, 1.0], [1.0, 0.0]]))
+    np.testing.assert_allclose(OracleHamiltonian.from_spec(spec).matrix_at(0.0).toarray(), 0.5 * sx3, atol=1e-14)
+    save("ref_effective_size_disjoint_xy", spec, h0=0.5 * sx3)
+
 
 if __name__ == "__main__" and "--slm" in sys.argv:
     slm()

@@ -177,3 +177,13 @@ def test_xy_slm_mask_evolution_integrators(engine, integrator):
         got = plan.get_state()[0]
     assert st["integrator"] == integrator
     assert np.max(np.abs(got - extra["orc_final"])) < STATE_TOL
+
+
+def test_effective_size_disjoint_xy_reference_golden(engine):
+    """reference test_simulation.py:1960-1998 through pb200_apply_h (bad atoms + SLM mask in XY mode)."""
+    spec, extra = load("ref_effective_size_disjoint_xy")
+    with engine.DevicePlan(spec) as plan:
+        np.testing.assert_allclose(dense_h(plan, 16, 0.0), extra["h0"], atol=1e-13)
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1])
+        assert abs(plan.norm2()[0] - 1.0) < 1e-10

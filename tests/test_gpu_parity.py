@@ -308,8 +308,8 @@ def _multilevel_spec(n, dim, seed=0, T=48):
     return base
 
 
-@pytest.mark.parametrize("n,dim,big", [(3, 3, 0), (7, 3, 0), (8, 3, 0), (9, 3, 1), (10, 3, 0), (5, 4, 0), (7, 4, 0), (7, 4, 1)])
-def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, big):
+@pytest.mark.parametrize("n,dim,k", [(3, 3, 0), (7, 3, 0), (8, 3, 6), (9, 3, 8), (10, 3, 0), (5, 4, 0), (7, 4, 4), (7, 4, 6)])
+def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, k):
     """stage_tiled_kernel (d = 3 / 4) == matrix-free oracle == the one-thread-per-amplitude generic kernel."""
     from oracle.matfree import MatFreeHamiltonian
 
@@ -319,7 +319,7 @@ def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, big):
     out = {}
     for tiled in (1, 0):
         monkeypatch.setenv("PB200_TILED", str(tiled))
-        monkeypatch.setenv("PB200_TILED_BIG", str(big))
+        monkeypatch.setenv("PB200_TILED_K", str(k))
         with engine.DevicePlan(spec) as plan:
             out[tiled] = [plan.apply_h(t, v) for t in (0.0071, 0.0302)]
     for t, got, gen in zip((0.0071, 0.0302), out[1], out[0]):

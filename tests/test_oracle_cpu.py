@@ -364,3 +364,13 @@ def test_doubled_xy_spec_is_the_commutator_generator():
     for t in (0.05, 0.1207, 0.25):
         h = H.matrix_at(t).toarray()
         np.testing.assert_allclose(Hd.matrix_at(t).toarray(), np.kron(h, eye) - np.kron(eye, h.T), atol=1e-12)
+
+
+def test_golden_effective_size_disjoint_xy():
+    """reference tests/pulser_simulation/test_simulation.py:1960-1998 (test_effective_size_disjoint, mw_global):
+    two unprepared atoms + one SLM-masked atom leave H(0) = 0.5 amp sigma_x on the last atom."""
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    spec, extra = load("ref_effective_size_disjoint_xy")
+    assert list(spec.bad_atoms) == [True, False, True, False] and spec.slm_targets == [1]
+    np.testing.assert_allclose(OracleHamiltonian.from_spec(spec).matrix_at(0.0).toarray(), extra["h0"], atol=1e-14)
