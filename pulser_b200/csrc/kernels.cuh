@@ -1230,6 +1230,170 @@ __global__ void __launch_bounds__(256) stage_tiled_kernel(GenArgs a) {
     }
 }
 
+// ---- register-blocked tiled stage kernel for d = 3 / 4 --------------------------------------------------------
+// stage_tiled_kernel is instruction-bound (ncu on C3: 1053 thread instructions per amplitude, issue-active 62 %,
+// DRAM 10 %: the digit decomposition, the coefficient selects and the table reads are redone for every amplitude).
+// Here a thread owns the R = DIM^RBD amplitudes that differ in the top RBD tile digits and keeps their
+// accumulators in registers: digits, selects and coefficients are computed once per (digit, drive) and reused for
+// the R amplitudes, exactly as the d = 2 kernel reuses them across its register block.
+__host__ __device__ constexpr int ipow_c(int b, int e) { return e <= 0 ? 1 : b * ipow_c(b, e - 1); }
+
+template <int DIM, int K, int RBD>
+__global__ void __launch_bounds__(256, 2) stage_multilevel_rb_kernel(GenArgs a) {
+    constexpr int R = ipow_c(DIM, RBD);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ TileExtra extra[PB200_MAX_DRIVES_K * PB200_TILED_MAX_HIGH];
+    __shared__ int n_extra;
+    __shared__ double diag_high;
+
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y;
+    const int n = a.n;
+    const int kk = n < K ? n : K;           // digits inside the tile (host guarantees kk >= RBD)
+    int nt_act = 1;
+    for (int j = 0; j < kk - RBD; ++j) nt_act *= DIM;   // active threads = stride of the first register digit
+    const int tsz = nt_act * R;
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    double* tab = reinterpret_cast<double*>(smem_raw + (((size_t)tsz * 16 + 127) / 128) * 128);
+    const int stride = gen_table_stride(n, a.n_drives);
+    const long long base = (long long)blockIdx.x * tsz;
+    const long long voff = traj * a.D;
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    for (int i = tid; i < stride; i += blockDim.x) tab[i] = a.table[traj * stride + i];
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&mbar, (uint32_t)tsz * 16u);
+        tma_load_1d(tile, a.v + voff + base, (uint32_t)tsz * 16u, &mbar);
+        int cnt = 0;
+        double dh = 0.0;
+        long long rem = blockIdx.x, st = tsz;
+        for (int j = kk; j < n; ++j) {
+            const int digit = (int)(rem % DIM);
+            rem /= DIM;
+            const int k = n - 1 - j;
+            for (int q = 0; q < a.n_drives; ++q) {
+                const double* gq = tab + q * 3 * n;
+                if (digit == a.to[q]) {
+                    extra[cnt++] = {(long long)(a.from[q] - a.to[q]) * st, gq[2 * k], gq[2 * k + 1]};
+                } else if (digit == a.from[q]) {
+                    extra[cnt++] = {(long long)(a.to[q] - a.from[q]) * st, gq[2 * k], -gq[2 * k + 1]};
+                    dh -= gq[2 * n + k];
+                }
+            }
+            st *= DIM;
+        }
+        n_extra = cnt;
+        diag_high = dh;
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+    if (tid >= nt_act) return;
+
+    double rr[R], ri[R], dd[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { rr[i] = 0.0; ri[i] = 0.0; dd[i] = 0.0; }
+    double diag_low = 0.0;
+    // --- the tile digits below the register block: selects once per (digit, drive), R shared-memory reads ---
+    {
+        int rem = tid, st = 1;
+#pragma unroll
+        for (int j = 0; j < K - RBD; ++j) {
+            if (j < kk - RBD) {
+                const int digit = rem % DIM;
+                rem /= DIM;
+                const int k = n - 1 - j;
+                for (int q = 0; q < a.n_drives; ++q) {
+                    const double* gq = tab + q * 3 * n;
+                    const bool is_to = digit == a.to[q], is_from = digit == a.from[q];
+                    if (is_to || is_from) {
+                        const int off = tid + (is_to ? (a.from[q] - a.to[q]) : (a.to[q] - a.from[q])) * st;
+                        const double gx = gq[2 * k];
+                        const double gy = is_to ? gq[2 * k + 1] : -gq[2 * k + 1];
+                        diag_low -= is_from ? gq[2 * n + k] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            const c2 pv = tile[off + i * nt_act];
+                            rr[i] = fma(gx, pv.x, rr[i]); rr[i] = fma(-gy, pv.y, rr[i]);
+                            ri[i] = fma(gx, pv.y, ri[i]); ri[i] = fma(gy, pv.x, ri[i]);
+                        }
+                    }
+                }
+                st *= DIM;
+            }
+        }
+    }
+    // --- the register-block digits: the digit of amplitude i is a compile-time constant ---
+#pragma unroll
+    for (int jj = 0; jj < RBD; ++jj) {
+        const int j = kk - RBD + jj;
+        const int k = n - 1 - j;
+        const int stj = nt_act * ipow_c(DIM, jj);
+        for (int q = 0; q < a.n_drives; ++q) {
+            const double* gq = tab + q * 3 * n;
+            const double gx0 = gq[2 * k], gy0 = gq[2 * k + 1], th = gq[2 * n + k];
+            const int to = a.to[q], from = a.from[q];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int digit = (i / ipow_c(DIM, jj)) % DIM;
+                const bool is_to = digit == to, is_from = digit == from;
+                if (is_to || is_from) {   // uniform across the CTA
+                    const c2 pv = tile[tid + i * nt_act + (is_to ? (from - to) : (to - from)) * stj];
+                    const double gy = is_to ? gy0 : -gy0;
+                    rr[i] = fma(gx0, pv.x, rr[i]); rr[i] = fma(-gy, pv.y, rr[i]);
+                    ri[i] = fma(gx0, pv.y, ri[i]); ri[i] = fma(gy, pv.x, ri[i]);
+                    dd[i] -= is_from ? th : 0.0;
+                }
+            }
+        }
+    }
+    // --- the digits above the tile: CTA-uniform (offset, coefficient) list, coalesced loads ---
+    const c2* vbase = a.v + voff + base + tid;
+    const int nex = n_extra;
+    for (int e = 0; e < nex; ++e) {
+        const long long off = extra[e].off;
+        const double gx = extra[e].gx, gy = extra[e].gy;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(vbase + off + i * nt_act));
+            rr[i] = fma(gx, raw.x, rr[i]); rr[i] = fma(-gy, raw.y, rr[i]);
+            ri[i] = fma(gx, raw.y, ri[i]); ri[i] = fma(gy, raw.x, ri[i]);
+        }
+    }
+    // --- epilogue ---
+    const double w = tab[stride - 2], gamma = tab[stride - 1];
+    const c2 cb2 = a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2;
+    const double dcommon = diag_high + diag_low - gamma;
+    const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
+    constexpr int H = (R % 3 == 0) ? 3 : 4;
+#pragma unroll
+    for (int h0 = 0; h0 < R; h0 += H) {
+        double dv[H];
+        c2 pv[H], bv[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const long long idx = base + tid + (long long)(h0 + r) * nt_act;
+            dv[r] = dsrc ? __ldcs(dsrc + idx) : 0.0;
+            pv[r] = {0.0, 0.0}; bv[r] = {0.0, 0.0};
+            if (a.psi) { const double2 t2 = __ldcs(reinterpret_cast<const double2*>(a.psi + voff + idx)); pv[r] = {t2.x, t2.y}; }
+            if (a.b2) { const double2 t2 = __ldcs(reinterpret_cast<const double2*>(a.b2 + voff + idx)); bv[r] = {t2.x, t2.y}; }
+        }
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const int i = h0 + r;
+            const long long idx = base + tid + (long long)i * nt_act;
+            const c2 vo = tile[tid + i * nt_act];
+            const double diag = fma(w, dv[r], dcommon + dd[i]);
+            const c2 gv = {fma(diag, vo.x, rr[i]), fma(diag, vo.y, ri[i])};
+            c2 res = cmul(a.coef.c_g, gv);
+            res = cadd(res, cmul(a.coef.c_psi, pv[r]));
+            res = cadd(res, cmul(cb2, bv[r]));
+            st_c2(a.out + voff + idx, res);
+        }
+    }
+}
+
 // ---- interaction diagonal ---------------------------------------------------
 // Dint[s] = sum_{i<j} U_ij [digit_i == r][digit_j == r]
 // (make_vdw_term, hamiltonian.py:260-274, after the + dag doubling of 0.5*U)

@@ -138,7 +138,7 @@ struct Plan {
     PassGeom fwd_geo[3];
     c2* wbuf[2] = {nullptr, nullptr};  // forwarded sums, one vector per chain
     int fwd_flags = 0;              // PB200_FWD_FLAGS: operand staging switches of stage_d2_fwd_kernel
-    bool use_tiled = true;          // PB200_TILED: d = 3 / 4 registers use stage_tiled_kernel
+    int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 2 plain tiled kernel, 0 generic
     int tiled_k = 0;                // PB200_TILED_K: digits per tile (d = 3: 6..8, default 7; d = 4: 4..6, default 5)
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
@@ -365,6 +365,19 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             a.xy_u = P.xy_u; a.xy_d = P.xy_d;
             a.slm_mask = P.has_slm ? P.slm_bits : 0ULL; a.dint2 = (P.has_slm && P.has_interaction) ? P.dint2 : nullptr;
             int threads = 256;
+            if (P.use_tiled == 1 && !P.has_xy && (P.dim == 3 || P.dim == 4) && N <= PB200_TILED_MAX_HIGH &&
+                N >= (P.dim == 3 ? 2 : 1)) {
+                // register-blocked tiled kernel: 3^7 (9 amplitudes per thread) / 4^5 (4 per thread) amplitudes per CTA
+                const int K = (P.dim == 3) ? 7 : 5;
+                long long tsz = 1;
+                for (int j = 0; j < std::min(K, N); ++j) tsz *= P.dim;
+                dim3 tgrid((unsigned)(P.D / tsz), (unsigned)P.B);
+                const size_t tsmem = (((size_t)tsz * 16 + 127) / 128) * 128 + (size_t)gen_table_stride(N, P.n_drives) * 8;
+                if (P.dim == 3) stage_multilevel_rb_kernel<3, 7, 2><<<tgrid, threads, tsmem, P.stream>>>(a);
+                else stage_multilevel_rb_kernel<4, 5, 1><<<tgrid, threads, tsmem, P.stream>>>(a);
+                ++launches;
+                continue;
+            }
             if (P.use_tiled && !P.has_xy && (P.dim == 3 || P.dim == 4) && N <= PB200_TILED_MAX_HIGH) {
                 // tiled kernel: one CTA per run of dim^K amplitudes (K low digits in shared memory)
                 const int Kdef = (P.dim == 3) ? 7 : 5;
@@ -1756,7 +1769,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_fwd = env_int("PB200_FWD", 0);
     P.fwd_flags = env_int("PB200_FWD_FLAGS", 0);
-    P.use_tiled = env_int("PB200_TILED", 1) != 0;
+    P.use_tiled = env_int("PB200_TILED", 1);
     P.tiled_k = env_int("PB200_TILED_K", 0);
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));

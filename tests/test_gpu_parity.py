@@ -308,7 +308,7 @@ def _multilevel_spec(n, dim, seed=0, T=48):
     return base
 
 
-@pytest.mark.parametrize("n,dim,k", [(3, 3, 0), (7, 3, 0), (8, 3, 6), (9, 3, 8), (10, 3, 0), (5, 4, 0), (7, 4, 4), (7, 4, 6)])
+@pytest.mark.parametrize("n,dim,k", [(2, 3, 0), (3, 3, 0), (7, 3, 0), (8, 3, 6), (9, 3, 8), (10, 3, 0), (1, 4, 0), (5, 4, 0), (7, 4, 4), (7, 4, 6)])
 def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, k):
     """stage_tiled_kernel (d = 3 / 4) == matrix-free oracle == the one-thread-per-amplitude generic kernel."""
     from oracle.matfree import MatFreeHamiltonian
@@ -317,16 +317,16 @@ def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, k):
     mf = MatFreeHamiltonian(spec)
     v = random_state(spec.hilbert_dim, n)
     out = {}
-    for tiled in (1, 0):
+    for tiled in (1, 2, 0):  # register-blocked tiled, plain tiled, generic
         monkeypatch.setenv("PB200_TILED", str(tiled))
         monkeypatch.setenv("PB200_TILED_K", str(k))
         with engine.DevicePlan(spec) as plan:
             out[tiled] = [plan.apply_h(t, v) for t in (0.0071, 0.0302)]
-    for t, got, gen in zip((0.0071, 0.0302), out[1], out[0]):
+    for i, t in enumerate((0.0071, 0.0302)):
         ref = mf.apply(t, v)
         scale = max(1.0, np.max(np.abs(ref)))
-        assert np.max(np.abs(got - ref)) < 1e-12 * scale
-        assert np.max(np.abs(got - gen)) < 1e-12 * scale
+        for tiled in (1, 2, 0):
+            assert np.max(np.abs(out[tiled][i] - ref)) < 1e-12 * scale, tiled
 
 
 def test_c4_noisy_trajectories_batch_vs_oracle(engine):
