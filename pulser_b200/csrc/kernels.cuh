@@ -1266,26 +1266,38 @@ __global__ void __launch_bounds__(256, 2) stage_multilevel_rb_kernel(GenArgs a) 
     if (tid == 0) {
         mbar_arrive_expect_tx(&mbar, (uint32_t)tsz * 16u);
         tma_load_1d(tile, a.v + voff + base, (uint32_t)tsz * 16u, &mbar);
+    }
+    if (tid < 32) {
+        // partners across the digits above the tile: one lane per (digit, drive), compacted in order by ballot
         int cnt = 0;
         double dh = 0.0;
-        long long rem = blockIdx.x, st = tsz;
-        for (int j = kk; j < n; ++j) {
-            const int digit = (int)(rem % DIM);
-            rem /= DIM;
-            const int k = n - 1 - j;
-            for (int q = 0; q < a.n_drives; ++q) {
+        const int total = (n - kk) * a.n_drives;
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + tid;
+            bool valid = false;
+            TileExtra te = {0, 0.0, 0.0};
+            if (e < total) {
+                const int j = kk + e / a.n_drives, q = e % a.n_drives;
+                long long rem = blockIdx.x, st = tsz;
+                for (int jj = kk; jj < j; ++jj) { rem /= DIM; st *= DIM; }
+                const int digit = (int)(rem % DIM);
+                const int k = n - 1 - j;
                 const double* gq = tab + q * 3 * n;
                 if (digit == a.to[q]) {
-                    extra[cnt++] = {(long long)(a.from[q] - a.to[q]) * st, gq[2 * k], gq[2 * k + 1]};
+                    valid = true;
+                    te = {(long long)(a.from[q] - a.to[q]) * st, gq[2 * k], gq[2 * k + 1]};
                 } else if (digit == a.from[q]) {
-                    extra[cnt++] = {(long long)(a.to[q] - a.from[q]) * st, gq[2 * k], -gq[2 * k + 1]};
+                    valid = true;
+                    te = {(long long)(a.to[q] - a.from[q]) * st, gq[2 * k], -gq[2 * k + 1]};
                     dh -= gq[2 * n + k];
                 }
             }
-            st *= DIM;
+            const unsigned m = __ballot_sync(0xffffffffu, valid);
+            if (valid) extra[cnt + __popc(m & ((1u << tid) - 1u))] = te;
+            cnt += __popc(m);
         }
-        n_extra = cnt;
-        diag_high = dh;
+        for (int o = 16; o > 0; o >>= 1) dh += __shfl_xor_sync(0xffffffffu, dh, o);
+        if (tid == 0) { n_extra = cnt; diag_high = dh; }
     }
     __syncthreads();
     mbar_wait(&mbar, 0);
