@@ -49,7 +49,7 @@ def config_dict(n_gpus: int) -> dict:
         "time_steps_per_sequence": 4000,
         "accuracy": "Richardson-extrapolated CF4 Magnus (exact spline moments), adaptive, 2-norm error budget 1e-8, Chebyshev-Clenshaw exponentials; "
                     "state error <= 1e-8 (tests/test_gpu_parity.py)",
-        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (one Sequence per GPU), 1 all-reduce",
+        "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (the same C2 Sequence on every GPU, no collective in the time loop), 1 all-reduce of the final densities",
         "l2": "L2 flushed between timed iterations (256 MiB write); the 16 MiB state is L2-resident within a step",
     }
 
@@ -190,7 +190,9 @@ def run_gpu(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    spec = workload(N_ATOMS + rank)  # replica r evolves its own register
+    # every replica evolves the same C2 Sequence (same register): equal work per GPU, so that the driver's
+    # weak-scaling ratio measures the machine and not the spread of step counts between random registers
+    spec = workload(N_ATOMS)
     T = spec.total_duration_ns
     tf = spec.sampling_times[-1]
     D = spec.hilbert_dim
