@@ -189,3 +189,30 @@ def test_run_xy(emu):
     assert sim.samples_obj._measurement == "XY"
     counts = res.sample_final_state(500)
     assert sum(counts.values()) == 500 and set(counts) <= {"00", "01", "10", "11"}
+
+
+def test_run_xy_slm_mask_equals_removed_qubit(emu):
+    """reference tests/pulser_simulation/test_simulation.py:1748-1790 (test_mask_equals_remove_xy), taken to the
+    evolved state: while the SLM mask covers the whole sequence the masked atom neither interacts nor is driven,
+    so the three-atom run factorises into the two-atom run and the untouched atom.  Exercises the spec extraction
+    of the mask (slm_end / slm_targets / coefficient) through the facade."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    pulse = Pulse.ConstantPulse(100, 10, 0, 0)
+    seq3 = Sequence(Register({"q0": (0, 0), "q1": (10, 10), "q2": (-10, -10)}), MockDevice)
+    seq3.set_magnetic_field(0, 1.0, 0.0)
+    seq3.declare_channel("ch", "mw_global")
+    seq3.config_slm_mask(["q2"])
+    seq3.add(pulse, "ch")
+    seq2 = Sequence(Register({"q0": (0, 0), "q1": (10, 10)}), MockDevice)
+    seq2.set_magnetic_field(0, 1.0, 0.0)
+    seq2.declare_channel("ch", "mw_global")
+    seq2.add(pulse, "ch")
+    sim3 = emu.B200Emulator.from_sequence(seq3, evaluation_times="Minimal")
+    sim2 = emu.B200Emulator.from_sequence(seq2, evaluation_times="Minimal")
+    f3 = sim3.run().get_final_state().full().ravel()
+    f2 = sim2.run().get_final_state().full().ravel()
+    # default initial state all-|u> (digit 0, simulation.py:498-505): the masked atom q2 never leaves it
+    np.testing.assert_allclose(f3.reshape(4, 2)[:, 0], f2, atol=1e-7)
+    assert np.max(np.abs(f3.reshape(4, 2)[:, 1])) < 1e-9
