@@ -379,14 +379,17 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         const double sg = (bit == to_bit) ? 1.0 : -1.0;
         const double gy = (bit == to_bit) ? gyt : -gyt;
         const c2* slot = nullptr;
-        if (ring) {
+        // dbg & 32 (hybrid): only the first two partner tiles come through the ring (prefetched at kernel start,
+        // no refill); the other bits are ordinary partner loads that are in flight at the same time
+        const bool from_ring = ring && (!(a.dbg & 32) || e_cnt < 2);
+        if (from_ring) {
             slot = ring + (size_t)(e_cnt & 1) * (1 << TBITS);
             mbar_wait(&rbar[e_cnt & 1], (uint32_t)((e_cnt >> 1) & 1));
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             double2 raw;
-            if (ring) { const c2 sv = slot[tid + r * NT]; raw = make_double2(sv.x, sv.y); }
+            if (from_ring) { const c2 sv = slot[tid + r * NT]; raw = make_double2(sv.x, sv.y); }
             else raw = COH ? __ldcg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))))
                            : __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
             if (UNIFORM) {
@@ -397,7 +400,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 pi[r] = fma(gx, raw.y, pi[r]); pi[r] = fma(gy, raw.x, pi[r]);
             }
         }
-        if (ring) {
+        if (ring && !(a.dbg & 32)) {
             __syncthreads();  // every thread has consumed the slot: refill it with the partner tile after next
             unsigned long long m2 = m & (m - 1);
             m2 &= m2 - 1;      // second next extra bit
@@ -481,7 +484,8 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 res = cadd(res, cmul(cb2, bv[r]));
                 dot0 = fma(v[rr].x, res.x, dot0); dot0 = fma(v[rr].y, res.y, dot0);
                 dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
-                if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
+                if (a.dbg & 64) __stcs(reinterpret_cast<double2*>(a.out + voff + idx[rr]), make_double2(res.x, res.y));  // streaming store
+                else if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
             }
         }
     } else {

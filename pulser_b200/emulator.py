@@ -80,6 +80,21 @@ _QUTIP_OPTIONS = {
 _B200_OPTIONS = {"b200_max_step", "b200_cheb_tol", "b200_refine_window", "b200_batch", "b200_tol"}
 
 
+class _NoiseModelConfig:
+    """Minimal SimConfig stand-in (``noise``, ``supported_noises``, ``to_noise_model``) used by ``add_config`` /
+    ``reset_config`` when ``pulser_simulation.simconfig`` (QuTiP) cannot be imported."""
+
+    def __init__(self, noise_model: NoiseModel, like: Any) -> None:
+        self._nm = noise_model
+        self.noise = tuple(noise_model.noise_types)
+        from pulser._hamiltonian_data.hamiltonian_data import SUPPORTED_NOISES  # type: ignore
+
+        self.supported_noises = getattr(like, "supported_noises", None) or SUPPORTED_NOISES
+
+    def to_noise_model(self) -> NoiseModel:
+        return self._nm
+
+
 class B200Emulator:
     r"""Emulator of a pulse sequence on a B200 GPU.
 
@@ -242,6 +257,204 @@ class B200Emulator:
     @property
     def total_duration_ns(self) -> int:
         return self._tot_duration
+
+    # ---- deprecated SimConfig interface (simulation.py:338-477) ---------------------------------
+    @staticmethod
+    def _simconfig_class() -> Any:
+        try:  # SimConfig lives in pulser_simulation, whose import needs QuTiP
+            from pulser_simulation.simconfig import SimConfig  # type: ignore
+
+            return SimConfig
+        except Exception as exc:  # pragma: no cover - depends on the installation
+            raise ImportError(
+                "SimConfig objects need 'pulser_simulation' (and QuTiP) to be importable; "
+                "instantiate the emulator with a 'NoiseModel' instead."
+            ) from exc
+
+    @property
+    def config(self) -> Any:
+        """The current configuration, as a SimConfig instance (``simulation.py:338-341``)."""
+        return self._simconfig_class().from_noise_model(self._hamiltonian_data.noise_model)
+
+    def set_config(self, cfg: Any) -> None:
+        """Sets current config to cfg and updates simulation parameters (``simulation.py:348-412``;
+        deprecated since v1.6 like the original).  ``cfg`` is duck-typed: ``noise``,
+        ``supported_noises`` and ``to_noise_model()``."""
+        warnings.warn(
+            "Supplying a 'SimConfig' to QutipEmulator has been deprecated."
+            " Please instantiate with a 'NoiseModel' instead.",
+            DeprecationWarning,
+            stacklevel=2,
+        )
+        if not (hasattr(cfg, "to_noise_model") and hasattr(cfg, "supported_noises")):
+            raise ValueError(f"Object {cfg} is not a valid `SimConfig`.")
+        interaction = self._hamiltonian_data.basis_data.interaction_type
+        not_supported = set(cfg.noise) - cfg.supported_noises[interaction]
+        if not_supported:
+            raise NotImplementedError(
+                f"Interaction mode '{interaction}' "
+                "does not support simulation of noise types:"
+                f"{', '.join(not_supported)}."
+            )
+        former_dim = self.dim
+        noise_model = cfg.to_noise_model()
+        self._noise_trajectories_used = False
+        self._hamiltonian_data = HamiltonianData(
+            self.samples_obj,
+            self._register,
+            self.device,
+            noise_model,
+            self._get_n_trajectories(noise_model, check_value=True),
+        )
+        self._current_spec = next(self._specs)[0]
+        self._noiseless_cache = {}
+        if self.dim == former_dim:
+            self.set_initial_state(self._initial_state)
+            return
+        if not self._initial_is_ground:
+            warnings.warn(
+                "Current initial state's dimension does not match new"
+                " dimensions. Setting it to 'all-ground'."
+            )
+        self.set_initial_state("all-ground")
+
+    def add_config(self, config: Any) -> None:
+        """Updates the current configuration with parameters of another one (``simulation.py:414-469``)."""
+        from dataclasses import asdict
+
+        warnings.warn(
+            "Supplying a 'SimConfig' to QutipEmulator has been deprecated."
+            " Please instantiate with a 'NoiseModel' instead.",
+            DeprecationWarning,
+            stacklevel=2,
+        )
+        if not (hasattr(config, "to_noise_model") and hasattr(config, "supported_noises")):
+            raise ValueError(f"Object {config} is not a valid `SimConfig`")
+        interaction = self._hamiltonian_data.basis_data.interaction_type
+        not_supported = set(config.noise) - config.supported_noises[interaction]
+        if not_supported:
+            raise NotImplementedError(
+                f"Interaction mode '{interaction}' "
+                "does not support simulation of noise types: "
+                f"{', '.join(not_supported)}."
+            )
+        noise_model = config.to_noise_model()
+        old_noise_set = set(self._hamiltonian_data.noise_model.noise_types)
+        diff_noise_set = old_noise_set.union(noise_model.noise_types) - old_noise_set
+        param_dict: dict[str, Any] = asdict(self._hamiltonian_data.noise_model)
+        relevant_params = NoiseModel._find_relevant_params(
+            diff_noise_set,
+            noise_model.state_prep_error,
+            noise_model.amp_sigma,
+            noise_model.laser_waist,
+        )
+        for param in relevant_params:
+            param_dict[param] = getattr(noise_model, param)
+        param_dict.pop("noise_types")
+        merged = NoiseModel(**param_dict)
+        try:
+            new_cfg = self._simconfig_class().from_noise_model(merged)
+        except ImportError:
+            new_cfg = _NoiseModelConfig(merged, type(config))
+        self.set_config(new_cfg)
+
+    def show_config(self, solver_options: bool = False) -> None:
+        """Shows current configuration (``simulation.py:471-473``)."""
+        print(self.config.__str__(solver_options))
+
+    def reset_config(self) -> None:
+        """Resets configuration to default (``simulation.py:475-477``)."""
+        try:
+            cfg = self._simconfig_class()()
+        except ImportError:
+            cfg = _NoiseModelConfig(NoiseModel(), None)
+        self.set_config(cfg)
+
+    # ---- operators (hamiltonian.py:145-244, simulation.py:601-623) -------------------------------
+    @property
+    def op_matrix(self) -> dict[str, Any]:
+        """``"I"`` and the projectors ``sigma_ab = |a><b|`` of the eigenbasis, as sparse matrices."""
+        import scipy.sparse as sp
+
+        eig = list(self._hamiltonian_data.basis_data.eigenbasis)
+        d = len(eig)
+        ops: dict[str, Any] = {"I": sp.identity(d, dtype=complex, format="csr")}
+        for i, a in enumerate(eig):
+            for j, b in enumerate(eig):
+                m = sp.lil_matrix((d, d), dtype=complex)
+                m[i, j] = 1.0
+                ops["sigma_" + a + b] = m.tocsr()
+        return ops
+
+    def build_operator(self, operations: Union[list, tuple]) -> Any:
+        """Creates an operator with non-trivial actions on some qubits: ``[(operator_1, qubits_1), ...]`` gives the
+        tensor product of ``operator_i`` on ``qubits_i`` and the identity elsewhere; ``(operator, 'global')`` the sum
+        over all qubits.  ``operator``: a key of ``op_matrix``, an array or anything with ``full()``/``toarray()``.
+        Returns a ``scipy.sparse`` matrix (accepted by ``SimulationResults.expect``)."""
+        import scipy.sparse as sp
+
+        qids = list(self._register.qubit_ids)
+        qindex = {q: i for i, q in enumerate(qids)}
+        op_matrix = self.op_matrix
+        op_list = [op_matrix["I"] for _ in qids]
+        if not isinstance(operations, list):
+            operations = [operations]
+        for operator, qubits in operations:
+            if isinstance(qubits, str) and qubits == "global":
+                total = None
+                for q_id in qids:
+                    term = self.build_operator([(operator, [q_id])])
+                    total = term if total is None else total + term
+                return total
+            qubits_set = set(qubits)
+            if len(qubits_set) < len(qubits):
+                raise ValueError("Duplicate atom ids in argument list.")
+            if not qubits_set.issubset(qindex.keys()):
+                v = qubits_set - qindex.keys()
+                raise ValueError("Invalid qubit names: " f"{v}")
+            if isinstance(operator, str):
+                try:
+                    operator = op_matrix[operator]
+                except KeyError:
+                    raise ValueError(f"{operator} is not a valid operator")
+            elif hasattr(operator, "full"):
+                operator = sp.csr_matrix(np.asarray(operator.full(), dtype=complex))
+            else:
+                operator = sp.csr_matrix(operator, dtype=complex)
+            for qubit in qubits:
+                op_list[qindex[qubit]] = operator
+        out = op_list[0]
+        for m in op_list[1:]:
+            out = sp.kron(out, m, format="csr")
+        return sp.csr_matrix(out)
+
+    def draw(
+        self,
+        draw_phase_area: bool = False,
+        draw_phase_shifts: bool = False,
+        draw_phase_curve: bool = False,
+        fig_name: str | None = None,
+        kwargs_savefig: dict = {},
+    ) -> None:
+        """Draws the samples of the sequence used for the emulation (``simulation.py:917-953``); needs matplotlib."""
+        try:
+            import matplotlib.pyplot as plt
+            from pulser._seq_drawer import draw_samples
+        except Exception as exc:  # pragma: no cover - plotting stack absent
+            raise ImportError("draw() needs matplotlib and pulser's sequence drawer") from exc
+        if type(getattr(plt, "__loader__", None)).__name__ == "_StubLoader":
+            raise ImportError("draw() needs matplotlib (pulser_b200._compat installed a stub because it is absent)")
+        draw_samples(
+            self.samples_obj,
+            self._register,
+            self._sampling_rate,
+            draw_phase_area=draw_phase_area,
+            draw_phase_shifts=draw_phase_shifts,
+            draw_phase_curve=draw_phase_curve,
+        )
+        if fig_name is not None:
+            plt.savefig(fig_name, **kwargs_savefig)
+        plt.show()
 
     # ------------------------------------------------------------------
     @property

@@ -216,3 +216,82 @@ def test_run_xy_slm_mask_equals_removed_qubit(emu):
     # default initial state all-|u> (digit 0, simulation.py:498-505): the masked atom q2 never leaves it
     np.testing.assert_allclose(f3.reshape(4, 2)[:, 0], f2, atol=1e-7)
     assert np.max(np.abs(f3.reshape(4, 2)[:, 1])) < 1e-9
+
+
+def test_build_operator_mirrors_reference(emu):
+    """reference hamiltonian.py:145-229 / test_simulation.py:383-450 (test_building_basis_and_projection_operators,
+    test_build_operator_exceptions): tensor products, 'global' sums, ids or labels, error messages."""
+    sim = emu.B200Emulator.from_sequence(_seq(), evaluation_times="Minimal")
+    ops = sim.op_matrix
+    assert set(ops) == {"I", "sigma_rr", "sigma_rg", "sigma_gr", "sigma_gg"}
+    r, g = np.array([1.0, 0.0]), np.array([0.0, 1.0])
+    np.testing.assert_array_equal(ops["sigma_gr"].toarray(), np.outer(g, r))
+    x = np.array([[0, 1], [1, 0]], dtype=complex)
+    eye = np.eye(2)
+    xiii = sim.build_operator([(x, ["q0"])]).toarray()
+    np.testing.assert_array_equal(xiii, np.kron(np.kron(np.kron(x, eye), eye), eye))
+    zz = np.diag([1.0, -1.0])
+    got = sim.build_operator([(zz, ["q1", "q2"]), ("sigma_rr", ["q3"])]).toarray()
+    np.testing.assert_array_equal(got, np.kron(np.kron(np.kron(eye, zz), zz), np.outer(r, r)))
+    glob = sim.build_operator([("sigma_rr", "global")]).toarray()
+    occ = sum(np.kron(np.kron(np.eye(2**k), np.outer(r, r)), np.eye(2 ** (3 - k))) for k in range(4))
+    np.testing.assert_array_equal(glob, occ)
+    with pytest.raises(ValueError, match="Duplicate atom"):
+        sim.build_operator([("sigma_gg", ["q0", "q0"])])
+    with pytest.raises(ValueError, match="not a valid operator"):
+        sim.build_operator([("wrong", ["q0"])])
+    with pytest.raises(ValueError, match="Invalid qubit names"):
+        sim.build_operator([("sigma_gg", ["wrong"])])
+    # usable as an observable of the results (qutip.expect replacement)
+    res = sim.run()
+    val = res.expect([sim.build_operator([("sigma_rr", "global")])])[0]
+    final = res.get_final_state().full().ravel()
+    assert abs(val[-1] - np.vdot(final, glob @ final).real) < 1e-12
+
+
+class _DuckConfig:
+    """What the deprecated SimConfig entry points need (pulser_simulation.simconfig imports QuTiP)."""
+
+    def __init__(self, noise_model):
+        from pulser._hamiltonian_data.hamiltonian_data import SUPPORTED_NOISES
+
+        self._nm = noise_model
+        self.noise = tuple(noise_model.noise_types)
+        self.supported_noises = SUPPORTED_NOISES
+
+    def to_noise_model(self):
+        return self._nm
+
+
+def test_deprecated_config_entry_points(emu):
+    """reference simulation.py:348-477 (set_config / add_config / reset_config) and their tests
+    (test_simulation.py:1305-1427): deprecation warnings, messages, the noise model is replaced / merged."""
+    from pulser import NoiseModel
+
+    sim = emu.B200Emulator.from_sequence(_seq(), evaluation_times="Minimal")
+    with pytest.warns(DeprecationWarning, match="Supplying a 'SimConfig'"):
+        with pytest.raises(ValueError, match="is not a valid `SimConfig`"):
+            sim.set_config("bad_config")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim.set_config(_DuckConfig(NoiseModel(dephasing_rate=0.3)))
+        assert sim.noise_model.noise_types == ("dephasing",) and sim.noise_model.dephasing_rate == 0.3
+        assert sim._has_collapse_ops()
+        # add_config keeps the parameters already set and adds the new noise types
+        sim.add_config(_DuckConfig(NoiseModel(dephasing_rate=0.9, relaxation_rate=0.2)))
+        assert set(sim.noise_model.noise_types) == {"dephasing", "relaxation"}
+        assert sim.noise_model.dephasing_rate == 0.3 and sim.noise_model.relaxation_rate == 0.2
+        sim.reset_config()
+        assert sim.noise_model == NoiseModel() and not sim._has_collapse_ops()
+        # XY mode does not support relaxation (SUPPORTED_NOISES)
+        from pulser import Pulse, Register, Sequence
+        from pulser.devices import MockDevice
+
+        seq = Sequence(Register.from_coordinates([[10, 0], [0, 0]], prefix="atom"), MockDevice)
+        seq.declare_channel("ch0", "mw_global")
+        seq.add(Pulse.ConstantPulse(200, 3.0, 1.0, 0.0), "ch0")
+        xy = emu.B200Emulator.from_sequence(seq)
+        with pytest.raises(NotImplementedError, match="Interaction mode 'XY' does not support simulation of noise types"):
+            xy.set_config(_DuckConfig(NoiseModel(relaxation_rate=0.3)))
+    with pytest.raises(ImportError, match="matplotlib"):
+        sim.draw()
