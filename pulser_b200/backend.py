@@ -640,3 +640,51 @@ class B200Backend(EmulatorBackend):
                     self._replay(hplan, cleanres, res)
                     results.append(res)
             return Results.aggregate(results)
+
+
+class B200LegacyBackend(pulser.backend.abc.Backend):
+    """Mirror of the deprecated V1 backend ``pulser_simulation.QutipBackend``
+    (``pulser-simulation/pulser_simulation/qutip_backend.py:44-118``): takes an
+    ``EmulatorConfig`` and returns ``CoherentResults`` / ``NoisyResults`` from
+    ``B200Emulator.run``.  Same checks, messages and deprecation warning."""
+
+    def __init__(self, sequence: pulser.Sequence, config: Any = None, mimic_qpu: bool = False):
+        from pulser.backend.config import EmulatorConfig
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("once")
+            warnings.warn(
+                "'QutipBackend' is deprecated. Please use "
+                "'pulser_simulation.QutipBackendV2' instead.",
+                DeprecationWarning,
+                stacklevel=2,
+            )
+        super().__init__(sequence, mimic_qpu=mimic_qpu)
+        if config is None:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", DeprecationWarning)
+                config = EmulatorConfig()
+        if not isinstance(config, EmulatorConfig):
+            raise TypeError(
+                "'config' must be of type 'EmulatorConfig', "
+                f"not {type(config)}."
+            )
+        self._config = config
+        noise_model = None
+        if self._config.prefer_device_noise_model:
+            noise_model = sequence.device.noise_model
+        self._sim_obj = B200Emulator.from_sequence(
+            sequence,
+            sampling_rate=self._config.sampling_rate,
+            noise_model=noise_model or self._config.noise_model,
+            evaluation_times=self._config.evaluation_times,
+            with_modulation=self._config.with_modulation,
+        )
+        self._sim_obj.set_initial_state(self._config.initial_state)
+
+    def run(self, progress_bar: bool = False, **options: Any) -> Any:
+        """Emulates the sequence on the B200 (``QutipBackend.run``, ``qutip_backend.py:89-118``); QuTiP solver
+        options are accepted and ignored like in ``B200Emulator.run``."""
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            return self._sim_obj.run(progress_bar=progress_bar, **options)

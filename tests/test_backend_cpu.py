@@ -187,3 +187,41 @@ def test_projector_patterns(backend):
     v = np.zeros(27, dtype=complex); v[0 * 9 + 1 * 3 + 0] = 1.0  # |r g r>
     st = backend.B200State(v, eigenstates=eig)
     assert (num(0) @ num(2)).expect(st) == pytest.approx(1.0) and (num(0) @ num(1)).expect(st) == pytest.approx(0.0)
+
+
+def test_legacy_v1_backend(monkeypatch):
+    """reference tests/pulser_simulation/test_qutip_backend.py:43-104 (test_qutip_backend, test_with_default_noise)
+    on the V1 mirror: type check, deprecation warning, pi pulse on a local Raman channel, device noise model."""
+    import dataclasses
+
+    import pulser
+    from fake_device import FakeDevicePlan, FakeLindbladPlan
+    from pulser.devices import MockDevice
+    from pulser.waveforms import BlackmanWaveform
+    from pulser_b200 import backend, engine, lindblad
+    from pulser_b200.results import CoherentResults, NoisyResults
+
+    monkeypatch.setattr(engine, "DevicePlan", FakeDevicePlan)
+    monkeypatch.setattr(lindblad, "LindbladPlan", FakeLindbladPlan)
+    seq = pulser.Sequence(pulser.Register({"q0": (0, 0)}), MockDevice)
+    seq.declare_channel("raman_local", "raman_local", initial_target="q0")
+    seq.add(pulser.Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0, 0), "raman_local")
+    with pytest.raises(TypeError, match="must be of type 'EmulatorConfig'"), pytest.deprecated_call(
+            match="'QutipBackend' is deprecated"):
+        backend.B200LegacyBackend(seq, pulser.NoiseModel())
+    with pytest.deprecated_call(match="'QutipBackend' is deprecated"):
+        be = backend.B200LegacyBackend(seq)
+    results = be.run()
+    assert isinstance(results, CoherentResults)
+    np.testing.assert_allclose(results[0].get_state().full().ravel(), [1, 0])
+    np.testing.assert_allclose(np.abs(results.get_final_state().full().ravel()), [0, 1], atol=1e-5)
+    with pytest.raises(TypeError, match="must be a real device"), pytest.deprecated_call():
+        backend.B200LegacyBackend(seq, mimic_qpu=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spam = pulser.NoiseModel(p_false_pos=0.1, p_false_neg=0.05, state_prep_error=0.1, runs=10, samples_per_run=1)
+        dev = dataclasses.replace(MockDevice, noise_model=spam)
+        be = backend.B200LegacyBackend(seq.with_new_device(dev), config=pulser.EmulatorConfig(prefer_device_noise_model=True))
+        noisy = be.run()
+    assert isinstance(noisy, NoisyResults)
+    assert be._sim_obj.noise_model == spam
