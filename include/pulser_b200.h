@@ -232,6 +232,11 @@ int pb200_state_overlap(pb200_plan* plan, int32_t traj0, int32_t count,
  * bitstring index of shot i.  Only 8*n_shots bytes travel each way. */
 int pb200_state_sample(pb200_plan* plan, int32_t traj, int32_t one_digit,
                        const double* uniforms, int32_t n_shots, int64_t* out);
+/* Copy the current state of trajectory src_traj of `src` into trajectory dst_traj of `dst`, device to device
+ * (same device, same Hilbert space).  Lets the observables of the generic backend evaluate <psi|H(t)|psi> with the
+ * NOISELESS Hamiltonian (the operator qutip_backend.py:258-264 hands to every observable) on the state of a noisy
+ * trajectory without a host round trip. */
+int pb200_state_copy(pb200_plan* dst, int32_t dst_traj, pb200_plan* src, int32_t src_traj);
 /* Device pointer of the current state buffer (complex128 [n_traj][D]). */
 int pb200_state_device_ptr(pb200_plan* plan, void** dptr);
 

@@ -108,6 +108,7 @@ def _load() -> C.CDLL:
         "pb200_state_overlap": (C.c_int, [vp, C.c_int32, C.c_int32, dp, dp]),
         "pb200_state_sample": (
             C.c_int, [vp, C.c_int32, C.c_int32, dp, C.c_int32, C.POINTER(C.c_int64)]),
+        "pb200_state_copy": (C.c_int, [vp, C.c_int32, vp, C.c_int32]),
         "pb200_state_device_ptr": (C.c_int, [vp, C.POINTER(vp)]),
         "pb200_propagate": (
             C.c_int, [vp, C.c_double, C.c_double, C.POINTER(RunOpts), C.POINTER(RunStats)]),
@@ -136,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "pb200_plan_set_interaction", "pb200_plan_set_xy", "pb200_plan_set_slm_mask", "pb200_plan_set_drive", "pb200_plan_set_dissipator", "pb200_plan_set_collapse",
     "pb200_plan_jump_counts", "pb200_state_set",
     "pb200_state_get", "pb200_state_probabilities", "pb200_state_norm2",
-    "pb200_state_occupation", "pb200_state_correlation", "pb200_state_energy", "pb200_state_overlap", "pb200_state_sample", "pb200_state_device_ptr", "pb200_propagate", "pb200_apply_h",
+    "pb200_state_occupation", "pb200_state_correlation", "pb200_state_energy", "pb200_state_overlap", "pb200_state_sample", "pb200_state_copy", "pb200_state_device_ptr", "pb200_propagate", "pb200_apply_h",
     "pb200_coefficients_at", "pb200_bench_apply", "pb200_host_interpolate",
     "pb200_host_moments", "pb200_host_chebyshev",
 ]

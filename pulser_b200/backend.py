@@ -163,7 +163,7 @@ class _DeviceResident:
 
 
 class DeviceStateView(_DeviceResident, B200State):
-    """The current state of trajectory 0 of a ``DevicePlan``, left on the GPU.
+    """The current state of one trajectory of a ``DevicePlan``, left on the GPU.
 
     Handed to the observables by ``B200Backend`` while it steps through the
     evaluation times: ``Occupation`` / ``CorrelationMatrix`` (number-operator
@@ -174,18 +174,19 @@ class DeviceStateView(_DeviceResident, B200State):
     ``qutip_backend.py:254-280``, which cannot hold one state per step at N >= 20.
     """
 
-    def __init__(self, plan: Any, *, eigenstates: Sequence[str]):
+    def __init__(self, plan: Any, *, eigenstates: Sequence[str], traj: int = 0, norm2: float | None = None):
         State.__init__(self, eigenstates=eigenstates)
         self._plan = plan
+        self._traj = int(traj)
         self._host: np.ndarray | None = None
-        self._norm2 = float(plan.norm2()[0])
+        self._norm2 = float(plan.norm2()[self._traj]) if norm2 is None else float(norm2)
         self._corr: dict[int, np.ndarray] = {}
-        self._energy: dict[float, tuple[float, float]] = {}
+        self._energy: dict[tuple[int, float], tuple[float, float]] = {}
 
     @property
     def _state(self) -> np.ndarray:  # host copy, normalised like qutip_backend.py:268-272
         if self._host is None:
-            self._host = self._plan.get_state()[0] / math.sqrt(self._norm2)
+            self._host = self._plan.get_state()[self._traj] / math.sqrt(self._norm2)
         return self._host
 
     @property
@@ -199,7 +200,7 @@ class DeviceStateView(_DeviceResident, B200State):
     def _correlations(self, letter: str) -> np.ndarray:
         digit = self.eigenstates.index(letter)
         if digit not in self._corr:
-            self._corr[digit] = self._plan.correlation(digit, 0, 1)[0] / self._norm2
+            self._corr[digit] = self._plan.correlation(digit, self._traj, 1)[0] / self._norm2
         return self._corr[digit]
 
     def _projector_expect(self, coeff, letter, targets):
@@ -211,17 +212,27 @@ class DeviceStateView(_DeviceResident, B200State):
         return complex(coeff) * float(self._correlations(letter)[idx[0], idx[-1]])
 
     def _energy_moments(self, plan: Any, t_us: float) -> tuple[float, float] | None:
-        if plan is not self._plan:
-            return None
-        if t_us not in self._energy:
-            e, e2 = plan.energy(t_us)
-            self._energy[t_us] = (float(e[0]) / self._norm2, float(e2[0]) / self._norm2)
-        return self._energy[t_us]
+        """``<H>``, ``<H^2>`` of this state under the Hamiltonian of ``plan``.  ``plan`` is either the plan that
+        holds the state or the single-trajectory plan of the NOISELESS sequence (the operator handed to the
+        observables of a noisy run): then the state is copied device to device first (``pb200_state_copy``)."""
+        key = (id(plan), t_us)
+        if key not in self._energy:
+            if plan is self._plan:
+                e, e2 = plan.energy(t_us)
+                k = self._traj
+            elif hasattr(plan, "copy_state_from") and getattr(plan, "n_traj", 1) == 1:
+                plan.copy_state_from(self._plan, self._traj, 0)
+                e, e2 = plan.energy(t_us)
+                k = 0
+            else:
+                return None
+            self._energy[key] = (float(e[k]) / self._norm2, float(e2[k]) / self._norm2)
+        return self._energy[key]
 
     def overlap(self, other: "B200State") -> float:
         if isinstance(other, B200State) and not isinstance(other, _DeviceResident) and other.is_ket \
                 and other.eigenstates == self.eigenstates and other.n_qudits == self.n_qudits:
-            return float(abs(self._plan.overlap(other._state, 0, 1)[0]) ** 2 / self._norm2)
+            return float(abs(self._plan.overlap(other._state, self._traj, 1)[0]) ** 2 / self._norm2)
         return B200State.overlap(self, other)
 
     def sample(self, *, num_shots: int, one_state: str | None = None, p_false_pos: float = 0.0,
@@ -230,7 +241,7 @@ class DeviceStateView(_DeviceResident, B200State):
         the global ``np.random`` stream, the recipe of ``qutip_result.py:101-158``); same distribution as
         ``B200State.sample`` without the host-side probability dictionary."""
         one_state = one_state or self.infer_one_state()
-        counts = self._plan.sample(int(num_shots), one_state, 0)
+        counts = self._plan.sample(int(num_shots), one_state, self._traj)
         if p_false_pos == 0.0 and p_false_neg == 0.0:
             return counts
         keys = list(counts)
@@ -609,6 +620,61 @@ class B200Backend(EmulatorBackend):
                 obs(config=config, t=t, state=state, hamiltonian=ham, result=res)
         sim.last_run_stats = stats
 
+    def _stream_noisy(self, hplan: Any, atom_order: tuple) -> list[Results]:
+        """Stochastic noise on pure states (noisy Hamiltonians, Monte-Carlo wave functions): the trajectories are
+        evolved in device batches through the evaluation times and every observable sees a ``DeviceStateView`` of
+        its trajectory; the Hamiltonian handed over is the noiseless one (``qutip_backend.py:258-264``), its
+        expectation on a noisy state goes through ``pb200_state_copy``.  One ``Results`` per trajectory repetition,
+        like the replay path; within a batch the observables are visited time-major (as ``_noisy_counts`` does)."""
+        from . import engine
+
+        sim, config = self._sim_obj, self._config
+        eig = sim._hamiltonian_data.basis_data.eigenbasis
+        opts = {"max_step": 0, "cheb_tol": 0.0, "refine_window": -1, "tol": 0.0}
+        times = sim._eval_times_array
+        pending = sim._pending_trajectories()
+        out: list[Results] = []
+        if not pending:
+            return out
+        D = pending[0][0].hilbert_dim
+        batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
+        traj_nb, n_trajectories = 0, sim.n_trajectories
+        for b0 in range(0, len(pending), batch):
+            chunk = pending[b0 : b0 + batch]
+            if config.print_progress:
+                for _, reps in chunk:
+                    if reps == 1:
+                        print(f"Emulating Trajectory {traj_nb+1}/{n_trajectories}")
+                    else:
+                        print("Emulating Trajectories " f"[{traj_nb+1} - {traj_nb+reps}]/{n_trajectories}")
+                    traj_nb += reps
+            per_traj = [[Results(atom_order=atom_order, total_duration=sim.total_duration_ns) for _ in range(reps)]
+                        for _, reps in chunk]
+            with engine.DevicePlan([s for s, _ in chunk], sim._interp_order, sim._gpu) as plan:
+                if sim._use_mcwf():
+                    plan.set_collapse(chunk[0][0].collapse_ops, seed=int(np.random.randint(0, 2**31 - 1)))
+                plan.set_state(sim._initial_state.full().reshape(-1))
+                prev = float(times[0])
+                for t_us in times:
+                    t_us = float(t_us)
+                    if t_us > prev:
+                        plan.propagate(prev, t_us, **opts)
+                        prev = t_us
+                    t = t_us / (sim._tot_duration * 1e-3)
+                    ham = DeviceHamiltonian(hplan, t_us, eig)
+                    norms = plan.norm2()
+                    for i, results in enumerate(per_traj):
+                        state = DeviceStateView(plan, eigenstates=eig, traj=i, norm2=float(norms[i]))
+                        for res in results:
+                            for callback in config.callbacks:
+                                callback(config=config, t=t, state=state, hamiltonian=ham, result=res)
+                            for obs in config.observables:
+                                obs(config=config, t=t, state=state, hamiltonian=ham, result=res)
+            sim._current_spec = chunk[-1][0]
+            for results in per_traj:
+                out.extend(results)
+        return out
+
     def run(self) -> Results:
         from . import engine
 
@@ -633,6 +699,9 @@ class B200Backend(EmulatorBackend):
             results: list[Results] = []
             sim._validate_options({})
             sim._check_supported()
+            if not sim._has_collapse_ops() or sim._use_mcwf():
+                # pure states: observables reduce on the device, nothing is stored per evaluation time
+                return Results.aggregate(self._stream_noisy(hplan, atom_order))
             for cleanres, reps in sim._noisy_runs(print_progress=self._config.print_progress, batch=0,
                                                   opts={"max_step": 0, "cheb_tol": 0.0, "refine_window": -1, "tol": 0.0}):
                 for _ in range(reps):

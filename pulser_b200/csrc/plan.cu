@@ -2299,6 +2299,25 @@ int pb200_state_sample(pb200_plan* h, int32_t traj, int32_t one_digit, const dou
     PB200_CATCH
 }
 
+int pb200_state_copy(pb200_plan* dst, int32_t dst_traj, pb200_plan* src, int32_t src_traj) {
+    PB200_TRY
+    if (!dst || !src) fail(PB200_ERR_INVALID, "null argument");
+    Plan& A = dst->p;
+    Plan& S = src->p;
+    if (!S.state_set) fail(PB200_ERR_STATE, "pb200_state_copy: the source plan has no state");
+    if (A.D != S.D || A.dim != S.dim) fail(PB200_ERR_INVALID, "pb200_state_copy: different Hilbert spaces");
+    if (A.desc.device != S.desc.device) fail(PB200_ERR_UNSUPPORTED, "pb200_state_copy: plans on different devices");
+    if (dst_traj < 0 || dst_traj >= A.B || src_traj < 0 || src_traj >= S.B) fail(PB200_ERR_INVALID, "trajectory range");
+    if (A.B > 1 && !A.state_set) fail(PB200_ERR_STATE, "pb200_state_copy: set the other trajectories of the destination first");
+    CUDA_CHECK(cudaSetDevice(A.desc.device));
+    CUDA_CHECK(cudaStreamSynchronize(S.stream));  // the source state is complete
+    CUDA_CHECK(cudaMemcpyAsync(A.buf[A.cur] + (size_t)dst_traj * A.D, S.buf[S.cur] + (size_t)src_traj * S.D,
+                               sizeof(c2) * (size_t)A.D, cudaMemcpyDeviceToDevice, A.stream));
+    CUDA_CHECK(cudaStreamSynchronize(A.stream));
+    A.state_set = true;
+    PB200_CATCH
+}
+
 int pb200_state_device_ptr(pb200_plan* h, void** dptr) {
     PB200_TRY
     if (!h || !dptr) fail(PB200_ERR_INVALID, "null argument");

@@ -268,6 +268,11 @@ class DevicePlan:
         check(lib.pb200_state_overlap(self._handle, traj0, count, _p(v.view(np.float64)), _p(out)))
         return out[:, 0] + 1j * out[:, 1]
 
+    def copy_state_from(self, other: "DevicePlan", src_traj: int = 0, dst_traj: int = 0) -> None:
+        """Device-to-device copy of one trajectory's current state of ``other`` into this plan
+        (``pb200_state_copy``)."""
+        check(lib.pb200_state_copy(self._handle, dst_traj, other._handle, src_traj))
+
     def sample(self, n_samples: int, one_state: str, traj: int = 0) -> "Counter[str]":
         """Bitstring samples of trajectory ``traj`` drawn on the device with the
         reference's recipe and the global ``np.random`` stream

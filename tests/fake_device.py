@@ -90,6 +90,18 @@ class FakeDevicePlan:
     def apply_h(self, t_us, vec, traj=0):
         return self.hams[traj].matrix_at(t_us, self.order) @ np.asarray(vec, dtype=complex)
 
+    @property
+    def n_traj(self):
+        return len(self.hams)
+
+    def copy_state_from(self, other, src_traj=0, dst_traj=0):
+        if self.states is None:
+            self.states = [None] * len(self.hams)
+        self.states[dst_traj] = np.array(other.states[src_traj], dtype=complex)
+
+    def set_collapse(self, ops, seed=0):
+        raise NotImplementedError("the oracle-backed fake has no Monte-Carlo wave-function path")
+
 
 class FakeLindbladPlan(FakeDevicePlan):
     def set_state(self, psi):

@@ -225,3 +225,34 @@ def test_legacy_v1_backend(monkeypatch):
         noisy = be.run()
     assert isinstance(noisy, NoisyResults)
     assert be._sim_obj.noise_model == spam
+
+
+def test_noisy_runs_stream_on_the_device_like_the_replay(backend, monkeypatch):
+    """Stochastic-noise runs of the V2 backend: the trajectory-streaming path (device-resident state views, noiseless
+    Hamiltonian through a device-to-device state copy) gives the observables the replay of stored states gave."""
+    import pulser
+    from pulser.backend.default_observables import CorrelationMatrix, Energy, EnergySecondMoment, Occupation
+
+    def run(stream):
+        np.random.seed(11)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            nm = pulser.NoiseModel(temperature=50.0, amp_sigma=0.05, laser_waist=175.0)
+            times = [0.5, 1.0]
+            cfg = backend.B200Config(observables=[Occupation(evaluation_times=times), Energy(evaluation_times=times),
+                                                  EnergySecondMoment(evaluation_times=times),
+                                                  CorrelationMatrix(evaluation_times=times)],
+                                     noise_model=nm, n_trajectories=4)
+            be = backend.B200Backend(_seq(n=3, duration=200), config=cfg)
+            if not stream:  # force the replay of stored states
+                monkeypatch.setattr(be._sim_obj, "_has_collapse_ops", lambda: True)
+                monkeypatch.setattr(be._sim_obj, "_use_mcwf", lambda: False)
+                monkeypatch.setattr(be._sim_obj, "_check_supported", lambda: None)
+            return be.run()
+
+    streamed, replayed = run(True), run(False)
+    for name in ("occupation", "energy", "energy_second_moment", "correlation_matrix"):
+        for t in (0.5, 1.0):
+            a = np.asarray(streamed.get_result(name, t), dtype=float)
+            b = np.asarray(replayed.get_result(name, t), dtype=float)
+            np.testing.assert_allclose(a, b, atol=1e-9, err_msg=f"{name} at {t}")

@@ -652,3 +652,30 @@ def test_partner_sum_forwarding_vs_oracle(engine, monkeypatch):
         plan.propagate(0.0, spec.sampling_times[-1])
         got = plan.get_state()[0]
     assert np.max(np.abs(got - ref)) < STATE_TOL
+
+
+def test_state_copy_between_plans(engine):
+    """pb200_state_copy: the state of one noisy trajectory evaluated under the NOISELESS Hamiltonian of another plan
+    (what the generic backend's Energy observables need for stochastic-noise runs), no host round trip."""
+    from oracle.matfree import MatFreeHamiltonian
+
+    noisy = [random_local_spec(9, T=80, seed=s) for s in (31, 32, 33)]
+    clean = W.config_c2(n=9, seed=5, t_rise=20, t_sweep=40, t_fall=20)
+    assert clean.hilbert_dim == noisy[0].hilbert_dim
+    psi0 = random_state(clean.hilbert_dim, 8)
+    t = 0.0413
+    with engine.DevicePlan(noisy) as plan, engine.DevicePlan(clean) as hplan:
+        plan.set_state(psi0)
+        plan.propagate(0.0, 0.05)
+        states = plan.get_state()
+        for traj in (2, 0):
+            hplan.copy_state_from(plan, traj, 0)
+            np.testing.assert_array_equal(hplan.get_state()[0], states[traj])
+            e, e2 = hplan.energy(t)
+            hpsi = MatFreeHamiltonian(clean).apply(t, states[traj])
+            assert abs(e[0] - np.vdot(states[traj], hpsi).real) < 1e-10 * max(1.0, np.linalg.norm(hpsi))
+            assert abs(e2[0] - np.vdot(hpsi, hpsi).real) < 1e-10 * max(1.0, np.vdot(hpsi, hpsi).real)
+        np.testing.assert_array_equal(plan.get_state(), states)  # the source is untouched
+        with pytest.raises(Exception, match="different Hilbert spaces"):
+            with engine.DevicePlan(W.config_c2(n=8, seed=5, t_rise=20, t_sweep=40, t_fall=20)) as small:
+                small.copy_state_from(plan, 0, 0)
