@@ -80,6 +80,34 @@ _QUTIP_OPTIONS = {
 _B200_OPTIONS = {"b200_max_step", "b200_cheb_tol", "b200_refine_window", "b200_batch", "b200_tol"}
 
 
+class _PendingTrajectories:
+    """Lazy list of ``(HamiltonianSpec, reps)`` of a noisy run: entry ``k`` is built from noise trajectory
+    ``entries[k][0]`` the way ``HamiltonianData.noisy_samples`` builds it
+    (``pulser/_hamiltonian_data/hamiltonian_data.py:536-545``) when it is indexed, and not before."""
+
+    def __init__(self, sim: "B200Emulator", hd: Any, entries: list) -> None:
+        self._sim, self._hd, self._entries = sim, hd, entries
+        self._last: tuple[int, HamiltonianSpec] | None = None
+
+    def __len__(self) -> int:
+        return len(self._entries)
+
+    def _make(self, k: int) -> tuple[HamiltonianSpec, int]:
+        index, reps = self._entries[k]
+        if self._last is None or self._last[0] != index:
+            traj = self._hd.noise_trajectories[index].trajectory
+            self._last = (index, self._sim._spec_of(self._hd, traj, self._hd._sample_with_trajectory(traj)))
+        return self._last[1], reps
+
+    def __getitem__(self, key: Any) -> Any:
+        if isinstance(key, slice):
+            return [self._make(k) for k in range(*key.indices(len(self._entries)))]
+        return self._make(key if key >= 0 else len(self._entries) + key)
+
+    def __iter__(self) -> Iterator[tuple[HamiltonianSpec, int]]:
+        return (self._make(k) for k in range(len(self._entries)))
+
+
 class _NoiseModelConfig:
     """Minimal SimConfig stand-in (``noise``, ``supported_noises``, ``to_noise_model``) used by ``add_config`` /
     ``reset_config`` when ``pulser_simulation.simconfig`` (QuTiP) cannot be imported."""
@@ -733,18 +761,21 @@ class B200Emulator:
                 self._get_n_trajectories(nm, check_value=True),
             )
         self._noise_trajectories_used = True
-        pending = list(self._specs)
+        # (index into hd.noise_trajectories, reps): the specs themselves are built when a batch asks for them, so
+        # a thousand trajectories never sit in host memory as per-atom sample tables at once
+        hd = self._hamiltonian_data
+        entries = [(i, int(reps)) for i, (_, reps) in enumerate(hd.noise_trajectories)]
         if self._use_mcwf():
             # every Monte-Carlo trajectory is its own random realisation: no merging by `reps`
             if not _has_stochastic_noise(self.noise_model):
-                pending = [(pending[0][0], 1)] * int(self.n_trajectories)
+                entries = [(entries[0][0], 1)] * int(self.n_trajectories)
             else:
-                pending = [(s, 1) for s, reps in pending for _ in range(reps)]
+                entries = [(i, 1) for i, reps in entries for _ in range(reps)]
         from . import parallel
 
         if parallel.world_size() > 1:  # trajectory j -> rank j mod world (same seed on every rank)
-            pending = [pending[j] for j in parallel.stripe(len(pending), parallel.rank(), parallel.world_size())]
-        return pending
+            entries = [entries[j] for j in parallel.stripe(len(entries), parallel.rank(), parallel.world_size())]
+        return _PendingTrajectories(self, hd, entries)
 
     def _noisy_counts(self, print_progress: bool, batch: int, opts: dict) -> np.ndarray:
         """Bitstring Counters per evaluation time of all noise trajectories, sampled ON THE DEVICE
