@@ -53,6 +53,18 @@ struct Error : std::runtime_error {
                  cudaGetErrorString(e__));                                                      \
     } while (0)
 
+// a pair of CUDA events released on every exit path (the propagators throw on CUDA errors)
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() {
+        CUDA_CHECK(cudaEventCreate(&a));
+        if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); a = nullptr; fail(PB200_ERR_CUDA, "cudaEventCreate failed"); }
+    }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+};
+
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
@@ -1235,8 +1247,8 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     }
     const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
     dim3 bgrid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
-    cudaEvent_t ev0, ev1;
-    CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
+    EventPair evs;
+    cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     CUDA_CHECK(cudaEventRecord(ev0, P.stream));
     std::vector<double> norms(P.B), occ((size_t)P.dim * P.n);
     double* d_occ = nullptr;
@@ -1329,7 +1341,6 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     st.gpu_ms = ms; st.integrator = 1; st.mean_step_samples = K;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) *stats = st;
 }
 
@@ -1377,9 +1388,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         return std::min(1e-12, std::max(2e-15, (check ? 0.01 : 0.2) * share));
     };
 
-    cudaEvent_t ev0, ev1;
-    CUDA_CHECK(cudaEventCreate(&ev0));
-    CUDA_CHECK(cudaEventCreate(&ev1));
+    EventPair evs;
+    cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     CUDA_CHECK(cudaEventRecord(ev0, P.stream));
 
     Program prog;
@@ -1614,7 +1624,6 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     st.gpu_ms = ms;
     st.mean_step_samples = smooth_steps ? smooth_len / smooth_steps : 0.0;
     st.integrator = P.use_krylov ? 2 : 1;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) *stats = st;
 }
 
@@ -2386,8 +2395,8 @@ int pb200_bench_apply(pb200_plan* h, double t_us, int32_t reps, double* ms_out, 
     ud.g = {E.g[0].real(), E.g[0].imag()}; ud.theta = E.th[0]; ud.w = 1.0; ud.gamma = 0.0;
     StageCoef sc{{0, 0}, {0, 0}, {1, 0}};
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    EventPair evs;
+    cudaEvent_t e0 = evs.a, e1 = evs.b;
     launches = 0;
     CUDA_CHECK(cudaEventRecord(e0, P.stream));
     for (int r = 0; r < reps; ++r)
@@ -2397,7 +2406,6 @@ int pb200_bench_apply(pb200_plan* h, double t_us, int32_t reps, double* ms_out, 
     CUDA_CHECK(cudaGetLastError());
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms_out = ms;
     if (launches_out) *launches_out = launches;
     PB200_CATCH
