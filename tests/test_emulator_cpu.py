@@ -295,3 +295,97 @@ def test_deprecated_config_entry_points(emu):
             xy.set_config(_DuckConfig(NoiseModel(relaxation_rate=0.3)))
     with pytest.raises(ImportError, match="matplotlib"):
         sim.draw()
+
+
+def test_amp_sigma_noise_reaches_the_spec(emu):
+    """reference tests/pulser_simulation/test_simulation.py:2193-2266 (test_amp_sigma_noise): per-channel amplitude
+    factors, constant from pulse to pulse, act on the per-qubit tables -- checked on the plain-array spec that
+    feeds the CUDA path (coef = 0.5 amp exp(-i phase)), 'all' basis with two addressed bases."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    seq = Sequence(Register({"q0": (0, 0), "q1": (10, 10)}), MockDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.declare_channel("ch1", "raman_local", initial_target="q0")
+    seq.declare_channel("ch2", "raman_local", initial_target="q1")
+    pulse1 = Pulse.ConstantPulse(120, 1, 0, 2.0)
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch1", protocol="no-delay")
+    seq.target("q1", "ch1")
+    seq.add(pulse1, "ch1", protocol="no-delay")
+    seq.add(pulse1, "ch2", protocol="no-delay")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(amp_sigma=0.1), n_trajectories=1)
+        clean = emu.B200Emulator.from_sequence(seq)
+    noisy, base = sim._current_spec, clean._noiseless_spec()
+    assert noisy.eigenbasis == ["r", "g", "h"] and [d.basis for d in noisy.drives] == [d.basis for d in base.drives]
+    ryd = {d.basis: d for d in noisy.drives}["ground-rydberg"]
+    ryd0 = {d.basis: d for d in base.drives}["ground-rydberg"]
+    dig = {d.basis: d for d in noisy.drives}["digital"]
+    dig0 = {d.basis: d for d in base.drives}["digital"]
+    nz = np.flatnonzero(ryd0.coef[0])
+    f0 = (ryd.coef[0, nz[0]] / ryd0.coef[0, nz[0]]).real  # factor of the global channel
+    assert f0 > 0 and f0 != 1.0
+    for q in range(2):  # same factor on both atoms and on both pulses; the phase survives
+        np.testing.assert_allclose(ryd.coef[q], ryd0.coef[q] * f0, rtol=1e-15)
+    np.testing.assert_array_equal(ryd.det, ryd0.det)
+    # digital basis: q0 driven by ch1 only; q1 first by ch2 then by ch1
+    nz0 = np.flatnonzero(dig0.coef[0])
+    f1 = (dig.coef[0, nz0[0]] / dig0.coef[0, nz0[0]]).real
+    np.testing.assert_allclose(dig.coef[0], dig0.coef[0] * f1, rtol=1e-15)
+    nz1 = np.flatnonzero(dig0.coef[1])
+    f2 = (dig.coef[1, nz1[0]] / dig0.coef[1, nz1[0]]).real
+    assert len({f0, f1, f2}) == 3 and all(f > 0 and f != 1 for f in (f1, f2))
+    expected = dig0.coef[1].copy()
+    expected[: pulse1.duration] *= f2
+    expected[-pulse1.duration - 1:] *= f1
+    np.testing.assert_allclose(dig.coef[1], expected, rtol=1e-15)
+    # identical rows (one factor for the global channel): the spec keeps the cheaper uniform-drive kernel
+    assert ryd.uniform and not dig.uniform
+
+
+def test_detuning_noise_reaches_the_spec(emu):
+    """reference tests/pulser_simulation/test_simulation.py:2269-2317 (test_detuning_noise): the shot-to-shot detuning
+    offsets of seed 1337, one per channel, land in the per-qubit detuning tables of the spec."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    duration = 10
+    np.random.seed(1337)
+    seq = Sequence(Register({"q0": (0, 0), "q1": (10, 10)}), MockDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.declare_channel("ch1", "raman_local", initial_target="q0")
+    seq.declare_channel("ch2", "raman_local", initial_target="q1")
+    pulse1 = Pulse.ConstantPulse(duration, 0, 0, 0)
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch1", protocol="no-delay")
+    seq.add(pulse1, "ch2", protocol="no-delay")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(detuning_sigma=0.1), n_trajectories=1)
+    tabs = {d.basis: d for d in sim._current_spec.drives}
+    ryd, dig = tabs["ground-rydberg"].det, tabs["digital"].det
+    np.testing.assert_allclose(ryd[0], np.array([-0.04902824] * (2 * duration) + [0.0]), atol=1e-8)
+    np.testing.assert_allclose(ryd[1], ryd[0], atol=0)
+    np.testing.assert_allclose(dig[0], np.array([-0.17550787] * duration + [0.0] * (duration + 1)), atol=1e-8)
+    np.testing.assert_allclose(dig[1], np.array([-0.20112646] * duration + [0.0] * (duration + 1)), atol=1e-8)
+
+
+def test_run_from_sequence_and_from_samples_agree(emu):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:615-650 / test_simulation.py (from_sequence vs the
+    constructor on sampled sequences): both entry points feed the same spec, hence the same state."""
+    from pulser.sampler import sampler
+
+    seq = _seq(duration=300)
+    a = emu.B200Emulator.from_sequence(seq, evaluation_times="Minimal")
+    b = emu.B200Emulator(sampler.sample(seq), seq.register, seq.device, evaluation_times="Minimal")
+    sa, sb = a._current_spec, b._current_spec
+    np.testing.assert_array_equal(sa.drives[0].coef, sb.drives[0].coef)
+    np.testing.assert_array_equal(sa.drives[0].det, sb.drives[0].det)
+    np.testing.assert_array_equal(sa.interaction_matrix, sb.interaction_matrix)
+    fa = a.run().get_final_state().full()
+    fb = b.run().get_final_state().full()
+    np.testing.assert_allclose(fa, fb, rtol=1e-16, atol=0)
