@@ -304,87 +304,68 @@ class B200Emulator:
         """The current configuration, as a SimConfig instance (``simulation.py:338-341``)."""
         return self._simconfig_class().from_noise_model(self._hamiltonian_data.noise_model)
 
-    def set_config(self, cfg: Any) -> None:
-        """Sets current config to cfg and updates simulation parameters (``simulation.py:348-412``;
-        deprecated since v1.6 like the original).  ``cfg`` is duck-typed: ``noise``,
-        ``supported_noises`` and ``to_noise_model()``."""
+    def _noise_model_of_config(self, cfg: Any, invalid_suffix: str, list_prefix: str) -> NoiseModel:
+        """Common front door of the deprecated SimConfig setters: deprecation warning, duck-type check
+        (``noise`` / ``supported_noises`` / ``to_noise_model``) and the interaction-mode support check, with the
+        reference's messages (``simulation.py:359-382`` and ``:431-451`` differ only in punctuation)."""
         warnings.warn(
             "Supplying a 'SimConfig' to QutipEmulator has been deprecated."
             " Please instantiate with a 'NoiseModel' instead.",
             DeprecationWarning,
-            stacklevel=2,
+            stacklevel=3,
         )
-        if not (hasattr(cfg, "to_noise_model") and hasattr(cfg, "supported_noises")):
-            raise ValueError(f"Object {cfg} is not a valid `SimConfig`.")
-        interaction = self._hamiltonian_data.basis_data.interaction_type
-        not_supported = set(cfg.noise) - cfg.supported_noises[interaction]
-        if not_supported:
+        if not all(hasattr(cfg, a) for a in ("to_noise_model", "supported_noises", "noise")):
+            raise ValueError(f"Object {cfg} is not a valid `SimConfig`{invalid_suffix}")
+        mode = self._hamiltonian_data.basis_data.interaction_type
+        unsupported = set(cfg.noise) - cfg.supported_noises[mode]
+        if unsupported:
             raise NotImplementedError(
-                f"Interaction mode '{interaction}' "
-                "does not support simulation of noise types:"
-                f"{', '.join(not_supported)}."
+                f"Interaction mode '{mode}' does not support simulation of noise types:"
+                f"{list_prefix}{', '.join(unsupported)}."
             )
-        former_dim = self.dim
-        noise_model = cfg.to_noise_model()
+        return cfg.to_noise_model()
+
+    def _adopt_noise_model(self, noise_model: NoiseModel) -> None:
+        """Rebuild the Hamiltonian data under a new noise model and keep or reset the initial state
+        (``simulation.py:383-412``)."""
+        dim_before = self.dim
         self._noise_trajectories_used = False
         self._hamiltonian_data = HamiltonianData(
-            self.samples_obj,
-            self._register,
-            self.device,
-            noise_model,
+            self.samples_obj, self._register, self.device, noise_model,
             self._get_n_trajectories(noise_model, check_value=True),
         )
         self._current_spec = next(self._specs)[0]
         self._noiseless_cache = {}
-        if self.dim == former_dim:
+        if self.dim != dim_before:
+            if not self._initial_is_ground:
+                warnings.warn(
+                    "Current initial state's dimension does not match new"
+                    " dimensions. Setting it to 'all-ground'."
+                )
+            self.set_initial_state("all-ground")
+        else:
             self.set_initial_state(self._initial_state)
-            return
-        if not self._initial_is_ground:
-            warnings.warn(
-                "Current initial state's dimension does not match new"
-                " dimensions. Setting it to 'all-ground'."
-            )
-        self.set_initial_state("all-ground")
+
+    def set_config(self, cfg: Any) -> None:
+        """Sets current config to cfg and updates simulation parameters (``simulation.py:348-412``; deprecated
+        since v1.6 like the original).  ``cfg`` is duck-typed."""
+        self._adopt_noise_model(self._noise_model_of_config(cfg, ".", ""))
 
     def add_config(self, config: Any) -> None:
-        """Updates the current configuration with parameters of another one (``simulation.py:414-469``)."""
-        from dataclasses import asdict
+        """Updates the current configuration with parameters of another one (``simulation.py:414-469``): noise
+        types that are new get their parameters from ``config``, the ones already present keep theirs."""
+        import dataclasses as _dc
 
-        warnings.warn(
-            "Supplying a 'SimConfig' to QutipEmulator has been deprecated."
-            " Please instantiate with a 'NoiseModel' instead.",
-            DeprecationWarning,
-            stacklevel=2,
-        )
-        if not (hasattr(config, "to_noise_model") and hasattr(config, "supported_noises")):
-            raise ValueError(f"Object {config} is not a valid `SimConfig`")
-        interaction = self._hamiltonian_data.basis_data.interaction_type
-        not_supported = set(config.noise) - config.supported_noises[interaction]
-        if not_supported:
-            raise NotImplementedError(
-                f"Interaction mode '{interaction}' "
-                "does not support simulation of noise types: "
-                f"{', '.join(not_supported)}."
-            )
-        noise_model = config.to_noise_model()
-        old_noise_set = set(self._hamiltonian_data.noise_model.noise_types)
-        diff_noise_set = old_noise_set.union(noise_model.noise_types) - old_noise_set
-        param_dict: dict[str, Any] = asdict(self._hamiltonian_data.noise_model)
-        relevant_params = NoiseModel._find_relevant_params(
-            diff_noise_set,
-            noise_model.state_prep_error,
-            noise_model.amp_sigma,
-            noise_model.laser_waist,
-        )
-        for param in relevant_params:
-            param_dict[param] = getattr(noise_model, param)
-        param_dict.pop("noise_types")
-        merged = NoiseModel(**param_dict)
-        try:
-            new_cfg = self._simconfig_class().from_noise_model(merged)
-        except ImportError:
-            new_cfg = _NoiseModelConfig(merged, type(config))
-        self.set_config(new_cfg)
+        incoming = self._noise_model_of_config(config, "", " ")
+        current = self._hamiltonian_data.noise_model
+        added = set(incoming.noise_types) - set(current.noise_types)
+        params = _dc.asdict(current)
+        params.pop("noise_types")
+        for name in NoiseModel._find_relevant_params(
+            added, incoming.state_prep_error, incoming.amp_sigma, incoming.laser_waist
+        ):
+            params[name] = getattr(incoming, name)
+        self._adopt_noise_model(NoiseModel(**params))
 
     def show_config(self, solver_options: bool = False) -> None:
         """Shows current configuration (``simulation.py:471-473``)."""
@@ -392,11 +373,7 @@ class B200Emulator:
 
     def reset_config(self) -> None:
         """Resets configuration to default (``simulation.py:475-477``)."""
-        try:
-            cfg = self._simconfig_class()()
-        except ImportError:
-            cfg = _NoiseModelConfig(NoiseModel(), None)
-        self.set_config(cfg)
+        self.set_config(_NoiseModelConfig(NoiseModel(), None))
 
     # ---- operators (hamiltonian.py:145-244, simulation.py:601-623) -------------------------------
     @property
