@@ -639,8 +639,7 @@ class B200Backend(EmulatorBackend):
         D = pending[0][0].hilbert_dim
         batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
         traj_nb, n_trajectories = 0, sim.n_trajectories
-        for b0 in range(0, len(pending), batch):
-            chunk = pending[b0 : b0 + batch]
+        for chunk in pending.batches(batch):
             if config.print_progress:
                 for _, reps in chunk:
                     if reps == 1:

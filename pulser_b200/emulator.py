@@ -107,6 +107,25 @@ class _PendingTrajectories:
     def __iter__(self) -> Iterator[tuple[HamiltonianSpec, int]]:
         return (self._make(k) for k in range(len(self._entries)))
 
+    def batches(self, batch: int) -> Iterator[list]:
+        """Chunks of ``batch`` entries; the specs of the NEXT chunk are assembled by a helper thread while the
+        caller's current chunk is on the GPU (``pb200_propagate`` runs without the GIL), so the per-trajectory host
+        work -- pulser-core's sample rebuilding and the spec extraction, ~20 ms per 16-atom trajectory -- is off
+        the critical path.  Building a spec draws no random numbers."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        n = len(self._entries)
+        if n == 0:
+            return
+        build = lambda b0: [self._make(k) for k in range(b0, min(b0 + batch, n))]  # noqa: E731
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(build, 0)
+            for b0 in range(0, n, batch):
+                chunk = pending.result()
+                if b0 + batch < n:
+                    pending = pool.submit(build, b0 + batch)
+                yield chunk
+
 
 class _NoiseModelConfig:
     """Minimal SimConfig stand-in (``noise``, ``supported_noises``, ``to_noise_model``) used by ``add_config`` /
@@ -795,8 +814,7 @@ class B200Emulator:
                     c = flipper._flip(c)
                 counts[t_index] += c
 
-        for b0 in range(0, len(pending), batch):
-            chunk = pending[b0 : b0 + batch]
+        for chunk in pending.batches(batch):
             if print_progress:
                 for _, reps in chunk:
                     if reps == 1:
@@ -826,8 +844,7 @@ class B200Emulator:
             # bound device memory: 3 state buffers + (maybe) per-trajectory Dint
             batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
         traj_nb = 0
-        for b0 in range(0, len(pending), batch):
-            chunk = pending[b0 : b0 + batch]
+        for chunk in pending.batches(batch):
             states = self._run_batch([s for s, _ in chunk], opts)
             for i, (spec, reps) in enumerate(chunk):
                 if print_progress:
