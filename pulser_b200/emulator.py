@@ -702,7 +702,7 @@ class B200Emulator:
         Returns ``CoherentResults``, or ``NoisyResults`` when the noise model
         has stochastic noise.
         """
-        if progress_bar not in (True, False, None):
+        if not (progress_bar is True or progress_bar is False or progress_bar is None):  # 1 == True is not a bool
             raise ValueError("`progress_bar` must be a bool.")
         opts = self._validate_options(options)
         self._check_supported()

@@ -389,3 +389,116 @@ def test_run_from_sequence_and_from_samples_agree(emu):
     fa = a.run().get_final_state().full()
     fb = b.run().get_final_state().full()
     np.testing.assert_allclose(fa, fb, rtol=1e-16, atol=0)
+
+
+def test_eval_times_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:721-816 (test_eval_times), statement by statement."""
+    seq = _seq()
+    new = lambda: emu.B200Emulator.from_sequence(seq, sampling_rate=1.0)  # noqa: E731
+    with pytest.raises(ValueError, match="evaluation_times float must be between 0 and 1."):
+        new().set_evaluation_times(3.0)
+    with pytest.raises(ValueError, match="Wrong evaluation time label."):
+        new().set_evaluation_times(123)
+    with pytest.raises(ValueError, match="Wrong evaluation time label."):
+        new().set_evaluation_times("Best")
+    sim = new()
+    with pytest.raises(ValueError, match="Provided evaluation-time list contains negative values."):
+        sim.set_evaluation_times([-1, 0, sim.sampling_times[-2]])
+    with pytest.raises(ValueError, match="Provided evaluation-time list extends further than sequence duration."):
+        sim.set_evaluation_times([0, sim.sampling_times[-1] + 10])
+    sim.set_evaluation_times("Full")
+    assert sim._eval_times_instruction == "Full"
+    np.testing.assert_almost_equal(sim._eval_times_array, sim.sampling_times)
+    sim.set_evaluation_times("Minimal")
+    np.testing.assert_almost_equal(sim._eval_times_array, np.array([sim.sampling_times[0], sim._tot_duration / 1000]))
+    sim.set_evaluation_times([0, sim.sampling_times[-3], sim._tot_duration / 1000])
+    np.testing.assert_almost_equal(sim._eval_times_array,
+                                   np.array([0, sim.sampling_times[-3], sim._tot_duration / 1000]))
+    sim.set_evaluation_times([])
+    np.testing.assert_almost_equal(sim._eval_times_array, np.array([0, sim._tot_duration / 1000]))
+    sim.set_evaluation_times(0.0001)
+    np.testing.assert_almost_equal(sim._eval_times_array, np.array([0, sim._tot_duration / 1000]))
+    sim = new()
+    sim.set_evaluation_times([sim.sampling_times[-10], sim.sampling_times[-3]])
+    np.testing.assert_almost_equal(
+        sim._eval_times_array,
+        np.array([0, sim.sampling_times[-10], sim.sampling_times[-3], sim._tot_duration / 1000]))
+    sim = new()
+    sim.set_evaluation_times(0.4)
+    np.testing.assert_almost_equal(
+        sim.sampling_times[np.linspace(0, len(sim.sampling_times) - 1, int(0.4 * len(sim.sampling_times)), dtype=int)],
+        sim._eval_times_array)
+
+
+def test_empty_sequences_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:434-473 (test_empty_sequences): messages, and a
+    sequence of delays only gives all-zero tables whatever the SPAM trajectory."""
+    from pulser import NoiseModel, Register, Sequence
+    from pulser.devices import MockDevice
+    from pulser.sampler import sampler
+
+    reg = Register({"control1": (-4, 0), "target": (0, 4), "control2": (4, 0)})
+    seq = Sequence(reg, MockDevice)
+    with pytest.raises(ValueError, match="no declared channels"):
+        emu.B200Emulator.from_sequence(seq)
+    seq.declare_channel("ch0", "mw_global")
+    with pytest.raises(ValueError, match="No instructions given"):
+        emu.B200Emulator.from_sequence(seq)
+    with pytest.raises(ValueError, match="SequenceSamples is empty"):
+        emu.B200Emulator(sampler.sample(seq), seq.register, seq.device)
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("test", "raman_local", "target")
+    seq.declare_channel("test2", "rydberg_global")
+    with pytest.raises(ValueError, match="No instructions given"):
+        emu.B200Emulator.from_sequence(seq)
+    seq.delay(100, "test")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(
+            seq, noise_model=NoiseModel(samples_per_run=1, state_prep_error=0.005, p_false_pos=0.01, p_false_neg=0.05),
+            n_trajectories=15)
+    for d in sim._current_spec.drives:
+        np.testing.assert_equal(d.coef, 0)
+        np.testing.assert_equal(d.det, 0)
+
+
+def test_run_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:636-718 (test_run) without the QuTiP-only pieces: initial
+    state validation, progress_bar validation, measurement basis, SPAM with a non-ground initial state."""
+    from pulser import NoiseModel
+
+    seq = _seq(duration=400)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01,
+                                             noise_model=NoiseModel(p_false_pos=0.01, p_false_neg=0.05))
+    n = sim._hamiltonian_data.n_qudits
+    bad_initial = np.array([1.0])
+    good_initial_array = np.r_[1, np.zeros(sim.dim**n - 1)]
+    good_no_dims = np.zeros(sim.dim**n)
+    good_no_dims[2] = 1.0
+    with pytest.raises(ValueError, match="Incompatible shape of initial state"):
+        sim.set_initial_state(bad_initial)
+    sim.set_initial_state(good_initial_array)
+    sim.run()
+    sim.set_initial_state(good_no_dims)
+    sim.run()
+    seq.measure("ground-rydberg")
+    sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01)
+    sim.set_initial_state(good_no_dims)
+    sim.run()
+    assert sim.samples_obj._measurement == "ground-rydberg"
+    sim.run(progress_bar=True)
+    sim.run(progress_bar=False)
+    sim.run(progress_bar=None)
+    with pytest.raises(ValueError, match="`progress_bar` must be a bool."):
+        sim.run(progress_bar=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01,
+                                             noise_model=NoiseModel(samples_per_run=1, state_prep_error=0.1),
+                                             n_trajectories=1)
+    sim.set_initial_state(good_no_dims)
+    with pytest.raises(NotImplementedError,
+                       match="Can't combine state preparation errors with an initial state different from the ground."):
+        sim.run()
