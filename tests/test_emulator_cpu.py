@@ -502,3 +502,111 @@ def test_run_port(emu):
     with pytest.raises(NotImplementedError,
                        match="Can't combine state preparation errors with an initial state different from the ground."):
         sim.run()
+
+
+def _ccz_sequence():
+    """The fixture sequence of the reference's simulation tests (test_simulation.py:40-95): three atoms, local Raman
+    pi_Y pulses then the CCZ on a local Rydberg channel -- 'all' basis, nine 1 us pulses."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.waveforms import BlackmanWaveform
+
+    reg = Register({"control1": np.array([-4.0, 0.0]), "target": np.array([0.0, 4.0]),
+                    "control2": np.array([4.0, 0.0])})
+    duration = 1000
+    pi_pulse = Pulse.ConstantDetuning(BlackmanWaveform(duration, np.pi), 0.0, 0)
+    twopi_pulse = Pulse.ConstantDetuning(BlackmanWaveform(duration, 2 * np.pi), 0.0, 0)
+    pi_y = Pulse.ConstantDetuning(BlackmanWaveform(duration, np.pi), 0.0, -np.pi / 2)
+    seq = Sequence(reg, DigitalAnalogDevice)
+    seq.declare_channel("raman", "raman_local", "control1")
+    seq.add(pi_y, "raman")
+    seq.target("target", "raman")
+    seq.add(pi_y, "raman")
+    seq.target("control2", "raman")
+    seq.add(pi_y, "raman")
+    seq.declare_channel("ryd", "rydberg_local", "control1")
+    seq.add(pi_pulse, "ryd", protocol="wait-for-all")
+    seq.target("control2", "ryd")
+    seq.add(pi_pulse, "ryd")
+    seq.target("target", "ryd")
+    seq.add(twopi_pulse, "ryd")
+    seq.target("control2", "ryd")
+    seq.add(pi_pulse, "ryd")
+    seq.target("control1", "ryd")
+    seq.add(pi_pulse, "ryd")
+    seq.add(Pulse.ConstantPulse(duration, 1, 0, 0), "ryd")
+    return seq
+
+
+def test_initialization_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:111-222 (test_initialization_and_construction_of_
+    hamiltonian) without the QuTiP type checks."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice, MockDevice
+    from pulser.register.register_layout import RegisterLayout
+    from pulser.sampler import sampler
+
+    seq = _ccz_sequence()
+    fake_sequence = {"pulse1": "fake", "pulse2": "fake"}
+    with pytest.raises(TypeError, match="sequence has to be a valid"):
+        emu.B200Emulator.from_sequence(fake_sequence)
+    with pytest.raises(TypeError, match="sequence has to be a valid"):
+        emu.B200Emulator(fake_sequence, Register.square(2, prefix="q"), MockDevice)
+    with pytest.raises(ValueError, match="The ids of qubits targeted in Local channels"):
+        emu.B200Emulator(sampler.sample(seq),
+                         Register({"target": np.array([0.0, 0.0]), "control2": np.array([1.0, 0.0])}), MockDevice)
+    with pytest.raises(ValueError, match="'noise_model' and 'config' cannot both be provided"):
+        emu.B200Emulator.from_sequence(seq, config=_DuckConfig(NoiseModel()), noise_model=NoiseModel())
+    with pytest.raises(ValueError, match="'n_trajectories' must be defined when the NoiseModel contains"
+                                         " stochastic noise"):
+        emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(amp_sigma=0.1))
+    sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.011)
+    sampled_seq = sampler.sample(seq)
+    ext = sampled_seq.extend_duration(sampled_seq.max_duration + 1)
+    for ch in sampled_seq.channels:
+        for qty in ("amp", "det", "phase"):
+            assert np.all(np.equal(getattr(sim.samples_obj.channel_samples[ch], qty),
+                                   getattr(ext.channel_samples[ch], qty)))
+    assert sim._current_spec.n_qudits == len(seq.qubit_info)
+    assert sim._tot_duration == 9000  # seq has 9 pulses of 1 us
+    assert sim._current_spec.qubit_ids == ["control1", "target", "control2"]
+    with pytest.raises(ValueError, match="too small, less than"):
+        emu.B200Emulator.from_sequence(seq, sampling_rate=0.0001)
+    with pytest.raises(ValueError, match="`sampling_rate`"):
+        emu.B200Emulator.from_sequence(seq, sampling_rate=5)
+    with pytest.raises(ValueError, match="`sampling_rate`"):
+        emu.B200Emulator.from_sequence(seq, sampling_rate=-1)
+    assert sim._sampling_rate == 0.011
+    assert len(sim.sampling_times) == int(sim._sampling_rate * sim._tot_duration)
+    with pytest.warns(UserWarning, match="returns a copy of itself"):
+        seq_copy = seq.build()
+    x = seq_copy.declare_variable("x")
+    seq_copy.add(Pulse.ConstantPulse(x, 1, 0, 0), "ryd")
+    with pytest.raises(ValueError, match="needs to be built"):
+        emu.B200Emulator.from_sequence(seq_copy)
+    mapp_reg = RegisterLayout([[0, 0], [10, 10]]).make_mappable_register(1)
+    with pytest.raises(ValueError, match="needs to be built"):
+        emu.B200Emulator.from_sequence(Sequence(mapp_reg, DigitalAnalogDevice))
+
+
+def test_extraction_of_sequences_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:225-251 (test_extraction_of_sequences): every pulse of
+    every local channel shows up in the per-qubit tables of the spec, as coef = 0.5 amp exp(-i phase) and det."""
+    from pulser import Pulse
+
+    seq = _ccz_sequence()
+    sim = emu.B200Emulator.from_sequence(seq)
+    spec = sim._current_spec
+    tabs = {d.basis: d for d in spec.drives}
+    qidx = {q: i for i, q in enumerate(spec.qubit_ids)}
+    for channel in seq.declared_channels:
+        basis = seq.declared_channels[channel].basis
+        assert seq.declared_channels[channel].addressing == "Local"
+        for slot in seq._schedule[channel]:
+            if isinstance(slot.type, Pulse):
+                for qubit in slot.targets:
+                    k = qidx[qubit]
+                    amp = slot.type.amplitude.samples
+                    np.testing.assert_allclose(tabs[basis].coef[k, slot.ti:slot.tf],
+                                               0.5 * amp * np.exp(-1j * float(slot.type.phase)), rtol=1e-15, atol=0)
+                    np.testing.assert_array_equal(tabs[basis].det[k, slot.ti:slot.tf], slot.type.detuning.samples)
