@@ -610,3 +610,41 @@ def test_extraction_of_sequences_port(emu):
                     np.testing.assert_allclose(tabs[basis].coef[k, slot.ti:slot.tf],
                                                0.5 * amp * np.exp(-1j * float(slot.type.phase)), rtol=1e-15, atol=0)
                     np.testing.assert_array_equal(tabs[basis].det[k, slot.ti:slot.tf], slot.type.detuning.samples)
+
+
+def test_noise_port(emu, capfd):
+    """reference tests/pulser_simulation/test_simulation.py:891-953 (test_noise): SPAM trajectories of seed 3 are merged
+    into the same groups (progress lines identical), the depolarizing channel is refused in the 3-level basis with
+    the reference's message, unprepared atoms get all-zero tables.  The reference's Counter golden depends on the order
+    in which QuTiP-era code consumed np.random; here it is a statistical target (first-level sample: 75 shots)."""
+    from pulser import NoiseModel
+
+    seq = _ccz_sequence()
+    np.random.seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim2 = emu.B200Emulator.from_sequence(
+            seq, sampling_rate=0.01,
+            noise_model=NoiseModel(samples_per_run=5, p_false_pos=0.01, p_false_neg=0.05, state_prep_error=0.9),
+            n_trajectories=15)
+        counts = sim2.run(print_progress=True).sample_final_state()
+    out, _ = capfd.readouterr()
+    assert out.rstrip("\n").split("\n") == [
+        "Emulating Trajectories [1 - 13]/15",
+        "Emulating Trajectory 14/15",
+        "Emulating Trajectory 15/15",
+    ]
+    ref = Counter({"000": 824, "100": 41, "101": 57, "001": 63, "010": 15})
+    assert sum(counts.values()) == 1000
+    tv = 0.5 * sum(abs(counts.get(k, 0) - ref.get(k, 0)) for k in set(counts) | set(ref)) / 1000
+    assert tv < 0.08, (counts, tv)
+    with pytest.raises(NotImplementedError, match="Cannot include"):
+        emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(depolarizing_rate=0.05))
+    pending = sim2._pending_trajectories()  # a second use redraws the trajectories (simulation.py:892-902)
+    bad = sim2._hamiltonian_data.noise_trajectories[0].trajectory.bad_atoms
+    assert any(bad.values())
+    spec = pending[0][0]
+    for d in spec.drives:
+        for q, is_bad in enumerate(bad.values()):
+            if is_bad:
+                assert np.all(d.coef[q] == 0.0) and np.all(d.det[q] == 0.0)
