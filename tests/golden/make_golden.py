@@ -2,7 +2,7 @@
 imported from /root/reference) plus the tight-tolerance oracle.
 
 Run in the build container only (the GPU box has no /root/reference):
-    python tests/golden/make_golden.py [--extra | --xy | --slm]
+    python tests/golden/make_golden.py [--extra | --xy | --slm | --counters]
 
 Each ``*.npz`` holds a HamiltonianSpec (what the reference's Hamiltonian
 constructor receives, extracted from real pulser objects), an initial state and
@@ -164,7 +164,7 @@ def main():
         save(f"orc_noisy_traj{i}", spec, psi0=psi0, orc_final=oracle_final(spec, psi0), reps=reps)
 
 
-if __name__ == "__main__" and "--extra" not in sys.argv and "--xy" not in sys.argv and "--slm" not in sys.argv:
+if __name__ == "__main__" and "--extra" not in sys.argv and "--xy" not in sys.argv and "--slm" not in sys.argv and "--counters" not in sys.argv:
     main()
 
 
@@ -315,3 +315,130 @@ def slm():
 
 if __name__ == "__main__" and "--slm" in sys.argv:
     slm()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fifth batch: the reference's Counter goldens of its master-equation tests (test_simulation.py:978-1046 test_noises_
+# rydberg, :1079-1171 test_noises_digital).  np.random.seed(123); build; run; sample_final_state() -- nothing between
+# the seed and the 1000 uniforms of the sampling draws from np.random, so the Counter is a function of the final
+# density matrix alone (populations resolved to ~1e-3) and of the sampling recipe.  The oracle reproduces all 14
+# EXACTLY (asserted below); the specs + expected counters are the fixtures of the GPU test.
+RYDBERG_COUNTERS = [
+    (("dephasing",), {"0": 572, "1": 428}, 1),
+    (("relaxation",), {"0": 572, "1": 428}, 1),
+    (("eff_noise",), {"0": 572, "1": 428}, 1),
+    (("depolarizing",), {"0": 561, "1": 439}, 3),
+    (("dephasing", "depolarizing", "relaxation"), {"0": 562, "1": 438}, 5),
+    (("eff_noise", "dephasing"), {"0": 573, "1": 427}, 2),
+    (("eff_noise", "leakage"), {"0": 572, "1": 428}, 1),
+]
+_DEPH = {"111": 978, "110": 12, "011": 7, "101": 3}
+_DEPO = {"111": 827, "101": 63, "011": 59, "110": 40, "010": 5, "001": 4, "000": 1, "100": 1}
+_DEPH_DEPO = {"111": 807, "101": 64, "011": 60, "110": 56, "001": 5, "010": 4, "100": 3, "000": 1}
+_EFF_DEPH = {"111": 961, "101": 15, "110": 14, "011": 9, "001": 1}
+DIGITAL_COUNTERS = [
+    (("dephasing",), _DEPH, 1),
+    (("eff_noise",), _DEPH, 1),
+    (("depolarizing",), _DEPO, 3),
+    (("dephasing", "depolarizing"), _DEPH_DEPO, 4),
+    (("eff_noise", "dephasing"), _EFF_DEPH, 2),
+    (("eff_noise", "leakage"), _DEPH, 1),
+    (("eff_noise", "leakage", "dephasing"), _EFF_DEPH, 2),
+]
+
+
+def _legacy_params(noise):
+    from pulser.noise_model import _LEGACY_DEFAULTS
+
+    return {
+        p: _LEGACY_DEFAULTS[p]
+        for p in NoiseModel._find_relevant_params(
+            [n for n in noise if n not in ["leakage", "eff_noise"]],
+            state_prep_error=_LEGACY_DEFAULTS["state_prep_error"],
+            amp_sigma=_LEGACY_DEFAULTS["amp_sigma"],
+            laser_waist=_LEGACY_DEFAULTS["laser_waist"],
+        )
+    }
+
+
+def counter_case(kind, noise):
+    """(sequence, NoiseModel, n_trajectories) of one parametrisation, as the reference test builds it."""
+    params = _legacy_params(noise)
+    with_leakage = "leakage" in noise
+    z = np.diag([1.0, -1.0]).astype(complex)
+    if kind == "rydberg":  # test_simulation.py:990-1026
+        seq = Sequence(Register.from_coordinates([(0, 0)], prefix="q"), DigitalAnalogDevice)
+        seq.declare_channel("ch0", "rydberg_global")
+        seq.add(Pulse.ConstantPulse(2500, np.pi, 0, 0), "ch0")
+        if with_leakage or "eff_noise" in noise:
+            params["eff_noise_opers"] = [np.diag([1.0, 0, 0]).astype(complex) if with_leakage else z]
+            params["eff_noise_rates"] = [0.1 if with_leakage else 0.025]
+    else:  # test_simulation.py:55-72 (seq_digital), :1115-1146
+        reg = Register({"control1": np.array([-4.0, 0.0]), "target": np.array([0.0, 4.0]),
+                        "control2": np.array([4.0, 0.0])})
+        pi_y = Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, -np.pi / 2)
+        seq = Sequence(reg, DigitalAnalogDevice)
+        seq.declare_channel("raman", "raman_local", "control1")
+        seq.add(pi_y, "raman")
+        seq.target("target", "raman")
+        seq.add(pi_y, "raman")
+        seq.target("control2", "raman")
+        seq.add(pi_y, "raman")
+        if "dephasing" in noise:
+            params["hyperfine_dephasing_rate"] = 0.05
+        if with_leakage or "eff_noise" in noise:
+            params["eff_noise_opers"] = [np.diag([0, 1.0, 0]).astype(complex) if with_leakage else z]
+            params["eff_noise_rates"] = [0.1 if with_leakage else 0.025]
+    n_traj = params.pop("runs", None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nm = NoiseModel(with_leakage=with_leakage, **params)
+    return seq, nm, n_traj
+
+
+def counters():
+    from collections import Counter
+
+    from oracle import evolve as ev
+    from pulser_b200.results import B200Result, CoherentResults, DensityMatrix
+
+    for kind, table in (("rydberg", RYDBERG_COUNTERS), ("digital", DIGITAL_COUNTERS)):
+        for noise, expected, n_ops in table:
+            from pulser_b200.emulator import B200Emulator
+
+            np.random.seed(123)
+            seq, nm, n_traj = counter_case(kind, noise)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                # same constructor path as QutipEmulator.from_sequence (needs no device): what it draws from
+                # np.random while building its HamiltonianData is part of the reference's recipe
+                sim = B200Emulator.from_sequence(seq, sampling_rate=0.01, noise_model=nm, n_trajectories=n_traj)
+            spec = sim._current_spec
+            assert len(spec.collapse_ops) == n_ops, (noise, len(spec.collapse_ops))
+            psi0 = ev.all_ground_state(spec)
+            tf = spec.sampling_times[-1]
+            rho = ev.mesolve(OracleHamiltonian.from_spec(spec), psi0, [0.0, tf], rtol=1e-9, atol=1e-11)[-1]
+            n, d = spec.n_qudits, spec.dim
+            meas = "ground-rydberg" if kind == "rydberg" else "digital"
+            res = CoherentResults(
+                [B200Result(tuple(spec.qubit_ids), meas, DensityMatrix(rho, [[d] * n, [d] * n]), True, evaluation_time=1.0)],
+                n, spec.basis_name, np.array([tf]), meas)
+            # the reference seeds ONCE, before building the emulator: the constructor has drawn uniforms from
+            # np.random by now (state-preparation draws of HamiltonianData, pulser/_hamiltonian_data/
+            # hamiltonian_data.py:795-800) -- count them so that the GPU test, which has no pulser, can put the global
+            # stream in the same position
+            probe = np.random.get_state()
+            nxt = np.random.rand(4)
+            np.random.seed(123)
+            stream = np.random.rand(64)
+            pre_draws = next(k for k in range(60) if np.array_equal(stream[k:k + 4], nxt))
+            np.random.set_state(probe)
+            got = res.sample_final_state()
+            assert got == Counter(expected), (kind, noise, got)
+            name = f"ref_counter_{kind}_" + "_".join(noise)
+            save(name, spec, psi0=psi0, orc_rho=rho, meas_basis=meas, seed=123, pre_draws=pre_draws,
+                 counter_keys=np.array(list(expected)), counter_values=np.array(list(expected.values())))
+
+
+if __name__ == "__main__" and "--counters" in sys.argv:
+    counters()

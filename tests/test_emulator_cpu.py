@@ -648,3 +648,53 @@ def test_noise_port(emu, capfd):
         for q, is_bad in enumerate(bad.values()):
             if is_bad:
                 assert np.all(d.coef[q] == 0.0) and np.all(d.det[q] == 0.0)
+
+
+@pytest.mark.parametrize("noise,result", [
+    (("dephasing",), {"0": 572, "1": 428}),
+    (("depolarizing",), {"0": 561, "1": 439}),
+    (("dephasing", "depolarizing", "relaxation"), {"0": 562, "1": 438}),
+    (("eff_noise", "leakage"), {"0": 572, "1": 428}),
+])
+def test_noises_rydberg_port(emu, noise, result):
+    """reference tests/pulser_simulation/test_simulation.py:978-1046 (test_noises_rydberg) through the facade, seed and
+    all: np.random.seed(123), build, run, sample_final_state() == the reference's hard-coded Counter.  Exact equality
+    means the facade draws from np.random exactly where QutipEmulator does, builds the same collapse operators and
+    (with the oracle-backed plan standing in for the device) evolves to the same populations as QuTiP's mesolve."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.noise_model import _LEGACY_DEFAULTS
+
+    np.random.seed(123)
+    seq = Sequence(Register.from_coordinates([(0, 0)], prefix="q"), DigitalAnalogDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.add(Pulse.ConstantPulse(2500, np.pi, 0, 0), "ch0")
+    params = {
+        p: _LEGACY_DEFAULTS[p]
+        for p in NoiseModel._find_relevant_params(
+            [n for n in noise if n not in ["leakage", "eff_noise"]],
+            state_prep_error=_LEGACY_DEFAULTS["state_prep_error"],
+            amp_sigma=_LEGACY_DEFAULTS["amp_sigma"],
+            laser_waist=_LEGACY_DEFAULTS["laser_waist"],
+        )
+    }
+    with_leakage = "leakage" in noise
+    if with_leakage or "eff_noise" in noise:
+        params["eff_noise_opers"] = [np.diag([1.0, 0, 0]).astype(complex) if with_leakage
+                                     else np.diag([1.0, -1.0]).astype(complex)]
+        params["eff_noise_rates"] = [0.1 if with_leakage else 0.025]
+    n_trajectories = params.pop("runs", None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01,
+                                             noise_model=NoiseModel(with_leakage=with_leakage, **params),
+                                             n_trajectories=n_trajectories)
+        assert set(sim.noise_model.noise_types) == set(noise)
+        res = sim.run()
+    assert res.sample_final_state() == Counter(result)
+    rho = res.states[-1].full()
+    trace_2 = np.trace(rho @ rho).real
+    assert trace_2 < 1 and not np.isclose(trace_2, 1)
+    if with_leakage:
+        state = res.get_final_state().full()
+        assert np.allclose(state[2, :], 0) and np.allclose(state[:, 2], 0)

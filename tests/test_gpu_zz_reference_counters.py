@@ -1,0 +1,60 @@
+"""GPU master-equation path against the reference's own Counter goldens (runs last: file name sorts after the
+other GPU tests).
+
+``tests/golden/ref_counter_*.npz`` <- the hard-coded Counters of the reference's
+``tests/pulser_simulation/test_simulation.py:978-1046`` (test_noises_rydberg) and ``:1079-1171``
+(test_noises_digital): real QuTiP ``mesolve`` outputs sampled with ``np.random.seed(123)``.  The CPU oracle reproduces
+all 14 exactly (``tests/golden/make_golden.py --counters`` asserts it, ``tests/test_oracle_cpu.py`` re-checks); here the
+CUDA Lindblad path must land on the same density matrix (north-star tolerance 1e-4) and -- sampled with the
+reference's recipe from the same stream position -- on the same Counter, up to the two shots a 1e-4 shift of a
+cumulative boundary can move.
+"""
+import glob
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from pulser_b200.spec import HamiltonianSpec
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "ref_counter_*.npz")))
+
+
+def load(name):
+    with np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False) as data:
+        return HamiltonianSpec.from_npz(data), {k: data[k] for k in data.files}
+
+
+def sample_like_the_reference(spec, rho, extra):
+    from pulser_b200.results import B200Result, CoherentResults, DensityMatrix
+
+    n, d = spec.n_qudits, spec.dim
+    meas = str(extra["meas_basis"])
+    res = CoherentResults(
+        [B200Result(tuple(spec.qubit_ids), meas, DensityMatrix(rho, [[d] * n, [d] * n]), True, evaluation_time=1.0)],
+        n, spec.basis_name, np.array([spec.sampling_times[-1]]), meas)
+    np.random.seed(int(extra["seed"]))
+    np.random.rand(int(extra["pre_draws"]))  # what the reference's constructor drew before the run
+    return res.sample_final_state()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_master_equation_reference_counters(lib, name):
+    from pulser_b200 import engine
+    from pulser_b200.lindblad import LindbladPlan
+
+    assert engine.device_count() > 0
+    spec, extra = load(name)
+    expected = Counter(dict(zip((str(k) for k in extra["counter_keys"]), (int(v) for v in extra["counter_values"]))))
+    with LindbladPlan(spec) as lp:
+        lp.set_state(extra["psi0"])
+        lp.propagate(0.0, spec.sampling_times[-1])
+        rho = lp.get_rho()[0]
+    assert abs(np.trace(rho).real - 1.0) < 1e-6
+    assert np.max(np.abs(rho - extra["orc_rho"])) < 1e-4
+    got = sample_like_the_reference(spec, rho, extra)
+    moved = sum(abs(got.get(k, 0) - expected.get(k, 0)) for k in set(got) | set(expected)) // 2
+    assert moved <= 2, (got, expected)
