@@ -440,5 +440,93 @@ def counters():
                  counter_keys=np.array(list(expected)), counter_values=np.array(list(expected.values())))
 
 
+def eom_counters():
+    """reference tests/pulser_simulation/test_simulation.py:2594-2650 (test_eom_limit_det): a NOISELESS three-atom run
+    (qutip.sesolve) in EOM mode at the detuning limits; np.random.seed(123); from_sequence; run; sample_final_state()
+    == hard-coded Counter.  Pins the Schroedinger path on real QuTiP output the way counters() pins mesolve."""
+    import dataclasses
+    from collections import Counter
+
+    from pulser.channels import Raman, Rydberg
+    from pulser.channels.dmm import DMM
+    from pulser.channels.eom import RydbergBeam, RydbergEOM
+    from pulser.devices import Device
+
+    from oracle import evolve as ev
+    from pulser_b200.emulator import B200Emulator
+    from pulser_b200.results import B200Result, CoherentResults, StateVector
+
+    def mod_device():  # tests/conftest.py:29-89 of the reference
+        return Device(
+            name="ModDevice", dimensions=3, rydberg_level=70, max_atom_num=2000, max_radial_distance=1000,
+            min_atom_distance=1, supports_slm_mask=True,
+            channel_objects=(
+                Rydberg.Global(1000, 200, clock_period=1, min_duration=1, mod_bandwidth=4.0,
+                               eom_config=RydbergEOM(mod_bandwidth=30.0, limiting_beam=RydbergBeam.RED,
+                                                     max_limiting_amp=50 * 2 * np.pi,
+                                                     intermediate_detuning=800 * 2 * np.pi,
+                                                     controlled_beams=(RydbergBeam.BLUE,))),
+                Rydberg.Local(2 * np.pi * 20, 2 * np.pi * 10, max_targets=2, fixed_retarget_t=0, clock_period=4,
+                              min_retarget_interval=220, mod_bandwidth=4.0,
+                              eom_config=RydbergEOM(mod_bandwidth=20.0, limiting_beam=RydbergBeam.RED,
+                                                    max_limiting_amp=60 * 2 * np.pi,
+                                                    intermediate_detuning=700 * 2 * np.pi,
+                                                    controlled_beams=tuple(RydbergBeam))),
+                Raman.Local(2 * np.pi * 20, 2 * np.pi * 10, max_targets=2, fixed_retarget_t=0,
+                            min_retarget_interval=220, clock_period=4, mod_bandwidth=4.0),
+            ),
+            dmm_objects=(DMM(bottom_detuning=-100, total_bottom_detuning=-10000),
+                         DMM(clock_period=4, mod_bandwidth=4.0, bottom_detuning=-50, total_bottom_detuning=-5000)),
+        )
+
+    reg = Register({"control1": np.array([-4.0, 0.0]), "target": np.array([0.0, 4.0]),
+                    "control2": np.array([4.0, 0.0])})
+    for min_detuning_on, expected in (
+        (True, {"000": 850, "100": 53, "001": 46, "010": 42, "101": 9}),
+        (False, {"000": 879, "010": 49, "100": 40, "001": 32}),
+    ):
+        dev = mod_device()
+        channels = dev.channels
+        if not min_detuning_on:
+            eom_config = dataclasses.replace(channels["rydberg_global"].eom_config, controlled_beams=(RydbergBeam.RED,))
+            channels["rydberg_global"] = dataclasses.replace(channels["rydberg_global"], eom_config=eom_config)
+            dev = dataclasses.replace(dev, channel_ids=list(channels), channel_objects=list(channels.values()))
+        seq = Sequence(reg, dev)
+        seq.declare_channel("ryd_glob", "rydberg_global")
+        seq.add(Pulse.ConstantPulse(1000, np.pi / 2, 0, 0), "ryd_glob")
+        max_abs_det = seq.declared_channels["ryd_glob"].max_abs_detuning
+        detuning_on = -max_abs_det if min_detuning_on else max_abs_det
+        seq.enable_eom_mode("ryd_glob", np.pi, detuning_on, correct_phase_drift=True)
+        seq.add_eom_pulse("ryd_glob", 1000, 0)
+        seq.delay(500, "ryd_glob")
+        seq.modify_eom_setpoint("ryd_glob", np.pi / 2, 0, 0, correct_phase_drift=True)
+        seq.add_eom_pulse("ryd_glob", 1000, 0)
+        np.random.seed(123)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim = B200Emulator.from_sequence(seq)
+        spec = sim._current_spec
+        psi0 = ev.all_ground_state(spec)
+        final = oracle_final(spec, psi0)
+        n, d = spec.n_qudits, spec.dim
+        res = CoherentResults(
+            [B200Result(tuple(spec.qubit_ids), "ground-rydberg", StateVector(final, [[d] * n, [1] * n]), True,
+                        evaluation_time=1.0)],
+            n, spec.basis_name, np.array([spec.sampling_times[-1]]), "ground-rydberg")
+        probe = np.random.get_state()
+        nxt = np.random.rand(4)
+        np.random.seed(123)
+        stream = np.random.rand(64)
+        pre_draws = next(k for k in range(60) if np.array_equal(stream[k:k + 4], nxt))
+        np.random.set_state(probe)
+        got = res.sample_final_state()
+        assert got == Counter(expected), (min_detuning_on, got)
+        save("ref_counter_eom_" + ("min_detuning" if min_detuning_on else "max_detuning"), spec, psi0=psi0,
+             orc_final=final, meas_basis="ground-rydberg", seed=123, pre_draws=pre_draws,
+             counter_keys=np.array(list(expected)), counter_values=np.array(list(expected.values())))
+
+
 if __name__ == "__main__" and "--counters" in sys.argv:
-    counters()
+    if "--eom-only" not in sys.argv:
+        counters()
+    eom_counters()

@@ -384,13 +384,14 @@ def _counter_fixture_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "ref_counter_*.npz")))
 
 
-def _sample_like_the_reference(spec, rho, extra):
-    from pulser_b200.results import B200Result, CoherentResults, DensityMatrix
+def _sample_like_the_reference(spec, state, extra):
+    from pulser_b200.results import B200Result, CoherentResults, DensityMatrix, StateVector
 
     n, d = spec.n_qudits, spec.dim
     meas = str(extra["meas_basis"])
+    wrapped = DensityMatrix(state, [[d] * n, [d] * n]) if np.ndim(state) == 2 else StateVector(state, [[d] * n, [1] * n])
     res = CoherentResults(
-        [B200Result(tuple(spec.qubit_ids), meas, DensityMatrix(rho, [[d] * n, [d] * n]), True, evaluation_time=1.0)],
+        [B200Result(tuple(spec.qubit_ids), meas, wrapped, True, evaluation_time=1.0)],
         n, spec.basis_name, np.array([spec.sampling_times[-1]]), meas)
     np.random.seed(int(extra["seed"]))
     np.random.rand(int(extra["pre_draws"]))  # what the reference's constructor drew before the run
@@ -412,6 +413,14 @@ def test_oracle_mesolve_reproduces_reference_counters(name):
 
     spec, extra = load(name)
     expected = Counter(dict(zip((str(k) for k in extra["counter_keys"]), (int(v) for v in extra["counter_values"]))))
+    if "_eom_" in name:  # test_simulation.py:2594-2650 (test_eom_limit_det): noiseless sesolve run
+        psi = extra["orc_final"]
+        if name.endswith("max_detuning"):  # re-integrate one of the two (|detuning| ~ 2 pi 100 MHz: many periods)
+            psi = evolve.sesolve(OracleHamiltonian.from_spec(spec), extra["psi0"], [0.0, spec.sampling_times[-1]],
+                                 rtol=1e-12, atol=1e-14)[-1]
+            assert np.max(np.abs(psi - extra["orc_final"])) < 1e-8
+        assert _sample_like_the_reference(spec, psi, extra) == expected
+        return
     if spec.n_qudits == 1 or name == "ref_counter_digital_dephasing":
         rho = evolve.mesolve(OracleHamiltonian.from_spec(spec), extra["psi0"], [0.0, spec.sampling_times[-1]],
                              rtol=1e-9, atol=1e-11)[-1]
