@@ -19,6 +19,9 @@ class FakeDevicePlan:
         self.specs = [specs] if isinstance(specs, HamiltonianSpec) else list(specs)
         self.hams = [OracleHamiltonian.from_spec(s) for s in self.specs]
         self.order = interp_order
+        # the coefficients are smooth between two samples: one sampling interval bounds the integrator step (the
+        # oracle's default, 1 ns, is QuTiP's max_step and makes coarse-sampled tests 10-100x slower for nothing)
+        self.max_step = float(np.min(np.diff(self.specs[0].sampling_times)))
         self.states = None
         FakeDevicePlan.calls += 1
 
@@ -34,7 +37,7 @@ class FakeDevicePlan:
 
     def propagate(self, t0, t1, **opts):
         self.states = [
-            evolve.sesolve(h, s, [t0, t1], order=self.order, rtol=1e-10, atol=1e-12)[-1]
+            evolve.sesolve(h, s, [t0, t1], order=self.order, rtol=1e-10, atol=1e-12, max_step=self.max_step)[-1]
             for h, s in zip(self.hams, self.states)
         ]
         return {"n_steps": 1, "n_applies": 1, "n_launches": 0, "max_rho": 0.0}
@@ -110,7 +113,7 @@ class FakeLindbladPlan(FakeDevicePlan):
 
     def propagate(self, t0, t1, **opts):
         self.states = [
-            evolve.mesolve(h, s, [t0, t1], order=self.order, rtol=1e-9, atol=1e-11)[-1]
+            evolve.mesolve(h, s, [t0, t1], order=self.order, rtol=1e-9, atol=1e-11, max_step=self.max_step)[-1]
             for h, s in zip(self.hams, self.states)
         ]
         return {"n_steps": 1, "n_applies": 1, "n_launches": 0, "max_rho": 0.0}
