@@ -698,3 +698,56 @@ def test_noises_rydberg_port(emu, noise, result):
     if with_leakage:
         state = res.get_final_state().full()
         assert np.allclose(state[2, :], 0) and np.allclose(state[:, 2], 0)
+
+
+@pytest.mark.parametrize("noisychannel", [True, False])
+def test_get_final_state_port(emu, noisychannel):
+    """reference tests/pulser_simulation/test_simresults.py:162-241 (test_get_final_state)."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.waveforms import BlackmanWaveform
+    from pulser_b200.results import CoherentResults
+
+    reg = Register({"A": np.array([0.0, 0.0]), "B": np.array([0.0, 10.0])})
+    pi_pulse = Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0)
+    seq_no_meas = Sequence(reg, DigitalAnalogDevice)
+    seq_no_meas.declare_channel("ryd", "rydberg_global")
+    seq_no_meas.add(pi_pulse, "ryd")
+    seq_no_meas.measure("ground-rydberg")
+    np.random.seed(123)
+    sim = emu.B200Emulator.from_sequence(seq_no_meas, evaluation_times=0.05)
+    results = sim.run()
+    if noisychannel:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim = emu.B200Emulator(sim.samples_obj, register=seq_no_meas.register,
+                                   device=seq_no_meas.device, noise_model=NoiseModel(dephasing_rate=0.01),
+                                   evaluation_times=0.05)
+    _results = sim.run()
+    assert isinstance(_results, CoherentResults)
+    final_state = _results.get_final_state()
+    assert (not final_state.isket) if noisychannel else final_state.isket
+    with pytest.raises(TypeError, match="Can't reduce"):
+        _results.get_final_state(reduce_to_basis="digital")
+    np.testing.assert_allclose(  # qutip.Qobj.__eq__ compares within qutip.settings.core["atol"] = 1e-12
+        _results.get_final_state(reduce_to_basis="ground-rydberg", ignore_global_phase=False).full(),
+        _results.states[-1].tidyup().full(), rtol=0, atol=1e-12)
+    assert np.all(np.isclose(np.abs(_results.get_final_state(ignore_global_phase=False).full()),
+                             np.abs(_results.states[-1].full())))
+    assert np.all(np.isclose(np.abs(_results.get_final_state(ignore_global_phase=True).full()),
+                             np.abs(_results.states[-1].full())))
+    seq_ = Sequence(reg, DigitalAnalogDevice)
+    seq_.declare_channel("ryd", "rydberg_global")
+    seq_.declare_channel("ram", "raman_local", initial_target="A")
+    seq_.add(pi_pulse, "ram")
+    seq_.add(pi_pulse, "ram")
+    seq_.add(pi_pulse, "ryd")
+    results_ = emu.B200Emulator.from_sequence(seq_, evaluation_times="Minimal").run()
+    with pytest.raises(ValueError, match="'reduce_to_basis' must be"):
+        results_.get_final_state(reduce_to_basis="all")
+    with pytest.raises(TypeError, match="Can't reduce to chosen basis"):
+        results_.get_final_state(reduce_to_basis="digital")
+    h_states = results_.get_final_state(reduce_to_basis="digital", tol=1, normalize=False).full()[1:]
+    assert np.linalg.norm(h_states) < 3e-6
+    assert np.all(np.isclose(np.abs(results_.get_final_state(reduce_to_basis="ground-rydberg").full()),
+                             np.abs(results.states[-1].full()), atol=1e-5))
