@@ -526,7 +526,40 @@ def eom_counters():
              counter_keys=np.array(list(expected)), counter_values=np.array(list(expected.values())))
 
 
+def expect_leakage():
+    """reference tests/pulser_simulation/test_simresults.py:339-361 (test_expect, "With leakage"): single atom, Blackman
+    pi pulse, collapse operator |x><g| at rate 0.5, sampling_rate 0.1; the reference hard-codes
+    <|r><r|>(T) = 0.7804005 (atol 1e-6), a QuTiP mesolve output.  With the 10 ns sampling grid the number depends on
+    the QobjEvo coefficient interpolation at the 1e-6 level: cubic spline (QuTiP 5 default) gives 0.780400534, linear
+    0.780401390, step 0.778431246 -- the seven printed digits select the cubic spline."""
+    from oracle import evolve as ev
+    from pulser_b200.emulator import B200Emulator
+
+    seq = Sequence(Register.from_coordinates([(0, 0)], prefix="q"), DigitalAnalogDevice)
+    seq.declare_channel("ryd", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0), "ryd")
+    eff = np.zeros((3, 3), dtype=complex)
+    eff[2, 1] = 1.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = B200Emulator.from_sequence(
+            seq, noise_model=NoiseModel(eff_noise_rates=[0.5], eff_noise_opers=[eff], with_leakage=True),
+            sampling_rate=0.1)
+    spec = sim._current_spec
+    psi0 = ev.all_ground_state(spec)
+    tf = spec.sampling_times[-1]
+    vals = {}
+    for order in (3, 1):
+        rho = ev.mesolve(OracleHamiltonian.from_spec(spec), psi0, [0.0, tf], order=order, rtol=1e-11, atol=1e-13)[-1]
+        vals[order] = rho[0, 0].real
+    assert abs(vals[3] - 0.7804005) < 5e-8 and abs(vals[1] - 0.7804005) > 5e-7, vals
+    rho = ev.mesolve(OracleHamiltonian.from_spec(spec), psi0, [0.0, tf], rtol=1e-11, atol=1e-13)[-1]
+    save("ref_expect_leakage", spec, psi0=psi0, orc_rho=rho, ref_value=0.7804005, linear_value=vals[1])
+
+
 if __name__ == "__main__" and "--counters" in sys.argv:
-    if "--eom-only" not in sys.argv:
+    if "--eom-only" not in sys.argv and "--expect-only" not in sys.argv:
         counters()
-    eom_counters()
+    if "--expect-only" not in sys.argv:
+        eom_counters()
+    expect_leakage()

@@ -751,3 +751,68 @@ def test_get_final_state_port(emu, noisychannel):
     assert np.linalg.norm(h_states) < 3e-6
     assert np.all(np.isclose(np.abs(results_.get_final_state(reduce_to_basis="ground-rydberg").full()),
                              np.abs(results.states[-1].full()), atol=1e-5))
+
+
+def test_expect_port(emu):
+    """reference tests/pulser_simulation/test_simresults.py:289-380 (test_expect): messages, pi pulse, SPAM pseudo-
+    density, and the QuTiP-derived number 0.7804005 (atol 1e-6) of a leakage run with the collapse operator |x><g|."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.waveforms import BlackmanWaveform
+    from pulser_b200.results import CoherentResults
+
+    reg = Register({"A": np.array([0.0, 0.0]), "B": np.array([0.0, 10.0])})
+    pi_pulse = Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0)
+    seq = Sequence(reg, DigitalAnalogDevice)
+    seq.declare_channel("ryd", "rydberg_global")
+    seq.add(pi_pulse, "ryd")
+    seq.measure("ground-rydberg")
+    results = emu.B200Emulator.from_sequence(seq, evaluation_times="Minimal").run()
+    with pytest.raises(TypeError, match="must be a list"):
+        results.expect("bad_observable")
+    with pytest.raises(TypeError, match="Incompatible type"):
+        results.expect(["bad_observable"])
+    with pytest.raises(ValueError, match="Incompatible shape"):
+        results.expect([np.array(3)])
+    seq_single = Sequence(Register.from_coordinates([(0, 0)], prefix="q"), DigitalAnalogDevice)
+    seq_single.declare_channel("ryd", "rydberg_global")
+    seq_single.add(pi_pulse, "ryd")
+    proj = lambda d, k: np.diag((np.arange(d) == k).astype(complex))  # noqa: E731
+    op = [proj(2, 0)]
+    results_single = emu.B200Emulator.from_sequence(seq_single, evaluation_times=0.05).run()
+    exp = results_single.expect(op)[0]
+    assert np.isclose(exp[-1], 1)
+    np.testing.assert_almost_equal(np.diag(results_single._calc_pseudo_density_diag(-1)), np.array([[1, 0], [0, 0]]))
+    noise_model = NoiseModel(p_false_pos=0.01, p_false_neg=0.05)
+    sim_single = emu.B200Emulator.from_sequence(seq_single, noise_model=noise_model)
+    sim_single.set_evaluation_times("Minimal")
+    results_single = sim_single.run()
+    exp = results_single.expect(op)[0]
+    assert len(exp) == 2
+    assert isinstance(results_single, CoherentResults)
+    assert results_single._meas_errors == {"epsilon": noise_model.p_false_pos,
+                                           "epsilon_prime": noise_model.p_false_neg}
+    assert np.isclose(exp[0], noise_model.p_false_pos)
+    assert np.isclose(exp[-1], 1 - noise_model.p_false_neg)
+    np.testing.assert_almost_equal(np.diag(results_single._calc_pseudo_density_diag(-1)),
+                                   np.array([[1 - noise_model.p_false_neg, 0], [0, noise_model.p_false_neg]]))
+    # with leakage: collapse operator |x><g| (basis(3, 2) @ basis(3, 1).dag()) at rate 0.5
+    eff_op = np.zeros((3, 3), dtype=complex)
+    eff_op[2, 1] = 1.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim_single = emu.B200Emulator.from_sequence(
+            seq_single, noise_model=NoiseModel(eff_noise_rates=[0.5], eff_noise_opers=[eff_op], with_leakage=True),
+            sampling_rate=0.1)
+    sim_single.set_evaluation_times(0.5)
+    res = sim_single.run()
+    assert isinstance(res, CoherentResults)
+    assert np.isclose(res.expect([proj(3, 0)])[0][-1], 0.7804005, atol=1e-6)  # value hard-coded in the reference
+    seq3dim = Sequence(reg, DigitalAnalogDevice)
+    seq3dim.declare_channel("ryd", "rydberg_global")
+    seq3dim.declare_channel("ram", "raman_local", initial_target="A")
+    seq3dim.add(pi_pulse, "ram")
+    seq3dim.add(pi_pulse, "ryd")
+    exp3dim = emu.B200Emulator.from_sequence(seq3dim, evaluation_times="Minimal").run().expect(
+        [np.kron(proj(3, 0), np.eye(3))])
+    assert abs(exp3dim[0][-1]) < 1e-9  # reference: 1.9e-14

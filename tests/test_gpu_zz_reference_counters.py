@@ -78,3 +78,17 @@ def test_master_equation_reference_counters(lib, name):
     got = sample_like_the_reference(spec, rho, extra)
     moved = sum(abs(got.get(k, 0) - expected.get(k, 0)) for k in set(got) | set(expected)) // 2
     assert moved <= 2, (got, expected)
+
+
+def test_expect_leakage_reference_value(lib):
+    """reference tests/pulser_simulation/test_simresults.py:339-361: <|r><r|>(T) = 0.7804005 (atol 1e-6, a QuTiP
+    mesolve output) for a single atom with the collapse operator |x><g|, on the CUDA master-equation path."""
+    from pulser_b200.lindblad import LindbladPlan
+
+    spec, extra = load("ref_expect_leakage")
+    with LindbladPlan(spec) as lp:
+        lp.set_state(extra["psi0"])
+        lp.propagate(0.0, spec.sampling_times[-1], tol=1e-9)
+        rho = lp.get_rho()[0]
+    assert np.isclose(rho[0, 0].real, float(extra["ref_value"]), atol=1e-6)  # the reference's own tolerance
+    assert np.max(np.abs(rho - extra["orc_rho"])) < 1e-6

@@ -428,3 +428,23 @@ def test_oracle_mesolve_reproduces_reference_counters(name):
     else:
         rho = extra["orc_rho"]
     assert _sample_like_the_reference(spec, rho, extra) == expected
+
+
+def test_golden_expect_leakage_pins_the_interpolation_order():
+    """reference tests/pulser_simulation/test_simresults.py:339-361 (test_expect, leakage case): QuTiP's mesolve gave
+    <|r><r|>(T) = 0.7804005 on a 10 ns sampling grid.  The oracle reproduces all seven digits with the cubic-spline
+    coefficients (QuTiP 5's default ``order=3``, until now an assumption taken from its documentation); with linear
+    interpolation the seventh digit is off by nine -- the reference number discriminates between the two."""
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
+
+    spec, extra = load("ref_expect_leakage")
+    tf = spec.sampling_times[-1]
+    H = OracleHamiltonian.from_spec(spec)
+    cubic = evolve.mesolve(H, extra["psi0"], [0.0, tf], order=3, rtol=1e-10, atol=1e-12)[-1][0, 0].real
+    linear = evolve.mesolve(H, extra["psi0"], [0.0, tf], order=1, rtol=1e-10, atol=1e-12)[-1][0, 0].real
+    ref = float(extra["ref_value"])
+    assert ref == 0.7804005
+    assert abs(cubic - ref) < 5e-8          # every printed digit
+    assert abs(linear - ref) > 5e-7         # 0.7804014 would have been printed
+    assert abs(cubic - extra["orc_rho"][0, 0].real) < 1e-9
