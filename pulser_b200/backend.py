@@ -546,7 +546,33 @@ class B200Config(EmulationConfig[B200State]):
             idx = np.linspace(0, total_duration_ns - 1, int(self.sampling_rate * total_duration_ns), dtype=int)
             rel = idx / total_duration_ns
         rel = np.union1d(np.asarray(rel, dtype=float), np.array(sorted(extra), dtype=float))
-        return np.asarray(rel) * total_duration_ns * 1e-3
+        # two requests that differ by a rounding error (0.493 vs 0.49299999999999994) are ONE evaluation: the
+        # observables match their times up to pulser's TIME_TOLERANCE, so evaluating both would store twice
+        from pulser.backend.observable import TIME_TOLERANCE
+
+        keep = np.concatenate(([True], np.diff(rel) >= TIME_TOLERANCE)) if len(rel) else np.zeros(0, dtype=bool)
+        return np.asarray(rel)[keep] * total_duration_ns * 1e-3
+
+
+def density_matrix_aggregator(values: list) -> "B200State":
+    """Average the states of the noise trajectories into a mixed state (each with probability 1/n): the custom
+    aggregator the reference attaches to its ``StateResult`` tag (``pulser_simulation/aggregators.py:20-39``)."""
+    acc = None
+    for value in values:
+        arr = np.asarray(value._state)
+        rho = np.outer(arr, arr.conj()) if value.is_ket else arr
+        acc = rho.astype(complex) if acc is None else acc + rho
+    return B200State(acc / len(values), eigenstates=values[0].eigenstates)
+
+
+def _state_aggregators(results: list) -> dict:
+    """``qutip_backend.py:37-42, 322-325``: the tag of the StateResult observable, if any, gets the aggregator."""
+    if not results:
+        return {}
+    for tag in results[0].get_result_tags():
+        if tag.startswith(StateResult()._base_tag):
+            return {tag: density_matrix_aggregator}
+    return {}
 
 
 class B200Backend(EmulatorBackend):
@@ -700,14 +726,15 @@ class B200Backend(EmulatorBackend):
             sim._check_supported()
             if not sim._has_collapse_ops() or sim._use_mcwf():
                 # pure states: observables reduce on the device, nothing is stored per evaluation time
-                return Results.aggregate(self._stream_noisy(hplan, atom_order))
+                streamed = self._stream_noisy(hplan, atom_order)
+                return Results.aggregate(streamed, **_state_aggregators(streamed))
             for cleanres, reps in sim._noisy_runs(print_progress=self._config.print_progress, batch=0,
                                                   opts={"max_step": 0, "cheb_tol": 0.0, "refine_window": -1, "tol": 0.0}):
                 for _ in range(reps):
                     res = Results(atom_order=atom_order, total_duration=sim.total_duration_ns)
                     self._replay(hplan, cleanres, res)
                     results.append(res)
-            return Results.aggregate(results)
+            return Results.aggregate(results, **_state_aggregators(results))
 
 
 class B200LegacyBackend(pulser.backend.abc.Backend):

@@ -256,3 +256,45 @@ def test_noisy_runs_stream_on_the_device_like_the_replay(backend, monkeypatch):
             a = np.asarray(streamed.get_result(name, t), dtype=float)
             b = np.asarray(replayed.get_result(name, t), dtype=float)
             np.testing.assert_allclose(a, b, atol=1e-9, err_msg=f"{name} at {t}")
+
+
+def test_rounding_error_eval_time_duplication_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:469-493: an evaluation time that differs from a grid
+    point by a rounding error must not be duplicated in the results."""
+    import pulser
+    from pulser.backend.default_observables import BitStrings
+
+    seq = pulser.Sequence(pulser.Register.square(1, prefix="q"), pulser.AnalogDevice)
+    seq.declare_channel("rydberg_global", "rydberg_global")
+    seq.add(pulser.Pulse.ConstantPulse(200, 1, 0, 0), "rydberg_global")
+    evaluation_times = np.linspace(0.0, 1.0, 201)
+    mod = float(evaluation_times[98]) - 1e-16 * 0.5
+    config = backend.B200Config(observables=[
+        BitStrings(evaluation_times=evaluation_times, num_shots=5),
+        BitStrings(evaluation_times=[0.49 - 6e-17], tag_suffix="mod", num_shots=5),
+    ])
+    res = backend.B200Backend(seq, config=config).run()
+    assert len(res.get_result_times("bitstrings")) == 201
+    assert len(res.get_result_times("bitstrings_mod")) == 1
+    del mod
+
+
+def test_run_twice_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:565-587 (test_run_twice): a second run() redraws the
+    noise trajectories, so the aggregated state differs."""
+    import pulser
+    from pulser.backend.default_observables import StateResult
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        noise_model = pulser.NoiseModel(trap_depth=1.0, trap_waist=1.0, temperature=50.0, disable_doppler=True,
+                                        detuning_sigma=5.0)
+        cfg = backend.B200Config(default_evaluation_times=[1.0], observables=[StateResult(evaluation_times=[1.0])],
+                                 noise_model=noise_model, n_trajectories=4)
+        be = backend.B200Backend(_seq(n=2, duration=200), config=cfg)
+        np.random.seed(5)
+        r1 = be.run()
+        r2 = be.run()
+    a1, a2 = r1.final_state.to_array(), r2.final_state.to_array()
+    ov = abs(np.vdot(a1.ravel(), a2.ravel())) / (np.linalg.norm(a1) * np.linalg.norm(a2))
+    assert ov != pytest.approx(1.0)
