@@ -298,3 +298,114 @@ def test_run_twice_port(backend):
     a1, a2 = r1.final_state.to_array(), r2.final_state.to_array()
     ov = abs(np.vdot(a1.ravel(), a2.ravel())) / (np.linalg.norm(a1) * np.linalg.norm(a2))
     assert ov != pytest.approx(1.0)
+
+
+def _ref_sequence(device=None, scale=1):
+    """The ``sequence()`` helper of the reference's V2 backend tests (test_qutip_backend_v2.py:57-88): two atoms at
+    the blockade radius, rise / detuning sweep / fall.  ``scale`` shortens the three pulses (oracle-backed CPU runs)."""
+    import math
+
+    import pulser
+
+    omega_max = 4 * 2 * math.pi
+    u = omega_max / 2
+    delta_0, delta_f = -6 * u, 2 * u
+    t_rise, t_fall = 500 // scale, 1000 // scale
+    t_sweep = int((delta_f - delta_0) / (2 * np.pi * 10) * 1000) // scale
+    r = pulser.devices.MockDevice.rydberg_blockade_radius(u)
+    reg = pulser.Register.rectangle(1, 2, r, prefix="q")
+    seq = pulser.Sequence(reg, device if device is not None else pulser.devices.MockDevice)
+    seq.declare_channel("ising_global", "rydberg_global")
+    seq.add(pulser.Pulse.ConstantDetuning(pulser.waveforms.RampWaveform(t_rise, 0.0, omega_max), delta_0, 0.0),
+            "ising_global")
+    seq.add(pulser.Pulse.ConstantAmplitude(omega_max, pulser.waveforms.RampWaveform(t_sweep, delta_0, delta_f), 0.0),
+            "ising_global")
+    seq.add(pulser.Pulse.ConstantDetuning(pulser.waveforms.RampWaveform(t_fall, omega_max, 0.0), delta_f, 0.0),
+            "ising_global")
+    return seq
+
+
+def test_callback_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:91-108 (test_callback): a callback forces the full
+    evaluation grid -- one call per sample, noiseless and with a stochastic noise trajectory."""
+    import pulser
+    from pulser.backend.observable import Callback
+
+    class CountCalls(Callback):
+        def __init__(self):
+            super().__init__()
+            self.counter = 0
+
+        def __call__(self, **kwargs):
+            self.counter += 1
+
+    seq = _ref_sequence(scale=10)
+    be = backend.B200Backend(seq, config=backend.B200Config(callbacks=[CountCalls()]))
+    be.run()
+    assert be._config.callbacks[0].counter == seq.get_duration() + 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cfg = backend.B200Config(callbacks=[CountCalls()], noise_model=pulser.NoiseModel(amp_sigma=0.1), n_trajectories=1)
+    be = backend.B200Backend(seq, config=cfg)
+    be.run()
+    assert be._config.callbacks[0].counter == seq.get_duration() + 1
+
+
+def test_energy_port(backend, capfd):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:111-154 (test_qutip_backend_v2_energy)."""
+    from pulser.backend.default_observables import Energy, StateResult
+
+    seq = _ref_sequence(scale=10)
+    with pytest.raises(TypeError, match="'config' must be an instance of 'EmulationConfig'"):
+        backend.B200Backend(seq, config="tralala")
+    T = seq.get_duration()
+    config = backend.B200Config(default_evaluation_times="Full",
+                                observables=[StateResult(), Energy(evaluation_times=[n / T for n in range(0, T + 1, 2)])],
+                                print_progress=True)
+    be = backend.B200Backend(seq, config=config)
+    results = be.run()
+    assert results.get_result_times("state") != results.get_result_times("energy")
+    out, _ = capfd.readouterr()
+    assert out == "Emulating Trajectory 1/1\n"
+    assert results.get_result("energy", 0.0) == results.energy[0] == pytest.approx(0.0)
+    sim = be._sim_obj
+    # <psi|H(t)|psi> from the dense Hamiltonian of the facade and the stored state (qutip.expect in the reference)
+    t_mid = results.get_result_times("energy")[len(results.energy) // 2]
+    psi_mid = results.get_result("state", t_mid).to_array()
+    h_mid = sim.get_hamiltonian(t_mid * T)
+    assert results.get_result("energy", t_mid) == pytest.approx(np.vdot(psi_mid, h_mid @ psi_mid).real, rel=1e-5)
+    psi_end = results.state[-1].to_array()
+    h_end = sim.get_hamiltonian(T)
+    assert results.get_result("energy", 1.0) == results.energy[-1]
+    assert results.energy[-1] == pytest.approx(np.vdot(psi_end, h_end @ psi_end).real, rel=1e-6, abs=1e-9)
+
+
+@pytest.mark.parametrize("print_progress", [True, False])
+def test_default_noise_model_port(backend, capfd, print_progress):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:157-196: prefer_device_noise_model takes the device's
+    noise model for the emulation while the config keeps its own; progress lines of the two trajectories."""
+    import dataclasses
+
+    import pulser
+    from pulser.backend.default_observables import StateResult
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        noisy_device = dataclasses.replace(pulser.devices.MockDevice,
+                                           noise_model=pulser.NoiseModel(dephasing_rate=0.01, temperature=50))
+        config = backend.B200Config(
+            observables=[StateResult(evaluation_times=[1.0])],
+            noise_model=pulser.NoiseModel(p_false_neg=0.1),
+            prefer_device_noise_model=True,
+            initial_state=backend.B200State(np.array([1.0, 0, 0, 0], dtype=complex), eigenstates=("r", "g")),
+            n_trajectories=2,
+            print_progress=print_progress,
+        )
+        be = backend.B200Backend(_ref_sequence(noisy_device, scale=10), config=config)
+        assert be._sim_obj._hamiltonian_data.noise_model.p_false_neg == 0.0
+        assert be._sim_obj._hamiltonian_data.noise_model.temperature == 50
+        assert be._sim_obj._hamiltonian_data.noise_model.dephasing_rate == 0.01
+        assert be._config.noise_model.p_false_neg == 0.1
+        be.run()
+    out, _ = capfd.readouterr()
+    assert out == ("Emulating Trajectory 1/2\nEmulating Trajectory 2/2\n" if print_progress else "")
