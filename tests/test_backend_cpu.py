@@ -409,3 +409,56 @@ def test_default_noise_model_port(backend, capfd, print_progress):
         be.run()
     out, _ = capfd.readouterr()
     assert out == ("Emulating Trajectory 1/2\nEmulating Trajectory 2/2\n" if print_progress else "")
+
+
+def test_eval_times_rounding_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:257-284 (test_qutip_backend_v2_eval_times_rounding):
+    the legacy evaluation times must never exceed the duration through a rounding error; a plain EmulationConfig
+    is accepted and every requested time is stored exactly once."""
+    import pulser
+
+    n_points = 25
+    for duration in range(400, 600, 28):
+        seq = pulser.Sequence(pulser.Register({"q0": (-5, 0), "q1": (5, 0)}), pulser.AnalogDevice)
+        seq.declare_channel("rydberg_global", "rydberg_global")
+        seq.add(pulser.Pulse(pulser.ConstantWaveform(duration, np.pi), pulser.ConstantWaveform(duration, 0.0), 0),
+                "rydberg_global")
+        evaluation_times = np.linspace(0, 1, n_points).tolist()
+        config = pulser.backend.EmulationConfig(observables=[pulser.backend.StateResult(evaluation_times=evaluation_times)])
+        result = backend.B200Backend(seq, config=config).run().state
+        assert len(result) == n_points
+
+
+def test_stochastic_noise_v2_equals_legacy_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:199-254 (test_qutip_backend_v2_stochastic_noise):
+    the V2 occupation of 30 noisy trajectories agrees with the legacy facade's within 0.03."""
+    import pulser
+    from pulser.backend.default_observables import Occupation, StateResult
+    from pulser_b200 import emulator
+
+    np.random.seed(123)
+
+    def get_noise_model(samples_per_run):
+        return pulser.NoiseModel(temperature=50.0, p_false_neg=0.01, amp_sigma=1e-3, samples_per_run=samples_per_run)
+
+    seq = _ref_sequence(scale=25)
+    T = seq.get_duration()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        config = backend.B200Config(default_evaluation_times=(1.0,),
+                                    observables=[StateResult(evaluation_times=[1.0]),
+                                                 Occupation(evaluation_times=[n / T for n in range(0, T + 1, 10)])],
+                                    noise_model=get_noise_model(1), n_trajectories=30)
+        be = backend.B200Backend(seq, config=config)
+        assert be._sim_obj.n_trajectories == config.n_trajectories
+        results = be.run()
+        # (the reference keeps the legacy run on the full grid; its states are only read at the occupation times)
+        old = emulator.B200Emulator.from_sequence(seq, noise_model=get_noise_model(100), n_trajectories=30,
+                                                  evaluation_times=[int(n / T * T) * 1e-3 for n in range(0, T + 1, 10)])
+        results_old_api = old.run()
+    times = results.get_result_times("occupation")
+    occupation = np.array([x[0] for x in results.occupation])
+    indices = np.searchsorted(results_old_api._sim_times, np.array([int(t * T) * 1e-3 for t in times]))
+    n0 = np.kron(np.diag([1.0, 0.0]), np.eye(2))
+    occupation_old_api = results_old_api.expect([n0])[0][indices]
+    assert np.max(np.abs(occupation - occupation_old_api)) < 0.03
