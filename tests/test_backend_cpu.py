@@ -462,3 +462,103 @@ def test_stochastic_noise_v2_equals_legacy_port(backend):
     n0 = np.kron(np.diag([1.0, 0.0]), np.eye(2))
     occupation_old_api = results_old_api.expect([n0])[0][indices]
     assert np.max(np.abs(occupation - occupation_old_api)) < 0.03
+
+
+@pytest.mark.parametrize("amp_sigma", [0.0, 1.0])
+def test_leakage_port(backend, amp_sigma):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:287-360 (test_leakage): two far-apart atoms leaking
+    from |r> and |g> into |x> at the same rate -- the leaked populations are analytic whatever the drive does."""
+    import math
+
+    import pulser
+    from pulser.backend.default_observables import StateResult
+
+    reg = pulser.Register.rectangle(1, 2, spacing=1000.0, prefix="q")
+    seq = pulser.Sequence(reg, pulser.MockDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    duration = 500
+    seq.add(pulser.Pulse.ConstantPulse(duration, np.pi, 0.0, 0.0), "ch0")
+    basisx = np.array([0.0, 0.0, 1.0]).reshape(3, 1)
+    basisg = np.array([0.0, 1.0, 0.0]).reshape(3, 1)
+    basisr = np.array([1.0, 0.0, 0.0]).reshape(3, 1)
+    rate = 0.5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        noise_model = pulser.NoiseModel(eff_noise_rates=[rate, rate],
+                                        eff_noise_opers=[basisx @ basisr.T, basisx @ basisg.T],
+                                        with_leakage=True, amp_sigma=amp_sigma)
+        cfg = backend.B200Config(default_evaluation_times=[1.0], observables=[StateResult(evaluation_times=[1.0])],
+                                 noise_model=noise_model, solver=backend.Solver.MESOLVER, n_trajectories=1)
+        result = backend.B200Backend(seq, config=cfg).run()
+    eig = ("r", "g", "x")
+    px = basisx @ basisx.T
+    p_no = np.diag([1.0, 1.0, 0.0])
+    both_leaked = backend.B200Operator(np.kron(px, px), eig)
+    one_leaked = backend.B200Operator(np.kron(px, p_no), eig) + backend.B200Operator(np.kron(p_no, px), eig)
+    no_leaked = backend.B200Operator(np.kron(p_no, p_no), eig)
+    decay = math.exp(-rate * duration / 1000)
+    assert one_leaked.expect(result.final_state) == pytest.approx(2 * (1 - decay) * decay, abs=1e-6)
+    assert no_leaked.expect(result.final_state) == pytest.approx(decay**2, abs=1e-6)
+    assert both_leaked.expect(result.final_state) == pytest.approx((1 - decay) ** 2, abs=1e-6)
+
+
+def test_register_detuning_detection_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:363-393: register + detuning noise are stochastic,
+    the aggregated final state of ten trajectories is a density matrix."""
+    import pulser
+    from pulser.backend.default_observables import StateResult
+
+    reg = pulser.Register.rectangle(1, 2, spacing=1000.0, prefix="q")
+    seq = pulser.Sequence(reg, pulser.MockDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.add(pulser.Pulse.ConstantPulse(200, np.pi, 0.0, 0.0), "ch0")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        noise_model = pulser.NoiseModel(trap_depth=1.0, trap_waist=1.0, temperature=50.0, disable_doppler=True,
+                                        detuning_sigma=5.0)
+        assert set(noise_model.noise_types) == {"register", "detuning"}
+        cfg = backend.B200Config(default_evaluation_times=[1.0], observables=[StateResult(evaluation_times=[1.0])],
+                                 noise_model=noise_model, n_trajectories=10)
+        result = backend.B200Backend(seq, config=cfg).run()
+    assert result.final_state._state.shape == (4, 4)  # density matrix
+
+
+def test_aggregation_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:400-466 (test_aggregation): five SPAM trajectories
+    with mocked bad atoms (0, 0, 1, 1, 2) on three non-interacting atoms after a pi pulse -- exact aggregated state,
+    occupation and bitstrings; EnergyVariance is skipped with a warning; tags keep their observables' UUIDs."""
+    from unittest.mock import patch
+
+    import pulser
+    from pulser.backend.default_observables import BitStrings, EnergyVariance, Occupation, StateResult
+
+    reg = pulser.Register({"q0": [-1e5, 0], "q1": [1e5, 0], "q2": [0, 1e5]})
+    seq = pulser.Sequence(reg, pulser.MockDevice)
+    seq.declare_channel("ryd", "rydberg_global")
+    seq.add(pulser.Pulse.ConstantDetuning(pulser.BlackmanWaveform(100, np.pi), 0.0, 0.0), "ryd")
+    occup = Occupation(evaluation_times=[1.0])
+    state = StateResult(evaluation_times=[1.0])
+    bitstrings = BitStrings(evaluation_times=[1.0])
+    variance = EnergyVariance(evaluation_times=[1.0])
+    cfg = backend.B200Config(observables=(occup, state, bitstrings, variance), n_trajectories=5,
+                             noise_model=pulser.NoiseModel(state_prep_error=1 / 3))
+    with pytest.warns(UserWarning, match="Skipping aggregation of `energy_variance`."):
+        with patch("pulser._hamiltonian_data.hamiltonian_data.np.random.uniform") as bad_atoms_mock:
+            bad_atoms_mock.side_effect = [
+                np.array([0.1, 0.5, 0.6]), np.array([0.1, 0.5, 0.6]), np.array([0.5, 0.1, 0.6]),
+                np.array([0.5, 0.1, 0.6]), np.array([0.5, 0.6, 0.1]), np.array([0.1, 0.2, 0.3]),
+            ] + [np.array([0.9, 0.9, 0.9])] * 6  # spare draws (noiseless helper data built more than once)
+            results = backend.B200Backend(seq, config=cfg).run()
+    expected_state = np.zeros((8, 8))
+    expected_state[1, 1], expected_state[2, 2], expected_state[4, 4] = 0.2, 0.4, 0.4
+    assert np.allclose(results.final_state.to_array(), expected_state, atol=1e-4)
+    assert np.allclose(results.occupation[-1], np.array([0.6, 0.6, 0.8]), atol=1e-4)
+    assert results.final_bitstrings == {"011": 2000, "101": 2000, "110": 1000}
+    assert "energy_variance" not in results.get_result_tags()
+    for obs_ in (occup, state, bitstrings):
+        assert results.get_result_times(obs_) == [1.0]
+
+
+def test_config_type_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:396-397."""
+    assert backend.B200Backend.config_type is backend.B200Config
