@@ -602,6 +602,28 @@ class B200Backend(EmulatorBackend):
         if self._config.initial_state is not None:
             self._sim_obj.set_initial_state(self._config.initial_state.to_array())
 
+    @staticmethod
+    def run_from_sequence_samples(sequence_samples: Any, register: Any, device: Any, *,
+                                  config: EmulationConfig | None = None) -> Results:
+        """Executes an already sampled sequence (``QutipBackendV2.run_from_sequence_samples``,
+        ``qutip_backend.py:193-232``): same emulator construction as ``__init__`` minus the ``Sequence`` checks."""
+        cfg = B200Backend.validate_config(config or B200Backend.default_config)
+        noise_model = device.noise_model if cfg.prefer_device_noise_model else None
+        sim = B200Emulator(
+            sequence_samples, register, device,
+            sampling_rate=cfg.sampling_rate,
+            config=None,
+            noise_model=noise_model or cfg.noise_model,
+            solver=cfg.solver,
+            n_trajectories=cfg.n_trajectories,
+        )
+        sim.set_evaluation_times(cfg._get_legacy_evaluation_times(sim.total_duration_ns))
+        if cfg.initial_state is not None:
+            sim.set_initial_state(cfg.initial_state.to_array())
+        runner = object.__new__(B200Backend)  # run() only needs the emulator and the validated config
+        runner._sim_obj, runner._config = sim, cfg
+        return runner.run()
+
     def _replay(self, plan: Any, coherent: Any, res: Results) -> None:
         """Feed the stored states to callbacks / observables (qutip_backend.py:254-280)."""
         sim, config = self._sim_obj, self._config

@@ -562,3 +562,55 @@ def test_aggregation_port(backend):
 def test_config_type_port(backend):
     """reference tests/pulser_simulation/test_qutip_backend_v2.py:396-397."""
     assert backend.B200Backend.config_type is backend.B200Config
+
+
+@pytest.mark.parametrize("modulation", [True, False])
+def test_run_from_sequence_samples_port(backend, modulation):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:615-650 (test_run_from_sequence_samples): the
+    Sequence entry point and the sampled-sequence entry point give the same state, to the last bit."""
+    import pulser
+    from pulser.backend.default_observables import StateResult
+    from pulser.sampler import sample
+
+    seq = pulser.Sequence(pulser.Register.square(1, prefix="q"), pulser.AnalogDevice)
+    seq.declare_channel("rydberg_global", "rydberg_global")
+    seq.add(pulser.Pulse.ConstantPulse(300, 1, 0, 0), "rydberg_global")
+    config = None
+    if modulation:
+        initial_state = backend.B200State.from_state_amplitudes(eigenstates=("r", "g"), amplitudes={"g": 1.0})
+        config = backend.B200Config(with_modulation=modulation, observables=[StateResult()],
+                                    initial_state=initial_state)
+    be = backend.B200Backend(seq, config=config)
+    results1 = be.run()
+    results2 = be.run_from_sequence_samples(
+        sample(seq, modulation=modulation, extended_duration=seq.get_duration(include_fall_time=modulation)),
+        seq.register, seq.device, config=config)
+    s1 = results1.final_state.to_array()
+    s2 = results2.final_state.to_array()
+    assert np.allclose(s1, s2, atol=0, rtol=1e-16)  # really the same
+
+
+def test_dmm_temperature_without_spot_waist_port(backend):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:583-612: register noise with a DMM needs
+    `detuning_map_spot_waist` (check inherited from ``EmulatorBackend.__init__``)."""
+    import dataclasses
+
+    import pulser
+    from pulser.backend.default_observables import StateResult
+    from pulser.channels.dmm import DMM
+    from pulser.devices import AnalogDevice
+
+    reg = pulser.Register.from_coordinates([(0.0, 0.0), (6.0, 0.0)], center=False, prefix="q")
+    det_map = reg.define_detuning_map({"q0": 1.0, "q1": 0.5})
+    mock_device = dataclasses.replace(AnalogDevice.to_virtual(), dmm_objects=(DMM(),), reusable_channels=True)
+    seq = pulser.Sequence(reg, mock_device)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.add(pulser.Pulse.ConstantPulse(100, 1, -1, 0), "ch0")
+    seq.config_detuning_map(det_map, "dmm_0")
+    seq.add_dmm_detuning(pulser.ConstantWaveform(100, -10), "dmm_0")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        config = backend.B200Config(noise_model=pulser.NoiseModel(trap_waist=1, trap_depth=1, temperature=0.5),
+                                    observables=[StateResult(evaluation_times=[1.0])])
+    with pytest.raises(ValueError, match="Combining register noise with a DMM requires"):
+        backend.B200Backend(seq, config=config)
