@@ -614,3 +614,37 @@ def test_dmm_temperature_without_spot_waist_port(backend):
                                     observables=[StateResult(evaluation_times=[1.0])])
     with pytest.raises(ValueError, match="Combining register noise with a DMM requires"):
         backend.B200Backend(seq, config=config)
+
+
+@pytest.mark.parametrize("amp_sigma", [0.0, 0.5])
+def test_output_state_normalization_port(backend, amp_sigma):
+    """reference tests/pulser_simulation/test_qutip_backend_v2.py:494-555 (test_output_state_normalization): states
+    handed to the observables are normalised -- no fidelity above one."""
+    import pulser
+    from pulser.backend.default_observables import Fidelity
+
+    factor = 1.2357175818662465 if not amp_sigma else 1.0
+    r_interatomic = 5
+    register = pulser.Register.hexagon(1, r_interatomic, prefix="q")
+    seq = pulser.Sequence(register, pulser.MockDevice)
+    seq.declare_channel("rydberg_global", "rydberg_global")
+    u = pulser.AnalogDevice.interaction_coeff / r_interatomic**6
+    total_duration = 400  # 4000 in the reference (oracle-backed run here)
+    interp_pts = np.linspace(0, 1, 4)
+    seq.add(pulser.Pulse(
+        pulser.InterpolatedWaveform(total_duration, u * np.array([1e-9, 0.22, 0.2181, 1e-9]) * factor, times=interp_pts),
+        pulser.InterpolatedWaveform(total_duration, u * np.array([-1, 0.0556, 0.332, 1]), times=interp_pts), 0),
+        "rydberg_global")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        noise_model = pulser.NoiseModel(amp_sigma=amp_sigma)
+        np.random.seed(1234)
+        config = backend.B200Backend.default_config.with_changes(noise_model=noise_model)
+        results = backend.B200Backend(seq, config=config).run()
+        final_state = results.final_state
+        assert np.linalg.norm(final_state.to_array()) < 1 + 1e-8
+        np.random.seed(1234)
+        config = backend.B200Backend.default_config.with_changes(noise_model=noise_model,
+                                                                 observables=[Fidelity(final_state)])
+        results = backend.B200Backend(seq, config=config).run()
+    assert results.fidelity[-1] < 1 + 1e-8
