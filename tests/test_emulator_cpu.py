@@ -816,3 +816,111 @@ def test_expect_port(emu):
     exp3dim = emu.B200Emulator.from_sequence(seq3dim, evaluation_times="Minimal").run().expect(
         [np.kron(proj(3, 0), np.eye(3))])
     assert abs(exp3dim[0][-1]) < 1e-9  # reference: 1.9e-14
+
+
+def test_concurrent_pulses_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:1402-1427 (test_concurrent_pulses): a local and a global
+    Rydberg pulse at the same time add up; doppler noise changes detunings, never the drive element H[0, 1]."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+
+    seq = Sequence(Register({"q0": (0, 0)}), DigitalAnalogDevice)
+    seq.declare_channel("ch_local", "rydberg_local", initial_target="q0")
+    seq.declare_channel("ch_global", "rydberg_global")
+    pulse = Pulse.ConstantPulse(20, 10, 0, 0)
+    seq.add(pulse, "ch_local")
+    seq.add(pulse, "ch_global", protocol="no-delay")
+    sim_no_noise = emu.B200Emulator.from_sequence(seq)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim_with_noise = emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(samples_per_run=5, temperature=50.0),
+                                                        n_trajectories=15)
+    for t in sim_no_noise.evaluation_times:
+        ham_no_noise = sim_no_noise.get_hamiltonian(t * 1000)
+        ham_with_noise = sim_with_noise.get_hamiltonian(t * 1000)
+        assert ham_no_noise[0, 1] == ham_with_noise[0, 1]
+    assert abs(sim_no_noise.get_hamiltonian(10)[0, 1] - 10.0) < 1e-12  # 0.5 * (10 + 10): both channels drive q0
+
+
+def test_mask_nopulses_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:1730-1745 (test_mask_nopulses)."""
+    from pulser import Register, Sequence
+    from pulser.devices import MockDevice
+    from pulser.sampler import sampler
+
+    reg = Register({"q0": (0, 0), "q1": (10, 10), "q2": (-10, -10)})
+    for channel_type in ["mw_global", "rydberg_global"]:
+        seq_empty = Sequence(reg, MockDevice)
+        if channel_type == "mw_global":
+            seq_empty.set_magnetic_field(0, 1.0, 0.0)
+        seq_empty.declare_channel("ch", channel_type)
+        seq_empty.delay(duration=100, channel="ch")
+        seq_empty.config_slm_mask(["q2"])
+        sim_empty = emu.B200Emulator.from_sequence(seq_empty)
+        assert seq_empty._slm_mask_time == []
+        assert sampler.sample(seq_empty)._slm_mask.end == 0
+        assert sim_empty.samples_obj._slm_mask.end == 0
+        assert sim_empty._current_spec.slm_coefficient() is None  # no time-dependent interaction without a mask end
+
+
+@pytest.mark.parametrize("noise", (
+    {"detuning_sigma": 1.0}, {"amp_sigma": 1.0}, {"temperature": 10},
+    {"temperature": 10, "disable_doppler": True, "trap_depth": 1000, "trap_waist": 0.1},
+    {"detuning_hf_psd": [1.0, 2.0], "detuning_hf_omegas": [3.0, 4.0]},
+))
+def test_noisy_runs_port(emu, noise):
+    """reference tests/pulser_simulation/test_simulation.py:2420-2466 (test_noisy_runs): every kind of stochastic noise
+    gives one solve per trajectory and a NoisyResults."""
+    from fake_device import FakeDevicePlan
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+    from pulser_b200.results import NoisyResults
+
+    np.random.seed(1337)
+    duration = 10
+    seq = Sequence(Register({"q0": (0, 0), "q1": (10, 10)}), MockDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.declare_channel("ch1", "raman_local", initial_target="q0")
+    seq.declare_channel("ch2", "raman_local", initial_target="q1")
+    pulse1 = Pulse.ConstantPulse(duration, 0, 0, 0)
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch1", protocol="no-delay")
+    seq.add(pulse1, "ch2", protocol="no-delay")
+    nruns = 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(**noise), n_trajectories=nruns)
+        result = sim.run()
+    assert isinstance(result, NoisyResults)
+    assert len(sim._pending_trajectories()) == nruns  # one trajectory per run (they share one device batch here)
+    del FakeDevicePlan
+
+
+@pytest.mark.parametrize("noise_data, expected", [
+    (dict(noise_types="doppler"), True),
+    (dict(noise_types="amplitude", amp_sigma=1.0), True),
+    (dict(noise_types="amplitude", amp_sigma=0.0), False),
+    (dict(noise_types="detuning"), True),
+    (dict(noise_types="register"), True),
+    (dict(noise_types="SPAM", state_prep_error=0.0), False),
+    (dict(noise_types="SPAM", state_prep_error=1.0), True),
+    (dict(noise_types="other"), False),
+    (dict(noise_types={"other", "detuning"}), True),
+])
+def test_has_stochastic_noise_port(emu, noise_data, expected):
+    """reference tests/pulser_simulation/test_simulation.py:2469-2499 (test_has_stochastic_noise)."""
+    from types import SimpleNamespace
+
+    assert emu._has_stochastic_noise(SimpleNamespace(**noise_data)) is expected
+
+
+def test_invalid_solver_error_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:2577-2591 (test_qutip_invalid_solver_error)."""
+    from pulser import NoiseModel
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(ValueError, match="'fakesolver' is not a valid Solver"):
+            emu.B200Emulator.from_sequence(_seq(), noise_model=NoiseModel(detuning_sigma=0.1), solver="fakesolver",
+                                           n_trajectories=1)
