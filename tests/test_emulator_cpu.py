@@ -924,3 +924,46 @@ def test_invalid_solver_error_port(emu):
         with pytest.raises(ValueError, match="'fakesolver' is not a valid Solver"):
             emu.B200Emulator.from_sequence(_seq(), noise_model=NoiseModel(detuning_sigma=0.1), solver="fakesolver",
                                            n_trajectories=1)
+
+
+def test_get_hamiltonian_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:476-588 (test_get_hamiltonian), seeds and numbers as they
+    are: the doppler (seed 123, 20000 uK) and register-noise (seed 456) Hamiltonians at t = 144 ns hard-coded in the
+    reference come out of the facade (get_hamiltonian = H(t) applied to the basis vectors by the plan)."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.waveforms import RampWaveform
+
+    simple_reg = Register.from_coordinates([[10, 0], [0, 0]], prefix="atom")
+    detun = 1.0
+    simple_seq = Sequence(simple_reg, DigitalAnalogDevice)
+    simple_seq.declare_channel("ising", "rydberg_global")
+    simple_seq.add(Pulse.ConstantDetuning(RampWaveform(1500, 0.0, 2.0), detun, 0.0), "ising")
+    simple_sim = emu.B200Emulator.from_sequence(simple_seq, sampling_rate=0.01)
+    with pytest.raises(ValueError, match="less than or equal to"):
+        simple_sim.get_hamiltonian(1650)
+    with pytest.raises(ValueError, match="greater than or equal to"):
+        simple_sim.get_hamiltonian(-10)
+    simple_ham = simple_sim.get_hamiltonian(143)
+    assert np.isclose(simple_ham[0, 0], DigitalAnalogDevice.interaction_coeff / 10**6 - 2 * detun)
+    np.random.seed(123)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim_noise = emu.B200Emulator.from_sequence(simple_seq, noise_model=NoiseModel(samples_per_run=1, temperature=20000),
+                                                   n_trajectories=15)
+    g = 0.09606404
+    np.testing.assert_allclose(sim_noise.get_hamiltonian(144), np.array([
+        [4.47984523, g, g, 0.0], [g, 12.03082372, 0.0, g], [g, 0.0, -12.97113702, g], [0.0, g, g, 0.0]], dtype=complex),
+        rtol=1e-7, atol=1e-8)
+    expected_noiseless = emu.B200Emulator.from_sequence(simple_seq).get_hamiltonian(144)
+    np.testing.assert_allclose(sim_noise.get_hamiltonian(144, noiseless=True), expected_noiseless)
+    np.random.seed(456)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim_noise = emu.B200Emulator.from_sequence(
+            simple_seq, noise_model=NoiseModel(samples_per_run=1, temperature=50.0, trap_depth=150.0, trap_waist=1.0),
+            n_trajectories=1)
+    np.testing.assert_allclose(sim_noise.get_hamiltonian(144), np.array([
+        [4.92294305, g, g, 0.0], [g, -0.59902269, 0.0, g], [g, 0.0, -0.70099956, g], [0.0, g, g, 0.0]], dtype=complex),
+        rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(sim_noise.get_hamiltonian(144, noiseless=True), expected_noiseless)
