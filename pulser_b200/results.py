@@ -512,7 +512,8 @@ class NoisyResults(SimulationResults):
 
     def __init__(self, run_output: Sequence[SampledCounts], size: int, basis_name: str,
                  sim_times: np.ndarray, n_measures: int) -> None:
-        basis_name_ = "digital" if basis_name == "all" else basis_name
+        basis = basis_name.replace("_with_error", "")  # simresults.py:281-282: bitstrings carry no leakage level
+        basis_name_ = "digital" if basis == "all" else basis
         super().__init__(size, basis_name_, sim_times)
         self.n_measures = n_measures
         self._results_seq = tuple(run_output)

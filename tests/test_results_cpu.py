@@ -88,3 +88,37 @@ def test_sample_state_with_measurement_errors_statistics():
     assert abs(c["00"] / 20000 - 0.49) < 0.02 and abs(c["11"] / 20000 - 0.09) < 0.01
     with pytest.raises(IndexError, match="absent from simulation times"):
         ce.sample_state(0.5)
+
+
+# ---- ports of the reference's tests/pulser_simulation/test_simresults.py (no device involved) ------------------
+@pytest.mark.parametrize("basis,exp_basis", [
+    ("ground-rydberg_with_error", "ground-rydberg"), ("digital_with_error", "digital"), ("all_with_error", "digital"),
+    ("all", "digital"), ("XY_with_error", "XY"),
+])
+def test_initialization_messages_port(basis, exp_basis):
+    """reference test_simresults.py:95-135 (test_initialization), constructor messages."""
+    from pulser_b200.results import CoherentResults
+
+    with pytest.raises(ValueError, match="`basis_name` must be"):
+        CoherentResults([], 2, "bad_basis", None, [0])
+    if "all" in basis:
+        with pytest.raises(ValueError, match="`meas_basis` must be 'ground-rydberg' or 'digital'."):
+            CoherentResults([], 1, basis, None, "XY")
+    else:
+        with pytest.raises(ValueError, match=f"`meas_basis` associated to basis_name '{basis}' must be"):
+            CoherentResults([], 1, basis, [0], "wrong_measurement_basis")
+    with pytest.raises(ValueError, match="only values of 'epsilon' and 'epsilon_prime'"):
+        CoherentResults([], 1, basis, [0], exp_basis, {"eta": 0.1, "epsilon": 0.0, "epsilon_prime": 0.4})
+
+
+@pytest.mark.parametrize("basis,exp_basis", [
+    ("ground-rydberg_with_error", "ground-rydberg"), ("digital_with_error", "digital"), ("all_with_error", "digital"),
+    ("all", "digital"), ("XY_with_error", "XY"),
+])
+def test_init_noisy_port(basis, exp_basis):
+    """reference test_simresults.py:138-152 (test_init_noisy)."""
+    from pulser_b200.results import NoisyResults
+
+    with pytest.raises(ValueError, match="`basis_name` must be"):
+        NoisyResults([], 2, "bad_basis", [0], 123)
+    assert NoisyResults([], 2, basis, [0], 100)._basis_name == exp_basis
