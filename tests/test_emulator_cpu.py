@@ -967,3 +967,79 @@ def test_get_hamiltonian_port(emu):
         [4.92294305, g, g, 0.0], [g, -0.59902269, 0.0, g], [g, 0.0, -0.70099956, g], [0.0, g, g, 0.0]], dtype=complex),
         rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(sim_noise.get_hamiltonian(144, noiseless=True), expected_noiseless)
+
+
+def test_results_xy_port(emu):
+    """reference tests/pulser_simulation/test_simresults.py:486-527 (test_results_xy)."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+    from pulser.waveforms import BlackmanWaveform
+
+    reg = Register({"A": np.array([0.0, 0.0]), "B": np.array([0.0, 10.0])})
+    seq_ = Sequence(reg, MockDevice)
+    seq_.declare_channel("ch0", "mw_global")
+    seq_.add(Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0), "ch0")
+    seq_.measure("XY")
+    results_ = emu.B200Emulator.from_sequence(seq_, evaluation_times="Minimal").run()
+    assert results_._dim == 2 and results_._size == 2
+    assert results_._basis_name == "XY" and results_._meas_basis == "XY"
+    np.testing.assert_array_equal(results_.states[0].full().ravel(), np.r_[1, 0, 0, 0])  # |uu>
+    for basis in ("all", "ground-rydberg", "digital"):
+        with pytest.raises(TypeError, match="Can't reduce a system in"):
+            results_.get_final_state(reduce_to_basis=basis)
+    state = results_.get_final_state(reduce_to_basis="XY")
+    assert np.all(np.isclose(np.abs(state.full()), np.abs(results_.states[-1].full()), atol=1e-5))
+
+
+def test_false_positive_port(emu):
+    """reference tests/pulser_simulation/test_simresults.py:530-550 (test_false_positive): a pulse padded with long
+    zero stretches must still act (the final state differs from the initial one)."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import AnalogDevice
+    from pulser.waveforms import BlackmanWaveform, CompositeWaveform, ConstantWaveform
+
+    seq = Sequence(Register.square(2, 5, prefix="q"), AnalogDevice)
+    seq.declare_channel("ryd_glob", "rydberg_global")
+    seq.add(Pulse.ConstantDetuning(CompositeWaveform(ConstantWaveform(2500, 0.0), BlackmanWaveform(1000, np.pi),
+                                                     ConstantWaveform(500, 0.0)), 0, 0), channel="ryd_glob")
+    sim = emu.B200Emulator.from_sequence(seq, evaluation_times="Minimal")
+    final = sim.run().get_final_state().full()
+    assert np.max(np.abs(final - sim.initial_state.full())) > 0.1
+
+
+def test_sample_final_state_ports(emu):
+    """reference tests/pulser_simulation/test_simresults.py:398-446 (test_sim_without_measurement,
+    test_sample_final_state, test_sample_final_state_three_level)."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.waveforms import BlackmanWaveform
+
+    reg = Register({"A": np.array([0.0, 0.0]), "B": np.array([0.0, 10.0])})
+    pi_pulse = Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0)
+
+    def seq_no_meas():
+        seq = Sequence(reg, DigitalAnalogDevice)
+        seq.declare_channel("ryd", "rydberg_global")
+        seq.add(pi_pulse, "ryd")
+        return seq
+
+    seq = seq_no_meas()
+    assert not seq.is_measured()
+    results_no_meas = emu.B200Emulator.from_sequence(seq, evaluation_times="Minimal").run()
+    np.random.seed(123)
+    assert results_no_meas.sample_final_state(1) == Counter({"11": 1})
+    seq.measure("ground-rydberg")
+    np.random.seed(123)
+    results = emu.B200Emulator.from_sequence(seq, evaluation_times="Minimal").run()
+    sampling = results.sample_final_state(1234)
+    assert len(sampling) == 4  # all states were observed
+    results[-1].matching_meas_basis = False
+    assert results.sample_final_state(N_samples=911) == {"00": 911}
+    seq3 = seq_no_meas()
+    seq3.declare_channel("raman", "raman_local", "B")
+    seq3.add(pi_pulse, "raman")
+    res_3level = emu.B200Emulator.from_sequence(seq3, evaluation_times="Minimal").run()
+    assert len(res_3level.sample_final_state()) == 2  # the Raman pi pulse on one atom leaves the other alone
+    seq3.measure("ground-rydberg")
+    res_3level_gb = emu.B200Emulator.from_sequence(seq3, evaluation_times="Minimal").run()
+    assert len(res_3level_gb.sample_final_state()) == 4  # the global Rydberg pulse affects both
