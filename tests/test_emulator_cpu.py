@@ -1043,3 +1043,35 @@ def test_sample_final_state_ports(emu):
     seq3.measure("ground-rydberg")
     res_3level_gb = emu.B200Emulator.from_sequence(seq3, evaluation_times="Minimal").run()
     assert len(res_3level_gb.sample_final_state()) == 4  # the global Rydberg pulse affects both
+
+
+def test_mask_local_channel_port(emu):
+    """reference tests/pulser_simulation/test_simulation.py:1841-1925 (test_mask_local_channel), on the spec: in Ising
+    mode the SLM mask is a detuning of -10 x amplitude on the masked atoms (local table) under the global drive; a
+    local Raman channel on q0 with phase pi shows up in the digital table."""
+    from pulser import Pulse, Register, Sequence
+    from pulser.devices import MockDevice
+
+    seq_ = Sequence(Register.square(2, prefix="q"), MockDevice)
+    seq_.declare_channel("rydberg_global", "rydberg_global")
+    pulse = Pulse.ConstantPulse(1000, 10, 0, 0)
+    seq_.config_slm_mask(["q0", "q3"])
+    seq_.add(pulse, "rydberg_global")
+    seq_.declare_channel("raman_local", "raman_local", initial_target="q0")
+    pulse2 = Pulse.ConstantPulse(1000, 10, -5, np.pi)
+    seq_.add(pulse2, "raman_local", protocol="no-delay")
+    assert seq_._slm_mask_time == [0, 1000] and seq_._slm_mask_targets == {"q0", "q3"}
+    sim = emu.B200Emulator.from_sequence(seq_)
+    spec = sim._current_spec
+    assert spec.slm_coefficient() is None  # only XY mode has a time-dependent interaction
+    tabs = {d.basis: d for d in spec.drives}
+    ryd, dig = tabs["ground-rydberg"], tabs["digital"]
+    amp = np.concatenate((pulse.amplitude.samples, [0]))
+    for k, q in enumerate(["q0", "q1", "q2", "q3"]):
+        np.testing.assert_array_equal(ryd.coef[k], 0.5 * amp)           # global drive, phase 0, on every atom
+        np.testing.assert_array_equal(ryd.det[k], -10 * amp if q in ("q0", "q3") else 0 * amp)
+    amp2 = np.concatenate((pulse2.amplitude.samples, [0]))
+    det2 = np.concatenate((pulse2.detuning.samples, [0]))
+    np.testing.assert_allclose(dig.coef[0], 0.5 * amp2 * np.exp(-1j * np.pi), rtol=1e-15, atol=1e-15)
+    np.testing.assert_array_equal(dig.det[0], det2)
+    assert np.all(dig.coef[1:] == 0) and np.all(dig.det[1:] == 0)
