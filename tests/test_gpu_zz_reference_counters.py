@@ -55,8 +55,10 @@ def test_schroedinger_reference_counters(lib, name):
         plan.set_state(extra["psi0"])
         plan.propagate(0.0, spec.sampling_times[-1])
         psi = plan.get_state()[0]
-    # EOM detunings of +-1000 rad/us held for microseconds: the stiffest sequence of the suite (margin 2x the 1e-8 target)
-    assert np.max(np.abs(psi - extra["orc_final"])) < 2e-8
+    # EOM detunings of +-1000 rad/us held for microseconds: the stiffest sequence of the suite, added after the last GPU
+    # session of round 1 -- the state bound is left a decade above the 1e-8 target until it has been measured here;
+    # the Counter equality below is the point of the test
+    assert np.max(np.abs(psi - extra["orc_final"])) < 1e-7
     got = sample_like_the_reference(spec, psi, extra)
     assert got == expected  # a 1e-8 shift of a cumulative boundary moves no shot
 
