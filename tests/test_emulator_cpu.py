@@ -614,9 +614,8 @@ def test_extraction_of_sequences_port(emu):
 
 def test_noise_port(emu, capfd):
     """reference tests/pulser_simulation/test_simulation.py:891-953 (test_noise): SPAM trajectories of seed 3 are merged
-    into the same groups (progress lines identical), the depolarizing channel is refused in the 3-level basis with
-    the reference's message, unprepared atoms get all-zero tables.  The reference's Counter golden depends on the order
-    in which QuTiP-era code consumed np.random; here it is a statistical target (first-level sample: 75 shots)."""
+    into the same groups (progress lines identical) and the reference's Counter comes out exactly; the depolarizing
+    channel is refused in the 3-level basis with the reference's message; unprepared atoms get all-zero tables."""
     from pulser import NoiseModel
 
     seq = _ccz_sequence()
@@ -627,17 +626,18 @@ def test_noise_port(emu, capfd):
             seq, sampling_rate=0.01,
             noise_model=NoiseModel(samples_per_run=5, p_false_pos=0.01, p_false_neg=0.05, state_prep_error=0.9),
             n_trajectories=15)
-        counts = sim2.run(print_progress=True).sample_final_state()
+        # one trajectory per device batch: the shots are then drawn trajectory by trajectory, the order in which the
+        # reference consumes np.random (a batch samples all its trajectories at one evaluation time before it moves
+        # on, which is the same distribution drawn in another order)
+        counts = sim2.run(print_progress=True, b200_batch=1).sample_final_state()
     out, _ = capfd.readouterr()
     assert out.rstrip("\n").split("\n") == [
         "Emulating Trajectories [1 - 13]/15",
         "Emulating Trajectory 14/15",
         "Emulating Trajectory 15/15",
     ]
-    ref = Counter({"000": 824, "100": 41, "101": 57, "001": 63, "010": 15})
-    assert sum(counts.values()) == 1000
-    tv = 0.5 * sum(abs(counts.get(k, 0) - ref.get(k, 0)) for k in set(counts) | set(ref)) / 1000
-    assert tv < 0.08, (counts, tv)
+    # the reference's hard-coded Counter (real QuTiP sesolve runs of the 3-level CCZ sequence), shot for shot
+    assert counts == Counter({"000": 824, "100": 41, "101": 57, "001": 63, "010": 15})
     with pytest.raises(NotImplementedError, match="Cannot include"):
         emu.B200Emulator.from_sequence(seq, noise_model=NoiseModel(depolarizing_rate=0.05))
     pending = sim2._pending_trajectories()  # a second use redraws the trajectories (simulation.py:892-902)
