@@ -522,6 +522,11 @@ class NoisyResults(SimulationResults):
     def states(self) -> list[np.ndarray]:
         return [self._calc_pseudo_density_diag(i) for i in range(len(self))]
 
+    @property
+    def results(self) -> list[Counter]:
+        """Probability distribution of the bitstrings (``simresults.py:290-293``)."""
+        return [Counter(res.sampling_dist) for res in self]
+
     def get_state(self, t: float, t_tol: float = 1.0e-3) -> np.ndarray:
         return self._calc_pseudo_density_diag(self._get_index_from_time(t, t_tol))
 

@@ -1075,3 +1075,4 @@ def test_mask_local_channel_port(emu):
     np.testing.assert_allclose(dig.coef[0], 0.5 * amp2 * np.exp(-1j * np.pi), rtol=1e-15, atol=1e-15)
     np.testing.assert_array_equal(dig.det[0], det2)
     assert np.all(dig.coef[1:] == 0) and np.all(dig.det[1:] == 0)
+

@@ -5,7 +5,8 @@ suite (tests/test_oracle_cpu.py, tests/test_emulator_cpu.py).
 
 * test_noisy_xy (reference tests/pulser_simulation/test_simulation.py:1536-1700, MESOLVER variants): XY mode, 15 SPAM
   trajectories x 10 samples with measurement errors, collapse operators, with and without an SLM mask;
-* test_noises_all (:1174-1302): three-level basis, 9-15 us sequences, effective noise / dephasing / relaxation.
+* test_noises_all (:1174-1302): three-level basis, 9-15 us sequences, effective noise / dephasing / relaxation;
+* the noisy goldens of tests/pulser_simulation/test_simresults.py (results_noisy fixture and the three tests using it).
 """
 import os
 import warnings
@@ -110,3 +111,60 @@ def test_noises_all_port(emu, noise, result):
         np.random.seed(123)
         got = sim.run().sample_final_state()
     assert got == Counter(result)
+
+
+def test_simresults_noisy_goldens_port(emu):
+    """reference tests/pulser_simulation/test_simresults.py:52-83 (results_noisy fixture), :448-483
+    (test_sample_final_state_noisy), :383-390 (test_expect_noisy), :244-276 (test_get_final_state_noisy): fifteen noisy
+    sesolve trajectories (doppler, amplitude, SPAM) under np.random.seed(123), drawn trajectory by trajectory like the
+    reference (b200_batch=1).  The reference's hard-coded Counter, expectation value and pseudo-density all come out
+    exactly -- including the second emulator of the same test, which continues on the same random stream."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice
+    from pulser.waveforms import BlackmanWaveform
+
+    reg = Register({"A": np.array([0.0, 0.0]), "B": np.array([0.0, 10.0])})
+    pi_pulse = Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0)
+    seq_no_meas = Sequence(reg, DigitalAnalogDevice)
+    seq_no_meas.declare_channel("ryd", "rydberg_global")
+    seq_no_meas.add(pi_pulse, "ryd")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(123)
+        sim = emu.B200Emulator.from_sequence(
+            seq_no_meas,
+            noise_model=NoiseModel(samples_per_run=5, temperature=50.0, state_prep_error=0.005, p_false_pos=0.01,
+                                   p_false_neg=0.05, amp_sigma=1e-3, laser_waist=175.0),
+            n_trajectories=15)
+        results_noisy = sim.run(b200_batch=1)
+        np.random.seed(123)
+        assert results_noisy.sample_final_state(N_samples=1234) == Counter({"11": 676, "10": 295, "01": 137, "00": 126})
+        res_3level = emu.B200Emulator.from_sequence(
+            seq_no_meas,
+            noise_model=NoiseModel(samples_per_run=5, temperature=50.0, state_prep_error=0.005, p_false_pos=0.01,
+                                   p_false_neg=0.05),
+            n_trajectories=10)
+        final_state = res_3level.run(b200_batch=1).states[-1]
+    assert np.isclose(np.asarray(final_state), np.array([0.38, 0.32, 0.2, 0.1])).all()
+    # test_expect_noisy
+    bad_op = np.kron(np.eye(2), np.array([[0.0, 1.0], [0.0, 0.0]]))
+    with pytest.raises(ValueError, match="non-diagonal"):
+        results_noisy.expect([bad_op])
+    op = np.kron(np.eye(2), np.diag([1.0, 0.0]))
+    assert np.isclose(results_noisy.expect([op])[0][-1], 0.68)
+    # test_get_final_state_noisy
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(123)
+        seq_ = Sequence(reg, DigitalAnalogDevice)
+        seq_.declare_channel("ram", "raman_local", initial_target="A")
+        seq_.add(pi_pulse, "ram")
+        sim_noisy = emu.B200Emulator.from_sequence(
+            seq_,
+            noise_model=NoiseModel(samples_per_run=5, temperature=50.0, trap_depth=0.01, trap_waist=0.02,
+                                   state_prep_error=0.005, p_false_pos=0.01, p_false_neg=0.05),
+            n_trajectories=15)
+        res3 = sim_noisy.run(b200_batch=1)
+    final = np.asarray(res3.get_final_state())
+    assert final[0] == 0.04 and final[2] == 0.96
+    assert res3.results[-1] == Counter({"10": 0.96, "00": 0.04})
