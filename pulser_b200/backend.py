@@ -520,6 +520,13 @@ class B200Config(EmulationConfig[B200State]):
                 "If provided, `initial_state` must be an instance of "
                 f"`B200State`, not {type(initial_state)}."
             )
+        noise_model = backend_options.get("noise_model")
+        if noise_model is not None and noise_model.samples_per_run not in [None, 1]:
+            warnings.warn(  # qutip_config.py:114-123: the V2 protocol samples through its observables
+                f"The number of samples per run (`samples_per_run` = {noise_model.samples_per_run}) "
+                "is ignored when using B200Backend.",
+                stacklevel=2,
+            )
         try:
             solver = Solver(solver)
         except ValueError:

@@ -648,3 +648,65 @@ def test_output_state_normalization_port(backend, amp_sigma):
                                                                  observables=[Fidelity(final_state)])
         results = backend.B200Backend(seq, config=config).run()
     assert results.fidelity[-1] < 1 + 1e-8
+
+
+def test_density_matrix_aggregator_port(backend):
+    """reference tests/pulser_simulation/test_aggregators.py:6-47."""
+    mk = lambda s: backend.B200State.from_state_amplitudes(eigenstates=("r", "g"), amplitudes={s: 1.0})  # noqa: E731
+    state1, state2, state3 = mk("rgg"), mk("grg"), mk("ggr")
+    acc = backend.density_matrix_aggregator([state1, state2])  # vector and vector
+    assert np.isclose(np.trace(acc.to_array()).real, 1.0)
+    res1 = np.zeros((8, 8))
+    res1[3, 3] = res1[5, 5] = 0.5
+    assert np.allclose(acc.to_array(), res1)
+    acc = backend.density_matrix_aggregator([acc, state3])  # vector and matrix
+    res2 = np.zeros((8, 8))
+    res2[3, 3] = res2[5, 5] = 0.25
+    res2[6, 6] = 0.5
+    assert np.allclose(acc.to_array(), res2)
+    acc = backend.density_matrix_aggregator([acc, acc])  # matrix and matrix
+    assert np.isclose(np.trace(acc.to_array()).real, 1.0)
+    assert np.allclose(acc.to_array(), res2)
+
+
+def test_config_ports(backend):
+    """reference tests/pulser_simulation/test_qutip_config.py:17-146, on B200Config."""
+    import json
+    import re
+
+    from pulser import NoiseModel
+    from pulser.backend.default_observables import BitStrings, StateResult
+
+    obs = [StateResult(evaluation_times=[1.0])]
+    with pytest.raises(NotImplementedError, match="does not handle custom interaction matrices."):
+        backend.B200Config(observables=obs, interaction_matrix=np.eye(4))
+    with pytest.raises(ValueError, match="be greater than 0 and less than or equal to 1"):
+        backend.B200Config(observables=obs, sampling_rate=1.2)
+    config = backend.B200Config(observables=obs, sampling_rate=0.5)
+    assert "sampling_rate" in config._expected_kwargs()
+    with pytest.warns(UserWarning, match="The number of samples per run .* is ignored when using"):
+        with pytest.warns(DeprecationWarning, match="Setting samples_per_run different to 1 is"):
+            backend.B200Config(observables=obs, noise_model=NoiseModel(temperature=45, samples_per_run=5))
+    with pytest.raises(TypeError, match=re.escape("If provided, `initial_state` must be an instance of `B200State`")):
+        backend.B200Config(observables=obs, initial_state="all-ground")
+    assert backend.B200Config.state_type is backend.B200State
+    assert backend.B200Config.operator_type is backend.B200Operator
+    config = backend.B200Config(observables=obs, progress_bar=True)
+    assert config.progress_bar and "progress_bar" in config._expected_kwargs()
+    default_times = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+    obs_times_1 = np.array([0.2, 0.4, 0.8])
+    obs_times_2 = np.array([0.15, 0.35, 0.65, 0.95])
+    config = backend.B200Config(
+        observables=[StateResult(evaluation_times=obs_times_1), StateResult(evaluation_times=obs_times_2, tag_suffix="second")],
+        default_evaluation_times=default_times)
+    expected = np.union1d(np.union1d(default_times, obs_times_1), obs_times_2)
+    np.testing.assert_almost_equal(config._get_legacy_evaluation_times(1000), expected)
+    for solver in backend.Solver:
+        for as_str in (True, False):
+            config = backend.B200Config(observables=[BitStrings(evaluation_times=[1.0])],
+                                        solver=solver if not as_str else str(solver.value))
+            ser = config.to_abstract_repr()
+            assert json.loads(ser)["solver"] == str(solver.value)
+            assert backend.B200Config.from_abstract_repr(ser).solver is solver
+    with pytest.raises(ValueError, match="Invalid solver 'fakesolver'"):
+        backend.B200Config(observables=[BitStrings(evaluation_times=[1.0])], solver="fakesolver")
