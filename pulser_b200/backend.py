@@ -299,6 +299,14 @@ class B200Operator(Operator[complex, complex, B200State]):
             self._builder, self._matrix = operator, None
         else:
             self._builder, self._matrix = None, self._as_matrix(operator)
+            # qutip_op.py:57 (QutipState._validate_shape): the dimension must be a power of the qudit dimension
+            d = len(eigenstates)
+            n = math.log(self._matrix.shape[0], d)
+            if self._matrix.shape[0] != self._matrix.shape[1] or not np.isclose(n, round(n)):
+                raise ValueError(
+                    f"A state with shape {tuple(self._matrix.shape)} is incompatible with "
+                    f"a system of {d}-level qudits."
+                )
 
     @staticmethod
     def _as_matrix(operator: Any) -> sp.csr_matrix:

@@ -174,3 +174,140 @@ class TestB200State:
         state._state = ket_r._state
         with pytest.raises(AbstractReprError, match="modified in place after its creation"):
             json.dumps(state, cls=AbstractReprEncoder)
+
+
+SX = np.array([[0, 1], [1, 0]], dtype=complex)
+SY = np.array([[0, -1j], [1j, 0]], dtype=complex)
+SZ = np.array([[1, 0], [0, -1]], dtype=complex)
+
+
+def proj(d, k):
+    return np.outer(basis(d, k), basis(d, k).conj())
+
+
+class TestB200Operator:
+    @pytest.fixture
+    def pauli_i(self, B):
+        return B.B200Operator(np.eye(2, dtype=complex), eigenstates=("r", "g"))
+
+    @pytest.fixture
+    def pauli_x(self, B):
+        return B.B200Operator(SX, eigenstates=("r", "g"))
+
+    @pytest.fixture
+    def pauli_y(self, B):
+        return B.B200Operator(SY, eigenstates=("r", "g"))
+
+    @pytest.fixture
+    def pauli_z(self, B):
+        return B.B200Operator(SZ, eigenstates=("r", "g"))
+
+    def test_init(self, B):
+        """test_qutip_state_op.py:307-330"""
+        with pytest.raises(ValueError, match="eigenstates must be represented by single characters"):
+            B.B200Operator(SZ, eigenstates=["ground", "rydberg"])
+        with pytest.raises(ValueError, match="can't contain repeated entries"):
+            B.B200Operator(SZ, eigenstates=["r", "g", "r"])
+        with pytest.raises(ValueError, match="incompatible with a system of 3-level qudits"):
+            B.B200Operator(SZ, eigenstates=["r", "g", "h"])
+        pauli_z = B.B200Operator(SZ, eigenstates=("r", "g"))
+        assert pauli_z.eigenstates == ("r", "g")
+        np.testing.assert_array_equal(pauli_z.to_array(), proj(2, 0) - proj(2, 1))
+
+    @pytest.mark.parametrize("op_name", ["apply_to", "expect"])
+    def test_errors_on_state(self, B, pauli_x, op_name):
+        """:351-372"""
+        op = getattr(pauli_x, op_name)
+        with pytest.raises(TypeError, match=re.escape(f"'B200Operator.{op_name}()' expects a 'B200State' instance")):
+            op(basis(2, 0))
+        err_msg = (f"Can't apply B200Operator.{op_name}() between a B200Operator "
+                   "with eigenstates ('r', 'g') and a B200State with {}")
+        with pytest.raises(ValueError, match=re.escape(err_msg.format(("g", "h")))):
+            op(B.B200State(basis(2, 0), eigenstates=("g", "h")))
+        with pytest.raises(NotImplementedError, match=re.escape(err_msg.format(("g", "r")))):
+            op(B.B200State(basis(2, 0), eigenstates=("g", "r")))
+
+    @pytest.mark.parametrize("op_name", ["__add__", "__matmul__"])
+    def test_errors_on_operator(self, B, pauli_x, ket_r, op_name):
+        """:374-394"""
+        op = getattr(pauli_x, op_name)
+        with pytest.raises(TypeError, match=re.escape(f"'{op_name}' expects a 'B200Operator' instance")):
+            op(ket_r)
+        err_msg = (f"Can't apply {op_name} between a B200Operator with eigenstates "
+                   "('r', 'g') and a B200Operator with {}")
+        with pytest.raises(ValueError, match=re.escape(err_msg.format(("g", "h")))):
+            op(B.B200Operator(proj(2, 0), eigenstates=("g", "h")))
+        with pytest.raises(NotImplementedError, match=re.escape(err_msg.format(("g", "r")))):
+            op(B.B200Operator(proj(2, 0), eigenstates=("g", "r")))
+
+    def test_apply_to(self, B, ket_r, dm_g, pauli_x):
+        """:396-402"""
+        assert pauli_x.apply_to(ket_r) == B.B200State.from_state_amplitudes(eigenstates=("r", "g"),
+                                                                            amplitudes={"g": 1.0})
+        assert pauli_x.apply_to(dm_g) == B.B200State(proj(2, 0), eigenstates=dm_g.eigenstates)
+
+    def test_expect(self, pauli_x, pauli_y, pauli_z, ket_r, dm_g, ket_plus):
+        """:404-421"""
+        assert pauli_x.expect(ket_r) == 0.0
+        assert pauli_x.expect(dm_g) == 0.0
+        assert np.isclose(pauli_x.expect(ket_plus), 1.0)
+        ket_minus = pauli_y.apply_to(ket_plus)
+        assert np.isclose(pauli_x.expect(ket_minus), -1.0)
+        assert pauli_z.expect(ket_r) == 1.0
+        assert pauli_z.expect(dm_g) == -1.0
+        assert np.isclose(pauli_z.expect(ket_plus), 0.0)
+
+    def test_add_rmul_matmul(self, B, pauli_i, pauli_x, pauli_y, pauli_z):
+        """:423-453"""
+        r, g = basis(2, 0), basis(2, 1)
+        assert pauli_x + pauli_y == B.B200Operator((1 - 1j) * np.outer(r, g) + (1 + 1j) * np.outer(g, r),
+                                                   eigenstates=pauli_x.eigenstates)
+        assert pauli_i + pauli_z == B.B200Operator(2 * proj(2, 0), eigenstates=pauli_z.eigenstates)
+        assert (1 - 2j) * pauli_i == B.B200Operator((1 - 2j) * np.eye(2), eigenstates=pauli_z.eigenstates)
+        assert 0.5 * (pauli_i + pauli_z) == B.B200Operator(proj(2, 0), eigenstates=pauli_z.eigenstates)
+        assert pauli_x @ pauli_x == pauli_y @ pauli_y == pauli_z @ pauli_z == pauli_i
+        assert pauli_x @ pauli_z == -1j * pauli_y
+        assert pauli_z @ pauli_x == 1j * pauli_y
+
+    def test_from_operator_repr(self, B, pauli_i):
+        """:455-562"""
+        mk = B.B200Operator.from_operator_repr
+        with pytest.raises(ValueError, match=re.escape(
+                "Every QuditOp key must be made up of two eigenstates among ('r', 'g'); instead, got 'gggg'.")):
+            mk(eigenstates=("r", "g"), n_qudits=2, operations=[(1.0, [({"gggg": 1.0, "rr": -1.0}, {0})])])
+        with pytest.raises(ValueError, match=re.escape(
+                "Every QuditOp key must be made up of two eigenstates among ('r', 'g'); instead, got 'hh'.")):
+            mk(eigenstates=("r", "g"), n_qudits=2, operations=[(1.0, [({"hh": 1.0, "rr": -1.0}, {0})])])
+        with pytest.raises(ValueError, match="Got invalid indices for a system with 2 qudits"):
+            mk(eigenstates=("r", "g"), n_qudits=2, operations=[(1.0, [({"gg": 1.0, "rr": -1.0}, {3, 5, 9})])])
+        with pytest.raises(ValueError, match=re.escape("only indices {1} were still available")):
+            mk(eigenstates=("r", "g"), n_qudits=2,
+               operations=[(1.0, [({"gg": 1.0, "rr": -1.0}, {0}), ({"rg": 1.0}, {0})])])
+        got = mk(eigenstates=("r", "g", "h"), n_qudits=3,
+                 operations=[(1.0, [({"rr": 1.0, "hh": -1.0}, {0}), ({"gr": -1j}, {2})])])
+        want = np.kron(np.kron(proj(3, 0) - proj(3, 2), np.eye(3)), -1j * np.outer(basis(3, 1), basis(3, 0)))
+        assert got == B.B200Operator(want, eigenstates=("r", "g", "h"))
+        assert mk(eigenstates=("r", "g"), n_qudits=1, operations=[(1, [])]) == pauli_i
+        got = mk(eigenstates=("r", "g"), n_qudits=2, operations=[(0.5, [({"rr": 1.0, "gg": -1.0}, {0})]), (0.5, [])])
+        assert got == B.B200Operator(np.kron(proj(2, 0), np.eye(2)), eigenstates=("r", "g"))
+
+    def test_eq(self, B, pauli_i, pauli_z, dm_g):
+        """:573-578"""
+        g_proj = 0.5 * (pauli_i + (-1) * pauli_z)
+        assert g_proj == B.B200Operator(proj(2, 1), eigenstates=pauli_i.eigenstates)
+        assert g_proj != dm_g
+
+    def test_abstract_repr(self, B):
+        """:580-605"""
+        from pulser.exceptions.serialization import AbstractReprError
+        from pulser.json.abstract_repr.serializer import AbstractReprEncoder
+
+        kwargs = dict(eigenstates=("r", "g"), n_qudits=3,
+                      operations=[(0.5, [({"rr": 1.0, "gg": 1.0j}, {0})]), (0.5, [])])
+        op = B.B200Operator.from_operator_repr(**kwargs)
+        ser_ops = [(0.5, [({"rr": 1.0, "gg": {"real": 0.0, "imag": 1.0}}, [0])]), (0.5, [])]
+        assert json.dumps(op, cls=AbstractReprEncoder) == json.dumps({**kwargs, "operations": ser_ops})
+        with pytest.raises(AbstractReprError, match=re.escape(
+                "Failed to serialize state of type 'B200Operator' because it was not created via "
+                "'B200Operator.from_operator_repr()'")):
+            json.dumps(B.B200Operator(op.to_array(), eigenstates=op.eigenstates), cls=AbstractReprEncoder)
