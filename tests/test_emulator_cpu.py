@@ -1076,3 +1076,35 @@ def test_mask_local_channel_port(emu):
     np.testing.assert_array_equal(dig.det[0], det2)
     assert np.all(dig.coef[1:] == 0) and np.all(dig.det[1:] == 0)
 
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_hamiltonian_constructor_arguments_port(three_d):
+    """reference tests/pulser_simulation/test_hamiltonian.py:29-80 (test_register_2d / test_register_3d, issue #940):
+    ``spec_from_pulser`` takes the exact arguments of the reference's ``Hamiltonian(noisy_samples, trajectory,
+    basis_data, lindblad_data, sampling_rate)`` for 2D and 3D registers."""
+    from pulser import Pulse, Register, Register3D, Sequence
+    from pulser._hamiltonian_data import HamiltonianData
+    from pulser.devices import MockDevice
+    from pulser_b200.spec import spec_from_pulser
+
+    reg = (Register3D({"q0": np.array([-4.0, 0.0, 0.0]), "q1": np.array([0.0, 4.0, 0.0])}) if three_d
+           else Register({"q0": np.array([-4.0, 0.0]), "q1": np.array([0.0, 4.0])}))
+    seq = Sequence(reg, MockDevice)
+    seq.declare_channel("ch0", "rydberg_global")
+    seq.declare_channel("ch1", "raman_local", initial_target="q0")
+    seq.declare_channel("ch2", "raman_local", initial_target="q1")
+    pulse1 = Pulse.ConstantPulse(10, 0, 0, 0)
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch0")
+    seq.add(pulse1, "ch1", protocol="no-delay")
+    seq.add(pulse1, "ch2", protocol="no-delay")
+    data = HamiltonianData.from_sequence(seq)
+    for traj, noisy_samples, _ in data.noisy_samples:
+        spec = spec_from_pulser(noisy_samples, traj, data.basis_data, data.lindblad_data, 0.5)
+        assert spec.n_qudits == 2 and len(spec.sampling_times) == int(0.5 * noisy_samples.max_duration)
+        assert spec.dim == data.basis_data.dim and spec.eigenbasis == list(data.basis_data.eigenbasis)
+        assert spec.interaction_matrix.shape == (1, 2, 2)
+        # (pulser rounds distances to its coordinate precision: 1e-6 relative)
+        np.testing.assert_allclose(spec.interaction_matrix[0, 0, 1], MockDevice.interaction_coeff / (4 * np.sqrt(2)) ** 6,
+                                   rtol=1e-6)
