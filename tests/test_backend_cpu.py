@@ -710,3 +710,15 @@ def test_config_ports(backend):
             assert backend.B200Config.from_abstract_repr(ser).solver is solver
     with pytest.raises(ValueError, match="Invalid solver 'fakesolver'"):
         backend.B200Config(observables=[BitStrings(evaluation_times=[1.0])], solver="fakesolver")
+
+
+def test_package_exports_mirror_pulser_simulation():
+    """pulser_simulation/__init__.py:17-40: the emulator, both backends, config / state / operator types, the solver
+    enum and the aggregator are importable from the package root."""
+    import pulser_b200
+
+    for name in ("B200Emulator", "B200Backend", "B200LegacyBackend", "B200Config", "B200State", "B200Operator",
+                 "Solver", "density_matrix_aggregator"):
+        assert getattr(pulser_b200, name) is not None and name in pulser_b200.__all__
+    with pytest.raises(AttributeError):
+        pulser_b200.QutipEmulator
