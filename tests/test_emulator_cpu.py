@@ -1108,3 +1108,70 @@ def test_hamiltonian_constructor_arguments_port(three_d):
         # (pulser rounds distances to its coordinate precision: 1e-6 relative)
         np.testing.assert_allclose(spec.interaction_matrix[0, 0, 1], MockDevice.interaction_coeff / (4 * np.sqrt(2)) ** 6,
                                    rtol=1e-6)
+
+
+@pytest.mark.parametrize("leakage", [False, True])
+def test_building_basis_and_projection_operators_port(emu, leakage):
+    """reference tests/pulser_simulation/test_simulation.py:254-431 (test_building_basis_and_projection_operators):
+    basis names, dimensions, basis kets and sigma_ab projectors of every addressing (all / ground-rydberg global and
+    local / digital / XY), with and without the leakage level; build_operator messages."""
+    from pulser import NoiseModel, Pulse, Register, Sequence
+    from pulser.devices import DigitalAnalogDevice, MockDevice
+    from pulser.sampler import sampler
+    from pulser.waveforms import BlackmanWaveform
+
+    def noise_model(dim):
+        if not leakage:
+            return NoiseModel()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return NoiseModel(with_leakage=True, eff_noise_opers=[np.eye(dim)], eff_noise_rates=[0.0])
+
+    def check(sim, name, letters, pairs):
+        dim = len(letters)
+        assert sim.basis_name == name + ("_with_error" if leakage else "")
+        assert sim.dim == dim
+        assert list(sim.basis) == list(letters)
+        for k, s in enumerate(letters):
+            np.testing.assert_array_equal(sim.basis[s].full().ravel(), np.eye(dim)[k])
+        for a, b in pairs:
+            want = np.outer(np.eye(dim)[letters.index(a)], np.eye(dim)[letters.index(b)])
+            np.testing.assert_array_equal(sim.op_matrix["sigma_" + a + b].toarray(), want)
+
+    seq = _ccz_sequence()
+    reg = Register({"control1": np.array([-4.0, 0.0]), "target": np.array([0.0, 4.0]), "control2": np.array([4.0, 0.0])})
+    x = ("x",) if leakage else ()
+    sim = emu.B200Emulator.from_sequence(seq, sampling_rate=0.01, noise_model=noise_model(3 + leakage))
+    check(sim, "all", ("r", "g", "h") + x, [("r", "r"), ("g", "r"), ("h", "g")] + ([("x", "r")] if leakage else []))
+    with pytest.raises(ValueError, match="Duplicate atom"):
+        sim.build_operator([("sigma_gg", ["target", "target"])])
+    with pytest.raises(ValueError, match="not a valid operator"):
+        sim.build_operator([("wrong", ["target"])])
+    with pytest.raises(ValueError, match="Invalid qubit names: {'wrong'}"):
+        sim.build_operator([("sigma_gg", ["wrong"])])
+    op_standard = sim.build_operator([("sigma_gg", ["target"])])
+    op_one = sim.build_operator(("sigma_gg", ["target"]))
+    assert abs(op_standard - op_one).max() < 1e-10
+    pi_pls = Pulse.ConstantDetuning(BlackmanWaveform(1000, np.pi), 0.0, 0)
+    dim = 2 + leakage
+
+    def one_channel(device, *decl):
+        s = Sequence(reg, device)
+        s.declare_channel(*decl)
+        s.add(pi_pls, decl[0])
+        return s
+
+    sim2 = emu.B200Emulator.from_sequence(one_channel(DigitalAnalogDevice, "global", "rydberg_global"),
+                                          sampling_rate=0.01, noise_model=noise_model(dim))
+    check(sim2, "ground-rydberg", ("r", "g") + x, [("r", "r"), ("g", "r")] + ([("x", "r")] if leakage else []))
+    sim2b = emu.B200Emulator.from_sequence(one_channel(DigitalAnalogDevice, "local", "raman_local", "target"),
+                                           sampling_rate=0.01, noise_model=noise_model(dim))
+    check(sim2b, "digital", ("g", "h") + x, [("g", "g"), ("h", "g")] + ([("x", "h")] if leakage else []))
+    sim2c = emu.B200Emulator.from_sequence(one_channel(DigitalAnalogDevice, "local_ryd", "rydberg_local", "target"),
+                                           sampling_rate=0.01, noise_model=noise_model(dim))
+    check(sim2c, "ground-rydberg", ("r", "g") + x, [("r", "r"), ("g", "r")] + ([("x", "g")] if leakage else []))
+    seq_xy = one_channel(MockDevice, "global", "mw_global")
+    with pytest.raises(ValueError, match="Bases used in samples should be supported by device."):
+        emu.B200Emulator(sampler.sample(seq_xy), seq_xy.register, DigitalAnalogDevice)
+    sim_xy = emu.B200Emulator.from_sequence(seq_xy, sampling_rate=0.01, noise_model=noise_model(dim))
+    check(sim_xy, "XY", ("u", "d") + x, [("u", "u"), ("d", "u"), ("u", "d")] + ([("u", "x")] if leakage else []))
