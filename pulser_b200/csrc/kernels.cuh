@@ -97,6 +97,37 @@ __device__ __forceinline__ void st_c2(c2* p, c2 v) {
     *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
 }
 
+// Fused Lanczos step (StageArgs::lz set).  The gather source `v` holds the RAW vector r_j = G v_j - beta_{j-1} v_{j-1}
+// of the previous stage; alpha_j = Re<v_j, r_j> and |r_j|^2 were reduced by that stage into lz.acc_prev.  This stage
+//   v_{j+1} = (r_j - alpha_j v_j) / beta_j                           (second output, own element)
+//   r_{j+1} = G v_{j+1} - beta_j v_j
+//           = [G r_j - alpha_j r_j - alpha_j beta_{j-1} v_{j-1}] / beta_j - beta_j v_j     (G v_j = r_j + beta_{j-1} v_{j-1})
+// so the separate vector-update kernel (48 B/amplitude, one launch per iteration) disappears: 88 B/amplitude per
+// Lanczos iteration instead of 104, one launch.  Reference call replaced: qutip.sesolve, simulation.py:729-735.
+struct LanczosFuse {
+    const c2* vj;            // v_j      [B][D] own element
+    const c2* vjm1;          // v_{j-1}  [B][D] own element (nullptr for j = 0)
+    c2* vout;                // v_{j+1}  [B][D]
+    const double* acc_prev;  // [B][2]: alpha_j, |r_j|^2
+    const double* beta_prev; // [B]: beta_{j-1} (nullptr for j = 0)
+    double* alpha_out;       // [B]: alpha_j recorded for the host
+    double* beta_out;        // [B]: beta_j
+    double* acc_clear;       // [B][2]: accumulator of the stage after this one, cleared here
+};
+
+struct LanczosCoef { double alpha, beta, inv, beta_prev; };
+
+__device__ __forceinline__ LanczosCoef lanczos_coef(const LanczosFuse& lz, long long traj) {
+    LanczosCoef c;
+    c.alpha = lz.acc_prev[2 * traj];
+    const double ww = lz.acc_prev[2 * traj + 1];
+    const double b2 = ww - c.alpha * c.alpha;
+    c.beta = (b2 > 1e-28 * fmax(ww, 1e-300)) ? sqrt(b2) : 0.0;   // 0: breakdown (invariant subspace reached)
+    c.inv = c.beta > 0.0 ? 1.0 / c.beta : 0.0;
+    c.beta_prev = lz.beta_prev ? lz.beta_prev[traj] : 0.0;
+    return c;
+}
+
 // ---- d = 2 tiled stage kernel ---------------------------------------------
 struct StageArgs {
     const c2* v;      // gather source      [B][D]
@@ -113,15 +144,9 @@ struct StageArgs {
     int to_bit;
     int from_is_one;
     const double* beta_dev;  // Lanczos: c_b2 = -beta_dev[traj] read on the device (nullptr: use coef.c_b2)
-    double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<v, out>, acc[traj][1] += <out, out> (fused reductions)
-    int swz;  // > 0: number of tile-id bits, tile order bit-reversed (L2 locality of high-bit partners)
-    // partner-sum forwarding (FWD kernels): w_in[s] = drive-weighted sum of v over the flips this stage does not
-    // perform itself (computed by the producer of v, whose tile was closed under them); w_out: the same sum of
-    // `out` over THIS stage's tile flips, for the consumer.  Both may alias (own-element read, then write).
-    const c2* w_in;
-    c2* w_out;
-    int fwd_flags;  // stage_d2_fwd_kernel: 1/2/4 stage w_in / b2 / psi tiles through TMA, 8 separate result tile, 16 L1 prefetch
-    int dbg;  // experiment switches (PB200_DBG): 1 skip smem flips, 2 skip global partners, 4 skip own loads, 8 skip store
+    double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<lhs, out>, acc[traj][1] += <out, out> (fused reductions;
+                             // lhs = v, or v_{j+1} in a fused Lanczos step)
+    LanczosFuse lz;          // fused Lanczos step when lz.vj != nullptr (register-blocked kernels)
 };
 
 // up to two independent Clenshaw chains per launch (the h and the h/2 branches of a Richardson step):
@@ -267,11 +292,9 @@ __global__ void __launch_bounds__(256) stage_d2_kernel(StageArgs a) {
 // (flipped tile bits - RB + 1) x 16 B.
 // Compute phase of one tile, shared by the one-shot and the persistent kernels: gathers from the tile in
 // shared memory (register-blocked), optional global-load partners, fused epilogue and store.
-// own-element global load: streaming (one-shot kernels) or L1-bypassing (cooperative kernel, where the data
-// was written by other CTAs earlier in the same launch and L1 is not coherent)
-template <bool COH>
+// own-element global load: streaming (read once per stage)
 __device__ __forceinline__ c2 ld_own(const c2* p) {
-    double2 r = COH ? __ldcg(reinterpret_cast<const double2*>(p)) : __ldcs(reinterpret_cast<const double2*>(p));
+    double2 r = __ldcs(reinterpret_cast<const double2*>(p));
     return {r.x, r.y};
 }
 
@@ -338,13 +361,12 @@ __device__ __forceinline__ void rb_tile_gather(const PassGeom& g, const c2* tile
     }
 }
 
-// `ring` (optional): two tile-sized shared-memory slots through which the out-of-tile partner tiles are
-// streamed by TMA (slots 0 and 1 already hold / are receiving the partners of the first two extra bits when
-// this function is entered); `rbar` their mbarriers.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB, bool COH = false>
+// Compute phase of one tile: gathers from the tile in shared memory (register-blocked), coalesced global loads
+// for the partners outside the tile, fused epilogue (diagonal, Clenshaw / Lanczos combination, reductions) and store.
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
 __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* tile,
                                                 const double* __restrict__ tab, long long base, long long traj,
-                                                int tid, c2* ring = nullptr, uint64_t* rbar = nullptr) {
+                                                int tid) {
     constexpr int R = 1 << RB;
     constexpr int NT = 1 << (TBITS - RB);
     const long long voff = traj * a.D;
@@ -361,7 +383,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         v[r] = tile[tid + r * NT];
         pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
     }
-    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, (a.dbg & 1) != 0, v, pr, pi, qr, qi);
+    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
     // global index of each owned amplitude
     long long idx[R];
 #pragma unroll
@@ -369,46 +391,23 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         const int t = tid + r * NT;
         idx[r] = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
     }
-    // --- flips of the bits outside the tile: partner tiles streamed through the TMA ring, or coalesced loads ---
-    int e_cnt = 0;
-    for (unsigned long long m = (a.dbg & 2) ? 0ULL : g.extra_mask; m; m &= m - 1, ++e_cnt) {
+    // --- flips of the bits outside the tile: coalesced partner loads ---
+    for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
         const int p = __ffsll((long long)m) - 1;
         double gx = 0.0, gyt = 0.0;
         if (!UNIFORM) { gx = tab[2 * p]; gyt = tab[2 * p + 1]; }
         const int bit = (int)((base >> p) & 1);  // extra bits are never tile bits
         const double sg = (bit == to_bit) ? 1.0 : -1.0;
         const double gy = (bit == to_bit) ? gyt : -gyt;
-        const c2* slot = nullptr;
-        // dbg & 32 (hybrid): only the first two partner tiles come through the ring (prefetched at kernel start,
-        // no refill); the other bits are ordinary partner loads that are in flight at the same time
-        const bool from_ring = ring && (!(a.dbg & 32) || e_cnt < 2);
-        if (from_ring) {
-            slot = ring + (size_t)(e_cnt & 1) * (1 << TBITS);
-            mbar_wait(&rbar[e_cnt & 1], (uint32_t)((e_cnt >> 1) & 1));
-        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            double2 raw;
-            if (from_ring) { const c2 sv = slot[tid + r * NT]; raw = make_double2(sv.x, sv.y); }
-            else raw = COH ? __ldcg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))))
-                           : __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
             if (UNIFORM) {
                 pr[r] += raw.x; pi[r] += raw.y;
                 if (!REAL_G) { qr[r] = fma(sg, raw.x, qr[r]); qi[r] = fma(sg, raw.y, qi[r]); }
             } else {
                 pr[r] = fma(gx, raw.x, pr[r]); pr[r] = fma(-gy, raw.y, pr[r]);
                 pi[r] = fma(gx, raw.y, pi[r]); pi[r] = fma(gy, raw.x, pi[r]);
-            }
-        }
-        if (ring && !(a.dbg & 32)) {
-            __syncthreads();  // every thread has consumed the slot: refill it with the partner tile after next
-            unsigned long long m2 = m & (m - 1);
-            m2 &= m2 - 1;      // second next extra bit
-            if (m2 && tid == 0) {
-                const int p2 = __ffsll((long long)m2) - 1;
-                mbar_arrive_expect_tx(&rbar[e_cnt & 1], (uint32_t)(1 << TBITS) * 16u);
-                tma_load_1d(ring + (size_t)(e_cnt & 1) * (1 << TBITS), vsrc + (base ^ (1LL << p2)),
-                            (uint32_t)(1 << TBITS) * 16u, &rbar[e_cnt & 1]);
             }
         }
     }
@@ -454,9 +453,12 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
     // of one half are all in flight together (the stores to `out` may alias them for the compiler)
     constexpr int H = (R >= 4) ? R / 2 : R;
     const c2 cb2 = a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2;
+    const bool fuse = a.lz.vj != nullptr;
+    LanczosCoef lc{0.0, 0.0, 0.0, 0.0};
+    if (fuse) lc = lanczos_coef(a.lz, traj);
     double dot0 = 0.0, dot1 = 0.0;
     if (g.first_pass) {
-        const double* dsrc = (a.dint && !(a.dbg & 4)) ? a.dint + traj * a.dint_stride : nullptr;
+        const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
 #pragma unroll
         for (int h0 = 0; h0 < R; h0 += H) {
             double dv[H];
@@ -464,8 +466,13 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 dv[r] = dsrc ? __ldcs(dsrc + idx[h0 + r]) : 0.0;
-                pv[r] = a.psi ? ld_own<COH>(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
-                bv[r] = a.b2 ? ld_own<COH>(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                if (fuse) {
+                    pv[r] = ld_own(a.lz.vj + voff + idx[h0 + r]);
+                    bv[r] = (a.lz.vjm1 && lc.beta_prev != 0.0) ? ld_own(a.lz.vjm1 + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                } else {
+                    pv[r] = a.psi ? ld_own(a.psi + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                    bv[r] = a.b2 ? ld_own(a.b2 + voff + idx[h0 + r]) : c2{0.0, 0.0};
+                }
             }
 #pragma unroll
             for (int r = 0; r < H; ++r) {
@@ -479,13 +486,24 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                     diag -= th_common + th_r[rr];
                 }
                 const c2 gv = {fma(diag, v[rr].x, pr[rr]), fma(diag, v[rr].y, pi[rr])};
-                c2 res = cmul(a.coef.c_g, gv);
-                res = cadd(res, cmul(a.coef.c_psi, pv[r]));
-                res = cadd(res, cmul(cb2, bv[r]));
-                dot0 = fma(v[rr].x, res.x, dot0); dot0 = fma(v[rr].y, res.y, dot0);
+                c2 res, lhs;
+                if (fuse) {
+                    // v_{j+1} and r_{j+1} from the raw vector (see LanczosFuse)
+                    const c2 vn = {(v[rr].x - lc.alpha * pv[r].x) * lc.inv, (v[rr].y - lc.alpha * pv[r].y) * lc.inv};
+                    const double ai = lc.alpha * lc.inv, abi = ai * lc.beta_prev;
+                    res.x = fma(lc.inv, gv.x, -fma(ai, v[rr].x, fma(abi, bv[r].x, lc.beta * pv[r].x)));
+                    res.y = fma(lc.inv, gv.y, -fma(ai, v[rr].y, fma(abi, bv[r].y, lc.beta * pv[r].y)));
+                    st_c2(a.lz.vout + voff + idx[rr], vn);
+                    lhs = vn;
+                } else {
+                    res = cmul(a.coef.c_g, gv);
+                    res = cadd(res, cmul(a.coef.c_psi, pv[r]));
+                    res = cadd(res, cmul(cb2, bv[r]));
+                    lhs = v[rr];
+                }
+                dot0 = fma(lhs.x, res.x, dot0); dot0 = fma(lhs.y, res.y, dot0);
                 dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
-                if (a.dbg & 64) __stcs(reinterpret_cast<double2*>(a.out + voff + idx[rr]), make_double2(res.x, res.y));  // streaming store
-                else if (!(a.dbg & 8) || res.x == 1.2345) st_c2(a.out + voff + idx[rr], res);
+                st_c2(a.out + voff + idx[rr], res);
             }
         }
     } else {
@@ -493,7 +511,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         for (int h0 = 0; h0 < R; h0 += H) {
             c2 ov[H];
 #pragma unroll
-            for (int r = 0; r < H; ++r) ov[r] = ld_own<COH>(a.out + voff + idx[h0 + r]);
+            for (int r = 0; r < H; ++r) ov[r] = ld_own(a.out + voff + idx[h0 + r]);
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 const int rr = h0 + r;
@@ -519,6 +537,12 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
             atomicAdd(a.dot_acc + 2 * traj, s0);
             atomicAdd(a.dot_acc + 2 * traj + 1, s1);
         }
+    }
+    if (fuse && blockIdx.x == 0 && tid == 0) {  // one CTA per trajectory records the recurrence coefficients
+        a.lz.alpha_out[traj] = lc.alpha;
+        a.lz.beta_out[traj] = lc.beta;
+        a.lz.acc_clear[2 * traj] = 0.0;
+        a.lz.acc_clear[2 * traj + 1] = 0.0;
     }
 }
 
@@ -555,11 +579,7 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
     const PassGeom g = a.geo;
     const int tid = threadIdx.x;
     const long long traj = blockIdx.y - chain * m.n_traj;
-    // tile order: with `swz` set, consecutive CTAs differ in the HIGHEST tile-id bits, so that the CTAs
-    // resident together form a sub-cube closed under the high-bit flips (their partners hit in L2)
-    long long tile_id = blockIdx.x;
-    if (a.swz > 0) tile_id = (long long)(__brev((unsigned)blockIdx.x) >> (32 - a.swz));
-    const long long base = tile_base_of(g, tile_id);
+    const long long base = tile_base_of(g, blockIdx.x);
     const c2* vsrc = a.v + traj * a.D;
 
     if (tid == 0) mbar_init(&mbar, 1);
@@ -572,458 +592,13 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
         for (int i = tid; i < stride; i += NT) tab[i] = src[i];
     }
     __syncthreads();
-    if (a.dbg & 16) {
-        // experiment: plain LDG.128 -> STS.128 tile load instead of TMA bulk copies
-        const long long lomask = (1LL << g.lo_bits) - 1;
-#pragma unroll
-        for (int r = 0; r < (1 << RB); ++r) {
-            const int t = tid + r * NT;
-            const long long idx = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
-            const double2 raw = __ldg(reinterpret_cast<const double2*>(vsrc + idx));
-            tile[t] = {raw.x, raw.y};
-        }
-        __syncthreads();
-    } else {
-        if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
-        const int rows = 1 << g.hi_bits;
-        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
-        for (int r = tid; r < rows; r += NT)
-            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
-        mbar_wait(&mbar, 0);
-    }
-    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
-}
-
-// ---- d = 2 stage kernel with partner-sum forwarding and TMA-staged operands ------------------------------------
-// One Clenshaw stage  out = c_psi psi + c_b2 b2 + c_g (Gt v)  on one tile, where the drive partners of the flips
-// outside the tile arrive as forwarded sums w_in (see StageArgs) and the sums of the result over the tile's own
-// flips leave as w_out.  The input tile and (fwd_flags) the own-element operand tiles w_in / b2 / psi are all
-// brought in by TMA bulk copies on ONE mbarrier, so a CTA has a single exposed memory latency; the remaining
-// own-element operands can be prefetched into L1 while the copies are in flight.
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
-__global__ void __launch_bounds__(1 << (TBITS - RB), (TBITS == 11 ? 2 : 1))
-stage_d2_fwd_kernel(const __grid_constant__ StageArgs2 m) {
-    constexpr int R = 1 << RB;
-    constexpr int NT = 1 << (TBITS - RB);
-    constexpr int TSIZE = 1 << TBITS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-
-    const int chain = blockIdx.y / m.n_traj;
-    const StageArgs& a = m.a[chain];
-    const PassGeom g = a.geo;
-    const int tid = threadIdx.x;
-    const long long traj = blockIdx.y - chain * m.n_traj;
-    const long long base = tile_base_of(g, blockIdx.x);
-    const long long voff = traj * a.D;
-    const int fl = a.fwd_flags;
-
-    c2* tile = reinterpret_cast<c2*>(smem_raw);
-    c2* nxt = tile + TSIZE;
-    const c2* s_w = nullptr; const c2* s_b2 = nullptr; const c2* s_psi = nullptr;
-    int n_staged = 1;
-    if ((fl & 1) && a.w_in) { s_w = nxt; nxt += TSIZE; ++n_staged; }
-    if ((fl & 2) && a.b2) { s_b2 = nxt; nxt += TSIZE; ++n_staged; }
-    if ((fl & 4) && a.psi) { s_psi = nxt; nxt += TSIZE; ++n_staged; }
-    c2* rtile = tile;
-    if (fl & 8) { rtile = nxt; nxt += TSIZE; }
-    double* tab = reinterpret_cast<double*>(nxt);
-
-    if (tid == 0) mbar_init(&mbar, 1);
-    pdl_wait();
-    pdl_launch_dependents();
-    if (!UNIFORM) {
-        const int stride = d2_table_stride(g.n_bits);
-        const double* src = a.table + traj * stride;
-        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
-    }
-    __syncthreads();
-    {
-        if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)n_staged * (uint32_t)TSIZE * 16u);
-        const int rows = 1 << g.hi_bits;
-        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
-        for (int r = tid; r < rows; r += NT) {
-            const long long goff = voff + base + ((long long)r << g.hi_shift);
-            const size_t soff = (size_t)r << g.lo_bits;
-            tma_load_1d(tile + soff, a.v + goff, row_bytes, &mbar);
-            if (s_w) tma_load_1d(const_cast<c2*>(s_w) + soff, a.w_in + goff, row_bytes, &mbar);
-            if (s_b2) tma_load_1d(const_cast<c2*>(s_b2) + soff, a.b2 + goff, row_bytes, &mbar);
-            if (s_psi) tma_load_1d(const_cast<c2*>(s_psi) + soff, a.psi + goff, row_bytes, &mbar);
-        }
-    }
-    const long long lomask = (1LL << g.lo_bits) - 1;
-    // global index of owned amplitude r: the thread's fixed part plus the register-block bits (recomputed on use)
-    const long long fixed = base | (tid & lomask) | ((long long)(tid >> g.lo_bits) << g.hi_shift);
-    int pq[RB];
-#pragma unroll
-    for (int q = 0; q < RB; ++q) {
-        const int j = TBITS - RB + q;
-        pq[q] = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
-    }
-    auto idx_of = [&](int r) {
-        long long o = fixed;
-#pragma unroll
-        for (int q = 0; q < RB; ++q) o |= (long long)((r >> q) & 1) << pq[q];
-        return o;
-    };
-    const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
-    if (fl & 16) {  // own-element operands that are not staged: pull their lines into L1 behind the bulk copies
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (dsrc) prefetch_l1(dsrc + idx_of(r));
-            if (a.psi && !s_psi) prefetch_l1(a.psi + voff + idx_of(r));
-            if (a.b2 && !s_b2) prefetch_l1(a.b2 + voff + idx_of(r));
-            if (a.w_in && !s_w) prefetch_l1(a.w_in + voff + idx_of(r));
-        }
-    }
-    mbar_wait(&mbar, 0);
-
-    const int to_bit = a.to_bit;
-    const int jstart = __ffs(g.tile_flip_mask) - 1;
-    c2 v[R];
-    double pr[R], pi[R], qr[R], qi[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        v[r] = tile[tid + r * NT];
-        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
-    }
-    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
-    // flips of the bits above both tile geometries (large registers only): coalesced partner loads
-    for (unsigned long long em = g.extra_mask; em; em &= em - 1) {
-        const int p = __ffsll((long long)em) - 1;
-        double gx = 0.0, gyt = 0.0;
-        if (!UNIFORM) { gx = tab[2 * p]; gyt = tab[2 * p + 1]; }
-        const int bit = (int)((base >> p) & 1);
-        const double sg = (bit == to_bit) ? 1.0 : -1.0;
-        const double gy = (bit == to_bit) ? gyt : -gyt;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + voff + (idx_of(r) ^ (1LL << p))));
-            if (UNIFORM) {
-                pr[r] += raw.x; pi[r] += raw.y;
-                if (!REAL_G) { qr[r] = fma(sg, raw.x, qr[r]); qi[r] = fma(sg, raw.y, qi[r]); }
-            } else {
-                pr[r] = fma(gx, raw.x, pr[r]); pr[r] = fma(-gy, raw.y, pr[r]);
-                pi[r] = fma(gx, raw.y, pi[r]); pi[r] = fma(gy, raw.x, pi[r]);
-            }
-        }
-    }
-    // diagonal parameters
-    double w = 0.0, gamma = 0.0, th_common = 0.0;
-    double th_r[R];
-    if (UNIFORM) { w = a.u.w; gamma = a.u.gamma; }
-    else {
-        w = tab[3 * g.n_bits]; gamma = tab[3 * g.n_bits + 1];
-        for (int p = 0; p < g.n_bits; ++p) {
-            const int bit = (int)((fixed >> p) & 1);
-            th_common += (bit == a.from_is_one) ? tab[2 * g.n_bits + p] : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < RB; ++q) {
-                const int j = TBITS - RB + q;
-                const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
-                const double th = tab[2 * g.n_bits + p];
-                const int bit = (r >> q) & 1;
-                acc += ((bit == a.from_is_one) ? th : 0.0) - ((0 == a.from_is_one) ? th : 0.0);
-            }
-            th_r[r] = acc;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (UNIFORM) {
-            const double dx = a.u.g.x * pr[r], dy = a.u.g.x * pi[r];
-            if (!REAL_G) { pr[r] = fma(-a.u.g.y, qi[r], dx); pi[r] = fma(a.u.g.y, qr[r], dy); }
-            else { pr[r] = dx; pi[r] = dy; }
-        }
-    }
-    constexpr int H = (R >= 4) ? R / 2 : R;
-#pragma unroll
-    for (int h0 = 0; h0 < R; h0 += H) {
-        double dv[H];
-        c2 pv[H], bv[H], wv[H];
-#pragma unroll
-        for (int r = 0; r < H; ++r) {
-            const int rr = h0 + r;
-            const int t = tid + rr * NT;
-            dv[r] = dsrc ? __ldcs(dsrc + idx_of(rr)) : 0.0;
-            pv[r] = s_psi ? s_psi[t] : (a.psi ? ld_own<false>(a.psi + voff + idx_of(rr)) : c2{0.0, 0.0});
-            bv[r] = s_b2 ? s_b2[t] : (a.b2 ? ld_own<false>(a.b2 + voff + idx_of(rr)) : c2{0.0, 0.0});
-            wv[r] = s_w ? s_w[t] : (a.w_in ? ld_own<false>(a.w_in + voff + idx_of(rr)) : c2{0.0, 0.0});
-        }
-#pragma unroll
-        for (int r = 0; r < H; ++r) {
-            const int rr = h0 + r;
-            double diag = fma(w, dv[r], -gamma);
-            if (UNIFORM) {
-                const int ones = __popcll((unsigned long long)idx_of(rr));
-                const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
-                diag = fma(-a.u.theta, (double)cnt, diag);
-            } else {
-                diag -= th_common + th_r[rr];
-            }
-            const c2 gv = {fma(diag, v[rr].x, pr[rr] + wv[r].x), fma(diag, v[rr].y, pi[rr] + wv[r].y)};
-            c2 res = cmul(a.coef.c_g, gv);
-            res = cadd(res, cmul(a.coef.c_psi, pv[r]));
-            res = cadd(res, cmul(a.coef.c_b2, bv[r]));
-            st_c2(a.out + voff + idx_of(rr), res);
-            v[rr] = res;
-        }
-    }
-    if (a.w_out) {
-        if (rtile == tile) __syncthreads();  // every thread has finished gathering the input tile
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            rtile[tid + r * NT] = v[r];
-            pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
-        }
-        __syncthreads();
-        rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, rtile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            c2 wsum = {pr[r], pi[r]};
-            if (UNIFORM) {
-                wsum.x = a.u.g.x * pr[r]; wsum.y = a.u.g.x * pi[r];
-                if (!REAL_G) { wsum.x = fma(-a.u.g.y, qi[r], wsum.x); wsum.y = fma(a.u.g.y, qr[r], wsum.y); }
-            }
-            st_c2(a.w_out + voff + idx_of(r), wsum);
-        }
-    }
-}
-
-// ---- d = 2 single-pass stage kernel with TMA-streamed partner tiles ----------------------------------------------
-// Same maths as stage_d2_rb_kernel, but the partner tiles of the bits above the tile (contiguous 2^TBITS
-// amplitudes each) are brought in by bulk copies into a two-slot shared-memory ring, two tiles ahead, instead
-// of latency-exposed LDG.128: the L2 traffic is identical, its latency is hidden behind the in-tile gathers.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
-__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
-stage_d2_stream_kernel(const __grid_constant__ StageArgs2 m) {
-    constexpr int NT = 1 << (TBITS - RB);
-    constexpr int TSIZE = 1 << TBITS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    c2* tile = reinterpret_cast<c2*>(smem_raw);
-    c2* ring = tile + TSIZE;                                          // 2 slots
-    double* tab = reinterpret_cast<double*>(ring + 2 * (size_t)TSIZE);
-    __shared__ __align__(8) uint64_t mbar[3];
-
-    const int chain = blockIdx.y / m.n_traj;
-    const StageArgs& a = m.a[chain];
-    const PassGeom g = a.geo;  // single pass: lo_bits = TBITS, hi_bits = 0, extra_mask = all higher bits
-    const int tid = threadIdx.x;
-    const long long traj = blockIdx.y - chain * m.n_traj;
-    const long long base = tile_base_of(g, blockIdx.x);
-    const c2* vsrc = a.v + traj * a.D;
-
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); }
-    pdl_wait();
-    pdl_launch_dependents();
-    if (!UNIFORM) {
-        const int stride = d2_table_stride(g.n_bits);
-        const double* src = a.table + traj * stride;
-        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&mbar[0], (uint32_t)TSIZE * 16u);
-        tma_load_1d(tile, vsrc + base, (uint32_t)TSIZE * 16u, &mbar[0]);
-        unsigned long long em = (a.dbg & 2) ? 0ULL : g.extra_mask;
-        for (int e = 0; e < 2 && em; ++e, em &= em - 1) {
-            const int p = __ffsll((long long)em) - 1;
-            mbar_arrive_expect_tx(&mbar[1 + e], (uint32_t)TSIZE * 16u);
-            tma_load_1d(ring + (size_t)e * TSIZE, vsrc + (base ^ (1LL << p)), (uint32_t)TSIZE * 16u, &mbar[1 + e]);
-        }
-    }
-    mbar_wait(&mbar[0], 0);
-    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid, ring, &mbar[1]);
-}
-
-// ---- d = 2 tiled stage kernel, persistent with a TMA prefetch pipeline -----------
-// One CTA loops over work items (tile, trajectory) w = blockIdx.x + i*gridDim.x and keeps STAGES tiles in
-// flight: the bulk copies of item i+STAGES-1 are issued before item i is computed, so the L2/HBM latency
-// of a tile load overlaps the shared-memory phase of the previous one.
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB, int STAGES>
-__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
-stage_d2_pipe_kernel(StageArgs a, long long tiles_per_traj, long long n_items) {
-    constexpr int NT = 1 << (TBITS - RB);
-    constexpr int TSIZE = 1 << TBITS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    c2* tiles = reinterpret_cast<c2*>(smem_raw);
-    double* tab = reinterpret_cast<double*>(tiles + (size_t)STAGES * TSIZE);
-    __shared__ __align__(8) uint64_t mbar[STAGES];
-
-    const PassGeom g = a.geo;
-    const int tid = threadIdx.x;
-    if (tid == 0)
-        for (int s = 0; s < STAGES; ++s) mbar_init(&mbar[s], 1);
-    pdl_wait();
-    pdl_launch_dependents();
-    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
     const int rows = 1 << g.hi_bits;
     const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
-    auto issue = [&](long long w, int s) {
-        const long long traj = w / tiles_per_traj;
-        const long long base = tile_base_of(g, w - traj * tiles_per_traj);
-        const c2* vsrc = a.v + traj * a.D;
-        c2* dst = tiles + (size_t)s * TSIZE;
-        if (tid == 0) mbar_arrive_expect_tx(&mbar[s], (uint32_t)TSIZE * 16u);
-        for (int r = tid; r < rows; r += NT)
-            tma_load_1d(dst + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar[s]);
-    };
-    const long long w0 = blockIdx.x, dw = gridDim.x;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s)
-        if (w0 + s * dw < n_items) issue(w0 + s * dw, s);
-    long long tab_traj = -1;
-    int it = 0;
-    for (long long w = w0; w < n_items; w += dw, ++it) {
-        const int s = it % STAGES;
-        const long long wn = w + (long long)(STAGES - 1) * dw;
-        if (wn < n_items) issue(wn, (it + STAGES - 1) % STAGES);  // that stage was released by the barrier below
-        const long long traj = w / tiles_per_traj;
-        const long long base = tile_base_of(g, w - traj * tiles_per_traj);
-        if (!UNIFORM && traj != tab_traj) {
-            const int stride = d2_table_stride(g.n_bits);
-            const double* src = a.table + traj * stride;
-            for (int i = tid; i < stride; i += NT) tab[i] = src[i];
-            tab_traj = traj;
-            __syncthreads();
-        }
-        mbar_wait(&mbar[s], (uint32_t)((it / STAGES) & 1));
-        rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tiles + (size_t)s * TSIZE, tab, base, traj, tid);
-        __syncthreads();  // everyone is done with stage s (and with tab) before it is refilled
-    }
-}
-
-// ---- d = 2 cooperative persistent kernel: a whole program of Clenshaw stages in ONE launch ----------------------
-// All CTAs are co-resident (cooperative launch).  Every stage runs its tile passes (pass A: the low TBITS bits,
-// later passes: the high bits gathered by strided TMA rows, 88-120 B/amplitude through L2 instead of ~200 with
-// out-of-tile partner loads) separated by grid-wide barriers; the stage list (buffers, Clenshaw scalars, drive
-// parameters of up to two chains) is a table in global memory, so a sequence of exponentials costs one launch.
-struct CoopChain {
-    const c2* v; const c2* psi; const c2* b2; c2* out;
-    StageCoef coef; UniformDrive u; const double* table;
-};
-struct CoopStage {
-    CoopChain c[2];
-    int n_chains;
-    int pad;
-};
-struct CoopArgs {
-    const CoopStage* stages;
-    int n_stages;
-    int n_passes;
-    PassGeom geo[4];
-    const double* dint; long long dint_stride; long long D;
-    int n_traj; int to_bit; int from_is_one;
-    unsigned int* barrier;  // [0] arrivals, [1] generation
-};
-
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& gen) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int prev = atomicAdd(&bar[0], 1u);
-        if (prev == nblocks - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(&bar[1], 1u);
-        } else {
-            unsigned int cur;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
-            } while (cur == gen);
-        }
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-    }
-    ++gen;
-    __syncthreads();
-}
-
-template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
-__global__ void __launch_bounds__(1 << (TBITS - RB), 2) coop_program_kernel(const __grid_constant__ CoopArgs A) {
-    constexpr int NT = 1 << (TBITS - RB);
-    constexpr int TSIZE = 1 << TBITS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    c2* tiles = reinterpret_cast<c2*>(smem_raw);                       // 2 tile buffers
-    double* tab = reinterpret_cast<double*>(tiles + 2 * (size_t)TSIZE);  // per-bit table (non-uniform drives)
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ StageArgs sargs[2];
-    __shared__ long long sbase[2];
-    __shared__ long long straj[2];
-
-    const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-    __syncthreads();
-    unsigned int gen = 0;  // only thread 0's copy is compared in the barrier
-    if (tid == 0) gen = *reinterpret_cast<volatile unsigned int*>(A.barrier + 1);
-    unsigned int it = 0;  // tile tasks processed by this CTA so far (mbarrier parity bookkeeping)
-
-    for (int s = 0; s < A.n_stages; ++s) {
-        const CoopStage* stg = A.stages + s;
-        const int n_chains = stg->n_chains;
-        for (int pass = 0; pass < A.n_passes; ++pass) {
-            const PassGeom g = A.geo[pass];
-            const int tbits = g.lo_bits + g.hi_bits;
-            const long long tiles_per_traj = A.D >> tbits;
-            const long long per_chain = tiles_per_traj * A.n_traj;
-            const long long n_tasks = per_chain * n_chains;
-            const int rows = 1 << g.hi_bits;
-            const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
-            auto issue = [&](long long w, int slot) {
-                const int chain = (int)(w / per_chain);
-                const long long r1 = w - chain * per_chain;
-                const long long traj = r1 / tiles_per_traj;
-                const long long base = tile_base_of(g, r1 - traj * tiles_per_traj);
-                const CoopChain& cc = stg->c[chain];
-                if (tid == 0) {
-                    StageArgs& a = sargs[slot];
-                    a.v = cc.v; a.psi = cc.psi; a.b2 = cc.b2; a.out = cc.out;
-                    a.dint = A.dint; a.dint_stride = A.dint_stride; a.D = A.D;
-                    a.geo = g; a.coef = cc.coef; a.u = cc.u; a.table = cc.table;
-                    a.to_bit = A.to_bit; a.from_is_one = A.from_is_one;
-                    a.beta_dev = nullptr; a.dot_acc = nullptr; a.swz = 0; a.dbg = 0;
-                    sbase[slot] = base; straj[slot] = traj;
-                    mbar_arrive_expect_tx(&mbar[slot], (uint32_t)TSIZE * 16u);
-                }
-                const c2* vsrc = cc.v + traj * A.D;
-                c2* dst = tiles + (size_t)slot * TSIZE;
-                for (int r = tid; r < rows; r += NT)
-                    tma_load_1d(dst + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar[slot]);
-            };
-            long long w = blockIdx.x;
-            if (w < n_tasks) issue(w, it & 1);
-            long long tab_key = -1;
-            for (; w < n_tasks; w += gridDim.x, ++it) {
-                const int slot = it & 1;
-                const long long wn = w + gridDim.x;
-                if (wn < n_tasks) issue(wn, slot ^ 1);  // the other buffer was released by the barrier below
-                __syncthreads();                          // sargs / sbase of `slot` written by thread 0 are visible
-                const long long traj = straj[slot];
-                if (!UNIFORM) {
-                    const int chain = (int)(w / per_chain);
-                    const long long key = chain * (long long)A.n_traj + traj;
-                    if (key != tab_key) {
-                        const int stride = d2_table_stride(g.n_bits);
-                        const double* src = stg->c[chain].table + traj * stride;
-                        for (int i = tid; i < stride; i += NT) tab[i] = __ldcg(src + i);
-                        tab_key = key;
-                        __syncthreads();
-                    }
-                }
-                mbar_wait(&mbar[slot], (it >> 1) & 1u);
-                rb_tile_compute<UNIFORM, REAL_G, TBITS, RB, true>(sargs[slot], g, tiles + (size_t)slot * TSIZE, tab,
-                                                                   sbase[slot], traj, tid);
-                __syncthreads();
-            }
-            grid_barrier(A.barrier, gridDim.x, gen);
-        }
-    }
+    for (int r = tid; r < rows; r += NT)
+        tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+    mbar_wait(&mbar, 0);
+    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
 }
 
 // ---- generic-d stage kernel (any dim, several drives; global gathers) -------
@@ -1048,6 +623,8 @@ struct GenArgs {
     // XY mode with an SLM mask (hamiltonian.py:399-424): pairs touching a masked qudit (bit k of slm_mask) carry the
     // weight wc = table[stride - 3] instead of w; dint2 = interaction diagonal of those pairs (dint: the others)
     unsigned long long slm_mask; const double* dint2;
+    double* dot_acc;   // fused reductions (register-blocked tiled kernel only): acc[traj][0] += Re<lhs, out>, [1] += <out, out>
+    LanczosFuse lz;    // fused Lanczos step when lz.vj != nullptr (register-blocked tiled kernel only)
 };
 
 __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
@@ -1131,109 +708,6 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(GenArgs a) {
 // their partners are a short CTA-uniform list of (offset, coefficient) pairs served by coalesced loads.
 struct TileExtra { long long off; double gx, gy; };
 
-template <int DIM, int K>
-__global__ void __launch_bounds__(256) stage_tiled_kernel(GenArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ TileExtra extra[PB200_MAX_DRIVES_K * PB200_TILED_MAX_HIGH];
-    __shared__ int n_extra;
-    __shared__ double diag_high;
-
-    const int tid = threadIdx.x;
-    const long long traj = blockIdx.y;
-    const int n = a.n;
-    const int kk = n < K ? n : K;           // digits inside the tile
-    int tsz = 1;
-    for (int j = 0; j < kk; ++j) tsz *= DIM;
-    c2* tile = reinterpret_cast<c2*>(smem_raw);
-    double* tab = reinterpret_cast<double*>(smem_raw + (((size_t)tsz * 16 + 127) / 128) * 128);
-    const int stride = gen_table_stride(n, a.n_drives);
-    const long long base = (long long)blockIdx.x * tsz;
-    const long long voff = traj * a.D;
-
-    if (tid == 0) mbar_init(&mbar, 1);
-    for (int i = tid; i < stride; i += blockDim.x) tab[i] = a.table[traj * stride + i];
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&mbar, (uint32_t)tsz * 16u);
-        tma_load_1d(tile, a.v + voff + base, (uint32_t)tsz * 16u, &mbar);
-        // partners across the high digits (identical for every amplitude of the tile)
-        int cnt = 0;
-        double dh = 0.0;
-        long long rem = blockIdx.x, st = tsz;
-        for (int j = kk; j < n; ++j) {       // digit j counted from the least significant one: qudit n - 1 - j
-            const int digit = (int)(rem % DIM);
-            rem /= DIM;
-            const int k = n - 1 - j;
-            for (int q = 0; q < a.n_drives; ++q) {
-                const double* gq = tab + q * 3 * n;
-                if (digit == a.to[q]) {
-                    extra[cnt++] = {(long long)(a.from[q] - a.to[q]) * st, gq[2 * k], gq[2 * k + 1]};
-                } else if (digit == a.from[q]) {
-                    extra[cnt++] = {(long long)(a.to[q] - a.from[q]) * st, gq[2 * k], -gq[2 * k + 1]};
-                    dh -= gq[2 * n + k];
-                }
-            }
-            st *= DIM;
-        }
-        n_extra = cnt;
-        diag_high = dh;
-    }
-    __syncthreads();
-    mbar_wait(&mbar, 0);
-
-    const double w = tab[stride - 2], gamma = tab[stride - 1];
-    const c2 cb2 = a.beta_dev ? c2{-a.beta_dev[traj], 0.0} : a.coef.c_b2;
-    const int nex = n_extra;
-    const double dhigh = diag_high - gamma;
-    const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
-    for (int t = tid; t < tsz; t += blockDim.x) {
-        const long long idx = base + t;
-        // own-element operands first: their latency overlaps the shared-memory gathers
-        const double dv = dsrc ? __ldcs(dsrc + idx) : 0.0;
-        c2 pv0 = {0.0, 0.0}, bv0 = {0.0, 0.0};
-        if (a.psi) { const double2 r = __ldcs(reinterpret_cast<const double2*>(a.psi + voff + idx)); pv0 = {r.x, r.y}; }
-        if (a.b2) { const double2 r = __ldcs(reinterpret_cast<const double2*>(a.b2 + voff + idx)); bv0 = {r.x, r.y}; }
-        const c2 vo = tile[t];
-        double diag = dhigh, rr = 0.0, ri = 0.0;
-        int rem = t, st = 1;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (j < kk) {
-                const int digit = rem % DIM;
-                rem /= DIM;
-                const int k = n - 1 - j;
-                for (int q = 0; q < a.n_drives; ++q) {
-                    const double* gq = tab + q * 3 * n;
-                    const bool is_to = digit == a.to[q], is_from = digit == a.from[q];
-                    const int delta = is_to ? (a.from[q] - a.to[q]) : (is_from ? (a.to[q] - a.from[q]) : 0);
-                    const c2 pv = tile[t + delta * st];
-                    const double use = (is_to || is_from) ? 1.0 : 0.0;
-                    const double gx = gq[2 * k] * use;
-                    const double gy = is_to ? gq[2 * k + 1] : (is_from ? -gq[2 * k + 1] : 0.0);
-                    rr = fma(gx, pv.x, rr); rr = fma(-gy, pv.y, rr);
-                    ri = fma(gx, pv.y, ri); ri = fma(gy, pv.x, ri);
-                    diag -= is_from ? gq[2 * n + k] : 0.0;
-                }
-                st *= DIM;
-            }
-        }
-#pragma unroll 4
-        for (int e = 0; e < nex; ++e) {
-            const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + voff + idx + extra[e].off));
-            const double gx = extra[e].gx, gy = extra[e].gy;
-            rr = fma(gx, raw.x, rr); rr = fma(-gy, raw.y, rr);
-            ri = fma(gx, raw.y, ri); ri = fma(gy, raw.x, ri);
-        }
-        diag = fma(w, dv, diag);
-        const c2 gv = {fma(diag, vo.x, rr), fma(diag, vo.y, ri)};
-        c2 res = cmul(a.coef.c_g, gv);
-        res = cadd(res, cmul(a.coef.c_psi, pv0));
-        res = cadd(res, cmul(cb2, bv0));
-        st_c2(a.out + voff + idx, res);
-    }
-}
-
 // ---- register-blocked tiled stage kernel for d = 3 / 4 --------------------------------------------------------
 // stage_tiled_kernel is instruction-bound (ncu on C3: 1053 thread instructions per amplitude, issue-active 62 %,
 // DRAM 10 %: the digit decomposition, the coefficient selects and the table reads are redone for every amplitude).
@@ -1305,7 +779,11 @@ __global__ void __launch_bounds__(256, 2) stage_multilevel_rb_kernel(GenArgs a) 
     }
     __syncthreads();
     mbar_wait(&mbar, 0);
-    if (tid >= nt_act) return;
+    double dot0 = 0.0, dot1 = 0.0;
+    const bool fuse = a.lz.vj != nullptr;
+    LanczosCoef lc{0.0, 0.0, 0.0, 0.0};
+    if (fuse) lc = lanczos_coef(a.lz, traj);
+    if (tid < nt_act) {
 
     double rr[R], ri[R], dd[R];
 #pragma unroll
@@ -1392,8 +870,13 @@ __global__ void __launch_bounds__(256, 2) stage_multilevel_rb_kernel(GenArgs a) 
             const long long idx = base + tid + (long long)(h0 + r) * nt_act;
             dv[r] = dsrc ? __ldcs(dsrc + idx) : 0.0;
             pv[r] = {0.0, 0.0}; bv[r] = {0.0, 0.0};
-            if (a.psi) { const double2 t2 = __ldcs(reinterpret_cast<const double2*>(a.psi + voff + idx)); pv[r] = {t2.x, t2.y}; }
-            if (a.b2) { const double2 t2 = __ldcs(reinterpret_cast<const double2*>(a.b2 + voff + idx)); bv[r] = {t2.x, t2.y}; }
+            if (fuse) {
+                pv[r] = ld_own(a.lz.vj + voff + idx);
+                if (a.lz.vjm1 && lc.beta_prev != 0.0) bv[r] = ld_own(a.lz.vjm1 + voff + idx);
+            } else {
+                if (a.psi) pv[r] = ld_own(a.psi + voff + idx);
+                if (a.b2) bv[r] = ld_own(a.b2 + voff + idx);
+            }
         }
 #pragma unroll
         for (int r = 0; r < H; ++r) {
@@ -1402,11 +885,47 @@ __global__ void __launch_bounds__(256, 2) stage_multilevel_rb_kernel(GenArgs a) 
             const c2 vo = tile[tid + i * nt_act];
             const double diag = fma(w, dv[r], dcommon + dd[i]);
             const c2 gv = {fma(diag, vo.x, rr[i]), fma(diag, vo.y, ri[i])};
-            c2 res = cmul(a.coef.c_g, gv);
-            res = cadd(res, cmul(a.coef.c_psi, pv[r]));
-            res = cadd(res, cmul(cb2, bv[r]));
+            c2 res, lhs;
+            if (fuse) {   // fused Lanczos step (see LanczosFuse)
+                const c2 vn = {(vo.x - lc.alpha * pv[r].x) * lc.inv, (vo.y - lc.alpha * pv[r].y) * lc.inv};
+                const double ai = lc.alpha * lc.inv, abi = ai * lc.beta_prev;
+                res.x = fma(lc.inv, gv.x, -fma(ai, vo.x, fma(abi, bv[r].x, lc.beta * pv[r].x)));
+                res.y = fma(lc.inv, gv.y, -fma(ai, vo.y, fma(abi, bv[r].y, lc.beta * pv[r].y)));
+                st_c2(a.lz.vout + voff + idx, vn);
+                lhs = vn;
+            } else {
+                res = cmul(a.coef.c_g, gv);
+                res = cadd(res, cmul(a.coef.c_psi, pv[r]));
+                res = cadd(res, cmul(cb2, bv[r]));
+                lhs = vo;
+            }
+            dot0 = fma(lhs.x, res.x, dot0); dot0 = fma(lhs.y, res.y, dot0);
+            dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
             st_c2(a.out + voff + idx, res);
         }
+    }
+    }  // active threads
+    if (a.dot_acc) {  // fused Lanczos inner products: warp __shfl reduction, one atomic pair per CTA
+        for (int o = 16; o > 0; o >>= 1) {
+            dot0 += __shfl_xor_sync(0xffffffffu, dot0, o);
+            dot1 += __shfl_xor_sync(0xffffffffu, dot1, o);
+        }
+        __shared__ double dred[2][8];
+        if ((tid & 31) == 0) { dred[0][tid >> 5] = dot0; dred[1][tid >> 5] = dot1; }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0 += dred[0][i]; s1 += dred[1][i]; }
+            atomicAdd(a.dot_acc + 2 * traj, s0);
+            atomicAdd(a.dot_acc + 2 * traj + 1, s1);
+        }
+    }
+    if (fuse && blockIdx.x == 0 && tid == 0) {
+        a.lz.alpha_out[traj] = lc.alpha;
+        a.lz.beta_out[traj] = lc.beta;
+        a.lz.acc_clear[2 * traj] = 0.0;
+        a.lz.acc_clear[2 * traj + 1] = 0.0;
     }
 }
 

@@ -11,6 +11,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <cmath>
 #include <complex>
 #include <cstdarg>
@@ -65,9 +68,95 @@ struct EventPair {
     EventPair& operator=(const EventPair&) = delete;
 };
 
+#define PB200_MAX_DEVICES 64
+
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
+}
+
+// ---- process-wide pool of device buffers ------------------------------------------------------------------
+// A caller that builds one plan per Sequence (QutipEmulator.from_sequence(...).run(), bench.py's end-to-end leg,
+// one plan per trajectory batch) would otherwise pay cudaMalloc / cudaFree (a device synchronisation each) for
+// ~10 state-sized buffers per plan.  Freed buffers are kept per device, keyed by size, up to PB200_POOL_MIB
+// (default 16 GiB); a plan synchronises its stream before returning buffers, so reuse by another plan is safe.
+struct DevicePool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_list[PB200_MAX_DEVICES];
+    std::unordered_map<void*, size_t> size_of;
+    size_t held[PB200_MAX_DEVICES] = {0};
+};
+static DevicePool& pool() { static DevicePool* p = new DevicePool(); return *p; }  // never destroyed (CUDA teardown order)
+
+static void* pool_alloc(int dev, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    DevicePool& pl = pool();
+    if (dev >= 0 && dev < PB200_MAX_DEVICES) {
+        std::lock_guard<std::mutex> lk(pl.mu);
+        auto it = pl.free_list[dev].lower_bound(bytes);
+        if (it != pl.free_list[dev].end() && it->first <= bytes + bytes / 4) {
+            void* p = it->second;
+            pl.held[dev] -= it->first;
+            pl.free_list[dev].erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {  // give the cached buffers back to the driver and retry once
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(pl.mu);
+            if (dev >= 0 && dev < PB200_MAX_DEVICES) {
+                for (auto& kv : pl.free_list[dev]) { pl.size_of.erase(kv.second); cudaFree(kv.second); }
+                pl.free_list[dev].clear(); pl.held[dev] = 0;
+            }
+        }
+        CUDA_CHECK(cudaMalloc(&p, bytes));
+    }
+    std::lock_guard<std::mutex> lk(pl.mu);
+    pl.size_of[p] = bytes;
+    return p;
+}
+
+static void pool_free(int dev, void* p) {
+    if (!p) return;
+    DevicePool& pl = pool();
+    static const size_t cap = (size_t)std::max(0, env_int("PB200_POOL_MIB", 16384)) << 20;
+    {
+        std::lock_guard<std::mutex> lk(pl.mu);
+        auto it = pl.size_of.find(p);
+        if (it != pl.size_of.end() && dev >= 0 && dev < PB200_MAX_DEVICES && pl.held[dev] + it->second <= cap) {
+            pl.free_list[dev].emplace(it->second, p);
+            pl.held[dev] += it->second;
+            return;
+        }
+        if (it != pl.size_of.end()) pl.size_of.erase(it);
+    }
+    cudaFree(p);
+}
+
+// once per device and process: SM count, > 48 KB of dynamic shared memory for the tile kernels
+static int device_setup(int dev) {
+    static std::mutex mu;
+    static int sm_count[PB200_MAX_DEVICES] = {0};
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < PB200_MAX_DEVICES && sm_count[dev] > 0) return sm_count[dev];
+    int sms = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int max_smem = (1 << 13) * 16 + 1024;
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define PB200_RB_ATTR(TB, RB)                                                                                                            \
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));   \
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));  \
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_RB_ATTR(11, 2) PB200_RB_ATTR(11, 3) PB200_RB_ATTR(12, 2) PB200_RB_ATTR(12, 3)
+#undef PB200_RB_ATTR
+    if (dev >= 0 && dev < PB200_MAX_DEVICES) sm_count[dev] = sms;
+    return sms;
 }
 
 struct DriveTables {  // one (trajectory, drive): rows x interpolants
@@ -106,18 +195,7 @@ struct Plan {
     int sm_count = 148;
     bool force_v1 = false;
     int reg_bits = 3;
-    bool use_pipe = false;
     bool use_dual = true;
-    bool use_coop = true;
-    bool use_stream = false;
-    bool coop_now = false;                 // decided per propagate call
-    std::vector<PassGeom> coop_passes;
-    CoopStage* d_coop = nullptr; size_t d_coop_cap = 0;
-    unsigned int* d_bar = nullptr;
-    int coop_slots[3] = {0, 0, 0};  // co-resident CTAs of the 3 template variants (0 = not queried)
-    int dbg = 0;
-    bool swizzle = false;
-    int swizzle_min_bits = 12;
     // Lindblad: per-qudit generators of the dissipator on the (row, column) digit pair
     std::vector<std::vector<cplx>> diss_gen;
     // Krylov (Lanczos) propagator workspace
@@ -143,15 +221,8 @@ struct Plan {
     std::vector<double> thresholds;               // per trajectory
     std::vector<long long> jump_count;
     bool use_pdl = true;
-    // partner-sum forwarding between Clenshaw stages (kernels.cuh, FWD): geometry of the first stage of an
-    // exponential [0], of the odd stages [1] (high-bit tile) and of the later even stages [2]
-    int use_fwd = 0;                // PB200_FWD: 1 on (experiment, slower than the single-pass stages)
-    bool fwd_now = false;           // decided per propagate call
-    PassGeom fwd_geo[3];
-    c2* wbuf[2] = {nullptr, nullptr};  // forwarded sums, one vector per chain
-    int fwd_flags = 0;              // PB200_FWD_FLAGS: operand staging switches of stage_d2_fwd_kernel
-    int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 2 plain tiled kernel, 0 generic
-    int tiled_k = 0;                // PB200_TILED_K: digits per tile (d = 3: 6..8, default 7; d = 4: 4..6, default 5)
+    bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
+    int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
         for (int q = 0; q < n_drives; ++q)
             if (!desc.drives[q].uniform) return false;
@@ -241,8 +312,7 @@ struct StageIO {  // one Clenshaw stage of one chain
     StageCoef coef; UniformDrive ud; const double* table; bool real_g;
     const double* beta_dev = nullptr;
     double* dot_acc = nullptr;  // fused <v,out>, <out,out> (only honoured by the register-blocked d=2 kernels)
-    // partner-sum forwarding: stage index inside its exponential and whether another stage follows
-    int stage_idx = 0; bool has_next = false; c2* wbuf = nullptr;
+    const LanczosFuse* lz = nullptr;  // fused Lanczos step (single-pass register-blocked geometry only)
 };
 
 static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io, bool geo_is_last = true) {
@@ -253,15 +323,16 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.D = P.D; a.geo = geo; a.coef = io.coef; a.u = io.ud; a.table = io.table;
     a.to_bit = P.desc.drives[0].state_to;
     a.from_is_one = P.desc.drives[0].state_from;
-    a.dbg = P.dbg;
-    {
-        const int tb = geo.lo_bits + geo.hi_bits;
-        const int idbits = P.n - tb;
-        a.swz = (P.swizzle && idbits >= P.swizzle_min_bits && idbits <= 31) ? idbits : 0;
-    }
     a.beta_dev = io.beta_dev;
     a.dot_acc = (geo_is_last ? io.dot_acc : nullptr);
+    if (geo_is_last && io.lz) a.lz = *io.lz;
     return a;
+}
+
+// d = 3 / 4 registers without an exchange term run on the register-blocked tiled kernel
+static bool multilevel_eligible(const Plan& P) {
+    return P.use_tiled == 1 && !P.has_xy && (P.dim == 3 || P.dim == 4) && P.n <= PB200_TILED_MAX_HIGH &&
+           P.n >= (P.dim == 3 ? 2 : 1) && !(P.dim == 2);
 }
 
 static bool rb_eligible(const Plan& P, const PassGeom& geo) {
@@ -294,41 +365,7 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             const int RBv = P.reg_bits;
             if (rb_eligible(P, geo)) {
                 const int threads = tsize >> RBv;
-                const long long n_items = tiles * (long long)P.B;
-                const long long slots = (long long)P.sm_count * ((tbits == 11) ? 2 : 1);
-                const bool pipe = P.use_pipe && n == 1 && n_items > slots;
-                if (pipe) {
-                    StageArgs a = make_stage_args(P, geo, io[0]);
-                    const int stages = (tbits == 11) ? 3 : 2;
-                    const size_t smem = (size_t)stages * tsize * 16 + tab_bytes;
-                    dim3 pgrid((unsigned)slots);
-#define PB200_LAUNCH_PIPE(TB, RB, ST)                                                                          \
-    do {                                                                                                       \
-        if (uniform) {                                                                                         \
-            if (real_g) launch_k(stage_d2_pipe_kernel<true, true, TB, RB, ST>, pgrid, dim3(threads), smem, P.stream, P.use_pdl, a, tiles, n_items);  \
-            else launch_k(stage_d2_pipe_kernel<true, false, TB, RB, ST>, pgrid, dim3(threads), smem, P.stream, P.use_pdl, a, tiles, n_items);        \
-        } else {                                                                                               \
-            launch_k(stage_d2_pipe_kernel<false, false, TB, RB, ST>, pgrid, dim3(threads), smem, P.stream, P.use_pdl, a, tiles, n_items);            \
-        }                                                                                                      \
-    } while (0)
-                    if (tbits == 11) { if (RBv == 3) PB200_LAUNCH_PIPE(11, 3, 3); else PB200_LAUNCH_PIPE(11, 2, 3); }
-                    else { if (RBv == 3) PB200_LAUNCH_PIPE(12, 3, 2); else PB200_LAUNCH_PIPE(12, 2, 2); }
-#undef PB200_LAUNCH_PIPE
-                    ++launches;
-                } else if (P.use_stream && tbits == 11 && RBv == 3 && geo.hi_bits == 0 && geo.extra_mask != 0) {
-                    StageArgs2 m{};
-                    for (int c = 0; c < n; ++c) m.a[c] = make_stage_args(P, geo, io[c], last_pass);
-                    m.n_traj = P.B;
-                    dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
-                    const size_t smem = (size_t)3 * tsize * 16 + tab_bytes;
-                    if (uniform) {
-                        if (real_g) launch_k(stage_d2_stream_kernel<true, true, 11, 3>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);
-                        else launch_k(stage_d2_stream_kernel<true, false, 11, 3>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);
-                    } else {
-                        launch_k(stage_d2_stream_kernel<false, false, 11, 3>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);
-                    }
-                    ++launches;
-                } else {
+                {
                     StageArgs2 m{};
                     for (int c = 0; c < n; ++c) m.a[c] = make_stage_args(P, geo, io[c], last_pass);
                     m.n_traj = P.B;
@@ -377,8 +414,9 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             a.xy_u = P.xy_u; a.xy_d = P.xy_d;
             a.slm_mask = P.has_slm ? P.slm_bits : 0ULL; a.dint2 = (P.has_slm && P.has_interaction) ? P.dint2 : nullptr;
             int threads = 256;
-            if (P.use_tiled == 1 && !P.has_xy && (P.dim == 3 || P.dim == 4) && N <= PB200_TILED_MAX_HIGH &&
-                N >= (P.dim == 3 ? 2 : 1)) {
+            if (multilevel_eligible(P)) {
+                a.dot_acc = io[c].dot_acc;
+                if (io[c].lz) a.lz = *io[c].lz;
                 // register-blocked tiled kernel: 3^7 (9 amplitudes per thread) / 4^5 (4 per thread) amplitudes per CTA
                 const int K = (P.dim == 3) ? 7 : 5;
                 long long tsz = 1;
@@ -390,26 +428,6 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
                 ++launches;
                 continue;
             }
-            if (P.use_tiled && !P.has_xy && (P.dim == 3 || P.dim == 4) && N <= PB200_TILED_MAX_HIGH) {
-                // tiled kernel: one CTA per run of dim^K amplitudes (K low digits in shared memory)
-                const int Kdef = (P.dim == 3) ? 7 : 5;
-                const int K = std::min(Kdef + 1, std::max(Kdef - 1, P.tiled_k ? P.tiled_k : Kdef));
-                long long tsz = 1;
-                for (int j = 0; j < std::min(K, N); ++j) tsz *= P.dim;
-                dim3 tgrid((unsigned)(P.D / tsz), (unsigned)P.B);
-                const size_t tsmem = (((size_t)tsz * 16 + 127) / 128) * 128 + (size_t)gen_table_stride(N, P.n_drives) * 8;
-                if (P.dim == 3) {
-                    if (K == 8) stage_tiled_kernel<3, 8><<<tgrid, threads, tsmem, P.stream>>>(a);
-                    else if (K == 7) stage_tiled_kernel<3, 7><<<tgrid, threads, tsmem, P.stream>>>(a);
-                    else stage_tiled_kernel<3, 6><<<tgrid, threads, tsmem, P.stream>>>(a);
-                } else {
-                    if (K == 6) stage_tiled_kernel<4, 6><<<tgrid, threads, tsmem, P.stream>>>(a);
-                    else if (K == 5) stage_tiled_kernel<4, 5><<<tgrid, threads, tsmem, P.stream>>>(a);
-                    else stage_tiled_kernel<4, 4><<<tgrid, threads, tsmem, P.stream>>>(a);
-                }
-                ++launches;
-                continue;
-            }
             long long blocks = std::min<long long>((P.D + threads - 1) / threads, (long long)P.sm_count * 8);
             dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
             size_t smem = (size_t)gen_table_stride(N, P.n_drives) * 8 + (P.has_xy ? (size_t)N * N * 8 : 0);
@@ -417,88 +435,6 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             ++launches;
         }
     }
-}
-
-// ---- partner-sum forwarding ------------------------------------------------------------------------------------
-// Inside one exponential the Clenshaw stages alternate between two tile geometries whose flip sets are
-// complementary: A = the low TB bits, B = the hb bits above them (plus TB - hb low bits that only fill the tile).
-// A stage gathers its own tile's flips from shared memory, receives the complementary sums from the stage that
-// produced its input (w_in) and emits the sums of its result over its own flips (w_out): no out-of-tile partner
-// loads at all (the 9 x 16 B per amplitude that bound the single-pass kernel at the L2 -> SM limit become
-// 2 x 16 B of streaming traffic).  Bits above TB + hb, if any, stay global partner loads; the first stage of an
-// exponential has no producer and is the ordinary single-pass stage (it only emits).
-static bool fwd_eligible(const Plan& P, const std::vector<PassGeom>& passes) {
-    if (!is_d2path(P) || P.force_v1 || P.use_pipe || P.use_stream) return false;
-    if (P.tile_bits != 11 && P.tile_bits != 12) return false;
-    if (passes.size() != 1 || passes[0].hi_bits != 0 || passes[0].lo_bits != P.tile_bits) return false;
-    if (P.n - P.tile_bits < P.reg_bits) return false;  // the register block of the B tile must consist of flipped bits
-    if ((long long)P.B * 2 > 65535) return false;
-    // operand staging must fit the 227 KB of an SM
-    const int extra = ((P.fwd_flags & 1) ? 1 : 0) + ((P.fwd_flags & 2) ? 1 : 0) + ((P.fwd_flags & 4) ? 1 : 0) +
-                      ((P.fwd_flags & 8) ? 1 : 0);
-    if ((size_t)(1 + extra) * ((size_t)16 << P.tile_bits) + (size_t)d2_table_stride(P.n) * 8 > (size_t)200 * 1024) return false;
-    // measured slower than the single-pass stages on B200: an experiment, off unless asked for
-    return P.use_fwd > 0;
-}
-
-static void plan_fwd_geometry(Plan& P) {
-    const int N = P.n, TB = P.tile_bits;
-    const int hb = std::min(N - TB, TB - 2);
-    const unsigned long long all = (N >= 64) ? ~0ULL : ((1ULL << N) - 1ULL);
-    const unsigned long long rest = all & ~((1ULL << (TB + hb)) - 1ULL);
-    PassGeom a{};
-    a.n_bits = N; a.lo_bits = TB; a.hi_shift = TB; a.hi_bits = 0; a.first_pass = 1;
-    a.tile_flip_mask = (1u << TB) - 1u;
-    a.extra_mask = all & ~((1ULL << TB) - 1ULL);
-    P.fwd_geo[0] = a;
-    a.extra_mask = rest;
-    P.fwd_geo[2] = a;
-    PassGeom b{};
-    b.n_bits = N; b.lo_bits = TB - hb; b.hi_shift = TB; b.hi_bits = hb; b.first_pass = 1;
-    b.tile_flip_mask = ((1u << hb) - 1u) << b.lo_bits;
-    b.extra_mask = rest;
-    P.fwd_geo[1] = b;
-}
-
-static void launch_stage_fwd(Plan& P, const StageIO* io, int n, bool uniform, long long& launches) {
-    bool real_g = true;
-    for (int c = 0; c < n; ++c) real_g = real_g && io[c].real_g;
-    const int tbits = P.tile_bits;
-    const long long tiles = P.D >> tbits;
-    const int tsize = 1 << tbits;
-    const size_t tab_bytes = uniform ? 0 : (size_t)d2_table_stride(P.n) * 8;
-    StageArgs2 m{};
-    int extra_tiles = 0;
-    for (int c = 0; c < n; ++c) {
-        const int role = (io[c].stage_idx == 0) ? 0 : ((io[c].stage_idx & 1) ? 1 : 2);
-        StageArgs& a = m.a[c];
-        a = make_stage_args(P, P.fwd_geo[role], io[c], true);
-        a.swz = 0;
-        a.w_in = (io[c].stage_idx > 0) ? io[c].wbuf : nullptr;
-        a.w_out = io[c].has_next ? io[c].wbuf : nullptr;
-        a.fwd_flags = P.fwd_flags;
-        if (!a.w_out) a.fwd_flags &= ~8;
-        const int t = (((a.fwd_flags & 1) && a.w_in) ? 1 : 0) + (((a.fwd_flags & 2) && a.b2) ? 1 : 0) +
-                      (((a.fwd_flags & 4) && a.psi) ? 1 : 0) + ((a.fwd_flags & 8) ? 1 : 0);
-        extra_tiles = std::max(extra_tiles, t);
-    }
-    m.n_traj = P.B;
-    dim3 grid((unsigned)tiles, (unsigned)(P.B * n));
-    const int threads = tsize >> P.reg_bits;
-    const size_t smem = (size_t)(1 + extra_tiles) * tsize * 16 + tab_bytes;
-#define PB200_LAUNCH_FWD(TB, RB)                                                                               \
-    do {                                                                                                       \
-        if (uniform) {                                                                                         \
-            if (real_g) launch_k(stage_d2_fwd_kernel<true, true, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);   \
-            else launch_k(stage_d2_fwd_kernel<true, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);         \
-        } else {                                                                                               \
-            launch_k(stage_d2_fwd_kernel<false, false, TB, RB>, grid, dim3(threads), smem, P.stream, P.use_pdl, m);             \
-        }                                                                                                      \
-    } while (0)
-    if (tbits == 11) { if (P.reg_bits == 3) PB200_LAUNCH_FWD(11, 3); else PB200_LAUNCH_FWD(11, 2); }
-    else { if (P.reg_bits == 3) PB200_LAUNCH_FWD(12, 3); else PB200_LAUNCH_FWD(12, 2); }
-#undef PB200_LAUNCH_FWD
-    ++launches;
 }
 
 static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
@@ -611,10 +547,10 @@ struct Program {  // a batch of exponentials prepared on the host
 
 static void ensure_table_capacity(Plan& P, size_t doubles) {
     if (doubles <= P.d_table_cap) return;
-    if (P.d_table) CUDA_CHECK(cudaFree(P.d_table));
+    if (P.d_table) { CUDA_CHECK(cudaStreamSynchronize(P.stream)); pool_free(P.desc.device, P.d_table); }
     P.d_table = nullptr;
     size_t cap = std::max(doubles, (size_t)1 << 16);
-    CUDA_CHECK(cudaMalloc(&P.d_table, cap * sizeof(double)));
+    P.d_table = (decltype(P.d_table))pool_alloc(P.desc.device, cap * sizeof(double));
     P.d_table_cap = cap;
 }
 
@@ -665,7 +601,6 @@ struct Chain {
         io.ud = prog->ud[e];
         io.table = uniform ? nullptr : P.d_table + table_base + prog->offset[e];
         io.real_g = prog->real_g[e] != 0;
-        io.stage_idx = (int)a.size() - 2 - j; io.has_next = (j > 0);
         // shift the recurrence
         if (b1_buf == psi) { b2_kind = 2; kappa = b1_scale; b2_buf = nullptr; }
         else { b2_kind = 1; b2_buf = const_cast<c2*>(b1_buf); }
@@ -700,9 +635,6 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
     }
     long long launches = 0;
     StageIO io[2];
-    if (P.fwd_now)
-        for (int c = 0; c < n; ++c)
-            if (!P.wbuf[c]) CUDA_CHECK(cudaMalloc(&P.wbuf[c], sizeof(c2) * (size_t)P.D * P.B));
     if (P.has_diss && n != 1) fail(PB200_ERR_STATE, "internal: Lindblad splitting runs one chain at a time");
     while (true) {
         int k = 0;
@@ -714,106 +646,15 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
                     if (chains[c].j < 0 && chains[c].prog->pre_diss[e_before] > 0.0)
                         apply_dissipator(P, chains[c].psi, chains[c].prog->pre_diss[e_before], launches);
                 }
-                io[k].wbuf = P.wbuf[c];
                 chains[c].next(P, uniform, io[k++]);
             }
         if (k == 0) break;
-        if (P.fwd_now) launch_stage_fwd(P, io, k, uniform, launches);
-        else launch_stage_multi(P, passes, io, k, uniform, launches);
+        launch_stage_multi(P, passes, io, k, uniform, launches);
         if (P.has_diss && chains[0].e != e_before && chains[0].prog->post_diss[e_before] > 0.0)
             apply_dissipator(P, chains[0].psi, chains[0].prog->post_diss[e_before], launches);
     }
     CUDA_CHECK(cudaGetLastError());
     st.n_launches += launches;
-    for (int c = 0; c < n; ++c) {
-        st.n_applies += chains[c].applies;
-        st.max_rho = std::max(st.max_rho, chains[c].max_rho);
-        st.n_exponentials += (long long)chains[c].prog->cheb.size();
-    }
-}
-
-// ---- cooperative persistent execution of whole programs ---------------------------------------------------------
-static bool coop_eligible(const Plan& P, const std::vector<PassGeom>& cpasses) {
-    if (!P.use_coop || !is_d2path(P) || P.has_diss || P.use_krylov || P.force_v1) return false;
-    if (P.reg_bits != 3 || cpasses.size() > 4) return false;
-    if ((double)P.D * P.B * 16.0 > (double)env_int("PB200_COOP_MIB", 72) * 1048576.0) return false;  // L2-resident only
-    if (P.n < 14) return false;
-    for (const PassGeom& g : cpasses) {
-        if (g.lo_bits + g.hi_bits != 11) return false;
-        if (!g.first_pass && g.hi_bits < 3) return false;
-    }
-    return true;
-}
-
-static void run_chains_coop(Plan& P, Chain* chains, int n, const std::vector<PassGeom>& cpasses, pb200_run_stats& st) {
-    const bool uniform = P.all_uniform() && P.B == 1;
-    if (!uniform) {
-        size_t total = 0;
-        for (int c = 0; c < n; ++c) { chains[c].table_base = total; total += chains[c].prog->tables.size(); }
-        ensure_table_capacity(P, total);
-        for (int c = 0; c < n; ++c)
-            if (!chains[c].prog->tables.empty())
-                CUDA_CHECK(cudaMemcpyAsync(P.d_table + chains[c].table_base, chains[c].prog->tables.data(),
-                                           chains[c].prog->tables.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                           P.stream));
-    }
-    // unroll the chains into the stage table
-    std::vector<CoopStage> table;
-    bool real_g = true;
-    while (true) {
-        CoopStage cs{};
-        int k = 0;
-        for (int c = 0; c < n; ++c)
-            if (!chains[c].done()) {
-                StageIO io{};
-                chains[c].next(P, uniform, io);
-                CoopChain& cc = cs.c[k++];
-                cc.v = io.v; cc.psi = io.psi; cc.b2 = io.b2; cc.out = io.out;
-                cc.coef = io.coef; cc.u = io.ud; cc.table = io.table;
-                real_g = real_g && io.real_g;
-            }
-        if (k == 0) break;
-        cs.n_chains = k;
-        table.push_back(cs);
-    }
-    if (table.empty()) return;
-    if (table.size() > P.d_coop_cap) {
-        if (P.d_coop) CUDA_CHECK(cudaFree(P.d_coop));
-        P.d_coop = nullptr;
-        P.d_coop_cap = std::max(table.size(), (size_t)4096);
-        CUDA_CHECK(cudaMalloc(&P.d_coop, sizeof(CoopStage) * P.d_coop_cap));
-    }
-    if (!P.d_bar) {
-        CUDA_CHECK(cudaMalloc(&P.d_bar, 2 * sizeof(unsigned int)));
-        CUDA_CHECK(cudaMemsetAsync(P.d_bar, 0, 2 * sizeof(unsigned int), P.stream));
-    }
-    CUDA_CHECK(cudaMemcpyAsync(P.d_coop, table.data(), sizeof(CoopStage) * table.size(), cudaMemcpyHostToDevice, P.stream));
-    CoopArgs A{};
-    A.stages = P.d_coop; A.n_stages = (int)table.size(); A.n_passes = (int)cpasses.size();
-    for (size_t i = 0; i < cpasses.size(); ++i) A.geo[i] = cpasses[i];
-    A.dint = P.has_interaction ? P.dint : nullptr;
-    A.dint_stride = P.dint_shared ? 0 : P.D;
-    A.D = P.D; A.n_traj = P.B;
-    A.to_bit = P.desc.drives[0].state_to; A.from_is_one = P.desc.drives[0].state_from;
-    A.barrier = P.d_bar;
-    const int threads = 256;
-    const size_t smem = (size_t)2 * 2048 * 16 + (uniform ? 0 : (size_t)d2_table_stride(P.n) * 8);
-    void* fn = uniform ? (real_g ? (void*)coop_program_kernel<true, true, 11, 3> : (void*)coop_program_kernel<true, false, 11, 3>)
-                       : (void*)coop_program_kernel<false, false, 11, 3>;
-    const int variant = uniform ? (real_g ? 0 : 1) : 2;
-    if (P.coop_slots[variant] == 0) {
-        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 2048 * 16 + 1024)));
-        int per_sm = 0;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
-        if (per_sm < 1) fail(PB200_ERR_CUDA, "cooperative kernel does not fit on an SM");
-        P.coop_slots[variant] = per_sm * P.sm_count;
-    }
-    const long long max_tasks = (P.D >> 11) * (long long)P.B * 2;
-    const int grid = (int)std::min<long long>(P.coop_slots[variant], std::max<long long>(max_tasks, 1));
-    void* kargs[] = {(void*)&A};
-    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, P.stream));
-    CUDA_CHECK(cudaStreamSynchronize(P.stream));  // the host-side stage / coefficient tables are reused next
-    st.n_launches += 1;
     for (int c = 0; c < n; ++c) {
         st.n_applies += chains[c].applies;
         st.max_rho = std::max(st.max_rho, chains[c].max_rho);
@@ -879,27 +720,41 @@ static std::vector<cplx> tridiag_exp_e1(const double* alpha, const double* beta,
 
 static void ensure_krylov(Plan& P, int m_cap) {
     if (P.kry && P.kry_cap >= m_cap) return;
-    if (P.kry) { CUDA_CHECK(cudaFree(P.kry)); P.kry = nullptr; }
-    if (P.d_kry) { CUDA_CHECK(cudaFree(P.d_kry)); P.d_kry = nullptr; }
-    CUDA_CHECK(cudaMalloc(&P.kry, sizeof(c2) * (size_t)P.D * P.B * (m_cap + 1)));
-    const size_t nd = (size_t)m_cap * P.B * 2 + (size_t)4 * P.B + P.B + (size_t)P.B * m_cap * 2;
-    CUDA_CHECK(cudaMalloc(&P.d_kry, sizeof(double) * nd));
+    if (P.kry || P.d_kry) CUDA_CHECK(cudaStreamSynchronize(P.stream));
+    if (P.kry) { pool_free(P.desc.device, P.kry); P.kry = nullptr; }
+    if (P.d_kry) { pool_free(P.desc.device, P.d_kry); P.d_kry = nullptr; }
+    // basis vectors V_0 .. V_{m_cap} and the two raw vectors of the fused recurrence
+    P.kry = (c2*)pool_alloc(P.desc.device, sizeof(c2) * (size_t)P.D * P.B * (m_cap + 3));
+    const size_t nd = (size_t)m_cap * P.B * 2 + (size_t)6 * P.B + P.B + (size_t)P.B * m_cap * 2;
+    P.d_kry = (double*)pool_alloc(P.desc.device, sizeof(double) * nd);
     P.kry_cap = m_cap;
+}
+
+// Largest Krylov dimension whose workspace fits: a third of the free device memory
+static int krylov_capacity(const Plan& P) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 64; }
+    const double per_vec = (double)sizeof(c2) * (double)P.D * P.B;
+    const int fit = (int)std::floor((double)free_b / 3.0 / per_vec) - 3;
+    return std::max(8, std::min(64, fit));
 }
 
 // psi <- exp(-iG) psi by the Lanczos process: orthonormal basis V_0..V_{m-1} of the Krylov space of (G, psi),
 // exponential of the m x m tridiagonal on the host, a-posteriori error estimate beta_{m-1} |y_{m-1}|.
+// On the register-blocked kernels every iteration is ONE launch: the stage computes the raw vector
+// r_j = G v_j - beta_{j-1} v_{j-1} with its two inner products fused, and the normalisation / orthogonalisation
+// of v_{j+1} is folded into the own-element operands of the next stage (LanczosFuse, kernels.cuh).
 static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const std::vector<PassGeom>& passes,
                                pb200_run_stats& st) {
-    const int M = 64;
-    ensure_krylov(P, M);
+    if (P.kry_cap == 0) ensure_krylov(P, krylov_capacity(P));
+    const int M = P.kry_cap;
     const int B = P.B;
     const long long D = P.D;
     const long long vstride = D * (long long)B;
     double* d_alpha = P.d_kry;
     double* d_beta = d_alpha + (size_t)M * B;
-    double* d_acc = d_beta + (size_t)M * B;   // [2][B][2]
-    double* d_norm = d_acc + (size_t)4 * B;
+    double* d_acc = d_beta + (size_t)M * B;   // [3][B][2]
+    double* d_norm = d_acc + (size_t)6 * B;
     double* d_y = d_norm + B;
     const bool d2path = is_d2path(P);
     const bool uniform = d2path && P.all_uniform() && B == 1;
@@ -913,46 +768,79 @@ static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const st
     UniformDrive ud{};
     ud.g = {E.g[0].real(), E.g[0].imag()}; ud.theta = E.th[0]; ud.w = E.w; ud.gamma = 0.0;
     const bool real_g = E.g[0].imag() == 0.0;
-    bool fused_dot = d2path && !P.use_pipe;
+    bool fused_dot = d2path;
     for (const PassGeom& g : passes) fused_dot = fused_dot && rb_eligible(P, g);
+    // one launch per iteration: single-pass register-blocked d = 2 geometry, or the tiled d = 3 / 4 kernel
+    const bool fused = P.use_lanczos_fuse && ((fused_dot && passes.size() == 1) || (!d2path && multilevel_eligible(P)));
+    if (fused) fused_dot = true;
     c2* psi = P.buf[P.cur];
     c2* outb = P.buf[(P.cur + 1) % 3];
+    c2* V = P.kry;                                  // V_j = V + j * vstride
+    c2* Rw[2] = {P.kry + (size_t)(M + 1) * vstride, P.kry + (size_t)(M + 2) * vstride};
+    auto acc = [&](int j) { return d_acc + (size_t)(((j % 3) + 3) % 3) * 2 * B; };
     const long long rblocks = std::min<long long>((D + 255) / 256, (long long)P.sm_count * 4);
     dim3 rgrid((unsigned)std::max<long long>(rblocks, 1), (unsigned)B);
     long long launches = 0;
-    CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 4 * B, P.stream));
-    dot2_kernel<<<rgrid, 256, 0, P.stream>>>(psi, psi, D, d_acc);
-    normalize_copy_kernel<<<rgrid, 256, 0, P.stream>>>(P.kry, psi, D, d_acc, d_norm, d_acc + 2 * B);
+    CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 6 * B, P.stream));
+    dot2_kernel<<<rgrid, 256, 0, P.stream>>>(psi, psi, D, acc(2));
+    normalize_copy_kernel<<<rgrid, 256, 0, P.stream>>>(V, psi, D, acc(2), d_norm, acc(1));
     launches += 2;
     int m_check = std::min(M, std::max(3, P.m_last));
-    std::vector<double> ha((size_t)M * B), hb((size_t)M * B), hn(B);
+    std::vector<double> ha((size_t)M * B), hb((size_t)M * B), hn(B), hacc((size_t)2 * B);
     std::vector<std::vector<cplx>> ys(B);
     int m_used = 0;
     int j = 0;
     while (true) {
         for (; j < m_check; ++j) {
             StageIO io{};
-            io.v = P.kry + (size_t)j * vstride;
-            io.psi = nullptr;
-            io.b2 = (j > 0) ? P.kry + (size_t)(j - 1) * vstride : nullptr;
-            io.out = P.kry + (size_t)(j + 1) * vstride;
             io.coef = StageCoef{{0, 0}, {0, 0}, {1, 0}};
             io.ud = ud; io.table = uniform ? nullptr : P.d_table; io.real_g = real_g;
-                    io.beta_dev = (j > 0) ? d_beta + (size_t)(j - 1) * B : nullptr;
-            const int p = (j + 1) & 1;
-            io.dot_acc = fused_dot ? d_acc + (size_t)p * 2 * B : nullptr;
-            launch_stage_multi(P, passes, &io, 1, uniform, launches);
-            if (!fused_dot) { dot2_kernel<<<rgrid, 256, 0, P.stream>>>(io.v, io.out, D, d_acc + (size_t)p * 2 * B); ++launches; }
-            lanczos_update_kernel<<<rgrid, 256, 0, P.stream>>>(io.out, io.v, D, d_acc + (size_t)p * 2 * B,
-                                                               d_alpha + (size_t)j * B, d_beta + (size_t)j * B,
-                                                               d_acc + (size_t)(p ^ 1) * 2 * B);
-            launches += 1;
+            LanczosFuse lz{};
+            if (fused) {
+                // stage j: raw r_j from raw r_{j-1} (j >= 1) or from v_0 (j = 0); materialises v_j
+                io.v = (j == 0) ? V : Rw[(j - 1) & 1];
+                io.out = Rw[j & 1];
+                io.dot_acc = acc(j);
+                if (j >= 1) {
+                    lz.vj = V + (size_t)(j - 1) * vstride;
+                    lz.vjm1 = (j >= 2) ? V + (size_t)(j - 2) * vstride : nullptr;
+                    lz.vout = V + (size_t)j * vstride;
+                    lz.acc_prev = acc(j - 1);
+                    lz.beta_prev = (j >= 2) ? d_beta + (size_t)(j - 2) * B : nullptr;
+                    lz.alpha_out = d_alpha + (size_t)(j - 1) * B;
+                    lz.beta_out = d_beta + (size_t)(j - 1) * B;
+                    lz.acc_clear = acc(j + 1);
+                    io.lz = &lz;
+                }
+                launch_stage_multi(P, passes, &io, 1, uniform, launches);
+            } else {
+                io.v = V + (size_t)j * vstride;
+                io.b2 = (j > 0) ? V + (size_t)(j - 1) * vstride : nullptr;
+                io.out = V + (size_t)(j + 1) * vstride;
+                io.beta_dev = (j > 0) ? d_beta + (size_t)(j - 1) * B : nullptr;
+                io.dot_acc = fused_dot ? acc(j) : nullptr;
+                launch_stage_multi(P, passes, &io, 1, uniform, launches);
+                if (!fused_dot) { dot2_kernel<<<rgrid, 256, 0, P.stream>>>(io.v, io.out, D, acc(j)); ++launches; }
+                lanczos_update_kernel<<<rgrid, 256, 0, P.stream>>>(io.out, io.v, D, acc(j), d_alpha + (size_t)j * B,
+                                                                   d_beta + (size_t)j * B, acc(j + 1));
+                launches += 1;
+            }
         }
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaMemcpyAsync(ha.data(), d_alpha, sizeof(double) * (size_t)m_check * B, cudaMemcpyDeviceToHost, P.stream));
-        CUDA_CHECK(cudaMemcpyAsync(hb.data(), d_beta, sizeof(double) * (size_t)m_check * B, cudaMemcpyDeviceToHost, P.stream));
+        const int n_rec = fused ? m_check - 1 : m_check;   // coefficients recorded on the device so far
+        if (n_rec > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(ha.data(), d_alpha, sizeof(double) * (size_t)n_rec * B, cudaMemcpyDeviceToHost, P.stream));
+            CUDA_CHECK(cudaMemcpyAsync(hb.data(), d_beta, sizeof(double) * (size_t)n_rec * B, cudaMemcpyDeviceToHost, P.stream));
+        }
+        if (fused) CUDA_CHECK(cudaMemcpyAsync(hacc.data(), acc(m_check - 1), sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, P.stream));
         CUDA_CHECK(cudaMemcpyAsync(hn.data(), d_norm, sizeof(double) * B, cudaMemcpyDeviceToHost, P.stream));
         CUDA_CHECK(cudaStreamSynchronize(P.stream));
+        if (fused)   // the last pair comes from the reductions of the last stage (the next stage would record it)
+            for (int b = 0; b < B; ++b) {
+                const double al = hacc[2 * b], ww = hacc[2 * b + 1], b2 = ww - al * al;
+                ha[(size_t)(m_check - 1) * B + b] = al;
+                hb[(size_t)(m_check - 1) * B + b] = (b2 > 1e-28 * std::max(ww, 1e-300)) ? std::sqrt(b2) : 0.0;
+            }
         double worst = 0.0;
         for (int b = 0; b < B; ++b) {
             // per-trajectory effective dimension: stop at a breakdown (beta = 0: invariant subspace reached)
@@ -976,7 +864,7 @@ static void krylov_exponential(Plan& P, const ExpParams& E, double tol, const st
     for (int b = 0; b < B; ++b)
         for (int i = 0; i < m_used; ++i) { hy[((size_t)b * m_used + i) * 2] = ys[b][i].real(); hy[((size_t)b * m_used + i) * 2 + 1] = ys[b][i].imag(); }
     CUDA_CHECK(cudaMemcpyAsync(d_y, hy.data(), sizeof(double) * hy.size(), cudaMemcpyHostToDevice, P.stream));
-    krylov_combine_kernel<<<rgrid, 256, 0, P.stream>>>(outb, P.kry, vstride, D, d_y, m_used);
+    krylov_combine_kernel<<<rgrid, 256, 0, P.stream>>>(outb, V, vstride, D, d_y, m_used);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaStreamSynchronize(P.stream));  // hy / host tables go out of scope
     launches += 1;
@@ -1006,8 +894,7 @@ static void run_program(Plan& P, const Program& prog, const std::vector<PassGeom
     ch.psi = P.buf[P.cur];
     ch.psi_is_private = true;
     for (int i = 0; i < 3; ++i) ch.pool[i] = P.buf[i];
-    if (P.coop_now) run_chains_coop(P, &ch, 1, P.coop_passes, st);
-    else run_chains(P, &ch, 1, passes, st);
+    run_chains(P, &ch, 1, passes, st);
     for (int i = 0; i < 3; ++i)
         if (P.buf[i] == ch.result()) P.cur = i;
 }
@@ -1225,7 +1112,7 @@ static int jump_substeps(const Plan& P, double a, double b, double magnus_tol) {
 
 static void ensure_aux_buffers(Plan& P) {
     for (int i = 0; i < 6; ++i)
-        if (!P.aux[i]) CUDA_CHECK(cudaMalloc(&P.aux[i], sizeof(c2) * (size_t)P.D * P.B));
+        if (!P.aux[i]) P.aux[i] = (c2*)pool_alloc(P.desc.device, sizeof(c2) * (size_t)P.D * P.B);
 }
 
 // ---- Monte-Carlo wave-function propagation (collapse operators without a density matrix) ------------------------
@@ -1233,7 +1120,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     const double eps = 1e-12;
     const int nt = (int)P.times.size();
     pb200_run_stats st{};
-    P.use_krylov = false; P.coop_now = false;
+    P.use_krylov = false;
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
     std::vector<char> jump; std::vector<int> dist;
     const std::vector<char> fine = fine_intervals(P, 8, 1e-4, 0.05, jump, dist);
@@ -1252,7 +1139,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     CUDA_CHECK(cudaEventRecord(ev0, P.stream));
     std::vector<double> norms(P.B), occ((size_t)P.dim * P.n);
     double* d_occ = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_occ, sizeof(double) * P.n));
+    d_occ = (decltype(d_occ))pool_alloc(P.desc.device, sizeof(double) * P.n);
     std::uniform_real_distribution<double> uni(0.0, 1.0);
     auto norms2 = [&]() {
         CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * P.B, P.stream));
@@ -1335,7 +1222,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
         P.thresholds[tr] = std::min(P.thresholds[tr], 1.0);
     }
     CUDA_CHECK(cudaGetLastError());
-    cudaFree(d_occ);
+    pool_free(P.desc.device, d_occ);
     CUDA_CHECK(cudaEventRecord(ev1, P.stream));
     CUDA_CHECK(cudaEventSynchronize(ev1));
     float ms = 0.f;
@@ -1354,7 +1241,6 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (t_start < tlo - eps || t_stop > thi + eps || t_stop < t_start)
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
-    P.fwd_now = false;
     if (P.has_collapse) { propagate_mcwf(P, t_start, t_stop, o, stats); return; }
     const double gtol = (o && o->tol != 0.0) ? o->tol : (P.has_diss ? 1e-6 : 1e-8);
     // Richardson extrapolation: on by default (extrapolate = 0 or 1), -1 switches it off
@@ -1444,11 +1330,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     }
     const double rho_cap = P.use_krylov ? env_int("PB200_RHO_CAP_KRYLOV_MILLI", 12000) * 1e-3
                                         : env_int("PB200_RHO_CAP_MILLI", 3600) * 1e-3;
-    P.coop_passes = plan_passes(P.n, 11, env_int("PB200_COOP_EXTRA", 0));
-    P.coop_now = coop_eligible(P, P.coop_passes);
-    P.fwd_now = !P.coop_now && !P.use_krylov && fwd_eligible(P, passes);
-    if (P.fwd_now) plan_fwd_geometry(P);
-    const bool dual_ok = (dual_chain_ok(P, passes) || P.coop_now) && !P.has_diss && !P.use_krylov;
+    const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss && !P.use_krylov;
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
     // a symmetric 2nd-order scheme whatever the order of its unitary part
     const int pw_base = P.has_diss ? 2 : ((order == 4) ? 4 : 2);
@@ -1473,8 +1355,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             Chain ch[2];
             ch[0].prog = &half; ch[0].psi = X; for (int i = 0; i < 3; ++i) ch[0].pool[i] = others[i];
             ch[1].prog = &big;  ch[1].psi = X; for (int i = 0; i < 3; ++i) ch[1].pool[i] = others[3 + i];
-            if (P.coop_now) run_chains_coop(P, ch, 2, P.coop_passes, st);
-            else run_chains(P, ch, 2, passes, st);
+            run_chains(P, ch, 2, passes, st);
             c2* res = ch[0].result();
             axpby_kernel<<<(unsigned)nb, 256, 0, P.stream>>>(res, ch[1].result(), 1.0 + 1.0 / sc, -1.0 / sc, total);
             CUDA_CHECK(cudaGetLastError());
@@ -1768,68 +1649,16 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.max_extra = std::max(0, env_int("PB200_MAX_EXTRA", 16));
     P.force_v1 = env_int("PB200_FORCE_V1", 0) != 0;
     P.reg_bits = env_int("PB200_REG_BITS", 3) == 2 ? 2 : 3;
-    P.use_pipe = env_int("PB200_PIPE", 0) != 0;
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
-    P.use_coop = env_int("PB200_COOP", 0) != 0;  // experiment: slower than per-stage launches
-    P.dbg = env_int("PB200_DBG", 0);
-    P.use_stream = env_int("PB200_STREAM", 0) != 0;
-    P.swizzle = env_int("PB200_SWIZZLE", 0) != 0;
-    P.swizzle_min_bits = env_int("PB200_SWIZZLE_MIN_BITS", 12);
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
-    P.use_fwd = env_int("PB200_FWD", 0);
-    P.fwd_flags = env_int("PB200_FWD_FLAGS", 0);
+    P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
     P.use_tiled = env_int("PB200_TILED", 1);
-    P.tiled_k = env_int("PB200_TILED_K", 0);
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, d->device));
-    P.sm_count = prop.multiProcessorCount;
+    P.sm_count = device_setup(d->device);
     try {
         CUDA_CHECK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
         P.own_stream = true;
-        for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaMalloc(&P.buf[i], sizeof(c2) * (size_t)D * P.B));
-        CUDA_CHECK(cudaMalloc(&P.d_scratch, sizeof(double) * 4096));
-        // > 48 KB of dynamic shared memory for the tile kernels
-        const int max_smem = (1 << 13) * 16 + 1024;
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, true, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<true, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 11, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 11, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 11, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 11, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 11, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 11, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 16 * 3 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, true, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<true, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_pipe_kernel<false, false, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 12) * 16 * 2 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_tiled_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-#define PB200_FWD_ATTR(TB, RB)                                                                                                              \
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, true, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   \
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  \
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<false, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        PB200_FWD_ATTR(11, 3) PB200_FWD_ATTR(11, 2) PB200_FWD_ATTR(12, 3) PB200_FWD_ATTR(12, 2)
-#undef PB200_FWD_ATTR
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(stage_d2_stream_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 2048 * 16 + 1024));
+        for (int i = 0; i < 3; ++i) P.buf[i] = (c2*)pool_alloc(d->device, sizeof(c2) * (size_t)D * P.B);
+        P.d_scratch = (double*)pool_alloc(d->device, sizeof(double) * 4096);
     } catch (...) {
         pb200_plan_destroy(h);
         throw;
@@ -1844,21 +1673,18 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
 int pb200_plan_destroy(pb200_plan* h) {
     if (!h) return PB200_OK;
     Plan& P = h->p;
-    for (int i = 0; i < 3; ++i)
-        if (P.buf[i]) cudaFree(P.buf[i]);
-    for (int i = 0; i < 6; ++i)
-        if (P.aux[i]) cudaFree(P.aux[i]);
-    if (P.d_coop) cudaFree(P.d_coop);
-    for (int i = 0; i < 2; ++i)
-        if (P.wbuf[i]) cudaFree(P.wbuf[i]);
-    if (P.d_bar) cudaFree(P.d_bar);
-    if (P.d_xy) cudaFree(P.d_xy);
-    if (P.dint2) cudaFree(P.dint2);
-    if (P.kry) cudaFree(P.kry);
-    if (P.d_kry) cudaFree(P.d_kry);
-    if (P.dint) cudaFree(P.dint);
-    if (P.d_table) cudaFree(P.d_table);
-    if (P.d_scratch) cudaFree(P.d_scratch);
+    const int dev = P.desc.device;
+    cudaSetDevice(dev);
+    if (P.stream) cudaStreamSynchronize(P.stream);  // nothing may still be using the buffers that go back to the pool
+    for (int i = 0; i < 3; ++i) pool_free(dev, P.buf[i]);
+    for (int i = 0; i < 6; ++i) pool_free(dev, P.aux[i]);
+    pool_free(dev, P.d_xy);
+    pool_free(dev, P.dint2);
+    pool_free(dev, P.kry);
+    pool_free(dev, P.d_kry);
+    pool_free(dev, P.dint);
+    pool_free(dev, P.d_table);
+    pool_free(dev, P.d_scratch);
     if (P.own_stream && P.stream) cudaStreamDestroy(P.stream);
     delete h;
     return PB200_OK;
@@ -1886,23 +1712,23 @@ int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, cons
     CUDA_CHECK(cudaSetDevice(P.desc.device));
     const int N = P.n;
     const bool want_shared = shared != 0;
-    if (P.dint && P.dint_shared != want_shared) { CUDA_CHECK(cudaFree(P.dint)); P.dint = nullptr; }
+    if (P.dint && P.dint_shared != want_shared) { CUDA_CHECK(cudaStreamSynchronize(P.stream)); pool_free(P.desc.device, P.dint); P.dint = nullptr; }
     if (!P.dint) {
-        CUDA_CHECK(cudaMalloc(&P.dint, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B)));
+        P.dint = (decltype(P.dint))pool_alloc(P.desc.device, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B));
         if (!want_shared) CUDA_CHECK(cudaMemsetAsync(P.dint, 0, sizeof(double) * (size_t)P.D * P.B, P.stream));
     }
     P.dint_shared = want_shared;
     P.dmin_traj.resize(want_shared ? 1 : P.B, 0.0);
     P.dmax_traj.resize(want_shared ? 1 : P.B, 0.0);
     if (P.has_slm) {
-        if (P.dint2) { CUDA_CHECK(cudaFree(P.dint2)); P.dint2 = nullptr; }
-        CUDA_CHECK(cudaMalloc(&P.dint2, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B)));
+        if (P.dint2) { CUDA_CHECK(cudaStreamSynchronize(P.stream)); pool_free(P.desc.device, P.dint2); P.dint2 = nullptr; }
+        P.dint2 = (decltype(P.dint2))pool_alloc(P.desc.device, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B));
         CUDA_CHECK(cudaMemsetAsync(P.dint2, 0, sizeof(double) * (size_t)P.D * (want_shared ? 1 : P.B), P.stream));
         P.dmin2_traj.assign(want_shared ? 1 : P.B, 0.0);
         P.dmax2_traj.assign(want_shared ? 1 : P.B, 0.0);
     }
     double* dU = nullptr;
-    CUDA_CHECK(cudaMalloc(&dU, sizeof(double) * N * N));
+    dU = (decltype(dU))pool_alloc(P.desc.device, sizeof(double) * N * N);
     std::vector<double> Uc((size_t)N * N);
     // part 0: pairs weighted by w (all pairs, or the pairs not touching the SLM mask); part 1: the pairs touching it
     for (int c = 0; c < count; ++c)
@@ -1947,7 +1773,7 @@ int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, cons
             P.dmin2_traj[slot] = mn; P.dmax2_traj[slot] = mx;
         }
       }
-    CUDA_CHECK(cudaFree(dU));
+    pool_free(P.desc.device, dU);
     P.has_interaction = true;
     PB200_CATCH
 }
@@ -1965,9 +1791,9 @@ int pb200_plan_set_xy(pb200_plan* h, int32_t traj0, int32_t count, const double*
     CUDA_CHECK(cudaSetDevice(P.desc.device));
     const int N = P.n;
     const bool want_shared = shared != 0;
-    if (P.d_xy && P.xy_shared != want_shared) { CUDA_CHECK(cudaFree(P.d_xy)); P.d_xy = nullptr; }
+    if (P.d_xy && P.xy_shared != want_shared) { CUDA_CHECK(cudaStreamSynchronize(P.stream)); pool_free(P.desc.device, P.d_xy); P.d_xy = nullptr; }
     if (!P.d_xy) {
-        CUDA_CHECK(cudaMalloc(&P.d_xy, sizeof(double) * (size_t)N * N * (want_shared ? 1 : P.B)));
+        P.d_xy = (decltype(P.d_xy))pool_alloc(P.desc.device, sizeof(double) * (size_t)N * N * (want_shared ? 1 : P.B));
         CUDA_CHECK(cudaMemsetAsync(P.d_xy, 0, sizeof(double) * (size_t)N * N * (want_shared ? 1 : P.B), P.stream));
     }
     P.xy_shared = want_shared;
@@ -2179,7 +2005,7 @@ int pb200_state_occupation(pb200_plan* h, int32_t traj0, int32_t count, int32_t 
     if (digit < 0 || digit >= P.dim) fail(PB200_ERR_INVALID, "digit out of range");
     CUDA_CHECK(cudaSetDevice(P.desc.device));
     double* d_occ = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_occ, sizeof(double) * (size_t)count * P.n));
+    d_occ = (decltype(d_occ))pool_alloc(P.desc.device, sizeof(double) * (size_t)count * P.n);
     CUDA_CHECK(cudaMemsetAsync(d_occ, 0, sizeof(double) * (size_t)count * P.n, P.stream));
     const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
     dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
@@ -2188,7 +2014,7 @@ int pb200_state_occupation(pb200_plan* h, int32_t traj0, int32_t count, int32_t 
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(occ, d_occ, sizeof(double) * (size_t)count * P.n, cudaMemcpyDeviceToHost, P.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
-    cudaFree(d_occ);
+    pool_free(P.desc.device, d_occ);
     if (e != cudaSuccess) fail(PB200_ERR_CUDA, "occupation: %s", cudaGetErrorString(e));
     PB200_CATCH
 }
@@ -2203,7 +2029,7 @@ int pb200_state_correlation(pb200_plan* h, int32_t traj0, int32_t count, int32_t
     CUDA_CHECK(cudaSetDevice(P.desc.device));
     const size_t nn = (size_t)P.n * P.n;
     double* d_c = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_c, sizeof(double) * count * nn));
+    d_c = (decltype(d_c))pool_alloc(P.desc.device, sizeof(double) * count * nn);
     CUDA_CHECK(cudaMemsetAsync(d_c, 0, sizeof(double) * count * nn, P.stream));
     const long long blocks = std::min<long long>((P.D + 2047) / 2048, (long long)P.sm_count * 4);
     dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
@@ -2211,7 +2037,7 @@ int pb200_state_correlation(pb200_plan* h, int32_t traj0, int32_t count, int32_t
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(corr, d_c, sizeof(double) * count * nn, cudaMemcpyDeviceToHost, P.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
-    cudaFree(d_c);
+    pool_free(P.desc.device, d_c);
     if (e != cudaSuccess) fail(PB200_ERR_CUDA, "correlation: %s", cudaGetErrorString(e));
     for (int c = 0; c < count; ++c)  // the kernel fills i <= j
         for (int i = 0; i < P.n; ++i)
@@ -2231,7 +2057,7 @@ int pb200_state_energy(pb200_plan* h, double t_us, double* energy, double* h2) {
     long long launches = 0;
     apply_h_device(P, t_us, P.buf[P.cur], hpsi, launches);
     double* d_acc = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_acc, sizeof(double) * 2 * P.B));
+    d_acc = (decltype(d_acc))pool_alloc(P.desc.device, sizeof(double) * 2 * P.B);
     CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * P.B, P.stream));
     const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
     dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)P.B);
@@ -2240,7 +2066,7 @@ int pb200_state_energy(pb200_plan* h, double t_us, double* energy, double* h2) {
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), d_acc, sizeof(double) * 2 * P.B, cudaMemcpyDeviceToHost, P.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
-    cudaFree(d_acc);
+    pool_free(P.desc.device, d_acc);
     if (e != cudaSuccess) fail(PB200_ERR_CUDA, "energy: %s", cudaGetErrorString(e));
     for (int b = 0; b < P.B; ++b) { energy[b] = acc[2 * b]; h2[b] = acc[2 * b + 1]; }
     PB200_CATCH
@@ -2255,7 +2081,7 @@ int pb200_state_overlap(pb200_plan* h, int32_t traj0, int32_t count, const doubl
     c2* d_phi = P.buf[(P.cur + 1) % 3];
     CUDA_CHECK(cudaMemcpyAsync(d_phi, phi, sizeof(c2) * (size_t)P.D, cudaMemcpyHostToDevice, P.stream));
     double* d_acc = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_acc, sizeof(double) * 2 * count));
+    d_acc = (decltype(d_acc))pool_alloc(P.desc.device, sizeof(double) * 2 * count);
     CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * count, P.stream));
     const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
     dim3 grid((unsigned)std::max<long long>(blocks, 1), (unsigned)count);
@@ -2263,7 +2089,7 @@ int pb200_state_overlap(pb200_plan* h, int32_t traj0, int32_t count, const doubl
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_acc, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost, P.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(P.stream);
-    cudaFree(d_acc);
+    pool_free(P.desc.device, d_acc);
     if (e != cudaSuccess) fail(PB200_ERR_CUDA, "overlap: %s", cudaGetErrorString(e));
     PB200_CATCH
 }
@@ -2275,17 +2101,17 @@ int pb200_state_sample(pb200_plan* h, int32_t traj, int32_t one_digit, const dou
     Plan& P = h->p;
     if (traj < 0 || traj >= P.B) fail(PB200_ERR_INVALID, "trajectory out of range");
     if (one_digit < 0 || one_digit >= P.dim) fail(PB200_ERR_INVALID, "one_digit out of range");
-    if (P.n > 40) fail(PB200_ERR_UNSUPPORTED, "too many qudits for bitstring sampling");
+    if (P.n > 30) fail(PB200_ERR_UNSUPPORTED, "bitstring sampling: at most 30 qudits (32-bit item count of the prefix scan)");
     CUDA_CHECK(cudaSetDevice(P.desc.device));
     const long long M = 1LL << P.n;
     double *d_w = nullptr, *d_u = nullptr; long long* d_idx = nullptr; void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
     cudaError_t e = cudaSuccess;
-    auto cleanup = [&]() { cudaFree(d_w); cudaFree(d_u); cudaFree(d_idx); cudaFree(d_tmp); };
+    auto cleanup = [&]() { pool_free(P.desc.device, d_w); pool_free(P.desc.device, d_u); pool_free(P.desc.device, d_idx); pool_free(P.desc.device, d_tmp); };
     try {
-        CUDA_CHECK(cudaMalloc(&d_w, sizeof(double) * (size_t)M));
-        CUDA_CHECK(cudaMalloc(&d_u, sizeof(double) * (size_t)n_shots));
-        CUDA_CHECK(cudaMalloc(&d_idx, sizeof(long long) * (size_t)n_shots));
+        d_w = (decltype(d_w))pool_alloc(P.desc.device, sizeof(double) * (size_t)M);
+        d_u = (decltype(d_u))pool_alloc(P.desc.device, sizeof(double) * (size_t)n_shots);
+        d_idx = (decltype(d_idx))pool_alloc(P.desc.device, sizeof(long long) * (size_t)n_shots);
         CUDA_CHECK(cudaMemsetAsync(d_w, 0, sizeof(double) * (size_t)M, P.stream));
         CUDA_CHECK(cudaMemcpyAsync(d_u, uniforms, sizeof(double) * (size_t)n_shots, cudaMemcpyHostToDevice, P.stream));
         const long long blocks = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 8);
@@ -2293,7 +2119,7 @@ int pb200_state_sample(pb200_plan* h, int32_t traj, int32_t one_digit, const dou
             P.buf[P.cur] + (size_t)traj * P.D, d_w, P.D, P.n, P.dim, one_digit);
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_w, d_w, (int)M, P.stream));
-        CUDA_CHECK(cudaMalloc(&d_tmp, tmp_bytes));
+        d_tmp = (decltype(d_tmp))pool_alloc(P.desc.device, tmp_bytes);
         CUDA_CHECK(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_w, d_w, (int)M, P.stream));
         search_sorted_kernel<<<(n_shots + 255) / 256, 256, 0, P.stream>>>(d_w, M, d_u, d_idx, n_shots);
         CUDA_CHECK(cudaGetLastError());

@@ -308,24 +308,23 @@ def _multilevel_spec(n, dim, seed=0, T=48):
     return base
 
 
-@pytest.mark.parametrize("n,dim,k", [(2, 3, 0), (3, 3, 0), (7, 3, 0), (8, 3, 6), (9, 3, 8), (10, 3, 0), (1, 4, 0), (5, 4, 0), (7, 4, 4), (7, 4, 6)])
-def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim, k):
-    """stage_tiled_kernel (d = 3 / 4) == matrix-free oracle == the one-thread-per-amplitude generic kernel."""
+@pytest.mark.parametrize("n,dim", [(2, 3), (3, 3), (7, 3), (8, 3), (9, 3), (10, 3), (1, 4), (5, 4), (7, 4)])
+def test_tiled_multilevel_kernel_apply_h(engine, monkeypatch, n, dim):
+    """stage_multilevel_rb_kernel (d = 3 / 4) == matrix-free oracle == the one-thread-per-amplitude generic kernel."""
     from oracle.matfree import MatFreeHamiltonian
 
     spec = _multilevel_spec(n, dim, seed=n)
     mf = MatFreeHamiltonian(spec)
     v = random_state(spec.hilbert_dim, n)
     out = {}
-    for tiled in (1, 2, 0):  # register-blocked tiled, plain tiled, generic
+    for tiled in (1, 0):  # register-blocked tiled, generic
         monkeypatch.setenv("PB200_TILED", str(tiled))
-        monkeypatch.setenv("PB200_TILED_K", str(k))
         with engine.DevicePlan(spec) as plan:
             out[tiled] = [plan.apply_h(t, v) for t in (0.0071, 0.0302)]
     for i, t in enumerate((0.0071, 0.0302)):
         ref = mf.apply(t, v)
         scale = max(1.0, np.max(np.abs(ref)))
-        for tiled in (1, 2, 0):
+        for tiled in (1, 0):
             assert np.max(np.abs(out[tiled][i] - ref)) < 1e-12 * scale, tiled
 
 
@@ -389,6 +388,38 @@ def test_lanczos_needs_fewer_applies_on_blockaded_register(engine):
     for st, got in out.values():
         assert np.max(np.abs(got - ref)) < STATE_TOL
     assert out[2][0]["n_applies"] < out[1][0]["n_applies"]
+
+
+@pytest.mark.parametrize("kind", ["d2-uniform", "d2-batch", "d3", "d4-leak"])
+def test_fused_lanczos_equals_separate_update(engine, monkeypatch, kind):
+    """The one-launch Lanczos iteration (normalisation / orthogonalisation folded into the next stage's own-element
+    operands, LanczosFuse in kernels.cuh) against the stage + vector-update pair and against the oracle."""
+    from oracle import evolve
+
+    if kind == "d2-uniform":
+        spec = W.config_c2(n=12, seed=20, t_rise=100, t_sweep=300, t_fall=100)
+    elif kind == "d2-batch":
+        spec = [random_local_spec(11, T=120, seed=s) for s in (41, 42, 43)]
+    elif kind == "d3":
+        spec = W.config_c3(n=6, t_raman=100, t_ryd=200)
+    else:
+        spec = _multilevel_spec(4, 4, seed=2, T=150)
+    first = spec[0] if isinstance(spec, list) else spec
+    tf = first.sampling_times[-1]
+    psi0 = evolve.all_ground_state(first)
+    out = {}
+    for fuse in (1, 0):
+        monkeypatch.setenv("PB200_LANCZOS_FUSE", str(fuse))
+        with engine.DevicePlan(spec) as plan:
+            plan.set_state("all-ground")
+            st = plan.propagate(0.0, tf, integrator=2)
+            out[fuse] = (plan.get_state().copy(), st)
+    assert out[1][1]["integrator"] == 2
+    assert np.max(np.abs(out[1][0] - out[0][0])) < 1e-10
+    assert out[1][1]["n_launches"] < out[0][1]["n_launches"]      # the update kernel is gone
+    specs = spec if isinstance(spec, list) else [spec]
+    for g, s1 in zip(out[1][0], specs):
+        assert np.max(np.abs(g - _oracle_final(s1, psi0))) < STATE_TOL
 
 
 # ---------------------------------------------------------------------------
@@ -597,63 +628,6 @@ def test_xy_with_leakage_level(engine):
 # ---------------------------------------------------------------------------
 # Partner-sum forwarding between Clenshaw stages (kernels.cuh FWD): the alternating-geometry
 # stages must reproduce the single-pass stages bit for bit up to rounding.
-def _fwd_specs(kind, n):
-    if kind == "uniform-real":
-        return W.config_c2(n=n, seed=3, t_rise=40, t_sweep=80, t_fall=40)
-    if kind == "uniform-complex":
-        amp, det = W.blockade_sweep_waveforms(t_rise=40, t_sweep=80, t_fall=40)
-        phase = 0.3 + 0.004 * np.arange(len(amp))
-        return W.ising_global_spec(W.disc_register(n, 38.0, 5.0, 3), W.C6_LEVEL_60, amp, det, phase=phase)
-    if kind == "local":
-        return random_local_spec(n, T=60, seed=n)
-    if kind == "batch":
-        return [random_local_spec(n, T=60, seed=s) for s in (21, 22)]
-    raise ValueError(kind)
-
-
-@pytest.mark.parametrize("kind,n,tile_bits,flags,reg_bits", [
-    ("uniform-real", 14, 11, 0, 3), ("uniform-real", 17, 11, 27, 3), ("uniform-real", 20, 11, 11, 3),
-    ("uniform-real", 21, 11, 16, 3), ("uniform-real", 16, 12, 0, 3), ("uniform-real", 16, 12, 9, 2),
-    ("uniform-complex", 15, 11, 0, 3), ("uniform-complex", 15, 11, 31, 2), ("local", 14, 11, 0, 3),
-    ("local", 15, 11, 15, 3), ("local", 16, 12, 24, 3), ("batch", 15, 11, 3, 3), ("batch", 14, 11, 0, 2),
-])
-def test_partner_sum_forwarding_equals_single_pass(engine, monkeypatch, kind, n, tile_bits, flags, reg_bits):
-    """flags = PB200_FWD_FLAGS (TMA-staged w_in / b2 / psi tiles, separate result tile, L1 prefetch)."""
-    monkeypatch.setenv("PB200_FWD_FLAGS", str(flags))
-    monkeypatch.setenv("PB200_REG_BITS", str(reg_bits))
-    spec = _fwd_specs(kind, n)
-    first = spec[0] if isinstance(spec, list) else spec
-    tf = first.sampling_times[-1]
-    psi0 = random_state(first.hilbert_dim, 5)
-    monkeypatch.setenv("PB200_TILE_BITS", str(tile_bits))
-    out = {}
-    for fwd in (0, 1):
-        monkeypatch.setenv("PB200_FWD", str(fwd))
-        with engine.DevicePlan(spec) as plan:
-            plan.set_state(psi0)
-            st = plan.propagate(0.0, tf)
-            out[fwd] = (plan.get_state().copy(), st)
-    a, b = out[0][0], out[1][0]
-    assert np.max(np.abs(a - b)) < 2e-13
-    assert out[0][1]["n_applies"] == out[1][1]["n_applies"]
-    assert out[0][1]["n_launches"] == out[1][1]["n_launches"]  # one launch per stage either way
-
-
-def test_partner_sum_forwarding_vs_oracle(engine, monkeypatch):
-    """The forwarding path against the tight-tolerance oracle at the smallest eligible register (N = 14)."""
-    from oracle import evolve
-
-    monkeypatch.setenv("PB200_FWD", "1")
-    spec = W.config_c2(n=14, seed=20, t_rise=100, t_sweep=300, t_fall=100)
-    psi0 = evolve.all_ground_state(spec)
-    ref = _oracle_final(spec, psi0)
-    with engine.DevicePlan(spec) as plan:
-        plan.set_state("all-ground")
-        plan.propagate(0.0, spec.sampling_times[-1])
-        got = plan.get_state()[0]
-    assert np.max(np.abs(got - ref)) < STATE_TOL
-
-
 def test_state_copy_between_plans(engine):
     """pb200_state_copy: the state of one noisy trajectory evaluated under the NOISELESS Hamiltonian of another plan
     (what the generic backend's Energy observables need for stochastic-noise runs), no host round trip."""

@@ -446,3 +446,12 @@ def test_golden_expect_leakage_pins_the_interpolation_order():
     assert abs(cubic - ref) < 5e-8          # every printed digit
     assert abs(linear - ref) > 5e-7         # 0.7804014 would have been printed
     assert abs(cubic - extra["orc_rho"][0, 0].real) < 1e-9
+
+
+def test_oracle_role_table_matches_product_table():
+    """oracle/matfree.py keeps its own (to, from) table (restated from hamiltonian.py:340-352); it must agree with
+    the one the product uses."""
+    from oracle.matfree import BASIS_ROLES as oracle_roles
+    from pulser_b200.spec import BASIS_ROLES as product_roles
+
+    assert oracle_roles == product_roles
