@@ -2,7 +2,7 @@
 
 Public names mirror ``pulser_simulation/__init__.py`` (``QutipEmulator`` -> ``B200Emulator``, ``QutipBackendV2`` ->
 ``B200Backend``, ``QutipBackend`` -> ``B200LegacyBackend``, ``QutipConfig / QutipState / QutipOperator`` ->
-``B200Config / B200State / B200Operator``); they resolve lazily so that the plain-array path (``engine``, ``spec``,
+``B200Config / B200State / B200Operator``, ``SimConfig`` -> the QuTiP-free ``SimConfig``); they resolve lazily so that the plain-array path (``engine``, ``spec``,
 ``workloads``) keeps working where pulser-core is not installed.
 """
 from ._compat import HAVE_PULSER  # noqa: F401  (installs the import hooks)
@@ -18,6 +18,7 @@ _LAZY = {
     "B200State": ("backend", "B200State"),
     "B200Operator": ("backend", "B200Operator"),
     "density_matrix_aggregator": ("backend", "density_matrix_aggregator"),
+    "SimConfig": ("simconfig", "SimConfig"),
 }
 
 __all__ = ["HAVE_PULSER", *_LAZY]

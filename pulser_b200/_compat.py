@@ -21,6 +21,9 @@ import sys
 import types
 
 _REFERENCE_CORE = "/root/reference/pulser-core"
+# offline install of the unmodified pulser-core (python -m pip install --no-deps --target baseline/_ref
+# /root/reference/pulser-core): git-ignored, travels to the GPU box with the repository snapshot
+_INSTALLED_CORE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
 class _Anything:
@@ -87,9 +90,10 @@ def ensure_pulser() -> bool:
         if not any(isinstance(f, _DrawingStubFinder) for f in sys.meta_path):
             sys.meta_path.append(_DrawingStubFinder())
     if not _have("pulser"):
-        root = os.environ.get("PULSER_B200_PULSER_PATH", _REFERENCE_CORE)
-        if os.path.isdir(os.path.join(root, "pulser")):
-            sys.path.insert(0, root)
+        for root in (os.environ.get("PULSER_B200_PULSER_PATH"), _REFERENCE_CORE, _INSTALLED_CORE):
+            if root and os.path.isdir(os.path.join(root, "pulser")):
+                sys.path.insert(0, root)
+                break
         else:
             return False
     try:

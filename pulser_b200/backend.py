@@ -743,7 +743,7 @@ class B200Backend(EmulatorBackend):
         sim = self._sim_obj
         opts = {"print_progress": self._config.print_progress, "progress_bar": self._config.progress_bar}
         atom_order = tuple(sim._register.qubit_ids)
-        with engine.DevicePlan(sim._noiseless_spec(), sim._interp_order, sim._gpu) as hplan:
+        with engine.DevicePlan(sim._noiseless_spec(sim.noise_model.with_leakage), sim._interp_order, sim._gpu) as hplan:
             if not sim.noise_model.noise_types:
                 # no noise at all: the evolved Hamiltonian IS the noiseless one handed to the observables
                 sim._validate_options({})

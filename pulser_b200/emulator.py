@@ -270,15 +270,20 @@ class B200Emulator:
         for traj, noisy_samples, reps in hd.noisy_samples:
             yield self._spec_of(hd, traj, noisy_samples), reps
 
-    def _noiseless_spec(self) -> HamiltonianSpec:
-        if False not in self._noiseless_cache:
-            hd = HamiltonianData(
-                self.samples_obj, self._register, self.device, NoiseModel(), n_trajectories=1
-            )
-            self._noiseless_cache[False] = self._spec_of(
-                hd, hd.noise_trajectories[0].trajectory, hd.samples
-            )
-        return self._noiseless_cache[False]
+    def _noiseless_spec(self, leakage: bool = False) -> HamiltonianSpec:
+        """Spec of the noiseless Hamiltonian handed to observables (``_get_noiseless_hamiltonian``,
+        simulation.py:266-297): with ``leakage`` the operator lives in the 3-level basis of the leakage run, which
+        the reference obtains from a NoiseModel carrying a zero effective-noise operator."""
+        leakage = bool(leakage)
+        if leakage not in self._noiseless_cache:
+            if leakage:
+                dim = self._hamiltonian_data.basis_data.dim
+                noise = NoiseModel(eff_noise_opers=(np.zeros((dim, dim)),), eff_noise_rates=(0.0,), with_leakage=True)
+            else:
+                noise = NoiseModel()
+            hd = HamiltonianData(self.samples_obj, self._register, self.device, noise, n_trajectories=1)
+            self._noiseless_cache[leakage] = self._spec_of(hd, hd.noise_trajectories[0].trajectory, hd.samples)
+        return self._noiseless_cache[leakage]
 
     @property
     def sampling_times(self) -> np.ndarray:
@@ -308,15 +313,10 @@ class B200Emulator:
     # ---- deprecated SimConfig interface (simulation.py:338-477) ---------------------------------
     @staticmethod
     def _simconfig_class() -> Any:
-        try:  # SimConfig lives in pulser_simulation, whose import needs QuTiP
-            from pulser_simulation.simconfig import SimConfig  # type: ignore
+        """``pulser_b200.simconfig.SimConfig``: the reference class without its qutip import."""
+        from .simconfig import SimConfig
 
-            return SimConfig
-        except Exception as exc:  # pragma: no cover - depends on the installation
-            raise ImportError(
-                "SimConfig objects need 'pulser_simulation' (and QuTiP) to be importable; "
-                "instantiate the emulator with a 'NoiseModel' instead."
-            ) from exc
+        return SimConfig
 
     @property
     def config(self) -> Any:
@@ -789,7 +789,7 @@ class B200Emulator:
         n = hd.n_qudits
         D = pending[0][0].hilbert_dim
         if batch <= 0:
-            batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
+            batch = self._auto_batch(D, len(pending), stored_states=False)
         one_state = {"ground-rydberg": "r", "digital": "h", "XY": "d"}[self._meas_basis]
         matching = self._meas_basis in self.basis_name
         spr = self.noise_model.samples_per_run
@@ -833,6 +833,17 @@ class B200Emulator:
             self._current_spec = chunk[-1][0]
         return counts
 
+    def _auto_batch(self, D: int, n_pending: int, stored_states: bool = True) -> int:
+        """Trajectories per device batch.  Device side: 3 state buffers + 6 step-doubling buffers + per-trajectory
+        Dint of ``D`` (wave functions) or ``D*D`` (the vectorised density matrix of the master equation) amplitudes
+        within 8 GiB; host side (``_run_batch`` keeps every evaluation-time state of the batch): 4 GiB."""
+        amps = D * D if (self._has_collapse_ops() and not self._use_mcwf()) else D
+        dev = (8 << 30) // (amps * (9 * 16 + 8))
+        host = dev
+        if stored_states:
+            host = (4 << 30) // max(1, len(self._eval_times_array) * amps * 16)
+        return int(max(1, min(n_pending, dev, host, 1024)))
+
     def _noisy_runs(self, print_progress: bool, batch: int, opts: dict):
         """simulation.py:885-915, trajectories evolved in device batches."""
         n_trajectories = self.n_trajectories
@@ -841,8 +852,7 @@ class B200Emulator:
             return
         D = pending[0][0].hilbert_dim
         if batch <= 0:
-            # bound device memory: 3 state buffers + (maybe) per-trajectory Dint
-            batch = max(1, min(len(pending), int((8 << 30) // (D * 56)), 1024))
+            batch = self._auto_batch(D, len(pending))
         traj_nb = 0
         for chunk in pending.batches(batch):
             states = self._run_batch([s for s, _ in chunk], opts)

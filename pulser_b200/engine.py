@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import PlanDesc, RunOpts, RunStats, check, lib
-from .spec import BASIS_ROLES, HamiltonianSpec
+from .spec import BASIS_ROLES, DriveTable, HamiltonianSpec
 
 _dp = C.POINTER(C.c_double)
 
@@ -34,6 +34,38 @@ def all_ground_index(spec: HamiltonianSpec) -> int:
     return idx
 
 
+def _with_common_drives(specs: list[HamiltonianSpec]) -> list[HamiltonianSpec]:
+    """Give every trajectory of a batch the same ordered list of addressed bases.
+
+    ``spec_from_pulser`` only creates a table for a basis whose samples are non-zero in that trajectory (the
+    reference skips all-zero terms the same way, ``hamiltonian.py:353-395``), so a state-preparation error that
+    removes the only atoms a channel addresses leaves that trajectory with fewer drives than its batch mates.  A
+    missing basis is an all-zero table: the Hamiltonian is unchanged and the batch shares one kernel geometry.
+    """
+    import copy
+
+    order: list[str] = []
+    for s in specs:
+        for d in s.drives:
+            if d.basis not in order:
+                order.append(d.basis)
+    if all([d.basis for d in s.drives] == order for s in specs):
+        return specs
+    out = []
+    for s in specs:
+        have = {d.basis: d for d in s.drives}
+        nt = len(s.sampling_times)
+        drives = [
+            have.get(b) or DriveTable(b, np.zeros((s.n_qudits, nt), dtype=np.complex128),
+                                      np.zeros((s.n_qudits, nt), dtype=np.float64), True)
+            for b in order
+        ]
+        s2 = copy.copy(s)
+        s2.drives = drives
+        out.append(s2)
+    return out
+
+
 class DevicePlan:
     """A batch of trajectories of one sequence resident on one GPU."""
 
@@ -45,7 +77,7 @@ class DevicePlan:
     ) -> None:
         if isinstance(specs, HamiltonianSpec):
             specs = [specs]
-        specs = list(specs)
+        specs = _with_common_drives(list(specs))
         s0 = specs[0]
         self._xy = s0.interaction_type == "XY"
         self._slm = s0.slm_coefficient()
