@@ -11,9 +11,18 @@ step   : one pass of the hot path over the whole 4000-step sequence.
     python bench.py --gpus N --steps K --warmup W          # this repo
     python bench.py --impl reference ...                   # CPU arm (oracle port)
 
-N > 1: one process per GPU (torchrun), replicas of the sequence with different
-register seeds (the single-state path does not shard: "replicas only",
-DESIGN.md), one NCCL all-reduce for the final observables; weak scaling.
+N > 1: one process per GPU (torchrun).  `value` stays C2: the single-state path
+does not shard ("replicas only"), every GPU evolves the same Sequence,
+one NCCL all-reduce of the final observables; weak scaling.
+
+Every run also carries
+  "c4": BASELINE configs[3], the path that DOES shard: the 16-atom doppler +
+        amplitude noise trajectories (1024 of them for N >= 2, 128 at N = 1)
+        striped over the N ranks, sampled on the device, ONE NCCL all-reduce of
+        the bitstring histogram + Rydberg densities; trajectories/s and the
+        speed-up against a 1-GPU reference leg measured in the same job;
+  "c5": BASELINE configs[4] (N = 1 only): the 24-atom anneal end to end (Krylov
+        propagator), steps/s, H-applies/ns, us per apply, achieved GB/s.
 """
 from __future__ import annotations
 
@@ -110,11 +119,12 @@ def measured_peak() -> tuple[float, str]:
 
 def ncu_traffic_per_launch() -> float | None:
     """dram bytes per launch of the dominant kernel from the committed ncu summary."""
-    p = os.path.join(ROOT, "profiles", "r01_stage_kernel_summary.json")
-    try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_stage_kernel_summary.json", "r01_stage_kernel_summary.json"):
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 # --------------------------------------------------------------------------
@@ -146,7 +156,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     spec = workload(N_ATOMS)
-    n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "25" if N_ATOMS >= 20 else "400"))
+    n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "50" if N_ATOMS >= 20 else "400"))
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_reference_run(spec, n_sample)
@@ -163,6 +173,137 @@ def run_reference(args) -> None:
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+
+# --------------------------------------------------------------------------
+C4_BATCH = int(os.environ.get("PB200_BENCH_C4_BATCH", "64"))
+
+
+def c4_stripe_run(local: int, rank: int, world: int, n_total: int, stream) -> dict:
+    """This rank's stripe of the C4 trajectories (BASELINE configs[3], reference loop simulation.py:885-915):
+    device batches, one shot per trajectory drawn on the device (pb200_state_sample), per-atom Rydberg densities
+    reduced on the device.  Returns the local histogram / sums and the device time of the stripe."""
+    import torch
+
+    from pulser_b200 import engine, parallel, workloads as W
+
+    mine = set(parallel.stripe(n_total, rank, world))
+    n = 16
+    hist = np.zeros(1 << n, dtype=np.float64)
+    dens = np.zeros(n)
+    stats = {"n_applies": 0, "n_launches": 0, "gpu_ms": 0.0, "batches": 0}
+    np.random.seed(4000 + rank)  # sampling uniforms of this rank (plan.sample draws from np.random)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    chunk = []
+
+    def flush():
+        if not chunk:
+            return
+        with engine.DevicePlan(chunk, device=local) as plan:
+            plan.set_stream(stream.cuda_stream)
+            plan.set_state("all-ground")
+            st = plan.propagate(0.0, chunk[0].sampling_times[-1])
+            for k in ("n_applies", "n_launches", "gpu_ms"):
+                stats[k] += st[k]
+            stats["batches"] += 1
+            stats["integrator"] = int(st["integrator"])
+            r = chunk[0].eigenbasis.index("r")
+            dens[:] += plan.occupation(r).sum(axis=0)
+            for i in range(len(chunk)):
+                (bits, cnt), = plan.sample(1, "r", traj=i).items()
+                hist[int(bits, 2)] += cnt
+        chunk.clear()
+
+    for _, spec in W.config_c4_stream(n_total, keep=mine):
+        chunk.append(spec)
+        if len(chunk) == C4_BATCH:
+            flush()
+    flush()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return {"hist": hist, "dens": dens, "ms": e0.elapsed_time(e1), "n_local": len(mine), **stats}
+
+
+def c4_leg(local: int, rank: int, world: int, dist, barrier, stream) -> dict | None:
+    import torch
+
+    n_total = int(os.environ.get("PB200_BENCH_C4_TRAJ", "1024" if world > 1 else "128"))
+    barrier()
+    r = c4_stripe_run(local, rank, world, n_total, stream)
+    # THE collective of the path: histogram + density sums + (max) time in one packed tensor pair
+    packed = torch.from_numpy(np.concatenate([r["hist"], r["dens"], [r["n_applies"], r["n_launches"]]])).to("cuda")
+    tmax = torch.tensor([r["ms"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    barrier()
+    tot = packed.cpu().numpy()
+    hist, dens = tot[: 1 << 16], tot[1 << 16: (1 << 16) + 16]
+    seconds = float(tmax.item()) * 1e-3
+    out = {
+        "workload": "C4: 16-atom 4x4 square (6 um, MockDevice C6), blockade sweep 4000 ns, SimConfig(doppler 50 uK + amplitude "
+                    "sigma 0.05, waist 175 um) noise trajectories, ground-rydberg, fp64",
+        "n_trajectories": n_total, "n_gpus": world, "trajectories_per_rank": r["n_local"], "device_batch": C4_BATCH,
+        "seconds": seconds, "trajectories_per_s": n_total / seconds, "traj_steps_per_s": n_total * 4000 / seconds,
+        "h_applies_per_traj_step": float(tot[-2]) / (4000.0 * n_total), "gpu_launches": int(tot[-1]),
+        "integrator": {1: "chebyshev-clenshaw", 2: "lanczos"}.get(r.get("integrator", 0), "?"),
+        "shots": int(round(hist.sum())), "mean_rydberg_density": float(dens.sum() / (16 * n_total)),
+        "collective": "1 all_reduce(SUM) of [2^16 histogram | 16 densities | counters] + 1 all_reduce(MAX) of the time",
+        "timing": "CUDA events on the stream of the plans around the whole stripe (host-side spec building, plan "
+                  "creation and sampling included), max over ranks",
+    }
+    if world > 1:
+        # 1-GPU reference leg in the same job: rank 0 alone evolves 64 of the same trajectories
+        barrier()
+        ref = c4_stripe_run(local, 0, 1, C4_BATCH, stream) if rank == 0 else None
+        barrier()
+        if rank == 0:
+            n1 = C4_BATCH / (ref["ms"] * 1e-3)
+            out["n1_reference_trajectories_per_s"] = n1
+            out["n1_reference_sample"] = f"{C4_BATCH} trajectories on rank 0 alone, same code path"
+            out["speedup_vs_n1"] = out["trajectories_per_s"] / n1
+    else:
+        out["speedup_vs_n1"] = 1.0
+    return out if rank == 0 else None
+
+
+def c5_leg(local: int, stream, peak: float) -> dict:
+    """BASELINE configs[4]: 24-atom adiabatic anneal, Krylov propagator, whole 4000-ns sequence on one GPU."""
+    import torch
+
+    from pulser_b200 import engine, workloads as W
+
+    n = int(os.environ.get("PB200_BENCH_C5_ATOMS", "24"))
+    spec = W.config_c5(n=n)
+    D = spec.hilbert_dim
+    with engine.DevicePlan(spec, device=local) as plan:
+        plan.set_stream(stream.cuda_stream)
+        plan.set_state("all-ground")
+        ms_apply, launches = plan.bench_apply(1.0, 20)
+        plan.set_state("all-ground")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = plan.propagate(0.0, spec.sampling_times[-1], integrator=2)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        norm2 = float(plan.norm2()[0])
+    T = spec.total_duration_ns
+    per_apply = st["gpu_ms"] * 1e-3 / max(st["n_applies"], 1)
+    bare = ms_apply * 1e-3 / 20
+    return {
+        "workload": f"C5: {n}-atom random 2D register, adiabatic anneal 0 -> Omega -> 0 with a detuning ramp, {T} ns, "
+                    "ground-rydberg, fp64, Lanczos (Krylov) exponentials, Richardson-extrapolated CF4 Magnus steps",
+        "hilbert_dim": D, "steps_per_s": T / (ms * 1e-3), "seconds": ms * 1e-3,
+        "h_applies_per_time_step": st["n_applies"] / T, "us_per_lanczos_iteration": per_apply * 1e6,
+        "us_per_bare_h_apply": bare * 1e6, "gpu_launches": int(st["n_launches"]), "norm2_final": norm2,
+        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                     "achieved_bare_apply": 40.0 * D / bare / 1e9, "frac_bare_apply": 40.0 * D / bare / 1e9 / peak,
+                     "achieved_sequence": 40.0 * D / per_apply / 1e9, "frac_sequence": 40.0 * D / per_apply / 1e9 / peak,
+                     "note": "40 B/amplitude algorithmic per H-apply; a Lanczos iteration moves 88 B/amplitude (DESIGN.md)"},
+    }
 
 
 # --------------------------------------------------------------------------
@@ -259,8 +400,14 @@ def run_gpu(args) -> None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * T * args.steps / float(e2e_t.item())
 
+    peak, peak_src = measured_peak()
+    c4 = None
+    if os.environ.get("PB200_BENCH_SKIP_C4", "0") != "1":
+        c4 = c4_leg(local, rank, world, dist, barrier, stream)
+    c5 = None
+    if world == 1 and os.environ.get("PB200_BENCH_SKIP_C5", "0") != "1":
+        c5 = c5_leg(local, stream, peak)
     if rank == 0:
-        peak, peak_src = measured_peak()
         per_launch_s = (kernel_ms * 1e-3) / max(launches, 1)
         # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply; a launch of the stage kernel
         # carries one H-apply, or two when the h and h/2 Richardson chains share it
@@ -288,11 +435,15 @@ def run_gpu(args) -> None:
                          "avg_launch_us": per_launch_s * 1e6,
                          "note": "achieved = algorithmic bytes / (CUDA-event time of the propagation / launches), launch "
                                  "gaps included; traffic = dram read+write per launch from the committed ncu --set full "
-                                 "capture (profiles/r01_stage_kernel_summary.json): two-chain launches (2 H-applies, 83.9 MB "
+                                 "capture (profiles/r0x_stage_kernel_summary.json): two-chain launches (2 H-applies, 83.9 MB "
                                  "algorithmic), cold L2 at every ncu replay; in the timed run the 16 MiB state stays L2-resident"},
         }
+        if c4 is not None:
+            line["c4"] = c4
+        if c5 is not None:
+            line["c5"] = c5
         if os.environ.get("PB200_BENCH_SKIP_CPU", "0") != "1":
-            n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "25" if N_ATOMS >= 20 else "400"))
+            n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "50" if N_ATOMS >= 20 else "400"))
             line["cpu_baseline"] = cpu_reference_run(workload(N_ATOMS), n_sample) if world == 1 else None
         print(json.dumps(line))
     if dist is not None:

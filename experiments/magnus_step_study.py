@@ -58,3 +58,42 @@ for hns in (4, 8, 16, 32, 64, 128):
     rich = half + (half - big) / 15.0
     e4 = np.linalg.norm(big - ref); e4h = np.linalg.norm(half - ref); er = np.linalg.norm(rich - ref)
     print(f"h={hns:4d} ns  CF4 {e4:.2e} ({e4/h:.2e}/us)  2xCF4(h/2) {e4h:.2e}  Richardson {er:.2e} ({er/h:.2e}/us)")
+
+# ---- CF6:5 from experiments/derive_cf.py (rows act first -> last) against Richardson(CF4)
+F65 = np.array([[0.3196541055316575, -0.2695321497695407, 0.1692882382453091],
+                [-0.0947598412780145, 0.0366853991682727, -0.0034216265944623],
+                [0.5502114714927142, 0.0, -0.3317332233016935],
+                [-0.0947598412780145, -0.0366853991682727, -0.0034216265944623],
+                [0.3196541055316575, 0.2695321497695407, 0.1692882382453091]])
+def cf65(a, b, v):
+    h = b - a; mid = 0.5 * (a + b)
+    a1 = h * Hm(mid); a2 = (h * h / 2.0) * Hp   # a3 = 0 for a linear sweep
+    for row in F65:
+        v = expmH(row[0] * a1 + row[1] * a2) @ v
+    return v
+print("CF6:5 vs Richardson(CF4), local error per step")
+for hns in (8, 16, 24, 32, 48, 64):
+    h = hns * 1e-3
+    ref = fine(t0, t0 + h, 64) @ psi
+    big = cf4(t0, t0 + h) @ psi
+    half = cf4(t0 + h / 2, t0 + h) @ (cf4(t0, t0 + h / 2) @ psi)
+    rich = half + (half - big) / 15.0
+    c6 = cf65(t0, t0 + h, psi)
+    print(f"h={hns:4d} ns  Richardson {np.linalg.norm(rich-ref):.2e}   CF6:5 {np.linalg.norm(c6-ref):.2e}")
+
+# ---- single-exponential 4th-order Magnus exp(-i(B0 + i[B0,B1])) (exact commutator; Pulser-shaped when only the detuning varies)
+def mag4(a, b):
+    h = b - a; mid = 0.5 * (a + b)
+    B0 = h * Hm(mid); B1 = (h * h / 12.0) * Hp
+    return expmH(B0 + 1j * (B0 @ B1 - B1 @ B0))
+print("Richardson on single-exponential Magnus-4 vs on CF4")
+for hns in (8, 16, 24, 32, 48):
+    h = hns * 1e-3
+    ref = fine(t0, t0 + h, 64) @ psi
+    out = {}
+    for name, stepper in (("CF4", cf4), ("Mag4", mag4)):
+        big = stepper(t0, t0 + h) @ psi
+        half = stepper(t0 + h / 2, t0 + h) @ (stepper(t0, t0 + h / 2) @ psi)
+        rich = half + (half - big) / 15.0
+        out[name] = (np.linalg.norm(big - ref), np.linalg.norm(rich - ref))
+    print(f"h={hns:4d} ns  CF4 {out['CF4'][0]:.2e} -> R {out['CF4'][1]:.2e}   Mag4 {out['Mag4'][0]:.2e} -> R {out['Mag4'][1]:.2e}")

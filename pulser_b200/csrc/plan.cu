@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "spline.hpp"
 #include <cub/device/device_scan.cuh>
+#include <nvtx3/nvToolsExt.h>
 #include <random>
 
 namespace pb200 {
@@ -69,6 +70,14 @@ struct EventPair {
 };
 
 #define PB200_MAX_DEVICES 64
+
+// NVTX range over a C-ABI entry point (visible in nsys / ncu timelines; a no-op without a profiler attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
@@ -221,6 +230,7 @@ struct Plan {
     std::vector<double> thresholds;               // per trajectory
     std::vector<long long> jump_count;
     bool use_pdl = true;
+    int l2hint = 0;                 // PB200_L2HINT (default: 3 once the batch of states exceeds PB200_L2HINT_MIB)
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
     int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
@@ -326,6 +336,7 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.beta_dev = io.beta_dev;
     a.dot_acc = (geo_is_last ? io.dot_acc : nullptr);
     if (geo_is_last && io.lz) a.lz = *io.lz;
+    a.l2hint = P.l2hint;
     return a;
 }
 
@@ -1610,6 +1621,7 @@ int pb200_device_count(void) {
 
 int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_plan_create");
     if (!out || !d) fail(PB200_ERR_INVALID, "null argument");
     *out = nullptr;
     if (d->n_qudits < 1 || d->n_qudits > PB200_MAX_QUDITS) fail(PB200_ERR_INVALID, "n_qudits out of range");
@@ -1652,6 +1664,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
+    P.l2hint = env_int("PB200_L2HINT", ((double)D * P.B * 16.0 > (double)env_int("PB200_L2HINT_MIB", 48) * 1048576.0) ? 3 : 0);
     P.use_tiled = env_int("PB200_TILED", 1);
     P.sm_count = device_setup(d->device);
     try {
@@ -1704,6 +1717,7 @@ int pb200_plan_set_stream(pb200_plan* h, void* s) {
 int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, const double* U, const uint8_t* bad,
                                int32_t shared) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_plan_set_interaction");
     if (!h || !U) fail(PB200_ERR_INVALID, "null argument");
     Plan& P = h->p;
     if (P.desc.rydberg_state < 0) fail(PB200_ERR_INVALID, "plan has no interaction term (rydberg_state < 0)");
@@ -1843,6 +1857,7 @@ int pb200_plan_set_slm_mask(pb200_plan* h, const uint8_t* masked, const double* 
 int pb200_plan_set_drive(pb200_plan* h, int32_t drive, int32_t traj0, int32_t count, const double* coef,
                          const double* det) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_plan_set_drive");
     if (!h || !coef || !det) fail(PB200_ERR_INVALID, "null argument");
     Plan& P = h->p;
     if (drive < 0 || drive >= P.n_drives) fail(PB200_ERR_INVALID, "drive index out of range");
@@ -1930,6 +1945,7 @@ int pb200_plan_jump_counts(pb200_plan* h, int64_t* jumps) {
 int pb200_state_set(pb200_plan* h, int32_t traj0, int32_t count, const double* psi, int64_t basis_index,
                     int32_t broadcast) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_state_set");
     if (!h) fail(PB200_ERR_INVALID, "null plan");
     Plan& P = h->p;
     if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
@@ -1954,6 +1970,7 @@ int pb200_state_set(pb200_plan* h, int32_t traj0, int32_t count, const double* p
 
 int pb200_state_get(pb200_plan* h, int32_t traj0, int32_t count, double* psi) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_state_get");
     if (!h || !psi) fail(PB200_ERR_INVALID, "null argument");
     Plan& P = h->p;
     if (traj0 < 0 || count < 1 || traj0 + count > P.B) fail(PB200_ERR_INVALID, "trajectory range");
@@ -2097,6 +2114,7 @@ int pb200_state_overlap(pb200_plan* h, int32_t traj0, int32_t count, const doubl
 int pb200_state_sample(pb200_plan* h, int32_t traj, int32_t one_digit, const double* uniforms, int32_t n_shots,
                        int64_t* out) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_state_sample");
     if (!h || !uniforms || !out || n_shots < 1) fail(PB200_ERR_INVALID, "bad argument");
     Plan& P = h->p;
     if (traj < 0 || traj >= P.B) fail(PB200_ERR_INVALID, "trajectory out of range");
@@ -2162,6 +2180,7 @@ int pb200_state_device_ptr(pb200_plan* h, void** dptr) {
 
 int pb200_propagate(pb200_plan* h, double t_start, double t_stop, const pb200_run_opts* opts, pb200_run_stats* stats) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_propagate");
     if (!h) fail(PB200_ERR_INVALID, "null plan");
     CUDA_CHECK(cudaSetDevice(h->p.desc.device));
     propagate(h->p, t_start, t_stop, opts, stats);
@@ -2170,6 +2189,7 @@ int pb200_propagate(pb200_plan* h, double t_start, double t_stop, const pb200_ru
 
 int pb200_apply_h(pb200_plan* h, int32_t traj, double t_us, const double* in, double* out) {
     PB200_TRY
+    NvtxRange nvtx_range("pb200_apply_h");
     if (!h || !in || !out) fail(PB200_ERR_INVALID, "null argument");
     Plan& P = h->p;
     if (traj < 0 || traj >= P.B) fail(PB200_ERR_INVALID, "trajectory out of range");

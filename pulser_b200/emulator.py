@@ -735,6 +735,7 @@ class B200Emulator:
             total_count = np.array(
                 parallel.merge_trajectory_counts(list(total_count), self._hamiltonian_data.n_qudits)
             )
+            parallel.sync_numpy_random()  # the ranks consumed different numbers of sampling uniforms
         n_measures = int(self.n_trajectories) * self.noise_model.samples_per_run
         hd = self._hamiltonian_data
         results = [
@@ -750,6 +751,13 @@ class B200Emulator:
 
     def _pending_trajectories(self) -> list:
         """(spec, reps) of this rank's stripe; redraws the trajectories on repeated runs (:892-902)."""
+        from . import parallel
+
+        if parallel.world_size() > 1:
+            # every rank must draw the same trajectory list before taking its stripe (ADVICE r01): common seed,
+            # then a fresh draw on every rank
+            parallel.sync_numpy_random()
+            self._noise_trajectories_used = True
         if self._noise_trajectories_used:
             nm = self._hamiltonian_data.noise_model
             self._hamiltonian_data = HamiltonianData(
@@ -767,9 +775,7 @@ class B200Emulator:
                 entries = [(entries[0][0], 1)] * int(self.n_trajectories)
             else:
                 entries = [(i, 1) for i, reps in entries for _ in range(reps)]
-        from . import parallel
-
-        if parallel.world_size() > 1:  # trajectory j -> rank j mod world (same seed on every rank)
+        if parallel.world_size() > 1:  # trajectory j -> rank j mod world (same list on every rank, see above)
             entries = [entries[j] for j in parallel.stripe(len(entries), parallel.rank(), parallel.world_size())]
         return _PendingTrajectories(self, hd, entries)
 

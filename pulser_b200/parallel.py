@@ -34,6 +34,23 @@ def rank() -> int:
         return 0
 
 
+def sync_numpy_random() -> None:
+    """Put the global ``np.random`` stream of every rank in the same state: rank 0 draws a seed from its own stream
+    and broadcasts it.  The striping below relies on every rank drawing the SAME list of noise trajectories
+    (``HamiltonianData`` samples them from ``np.random`` in its constructor), while the ranks consume different
+    numbers of sampling uniforms afterwards; called before every (re)draw and after every striped run."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    seed = torch.tensor([int(np.random.randint(0, 2**31 - 1)) if dist.get_rank() == 0 else 0], dtype=torch.int64)
+    if dist.get_backend() == "nccl":
+        seed = seed.to(f"cuda:{torch.cuda.current_device()}")
+    dist.broadcast(seed, src=0)
+    np.random.seed(int(seed.item()))
+
+
 def stripe(n_items: int, rank: int, world: int) -> list[int]:
     """Trajectory j -> rank j mod world."""
     return list(range(rank, n_items, world))

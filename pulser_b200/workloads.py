@@ -224,20 +224,27 @@ def noisy_trajectory_spec(base: HamiltonianSpec, coords: np.ndarray, doppler: np
     return spec
 
 
-def config_c4(n_traj: int = 1024, seed: int = 4, side: int = 4, temperature: float = 50.0,
-              amp_sigma: float = 0.05, laser_waist: float = 175.0) -> list[HamiltonianSpec]:
-    """C4: 16-atom 4x4 square (6 um), blockade sweep, doppler + amplitude noise trajectories."""
+def config_c4_stream(n_traj: int = 1024, seed: int = 4, side: int = 4, temperature: float = 50.0,
+                     amp_sigma: float = 0.05, laser_waist: float = 175.0, keep=None):
+    """Generator over the C4 trajectories in order: yields ``(j, spec)``; with ``keep`` (a set of indices) the other
+    trajectories only advance the random stream, so that every rank of a striped run draws the same list without
+    materialising the 1.5 MB of per-atom sample tables of the trajectories it does not own."""
     coords = square_register(side, 6.0)
     amp, det = blockade_sweep_waveforms()
     base = ising_global_spec(coords, C6_LEVEL_70, amp, det)
     rng = np.random.default_rng(seed)
     sig = doppler_sigma(temperature)
-    out = []
-    for _ in range(n_traj):
+    for j in range(n_traj):
         dop = rng.normal(0.0, sig, size=len(coords))
         fl = max(0.0, rng.normal(1.0, amp_sigma))
-        out.append(noisy_trajectory_spec(base, coords, dop, fl, laser_waist))
-    return out
+        if keep is None or j in keep:
+            yield j, noisy_trajectory_spec(base, coords, dop, fl, laser_waist)
+
+
+def config_c4(n_traj: int = 1024, seed: int = 4, side: int = 4, temperature: float = 50.0,
+              amp_sigma: float = 0.05, laser_waist: float = 175.0) -> list[HamiltonianSpec]:
+    """C4: 16-atom 4x4 square (6 um), blockade sweep, doppler + amplitude noise trajectories."""
+    return [s for _, s in config_c4_stream(n_traj, seed, side, temperature, amp_sigma, laser_waist)]
 
 
 # ---------------------------------------------------------------- 3-level "all" basis (C3)

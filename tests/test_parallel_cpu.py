@@ -38,7 +38,10 @@ def _worker(rank, world, port, q):
                 local[e] += Counter(np.binary_repr(int(i), n_bits) for i in idx)
         merged = parallel.merge_trajectory_counts(local, n_bits)
         obs = parallel.all_reduce_sum(np.array([float(rank + 1), 2.0]))
-        q.put((rank, [dict(c) for c in merged], obs.tolist()))
+        np.random.seed(1000 + rank)          # ranks start from different global streams ...
+        parallel.sync_numpy_random()         # ... and leave with the same one
+        draws = np.random.rand(3).tolist()
+        q.put((rank, [dict(c) for c in merged], obs.tolist(), draws))
     finally:
         dist.destroy_process_group()
 
@@ -65,6 +68,7 @@ def test_two_rank_merge_equals_serial():
         for e in range(2):
             idx = rng.integers(0, 8, size=5)
             serial[e] += Counter(np.binary_repr(int(i), 3) for i in idx)
-    for rank, merged, obs in results:
+    for rank, merged, obs, draws in results:
         assert [Counter(m) for m in merged] == serial
         assert obs == [3.0, 4.0]
+    assert results[0][3] == results[1][3]  # sync_numpy_random: identical streams afterwards
