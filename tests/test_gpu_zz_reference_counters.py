@@ -55,10 +55,11 @@ def test_schroedinger_reference_counters(lib, name):
         plan.set_state(extra["psi0"])
         plan.propagate(0.0, spec.sampling_times[-1])
         psi = plan.get_state()[0]
-    # EOM detunings of +-1000 rad/us held for microseconds: the stiffest sequence of the suite, added after the last GPU
-    # session of round 1 -- the state bound is left a decade above the 1e-8 target until it has been measured here;
-    # the Counter equality below is the point of the test
-    assert np.max(np.abs(psi - extra["orc_final"])) < 1e-7
+    # EOM detunings of +-1000 rad/us held for microseconds: the stiffest sequence of the suite; north-star bound,
+    # the measured error is printed (pytest -s) and recorded in profiles/r02_gpu_tests.log
+    err = float(np.max(np.abs(psi - extra["orc_final"])))
+    print(f"{name}: max |psi_gpu - psi_oracle| = {err:.3e}")
+    assert err < 1e-8
     got = sample_like_the_reference(spec, psi, extra)
     assert got == expected  # a 1e-8 shift of a cumulative boundary moves no shot
 
