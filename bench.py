@@ -192,7 +192,7 @@ def c4_stripe_run(local: int, rank: int, world: int, n_total: int, stream) -> di
     n = 16
     hist = np.zeros(1 << n, dtype=np.float64)
     dens = np.zeros(n)
-    stats = {"n_applies": 0, "n_launches": 0, "gpu_ms": 0.0, "batches": 0}
+    stats = {"n_applies": 0, "n_launches": 0, "gpu_ms": 0.0, "batches": 0, "traj_applies": 0}
     np.random.seed(4000 + rank)  # sampling uniforms of this rank (plan.sample draws from np.random)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -208,6 +208,7 @@ def c4_stripe_run(local: int, rank: int, world: int, n_total: int, stream) -> di
             for k in ("n_applies", "n_launches", "gpu_ms"):
                 stats[k] += st[k]
             stats["batches"] += 1
+            stats["traj_applies"] += st["n_applies"] * len(chunk)   # n_applies counts per trajectory of the batch
             stats["integrator"] = int(st["integrator"])
             r = chunk[0].eigenbasis.index("r")
             dens[:] += plan.occupation(r).sum(axis=0)
@@ -233,7 +234,7 @@ def c4_leg(local: int, rank: int, world: int, dist, barrier, stream) -> dict | N
     barrier()
     r = c4_stripe_run(local, rank, world, n_total, stream)
     # THE collective of the path: histogram + density sums + (max) time in one packed tensor pair
-    packed = torch.from_numpy(np.concatenate([r["hist"], r["dens"], [r["n_applies"], r["n_launches"]]])).to("cuda")
+    packed = torch.from_numpy(np.concatenate([r["hist"], r["dens"], [r["traj_applies"], r["n_launches"]]])).to("cuda")
     tmax = torch.tensor([r["ms"]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)

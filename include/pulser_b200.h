@@ -109,6 +109,7 @@ typedef struct pb200_run_stats {
     double err_estimate;    /* accumulated local-error estimate (adaptive mode) */
     double mean_step_samples; /* average smooth-step length, in sampling intervals */
     int64_t integrator;     /* 1 Chebyshev, 2 Lanczos: what the run used */
+    int64_t n_rejected;     /* checked steps redone with a shorter step (adaptive mode) */
 } pb200_run_stats;
 
 int pb200_version(void);

@@ -65,6 +65,7 @@ class RunStats(C.Structure):
         ("err_estimate", C.c_double),
         ("mean_step_samples", C.c_double),
         ("integrator", C.c_int64),
+        ("n_rejected", C.c_int64),
     ]
 
 

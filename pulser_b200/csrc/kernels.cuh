@@ -97,39 +97,6 @@ __device__ __forceinline__ void st_c2(c2* p, c2 v) {
     *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
 }
 
-// ---- L2 eviction priorities ----------------------------------------------------------------------------------
-// Once the state no longer fits L2 (N >= 22), the partners across the highest bits are re-read from HBM unless the
-// gather source survives in L2 between the CTA that first touches a tile and the CTA that owns it (2^b amplitudes
-// later for bit b).  The gather source is therefore loaded evict_last (tile TMA copy and partner loads) while the
-// own-element operands and the result stream through evict_first, so that they cannot push the source out.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-// read-only 16-byte load of the gather source with an L2 cache policy (the source is never written by the kernel)
-__device__ __forceinline__ double2 ldg_policy(const c2* p, uint64_t pol) {
-    double2 r;
-    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ void st_c2_policy(c2* p, c2 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d_policy(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
-                                                   uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
-
 // Fused Lanczos step (StageArgs::lz set).  The gather source `v` holds the RAW vector r_j = G v_j - beta_{j-1} v_{j-1}
 // of the previous stage; alpha_j = Re<v_j, r_j> and |r_j|^2 were reduced by that stage into lz.acc_prev.  This stage
 //   v_{j+1} = (r_j - alpha_j v_j) / beta_j                           (second output, own element)
@@ -180,7 +147,6 @@ struct StageArgs {
     double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<lhs, out>, acc[traj][1] += <out, out> (fused reductions;
                              // lhs = v, or v_{j+1} in a fused Lanczos step)
     LanczosFuse lz;          // fused Lanczos step when lz.vj != nullptr (register-blocked kernels)
-    int l2hint;              // bit 0: gather source evict_last in L2; bit 1: results stored evict_first
 };
 
 // up to two independent Clenshaw chains per launch (the h and the h/2 branches of a Richardson step):
@@ -426,8 +392,6 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         idx[r] = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
     }
     // --- flips of the bits outside the tile: coalesced partner loads ---
-    const uint64_t pol_last = (a.l2hint & 1) ? l2_policy_evict_last() : 0ULL;
-    const uint64_t pol_first = (a.l2hint & 2) ? l2_policy_evict_first() : 0ULL;
     for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
         const int p = __ffsll((long long)m) - 1;
         double gx = 0.0, gyt = 0.0;
@@ -436,13 +400,8 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
         const double sg = (bit == to_bit) ? 1.0 : -1.0;
         const double gy = (bit == to_bit) ? gyt : -gyt;
         double2 raw[R];
-        if (a.l2hint & 1) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) raw[r] = ldg_policy(vsrc + (idx[r] ^ (1LL << p)), pol_last);
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) raw[r] = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
-        }
+        for (int r = 0; r < R; ++r) raw[r] = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (UNIFORM) {
@@ -536,8 +495,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                     const double ai = lc.alpha * lc.inv, abi = ai * lc.beta_prev;
                     res.x = fma(lc.inv, gv.x, -fma(ai, v[rr].x, fma(abi, bv[r].x, lc.beta * pv[r].x)));
                     res.y = fma(lc.inv, gv.y, -fma(ai, v[rr].y, fma(abi, bv[r].y, lc.beta * pv[r].y)));
-                    if (a.l2hint & 2) st_c2_policy(a.lz.vout + voff + idx[rr], vn, pol_first);
-                    else st_c2(a.lz.vout + voff + idx[rr], vn);
+                    st_c2(a.lz.vout + voff + idx[rr], vn);
                     lhs = vn;
                 } else {
                     res = cmul(a.coef.c_g, gv);
@@ -547,8 +505,7 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
                 }
                 dot0 = fma(lhs.x, res.x, dot0); dot0 = fma(lhs.y, res.y, dot0);
                 dot1 = fma(res.x, res.x, dot1); dot1 = fma(res.y, res.y, dot1);
-                if (a.l2hint & 2) st_c2_policy(a.out + voff + idx[rr], res, pol_first);
-                else st_c2(a.out + voff + idx[rr], res);
+                st_c2(a.out + voff + idx[rr], res);
             }
         }
     } else {
@@ -628,25 +585,21 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
     const c2* vsrc = a.v + traj * a.D;
 
     if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();          // the barrier is initialised before any thread issues a copy on it
     pdl_wait();
     pdl_launch_dependents();
+    // the tile copy goes out first; the per-trajectory coefficient table (non-uniform drives) is read behind it
+    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
+    const int rows = 1 << g.hi_bits;
+    const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+    for (int r = tid; r < rows; r += NT)
+        tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
     double* tab = reinterpret_cast<double*>(tile + TSIZE);
     if (!UNIFORM) {
         const int stride = d2_table_stride(g.n_bits);
         const double* src = a.table + traj * stride;
         for (int i = tid; i < stride; i += NT) tab[i] = src[i];
-    }
-    __syncthreads();
-    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
-    const int rows = 1 << g.hi_bits;
-    const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
-    if (a.l2hint & 1) {
-        const uint64_t pol = l2_policy_evict_last();
-        for (int r = tid; r < rows; r += NT)
-            tma_load_1d_policy(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar, pol);
-    } else {
-        for (int r = tid; r < rows; r += NT)
-            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+        __syncthreads();
     }
     mbar_wait(&mbar, 0);
     rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);

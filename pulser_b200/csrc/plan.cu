@@ -230,7 +230,11 @@ struct Plan {
     std::vector<double> thresholds;               // per trajectory
     std::vector<long long> jump_count;
     bool use_pdl = true;
-    int l2hint = 0;                 // PB200_L2HINT (default: 3 once the batch of states exceeds PB200_L2HINT_MIB)
+    // step-controller state kept between pb200_propagate calls (evaluation times cut a run into many calls):
+    // interval classification of the sampling grid (cache key = window, rough_tol) and the current smooth-step length
+    struct FineCache { bool valid = false; int window = -1; double rtol = -1.0; std::vector<char> fine, jump; std::vector<int> dist; } fine_cache;
+    double ctrl_Kc = -1.0; double ctrl_key = 0.0; double ctrl_t_end = -1e300;
+    bool use_mag4 = true;           // PB200_MAG4=0: always the two-exponential commutator-free step
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
     int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
@@ -336,7 +340,6 @@ static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const Stage
     a.beta_dev = io.beta_dev;
     a.dot_acc = (geo_is_last ? io.dot_acc : nullptr);
     if (geo_is_last && io.lz) a.lz = *io.lz;
-    a.l2hint = P.l2hint;
     return a;
 }
 
@@ -1083,6 +1086,22 @@ static void add_step(const Plan& P, Program& prog, double a, double b, int order
             }
         }
     } mark{P, prog, first, h};
+    // Single-exponential 4th-order Magnus step.  Omega = -i B0 + [B0, B1]; when the drive coefficients have no first
+    // moment over the step (constant amplitude and phase: only the detuning moves, the adiabatic-sweep case) B1 is
+    // the diagonal -sum_k th1_k |from><from|_k and i [B0, B1] = sum_k (-i th1_k g0_k |to><from|_k + h.c.) is again a
+    // single-qudit drive: U = exp(-i G) with G = B0 and g_k -> g0_k (1 - i th1_k).  One exponential instead of the
+    // two of the commutator-free scheme (same order, time-symmetric, so Richardson still gains two orders).
+    if (order == 4 && P.use_mag4 && P.n_drives == 1 && !P.has_xy && !P.has_slm && !P.has_diss) {
+        double g0max = 0.0, g1max = 0.0;
+        for (size_t x = 0; x < cnt; ++x) { g0max = std::max(g0max, std::abs(g0[x])); g1max = std::max(g1max, std::abs(g1[x])); }
+        if (g1max <= 1e-14 * std::max(g0max, 1e-3 * h)) {
+            ExpParams E;
+            E.g.resize(cnt); E.th = th0; E.w = h;
+            for (size_t x = 0; x < cnt; ++x) E.g[x] = g0[x] * cplx(1.0, -th1[x]);
+            add_exponential(P, prog, E, tol);
+            return;
+        }
+    }
     if (order == 4) {
         ExpParams E1, E2;
         E1.g.resize(cnt); E1.th.resize(cnt); E2.g.resize(cnt); E2.th.resize(cnt);
@@ -1268,10 +1287,14 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
 
     pb200_run_stats st{};
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
-    std::vector<char> jump;
-    std::vector<int> dist;
-    std::vector<char> fine = fine_intervals(P, W, rtol, 0.05, jump, dist);
-    for (size_t i = 0; i < fine.size(); ++i) if (jump[i]) fine[i] = 1;
+    if (!P.fine_cache.valid || P.fine_cache.window != W || P.fine_cache.rtol != rtol) {
+        P.fine_cache.fine = fine_intervals(P, W, rtol, 0.05, P.fine_cache.jump, P.fine_cache.dist);
+        for (size_t i = 0; i < P.fine_cache.fine.size(); ++i) if (P.fine_cache.jump[i]) P.fine_cache.fine[i] = 1;
+        P.fine_cache.window = W; P.fine_cache.rtol = rtol; P.fine_cache.valid = true;
+    }
+    const std::vector<char>& jump = P.fine_cache.jump;
+    const std::vector<int>& dist = P.fine_cache.dist;
+    const std::vector<char>& fine = P.fine_cache.fine;
     const double magnus_tol = 1e-11;
     const int nt = (int)P.times.size();
     // error budget per unit of time: gtol over the whole sampling-time range
@@ -1395,6 +1418,15 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     // current smooth-step length in sampling intervals (real: < 1 means sub-steps)
     double Kc = adaptive ? std::min(extrap ? 8.0 : 4.0, (double)Kmax) : (double)Kmax;
     int since_check = 1 << 30;  // force a check at the first smooth step
+    int n_rejected = 0;         // consecutive rejections of the current step
+    // a call that continues where the previous one stopped (same tolerances) inherits its step length: with "Full"
+    // evaluation times every sampling interval is its own call, and re-growing the step from scratch (and paying
+    // the 3x-cost check) on each of them would dominate the run
+    const double ctrl_key = gtol * 1e3 + (extrap ? 1.0 : 0.0) + 2.0 * order + 16.0 * Kmax;
+    if (adaptive && P.ctrl_Kc > 0.0 && P.ctrl_key == ctrl_key && std::fabs(P.ctrl_t_end - t_start) < 1e-9) {
+        Kc = std::min(P.ctrl_Kc, (double)Kmax);
+        since_check = check_every / 2;
+    }
     double smooth_len = 0.0; long long smooth_steps = 0;
     bool last_fine = false;
     double t = t_start;
@@ -1496,6 +1528,18 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
                 // maximum rate (so that the step recovers quickly after a non-smooth stretch)
                 since_check = (factor < 0.7) ? check_every - 2
                                              : ((factor >= 1.9 && controller_limited) ? check_every - 3 : 0);
+                // the state kept by a check is the pair of half steps, whose own error is err_big / 2^pw; if even
+                // that exceeds the step's share of the budget the step is REJECTED: restore the saved state and
+                // retry with the shortened step (at most 4 times in a row, then accept and let the budget absorb it)
+                const double kept_rate = std::sqrt(e) / scale / std::max(b - t, 1e-30);
+                if (kept_rate > rate_allowed && n_rejected < 4 && h_samples > 1.0 / 16.0 + 1e-12) {
+                    copy_state(P.buf[P.cur], extrap ? P.aux[4] : P.aux[0]);
+                    st.err_estimate -= std::sqrt(e) / scale;
+                    ++n_rejected; ++st.n_rejected;
+                    since_check = 1 << 30;
+                    continue;
+                }
+                n_rejected = 0;
             } else {
                 ++since_check;
             }
@@ -1509,6 +1553,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         t = b;
     }
     flush();
+    P.ctrl_Kc = Kc; P.ctrl_key = ctrl_key; P.ctrl_t_end = t_stop;
     CUDA_CHECK(cudaEventRecord(ev1, P.stream));
     CUDA_CHECK(cudaEventSynchronize(ev1));
     float ms = 0.f;
@@ -1664,7 +1709,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
-    P.l2hint = env_int("PB200_L2HINT", ((double)D * P.B * 16.0 > (double)env_int("PB200_L2HINT_MIB", 48) * 1048576.0) ? 3 : 0);
+    P.use_mag4 = env_int("PB200_MAG4", 1) != 0;
     P.use_tiled = env_int("PB200_TILED", 1);
     P.sm_count = device_setup(d->device);
     try {
@@ -1881,6 +1926,7 @@ int pb200_plan_set_drive(pb200_plan* h, int32_t drive, int32_t traj0, int32_t co
             }
         }
         P.tabs_set[traj0 + c][drive] = true;
+        P.fine_cache.valid = false; P.ctrl_Kc = -1.0;
     }
     PB200_CATCH
 }

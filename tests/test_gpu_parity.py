@@ -422,6 +422,35 @@ def test_fused_lanczos_equals_separate_update(engine, monkeypatch, kind):
         assert np.max(np.abs(g - _oracle_final(s1, psi0))) < STATE_TOL
 
 
+@pytest.mark.parametrize("integrator", [1, 2])
+def test_single_exponential_magnus_steps(engine, monkeypatch, integrator):
+    """Where only the detuning moves over a step, the 4th-order Magnus generator B0 + i[B0, B1] is itself
+    Pulser-shaped (drive g0 (1 - i th1)) and the step is ONE exponential (plan.cu add_step): fewer H-applies than
+    the two-exponential commutator-free step, same state within the north-star bound (uniform and per-atom drives)."""
+    from oracle import evolve
+
+    uni = W.config_c2(n=10, seed=20, t_rise=100, t_sweep=600, t_fall=100)
+    coords = W.disc_register(8, 30.0, 5.0, 3)
+    amp, det = W.blockade_sweep_waveforms(t_rise=100, t_sweep=500, t_fall=100)
+    base = W.ising_global_spec(coords, W.C6_LEVEL_60, amp, det)
+    rng = np.random.default_rng(1)
+    loc = W.noisy_trajectory_spec(base, coords, rng.normal(0, 0.6, 8), 0.97, 175.0)
+    for spec in (uni, loc):
+        psi0 = evolve.all_ground_state(spec)
+        ref = _oracle_final(spec, psi0)
+        out = {}
+        for mag4 in (1, 0):
+            monkeypatch.setenv("PB200_MAG4", str(mag4))
+            with engine.DevicePlan(spec) as plan:
+                plan.set_state("all-ground")
+                st = plan.propagate(0.0, spec.sampling_times[-1], integrator=integrator)
+                out[mag4] = (plan.get_state()[0], st)
+        for got, _ in out.values():
+            assert np.max(np.abs(got - ref)) < STATE_TOL
+        assert out[1][1]["n_exponentials"] < out[0][1]["n_exponentials"]
+        assert out[1][1]["n_applies"] < out[0][1]["n_applies"]
+
+
 # ---------------------------------------------------------------------------
 # measurement on the device
 def test_device_sampling_equals_reference_recipe(engine):
