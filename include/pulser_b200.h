@@ -179,8 +179,11 @@ int pb200_plan_set_dissipator(pb200_plan* plan, int32_t n_pairs,
  * simulation.py:710-735) for registers whose density matrix does not fit:
  * `ops` = n_ops single-qudit collapse matrices (d x d, row-major, interleaved
  * complex, coefficient included), each acting on every qudit
- * (hamiltonian.py:97-124).  Every L^+L must be diagonal (dephasing, relaxation,
- * depolarizing and transition/projector-type effective noise).  Afterwards
+ * (hamiltonian.py:97-124).  When every L^+L is diagonal (dephasing, relaxation,
+ * depolarizing, transition/projector-type effective noise) the no-jump decay is one
+ * elementwise kernel and the jump weights come from the per-qudit populations; general
+ * operators use exp(-tau sum L^+L) applied qudit by qudit and the single-qudit reduced
+ * density matrices.  Afterwards
  * pb200_propagate evolves every trajectory under
  * H_eff = H - i/2 sum L^+L (symmetric splitting around the unitary step), and
  * applies a quantum jump whenever a trajectory's squared norm falls below its

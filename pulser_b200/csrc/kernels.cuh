@@ -366,7 +366,7 @@ __device__ __forceinline__ void rb_tile_gather(const PassGeom& g, const c2* tile
 template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
 __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGeom& g, const c2* tile,
                                                 const double* __restrict__ tab, long long base, long long traj,
-                                                int tid) {
+                                                int tid, uint64_t* tile_bar) {
     constexpr int R = 1 << RB;
     constexpr int NT = 1 << (TBITS - RB);
     const long long voff = traj * a.D;
@@ -378,20 +378,16 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
 
     c2 v[R];
     double pr[R], pi[R], qr[R], qi[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        v[r] = tile[tid + r * NT];
-        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
-    }
-    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
     // global index of each owned amplitude
     long long idx[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int t = tid + r * NT;
         idx[r] = base | (t & lomask) | ((long long)(t >> g.lo_bits) << g.hi_shift);
+        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
     }
-    // --- flips of the bits outside the tile: coalesced partner loads ---
+    // --- flips of the bits outside the tile: coalesced partner loads.  They do not depend on the tile, so they go
+    //     out while the bulk copy of the tile is still in flight (the wait on its mbarrier comes after them) ---
     for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
         const int p = __ffsll((long long)m) - 1;
         double gx = 0.0, gyt = 0.0;
@@ -413,6 +409,10 @@ __device__ __forceinline__ void rb_tile_compute(const StageArgs& a, const PassGe
             }
         }
     }
+    if (tile_bar) mbar_wait(tile_bar, 0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = tile[tid + r * NT];
+    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
     // --- epilogue ---
     double w = 0.0, gamma = 0.0, th_common = 0.0;
     double th_r[R];
@@ -601,8 +601,7 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
         for (int i = tid; i < stride; i += NT) tab[i] = src[i];
         __syncthreads();
     }
-    mbar_wait(&mbar, 0);
-    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid);
+    rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid, &mbar);
 }
 
 // ---- generic-d stage kernel (any dim, several drives; global gathers) -------
@@ -1286,6 +1285,7 @@ __global__ void mcwf_decay_kernel(c2* psi, long long D, int n, int dim, double h
 // psi <- scale * (L on qudit with stride `st`) psi for one trajectory; L row-major d x d
 struct QuditOp { c2 m[16]; };
 __global__ void qudit_op_kernel(c2* psi, long long D, int dim, long long st, double scale, const __grid_constant__ QuditOp op) {
+    psi += (long long)blockIdx.y * D;   // gridDim.y = trajectories (1 for a single-trajectory jump)
     const long long groups = D / dim;
     for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < groups;
          gidx += (long long)gridDim.x * blockDim.x) {
@@ -1303,6 +1303,35 @@ __global__ void qudit_op_kernel(c2* psi, long long D, int dim, long long st, dou
             w[r] = {xr * scale, xi * scale};
         }
         for (int a = 0; a < dim; ++a) psi[idx0 + a * st] = w[a];
+    }
+}
+
+// Single-qudit reduced density matrix rho[a][b] = sum_rest psi(a, rest) conj(psi(b, rest)) of the qudit with stride
+// `st` (one trajectory), accumulated into acc[2 * (a * dim + b) + {0, 1}]: the jump weights <L^+L> of a general
+// (non-diagonal L^+L) collapse operator are Tr(L^+L rho) (hamiltonian.py:97-124 builds the operators).
+__global__ void reduced_density_kernel(const c2* psi, long long D, int dim, long long st, double* acc) {
+    const long long groups = D / dim;
+    double re[16], im[16];
+    for (int i = 0; i < 16; ++i) { re[i] = 0.0; im[i] = 0.0; }
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < groups;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        const long long low = gidx % st, high = gidx / st;
+        const long long idx0 = low + high * st * dim;
+        c2 v[4];
+        for (int a = 0; a < dim; ++a) v[a] = psi[idx0 + a * st];
+        for (int a = 0; a < dim; ++a)
+            for (int b = 0; b < dim; ++b) {
+                re[a * dim + b] = fma(v[a].x, v[b].x, fma(v[a].y, v[b].y, re[a * dim + b]));
+                im[a * dim + b] = fma(v[a].y, v[b].x, fma(-v[a].x, v[b].y, im[a * dim + b]));
+            }
+    }
+    for (int i = 0; i < dim * dim; ++i) {
+        double x = re[i], y = im[i];
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+            y += __shfl_xor_sync(0xffffffffu, y, o);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(acc + 2 * i, x); atomicAdd(acc + 2 * i + 1, y); }
     }
 }
 

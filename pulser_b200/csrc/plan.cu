@@ -217,6 +217,8 @@ struct Plan {
     // Monte-Carlo wave function: single-qudit collapse operators (L^+L diagonal), thresholds, RNG
     std::vector<std::vector<cplx>> jump_ops;      // [n_ops][d*d]
     std::vector<std::vector<double>> jump_ldl;    // [n_ops][d]: diagonal of L^+L
+    std::vector<std::vector<cplx>> jump_ldl_full; // [n_ops][d*d]: L^+L
+    bool jump_diag = true;                        // every L^+L is diagonal (decay = one elementwise kernel)
     bool has_collapse = false;
     // XY mode: exchange couplings on the device, their absolute row sums (spectral bound)
     double* d_xy = nullptr; bool xy_shared = true; bool has_xy = false; int xy_u = 0, xy_d = 1;
@@ -234,7 +236,6 @@ struct Plan {
     // interval classification of the sampling grid (cache key = window, rough_tol) and the current smooth-step length
     struct FineCache { bool valid = false; int window = -1; double rtol = -1.0; std::vector<char> fine, jump; std::vector<int> dist; } fine_cache;
     double ctrl_Kc = -1.0; double ctrl_key = 0.0; double ctrl_t_end = -1e300;
-    bool use_mag4 = true;           // PB200_MAG4=0: always the two-exponential commutator-free step
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
     int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
@@ -1086,22 +1087,6 @@ static void add_step(const Plan& P, Program& prog, double a, double b, int order
             }
         }
     } mark{P, prog, first, h};
-    // Single-exponential 4th-order Magnus step.  Omega = -i B0 + [B0, B1]; when the drive coefficients have no first
-    // moment over the step (constant amplitude and phase: only the detuning moves, the adiabatic-sweep case) B1 is
-    // the diagonal -sum_k th1_k |from><from|_k and i [B0, B1] = sum_k (-i th1_k g0_k |to><from|_k + h.c.) is again a
-    // single-qudit drive: U = exp(-i G) with G = B0 and g_k -> g0_k (1 - i th1_k).  One exponential instead of the
-    // two of the commutator-free scheme (same order, time-symmetric, so Richardson still gains two orders).
-    if (order == 4 && P.use_mag4 && P.n_drives == 1 && !P.has_xy && !P.has_slm && !P.has_diss) {
-        double g0max = 0.0, g1max = 0.0;
-        for (size_t x = 0; x < cnt; ++x) { g0max = std::max(g0max, std::abs(g0[x])); g1max = std::max(g1max, std::abs(g1[x])); }
-        if (g1max <= 1e-14 * std::max(g0max, 1e-3 * h)) {
-            ExpParams E;
-            E.g.resize(cnt); E.th = th0; E.w = h;
-            for (size_t x = 0; x < cnt; ++x) E.g[x] = g0[x] * cplx(1.0, -th1[x]);
-            add_exponential(P, prog, E, tol);
-            return;
-        }
-    }
     if (order == 4) {
         ExpParams E1, E2;
         E1.g.resize(cnt); E1.th.resize(cnt); E2.g.resize(cnt); E2.th.resize(cnt);
@@ -1181,6 +1166,40 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
         CUDA_CHECK(cudaStreamSynchronize(P.stream));
         st.n_launches += 1;
     };
+    // K_tot = sum_c L_c^+ L_c (d x d): its norm bounds the jump rate per qudit
+    const int d = P.dim;
+    std::vector<cplx> Ktot((size_t)d * d, cplx(0));
+    double rate_max = 0.0;
+    for (const auto& kf : P.jump_ldl_full)
+        for (int q = 0; q < d * d; ++q) Ktot[q] += kf[q];
+    for (int a = 0; a < d; ++a) {
+        double row = 0.0;
+        for (int c = 0; c < d; ++c) row += std::abs(Ktot[a * d + c]);
+        rate_max = std::max(rate_max, row);
+    }
+    // the no-jump evolution exp(-tau sum_k K_tot^(k)): one elementwise kernel when every L^+L is diagonal, else the
+    // d x d matrix exp(-tau K_tot) applied to each qudit in turn (general effective-noise operators)
+    auto decay = [&](double tau) {
+        if (P.jump_diag) {
+            mcwf_decay_kernel<<<bgrid, 256, 0, P.stream>>>(P.buf[P.cur], P.D, P.n, P.dim, tau, dt);
+            st.n_launches += 1;
+            return;
+        }
+        std::vector<cplx> A((size_t)d * d);
+        for (int q = 0; q < d * d; ++q) A[q] = -Ktot[q];
+        const std::vector<cplx> M = small_expm(A, d, tau);
+        QuditOp qo{};
+        for (int q = 0; q < d * d; ++q) qo.m[q] = {M[q].real(), M[q].imag()};
+        const long long nb = std::min<long long>((P.D / d + 255) / 256, (long long)P.sm_count * 8);
+        long long stq = 1;
+        for (int k = P.n - 1; k >= 0; --k) {  // qudit k has stride d^(n-1-k)
+            qudit_op_kernel<<<dim3((unsigned)std::max<long long>(nb, 1), (unsigned)P.B), 256, 0, P.stream>>>(
+                P.buf[P.cur], P.D, d, stq, 1.0, qo);
+            stq *= d;
+        }
+        st.n_launches += P.n;
+    };
+    const double ctol = (o && o->cheb_tol > 0) ? o->cheb_tol : 1e-11;
     double t = t_start;
     while (t < t_stop - eps) {
         const int i = find_piece(P.times, t + eps);
@@ -1190,24 +1209,51 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
             const int nsub = jump_substeps(P, t, std::min(P.times[i + 1], t_stop), 1e-9);
             b = std::min(P.times[i + 1], t + hi_i / nsub);
         }
+        // jump times are resolved to one step: keep the jump probability of a qudit per step below 5 %
+        if (rate_max > 0.0) b = std::min(b, std::max(t + 0.05 / rate_max, std::min(P.times[i + 1], t + hi_i / 64.0)));
         b = std::min(b, t_stop);
         const double h = b - t;
         // exp(-i H_eff h) ~ decay(h/2) U(h) decay(h/2)
-        mcwf_decay_kernel<<<bgrid, 256, 0, P.stream>>>(P.buf[P.cur], P.D, P.n, P.dim, 0.25 * h, dt);
+        decay(0.25 * h);
         Program prog;
-        add_step(P, prog, t, b, 4, 1e-11);
+        add_step(P, prog, t, b, 4, ctol);
         run_program(P, prog, passes, st);
         CUDA_CHECK(cudaStreamSynchronize(P.stream));
-        mcwf_decay_kernel<<<bgrid, 256, 0, P.stream>>>(P.buf[P.cur], P.D, P.n, P.dim, 0.25 * h, dt);
+        decay(0.25 * h);
         CUDA_CHECK(cudaGetLastError());
-        st.n_launches += 2; ++st.n_steps;
+        ++st.n_steps;
         // quantum jumps
         norms2();
         for (int tr = 0; tr < P.B; ++tr) {
             if (norms[tr] > P.thresholds[tr]) continue;
             c2* psi = P.buf[P.cur] + (size_t)tr * P.D;
+            std::vector<double> wts(P.jump_ops.size() * (size_t)P.n);
+            double tot = 0.0;
+            if (!P.jump_diag) {
+                // <L_c^+ L_c> on qudit k = Tr(L_c^+ L_c rho_k) with the single-qudit reduced density matrix rho_k
+                std::vector<double> hr((size_t)2 * d * d);
+                const long long nbq = std::min<long long>((P.D / d + 255) / 256, (long long)P.sm_count * 4);
+                long long stq = 1;
+                for (int k = P.n - 1; k >= 0; --k) {
+                    CUDA_CHECK(cudaMemsetAsync(P.d_scratch, 0, sizeof(double) * 2 * d * d, P.stream));
+                    reduced_density_kernel<<<(unsigned)std::max<long long>(nbq, 1), 256, 0, P.stream>>>(psi, P.D, d, stq, P.d_scratch);
+                    CUDA_CHECK(cudaGetLastError());
+                    CUDA_CHECK(cudaMemcpyAsync(hr.data(), P.d_scratch, sizeof(double) * 2 * d * d, cudaMemcpyDeviceToHost, P.stream));
+                    CUDA_CHECK(cudaStreamSynchronize(P.stream));
+                    for (size_t op = 0; op < P.jump_ops.size(); ++op) {
+                        cplx tr_k = 0.0;
+                        for (int a = 0; a < d; ++a)
+                            for (int c = 0; c < d; ++c)
+                                tr_k += P.jump_ldl_full[op][a * d + c] * cplx(hr[2 * (c * d + a)], hr[2 * (c * d + a) + 1]);
+                        const double wv = std::max(tr_k.real(), 0.0);
+                        wts[op * P.n + k] = wv; tot += wv;
+                    }
+                    stq *= d;
+                }
+                st.n_launches += P.n;
+            }
             // populations of every digit on every qudit
-            for (int dgt = 0; dgt < P.dim; ++dgt) {
+            for (int dgt = 0; P.jump_diag && dgt < P.dim; ++dgt) {
                 CUDA_CHECK(cudaMemsetAsync(d_occ, 0, sizeof(double) * P.n, P.stream));
                 const long long nb = std::min<long long>((P.D + 255) / 256, (long long)P.sm_count * 4);
                 occupation_kernel<<<(unsigned)std::max<long long>(nb, 1), 256, sizeof(double) * P.n, P.stream>>>(
@@ -1216,9 +1262,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
             }
             CUDA_CHECK(cudaStreamSynchronize(P.stream));
             // channel (op, qudit) with probability <L^+L>
-            std::vector<double> wts(P.jump_ops.size() * (size_t)P.n);
-            double tot = 0.0;
-            for (size_t op = 0; op < P.jump_ops.size(); ++op)
+            for (size_t op = 0; P.jump_diag && op < P.jump_ops.size(); ++op)
                 for (int k = 0; k < P.n; ++k) {
                     double wv = 0.0;
                     for (int dgt = 0; dgt < P.dim; ++dgt) wv += P.jump_ldl[op][dgt] * occ[(size_t)dgt * P.n + k];
@@ -1709,7 +1753,6 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
-    P.use_mag4 = env_int("PB200_MAG4", 1) != 0;
     P.use_tiled = env_int("PB200_TILED", 1);
     P.sm_count = device_setup(d->device);
     try {
@@ -1958,6 +2001,8 @@ int pb200_plan_set_collapse(pb200_plan* h, int32_t n_ops, const double* ops, uin
     const int d = P.dim;
     P.jump_ops.assign(n_ops, std::vector<cplx>((size_t)d * d));
     P.jump_ldl.assign(n_ops, std::vector<double>(d, 0.0));
+    P.jump_ldl_full.assign(n_ops, std::vector<cplx>((size_t)d * d, cplx(0)));
+    P.jump_diag = true;
     const cplx* src = reinterpret_cast<const cplx*>(ops);
     for (int op = 0; op < n_ops; ++op) {
         for (int q = 0; q < d * d; ++q) P.jump_ops[op][q] = src[(size_t)op * d * d + q];
@@ -1966,9 +2011,8 @@ int pb200_plan_set_collapse(pb200_plan* h, int32_t n_ops, const double* ops, uin
                 cplx acc = 0.0;  // (L^+ L)[a][b] = sum_c conj(L[c][a]) L[c][b]
                 for (int c = 0; c < d; ++c) acc += std::conj(P.jump_ops[op][c * d + a]) * P.jump_ops[op][c * d + b];
                 if (a == b) P.jump_ldl[op][a] = acc.real();
-                else if (std::abs(acc) > 1e-12)
-                    fail(PB200_ERR_UNSUPPORTED, "collapse operator %d: L^+L is not diagonal (wave-function Monte Carlo "
-                         "supports dephasing, relaxation, depolarizing and projector/transition-type operators)", op);
+                else if (std::abs(acc) > 1e-12) P.jump_diag = false;
+                P.jump_ldl_full[op][a * d + b] = acc;
             }
     }
     P.rng.seed(seed);

@@ -422,35 +422,6 @@ def test_fused_lanczos_equals_separate_update(engine, monkeypatch, kind):
         assert np.max(np.abs(g - _oracle_final(s1, psi0))) < STATE_TOL
 
 
-@pytest.mark.parametrize("integrator", [1, 2])
-def test_single_exponential_magnus_steps(engine, monkeypatch, integrator):
-    """Where only the detuning moves over a step, the 4th-order Magnus generator B0 + i[B0, B1] is itself
-    Pulser-shaped (drive g0 (1 - i th1)) and the step is ONE exponential (plan.cu add_step): fewer H-applies than
-    the two-exponential commutator-free step, same state within the north-star bound (uniform and per-atom drives)."""
-    from oracle import evolve
-
-    uni = W.config_c2(n=10, seed=20, t_rise=100, t_sweep=600, t_fall=100)
-    coords = W.disc_register(8, 30.0, 5.0, 3)
-    amp, det = W.blockade_sweep_waveforms(t_rise=100, t_sweep=500, t_fall=100)
-    base = W.ising_global_spec(coords, W.C6_LEVEL_60, amp, det)
-    rng = np.random.default_rng(1)
-    loc = W.noisy_trajectory_spec(base, coords, rng.normal(0, 0.6, 8), 0.97, 175.0)
-    for spec in (uni, loc):
-        psi0 = evolve.all_ground_state(spec)
-        ref = _oracle_final(spec, psi0)
-        out = {}
-        for mag4 in (1, 0):
-            monkeypatch.setenv("PB200_MAG4", str(mag4))
-            with engine.DevicePlan(spec) as plan:
-                plan.set_state("all-ground")
-                st = plan.propagate(0.0, spec.sampling_times[-1], integrator=integrator)
-                out[mag4] = (plan.get_state()[0], st)
-        for got, _ in out.values():
-            assert np.max(np.abs(got - ref)) < STATE_TOL
-        assert out[1][1]["n_exponentials"] < out[0][1]["n_exponentials"]
-        assert out[1][1]["n_applies"] < out[0][1]["n_applies"]
-
-
 # ---------------------------------------------------------------------------
 # measurement on the device
 def test_device_sampling_equals_reference_recipe(engine):
@@ -507,13 +478,36 @@ def test_mcwf_average_matches_master_equation(engine):
     assert np.all(np.abs(mean - ref) < 5 * sigma + 2e-3)
 
 
-def test_mcwf_rejects_non_diagonal_ldl(engine):
-    from pulser_b200._lib import PB200Error
+def test_mcwf_general_collapse_operators(engine):
+    """Collapse operators whose L^+L is NOT diagonal (general effective noise, hamiltonian.py:97-124): the no-jump
+    evolution applies exp(-tau sum L^+L) qudit by qudit and the jump weights come from the single-qudit reduced
+    density matrices.  Ensemble average against the Lindblad oracle."""
+    from oracle import evolve
+    from oracle.ref_hamiltonian import OracleHamiltonian
 
-    spec = _lindblad_spec(2, 100, [np.eye(2)])
-    with engine.DevicePlan(spec) as plan:
-        with pytest.raises(PB200Error, match="not diagonal"):
-            plan.set_collapse(np.array([[[1, 1], [0, 1]]], dtype=complex))
+    plus = np.array([1.0, 1.0]) / np.sqrt(2.0)
+    ops = [np.sqrt(1.8) * np.outer([0.0, 1.0], plus),            # |g><+| : L^+L = 1.8 |+><+|
+           np.sqrt(0.9) * np.array([[0.0, 1.0], [1.0, 0.0]]) * np.array([[1.0, 1.0], [1.0, -1.0]]) / np.sqrt(2.0)]
+    assert abs((ops[0].conj().T @ ops[0])[0, 1]) > 0.1           # genuinely non-diagonal
+    spec = _lindblad_spec(2, 300, ops)
+    tf = spec.sampling_times[-1]
+    psi0 = evolve.all_ground_state(spec)
+    rho = evolve.mesolve(OracleHamiltonian.from_spec(spec), psi0, [0.0, tf])[-1]
+    ref = np.real(np.diag(rho))
+    B = 3000
+    with engine.DevicePlan([spec] * B) as plan:
+        plan.set_collapse(np.asarray(ops, dtype=complex), seed=4321)
+        plan.set_state("all-ground")
+        plan.propagate(0.0, 0.4 * tf)
+        plan.propagate(0.4 * tf, tf)
+        probs = plan.probabilities()
+        jumps = plan.jump_counts()
+        n2 = plan.norm2()
+    np.testing.assert_allclose(n2, 1.0, atol=1e-9)
+    assert jumps.sum() > B // 20
+    mean = probs.mean(axis=0)
+    sigma = np.sqrt(np.maximum(ref * (1 - ref), 1e-4) / B)
+    assert np.all(np.abs(mean - ref) < 5 * sigma + 2e-3)
 
 
 @pytest.mark.parametrize("n,local_rows", [(2, False), (5, False), (9, True), (12, False), (13, True)])
