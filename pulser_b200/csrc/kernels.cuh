@@ -147,6 +147,13 @@ struct StageArgs {
     double* dot_acc;         // Lanczos: if set, acc[traj][0] += Re<lhs, out>, acc[traj][1] += <out, out> (fused reductions;
                              // lhs = v, or v_{j+1} in a fused Lanczos step)
     LanczosFuse lz;          // fused Lanczos step when lz.vj != nullptr (register-blocked kernels)
+    // partner-sum forwarding (stage_d2_fwd_kernel, uniform drives): w_in[s] = sum of v over the flips this stage
+    // does NOT perform (its producer's tile was closed under them), w_out[s] = the same sum of `out` over THIS
+    // stage's tile flips for the consumer.  Plane 0 ([D]) holds P = sum v[s^k]; plane 1 (at + D * n_traj) holds the
+    // signed sum Q a complex drive also needs.  Both may be null (first stage of a chain / nobody follows).
+    const c2* w_in;
+    c2* w_out;
+    long long w_plane;       // distance between the P and the Q plane
 };
 
 // up to two independent Clenshaw chains per launch (the h and the h/2 branches of a Richardson step):
@@ -602,6 +609,131 @@ stage_d2_rb_kernel(const __grid_constant__ StageArgs2 m) {
         __syncthreads();
     }
     rb_tile_compute<UNIFORM, REAL_G, TBITS, RB>(a, g, tile, tab, base, traj, tid, &mbar);
+}
+
+// ---- d = 2 stage kernel with partner-sum forwarding (uniform drives) ---------------------------------------------
+// The single-pass kernel above sits at the L2 throughput cap (~6300 B/clk chip-wide): (N - TBITS) x 16 B of partner
+// loads per amplitude dominate its L2 sectors (profiles/r02_l2_hint_experiment.json).  Here consecutive Clenshaw
+// stages alternate between two tile geometries with complementary flip sets -- A: the TBITS low bits; B: the
+// hb = min(N - TBITS, TBITS - 2) bits above them, gathered as 2^hb rows of 2^(TBITS - hb) amplitudes -- and a stage
+// receives the partner sums over the OTHER geometry's flips from the stage that produced its input (w_in, 16 B per
+// amplitude) and emits the sums of its own result over ITS flips (w_out): 104 B of L2 traffic per amplitude and stage
+// instead of 72 + 16 (N - TBITS).  Bits above TBITS + hb (N > 20) stay coalesced partner loads in both geometries.
+// Unlike the round-1 attempt (latency-bound: operand loads after the gathers, profiles/r02_forwarding_kernel_ncu_
+// summary.json) every global operand of the stage is requested BEFORE the wait on the tile copy and folded into the
+// accumulators as it arrives, so a CTA has one exposed memory latency.
+template <bool REAL_G, int TBITS, int RB>
+__global__ void __launch_bounds__(1 << (TBITS - RB), 2) stage_d2_fwd_kernel(const __grid_constant__ StageArgs2 m) {
+    constexpr int R = 1 << RB;
+    constexpr int NT = 1 << (TBITS - RB);
+    constexpr int TSIZE = 1 << TBITS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    c2* tile = reinterpret_cast<c2*>(smem_raw);
+    c2* rtile = tile + TSIZE;
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int chain = blockIdx.y / m.n_traj;
+    const StageArgs& a = m.a[chain];
+    const PassGeom g = a.geo;
+    const int tid = threadIdx.x;
+    const long long traj = blockIdx.y - chain * m.n_traj;
+    const long long base = tile_base_of(g, blockIdx.x);
+    const long long voff = traj * a.D;
+    const c2* vsrc = a.v + voff;
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    pdl_wait();
+    pdl_launch_dependents();
+    if (tid == 0) mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
+    {
+        const int rows = 1 << g.hi_bits;
+        const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
+        for (int r = tid; r < rows; r += NT)
+            tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+    }
+    const long long lomask = (1LL << g.lo_bits) - 1;
+    const long long fixed = base | (tid & lomask) | ((long long)(tid >> g.lo_bits) << g.hi_shift);
+    // the register-block bits are the top RB tile bits: their global positions
+    int pq[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+        const int j = TBITS - RB + q;
+        pq[q] = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+    }
+    auto idx_of = [&](int r) {
+        long long o = fixed;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) o |= (long long)((r >> q) & 1) << pq[q];
+        return o;
+    };
+    // ---- every global operand goes out now; each is folded into an accumulator as soon as it is used ----
+    double pr[R], pi[R], qr[R], qi[R];
+    c2 part[R];      // c_psi psi + c_b2 b2
+    double dg[R];    // scaled diagonal of the amplitude
+    {
+        const double* dsrc = a.dint ? a.dint + traj * a.dint_stride : nullptr;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long ix = idx_of(r);
+            c2 w0 = {0.0, 0.0}, w1 = {0.0, 0.0}, ps = {0.0, 0.0}, bb = {0.0, 0.0};
+            if (a.w_in) { w0 = ld_own(a.w_in + voff + ix); if (!REAL_G) w1 = ld_own(a.w_in + a.w_plane + voff + ix); }
+            if (a.psi) ps = ld_own(a.psi + voff + ix);
+            if (a.b2) bb = ld_own(a.b2 + voff + ix);
+            const double dv = dsrc ? __ldcs(dsrc + ix) : 0.0;
+            pr[r] = w0.x; pi[r] = w0.y; qr[r] = w1.x; qi[r] = w1.y;
+            part[r] = cadd(cmul(a.coef.c_psi, ps), cmul(a.coef.c_b2, bb));
+            const int ones = __popcll((unsigned long long)ix);
+            const int cnt = a.from_is_one ? ones : (g.n_bits - ones);
+            dg[r] = fma(-a.u.theta, (double)cnt, fma(a.u.w, dv, -a.u.gamma));
+        }
+    }
+    const int to_bit = a.to_bit;
+    // partners across the bits above both geometries (N > TBITS + hb): coalesced loads, also ahead of the wait
+    for (unsigned long long em = g.extra_mask; em; em &= em - 1) {
+        const int p = __ffsll((long long)em) - 1;
+        const double sg = (((base >> p) & 1) == to_bit) ? 1.0 : -1.0;
+        double2 raw[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) raw[r] = __ldg(reinterpret_cast<const double2*>(vsrc + (idx_of(r) ^ (1LL << p))));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            pr[r] += raw[r].x; pi[r] += raw[r].y;
+            if (!REAL_G) { qr[r] = fma(sg, raw[r].x, qr[r]); qi[r] = fma(sg, raw[r].y, qi[r]); }
+        }
+    }
+    mbar_wait(&mbar, 0);
+    const int jstart = __ffs(g.tile_flip_mask) - 1;
+    c2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = tile[tid + r * NT];
+    rb_tile_gather<true, REAL_G, TBITS, RB>(g, tile, nullptr, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
+    // ---- epilogue: out = part + c_g (diag v + g (P + w_in)) ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double dx = a.u.g.x * pr[r], dy = a.u.g.x * pi[r];
+        if (!REAL_G) { dx = fma(-a.u.g.y, qi[r], dx); dy = fma(a.u.g.y, qr[r], dy); }
+        const c2 gv = {fma(dg[r], v[r].x, dx), fma(dg[r], v[r].y, dy)};
+        const c2 res = cadd(part[r], cmul(a.coef.c_g, gv));
+        st_c2(a.out + voff + idx_of(r), res);
+        v[r] = res;
+    }
+    if (a.w_out) {
+        // sums of the RESULT over this tile's flips for the next stage (whose tile is not closed under them)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            rtile[tid + r * NT] = v[r];
+            pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
+        }
+        __syncthreads();
+        rb_tile_gather<true, REAL_G, TBITS, RB>(g, rtile, nullptr, tid, to_bit, jstart, false, v, pr, pi, qr, qi);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long ix = idx_of(r);
+            st_c2(a.w_out + voff + ix, c2{pr[r], pi[r]});
+            if (!REAL_G) st_c2(a.w_out + a.w_plane + voff + ix, c2{qr[r], qi[r]});
+        }
+    }
 }
 
 // ---- generic-d stage kernel (any dim, several drives; global gathers) -------

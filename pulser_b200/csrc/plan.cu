@@ -164,6 +164,8 @@ static int device_setup(int dev) {
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_RB_ATTR(11, 2) PB200_RB_ATTR(11, 3) PB200_RB_ATTR(12, 2) PB200_RB_ATTR(12, 3)
 #undef PB200_RB_ATTR
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     if (dev >= 0 && dev < PB200_MAX_DEVICES) sm_count[dev] = sms;
     return sms;
 }
@@ -236,6 +238,12 @@ struct Plan {
     // interval classification of the sampling grid (cache key = window, rough_tol) and the current smooth-step length
     struct FineCache { bool valid = false; int window = -1; double rtol = -1.0; std::vector<char> fine, jump; std::vector<int> dist; } fine_cache;
     double ctrl_Kc = -1.0; double ctrl_key = 0.0; double ctrl_t_end = -1e300;
+    // partner-sum forwarding between Clenshaw stages (stage_d2_fwd_kernel): geometry of a chain's first stage [0],
+    // of the high-bit tile [1] and of the later low-bit stages [2]; one buffer of forwarded sums per chain
+    bool use_fwd = true;            // PB200_FWD=0: single-pass stages only
+    bool fwd_now = false;           // decided per propagate call
+    PassGeom fwd_geo[3];
+    c2* wbuf[2] = {nullptr, nullptr};
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
     int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
@@ -328,6 +336,9 @@ struct StageIO {  // one Clenshaw stage of one chain
     const double* beta_dev = nullptr;
     double* dot_acc = nullptr;  // fused <v,out>, <out,out> (only honoured by the register-blocked d=2 kernels)
     const LanczosFuse* lz = nullptr;  // fused Lanczos step (single-pass register-blocked geometry only)
+    // partner-sum forwarding: 0 first stage of a chain (no forwarded input), 1 high-bit tile, 2 low-bit tile;
+    // `emit`: a later stage of the chain consumes the sums of this stage's result
+    int fwd_role = 0; bool fwd_emit = false; c2* wbuf = nullptr;
 };
 
 static StageArgs make_stage_args(const Plan& P, const PassGeom& geo, const StageIO& io, bool geo_is_last = true) {
@@ -450,6 +461,57 @@ static void launch_stage_multi(Plan& P, const std::vector<PassGeom>& passes, con
             ++launches;
         }
     }
+}
+
+// ---- partner-sum forwarding (uniform drives, Chebyshev chains) ----------------------------------------------------
+static bool fwd_eligible(const Plan& P, const std::vector<PassGeom>& passes) {
+    if (!P.use_fwd || !is_d2path(P) || P.force_v1 || !P.all_uniform() || P.B != 1) return false;
+    if (P.tile_bits != 11 || P.reg_bits != 3) return false;
+    if (passes.size() != 1 || passes[0].hi_bits != 0 || passes[0].lo_bits != 11) return false;
+    // Measured (profiles/r02_forwarding_ab.jsonl): the second in-tile gather and the 64-byte rows of the high-bit
+    // tile cost as much shared-memory / LSU time as the forwarded sums save in L2 traffic once N >= 20 (N = 20:
+    // 24.0 vs 21.9 us per apply, N = 22: 123 vs 93), while at N = 18 (256-byte rows) forwarding wins 5.55 vs 6.35 us:
+    // it is used for the registers in between only.
+    return P.n >= env_int("PB200_FWD_MIN_N", 17) && P.n <= env_int("PB200_FWD_MAX_N", 19);
+}
+
+static void plan_fwd_geometry(Plan& P) {
+    const int N = P.n, TB = P.tile_bits;
+    const int hb = std::min(N - TB, TB - 2);
+    const unsigned long long all = (N >= 64) ? ~0ULL : ((1ULL << N) - 1ULL);
+    const unsigned long long rest = all & ~((1ULL << (TB + hb)) - 1ULL);
+    PassGeom a{};
+    a.n_bits = N; a.lo_bits = TB; a.hi_shift = TB; a.hi_bits = 0; a.first_pass = 1;
+    a.tile_flip_mask = (1u << TB) - 1u;
+    a.extra_mask = all & ~((1ULL << TB) - 1ULL);
+    P.fwd_geo[0] = a;
+    a.extra_mask = rest;
+    P.fwd_geo[2] = a;
+    PassGeom b{};
+    b.n_bits = N; b.lo_bits = TB - hb; b.hi_shift = TB; b.hi_bits = hb; b.first_pass = 1;
+    b.tile_flip_mask = ((1u << hb) - 1u) << b.lo_bits;
+    b.extra_mask = rest;
+    P.fwd_geo[1] = b;
+}
+
+static void launch_stage_fwd(Plan& P, const StageIO* io, int n, long long& launches) {
+    bool real_g = true;
+    for (int c = 0; c < n; ++c) real_g = real_g && io[c].real_g;
+    const int tbits = P.tile_bits;
+    StageArgs2 m{};
+    for (int c = 0; c < n; ++c) {
+        StageArgs& a = m.a[c];
+        a = make_stage_args(P, P.fwd_geo[io[c].fwd_role], io[c], true);
+        a.w_in = (io[c].fwd_role > 0) ? io[c].wbuf : nullptr;
+        a.w_out = io[c].fwd_emit ? io[c].wbuf : nullptr;
+        a.w_plane = P.D * (long long)P.B;
+    }
+    m.n_traj = P.B;
+    dim3 grid((unsigned)(P.D >> tbits), (unsigned)(P.B * n));
+    const size_t smem = (size_t)2 * ((size_t)16 << tbits);
+    if (real_g) launch_k(stage_d2_fwd_kernel<true, 11, 3>, grid, dim3(256), smem, P.stream, P.use_pdl, m);
+    else launch_k(stage_d2_fwd_kernel<false, 11, 3>, grid, dim3(256), smem, P.stream, P.use_pdl, m);
+    ++launches;
 }
 
 static void launch_stage(Plan& P, const std::vector<PassGeom>& passes, const c2* v, const c2* psi, const c2* b2,
@@ -584,6 +646,7 @@ struct Chain {
     c2* out = nullptr;
     c2* scratch[2] = {nullptr, nullptr};
     long long applies = 0; double max_rho = 0.0;
+    int fwd_parity = 0; bool fwd_valid = false;   // partner-sum forwarding: geometry of the next stage, sums available
 
     bool done() const { return e >= prog->cheb.size(); }
     c2* result() const { return psi; }
@@ -616,6 +679,11 @@ struct Chain {
         io.ud = prog->ud[e];
         io.table = uniform ? nullptr : P.d_table + table_base + prog->offset[e];
         io.real_g = prog->real_g[e] != 0;
+        // partner-sum forwarding: this stage's geometry and whether a later stage of the chain consumes its sums
+        io.fwd_role = !fwd_valid ? 0 : (fwd_parity ? 1 : 2);
+        io.fwd_emit = !(j == 0 && e + 1 == prog->cheb.size());
+        fwd_parity = (io.fwd_role == 1) ? 0 : 1;
+        fwd_valid = io.fwd_emit;
         // shift the recurrence
         if (b1_buf == psi) { b2_kind = 2; kappa = b1_scale; b2_buf = nullptr; }
         else { b2_kind = 1; b2_buf = const_cast<c2*>(b1_buf); }
@@ -650,6 +718,9 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
     }
     long long launches = 0;
     StageIO io[2];
+    if (P.fwd_now)
+        for (int c = 0; c < n; ++c)
+            if (!P.wbuf[c]) P.wbuf[c] = (c2*)pool_alloc(P.desc.device, sizeof(c2) * (size_t)P.D * P.B * 2);
     if (P.has_diss && n != 1) fail(PB200_ERR_STATE, "internal: Lindblad splitting runs one chain at a time");
     while (true) {
         int k = 0;
@@ -661,10 +732,12 @@ static void run_chains(Plan& P, Chain* chains, int n, const std::vector<PassGeom
                     if (chains[c].j < 0 && chains[c].prog->pre_diss[e_before] > 0.0)
                         apply_dissipator(P, chains[c].psi, chains[c].prog->pre_diss[e_before], launches);
                 }
+                io[k].wbuf = P.wbuf[c];
                 chains[c].next(P, uniform, io[k++]);
             }
         if (k == 0) break;
-        launch_stage_multi(P, passes, io, k, uniform, launches);
+        if (P.fwd_now) launch_stage_fwd(P, io, k, launches);
+        else launch_stage_multi(P, passes, io, k, uniform, launches);
         if (P.has_diss && chains[0].e != e_before && chains[0].prog->post_diss[e_before] > 0.0)
             apply_dissipator(P, chains[0].psi, chains[0].prog->post_diss[e_before], launches);
     }
@@ -1135,7 +1208,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     const double eps = 1e-12;
     const int nt = (int)P.times.size();
     pb200_run_stats st{};
-    P.use_krylov = false;
+    P.use_krylov = false; P.fwd_now = false;
     const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
     std::vector<char> jump; std::vector<int> dist;
     const std::vector<char> fine = fine_intervals(P, 8, 1e-4, 0.05, jump, dist);
@@ -1401,7 +1474,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             build_tables(P, E, gm, rh1, scratch_tab, is_d2path(P));
             // ... or when the state no longer fits L2 (fewer, fatter iterations win once HBM-bound)
             kry = rh1 > env_int("PB200_KRYLOV_RHO_MILLI", 900) * 1e-3 ||
-                  (double)P.D * P.B * 16.0 > (double)env_int("PB200_KRYLOV_MIB", 96) * 1048576.0;
+                  (double)P.D * P.B * 16.0 > (double)env_int("PB200_KRYLOV_MIB", 64) * 1048576.0;
             (void)tb;
         }
         P.use_krylov = kry;
@@ -1409,6 +1482,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     const double rho_cap = P.use_krylov ? env_int("PB200_RHO_CAP_KRYLOV_MILLI", 12000) * 1e-3
                                         : env_int("PB200_RHO_CAP_MILLI", 3600) * 1e-3;
     const bool dual_ok = dual_chain_ok(P, passes) && !P.has_diss && !P.use_krylov;
+    P.fwd_now = !P.use_krylov && !P.has_diss && fwd_eligible(P, passes);
+    if (P.fwd_now) plan_fwd_geometry(P);
     // order of the one-step map whose error the controller / extrapolation sees: the Lindblad splitting is
     // a symmetric 2nd-order scheme whatever the order of its unitary part
     const int pw_base = P.has_diss ? 2 : ((order == 4) ? 4 : 2);
@@ -1753,6 +1828,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
+    P.use_fwd = env_int("PB200_FWD", 1) != 0;
     P.use_tiled = env_int("PB200_TILED", 1);
     P.sm_count = device_setup(d->device);
     try {
@@ -1786,6 +1862,7 @@ int pb200_plan_destroy(pb200_plan* h) {
     pool_free(dev, P.dint);
     pool_free(dev, P.d_table);
     pool_free(dev, P.d_scratch);
+    for (int i = 0; i < 2; ++i) pool_free(dev, P.wbuf[i]);
     if (P.own_stream && P.stream) cudaStreamDestroy(P.stream);
     delete h;
     return PB200_OK;

@@ -422,6 +422,51 @@ def test_fused_lanczos_equals_separate_update(engine, monkeypatch, kind):
         assert np.max(np.abs(g - _oracle_final(s1, psi0))) < STATE_TOL
 
 
+def _uniform_spec(kind, n):
+    if kind == "real":
+        return W.config_c2(n=n, seed=3, t_rise=40, t_sweep=80, t_fall=40)
+    amp, det = W.blockade_sweep_waveforms(t_rise=40, t_sweep=80, t_fall=40)
+    phase = 0.3 + 0.004 * np.arange(len(amp))
+    return W.ising_global_spec(W.disc_register(n, 38.0, 5.0, 3), W.C6_LEVEL_60, amp, det, phase=phase)
+
+
+@pytest.mark.parametrize("kind,n", [("real", 17), ("real", 20), ("real", 21), ("complex", 17), ("complex", 20)])
+def test_partner_sum_forwarding_equals_single_pass(engine, monkeypatch, kind, n):
+    """stage_d2_fwd_kernel (alternating tile geometries, forwarded partner sums) against the single-pass stage kernel
+    on the same Chebyshev chains: same H-applies, same launches, states equal to rounding.  N = 21 keeps one bit above
+    both geometries (coalesced partner loads in either)."""
+    spec = _uniform_spec(kind, n)
+    tf = spec.sampling_times[-1]
+    psi0 = random_state(spec.hilbert_dim, 5)
+    out = {}
+    monkeypatch.setenv("PB200_FWD_MAX_N", "30")   # the automatic rule keeps forwarding to 17 <= N <= 19
+    for fwd in (0, 1):
+        monkeypatch.setenv("PB200_FWD", str(fwd))
+        with engine.DevicePlan(spec) as plan:
+            plan.set_state(psi0)
+            st = plan.propagate(0.0, tf, integrator=1)
+            out[fwd] = (plan.get_state()[0].copy(), st)
+    assert np.max(np.abs(out[0][0] - out[1][0])) < 5e-13
+    assert out[0][1]["n_applies"] == out[1][1]["n_applies"]
+    assert out[0][1]["n_launches"] == out[1][1]["n_launches"]  # one launch per stage either way
+
+
+def test_partner_sum_forwarding_vs_oracle(engine, monkeypatch):
+    """The forwarding path against the tight-tolerance oracle at the smallest register it is used on (N = 17 is
+    beyond the oracle: force it at N = 14)."""
+    from oracle import evolve
+
+    monkeypatch.setenv("PB200_FWD_MIN_N", "14")
+    spec = W.config_c2(n=14, seed=20, t_rise=100, t_sweep=300, t_fall=100)
+    psi0 = evolve.all_ground_state(spec)
+    ref = _oracle_final(spec, psi0)
+    with engine.DevicePlan(spec) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, spec.sampling_times[-1], integrator=1)
+        got = plan.get_state()[0]
+    assert np.max(np.abs(got - ref)) < STATE_TOL
+
+
 # ---------------------------------------------------------------------------
 # measurement on the device
 def test_device_sampling_equals_reference_recipe(engine):
