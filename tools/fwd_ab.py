@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pulser_b200 import engine, workloads as W
 for n in [int(a) for a in sys.argv[1:]] or [18, 20, 22]:
     spec = W.config_c2(n=n)
+    os.environ["PB200_FWD_MAX_N"] = "30"   # A/B beyond the automatic 17 <= N <= 19 window
     for fwd in (0, 1):
         os.environ["PB200_FWD"] = str(fwd)
         with engine.DevicePlan(spec) as plan:
