@@ -93,9 +93,12 @@ typedef struct pb200_run_opts {
     int32_t extrapolate;      /* 0 / 1 (default): every smooth step is a step-doubling
                                  pair combined by Richardson extrapolation (6th
                                  order); -1: plain 4th-order steps */
-    int32_t integrator;       /* exponential of each Magnus step: 1 Chebyshev-Clenshaw,
-                                 2 Lanczos (Krylov), 0 auto (Lanczos for strongly
-                                 blockaded registers whose spectrum is wide) */
+    int32_t integrator;       /* 1 Chebyshev-Clenshaw / 2 Lanczos (Krylov) exponentials of
+                                 Richardson-CF4 Magnus steps; 3 time-dependent Taylor
+                                 series (one global drive of constant phase, d = 2, one
+                                 state: no Magnus error, ~1 H-apply per ns on C2);
+                                 0 auto: 3 where it applies, else 2 for strongly
+                                 blockaded / HBM-resident registers, else 1 */
 } pb200_run_opts;
 
 typedef struct pb200_run_stats {
@@ -108,7 +111,7 @@ typedef struct pb200_run_stats {
     int64_t n_checks;       /* step-doubling checks performed (adaptive mode) */
     double err_estimate;    /* accumulated local-error estimate (adaptive mode) */
     double mean_step_samples; /* average smooth-step length, in sampling intervals */
-    int64_t integrator;     /* 1 Chebyshev, 2 Lanczos: what the run used */
+    int64_t integrator;     /* 1 Chebyshev, 2 Lanczos, 3 Taylor: what the run used */
     int64_t n_rejected;     /* checked steps redone with a shorter step (adaptive mode) */
 } pb200_run_stats;
 
@@ -277,6 +280,17 @@ int pb200_host_interpolate(const double* x, const double* y, int32_t n,
  * out[0..1] = B0 = int S dt, out[2..3] = B1 = (1/(b-a)) int (t - (a+b)/2) S dt */
 int pb200_host_moments(const double* x, const double* y, int32_t n,
                        int32_t order, double a, double b, double* out4);
+/* Time-dependent Taylor propagator (integrator 3), host side.  Degree-p
+ * polynomial in u = (t-a)/h, u in [0,1], of the same interpolant of REAL samples
+ * y[n] on [a, a+h] (Chebyshev interpolation): coeffs[p+1] monomial coefficients,
+ * *resid = max |polynomial - interpolant| on the step.  p <= 8. */
+int pb200_host_taylor_fit(const double* x, const double* y, int32_t n,
+                          int32_t order, double a, double h, int32_t p,
+                          double* coeffs, double* resid);
+/* Order K of the Taylor series of a step of length h whose generator obeys
+ * |H_j| <= m[j] (j = 0..p): smallest K with remainder bound *tail_out <= tol. */
+int pb200_host_taylor_order(double h, const double* m, int32_t p, double tol,
+                            int32_t* order_out, double* tail_out);
 /* Chebyshev coefficients a_j of exp(-i*rho*x) on [-1,1], truncated at tol:
  * writes up to cap (re,im) pairs, returns the count through *count. */
 int pb200_host_chebyshev(double rho, double tol, double* out, int32_t cap,

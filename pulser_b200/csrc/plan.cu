@@ -164,6 +164,8 @@ static int device_setup(int dev) {
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_RB_ATTR(11, 2) PB200_RB_ATTR(11, 3) PB200_RB_ATTR(12, 2) PB200_RB_ATTR(12, 3)
 #undef PB200_RB_ATTR
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     if (dev >= 0 && dev < PB200_MAX_DEVICES) sm_count[dev] = sms;
@@ -244,6 +246,11 @@ struct Plan {
     bool fwd_now = false;           // decided per propagate call
     PassGeom fwd_geo[3];
     c2* wbuf[2] = {nullptr, nullptr};
+    // time-dependent Taylor propagator: drive projected on its constant phase, half-width of H at the sampling times,
+    // extra ring buffers (beyond buf / aux) for polynomial degrees > 2
+    struct TaylorCache { bool valid = false, ok = false; c2 unit{1.0, 0.0}; PiecewiseCubic<double> om; std::vector<double> w_knot; } tay;
+    std::vector<c2*> tay_ws;
+    bool use_taylor = true;         // PB200_TAYLOR=0: never chosen automatically
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
     int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
@@ -1378,6 +1385,11 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     if (stats) *stats = st;
 }
 
+static bool taylor_prepare(Plan& P);
+static bool taylor_worthwhile(const Plan& P, double gtol);
+static bool taylor_geometry(const Plan& P, const std::vector<PassGeom>& passes, bool& use_rb);
+static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats);
+
 static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats) {
     if (!P.state_set) fail(PB200_ERR_STATE, "pb200_propagate: no state set (call pb200_state_set first)");
     for (int tr = 0; tr < P.B; ++tr)
@@ -1389,6 +1401,27 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         fail(PB200_ERR_INVALID, "pb200_propagate: [%g, %g] outside sampling times [%g, %g]", t_start, t_stop, tlo, thi);
     t_start = std::max(t_start, tlo); t_stop = std::min(t_stop, thi);
     if (P.has_collapse) { propagate_mcwf(P, t_start, t_stop, o, stats); return; }
+    {   // integrator 3 / auto: the time-dependent Taylor propagator wherever it applies (global drive of constant
+        // phase, d = 2, one state) unless the caller steers the Magnus controller explicitly
+        const int req = o ? o->integrator : 0;
+        if (req < 0 || req > 3) fail(PB200_ERR_INVALID, "integrator must be 0 (auto), 1, 2 or 3");
+        bool want = req == 3;
+        if (req == 0 && P.use_taylor) {
+            const bool steered = o && (o->max_step_samples > 0 || o->tol < 0.0 || o->extrapolate < 0 || o->check_every > 0 ||
+                                       o->cheb_tol > 0.0 || (o->magnus_order != 0 && o->magnus_order != 4));
+            const double hi_mean = (thi - tlo) / std::max((int)P.times.size() - 1, 1);
+            want = !steered && (t_stop - t_start) >= 4.0 * hi_mean;
+        }
+        if (want) {
+            bool use_rb = false;
+            const bool ok = taylor_prepare(P) && taylor_geometry(P, plan_passes(P.n, P.tile_bits, P.max_extra), use_rb) &&
+                            (req == 3 || taylor_worthwhile(P, (o && o->tol > 0.0) ? o->tol : 1e-8));
+            if (ok) { propagate_taylor(P, t_start, t_stop, o, stats); return; }
+            if (req == 3)
+                fail(PB200_ERR_UNSUPPORTED, "integrator 3 (Taylor) needs one global drive of constant phase on a d = 2 register, "
+                                            "a single state, no collapse operators / SLM mask");
+        }
+    }
     const double gtol = (o && o->tol != 0.0) ? o->tol : (P.has_diss ? 1e-6 : 1e-8);
     // Richardson extrapolation: on by default (extrapolate = 0 or 1), -1 switches it off
     const bool extrap = !(o && o->extrapolate < 0);
@@ -1683,6 +1716,389 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (stats) *stats = st;
 }
 
+// ---- time-dependent Taylor propagator (global drive of constant phase, d = 2) --------------------------------------
+// Replaces the whole Magnus / exponential machinery above where it applies (C2, C5): the interpolated coefficients
+// are polynomials in u = (t-a)/h on a step, the solution is the Taylor series in u (kernels.cuh,
+// stage_d2_taylor_kernel), one H-apply per order.  A step spans rho = h W ~ 10 (W = spectral half-width) instead of
+// the ~1.5 a Richardson-CF4 exponential manages, and pays no Chebyshev start-up per exponential: ~1 H-apply per ns on
+// C2 against 6.9.  Error = fit residual of the splines (measured) + Taylor remainder (majorant bound) -- both a priori,
+// so a run never synchronises with the host.
+
+// real part of the drive along its constant phase, and the half-width of H(t) at every sampling time
+static bool taylor_prepare(Plan& P) {
+    Plan::TaylorCache& C = P.tay;
+    if (!(is_d2path(P) && P.all_uniform() && P.B == 1)) return false;
+    if (P.has_diss || P.has_collapse || P.has_slm || P.force_v1) return false;
+    if (P.desc.interp_order != 3 && P.desc.interp_order != 1) return false;
+    if (C.valid) return C.ok;
+    C.valid = true; C.ok = false;
+    const DriveTables& T = P.tabs[0][0];
+    if (T.coef.size() != 1 || T.det.size() != 1) return false;
+    const PiecewiseCubic<cplx>& pc = T.coef[0];
+    const int np = pc.pieces();
+    cplx big = pc.y_last;
+    for (int i = 0; i < np; ++i) if (std::abs(pc.c0[i]) > std::abs(big)) big = pc.c0[i];
+    const double scale = std::abs(big);
+    const cplx unit = scale > 0.0 ? big / scale : cplx(1.0, 0.0);
+    C.om = PiecewiseCubic<double>();
+    C.om.c0.resize(np); C.om.c1.resize(np); C.om.c2.resize(np); C.om.c3.resize(np);
+    const cplx cu = std::conj(unit);
+    for (int i = 0; i < np; ++i) {
+        const double hi = P.times[i + 1] - P.times[i];
+        const cplx v0 = pc.c0[i] * cu, v1 = pc.c1[i] * cu, v2 = pc.c2[i] * cu, v3 = pc.c3[i] * cu;
+        const double im = std::max(std::max(std::fabs(v0.imag()), std::fabs(v1.imag()) * hi),
+                                   std::max(std::fabs(v2.imag()) * hi * hi, std::fabs(v3.imag()) * hi * hi * hi));
+        if (im > 1e-13 * scale) return false;   // the phase moves: not a single real polynomial
+        C.om.c0[i] = v0.real(); C.om.c1[i] = v1.real(); C.om.c2[i] = v2.real(); C.om.c3[i] = v3.real();
+    }
+    C.om.y_last = (pc.y_last * cu).real();
+    C.unit = {unit.real(), unit.imag()};
+    C.ok = true;
+    return true;
+}
+
+// Is the Taylor propagator the cheaper choice?  A cubic spline through samples of a curved function deviates from
+// every smooth function by ~ |4th difference| / 384 per interval; where that floor exceeds what the fit may leave
+// behind, no polynomial spans more than one sampling interval and a step costs ~10 H-applies per interval -- more than
+// the Magnus path.  Worth it when at most a quarter of the intervals are like that (C2 / C5: only those at the kinks).
+static bool taylor_worthwhile(const Plan& P, double gtol) {
+    const int nt = (int)P.times.size();
+    if (nt < 8) return false;
+    const double rate = gtol / std::max(P.times.back() - P.times.front(), 1e-30);
+    const double allow = 0.25 * rate / P.n;
+    const PiecewiseCubic<double>* pcs[2] = {&P.tay.om, &P.tabs[0][0].det[0]};
+    std::vector<char> rough(nt, 0);
+    for (const PiecewiseCubic<double>* pc : pcs) {
+        const int np = pc->pieces();
+        auto y = [&](int i) { return i < np ? pc->c0[i] : pc->y_last; };
+        for (int i = 2; i + 2 < nt; ++i) {
+            const double d4 = std::fabs(y(i + 2) - 4.0 * y(i + 1) + 6.0 * y(i) - 4.0 * y(i - 1) + y(i - 2));
+            if (d4 / 384.0 > allow) rough[i] = 1;
+        }
+    }
+    int cnt = 0;
+    for (char c : rough) cnt += c;
+    return 4 * cnt <= nt;
+}
+
+// centre and half-width of  Dint - th n_from + om X  (rigorous bounds, the ones the Chebyshev path uses)
+static void taylor_bounds(const Plan& P, double om, double th, double& centre, double& half) {
+    ExpParams E;
+    const cplx g = om * cplx(P.tay.unit.x, P.tay.unit.y);
+    E.g.assign((size_t)P.n, g); E.th.assign((size_t)P.n, th); E.w = 1.0;
+    std::vector<double> scratch_tab;
+    build_tables(P, E, centre, half, scratch_tab, true);
+}
+
+struct TaylorPoly {      // monomial coefficients in u of one coefficient function on a step, and the fit residual
+    std::vector<double> c;
+    double resid = 0.0;
+};
+
+// degree-p Chebyshev interpolant of the spline on [a, a+h], as monomials in u = (t-a)/h; residual on a fine grid
+static TaylorPoly taylor_fit(const PiecewiseCubic<double>& pc, const std::vector<double>& x, int order, double a, double h,
+                             int p) {
+    typedef long double ld;
+    const ld PI = 3.14159265358979323846264338327950288L;
+    const int m = p + 1;
+    std::vector<ld> f(m), ck(m, 0.0L);
+    for (int i = 0; i < m; ++i) {
+        const ld xi = cosl(PI * (2 * i + 1) / (2.0L * m));
+        f[i] = (ld)eval_at(pc, x, a + h * (double)(0.5L * (xi + 1.0L)), order);
+    }
+    for (int k = 0; k < m; ++k) {
+        ld s = 0.0L;
+        for (int i = 0; i < m; ++i) s += f[i] * cosl(PI * k * (2 * i + 1) / (2.0L * m));
+        ck[k] = s * (k == 0 ? 1.0L : 2.0L) / m;
+    }
+    // Chebyshev series in x -> monomials in x
+    std::vector<ld> mono(m, 0.0L), Tm2(m, 0.0L), Tm1(m, 0.0L), Tk(m, 0.0L);
+    Tm2[0] = 1.0L;                       // T_0
+    mono[0] += ck[0];
+    if (m > 1) { Tm1[1] = 1.0L; for (int i = 0; i < m; ++i) mono[i] += ck[1] * Tm1[i]; }
+    for (int k = 2; k < m; ++k) {
+        for (int i = 0; i < m; ++i) Tk[i] = (i > 0 ? 2.0L * Tm1[i - 1] : 0.0L) - Tm2[i];
+        for (int i = 0; i < m; ++i) mono[i] += ck[k] * Tk[i];
+        Tm2 = Tm1; Tm1 = Tk;
+    }
+    // x = 2u - 1
+    std::vector<ld> cu(m, 0.0L), pw(m, 0.0L), nx(m, 0.0L);
+    pw[0] = 1.0L;                        // (2u - 1)^0
+    for (int k = 0; k < m; ++k) {
+        for (int i = 0; i < m; ++i) cu[i] += mono[k] * pw[i];
+        for (int i = 0; i < m; ++i) nx[i] = (i > 0 ? 2.0L * pw[i - 1] : 0.0L) - pw[i];
+        pw = nx;
+    }
+    TaylorPoly out;
+    out.c.resize(m);
+    for (int i = 0; i < m; ++i) out.c[i] = (double)cu[i];
+    // residual: 4 points per sampling interval inside the step (at least 9 points)
+    const int ia = find_piece(x, a + 1e-15), ib = find_piece(x, a + h - 1e-15);
+    const int npts = std::max(9, 4 * (ib - ia + 1) + 1);
+    double r = 0.0;
+    for (int q = 0; q < npts; ++q) {
+        const double u = (double)q / (npts - 1);
+        double pv = 0.0;
+        for (int i = m - 1; i >= 0; --i) pv = pv * u + out.c[i];
+        r = std::max(r, std::fabs(pv - eval_at(pc, x, a + h * u, order)));
+    }
+    out.resid = r;
+    return out;
+}
+
+// Taylor order from the scalar majorant  y' = h m(u) y,  m(u) = sum_j m_j u^j >= |H~(u)|:  |chi_k| <= y_k with
+// (k+1) y_{k+1} = h sum_j m_j y_{k-j}.  Returns the smallest K whose remainder sum_{k>K} y_k is below tol.
+static int taylor_order(double h, const std::vector<double>& mj, double tol, double& tail_out) {
+    const int p = (int)mj.size() - 1;
+    std::vector<double> y(1, 1.0);
+    const int kcap = 1200;
+    for (int k = 0; k < kcap; ++k) {
+        double s = 0.0;
+        for (int j = 0; j <= std::min(p, k); ++j) s += mj[j] * y[k - j];
+        y.push_back(h * s / (k + 1));
+        if (k > 8 && y.back() < 1e-40 && y.back() < y[k]) break;
+    }
+    double tail = 0.0;
+    int kk = (int)y.size() - 1;
+    for (; kk >= 1; --kk) {
+        if (tail + y[kk] > tol) break;
+        tail += y[kk];
+    }
+    tail_out = tail;
+    return std::max(kk, 1);
+}
+
+static void launch_taylor_stage(Plan& P, const PassGeom* geo, const TaylorArgs& a, long long& launches) {
+    if (geo) {
+        dim3 grid((unsigned)(P.D >> 11)), block(256);
+        const size_t smem = (size_t)2048 * 16;
+        const bool real_g = a.unit.y == 0.0;
+        if (real_g) launch_k(stage_d2_taylor_kernel<true, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
+        else launch_k(stage_d2_taylor_kernel<false, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
+    } else {
+        const unsigned blocks = (unsigned)((P.D + 255) / 256);
+        stage_d2_taylor_small_kernel<<<blocks, 256, 0, P.stream>>>(a);
+    }
+    ++launches;
+}
+
+// geometry of the Taylor stage: the register-blocked single-pass kernel, or the plain kernel for small registers
+static bool taylor_geometry(const Plan& P, const std::vector<PassGeom>& passes, bool& use_rb) {
+    use_rb = passes.size() == 1 && passes[0].first_pass && passes[0].hi_bits == 0 && passes[0].lo_bits == 11 &&
+             P.tile_bits == 11 && P.reg_bits == 3;
+    return use_rb || P.n <= 16;
+}
+
+static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats) {
+    const double tlo = P.times.front(), thi = P.times.back();
+    const double eps = 1e-12;
+    const double gtol = (o && o->tol > 0.0) ? o->tol : 1e-8;
+    const double rate = gtol / std::max(thi - tlo, 1e-30);       // error budget per unit of time
+    const double rho_target = env_int("PB200_TAYLOR_RHO_MILLI", 10000) * 1e-3;
+    const int pmax = std::min(PB200_TAYLOR_PMAX, std::max(1, env_int("PB200_TAYLOR_P", PB200_TAYLOR_PMAX)));
+    const int order = P.desc.interp_order;
+    const int N = P.n;
+    const int nt = (int)P.times.size();
+    const std::vector<PassGeom> passes = plan_passes(P.n, P.tile_bits, P.max_extra);
+    bool use_rb = false;
+    if (!taylor_geometry(P, passes, use_rb)) fail(PB200_ERR_UNSUPPORTED, "Taylor propagator: unsupported register size");
+    const PiecewiseCubic<double>& om_pc = P.tay.om;
+    const PiecewiseCubic<double>& th_pc = P.tabs[0][0].det[0];
+    Plan::TaylorCache& C = P.tay;
+    if ((int)C.w_knot.size() != nt) {   // half-width of H at every sampling time (step-length rule)
+        C.w_knot.resize(nt);
+        for (int i = 0; i < nt; ++i) {
+            double c, hw;
+            taylor_bounds(P, eval_at(om_pc, P.times, P.times[i], order), eval_at(th_pc, P.times, P.times[i], order), c, hw);
+            C.w_knot[i] = hw;
+        }
+    }
+    pb200_run_stats st{};
+    EventPair evs;
+    CUDA_CHECK(cudaEventRecord(evs.a, P.stream));
+    ensure_aux_buffers(P);
+
+    // fit of both coefficient functions on [a, a+h] with the smallest degrees that meet the residual budget
+    // The fit error is budgeted over the call: 50 % of its share of the tolerance (10 % goes to the Taylor remainders).  Smooth stretches fit to rounding
+    // and spend nothing, so a step may also use 2 % of what is still unspent -- this is what shortens the stretches of
+    // one-interval steps around a non-smooth sample, where the not-a-knot spline rings with a factor 0.268 per
+    // interval (|dH| <= (r_om + r_th) N, state error <= h |dH|).
+    const double fit_total = 0.5 * rate * (t_stop - t_start);
+    double fit_spent = 0.0;
+    struct Fit { TaylorPoly om, th; bool ok; };
+    auto fit_step = [&](double a, double h, bool single_piece) {
+        Fit F; F.ok = false;
+        const double budget = std::max(0.5 * rate * h, 0.02 * std::max(fit_total - fit_spent, 0.0));
+        const double allow = budget / (h * N) * 0.5;
+        bool ok_om = false, ok_th = false;
+        for (int p = 0; p <= pmax && !ok_om; ++p) {
+            F.om = taylor_fit(om_pc, P.times, order, a, h, p);
+            ok_om = F.om.resid <= allow || (single_piece && p >= 3);
+        }
+        for (int p = 0; p <= pmax && !ok_th; ++p) {
+            F.th = taylor_fit(th_pc, P.times, order, a, h, p);
+            ok_th = F.th.resid <= allow || (single_piece && p >= 3);
+        }
+        F.ok = ok_om && ok_th;
+        return F;
+    };
+
+    double t = t_start;
+    double steps_len = 0.0;
+    double t_retry_len = 0.0;   // > 0: the previous attempt at this step overshot rho; cap on the step length
+    while (t < t_stop - eps) {
+        const int i0 = find_piece(P.times, t + eps);
+        // longest candidate: accumulate rho over the sampling intervals
+        double b = t;
+        {
+            double acc = 0.0;
+            int i = i0;
+            double cur = t;
+            while (i < nt - 1) {
+                const double e1 = std::min(P.times[i + 1], t_stop);
+                const double w = std::max(C.w_knot[i], C.w_knot[i + 1]);
+                const double need = w * (e1 - cur);
+                if (acc + need > rho_target) {
+                    if (i == i0 || acc == 0.0) b = cur + (rho_target - acc) / std::max(w, 1e-300);  // inside the first interval
+                    else b = cur;
+                    break;
+                }
+                acc += need; cur = e1; b = e1; ++i;
+                if (e1 >= t_stop - eps) break;
+            }
+            b = std::min(b, t_stop);
+            if (t_retry_len > 0.0) { b = std::min(b, t + t_retry_len); t_retry_len = 0.0; }
+            if (b <= t + eps) b = std::min(P.times[i0 + 1], t_stop);
+        }
+        // longest step on which both splines are polynomials of degree <= pmax to within the budget: bisection over
+        // the number of whole sampling intervals beyond the first one (a step inside one interval is a cubic: exact)
+        Fit F;
+        {
+            bool single = b <= P.times[i0 + 1] + eps;
+            F = fit_step(t, b - t, single);
+            if (!F.ok && !single) {
+                int lo_keep = 0, hi_keep = find_piece(P.times, b - eps) - i0;   // lo passes (one interval), hi fails
+                Fit Flo; bool have_lo = false;
+                while (hi_keep - lo_keep > 1) {
+                    const int mid = (lo_keep + hi_keep) / 2;
+                    const double bm = P.times[i0 + 1 + mid];
+                    Fit Fm = fit_step(t, bm - t, false);
+                    if (Fm.ok) { lo_keep = mid; Flo = Fm; have_lo = true; } else hi_keep = mid;
+                }
+                b = P.times[i0 + 1 + lo_keep];
+                single = lo_keep == 0;
+                F = have_lo ? Flo : fit_step(t, b - t, single);
+            }
+        }
+        double h = b - t;
+        // strip trailing zero coefficients
+        auto trim = [](std::vector<double>& c, double scale) {
+            while (c.size() > 1 && std::fabs(c.back()) <= 1e-15 * scale) c.pop_back();
+        };
+        {
+            double so = 0.0, sh = 0.0;
+            for (double v : F.om.c) so = std::max(so, std::fabs(v));
+            for (double v : F.th.c) sh = std::max(sh, std::fabs(v));
+            trim(F.om.c, std::max(so, 1e-300)); trim(F.th.c, std::max(sh, 1e-300));
+        }
+        const int p_om = (int)F.om.c.size() - 1, p_th = (int)F.th.c.size() - 1;
+        const int p = std::max(p_om, p_th);
+        // centres and norm bounds of H_j
+        std::vector<double> gam(p + 1, 0.0), mj(p + 1, 0.0);
+        {
+            double c0, hw0;
+            taylor_bounds(P, F.om.c[0], F.th.c[0], c0, hw0);
+            gam[0] = c0; mj[0] = hw0;
+            const bool from_counts = true;
+            (void)from_counts;
+            for (int j = 1; j <= p; ++j) {
+                const double thj = j <= p_th ? F.th.c[j] : 0.0, omj = j <= p_om ? F.om.c[j] : 0.0;
+                gam[j] = -thj * 0.5 * N;
+                mj[j] = std::fabs(thj) * 0.5 * N + std::fabs(omj) * N;
+            }
+        }
+        {   // the fp64 cancellation of the series grows like e^rho: a step whose majorant exponent overshoots the
+            // target (the half-width grew inside the step) is cut and fitted again
+            double rho_eff = 0.0;
+            for (int j = 0; j <= p; ++j) rho_eff += mj[j] / (j + 1);
+            rho_eff *= h;
+            if (rho_eff > 1.3 * rho_target && h > 1e-9) {
+                t_retry_len = h * rho_target / rho_eff;
+                continue;
+            }
+        }
+        double trunc_bound = 0.0;
+        const int K = taylor_order(h, mj, std::max(1e-15, 0.1 * rate * h), trunc_bound);
+        // buffers: chi ring (slot 0 = the current state), G ring, accumulator
+        const int n_chi = p_th + 2;
+        const int n_g = p_om >= 1 ? p_om + 1 : 0;
+        std::vector<c2**> free_slots;
+        for (int i = 0; i < 3; ++i) if (i != P.cur) free_slots.push_back(&P.buf[i]);
+        for (int i = 0; i < 6; ++i) free_slots.push_back(&P.aux[i]);
+        const int need = (n_chi - 1) + n_g + 1;
+        while ((int)free_slots.size() + (int)P.tay_ws.size() < need)
+            P.tay_ws.push_back((c2*)pool_alloc(P.desc.device, sizeof(c2) * (size_t)P.D * P.B));
+        for (size_t i = 0; i < P.tay_ws.size(); ++i) free_slots.push_back(&P.tay_ws[i]);
+        std::vector<c2*> chi(n_chi), gr(n_g);
+        int fs = 0;
+        chi[0] = P.buf[P.cur];
+        for (int i = 1; i < n_chi; ++i) chi[i] = *free_slots[fs++];
+        for (int i = 0; i < n_g; ++i) gr[i] = *free_slots[fs++];
+        c2** acc_slot = free_slots[fs++];
+        c2* acc = *acc_slot;
+        // phase of the scalar centre: exp(-i h int_0^1 sum_j gam_j u^j du)
+        double phi = 0.0;
+        for (int j = 0; j <= p; ++j) phi += gam[j] / (j + 1);
+        phi *= h;
+        long long launches = 0;
+        for (int k = 0; k < K; ++k) {
+            TaylorArgs a{};
+            a.v = chi[k % n_chi]; a.out = chi[(k + 1) % n_chi];
+            a.g_out = (n_g && k + 1 < K) ? gr[k % n_g] : nullptr;
+            a.acc = acc;
+            a.dint = P.has_interaction ? P.dint : nullptr;
+            a.D = P.D;
+            a.geo = passes[0];
+            a.unit = C.unit;
+            a.to_bit = P.desc.drives[0].state_to; a.from_is_one = P.desc.drives[0].state_from;
+            a.th0 = F.th.c[0]; a.gam0 = gam[0]; a.om0 = F.om.c[0];
+            a.scale = {0.0, -h / (k + 1)};
+            a.nh = std::min(p, k);
+            for (int j = 1; j <= a.nh; ++j) {
+                const double thj = j <= p_th ? F.th.c[j] : 0.0, omj = j <= p_om ? F.om.c[j] : 0.0;
+                a.hth[j - 1] = thj; a.hgam[j - 1] = gam[j]; a.hom[j - 1] = omj;
+                a.hchi[j - 1] = (thj != 0.0 || gam[j] != 0.0) ? chi[(k - j) % n_chi] : nullptr;
+                a.hg[j - 1] = (omj != 0.0) ? gr[(k - j) % n_g] : nullptr;
+            }
+            const bool last = (k + 1 == K);
+            if ((k & 1) == 0) { a.acc_on = 1; a.acc_add_v = 1; a.acc_read = k > 0; }
+            else { a.acc_on = last ? 1 : 0; a.acc_add_v = 0; a.acc_read = 1; }
+            a.acc_mul = last ? c2{std::cos(phi), -std::sin(phi)} : c2{1.0, 0.0};
+            launch_taylor_stage(P, use_rb ? &passes[0] : nullptr, a, launches);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        // the accumulator becomes the current state buffer
+        std::swap(P.buf[P.cur], *acc_slot);
+        st.n_launches += launches; st.n_applies += K; st.n_exponentials += 1; ++st.n_steps;
+        double rho_eff = 0.0;
+        for (int j = 0; j <= p; ++j) rho_eff += mj[j] / (j + 1);
+        st.max_rho = std::max(st.max_rho, rho_eff * h);
+        st.err_estimate += trunc_bound + h * N * (F.om.resid + F.th.resid);
+        fit_spent += h * N * (F.om.resid + F.th.resid);
+        steps_len += h;
+        t = b;
+    }
+    CUDA_CHECK(cudaEventRecord(evs.b, P.stream));
+    CUDA_CHECK(cudaEventSynchronize(evs.b));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, evs.a, evs.b));
+    st.gpu_ms = ms;
+    const double hi_mean = (thi - tlo) / std::max(nt - 1, 1);
+    st.mean_step_samples = st.n_steps ? steps_len / st.n_steps / hi_mean : 0.0;
+    st.integrator = 3;
+    if (stats) *stats = st;
+}
+
 // H(t) parameters as an "exponential" description with w = 1 (for apply_h)
 static ExpParams params_at(const Plan& P, double t) {
     ExpParams E;
@@ -1828,6 +2244,7 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_dual = env_int("PB200_DUAL", 1) != 0;
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
+    P.use_taylor = env_int("PB200_TAYLOR", 1) != 0;
     P.use_fwd = env_int("PB200_FWD", 1) != 0;
     P.use_tiled = env_int("PB200_TILED", 1);
     P.sm_count = device_setup(d->device);
@@ -1863,6 +2280,7 @@ int pb200_plan_destroy(pb200_plan* h) {
     pool_free(dev, P.d_table);
     pool_free(dev, P.d_scratch);
     for (int i = 0; i < 2; ++i) pool_free(dev, P.wbuf[i]);
+    for (c2* w : P.tay_ws) pool_free(dev, w);
     if (P.own_stream && P.stream) cudaStreamDestroy(P.stream);
     delete h;
     return PB200_OK;
@@ -1954,6 +2372,7 @@ int pb200_plan_set_interaction(pb200_plan* h, int32_t traj0, int32_t count, cons
       }
     pool_free(P.desc.device, dU);
     P.has_interaction = true;
+    P.tay.w_knot.clear();
     PB200_CATCH
 }
 
@@ -2046,7 +2465,7 @@ int pb200_plan_set_drive(pb200_plan* h, int32_t drive, int32_t traj0, int32_t co
             }
         }
         P.tabs_set[traj0 + c][drive] = true;
-        P.fine_cache.valid = false; P.ctrl_Kc = -1.0;
+        P.fine_cache.valid = false; P.ctrl_Kc = -1.0; P.tay.valid = false; P.tay.w_knot.clear();
     }
     PB200_CATCH
 }
@@ -2445,6 +2864,27 @@ int pb200_host_moments(const double* x, const double* y, int32_t n, int32_t orde
     cplx b0, b1;
     magnus_moments(pc, xs, a, b, b0, b1);
     out4[0] = b0.real(); out4[1] = b0.imag(); out4[2] = b1.real(); out4[3] = b1.imag();
+    PB200_CATCH
+}
+
+int pb200_host_taylor_fit(const double* x, const double* y, int32_t n, int32_t order, double a, double h, int32_t p,
+                          double* coeffs, double* resid) {
+    PB200_TRY
+    if (!x || !y || !coeffs || n < 2 || p < 0 || p > PB200_TAYLOR_PMAX || !(h > 0.0)) fail(PB200_ERR_INVALID, "bad argument");
+    std::vector<double> xs(x, x + n);
+    auto pc = make_interpolant<double>(x, y, n, order);
+    const TaylorPoly f = taylor_fit(pc, xs, order, a, h, p);
+    for (int i = 0; i <= p; ++i) coeffs[i] = f.c[i];
+    if (resid) *resid = f.resid;
+    PB200_CATCH
+}
+
+int pb200_host_taylor_order(double h, const double* m, int32_t p, double tol, int32_t* order_out, double* tail_out) {
+    PB200_TRY
+    if (!m || !order_out || p < 0 || p > PB200_TAYLOR_PMAX) fail(PB200_ERR_INVALID, "bad argument");
+    double tail = 0.0;
+    *order_out = taylor_order(h, std::vector<double>(m, m + p + 1), tol, tail);
+    if (tail_out) *tail_out = tail;
     PB200_CATCH
 }
 

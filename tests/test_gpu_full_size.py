@@ -40,22 +40,24 @@ def test_apply_h_at_configured_size_vs_matrix_free_oracle(engine, name):
 
 
 def test_c5_whole_sequence(engine):
-    """configs[4]: 24 atoms, 4000 ns, Krylov propagator.  The Lanczos run (what the auto rule picks at this size)
-    agrees with the Chebyshev run and with a 1000x tighter controller to the north-star 1e-8."""
+    """configs[4]: 24 atoms, 4000 ns.  The Taylor run (what the auto rule picks for a global drive of constant phase),
+    the Lanczos (Krylov) run, the Chebyshev run and a 1000x tighter Krylov run agree to the north-star 1e-8."""
     spec = W.config_c5(n=24)
     tf = spec.sampling_times[-1]
     outs = {}
     with engine.DevicePlan(spec) as plan:
-        for key, kw in (("auto", {}), ("cheb", {"integrator": 1}), ("tight", {"tol": 1e-11})):
+        for key, kw in (("auto", {}), ("lanczos", {"integrator": 2}), ("cheb", {"integrator": 1}),
+                        ("tight", {"integrator": 2, "tol": 1e-11})):
             plan.set_state("all-ground")
             st = plan.propagate(0.0, tf, **kw)
             assert abs(plan.norm2()[0] - 1.0) < 1e-9
             outs[key] = (plan.get_state()[0], st)
-    assert outs["auto"][1]["integrator"] == 2          # the HBM-resident state goes to the Krylov propagator
-    assert outs["cheb"][1]["integrator"] == 1
-    assert np.max(np.abs(outs["auto"][0] - outs["cheb"][0])) < STATE_TOL
-    assert np.max(np.abs(outs["auto"][0] - outs["tight"][0])) < STATE_TOL
-    assert outs["auto"][1]["n_applies"] < outs["cheb"][1]["n_applies"]
+    assert outs["auto"][1]["integrator"] == 3          # global drive of constant phase: the time-dependent Taylor propagator
+    assert outs["lanczos"][1]["integrator"] == 2 and outs["cheb"][1]["integrator"] == 1
+    for key in ("lanczos", "cheb", "tight"):
+        assert np.max(np.abs(outs["auto"][0] - outs[key][0])) < STATE_TOL, key
+    assert outs["lanczos"][1]["n_applies"] < outs["cheb"][1]["n_applies"]
+    assert outs["auto"][1]["n_applies"] < 0.5 * outs["lanczos"][1]["n_applies"]
 
 
 def test_c5_code_path_vs_oracle(engine, monkeypatch):
@@ -64,6 +66,7 @@ def test_c5_code_path_vs_oracle(engine, monkeypatch):
     from oracle.ref_hamiltonian import OracleHamiltonian
 
     monkeypatch.setenv("PB200_KRYLOV_MIB", "0")
+    monkeypatch.setenv("PB200_TAYLOR", "0")   # the Magnus / Krylov path is what this test pins
     spec = W.config_c5(n=10, t_total=800)
     psi0 = evolve.all_ground_state(spec)
     tf = spec.sampling_times[-1]
