@@ -21,8 +21,8 @@ Every run also carries
         striped over the N ranks, sampled on the device, ONE NCCL all-reduce of
         the bitstring histogram + Rydberg densities; trajectories/s and the
         speed-up against a 1-GPU reference leg measured in the same job;
-  "c5": BASELINE configs[4] (N = 1 only): the 24-atom anneal end to end (Krylov
-        propagator), steps/s, H-applies/ns, us per apply, achieved GB/s.
+  "c5": BASELINE configs[4] (N = 1 only): the 24-atom anneal end to end,
+        steps/s, H-applies/ns, us per apply, achieved GB/s.
 """
 from __future__ import annotations
 
@@ -40,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ATOMS = int(os.environ.get("PB200_BENCH_ATOMS", "20"))
+INTEGRATOR_NAMES = {1: "chebyshev-clenshaw (Richardson-CF4 Magnus)", 2: "lanczos (Richardson-CF4 Magnus)", 3: "time-dependent taylor"}
 METRIC = "time-steps/s (1 ns sampling intervals of the Sequence evolved per second)"
 UNIT = "steps/s"
 
@@ -56,8 +57,9 @@ def config_dict(n_gpus: int) -> dict:
                     "Rydberg-blockade sweep 500+2500+1000 ns, ground-rydberg basis, Schroedinger fp64",
         "hilbert_dim": 2**N_ATOMS,
         "time_steps_per_sequence": 4000,
-        "accuracy": "Richardson-extrapolated CF4 Magnus (exact spline moments), adaptive, 2-norm error budget 1e-8, Chebyshev-Clenshaw exponentials; "
-                    "state error <= 1e-8 (tests/test_gpu_parity.py)",
+        "accuracy": "time-dependent Taylor propagator (integrator 3): QobjEvo splines fitted by polynomials per step, one H-apply per "
+                    "Taylor order, a-priori 2-norm error budget 1e-8 (fit residuals + remainders); state error <= 1e-8 against the "
+                    "DOP853 oracle and against the Richardson-CF4 Magnus path (tests/test_gpu_taylor.py)",
         "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} replicas (the same C2 Sequence on every GPU, no collective in the time loop), 1 all-reduce of the final densities",
         "l2": "L2 flushed between timed iterations (256 MiB write); the 16 MiB state is L2-resident within a step",
     }
@@ -119,7 +121,7 @@ def measured_peak() -> tuple[float, str]:
 
 def ncu_traffic_per_launch() -> float | None:
     """dram bytes per launch of the dominant kernel from the committed ncu summary."""
-    for name in ("r02_stage_kernel_summary.json", "r01_stage_kernel_summary.json"):
+    for name in ("r02_taylor_stage_kernel_summary.json", "r02_stage_kernel_summary.json", "r01_stage_kernel_summary.json"):
         try:
             return float(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
         except Exception:
@@ -249,7 +251,7 @@ def c4_leg(local: int, rank: int, world: int, dist, barrier, stream) -> dict | N
         "n_trajectories": n_total, "n_gpus": world, "trajectories_per_rank": r["n_local"], "device_batch": C4_BATCH,
         "seconds": seconds, "trajectories_per_s": n_total / seconds, "traj_steps_per_s": n_total * 4000 / seconds,
         "h_applies_per_traj_step": float(tot[-2]) / (4000.0 * n_total), "gpu_launches": int(tot[-1]),
-        "integrator": {1: "chebyshev-clenshaw", 2: "lanczos"}.get(r.get("integrator", 0), "?"),
+        "integrator": INTEGRATOR_NAMES.get(r.get("integrator", 0), "?"),
         "shots": int(round(hist.sum())), "mean_rydberg_density": float(dens.sum() / (16 * n_total)),
         "collective": "1 all_reduce(SUM) of [2^16 histogram | 16 densities | counters] + 1 all_reduce(MAX) of the time",
         "timing": "CUDA events on the stream of the plans around the whole stripe (host-side spec building, plan "
@@ -271,7 +273,7 @@ def c4_leg(local: int, rank: int, world: int, dist, barrier, stream) -> dict | N
 
 
 def c5_leg(local: int, stream, peak: float) -> dict:
-    """BASELINE configs[4]: 24-atom adiabatic anneal, Krylov propagator, whole 4000-ns sequence on one GPU."""
+    """BASELINE configs[4]: 24-atom adiabatic anneal, whole 4000-ns sequence on one GPU (auto integrator)."""
     import torch
 
     from pulser_b200 import engine, workloads as W
@@ -286,7 +288,7 @@ def c5_leg(local: int, stream, peak: float) -> dict:
         plan.set_state("all-ground")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        st = plan.propagate(0.0, spec.sampling_times[-1], integrator=2)
+        st = plan.propagate(0.0, spec.sampling_times[-1])
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -296,14 +298,17 @@ def c5_leg(local: int, stream, peak: float) -> dict:
     bare = ms_apply * 1e-3 / 20
     return {
         "workload": f"C5: {n}-atom random 2D register, adiabatic anneal 0 -> Omega -> 0 with a detuning ramp, {T} ns, "
-                    "ground-rydberg, fp64, Lanczos (Krylov) exponentials, Richardson-extrapolated CF4 Magnus steps",
+                    "ground-rydberg, fp64, " + INTEGRATOR_NAMES.get(int(st["integrator"]), "?") + " propagator "
+                    "(the Krylov / Lanczos path of round 1 is integrator=2: tests/test_gpu_full_size.py compares the two)",
+        "integrator": INTEGRATOR_NAMES.get(int(st["integrator"]), "?"),
         "hilbert_dim": D, "steps_per_s": T / (ms * 1e-3), "seconds": ms * 1e-3,
-        "h_applies_per_time_step": st["n_applies"] / T, "us_per_lanczos_iteration": per_apply * 1e6,
+        "h_applies_per_time_step": st["n_applies"] / T, "us_per_h_apply_in_sequence": per_apply * 1e6,
         "us_per_bare_h_apply": bare * 1e6, "gpu_launches": int(st["n_launches"]), "norm2_final": norm2,
         "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
                      "achieved_bare_apply": 40.0 * D / bare / 1e9, "frac_bare_apply": 40.0 * D / bare / 1e9 / peak,
                      "achieved_sequence": 40.0 * D / per_apply / 1e9, "frac_sequence": 40.0 * D / per_apply / 1e9 / peak,
-                     "note": "40 B/amplitude algorithmic per H-apply; a Lanczos iteration moves 88 B/amplitude (DESIGN.md)"},
+                     "note": "40 B/amplitude algorithmic per H-apply (psi 16 + Dint 8 + out 16); a Taylor order moves 72-104 "
+                             "B/amplitude of own-element traffic (history term, accumulator), a Lanczos iteration 88 (DESIGN.md)"},
     }
 
 
@@ -410,8 +415,8 @@ def run_gpu(args) -> None:
         c5 = c5_leg(local, stream, peak)
     if rank == 0:
         per_launch_s = (kernel_ms * 1e-3) / max(launches, 1)
-        # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply; a launch of the stage kernel
-        # carries one H-apply, or two when the h and h/2 Richardson chains share it
+        # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply; a launch of the Taylor stage kernel
+        # carries one H-apply (the history / accumulator traffic of the order is NOT counted as algorithmic)
         applies_per_launch = applies / max(launches, 1)
         alg_bytes = 40.0 * D * applies_per_launch
         achieved = alg_bytes / per_launch_s / 1e9
@@ -422,7 +427,7 @@ def run_gpu(args) -> None:
             "config": config_dict(world),
             "steps_x_dim": value * D,
             "h_applies_per_time_step": applies / (T * args.steps),
-            "integrator": {1: "chebyshev-clenshaw", 2: "lanczos"}.get(int(st.get("integrator", 1)), "?"),
+            "integrator": INTEGRATOR_NAMES.get(int(st.get("integrator", 1)), "?"),
             "norm2_final": norm2,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -430,14 +435,14 @@ def run_gpu(args) -> None:
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
-                         "kernel": "stage_d2_rb_kernel (fused H-apply + Clenshaw update; 1 or 2 chains per launch)",
+                         "kernel": "stage_d2_taylor_kernel (fused H-apply + Taylor-order update + accumulation; one order per launch)",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "h_applies_per_launch": applies_per_launch,
                          "avg_launch_us": per_launch_s * 1e6,
                          "note": "achieved = algorithmic bytes / (CUDA-event time of the propagation / launches), launch "
                                  "gaps included; traffic = dram read+write per launch from the committed ncu --set full "
-                                 "capture (profiles/r0x_stage_kernel_summary.json): two-chain launches (2 H-applies, 83.9 MB "
-                                 "algorithmic), cold L2 at every ncu replay; in the timed run the 16 MiB state stays L2-resident"},
+                                 "capture (profiles/r02_taylor_stage_kernel_summary.json), cold L2 at every ncu replay; in the "
+                                 "timed run the 16 MiB state and its ring buffers stay L2-resident"},
         }
         if c4 is not None:
             line["c4"] = c4

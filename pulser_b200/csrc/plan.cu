@@ -1781,13 +1781,29 @@ static bool taylor_worthwhile(const Plan& P, double gtol) {
     return 4 * cnt <= nt;
 }
 
-// centre and half-width of  Dint - th n_from + om X  (rigorous bounds, the ones the Chebyshev path uses)
+// centre and half-width of  Dint - th n_from + om X : the rigorous bounds build_tables gives the Chebyshev path
+// (per-excitation-number bounds of the shared Dint where they exist), without its table building
 static void taylor_bounds(const Plan& P, double om, double th, double& centre, double& half) {
-    ExpParams E;
-    const cplx g = om * cplx(P.tay.unit.x, P.tay.unit.y);
-    E.g.assign((size_t)P.n, g); E.th.assign((size_t)P.n, th); E.w = 1.0;
-    std::vector<double> scratch_tab;
-    build_tables(P, E, centre, half, scratch_tab, true);
+    const int N = P.n;
+    const double dr = std::fabs(om) * N;
+    double dlo, dhi;
+    const bool caseA = P.has_interaction && P.dint_shared && P.desc.drives[0].state_from == P.desc.rydberg_state &&
+                       !P.dmin_cnt.empty();
+    if (caseA) {
+        dlo = 1e300; dhi = -1e300;
+        for (int c = 0; c <= N; ++c) {
+            if (P.dmin_cnt[c] > P.dmax_cnt[c]) continue;  // empty bin
+            dlo = std::min(dlo, P.dmin_cnt[c] - th * c);
+            dhi = std::max(dhi, P.dmax_cnt[c] - th * c);
+        }
+    } else {
+        dlo = P.has_interaction ? P.dmin_traj[0] : 0.0;
+        dhi = P.has_interaction ? P.dmax_traj[0] : 0.0;
+        dlo += N * std::min(0.0, -th); dhi += N * std::max(0.0, -th);
+    }
+    const double lo = dlo - dr, hi = dhi + dr;
+    centre = 0.5 * (lo + hi);
+    half = std::max(0.5 * (hi - lo) * (1.0 + 1e-9), 1e-9);
 }
 
 struct TaylorPoly {      // monomial coefficients in u of one coefficient function on a step, and the fit residual
@@ -1930,16 +1946,21 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
         Fit F; F.ok = false;
         const double budget = std::max(0.5 * rate * h, 0.02 * std::max(fit_total - fit_spent, 0.0));
         const double allow = budget / (h * N) * 0.5;
-        bool ok_om = false, ok_th = false;
-        for (int p = 0; p <= pmax && !ok_om; ++p) {
-            F.om = taylor_fit(om_pc, P.times, order, a, h, p);
-            ok_om = F.om.resid <= allow || (single_piece && p >= 3);
-        }
-        for (int p = 0; p <= pmax && !ok_th; ++p) {
-            F.th = taylor_fit(th_pc, P.times, order, a, h, p);
-            ok_th = F.th.resid <= allow || (single_piece && p >= 3);
-        }
-        F.ok = ok_om && ok_th;
+        // smallest passing degree; a candidate that spans several intervals is first tried at the highest degree so
+        // that a step across a non-smooth sample is refused after one fit instead of pmax + 1
+        auto one = [&](const PiecewiseCubic<double>& pc, TaylorPoly& out) {
+            if (!single_piece) {
+                out = taylor_fit(pc, P.times, order, a, h, pmax);
+                if (out.resid > allow) return false;
+            }
+            for (int p = 0; p < pmax; ++p) {
+                TaylorPoly f = taylor_fit(pc, P.times, order, a, h, p);
+                if (f.resid <= allow || (single_piece && p >= 3)) { out = f; return true; }
+            }
+            if (single_piece) out = taylor_fit(pc, P.times, order, a, h, pmax);
+            return true;
+        };
+        F.ok = one(om_pc, F.om) && one(th_pc, F.th);
         return F;
     };
 
