@@ -894,111 +894,6 @@ stage_d2_taylor_kernel(const __grid_constant__ TaylorArgs a) {
     taylor_epilogue<R>(a, idx, v, pr, pi);
 }
 
-// ---- thread-block-cluster variant: the partners across the CBITS bits just above the tile come from the PEER CTAs'
-// shared memory (DSMEM) instead of L2 --------------------------------------------------------------------------------
-// The single-CTA kernel is bound by L2 sector throughput: (N - TBITS) x 16 B of partner loads per amplitude
-// (DESIGN.md section 8).  A cluster of 2^CBITS consecutive tiles is closed under the flips of bits TBITS ..
-// TBITS+CBITS-1, and every CTA of it holds its tile in shared memory anyway: those partners are read with
-// ld.shared::cluster from the peer whose rank differs in that bit -- 16 x CBITS bytes per amplitude leave the L2 path
-// for the SM-to-SM network.  Two cluster barriers: tiles complete before any peer reads them (arrive right after the
-// own tile landed, wait after the local gather), and nobody exits while a peer may still read its tile.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t dsmem_map(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ double2 ld_dsmem(uint32_t addr) {
-    double2 v;
-    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-
-template <bool REAL_G, int TBITS, int RB, int CBITS>
-__global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
-stage_d2_taylor_cluster_kernel(const __grid_constant__ TaylorArgs a) {
-    constexpr int R = 1 << RB;
-    constexpr int NT = 1 << (TBITS - RB);
-    constexpr int TSIZE = 1 << TBITS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    c2* tile = reinterpret_cast<c2*>(smem_raw);
-    __shared__ __align__(8) uint64_t mbar;
-    const PassGeom& g = a.geo;
-    const int tid = threadIdx.x;
-    const long long base = (long long)blockIdx.x << TBITS;   // single-pass geometry: the tile is the TBITS low bits
-    const c2* vsrc = a.v;
-
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    pdl_wait();
-    pdl_launch_dependents();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&mbar, (uint32_t)TSIZE * 16u);
-        tma_load_1d(tile, vsrc + base, (uint32_t)TSIZE * 16u, &mbar);
-    }
-    const int to_bit = a.to_bit;
-    c2 v[R];
-    double pr[R], pi[R], qr[R], qi[R];
-    long long idx[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        idx[r] = base | (long long)(tid + r * NT);
-        pr[r] = 0.0; pi[r] = 0.0; qr[r] = 0.0; qi[r] = 0.0;
-    }
-    // partners across the bits above the cluster: coalesced L2 loads, in flight while the tile copy lands
-    const unsigned long long cl_mask = ((1ULL << CBITS) - 1ULL) << TBITS;
-    for (unsigned long long m = g.extra_mask & ~cl_mask; m; m &= m - 1) {
-        const int p = __ffsll((long long)m) - 1;
-        const double sg = ((int)((base >> p) & 1) == to_bit) ? 1.0 : -1.0;
-        double2 raw[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) raw[r] = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            pr[r] += raw[r].x; pi[r] += raw[r].y;
-            if (!REAL_G) { qr[r] = fma(sg, raw[r].x, qr[r]); qi[r] = fma(sg, raw[r].y, qi[r]); }
-        }
-    }
-    mbar_wait(&mbar, 0);
-    cluster_arrive();            // this CTA's tile is complete: peers may read it once they have waited
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = tile[tid + r * NT];
-    rb_tile_gather<true, REAL_G, TBITS, RB>(g, tile, nullptr, tid, to_bit, 0, false, v, pr, pi, qr, qi);
-    cluster_wait();              // every tile of the cluster is complete
-    {
-        const uint32_t rank = cluster_ctarank();
-        const uint32_t mine = smem_u32(tile) + (uint32_t)tid * 16u;
-#pragma unroll
-        for (int c = 0; c < CBITS; ++c) {
-            const uint32_t peer = dsmem_map(mine, rank ^ (1u << c));
-            const double sg = ((int)((base >> (TBITS + c)) & 1) == to_bit) ? 1.0 : -1.0;
-            double2 raw[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) raw[r] = ld_dsmem(peer + (uint32_t)(r * NT) * 16u);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                pr[r] += raw[r].x; pi[r] += raw[r].y;
-                if (!REAL_G) { qr[r] = fma(sg, raw[r].x, qr[r]); qi[r] = fma(sg, raw[r].y, qi[r]); }
-            }
-        }
-    }
-    cluster_arrive();            // done with the peers' tiles
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const double dx = a.unit.x * pr[r], dy = a.unit.x * pi[r];
-        if (!REAL_G) { pr[r] = fma(-a.unit.y, qi[r], dx); pi[r] = fma(a.unit.y, qr[r], dy); }
-        else { pr[r] = dx; pi[r] = dy; }
-    }
-    taylor_epilogue<R>(a, idx, v, pr, pi);
-    cluster_wait();              // no peer still reads this CTA's tile
-}
-
 // any register size (N < 11 in particular): one thread per amplitude, partners through global loads
 __global__ void __launch_bounds__(256) stage_d2_taylor_small_kernel(const __grid_constant__ TaylorArgs a) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;

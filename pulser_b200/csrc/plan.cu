@@ -166,8 +166,6 @@ static int device_setup(int dev) {
 #undef PB200_RB_ATTR
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_cluster_kernel<true, 11, 3, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_cluster_kernel<false, 11, 3, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     if (dev >= 0 && dev < PB200_MAX_DEVICES) sm_count[dev] = sms;
@@ -253,7 +251,6 @@ struct Plan {
     struct TaylorCache { bool valid = false, ok = false; c2 unit{1.0, 0.0}; PiecewiseCubic<double> om; std::vector<double> w_knot; } tay;
     std::vector<c2*> tay_ws;
     bool use_taylor = true;         // PB200_TAYLOR=0: never chosen automatically
-    int tay_cluster_bits = 0;       // PB200_TAYLOR_CLUSTER: 2^bits tiles per thread-block cluster (DSMEM partners); 0 = off
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
     int use_tiled = 1;              // PB200_TILED: d = 3 / 4 registers: 1 register-blocked tiled kernel, 0 generic
     bool all_uniform() const {
@@ -1887,38 +1884,13 @@ static int taylor_order(double h, const std::vector<double>& mj, double tol, dou
     return std::max(kk, 1);
 }
 
-// launch with a thread-block cluster of `csize` CTAs along x (and, optionally, programmatic dependent launch)
-template <typename... KArgs, typename... Args>
-static void launch_cluster_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
-                             unsigned csize, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
-}
-
 static void launch_taylor_stage(Plan& P, const PassGeom* geo, const TaylorArgs& a, long long& launches) {
     if (geo) {
         dim3 grid((unsigned)(P.D >> 11)), block(256);
         const size_t smem = (size_t)2048 * 16;
         const bool real_g = a.unit.y == 0.0;
-        const int cb = (P.n >= 11 + P.tay_cluster_bits) ? P.tay_cluster_bits : 0;
-#define PB200_TAYLOR_CL(CB)                                                                                              \
-    do {                                                                                                                 \
-        if (real_g) launch_cluster_k(stage_d2_taylor_cluster_kernel<true, 11, 3, CB>, grid, block, smem, P.stream, P.use_pdl, 1u << CB, a);   \
-        else launch_cluster_k(stage_d2_taylor_cluster_kernel<false, 11, 3, CB>, grid, block, smem, P.stream, P.use_pdl, 1u << CB, a);          \
-    } while (0)
-        if (cb == 3) PB200_TAYLOR_CL(3);
-        else if (cb == 2) PB200_TAYLOR_CL(2);
-        else if (cb == 4) PB200_TAYLOR_CL(4);
-        else if (real_g) launch_k(stage_d2_taylor_kernel<true, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
+        if (real_g) launch_k(stage_d2_taylor_kernel<true, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
         else launch_k(stage_d2_taylor_kernel<false, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
-#undef PB200_TAYLOR_CL
     } else {
         const unsigned blocks = (unsigned)((P.D + 255) / 256);
         stage_d2_taylor_small_kernel<<<blocks, 256, 0, P.stream>>>(a);
@@ -1938,7 +1910,7 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     const double eps = 1e-12;
     const double gtol = (o && o->tol > 0.0) ? o->tol : 1e-8;
     const double rate = gtol / std::max(thi - tlo, 1e-30);       // error budget per unit of time
-    const double rho_target = env_int("PB200_TAYLOR_RHO_MILLI", 10000) * 1e-3;
+    const double rho_target = env_int("PB200_TAYLOR_RHO_MILLI", 14000) * 1e-3;
     const int pmax = std::min(PB200_TAYLOR_PMAX, std::max(1, env_int("PB200_TAYLOR_P", PB200_TAYLOR_PMAX)));
     const int order = P.desc.interp_order;
     const int N = P.n;
@@ -1995,6 +1967,7 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     double t = t_start;
     double steps_len = 0.0;
     double t_retry_len = 0.0;   // > 0: the previous attempt at this step overshot rho; cap on the step length
+    const bool log_steps = env_int("PB200_TAYLOR_LOG", 0) != 0;
     while (t < t_stop - eps) {
         const int i0 = find_piece(P.times, t + eps);
         // longest candidate: accumulate rho over the sampling intervals
@@ -2129,6 +2102,9 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
         // the accumulator becomes the current state buffer
         std::swap(P.buf[P.cur], *acc_slot);
         st.n_launches += launches; st.n_applies += K; st.n_exponentials += 1; ++st.n_steps;
+        if (log_steps)
+            fprintf(stderr, "taylor step t=%.6f h_ns=%.3f p_om=%d p_th=%d K=%d rho=%.3f resid=%.2e/%.2e\n", t, h * 1e3, p_om, p_th, K,
+                    mj[0] * h, F.om.resid, F.th.resid);
         double rho_eff = 0.0;
         for (int j = 0; j <= p; ++j) rho_eff += mj[j] / (j + 1);
         st.max_rho = std::max(st.max_rho, rho_eff * h);
@@ -2294,8 +2270,6 @@ int pb200_plan_create(pb200_plan** out, const pb200_plan_desc* d) {
     P.use_pdl = env_int("PB200_PDL", 1) != 0;
     P.use_lanczos_fuse = env_int("PB200_LANCZOS_FUSE", 1) != 0;
     P.use_taylor = env_int("PB200_TAYLOR", 1) != 0;
-    P.tay_cluster_bits = env_int("PB200_TAYLOR_CLUSTER", 0);
-    if (P.tay_cluster_bits < 2 || P.tay_cluster_bits > 4) P.tay_cluster_bits = 0;
     P.use_fwd = env_int("PB200_FWD", 1) != 0;
     P.use_tiled = env_int("PB200_TILED", 1);
     P.sm_count = device_setup(d->device);
