@@ -2044,7 +2044,7 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
             double rho_eff = 0.0;
             for (int j = 0; j <= p; ++j) rho_eff += mj[j] / (j + 1);
             rho_eff *= h;
-            if (rho_eff > 1.3 * rho_target && h > 1e-9) {
+            if (rho_eff > 1.12 * rho_target && h > 1e-9) {
                 t_retry_len = h * rho_target / rho_eff;
                 continue;
             }
