@@ -748,31 +748,38 @@ __global__ void __launch_bounds__(1 << (TBITS - RB), 2) stage_d2_fwd_kernel(cons
 // order.  Replaces qutip.sesolve (simulation.py:729-735) for global drives of constant phase.
 #define PB200_TAYLOR_PMAX 8
 struct TaylorArgs {
-    const c2* v;       // chi_k, gather source [D]
+    const c2* v;       // chi_k, gather source [B][D]
     c2* out;           // chi_{k+1}
     c2* g_out;         // G_k = X chi_k (nullptr: nobody reads it later)
     c2* acc;           // accumulator of sum_k chi_k
     const double* dint;  // nullptr: no interaction
+    long long dint_stride;  // 0: Dint shared by the trajectories
     long long D;
     PassGeom geo;
-    c2 unit;           // e^{-i phi}: the constant phase of the drive
+    c2 unit;           // uniform drive: e^{-i phi}, the constant phase
+    // separable per-qubit drives (trajectory batches with static noise): coef_{b,k}(t) = a_{b,k} unit omega(t),
+    // det_{b,k}(t) = theta(t) + c_{b,k} M(t).  table[b][0 .. 2N) = a unit per BIT position (re, im),
+    // table[b][2N .. 3N) = c per bit position (layout of d2_table_stride); nullptr in the uniform case
+    const double* table;
     int to_bit, from_is_one;
-    double th0, gam0, om0;  // H_0
+    double th0, gam0, om0, m0;  // H_0 = Dint - th0 n_from - m0 sum_k c_k n_k - gam0 + om0 X
     c2 scale;          // -i h / (k+1)
     int nh;            // history terms j = 1 .. nh
-    const c2* hchi[PB200_TAYLOR_PMAX];   // chi_{k-j}   (nullptr when th_j = gam_j = 0)
+    const c2* hchi[PB200_TAYLOR_PMAX];   // chi_{k-j}   (nullptr when th_j = m_j = gam_j = 0)
     const c2* hg[PB200_TAYLOR_PMAX];     // G_{k-j}     (nullptr when om_j = 0)
-    double hth[PB200_TAYLOR_PMAX], hgam[PB200_TAYLOR_PMAX], hom[PB200_TAYLOR_PMAX];
+    double hth[PB200_TAYLOR_PMAX], hgam[PB200_TAYLOR_PMAX], hom[PB200_TAYLOR_PMAX], hm[PB200_TAYLOR_PMAX];
     int acc_read;      // 1: acc is read before it is updated (0: first write of the step)
     int acc_add_v;     // 1: chi_k joins the update (even orders), 0: chi_{k+1} alone
     int acc_on;        // 0: this order leaves the accumulator alone
     c2 acc_mul;        // factor of the whole accumulator (phase of the scalar centre on the last order, else 1)
 };
 
-// epilogue of one amplitude block: everything after the partner sums
+// epilogue of one amplitude block: everything after the partner sums.  `off[r]` = sum_k c_k [digit_k == from] of the
+// amplitude (0 for uniform drives); idx is the index inside the trajectory, voff the trajectory's offset.
 template <int R>
 __device__ __forceinline__ void taylor_epilogue(const TaylorArgs& a, const long long (&idx)[R], const c2 (&v)[R],
-                                                const double (&gx)[R], const double (&gy)[R]) {
+                                                const double (&gx)[R], const double (&gy)[R], const double (&off)[R],
+                                                long long voff, const double* __restrict__ dsrc) {
     constexpr int H = (R >= 4) ? R / 2 : R;
     const int nb = a.geo.n_bits;
 #pragma unroll
@@ -781,12 +788,12 @@ __device__ __forceinline__ void taylor_epilogue(const TaylorArgs& a, const long 
         {
             double dv[H];
 #pragma unroll
-            for (int r = 0; r < H; ++r) dv[r] = a.dint ? __ldcs(a.dint + idx[h0 + r]) : 0.0;
+            for (int r = 0; r < H; ++r) dv[r] = dsrc ? __ldcs(dsrc + idx[h0 + r]) : 0.0;
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 const int ones = __popcll((unsigned long long)idx[h0 + r]);
                 cn[r] = (double)(a.from_is_one ? ones : (nb - ones));
-                const double diag = fma(-a.th0, cn[r], dv[r] - a.gam0);
+                const double diag = fma(-a.th0, cn[r], fma(-a.m0, off[h0 + r], dv[r] - a.gam0));
                 sx[r] = fma(diag, v[h0 + r].x, a.om0 * gx[h0 + r]);
                 sy[r] = fma(diag, v[h0 + r].y, a.om0 * gy[h0 + r]);
             }
@@ -795,17 +802,17 @@ __device__ __forceinline__ void taylor_epilogue(const TaylorArgs& a, const long 
             if (a.hchi[j]) {
                 c2 c[H];
 #pragma unroll
-                for (int r = 0; r < H; ++r) c[r] = ld_own(a.hchi[j] + idx[h0 + r]);
+                for (int r = 0; r < H; ++r) c[r] = ld_own(a.hchi[j] + voff + idx[h0 + r]);
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
-                    const double d = -fma(a.hth[j], cn[r], a.hgam[j]);
+                    const double d = -fma(a.hth[j], cn[r], fma(a.hm[j], off[h0 + r], a.hgam[j]));
                     sx[r] = fma(d, c[r].x, sx[r]); sy[r] = fma(d, c[r].y, sy[r]);
                 }
             }
             if (a.hg[j]) {
                 c2 c[H];
 #pragma unroll
-                for (int r = 0; r < H; ++r) c[r] = ld_own(a.hg[j] + idx[h0 + r]);
+                for (int r = 0; r < H; ++r) c[r] = ld_own(a.hg[j] + voff + idx[h0 + r]);
 #pragma unroll
                 for (int r = 0; r < H; ++r) { sx[r] = fma(a.hom[j], c[r].x, sx[r]); sy[r] = fma(a.hom[j], c[r].y, sy[r]); }
             }
@@ -814,24 +821,26 @@ __device__ __forceinline__ void taylor_epilogue(const TaylorArgs& a, const long 
 #pragma unroll
         for (int r = 0; r < H; ++r) {
             res[r] = {a.scale.x * sx[r] - a.scale.y * sy[r], a.scale.x * sy[r] + a.scale.y * sx[r]};
-            st_c2(a.out + idx[h0 + r], res[r]);
-            if (a.g_out) st_c2(a.g_out + idx[h0 + r], c2{gx[h0 + r], gy[h0 + r]});
+            st_c2(a.out + voff + idx[h0 + r], res[r]);
+            if (a.g_out) st_c2(a.g_out + voff + idx[h0 + r], c2{gx[h0 + r], gy[h0 + r]});
         }
         if (a.acc_on) {
             c2 ac[H];
 #pragma unroll
-            for (int r = 0; r < H; ++r) ac[r] = a.acc_read ? ld_own(a.acc + idx[h0 + r]) : c2{0.0, 0.0};
+            for (int r = 0; r < H; ++r) ac[r] = a.acc_read ? ld_own(a.acc + voff + idx[h0 + r]) : c2{0.0, 0.0};
 #pragma unroll
             for (int r = 0; r < H; ++r) {
                 c2 s = cadd(ac[r], res[r]);
                 if (a.acc_add_v) s = cadd(s, v[h0 + r]);
-                st_c2(a.acc + idx[h0 + r], cmul(a.acc_mul, s));
+                st_c2(a.acc + voff + idx[h0 + r], cmul(a.acc_mul, s));
             }
         }
     }
 }
 
-template <bool REAL_G, int TBITS, int RB>
+// UNIFORM: one drive coefficient for every qubit and a single state (C2, C5); otherwise per-(trajectory, qubit) static
+// factors from `table`, blockIdx.y = trajectory (C4: doppler + amplitude noise batches).
+template <bool UNIFORM, bool REAL_G, int TBITS, int RB>
 __global__ void __launch_bounds__(1 << (TBITS - RB), (65536 / ((1 << (TBITS - RB)) * (RB >= 3 ? 128 : 64))))
 stage_d2_taylor_kernel(const __grid_constant__ TaylorArgs a) {
     constexpr int R = 1 << RB;
@@ -842,8 +851,10 @@ stage_d2_taylor_kernel(const __grid_constant__ TaylorArgs a) {
     __shared__ __align__(8) uint64_t mbar;
     const PassGeom& g = a.geo;
     const int tid = threadIdx.x;
+    const long long traj = UNIFORM ? 0 : (long long)blockIdx.y;
+    const long long voff = traj * a.D;
     const long long base = tile_base_of(g, blockIdx.x);
-    const c2* vsrc = a.v;
+    const c2* vsrc = a.v + voff;
 
     if (tid == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -855,6 +866,13 @@ stage_d2_taylor_kernel(const __grid_constant__ TaylorArgs a) {
         const uint32_t row_bytes = (uint32_t)(16u << g.lo_bits);
         for (int r = tid; r < rows; r += NT)
             tma_load_1d(tile + ((size_t)r << g.lo_bits), vsrc + base + ((long long)r << g.hi_shift), row_bytes, &mbar);
+    }
+    double* tab = reinterpret_cast<double*>(tile + TSIZE);
+    if (!UNIFORM) {   // the per-trajectory table is read behind the tile copy
+        const int stride = d2_table_stride(g.n_bits);
+        const double* src = a.table + traj * stride;
+        for (int i = tid; i < stride; i += NT) tab[i] = src[i];
+        __syncthreads();
     }
     const long long lomask = (1LL << g.lo_bits) - 1;
     const int to_bit = a.to_bit;
@@ -870,28 +888,62 @@ stage_d2_taylor_kernel(const __grid_constant__ TaylorArgs a) {
     // partners across the bits outside the tile: coalesced loads issued while the bulk copy of the tile is in flight
     for (unsigned long long m = g.extra_mask; m; m &= m - 1) {
         const int p = __ffsll((long long)m) - 1;
-        const double sg = ((int)((base >> p) & 1) == to_bit) ? 1.0 : -1.0;
+        const int bit = (int)((base >> p) & 1);
+        const double sg = (bit == to_bit) ? 1.0 : -1.0;
+        double gx = 0.0, gy = 0.0;
+        if (!UNIFORM) { gx = tab[2 * p]; gy = (bit == to_bit) ? tab[2 * p + 1] : -tab[2 * p + 1]; }
         double2 raw[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) raw[r] = __ldg(reinterpret_cast<const double2*>(vsrc + (idx[r] ^ (1LL << p))));
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            pr[r] += raw[r].x; pi[r] += raw[r].y;
-            if (!REAL_G) { qr[r] = fma(sg, raw[r].x, qr[r]); qi[r] = fma(sg, raw[r].y, qi[r]); }
+            if (UNIFORM) {
+                pr[r] += raw[r].x; pi[r] += raw[r].y;
+                if (!REAL_G) { qr[r] = fma(sg, raw[r].x, qr[r]); qi[r] = fma(sg, raw[r].y, qi[r]); }
+            } else {
+                pr[r] = fma(gx, raw[r].x, pr[r]); pr[r] = fma(-gy, raw[r].y, pr[r]);
+                pi[r] = fma(gx, raw[r].y, pi[r]); pi[r] = fma(gy, raw[r].x, pi[r]);
+            }
         }
     }
     mbar_wait(&mbar, 0);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = tile[tid + r * NT];
-    rb_tile_gather<true, REAL_G, TBITS, RB>(g, tile, nullptr, tid, to_bit, 0, false, v, pr, pi, qr, qi);
-    // G = unit S_to + conj(unit) S_from = ux P + i uy Q
+    rb_tile_gather<UNIFORM, REAL_G, TBITS, RB>(g, tile, tab, tid, to_bit, 0, false, v, pr, pi, qr, qi);
+    double off[R];
+    if (UNIFORM) {
+        // G = unit S_to + conj(unit) S_from = ux P + i uy Q
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const double dx = a.unit.x * pr[r], dy = a.unit.x * pi[r];
-        if (!REAL_G) { pr[r] = fma(-a.unit.y, qi[r], dx); pi[r] = fma(a.unit.y, qr[r], dy); }
-        else { pr[r] = dx; pi[r] = dy; }
+        for (int r = 0; r < R; ++r) {
+            const double dx = a.unit.x * pr[r], dy = a.unit.x * pi[r];
+            if (!REAL_G) { pr[r] = fma(-a.unit.y, qi[r], dx); pi[r] = fma(a.unit.y, qr[r], dy); }
+            else { pr[r] = dx; pi[r] = dy; }
+            off[r] = 0.0;
+        }
+    } else {
+        // static per-qubit detuning weights: sum over (bits of base) + (bits of tid) + (register bits)
+        const int nb = g.n_bits;
+        const long long fixed = base | (tid & lomask) | ((long long)(tid >> g.lo_bits) << g.hi_shift);
+        double common = 0.0;
+        for (int p = 0; p < nb; ++p) {
+            const int bit = (int)((fixed >> p) & 1);
+            common += (bit == a.from_is_one) ? tab[2 * nb + p] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double acc = common;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int j = TBITS - RB + q;
+                const int p = (j < g.lo_bits) ? j : (j - g.lo_bits + g.hi_shift);
+                const double th = tab[2 * nb + p];
+                const int bit = (r >> q) & 1;   // `fixed` has these bits at 0
+                acc += ((bit == a.from_is_one) ? th : 0.0) - ((0 == a.from_is_one) ? th : 0.0);
+            }
+            off[r] = acc;
+        }
     }
-    taylor_epilogue<R>(a, idx, v, pr, pi);
+    taylor_epilogue<R>(a, idx, v, pr, pi, off, voff, a.dint ? a.dint + traj * a.dint_stride : nullptr);
 }
 
 // any register size (N < 11 in particular): one thread per amplitude, partners through global loads
@@ -899,18 +951,34 @@ __global__ void __launch_bounds__(256) stage_d2_taylor_small_kernel(const __grid
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.D) return;
     const int nb = a.geo.n_bits;
-    double pr = 0.0, pi = 0.0, qr = 0.0, qi = 0.0;
-    for (int p = 0; p < nb; ++p) {
-        const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + (s ^ (1LL << p))));
-        const double sg = ((int)((s >> p) & 1) == a.to_bit) ? 1.0 : -1.0;
-        pr += raw.x; pi += raw.y; qr = fma(sg, raw.x, qr); qi = fma(sg, raw.y, qi);
+    const long long traj = blockIdx.y;
+    const long long voff = traj * a.D;
+    const double* tab = a.table ? a.table + traj * d2_table_stride(nb) : nullptr;
+    double gxs = 0.0, gys = 0.0, offv = 0.0;
+    if (tab) {
+        for (int p = 0; p < nb; ++p) {
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + voff + (s ^ (1LL << p))));
+            const int bit = (int)((s >> p) & 1);
+            const double gx = tab[2 * p], gy = (bit == a.to_bit) ? tab[2 * p + 1] : -tab[2 * p + 1];
+            gxs = fma(gx, raw.x, gxs); gxs = fma(-gy, raw.y, gxs);
+            gys = fma(gx, raw.y, gys); gys = fma(gy, raw.x, gys);
+            offv += (bit == a.from_is_one) ? tab[2 * nb + p] : 0.0;
+        }
+    } else {
+        double pr = 0.0, pi = 0.0, qr = 0.0, qi = 0.0;
+        for (int p = 0; p < nb; ++p) {
+            const double2 raw = __ldg(reinterpret_cast<const double2*>(a.v + voff + (s ^ (1LL << p))));
+            const double sg = ((int)((s >> p) & 1) == a.to_bit) ? 1.0 : -1.0;
+            pr += raw.x; pi += raw.y; qr = fma(sg, raw.x, qr); qi = fma(sg, raw.y, qi);
+        }
+        gxs = fma(-a.unit.y, qi, a.unit.x * pr);
+        gys = fma(a.unit.y, qr, a.unit.x * pi);
     }
     const long long idx[1] = {s};
-    const double2 own = __ldg(reinterpret_cast<const double2*>(a.v + s));
+    const double2 own = __ldg(reinterpret_cast<const double2*>(a.v + voff + s));
     const c2 v[1] = {{own.x, own.y}};
-    const double gx[1] = {fma(-a.unit.y, qi, a.unit.x * pr)};
-    const double gy[1] = {fma(a.unit.y, qr, a.unit.x * pi)};
-    taylor_epilogue<1>(a, idx, v, gx, gy);
+    const double gx[1] = {gxs}, gy[1] = {gys}, off[1] = {offv};
+    taylor_epilogue<1>(a, idx, v, gx, gy, off, voff, a.dint ? a.dint + traj * a.dint_stride : nullptr);
 }
 
 // ---- generic-d stage kernel (any dim, several drives; global gathers) -------

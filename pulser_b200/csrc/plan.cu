@@ -164,8 +164,9 @@ static int device_setup(int dev) {
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_rb_kernel<false, false, TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_RB_ATTR(11, 2) PB200_RB_ATTR(11, 3) PB200_RB_ATTR(12, 2) PB200_RB_ATTR(12, 3)
 #undef PB200_RB_ATTR
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
-    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<true, true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<true, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 256));
+    CUDA_CHECK(cudaFuncSetAttribute(stage_d2_taylor_kernel<false, false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 16 + 2048));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<true, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     CUDA_CHECK(cudaFuncSetAttribute(stage_d2_fwd_kernel<false, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2048 * 16 + 256));
     if (dev >= 0 && dev < PB200_MAX_DEVICES) sm_count[dev] = sms;
@@ -248,7 +249,21 @@ struct Plan {
     c2* wbuf[2] = {nullptr, nullptr};
     // time-dependent Taylor propagator: drive projected on its constant phase, half-width of H at the sampling times,
     // extra ring buffers (beyond buf / aux) for polynomial degrees > 2
-    struct TaylorCache { bool valid = false, ok = false; c2 unit{1.0, 0.0}; PiecewiseCubic<double> om; std::vector<double> w_knot; } tay;
+    struct TaylorCache {
+        bool valid = false, ok = false;
+        c2 unit{1.0, 0.0};
+        PiecewiseCubic<double> om;         // omega(t): the drive along its constant phase (reference row)
+        std::vector<double> w_knot;        // spectral half-width of H at the sampling times
+        // separable per-(trajectory, qubit) drives: coef = a unit omega(t), det = theta(t) + c M(t)
+        bool uniform = true;               // one state, one coefficient for every qubit (a = 1, c = 0)
+        bool has_m = false;                // some c != 0
+        PiecewiseCubic<double> mshape;     // M(t)
+        std::vector<cplx> a;               // [B][N] per qubit
+        std::vector<double> c;             // [B][N]
+        double a_sum_max = 0.0, c_sum_max = 0.0;   // max over trajectories of sum_k |a|, sum_k |c|
+        std::vector<double> tab_host;      // [B][3N+2] device table image
+        double* d_tab = nullptr;
+    } tay;
     std::vector<c2*> tay_ws;
     bool use_taylor = true;         // PB200_TAYLOR=0: never chosen automatically
     bool use_lanczos_fuse = true;   // PB200_LANCZOS_FUSE=0: separate vector-update kernel (cross-check)
@@ -1386,7 +1401,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
 }
 
 static bool taylor_prepare(Plan& P);
-static bool taylor_worthwhile(const Plan& P, double gtol);
+static bool taylor_worthwhile(Plan& P, double gtol);
 static bool taylor_geometry(const Plan& P, const std::vector<PassGeom>& passes, bool& use_rb);
 static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200_run_opts* o, pb200_run_stats* stats);
 
@@ -1418,8 +1433,8 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
                             (req == 3 || taylor_worthwhile(P, (o && o->tol > 0.0) ? o->tol : 1e-8));
             if (ok) { propagate_taylor(P, t_start, t_stop, o, stats); return; }
             if (req == 3)
-                fail(PB200_ERR_UNSUPPORTED, "integrator 3 (Taylor) needs one global drive of constant phase on a d = 2 register, "
-                                            "a single state, no collapse operators / SLM mask");
+                fail(PB200_ERR_UNSUPPORTED, "integrator 3 (Taylor) needs a d = 2 register whose drive is one time shape of constant phase "
+                                            "(per-qubit static factors / detuning offsets allowed), no collapse operators / SLM mask");
         }
     }
     const double gtol = (o && o->tol != 0.0) ? o->tol : (P.has_diss ? 1e-6 : 1e-8);
@@ -1727,46 +1742,189 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
 // real part of the drive along its constant phase, and the half-width of H(t) at every sampling time
 static bool taylor_prepare(Plan& P) {
     Plan::TaylorCache& C = P.tay;
-    if (!(is_d2path(P) && P.all_uniform() && P.B == 1)) return false;
+    if (!is_d2path(P)) return false;
     if (P.has_diss || P.has_collapse || P.has_slm || P.force_v1) return false;
     if (P.desc.interp_order != 3 && P.desc.interp_order != 1) return false;
     if (C.valid) return C.ok;
     C.valid = true; C.ok = false;
-    const DriveTables& T = P.tabs[0][0];
-    if (T.coef.size() != 1 || T.det.size() != 1) return false;
-    const PiecewiseCubic<cplx>& pc = T.coef[0];
-    const int np = pc.pieces();
-    cplx big = pc.y_last;
-    for (int i = 0; i < np; ++i) if (std::abs(pc.c0[i]) > std::abs(big)) big = pc.c0[i];
-    const double scale = std::abs(big);
+    const int N = P.n, B = P.B, nt = (int)P.times.size();
+    auto rows_of = [&](int b) { return (int)P.tabs[b][0].coef.size(); };
+    auto coef_pc = [&](int b, int k) -> const PiecewiseCubic<cplx>& { return P.tabs[b][0].coef[rows_of(b) == 1 ? 0 : k]; };
+    auto det_pc = [&](int b, int k) -> const PiecewiseCubic<double>& { return P.tabs[b][0].det[rows_of(b) == 1 ? 0 : k]; };
+    // the interpolants are linear in the samples (same knots everywhere): the structure is read off the samples
+    auto csample = [&](const PiecewiseCubic<cplx>& pc, int i) { return i < pc.pieces() ? pc.c0[i] : pc.y_last; };
+    auto dsample = [&](const PiecewiseCubic<double>& pc, int i) { return i < pc.pieces() ? pc.c0[i] : pc.y_last; };
+    // reference drive row: the largest one
+    int rb = 0, rk = 0; double scale = 0.0; cplx big = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < (rows_of(b) == 1 ? 1 : N); ++k)
+            for (int i = 0; i < nt; ++i) {
+                const cplx y = csample(coef_pc(b, k), i);
+                if (std::abs(y) > scale) { scale = std::abs(y); big = y; rb = b; rk = k; }
+            }
     const cplx unit = scale > 0.0 ? big / scale : cplx(1.0, 0.0);
+    const cplx cu = std::conj(unit);
+    const PiecewiseCubic<cplx>& ref = coef_pc(rb, rk);
+    const int np = ref.pieces();
     C.om = PiecewiseCubic<double>();
     C.om.c0.resize(np); C.om.c1.resize(np); C.om.c2.resize(np); C.om.c3.resize(np);
-    const cplx cu = std::conj(unit);
     for (int i = 0; i < np; ++i) {
         const double hi = P.times[i + 1] - P.times[i];
-        const cplx v0 = pc.c0[i] * cu, v1 = pc.c1[i] * cu, v2 = pc.c2[i] * cu, v3 = pc.c3[i] * cu;
+        const cplx v0 = ref.c0[i] * cu, v1 = ref.c1[i] * cu, v2 = ref.c2[i] * cu, v3 = ref.c3[i] * cu;
         const double im = std::max(std::max(std::fabs(v0.imag()), std::fabs(v1.imag()) * hi),
                                    std::max(std::fabs(v2.imag()) * hi * hi, std::fabs(v3.imag()) * hi * hi * hi));
         if (im > 1e-13 * scale) return false;   // the phase moves: not a single real polynomial
         C.om.c0[i] = v0.real(); C.om.c1[i] = v1.real(); C.om.c2[i] = v2.real(); C.om.c3[i] = v3.real();
     }
-    C.om.y_last = (pc.y_last * cu).real();
+    C.om.y_last = (ref.y_last * cu).real();
     C.unit = {unit.real(), unit.imag()};
+    // every drive row = a (complex constant) x the reference row
+    C.a.assign((size_t)B * N, cplx(1.0, 0.0));
+    double ref2 = 0.0;
+    for (int i = 0; i < nt; ++i) ref2 += std::norm(csample(ref, i));
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < N; ++k) {
+            const PiecewiseCubic<cplx>& pc = coef_pc(b, k);
+            cplx aa = 0.0;
+            if (ref2 > 0.0) {
+                for (int i = 0; i < nt; ++i) aa += csample(pc, i) * std::conj(csample(ref, i));
+                aa /= ref2;
+            }
+            for (int i = 0; i < nt; ++i)
+                if (std::abs(csample(pc, i) - aa * csample(ref, i)) > 1e-13 * std::max(scale, 1e-300)) return false;
+            C.a[(size_t)b * N + k] = (ref2 > 0.0) ? aa : cplx(0.0, 0.0);
+        }
+    // every detuning row = the reference row + c x one common shape M
+    const PiecewiseCubic<double>& dref = det_pc(0, 0);
+    double dscale = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < (rows_of(b) == 1 ? 1 : N); ++k)
+            for (int i = 0; i < nt; ++i) dscale = std::max(dscale, std::fabs(dsample(det_pc(b, k), i)));
+    int mb = -1, mk = -1; double emax = 0.0; int mi = 0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < (rows_of(b) == 1 ? 1 : N); ++k)
+            for (int i = 0; i < nt; ++i) {
+                const double e = std::fabs(dsample(det_pc(b, k), i) - dsample(dref, i));
+                if (e > emax) { emax = e; mb = b; mk = k; mi = i; }
+            }
+    C.c.assign((size_t)B * N, 0.0);
+    C.has_m = emax > 1e-13 * std::max(dscale, 1e-300);
+    if (C.has_m) {
+        std::vector<double> m(nt);
+        const double norm = dsample(det_pc(mb, mk), mi) - dsample(dref, mi);
+        double m2 = 0.0;
+        for (int i = 0; i < nt; ++i) { m[i] = (dsample(det_pc(mb, mk), i) - dsample(dref, i)) / norm; m2 += m[i] * m[i]; }
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < N; ++k) {
+                const PiecewiseCubic<double>& pc = det_pc(b, k);
+                double cc = 0.0;
+                for (int i = 0; i < nt; ++i) cc += (dsample(pc, i) - dsample(dref, i)) * m[i];
+                cc /= m2;
+                for (int i = 0; i < nt; ++i)
+                    if (std::fabs(dsample(pc, i) - dsample(dref, i) - cc * m[i]) > 1e-13 * std::max(dscale, 1e-300)) return false;
+                C.c[(size_t)b * N + k] = cc;
+            }
+        C.mshape = make_interpolant<double>(P.times.data(), m.data(), nt, P.desc.interp_order);
+    }
+    C.uniform = (B == 1) && !C.has_m;
+    C.a_sum_max = 0.0; C.c_sum_max = 0.0;
+    for (int b = 0; b < B; ++b) {
+        double sa = 0.0, sc = 0.0;
+        for (int k = 0; k < N; ++k) {
+            sa += std::abs(C.a[(size_t)b * N + k]); sc += std::fabs(C.c[(size_t)b * N + k]);
+            if (std::abs(C.a[(size_t)b * N + k] - cplx(1.0, 0.0)) > 0.0) C.uniform = false;
+        }
+        C.a_sum_max = std::max(C.a_sum_max, sa); C.c_sum_max = std::max(C.c_sum_max, sc);
+    }
+    if (!C.uniform) {   // static device table: a unit per BIT position (re, im), c per bit position
+        const int stride = d2_table_stride(N);
+        C.tab_host.assign((size_t)B * stride, 0.0);
+        for (int b = 0; b < B; ++b) {
+            double* t = C.tab_host.data() + (size_t)b * stride;
+            for (int k = 0; k < N; ++k) {
+                const int p = N - 1 - k;
+                const cplx g = C.a[(size_t)b * N + k] * unit;
+                t[2 * p] = g.real(); t[2 * p + 1] = g.imag();
+                t[2 * N + p] = C.c[(size_t)b * N + k];
+            }
+        }
+        if (C.d_tab) { CUDA_CHECK(cudaStreamSynchronize(P.stream)); pool_free(P.desc.device, C.d_tab); C.d_tab = nullptr; }
+        C.d_tab = (double*)pool_alloc(P.desc.device, C.tab_host.size() * sizeof(double));
+        CUDA_CHECK(cudaMemcpyAsync(C.d_tab, C.tab_host.data(), C.tab_host.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                   P.stream));
+    }
+    C.w_knot.clear();
     C.ok = true;
     return true;
 }
 
-// Is the Taylor propagator the cheaper choice?  A cubic spline through samples of a curved function deviates from
+// centre and half-width of  Dint - th n_from - mv sum_k c_k n_k + om X  over the batch: the rigorous bounds build_tables
+// gives the Chebyshev path (per-excitation-number bounds of the shared Dint where they exist), without its tables
+static void taylor_bounds(const Plan& P, double om, double th, double mv, double& centre, double& half) {
+    const int N = P.n;
+    const Plan::TaylorCache& C = P.tay;
+    double lo = 1e300, hi = -1e300;
+    const bool caseA = C.uniform && P.has_interaction && P.dint_shared &&
+                       P.desc.drives[0].state_from == P.desc.rydberg_state && !P.dmin_cnt.empty();
+    if (caseA) {
+        const double dr = std::fabs(om) * N;
+        double dlo = 1e300, dhi = -1e300;
+        for (int c = 0; c <= N; ++c) {
+            if (P.dmin_cnt[c] > P.dmax_cnt[c]) continue;  // empty bin
+            dlo = std::min(dlo, P.dmin_cnt[c] - th * c);
+            dhi = std::max(dhi, P.dmax_cnt[c] - th * c);
+        }
+        lo = dlo - dr; hi = dhi + dr;
+    } else {
+        for (int b = 0; b < P.B; ++b) {
+            double dr = 0.0;
+            double dlo = 0.0, dhi = 0.0;
+            if (P.has_interaction) {
+                dlo = P.dint_shared ? P.dmin_traj[0] : P.dmin_traj[b];
+                dhi = P.dint_shared ? P.dmax_traj[0] : P.dmax_traj[b];
+            }
+            for (int k = 0; k < N; ++k) {
+                dr += std::abs(C.a[(size_t)b * N + k]);
+                const double val = -(th + C.c[(size_t)b * N + k] * mv);   // diagonal of a qubit in |from>, 0 otherwise
+                dlo += std::min(0.0, val); dhi += std::max(0.0, val);
+            }
+            dr *= std::fabs(om);
+            lo = std::min(lo, dlo - dr); hi = std::max(hi, dhi + dr);
+        }
+    }
+    centre = 0.5 * (lo + hi);
+    half = std::max(0.5 * (hi - lo) * (1.0 + 1e-9), 1e-9);
+}
+
+// half-width of H at every sampling time (step-length rule, cost estimate)
+static void taylor_knot_widths(Plan& P) {
+    Plan::TaylorCache& C = P.tay;
+    const int nt = (int)P.times.size();
+    if ((int)C.w_knot.size() == nt) return;
+    const int order = P.desc.interp_order;
+    const PiecewiseCubic<double>& th_pc = P.tabs[0][0].det[0];
+    C.w_knot.resize(nt);
+    for (int i = 0; i < nt; ++i) {
+        double c, hw;
+        taylor_bounds(P, eval_at(C.om, P.times, P.times[i], order), eval_at(th_pc, P.times, P.times[i], order),
+                      C.has_m ? eval_at(C.mshape, P.times, P.times[i], order) : 0.0, c, hw);
+        C.w_knot[i] = hw;
+    }
+}
+
+// Is the Taylor propagator the cheaper choice?  (i) A cubic spline through samples of a curved function deviates from
 // every smooth function by ~ |4th difference| / 384 per interval; where that floor exceeds what the fit may leave
 // behind, no polynomial spans more than one sampling interval and a step costs ~10 H-applies per interval -- more than
 // the Magnus path.  Worth it when at most a quarter of the intervals are like that (C2 / C5: only those at the kinks).
-static bool taylor_worthwhile(const Plan& P, double gtol) {
+// (ii) Its cost is ~4.1 H-applies per unit of (spectral half-width x time) of the FULL spectrum; for very strongly
+// blockaded registers the Krylov path (populated spectrum) is cheaper: limit ~12 applies per ns (C4: 7, C2: 1).
+static bool taylor_worthwhile(Plan& P, double gtol) {
     const int nt = (int)P.times.size();
     if (nt < 8) return false;
     const double rate = gtol / std::max(P.times.back() - P.times.front(), 1e-30);
     const double allow = 0.25 * rate / P.n;
-    const PiecewiseCubic<double>* pcs[2] = {&P.tay.om, &P.tabs[0][0].det[0]};
+    std::vector<const PiecewiseCubic<double>*> pcs = {&P.tay.om, &P.tabs[0][0].det[0]};
+    if (P.tay.has_m) pcs.push_back(&P.tay.mshape);
     std::vector<char> rough(nt, 0);
     for (const PiecewiseCubic<double>* pc : pcs) {
         const int np = pc->pieces();
@@ -1778,32 +1936,13 @@ static bool taylor_worthwhile(const Plan& P, double gtol) {
     }
     int cnt = 0;
     for (char c : rough) cnt += c;
-    return 4 * cnt <= nt;
-}
-
-// centre and half-width of  Dint - th n_from + om X : the rigorous bounds build_tables gives the Chebyshev path
-// (per-excitation-number bounds of the shared Dint where they exist), without its table building
-static void taylor_bounds(const Plan& P, double om, double th, double& centre, double& half) {
-    const int N = P.n;
-    const double dr = std::fabs(om) * N;
-    double dlo, dhi;
-    const bool caseA = P.has_interaction && P.dint_shared && P.desc.drives[0].state_from == P.desc.rydberg_state &&
-                       !P.dmin_cnt.empty();
-    if (caseA) {
-        dlo = 1e300; dhi = -1e300;
-        for (int c = 0; c <= N; ++c) {
-            if (P.dmin_cnt[c] > P.dmax_cnt[c]) continue;  // empty bin
-            dlo = std::min(dlo, P.dmin_cnt[c] - th * c);
-            dhi = std::max(dhi, P.dmax_cnt[c] - th * c);
-        }
-    } else {
-        dlo = P.has_interaction ? P.dmin_traj[0] : 0.0;
-        dhi = P.has_interaction ? P.dmax_traj[0] : 0.0;
-        dlo += N * std::min(0.0, -th); dhi += N * std::max(0.0, -th);
-    }
-    const double lo = dlo - dr, hi = dhi + dr;
-    centre = 0.5 * (lo + hi);
-    half = std::max(0.5 * (hi - lo) * (1.0 + 1e-9), 1e-9);
+    if (4 * cnt > nt) return false;
+    taylor_knot_widths(P);
+    double wsum = 0.0;
+    for (int i = 0; i + 1 < nt; ++i) wsum += 0.5 * (P.tay.w_knot[i] + P.tay.w_knot[i + 1]) * (P.times[i + 1] - P.times[i]);
+    const double applies_per_interval = 4.1 * wsum / std::max(nt - 1, 1);
+    const double hi_mean_ns = (P.times.back() - P.times.front()) / std::max(nt - 1, 1) * 1e3;
+    return applies_per_interval / std::max(hi_mean_ns, 1e-30) <= env_int("PB200_TAYLOR_MAX_APPLIES_MILLI", 12000) * 1e-3;
 }
 
 struct TaylorPoly {      // monomial coefficients in u of one coefficient function on a step, and the fit residual
@@ -1885,15 +2024,17 @@ static int taylor_order(double h, const std::vector<double>& mj, double tol, dou
 }
 
 static void launch_taylor_stage(Plan& P, const PassGeom* geo, const TaylorArgs& a, long long& launches) {
+    const bool uniform = a.table == nullptr;
     if (geo) {
-        dim3 grid((unsigned)(P.D >> 11)), block(256);
-        const size_t smem = (size_t)2048 * 16;
+        dim3 grid((unsigned)(P.D >> 11), (unsigned)(uniform ? 1 : P.B)), block(256);
+        const size_t smem = (size_t)2048 * 16 + (uniform ? 0 : (size_t)d2_table_stride(P.n) * 8);
         const bool real_g = a.unit.y == 0.0;
-        if (real_g) launch_k(stage_d2_taylor_kernel<true, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
-        else launch_k(stage_d2_taylor_kernel<false, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
+        if (!uniform) launch_k(stage_d2_taylor_kernel<false, false, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
+        else if (real_g) launch_k(stage_d2_taylor_kernel<true, true, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
+        else launch_k(stage_d2_taylor_kernel<true, false, 11, 3>, grid, block, smem, P.stream, P.use_pdl, a);
     } else {
-        const unsigned blocks = (unsigned)((P.D + 255) / 256);
-        stage_d2_taylor_small_kernel<<<blocks, 256, 0, P.stream>>>(a);
+        dim3 grid((unsigned)((P.D + 255) / 256), (unsigned)P.B);
+        stage_d2_taylor_small_kernel<<<grid, 256, 0, P.stream>>>(a);
     }
     ++launches;
 }
@@ -1921,14 +2062,9 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     const PiecewiseCubic<double>& om_pc = P.tay.om;
     const PiecewiseCubic<double>& th_pc = P.tabs[0][0].det[0];
     Plan::TaylorCache& C = P.tay;
-    if ((int)C.w_knot.size() != nt) {   // half-width of H at every sampling time (step-length rule)
-        C.w_knot.resize(nt);
-        for (int i = 0; i < nt; ++i) {
-            double c, hw;
-            taylor_bounds(P, eval_at(om_pc, P.times, P.times[i], order), eval_at(th_pc, P.times, P.times[i], order), c, hw);
-            C.w_knot[i] = hw;
-        }
-    }
+    taylor_knot_widths(P);
+    const PiecewiseCubic<double>& m_pc = C.mshape;
+    const double A_sum = std::max(C.a_sum_max, 1e-300), C_sum = std::max(C.c_sum_max, 1e-300);
     pb200_run_stats st{};
     EventPair evs;
     CUDA_CHECK(cudaEventRecord(evs.a, P.stream));
@@ -1941,14 +2077,15 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     // interval (|dH| <= (r_om + r_th) N, state error <= h |dH|).
     const double fit_total = 0.5 * rate * (t_stop - t_start);
     double fit_spent = 0.0;
-    struct Fit { TaylorPoly om, th; bool ok; };
+    struct Fit { TaylorPoly om, th, m; bool ok; };
     auto fit_step = [&](double a, double h, bool single_piece) {
         Fit F; F.ok = false;
         const double budget = std::max(0.5 * rate * h, 0.02 * std::max(fit_total - fit_spent, 0.0));
-        const double allow = budget / (h * N) * 0.5;
+        // |dH| <= r_om sum|a| + r_th N + r_M sum|c| : a third of the step's allowance each
+        const double third = budget / (3.0 * h);
         // smallest passing degree; a candidate that spans several intervals is first tried at the highest degree so
         // that a step across a non-smooth sample is refused after one fit instead of pmax + 1
-        auto one = [&](const PiecewiseCubic<double>& pc, TaylorPoly& out) {
+        auto one = [&](const PiecewiseCubic<double>& pc, TaylorPoly& out, double allow) {
             if (!single_piece) {
                 out = taylor_fit(pc, P.times, order, a, h, pmax);
                 if (out.resid > allow) return false;
@@ -1960,7 +2097,9 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
             if (single_piece) out = taylor_fit(pc, P.times, order, a, h, pmax);
             return true;
         };
-        F.ok = one(om_pc, F.om) && one(th_pc, F.th);
+        F.ok = one(om_pc, F.om, third / A_sum) && one(th_pc, F.th, third / N);
+        if (F.ok && C.has_m) F.ok = one(m_pc, F.m, third / C_sum);
+        if (!C.has_m) { F.m.c.assign(1, 0.0); F.m.resid = 0.0; }
         return F;
     };
 
@@ -2018,25 +2157,27 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
             while (c.size() > 1 && std::fabs(c.back()) <= 1e-15 * scale) c.pop_back();
         };
         {
-            double so = 0.0, sh = 0.0;
+            double so = 0.0, sh = 0.0, sm = 0.0;
             for (double v : F.om.c) so = std::max(so, std::fabs(v));
             for (double v : F.th.c) sh = std::max(sh, std::fabs(v));
-            trim(F.om.c, std::max(so, 1e-300)); trim(F.th.c, std::max(sh, 1e-300));
+            for (double v : F.m.c) sm = std::max(sm, std::fabs(v));
+            trim(F.om.c, std::max(so, 1e-300)); trim(F.th.c, std::max(sh, 1e-300)); trim(F.m.c, std::max(sm, 1e-300));
         }
-        const int p_om = (int)F.om.c.size() - 1, p_th = (int)F.th.c.size() - 1;
+        const int p_om = (int)F.om.c.size() - 1, p_m = (int)F.m.c.size() - 1;
+        const int p_th = std::max((int)F.th.c.size() - 1, p_m);   // degree of the diagonal (own-element) history
         const int p = std::max(p_om, p_th);
+        auto th_c = [&](int j) { return j < (int)F.th.c.size() ? F.th.c[j] : 0.0; };
+        auto m_c = [&](int j) { return j < (int)F.m.c.size() ? F.m.c[j] : 0.0; };
         // centres and norm bounds of H_j
         std::vector<double> gam(p + 1, 0.0), mj(p + 1, 0.0);
         {
             double c0, hw0;
-            taylor_bounds(P, F.om.c[0], F.th.c[0], c0, hw0);
+            taylor_bounds(P, F.om.c[0], F.th.c[0], m_c(0), c0, hw0);
             gam[0] = c0; mj[0] = hw0;
-            const bool from_counts = true;
-            (void)from_counts;
             for (int j = 1; j <= p; ++j) {
-                const double thj = j <= p_th ? F.th.c[j] : 0.0, omj = j <= p_om ? F.om.c[j] : 0.0;
+                const double thj = th_c(j), omj = j <= p_om ? F.om.c[j] : 0.0;
                 gam[j] = -thj * 0.5 * N;
-                mj[j] = std::fabs(thj) * 0.5 * N + std::fabs(omj) * N;
+                mj[j] = std::fabs(thj) * 0.5 * N + std::fabs(m_c(j)) * C_sum + std::fabs(omj) * A_sum;
             }
         }
         {   // the fp64 cancellation of the series grows like e^rho: a step whose majorant exponent overshoots the
@@ -2079,17 +2220,19 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
             a.g_out = (n_g && k + 1 < K) ? gr[k % n_g] : nullptr;
             a.acc = acc;
             a.dint = P.has_interaction ? P.dint : nullptr;
+            a.dint_stride = P.dint_shared ? 0 : P.D;
             a.D = P.D;
             a.geo = passes[0];
             a.unit = C.unit;
+            a.table = C.uniform ? nullptr : C.d_tab;
             a.to_bit = P.desc.drives[0].state_to; a.from_is_one = P.desc.drives[0].state_from;
-            a.th0 = F.th.c[0]; a.gam0 = gam[0]; a.om0 = F.om.c[0];
+            a.th0 = F.th.c[0]; a.gam0 = gam[0]; a.om0 = F.om.c[0]; a.m0 = m_c(0);
             a.scale = {0.0, -h / (k + 1)};
             a.nh = std::min(p, k);
             for (int j = 1; j <= a.nh; ++j) {
-                const double thj = j <= p_th ? F.th.c[j] : 0.0, omj = j <= p_om ? F.om.c[j] : 0.0;
-                a.hth[j - 1] = thj; a.hgam[j - 1] = gam[j]; a.hom[j - 1] = omj;
-                a.hchi[j - 1] = (thj != 0.0 || gam[j] != 0.0) ? chi[(k - j) % n_chi] : nullptr;
+                const double thj = th_c(j), mjv = m_c(j), omj = j <= p_om ? F.om.c[j] : 0.0;
+                a.hth[j - 1] = thj; a.hgam[j - 1] = gam[j]; a.hom[j - 1] = omj; a.hm[j - 1] = mjv;
+                a.hchi[j - 1] = (thj != 0.0 || mjv != 0.0 || gam[j] != 0.0) ? chi[(k - j) % n_chi] : nullptr;
                 a.hg[j - 1] = (omj != 0.0) ? gr[(k - j) % n_g] : nullptr;
             }
             const bool last = (k + 1 == K);
@@ -2103,13 +2246,14 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
         std::swap(P.buf[P.cur], *acc_slot);
         st.n_launches += launches; st.n_applies += K; st.n_exponentials += 1; ++st.n_steps;
         if (log_steps)
-            fprintf(stderr, "taylor step t=%.6f h_ns=%.3f p_om=%d p_th=%d K=%d rho=%.3f resid=%.2e/%.2e\n", t, h * 1e3, p_om, p_th, K,
-                    mj[0] * h, F.om.resid, F.th.resid);
+            fprintf(stderr, "taylor step t=%.6f h_ns=%.3f p_om=%d p_th=%d p_m=%d K=%d rho=%.3f resid=%.2e/%.2e/%.2e\n", t, h * 1e3, p_om,
+                    p_th, p_m, K, mj[0] * h, F.om.resid, F.th.resid, F.m.resid);
         double rho_eff = 0.0;
         for (int j = 0; j <= p; ++j) rho_eff += mj[j] / (j + 1);
         st.max_rho = std::max(st.max_rho, rho_eff * h);
-        st.err_estimate += trunc_bound + h * N * (F.om.resid + F.th.resid);
-        fit_spent += h * N * (F.om.resid + F.th.resid);
+        const double fit_err = h * (A_sum * F.om.resid + N * F.th.resid + C_sum * F.m.resid);
+        st.err_estimate += trunc_bound + fit_err;
+        fit_spent += fit_err;
         steps_len += h;
         t = b;
     }
@@ -2306,6 +2450,7 @@ int pb200_plan_destroy(pb200_plan* h) {
     pool_free(dev, P.d_scratch);
     for (int i = 0; i < 2; ++i) pool_free(dev, P.wbuf[i]);
     for (c2* w : P.tay_ws) pool_free(dev, w);
+    pool_free(dev, P.tay.d_tab);
     if (P.own_stream && P.stream) cudaStreamDestroy(P.stream);
     delete h;
     return PB200_OK;

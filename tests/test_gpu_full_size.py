@@ -96,7 +96,8 @@ def test_c3_configured_size_self_convergence(engine):
 
 
 def test_c4_configured_size_batch(engine):
-    """configs[3] at N = 16: a device batch of noise trajectories, Lanczos against Chebyshev, unit norms, and the
+    """configs[3] at N = 16: a device batch of noise trajectories, the batched Taylor propagator (what integrator 0
+    picks: per-qubit static amplitude factors and doppler offsets) against Lanczos and Chebyshev, unit norms, and the
     device-side shot + density reductions bench.py uses."""
     amp, det = W.blockade_sweep_waveforms(t_rise=60, t_sweep=160, t_fall=60)
     base = W.ising_global_spec(W.square_register(4, 6.0), W.C6_LEVEL_70, amp, det)
@@ -107,15 +108,17 @@ def test_c4_configured_size_batch(engine):
     tf = base.sampling_times[-1]
     outs = {}
     with engine.DevicePlan(specs) as plan:
-        for integ in (1, 2):
+        for integ in (1, 2, 0):
             plan.set_state("all-ground")
-            plan.propagate(0.0, tf, integrator=integ)
+            st = plan.propagate(0.0, tf, integrator=integ)
             assert np.max(np.abs(plan.norm2() - 1.0)) < 1e-9
             outs[integ] = plan.get_state().copy()
+        assert st["integrator"] == 3
         occ = plan.occupation(base.eigenbasis.index("r"))
         np.random.seed(0)
         shots = plan.sample(50, "r", traj=3)
     assert np.max(np.abs(outs[1] - outs[2])) < STATE_TOL
+    assert np.max(np.abs(outs[0] - outs[2])) < STATE_TOL
     idx = np.arange(base.hilbert_dim)
     p = np.abs(outs[2][3]) ** 2
     ref_occ = np.array([p[((idx >> (15 - k)) & 1) == 0].sum() for k in range(16)])

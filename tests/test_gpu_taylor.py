@@ -94,6 +94,34 @@ def test_auto_rule_and_evaluation_times(engine):
         assert st["integrator"] in (1, 2)
 
 
+@pytest.mark.parametrize("n", [5, 11, 12])
+def test_noise_trajectory_batch_vs_oracle(engine, n):
+    """C4-shaped batch: doppler offsets (zero on the padded last sample, i.e. det_k = theta + c_k M(t)) and per-atom
+    amplitude factors -- the separable form the batched Taylor stage handles (blockIdx.y = trajectory)."""
+    from oracle import evolve
+
+    amp, det = W.blockade_sweep_waveforms(t_rise=80, t_sweep=200, t_fall=80)
+    coords = W.disc_register(n, 14.0, 5.0, 5)
+    base = W.ising_global_spec(coords, W.C6_LEVEL_60, amp, det, phase=0.4)
+    rng = np.random.default_rng(n)
+    specs = [W.noisy_trajectory_spec(base, coords, rng.normal(0, 1.5, n), max(0.0, rng.normal(1.0, 0.05)), 60.0)
+             for _ in range(3)]
+    tf = base.sampling_times[-1]
+    psi0 = evolve.all_ground_state(base)
+    with engine.DevicePlan(specs) as plan:
+        plan.set_state("all-ground")
+        st = plan.propagate(0.0, tf)
+        got = plan.get_state().copy()
+        plan.set_state("all-ground")
+        st2 = plan.propagate(0.0, tf, integrator=2)
+        lan = plan.get_state().copy()
+    assert st["integrator"] == 3 and st2["integrator"] == 2
+    assert np.max(np.abs(got - lan)) < STATE_TOL
+    for b, spec in enumerate(specs):
+        ref = _oracle(spec, psi0, [0.0, tf])[-1]
+        assert np.max(np.abs(got[b] - ref)) < STATE_TOL, b
+
+
 def test_not_applicable_falls_back_or_raises(engine):
     """per-qubit drives with moving phases: auto keeps the Magnus path, integrator 3 is refused loudly."""
     spec = random_local_spec(6, T=120, seed=3)
