@@ -22,7 +22,8 @@ Every run also carries
         the bitstring histogram + Rydberg densities; trajectories/s and the
         speed-up against a 1-GPU reference leg measured in the same job;
   "c5": BASELINE configs[4] (N = 1 only): the 24-atom anneal end to end,
-        steps/s, H-applies/ns, us per apply, achieved GB/s.
+        steps/s, H-applies/ns, us per apply, achieved GB/s;
+  "c3": BASELINE configs[2] (N = 1 only): the 14-atom three-level sequence.
 """
 from __future__ import annotations
 
@@ -212,6 +213,7 @@ def c4_stripe_run(local: int, rank: int, world: int, n_total: int, stream) -> di
             stats["batches"] += 1
             stats["traj_applies"] += st["n_applies"] * len(chunk)   # n_applies counts per trajectory of the batch
             stats["integrator"] = int(st["integrator"])
+            stats["taylor_batches"] = stats.get("taylor_batches", 0) + (1 if int(st["integrator"]) == 3 else 0)
             r = chunk[0].eigenbasis.index("r")
             dens[:] += plan.occupation(r).sum(axis=0)
             for i in range(len(chunk)):
@@ -229,19 +231,66 @@ def c4_stripe_run(local: int, rank: int, world: int, n_total: int, stream) -> di
     return {"hist": hist, "dens": dens, "ms": e0.elapsed_time(e1), "n_local": len(mine), **stats}
 
 
+def c4_warmup(local: int) -> None:
+    from pulser_b200 import engine, workloads as W
+
+    specs = W.config_c4(C4_BATCH, seed=99)
+    with engine.DevicePlan(specs, device=local) as plan:
+        plan.set_state("all-ground")
+        plan.propagate(0.0, 0.25)
+        plan.sample(1, "r", traj=0)
+
+
+def c3_leg(local: int, stream) -> dict:
+    """BASELINE configs[2]: 14-atom 'all' basis (3 levels, Raman + Rydberg channels), whole 2000-ns sequence."""
+    import torch
+
+    from pulser_b200 import engine, workloads as W
+
+    n = int(os.environ.get("PB200_BENCH_C3_ATOMS", "14"))
+    spec = W.config_c3(n=n)
+    with engine.DevicePlan(spec, device=local) as plan:
+        plan.set_stream(stream.cuda_stream)
+        plan.set_state("all-ground")
+        plan.propagate(0.0, 0.05)   # warm-up
+        plan.set_state("all-ground")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = plan.propagate(0.0, spec.sampling_times[-1])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        norm2 = float(plan.norm2()[0])
+    T = spec.total_duration_ns
+    return {"workload": f"C3: {n}-atom random 2D register, basis 'all' (r, g, h), raman_global Blackman pi/2 - rydberg_global "
+                        f"Blackman pi - raman_global Blackman pi/2, {T} ns, fp64",
+            "hilbert_dim": spec.hilbert_dim, "steps_per_s": T / (ms * 1e-3), "seconds": ms * 1e-3,
+            "h_applies_per_time_step": st["n_applies"] / T, "integrator": INTEGRATOR_NAMES.get(int(st["integrator"]), "?"),
+            "gpu_launches": int(st["n_launches"]), "norm2_final": norm2}
+
+
 def c4_leg(local: int, rank: int, world: int, dist, barrier, stream) -> dict | None:
     import torch
 
     n_total = int(os.environ.get("PB200_BENCH_C4_TRAJ", "1024" if world > 1 else "128"))
+    # untimed warm-up: one full-size device batch over a short stretch, so that the buffer pool and the kernels of this
+    # path exist before the timed stripe (the 1-GPU reference leg below runs warm too)
+    c4_warmup(local)
     barrier()
     r = c4_stripe_run(local, rank, world, n_total, stream)
     # THE collective of the path: histogram + density sums + (max) time in one packed tensor pair
     packed = torch.from_numpy(np.concatenate([r["hist"], r["dens"], [r["traj_applies"], r["n_launches"]]])).to("cuda")
     tmax = torch.tensor([r["ms"]], dtype=torch.float64, device="cuda")
+    # diagnostics only (not part of the path): every rank's device time, device-batch count and how many of its batches
+    # ran on the Taylor propagator, placed in its own slot of a zero vector that rides on a second SUM
+    diag = torch.zeros(3 * world, dtype=torch.float64, device="cuda")
+    diag[3 * rank: 3 * rank + 3] = torch.tensor([r["ms"] * 1e-3, r["batches"], r.get("taylor_batches", 0)], dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(diag, op=dist.ReduceOp.SUM)
     barrier()
+    diag = diag.cpu().numpy().reshape(world, 3)
     tot = packed.cpu().numpy()
     hist, dens = tot[: 1 << 16], tot[1 << 16: (1 << 16) + 16]
     seconds = float(tmax.item()) * 1e-3
@@ -252,8 +301,11 @@ def c4_leg(local: int, rank: int, world: int, dist, barrier, stream) -> dict | N
         "seconds": seconds, "trajectories_per_s": n_total / seconds, "traj_steps_per_s": n_total * 4000 / seconds,
         "h_applies_per_traj_step": float(tot[-2]) / (4000.0 * n_total), "gpu_launches": int(tot[-1]),
         "integrator": INTEGRATOR_NAMES.get(r.get("integrator", 0), "?"),
+        "per_rank": {"seconds": [round(float(x), 3) for x in diag[:, 0]], "device_batches": [int(x) for x in diag[:, 1]],
+                     "taylor_batches": [int(x) for x in diag[:, 2]]},
         "shots": int(round(hist.sum())), "mean_rydberg_density": float(dens.sum() / (16 * n_total)),
-        "collective": "1 all_reduce(SUM) of [2^16 histogram | 16 densities | counters] + 1 all_reduce(MAX) of the time",
+        "collective": "1 all_reduce(SUM) of [2^16 histogram | 16 densities | counters] + 1 all_reduce(MAX) of the time "
+                      "(+ 1 diagnostic SUM of the per-rank timings, outside the timed region)",
         "timing": "CUDA events on the stream of the plans around the whole stripe (host-side spec building, plan "
                   "creation and sampling included), max over ranks",
     }
@@ -413,6 +465,9 @@ def run_gpu(args) -> None:
     c5 = None
     if world == 1 and os.environ.get("PB200_BENCH_SKIP_C5", "0") != "1":
         c5 = c5_leg(local, stream, peak)
+    c3 = None
+    if world == 1 and os.environ.get("PB200_BENCH_SKIP_C3", "0") != "1":
+        c3 = c3_leg(local, stream)
     if rank == 0:
         per_launch_s = (kernel_ms * 1e-3) / max(launches, 1)
         # 16 (psi) + 8 (Dint) + 16 (out) per amplitude per H-apply; a launch of the Taylor stage kernel
@@ -448,6 +503,8 @@ def run_gpu(args) -> None:
             line["c4"] = c4
         if c5 is not None:
             line["c5"] = c5
+        if c3 is not None:
+            line["c3"] = c3
         if os.environ.get("PB200_BENCH_SKIP_CPU", "0") != "1":
             n_sample = int(os.environ.get("PB200_REF_SAMPLE_STEPS", "50" if N_ATOMS >= 20 else "400"))
             line["cpu_baseline"] = cpu_reference_run(workload(N_ATOMS), n_sample) if world == 1 else None

@@ -1400,6 +1400,7 @@ static void propagate_mcwf(Plan& P, double t_start, double t_stop, const pb200_r
     if (stats) *stats = st;
 }
 
+static thread_local const char* g_taylor_why = "";   // why the Taylor propagator was not taken (PB200_TAYLOR_LOG)
 static bool taylor_prepare(Plan& P);
 static bool taylor_worthwhile(Plan& P, double gtol);
 static bool taylor_geometry(const Plan& P, const std::vector<PassGeom>& passes, bool& use_rb);
@@ -1432,6 +1433,7 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
             const bool ok = taylor_prepare(P) && taylor_geometry(P, plan_passes(P.n, P.tile_bits, P.max_extra), use_rb) &&
                             (req == 3 || taylor_worthwhile(P, (o && o->tol > 0.0) ? o->tol : 1e-8));
             if (ok) { propagate_taylor(P, t_start, t_stop, o, stats); return; }
+            if (env_int("PB200_TAYLOR_LOG", 0)) fprintf(stderr, "taylor not taken: %s\n", g_taylor_why);
             if (req == 3)
                 fail(PB200_ERR_UNSUPPORTED, "integrator 3 (Taylor) needs a d = 2 register whose drive is one time shape of constant phase "
                                             "(per-qubit static factors / detuning offsets allowed), no collapse operators / SLM mask");
@@ -1742,10 +1744,11 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
 // real part of the drive along its constant phase, and the half-width of H(t) at every sampling time
 static bool taylor_prepare(Plan& P) {
     Plan::TaylorCache& C = P.tay;
+    g_taylor_why = "structure (d, drives, collapse / dissipator / mask, interpolation order)";
     if (!is_d2path(P)) return false;
     if (P.has_diss || P.has_collapse || P.has_slm || P.force_v1) return false;
     if (P.desc.interp_order != 3 && P.desc.interp_order != 1) return false;
-    if (C.valid) return C.ok;
+    if (C.valid) { if (C.ok) g_taylor_why = ""; return C.ok; }
     C.valid = true; C.ok = false;
     const int N = P.n, B = P.B, nt = (int)P.times.size();
     auto rows_of = [&](int b) { return (int)P.tabs[b][0].coef.size(); };
@@ -1773,26 +1776,35 @@ static bool taylor_prepare(Plan& P) {
         const cplx v0 = ref.c0[i] * cu, v1 = ref.c1[i] * cu, v2 = ref.c2[i] * cu, v3 = ref.c3[i] * cu;
         const double im = std::max(std::max(std::fabs(v0.imag()), std::fabs(v1.imag()) * hi),
                                    std::max(std::fabs(v2.imag()) * hi * hi, std::fabs(v3.imag()) * hi * hi * hi));
-        if (im > 1e-13 * scale) return false;   // the phase moves: not a single real polynomial
+        if (im > 1e-13 * scale) { g_taylor_why = "the drive phase moves in time"; return false; }
         C.om.c0[i] = v0.real(); C.om.c1[i] = v1.real(); C.om.c2[i] = v2.real(); C.om.c3[i] = v3.real();
     }
     C.om.y_last = (ref.y_last * cu).real();
     C.unit = {unit.real(), unit.imag()};
     // every drive row = a (complex constant) x the reference row
     C.a.assign((size_t)B * N, cplx(1.0, 0.0));
-    double ref2 = 0.0;
-    for (int i = 0; i < nt; ++i) ref2 += std::norm(csample(ref, i));
+    // least-squares factors with extended-precision sums (4001 same-sign terms: a plain double sum is only good to
+    // ~1e-13, which is the size of the residual being tested)
+    long double ref2 = 0.0L;
+    for (int i = 0; i < nt; ++i) ref2 += (long double)std::norm(csample(ref, i));
     for (int b = 0; b < B; ++b)
         for (int k = 0; k < N; ++k) {
             const PiecewiseCubic<cplx>& pc = coef_pc(b, k);
             cplx aa = 0.0;
-            if (ref2 > 0.0) {
-                for (int i = 0; i < nt; ++i) aa += csample(pc, i) * std::conj(csample(ref, i));
-                aa /= ref2;
+            if (ref2 > 0.0L) {
+                long double sr = 0.0L, si = 0.0L;
+                for (int i = 0; i < nt; ++i) {
+                    const cplx z = csample(pc, i) * std::conj(csample(ref, i));
+                    sr += (long double)z.real(); si += (long double)z.imag();
+                }
+                aa = cplx((double)(sr / ref2), (double)(si / ref2));
             }
             for (int i = 0; i < nt; ++i)
-                if (std::abs(csample(pc, i) - aa * csample(ref, i)) > 1e-13 * std::max(scale, 1e-300)) return false;
-            C.a[(size_t)b * N + k] = (ref2 > 0.0) ? aa : cplx(0.0, 0.0);
+                if (std::abs(csample(pc, i) - aa * csample(ref, i)) > 2e-13 * std::max(scale, 1e-300)) {
+                    g_taylor_why = "a drive row is not a constant multiple of the reference row";
+                    return false;
+                }
+            C.a[(size_t)b * N + k] = (ref2 > 0.0L) ? aa : cplx(0.0, 0.0);
         }
     // every detuning row = the reference row + c x one common shape M
     const PiecewiseCubic<double>& dref = det_pc(0, 0);
@@ -1812,16 +1824,22 @@ static bool taylor_prepare(Plan& P) {
     if (C.has_m) {
         std::vector<double> m(nt);
         const double norm = dsample(det_pc(mb, mk), mi) - dsample(dref, mi);
-        double m2 = 0.0;
-        for (int i = 0; i < nt; ++i) { m[i] = (dsample(det_pc(mb, mk), i) - dsample(dref, i)) / norm; m2 += m[i] * m[i]; }
+        long double m2 = 0.0L;
+        for (int i = 0; i < nt; ++i) {
+            m[i] = (dsample(det_pc(mb, mk), i) - dsample(dref, i)) / norm;
+            m2 += (long double)m[i] * m[i];
+        }
         for (int b = 0; b < B; ++b)
             for (int k = 0; k < N; ++k) {
                 const PiecewiseCubic<double>& pc = det_pc(b, k);
-                double cc = 0.0;
-                for (int i = 0; i < nt; ++i) cc += (dsample(pc, i) - dsample(dref, i)) * m[i];
-                cc /= m2;
+                long double acc = 0.0L;
+                for (int i = 0; i < nt; ++i) acc += (long double)(dsample(pc, i) - dsample(dref, i)) * m[i];
+                const double cc = (double)(acc / m2);
                 for (int i = 0; i < nt; ++i)
-                    if (std::fabs(dsample(pc, i) - dsample(dref, i) - cc * m[i]) > 1e-13 * std::max(dscale, 1e-300)) return false;
+                    if (std::fabs(dsample(pc, i) - dsample(dref, i) - cc * m[i]) > 2e-13 * std::max(dscale, 1e-300)) {
+                        g_taylor_why = "a detuning row is not the reference row plus a multiple of the common shape";
+                        return false;
+                    }
                 C.c[(size_t)b * N + k] = cc;
             }
         C.mshape = make_interpolant<double>(P.times.data(), m.data(), nt, P.desc.interp_order);
@@ -1936,13 +1954,15 @@ static bool taylor_worthwhile(Plan& P, double gtol) {
     }
     int cnt = 0;
     for (char c : rough) cnt += c;
-    if (4 * cnt > nt) return false;
+    if (4 * cnt > nt) { g_taylor_why = "splines too rough for multi-interval polynomial steps"; return false; }
     taylor_knot_widths(P);
     double wsum = 0.0;
     for (int i = 0; i + 1 < nt; ++i) wsum += 0.5 * (P.tay.w_knot[i] + P.tay.w_knot[i + 1]) * (P.times[i + 1] - P.times[i]);
     const double applies_per_interval = 4.1 * wsum / std::max(nt - 1, 1);
     const double hi_mean_ns = (P.times.back() - P.times.front()) / std::max(nt - 1, 1) * 1e3;
-    return applies_per_interval / std::max(hi_mean_ns, 1e-30) <= env_int("PB200_TAYLOR_MAX_APPLIES_MILLI", 12000) * 1e-3;
+    const bool cheap = applies_per_interval / std::max(hi_mean_ns, 1e-30) <= env_int("PB200_TAYLOR_MAX_APPLIES_MILLI", 12000) * 1e-3;
+    if (!cheap) g_taylor_why = "spectrum too wide: the Krylov path is expected to be cheaper";
+    return cheap;
 }
 
 struct TaylorPoly {      // monomial coefficients in u of one coefficient function on a step, and the fit residual
