@@ -1425,8 +1425,9 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
         if (req == 0 && P.use_taylor) {
             const bool steered = o && (o->max_step_samples > 0 || o->tol < 0.0 || o->extrapolate < 0 || o->check_every > 0 ||
                                        o->cheb_tol > 0.0 || (o->magnus_order != 0 && o->magnus_order != 4));
-            const double hi_mean = (thi - tlo) / std::max((int)P.times.size() - 1, 1);
-            want = !steered && (t_stop - t_start) >= 4.0 * hi_mean;
+            want = !steered && t_stop > t_start;   // short calls too ("Full" evaluation times: one call per sampling
+                                                   // interval = one exact cubic step of ~10 orders, against ~50
+                                                   // H-applies for a Richardson-CF4 step of the same length)
         }
         if (want) {
             bool use_rb = false;

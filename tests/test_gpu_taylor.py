@@ -75,7 +75,8 @@ def test_smooth_waveforms_and_constant_phase(engine, n, phase):
 
 def test_auto_rule_and_evaluation_times(engine):
     """integrator 0 takes the Taylor propagator here; a run cut at arbitrary (off-grid) evaluation times gives the
-    oracle's states at each of them; a short call (< 4 sampling intervals) stays on the Magnus path."""
+    oracle's states at each of them, and so does a run cut at EVERY sampling time ("Full" evaluation times: one call,
+    i.e. one exact cubic step, per interval)."""
     from oracle import evolve
 
     spec = W.config_c2(n=9, seed=4)
@@ -90,8 +91,16 @@ def test_auto_rule_and_evaluation_times(engine):
             assert st["integrator"] == 3
             assert np.max(np.abs(plan.get_state()[0] - ref)) < STATE_TOL
         plan.set_state("all-ground")
-        st = plan.propagate(0.0, 0.002)
-        assert st["integrator"] in (1, 2)
+        t_full = spec.sampling_times[480:561]          # across the kink of the waveform at 500 ns
+        plan.set_state(_oracle(spec, psi0, [0.0, t_full[0]])[-1])
+        applies = 0
+        for a, b in zip(t_full[:-1], t_full[1:]):
+            st = plan.propagate(float(a), float(b))
+            assert st["integrator"] == 3
+            applies += st["n_applies"]
+        ref_end = _oracle(spec, psi0, [0.0, float(t_full[-1])])[-1]
+        assert np.max(np.abs(plan.get_state()[0] - ref_end)) < STATE_TOL
+        assert applies < 16 * (len(t_full) - 1)
 
 
 @pytest.mark.parametrize("n", [5, 11, 12])
