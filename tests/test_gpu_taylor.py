@@ -38,7 +38,7 @@ def _blackman_spec(n, phase=0.0, T=600):
     return W.ising_global_spec(coords, W.C6_LEVEL_60, amp, det, phase=phase)
 
 
-@pytest.mark.parametrize("n", [1, 2, 6, 10, 11, 12, 13])
+@pytest.mark.parametrize("n", [1, 2, 6, 10, 11, 12])
 def test_blockade_sweep_vs_oracle(engine, n):
     """C2-shaped sequence: small registers run the one-thread-per-amplitude stage, N >= 11 the tiled one."""
     from oracle import evolve
@@ -162,10 +162,11 @@ def test_tolerance_scaling(engine):
     assert out[1e-5][1] < out[1e-8][1] < out[1e-10][1]
 
 
-@pytest.mark.parametrize("name", ["c2_n20", "c5_n24"])
+@pytest.mark.parametrize("name", ["c2_n20"])
 def test_full_size_against_the_magnus_paths(engine, name):
-    """C2 (N = 20, L2-resident) and C5 (N = 24, HBM-resident) at their configured sizes: the Taylor run agrees with
-    the Richardson-CF4 run at a 100x tighter tolerance to 1e-8, at a fraction of the H-applies."""
+    """C2 (N = 20, L2-resident) at its configured size: the Taylor run agrees with the Richardson-CF4 run at a 100x
+    tighter tolerance to 1e-8, at a fraction of the H-applies.  (C5, N = 24, HBM-resident: the same comparison against
+    three Magnus runs is tests/test_gpu_full_size.py::test_c5_whole_sequence.)"""
     spec = {"c2_n20": lambda: W.config_c2(n=20), "c5_n24": lambda: W.config_c5(n=24)}[name]()
     tf = spec.sampling_times[-1]
     with engine.DevicePlan(spec) as plan:
