@@ -287,6 +287,20 @@ int pb200_host_moments(const double* x, const double* y, int32_t n,
 int pb200_host_taylor_fit(const double* x, const double* y, int32_t n,
                           int32_t order, double a, double h, int32_t p,
                           double* coeffs, double* resid);
+/* Separable structure of a batch of drive tables (what lets noise-trajectory
+ * batches run on integrator 3): coef[n_traj][n_qudits][n_times] (re,im) and
+ * det[n_traj][n_qudits][n_times] as handed to pb200_plan_set_drive (rows = N).
+ * *separable = 1 when coef_{b,k} = a_{b,k} * (largest drive row) and
+ * det_{b,k} = det_{0,0} + c_{b,k} * m with one common shape m (max |m| = 1), to
+ * 2e-13 of the largest sample; then a_out[n_traj][n_qudits] (re,im),
+ * c_out[n_traj][n_qudits], m_out[n_times] (any may be NULL).  Restates what
+ * HamiltonianData._sample_with_trajectory does to Global samples
+ * (pulser-core/pulser/_hamiltonian_data/hamiltonian_data.py:408-534): amp *=
+ * fluctuation * waist factor, det += doppler shift inside the pulse slots. */
+int pb200_host_taylor_separable(const double* coef, const double* det,
+                                int32_t n_traj, int32_t n_qudits,
+                                int32_t n_times, int32_t* separable,
+                                double* a_out, double* c_out, double* m_out);
 /* Order K of the Taylor series of a step of length h whose generator obeys
  * |H_j| <= m[j] (j = 0..p): smallest K with remainder bound *tail_out <= tol. */
 int pb200_host_taylor_order(double h, const double* m, int32_t p, double tol,

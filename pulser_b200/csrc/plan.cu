@@ -1742,7 +1742,92 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
 // C2 against 6.9.  Error = fit residual of the splines (measured) + Taylor remainder (majorant bound) -- both a priori,
 // so a run never synchronises with the host.
 
-// real part of the drive along its constant phase, and the half-width of H(t) at every sampling time
+// Separable structure of a batch of drive tables, read off the samples (the interpolants are linear in the samples and
+// share their knots):  coef_{b,k}[i] = a_{b,k} * coef_ref[i]  and  det_{b,k}[i] = det_{0,0}[i] + c_{b,k} * m[i]  with ONE
+// reference drive row (the largest one) and ONE common shape m (max |m| = 1).  cs(b,k,i) / ds(b,k,i) return the samples.
+// Least-squares factors with extended-precision sums (4001 same-sign terms: a plain double sum is only good to ~1e-13,
+// which is the size of the residual being tested).  Host only; also reachable through pb200_host_taylor_separable.
+struct SeparableFit {
+    bool ok = false;
+    const char* why = "";
+    int ref_b = 0, ref_k = 0;       // reference drive row
+    cplx big = 0.0; double scale = 0.0;
+    std::vector<cplx> a;            // [B][N]
+    std::vector<double> c, m;       // [B][N], [nt]
+    bool has_m = false;
+};
+
+template <class CS, class DS>
+static SeparableFit taylor_separable(int B, int N, int nt, CS cs, DS ds) {
+    SeparableFit F;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < nt; ++i) {
+                const cplx y = cs(b, k, i);
+                if (std::abs(y) > F.scale) { F.scale = std::abs(y); F.big = y; F.ref_b = b; F.ref_k = k; }
+            }
+    const double scale = F.scale;
+    F.a.assign((size_t)B * N, cplx(1.0, 0.0));
+    long double ref2 = 0.0L;
+    for (int i = 0; i < nt; ++i) ref2 += (long double)std::norm(cs(F.ref_b, F.ref_k, i));
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < N; ++k) {
+            cplx aa = 0.0;
+            if (ref2 > 0.0L) {
+                long double sr = 0.0L, si = 0.0L;
+                for (int i = 0; i < nt; ++i) {
+                    const cplx z = cs(b, k, i) * std::conj(cs(F.ref_b, F.ref_k, i));
+                    sr += (long double)z.real(); si += (long double)z.imag();
+                }
+                aa = cplx((double)(sr / ref2), (double)(si / ref2));
+            }
+            for (int i = 0; i < nt; ++i)
+                if (std::abs(cs(b, k, i) - aa * cs(F.ref_b, F.ref_k, i)) > 2e-13 * std::max(scale, 1e-300)) {
+                    F.why = "a drive row is not a constant multiple of the reference row";
+                    return F;
+                }
+            F.a[(size_t)b * N + k] = (ref2 > 0.0L) ? aa : cplx(0.0, 0.0);
+        }
+    // every detuning row = the reference row (trajectory 0, qubit 0) + c x one common shape m
+    double dscale = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < nt; ++i) dscale = std::max(dscale, std::fabs(ds(b, k, i)));
+    int mb = -1, mk = -1, mi = 0; double emax = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < nt; ++i) {
+                const double e = std::fabs(ds(b, k, i) - ds(0, 0, i));
+                if (e > emax) { emax = e; mb = b; mk = k; mi = i; }
+            }
+    F.c.assign((size_t)B * N, 0.0);
+    F.m.assign(nt, 0.0);
+    F.has_m = emax > 1e-13 * std::max(dscale, 1e-300);
+    if (F.has_m) {
+        const double norm = ds(mb, mk, mi) - ds(0, 0, mi);
+        long double m2 = 0.0L;
+        for (int i = 0; i < nt; ++i) {
+            F.m[i] = (ds(mb, mk, i) - ds(0, 0, i)) / norm;
+            m2 += (long double)F.m[i] * F.m[i];
+        }
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < N; ++k) {
+                long double acc = 0.0L;
+                for (int i = 0; i < nt; ++i) acc += (long double)(ds(b, k, i) - ds(0, 0, i)) * F.m[i];
+                const double cc = (double)(acc / m2);
+                for (int i = 0; i < nt; ++i)
+                    if (std::fabs(ds(b, k, i) - ds(0, 0, i) - cc * F.m[i]) > 2e-13 * std::max(dscale, 1e-300)) {
+                        F.why = "a detuning row is not the reference row plus a multiple of the common shape";
+                        return F;
+                    }
+                F.c[(size_t)b * N + k] = cc;
+            }
+    }
+    F.ok = true;
+    return F;
+}
+
+// real part of the drive along its constant phase, per-(trajectory, qubit) static factors, device table
 static bool taylor_prepare(Plan& P) {
     Plan::TaylorCache& C = P.tay;
     g_taylor_why = "structure (d, drives, collapse / dissipator / mask, interpolation order)";
@@ -1755,20 +1840,15 @@ static bool taylor_prepare(Plan& P) {
     auto rows_of = [&](int b) { return (int)P.tabs[b][0].coef.size(); };
     auto coef_pc = [&](int b, int k) -> const PiecewiseCubic<cplx>& { return P.tabs[b][0].coef[rows_of(b) == 1 ? 0 : k]; };
     auto det_pc = [&](int b, int k) -> const PiecewiseCubic<double>& { return P.tabs[b][0].det[rows_of(b) == 1 ? 0 : k]; };
-    // the interpolants are linear in the samples (same knots everywhere): the structure is read off the samples
-    auto csample = [&](const PiecewiseCubic<cplx>& pc, int i) { return i < pc.pieces() ? pc.c0[i] : pc.y_last; };
-    auto dsample = [&](const PiecewiseCubic<double>& pc, int i) { return i < pc.pieces() ? pc.c0[i] : pc.y_last; };
-    // reference drive row: the largest one
-    int rb = 0, rk = 0; double scale = 0.0; cplx big = 0.0;
-    for (int b = 0; b < B; ++b)
-        for (int k = 0; k < (rows_of(b) == 1 ? 1 : N); ++k)
-            for (int i = 0; i < nt; ++i) {
-                const cplx y = csample(coef_pc(b, k), i);
-                if (std::abs(y) > scale) { scale = std::abs(y); big = y; rb = b; rk = k; }
-            }
-    const cplx unit = scale > 0.0 ? big / scale : cplx(1.0, 0.0);
+    const SeparableFit F = taylor_separable(
+        B, N, nt,
+        [&](int b, int k, int i) { const PiecewiseCubic<cplx>& pc = coef_pc(b, k); return i < pc.pieces() ? pc.c0[i] : pc.y_last; },
+        [&](int b, int k, int i) { const PiecewiseCubic<double>& pc = det_pc(b, k); return i < pc.pieces() ? pc.c0[i] : pc.y_last; });
+    if (!F.ok) { g_taylor_why = F.why; return false; }
+    const double scale = F.scale;
+    const cplx unit = scale > 0.0 ? F.big / scale : cplx(1.0, 0.0);
     const cplx cu = std::conj(unit);
-    const PiecewiseCubic<cplx>& ref = coef_pc(rb, rk);
+    const PiecewiseCubic<cplx>& ref = coef_pc(F.ref_b, F.ref_k);
     const int np = ref.pieces();
     C.om = PiecewiseCubic<double>();
     C.om.c0.resize(np); C.om.c1.resize(np); C.om.c2.resize(np); C.om.c3.resize(np);
@@ -1782,69 +1862,8 @@ static bool taylor_prepare(Plan& P) {
     }
     C.om.y_last = (ref.y_last * cu).real();
     C.unit = {unit.real(), unit.imag()};
-    // every drive row = a (complex constant) x the reference row
-    C.a.assign((size_t)B * N, cplx(1.0, 0.0));
-    // least-squares factors with extended-precision sums (4001 same-sign terms: a plain double sum is only good to
-    // ~1e-13, which is the size of the residual being tested)
-    long double ref2 = 0.0L;
-    for (int i = 0; i < nt; ++i) ref2 += (long double)std::norm(csample(ref, i));
-    for (int b = 0; b < B; ++b)
-        for (int k = 0; k < N; ++k) {
-            const PiecewiseCubic<cplx>& pc = coef_pc(b, k);
-            cplx aa = 0.0;
-            if (ref2 > 0.0L) {
-                long double sr = 0.0L, si = 0.0L;
-                for (int i = 0; i < nt; ++i) {
-                    const cplx z = csample(pc, i) * std::conj(csample(ref, i));
-                    sr += (long double)z.real(); si += (long double)z.imag();
-                }
-                aa = cplx((double)(sr / ref2), (double)(si / ref2));
-            }
-            for (int i = 0; i < nt; ++i)
-                if (std::abs(csample(pc, i) - aa * csample(ref, i)) > 2e-13 * std::max(scale, 1e-300)) {
-                    g_taylor_why = "a drive row is not a constant multiple of the reference row";
-                    return false;
-                }
-            C.a[(size_t)b * N + k] = (ref2 > 0.0L) ? aa : cplx(0.0, 0.0);
-        }
-    // every detuning row = the reference row + c x one common shape M
-    const PiecewiseCubic<double>& dref = det_pc(0, 0);
-    double dscale = 0.0;
-    for (int b = 0; b < B; ++b)
-        for (int k = 0; k < (rows_of(b) == 1 ? 1 : N); ++k)
-            for (int i = 0; i < nt; ++i) dscale = std::max(dscale, std::fabs(dsample(det_pc(b, k), i)));
-    int mb = -1, mk = -1; double emax = 0.0; int mi = 0;
-    for (int b = 0; b < B; ++b)
-        for (int k = 0; k < (rows_of(b) == 1 ? 1 : N); ++k)
-            for (int i = 0; i < nt; ++i) {
-                const double e = std::fabs(dsample(det_pc(b, k), i) - dsample(dref, i));
-                if (e > emax) { emax = e; mb = b; mk = k; mi = i; }
-            }
-    C.c.assign((size_t)B * N, 0.0);
-    C.has_m = emax > 1e-13 * std::max(dscale, 1e-300);
-    if (C.has_m) {
-        std::vector<double> m(nt);
-        const double norm = dsample(det_pc(mb, mk), mi) - dsample(dref, mi);
-        long double m2 = 0.0L;
-        for (int i = 0; i < nt; ++i) {
-            m[i] = (dsample(det_pc(mb, mk), i) - dsample(dref, i)) / norm;
-            m2 += (long double)m[i] * m[i];
-        }
-        for (int b = 0; b < B; ++b)
-            for (int k = 0; k < N; ++k) {
-                const PiecewiseCubic<double>& pc = det_pc(b, k);
-                long double acc = 0.0L;
-                for (int i = 0; i < nt; ++i) acc += (long double)(dsample(pc, i) - dsample(dref, i)) * m[i];
-                const double cc = (double)(acc / m2);
-                for (int i = 0; i < nt; ++i)
-                    if (std::fabs(dsample(pc, i) - dsample(dref, i) - cc * m[i]) > 2e-13 * std::max(dscale, 1e-300)) {
-                        g_taylor_why = "a detuning row is not the reference row plus a multiple of the common shape";
-                        return false;
-                    }
-                C.c[(size_t)b * N + k] = cc;
-            }
-        C.mshape = make_interpolant<double>(P.times.data(), m.data(), nt, P.desc.interp_order);
-    }
+    C.a = F.a; C.c = F.c; C.has_m = F.has_m;
+    if (C.has_m) C.mshape = make_interpolant<double>(P.times.data(), F.m.data(), nt, P.desc.interp_order);
     C.uniform = (B == 1) && !C.has_m;
     C.a_sum_max = 0.0; C.c_sum_max = 0.0;
     for (int b = 0; b < B; ++b) {
@@ -3067,6 +3086,26 @@ int pb200_host_taylor_fit(const double* x, const double* y, int32_t n, int32_t o
     const TaylorPoly f = taylor_fit(pc, xs, order, a, h, p);
     for (int i = 0; i <= p; ++i) coeffs[i] = f.c[i];
     if (resid) *resid = f.resid;
+    PB200_CATCH
+}
+
+int pb200_host_taylor_separable(const double* coef, const double* det, int32_t n_traj, int32_t n_qudits, int32_t n_times,
+                                int32_t* separable, double* a_out, double* c_out, double* m_out) {
+    PB200_TRY
+    if (!coef || !det || !separable || n_traj < 1 || n_qudits < 1 || n_times < 2) fail(PB200_ERR_INVALID, "bad argument");
+    const cplx* y = reinterpret_cast<const cplx*>(coef);
+    const size_t nt = (size_t)n_times, N = (size_t)n_qudits;
+    const SeparableFit F = taylor_separable(
+        n_traj, n_qudits, n_times, [&](int b, int k, int i) { return y[((size_t)b * N + k) * nt + i]; },
+        [&](int b, int k, int i) { return det[((size_t)b * N + k) * nt + i]; });
+    *separable = F.ok ? 1 : 0;
+    if (F.ok) {
+        // the factors refer to the reference row: report them scaled by its phase so that coef = a x |ref row| shape
+        if (a_out)
+            for (size_t x = 0; x < F.a.size(); ++x) { a_out[2 * x] = F.a[x].real(); a_out[2 * x + 1] = F.a[x].imag(); }
+        if (c_out) for (size_t x = 0; x < F.c.size(); ++x) c_out[x] = F.c[x];
+        if (m_out) for (size_t i = 0; i < F.m.size(); ++i) m_out[i] = F.m[i];
+    }
     PB200_CATCH
 }
 

@@ -143,3 +143,61 @@ def test_recurrence_with_library_host_math_vs_oracle(lib):
                          rtol=1e-13, atol=1e-15)[-1]
     assert np.max(np.abs(psi - ref)) < 1e-8
     assert applies < 1.5 * (nt - 1)      # ~0.6 H-applies per ns at this size (the Magnus path needs ~4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# separable structure of noise-trajectory batches (what lets C4 batches run on integrator 3)
+def _separable(lib, coef, det):
+    B, N, nt = det.shape
+    ok = C.c_int32(-1)
+    a = np.zeros((B, N), dtype=np.complex128)
+    c = np.zeros((B, N))
+    m = np.zeros(nt)
+    coef = np.ascontiguousarray(coef, dtype=np.complex128)
+    det = np.ascontiguousarray(det, dtype=np.float64)
+    assert lib.pb200_host_taylor_separable(P(coef.view(np.float64)), P(det), B, N, nt, C.byref(ok), P(a.view(np.float64)),
+                                           P(c), P(m)) == 0
+    return ok.value, a, c, m
+
+
+def test_c4_batches_are_separable(lib):
+    """every device batch of the striped C4 run (bench.py: 1024 trajectories over 8 ranks, batches of 64) has the form
+    coef = a_k x one row, det = det_00 + c_k x slot mask; a = amplitude fluctuation x waist factor, c = doppler shifts.
+    (A plain double sum in the least-squares fit used to reject 3 batches in 8 on rounding.)"""
+    from pulser_b200 import parallel
+
+    for rank in (0, 5):
+        mine = set(parallel.stripe(1024, rank, 8))
+        chunk = []
+        for _, spec in W.config_c4_stream(1024, keep=mine):
+            chunk.append(spec)
+            if len(chunk) == 64:
+                coef = np.array([s.drives[0].coef for s in chunk])
+                det = np.array([s.drives[0].det for s in chunk])
+                ok, a, c, m = _separable(lib, coef, det)
+                assert ok == 1
+                # reconstruct the tables from the factors
+                b, k, _ = np.unravel_index(np.argmax(np.abs(coef)), coef.shape)
+                assert np.max(np.abs(coef - a[:, :, None] * coef[b, k][None, None, :])) < 1e-12
+                assert np.max(np.abs(det - det[0, 0][None, None, :] - c[:, :, None] * m[None, None, :])) < 1e-11
+                assert np.max(np.abs(np.abs(m[:-1]) - 1.0)) < 1e-12 and m[-1] == 0.0   # slot mask: 0 on the padded sample
+                assert np.all(np.abs(a.imag) < 1e-15) and 0.6 < a.real.min() and a.real.max() == 1.0
+                chunk = []
+
+
+def test_non_separable_tables_are_refused(lib):
+    """per-qubit time shapes (a Local pulse on one atom) or moving phases are not of that form"""
+    specs = W.config_c4(3)
+    coef = np.array([s.drives[0].coef for s in specs])
+    det = np.array([s.drives[0].det for s in specs])
+    assert _separable(lib, coef, det)[0] == 1
+    bad = coef.copy()
+    bad[1, 4, 1000:1500] *= 1.0 + 1e-9            # one qubit's amplitude changes shape
+    assert _separable(lib, bad, det)[0] == 0
+    bad = det.copy()
+    bad[2, 7, 2000:] += 1e-6                       # a second detuning shape
+    assert _separable(lib, coef, bad)[0] == 0
+    # a uniform single trajectory is trivially separable: a = 1, c = 0
+    spec = W.config_c2(n=6)
+    ok, a, c, m = _separable(lib, spec.drives[0].coef[None], spec.drives[0].det[None])
+    assert ok == 1 and np.all(a == 1.0) and np.all(c == 0.0)
