@@ -1840,10 +1840,16 @@ static bool taylor_prepare(Plan& P) {
     auto rows_of = [&](int b) { return (int)P.tabs[b][0].coef.size(); };
     auto coef_pc = [&](int b, int k) -> const PiecewiseCubic<cplx>& { return P.tabs[b][0].coef[rows_of(b) == 1 ? 0 : k]; };
     auto det_pc = [&](int b, int k) -> const PiecewiseCubic<double>& { return P.tabs[b][0].det[rows_of(b) == 1 ? 0 : k]; };
+    // row pointers once: the fit reads every sample of every row several times
+    std::vector<const PiecewiseCubic<cplx>*> crow((size_t)B * N);
+    std::vector<const PiecewiseCubic<double>*> drow((size_t)B * N);
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < N; ++k) { crow[(size_t)b * N + k] = &coef_pc(b, k); drow[(size_t)b * N + k] = &det_pc(b, k); }
+    const int npc = nt - 1;   // pieces of every interpolant; sample i = c0[i], the last one = y_last
     const SeparableFit F = taylor_separable(
         B, N, nt,
-        [&](int b, int k, int i) { const PiecewiseCubic<cplx>& pc = coef_pc(b, k); return i < pc.pieces() ? pc.c0[i] : pc.y_last; },
-        [&](int b, int k, int i) { const PiecewiseCubic<double>& pc = det_pc(b, k); return i < pc.pieces() ? pc.c0[i] : pc.y_last; });
+        [&](int b, int k, int i) { const PiecewiseCubic<cplx>* pc = crow[(size_t)b * N + k]; return i < npc ? pc->c0[i] : pc->y_last; },
+        [&](int b, int k, int i) { const PiecewiseCubic<double>* pc = drow[(size_t)b * N + k]; return i < npc ? pc->c0[i] : pc->y_last; });
     if (!F.ok) { g_taylor_why = F.why; return false; }
     const double scale = F.scale;
     const cplx unit = scale > 0.0 ? F.big / scale : cplx(1.0, 0.0);
