@@ -1734,8 +1734,9 @@ static void propagate(Plan& P, double t_start, double t_stop, const pb200_run_op
     if (stats) *stats = st;
 }
 
-// ---- time-dependent Taylor propagator (global drive of constant phase, d = 2) --------------------------------------
-// Replaces the whole Magnus / exponential machinery above where it applies (C2, C5): the interpolated coefficients
+// ---- time-dependent Taylor propagator (one drive time shape of constant phase, d = 2) -----------------------------
+// Replaces the whole Magnus / exponential machinery above where it applies (C2, C5; C4 batches through per-qubit static
+// factors, taylor_separable): the interpolated coefficients
 // are polynomials in u = (t-a)/h on a step, the solution is the Taylor series in u (kernels.cuh,
 // stage_d2_taylor_kernel), one H-apply per order.  A step spans rho = h W ~ 10 (W = spectral half-width) instead of
 // the ~1.5 a Richardson-CF4 exponential manages, and pays no Chebyshev start-up per exponential: ~1 H-apply per ns on
