@@ -2098,7 +2098,7 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     const double eps = 1e-12;
     const double gtol = (o && o->tol > 0.0) ? o->tol : 1e-8;
     const double rate = gtol / std::max(thi - tlo, 1e-30);       // error budget per unit of time
-    const double rho_target = env_int("PB200_TAYLOR_RHO_MILLI", 14000) * 1e-3;
+    const double rho_max = env_int("PB200_TAYLOR_RHO_MILLI", 14000) * 1e-3;
     const int pmax = std::min(PB200_TAYLOR_PMAX, std::max(1, env_int("PB200_TAYLOR_P", PB200_TAYLOR_PMAX)));
     const int order = P.desc.interp_order;
     const int N = P.n;
@@ -2110,6 +2110,21 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     const PiecewiseCubic<double>& th_pc = P.tabs[0][0].det[0];
     Plan::TaylorCache& C = P.tay;
     taylor_knot_widths(P);
+    // Step length: rho = h W <= rho_max, lowered where the fp64 cancellation of the series would eat the tolerance.  The
+    // rounding error of a step grows like e^rho: ~0.05 eps e^rho measured (profiles/r02_taylor_rho_sweep.jsonl: 6e-12 per
+    // step at rho = 14, 1.4e-10 at 18), random from step to step, n ~ (int W dt) / rho steps over the whole sequence;
+    // it may use a fifth of the tolerance.  At the default 1e-8 this never binds (17 > 14 for C2, C4, C5).
+    const double kRoundUnit = 0.05 * 1.1102230246251565e-16;
+    double rho_target = rho_max;
+    {
+        double w_total = 0.0;
+        for (int i = 0; i + 1 < nt; ++i) w_total += 0.5 * (C.w_knot[i] + C.w_knot[i + 1]) * (P.times[i + 1] - P.times[i]);
+        for (int it = 0; it < 3; ++it) {
+            const double n_est = std::max(w_total / std::max(rho_target, 1.0), 1.0);
+            rho_target = std::min(rho_max, std::max(4.0, std::log(0.2 * gtol / (kRoundUnit * std::sqrt(n_est)))));
+        }
+    }
+    double round2 = 0.0;   // sum of squares of the per-step rounding estimates
     const PiecewiseCubic<double>& m_pc = C.mshape;
     const double A_sum = std::max(C.a_sum_max, 1e-300), C_sum = std::max(C.c_sum_max, 1e-300);
     pb200_run_stats st{};
@@ -2301,6 +2316,7 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
         const double fit_err = h * (A_sum * F.om.resid + N * F.th.resid + C_sum * F.m.resid);
         st.err_estimate += trunc_bound + fit_err;
         fit_spent += fit_err;
+        { const double r = kRoundUnit * std::exp(std::min(rho_eff * h, 40.0)); round2 += r * r; }
         steps_len += h;
         t = b;
     }
@@ -2311,6 +2327,7 @@ static void propagate_taylor(Plan& P, double t_start, double t_stop, const pb200
     st.gpu_ms = ms;
     const double hi_mean = (thi - tlo) / std::max(nt - 1, 1);
     st.mean_step_samples = st.n_steps ? steps_len / st.n_steps / hi_mean : 0.0;
+    st.err_estimate += std::sqrt(round2);
     st.integrator = 3;
     if (stats) *stats = st;
 }
