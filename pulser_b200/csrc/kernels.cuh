@@ -736,16 +736,17 @@ __global__ void __launch_bounds__(1 << (TBITS - RB), 2) stage_d2_fwd_kernel(cons
     }
 }
 
-// ---- d = 2 stage kernel of the time-dependent Taylor propagator (uniform drives, constant phase) -----------------
+// ---- d = 2 stage kernel of the time-dependent Taylor propagator (one drive time shape of constant phase) ---------
 // On a step [a, a+h] the interpolated coefficients (QobjEvo's cubic splines, hamiltonian.py:436) are polynomials in
 // u = (t-a)/h:  H(u) = sum_j H_j u^j,  H_0 = Dint - th_0 n_from - gam_0 + om_0 X,  H_j = -th_j n_from - gam_j + om_j X
 // with X = sum_k (unit |to><from|_k + h.c.).  psi(u) = sum_k chi_k u^k solves psi' = -i h H(u) psi exactly when
 //     (k+1) chi_{k+1} = -i h sum_{j <= min(p,k)} H_j chi_{k-j} ,
 // i.e. ONE gather G_k = X chi_k per order and own-element history terms: no Magnus commutator error, no inner
-// products, no host synchronisation; the step length is bounded by the spectral width (rho = h W ~ 10, fp64
-// cancellation) and by the polynomial fit of the splines only.  The stage computes chi_{k+1} from the tile of chi_k,
+// products, no host synchronisation; the step length is bounded by the spectral width (rho = h W, fp64
+// cancellation: rho <= 14) and by the polynomial fit of the splines only.  The stage computes chi_{k+1} from the tile of chi_k,
 // optionally stores G_k for later orders and folds chi_k + chi_{k+1} into the accumulator of psi(1) on every other
-// order.  Replaces qutip.sesolve (simulation.py:729-735) for global drives of constant phase.
+// order.  Replaces qutip.sesolve (simulation.py:729-735) for global drives of constant phase, and -- with per-qubit
+// static factors from a per-trajectory table (TaylorArgs::table) -- the trajectory loop's solves (simulation.py:885-915).
 #define PB200_TAYLOR_PMAX 8
 struct TaylorArgs {
     const c2* v;       // chi_k, gather source [B][D]
